@@ -1,0 +1,1441 @@
+// BnpC MCMC hot path -- sm_100a kernels and their C ABI (include/bnpc_b200.h).
+//
+// Kernel inventory (reference function each one stands in for is cited in the header):
+//   pack_planes_kernel      float64/int8 matrix -> two cell-major bit-planes + popcounts
+//   fill_uniform_kernel     Philox4x32-10 uniforms / small integers
+//   fill_permutation_kernel keyed Feistel permutation with cycle walking
+//   logprob_tables_kernel   theta -> (log p1, log p0) per (cluster, mutation)
+//   ll_matrix_kernel        cells x clusters log-likelihood, FP64 FMA over bit-planes
+//   gibbs_prepare_kernel    per-visit records of a sweep
+//   gibbs_epoch_begin_kernel
+//   gibbs_sweep_kernel      the sequential Gibbs sweep: one persistent CTA per chain,
+//                           warp-level categorical sampling for K<=31 (ll rows and visit
+//                           records staged into shared memory by bulk async copies),
+//                           CTA-wide sampling for larger K, cluster births/deaths on device
+//   group_members_kernel / suffstat_kernel   per-cluster sufficient statistics
+//   beta_rows_kernel / theta_from_uniform_kernel
+//   mh_theta_kernel / theta_log_ratio_kernel   Metropolis-Hastings on theta
+//   row_loglik_kernel / row_sum_kernel         deterministic [R][M] reductions
+//   gather_* / anchor_swaps / rg_*             split-merge restricted Gibbs support
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bnpc_b200.h"
+#include "bnpc_math.cuh"
+
+using namespace bnpc;
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char* what, cudaError_t e) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return 1;
+}
+static int bad_arg(const char* what) {
+    snprintf(g_err, sizeof(g_err), "invalid argument: %s", what);
+    return 2;
+}
+#define LAUNCH_CHECK(name)                                        \
+    do {                                                          \
+        cudaError_t e__ = cudaGetLastError();                     \
+        if (e__ != cudaSuccess) return fail(name, e__);           \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// =============================================================================
+// warp / block helpers
+// =============================================================================
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_scan_incl(double v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(FULL, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// CTA-wide reductions over up to 1024 threads; `red` is 33 doubles of shared memory.
+// Fixed combination order => deterministic.  All threads get the result.
+__device__ __forceinline__ double block_max(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double x = (lane < nw) ? red[lane] : -BNPC_INF;
+        x = warp_max(x);
+        if (lane == 0) red[32] = x;
+    }
+    __syncthreads();
+    return red[32];
+}
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double x = (lane < nw) ? red[lane] : 0.0;
+        x = warp_sum(x);
+        if (lane == 0) red[32] = x;
+    }
+    __syncthreads();
+    return red[32];
+}
+// inclusive scan across threads; returns this thread's inclusive value, *total = sum
+__device__ __forceinline__ double block_scan_incl(double v, double* red, double* total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    double inc = warp_scan_incl(v, lane);
+    __syncthreads();
+    if (lane == 31) red[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        double x = (lane < nw) ? red[lane] : 0.0;
+        double s = warp_scan_incl(x, lane);
+        red[lane] = s - x;                       // exclusive prefix of warp sums
+        if (lane == 31) red[32] = s;
+    }
+    __syncthreads();
+    inc += red[w];
+    *total = red[32];
+    return inc;
+}
+
+// =============================================================================
+// input path: bit-plane packing
+// =============================================================================
+__global__ void pack_planes_kernel(const double* __restrict__ xf, const int8_t* __restrict__ xi,
+                                   int N, int M, int W, uint32_t* __restrict__ x1,
+                                   uint32_t* __restrict__ x0, int32_t* __restrict__ n1,
+                                   int32_t* __restrict__ n0) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long cell = warp; cell < N; cell += nwarps) {
+        int c1 = 0, c0 = 0;
+        for (int w = 0; w < W; ++w) {
+            const int m = w * 32 + lane;
+            int code = 0;
+            if (m < M) {
+                if (xf) {
+                    const double v = xf[cell * M + m];
+                    code = (v == 1.0) ? 1 : ((v == 0.0) ? 2 : 0);
+                } else {
+                    const int v = xi[cell * M + m];
+                    code = (v == 1) ? 1 : ((v == 0) ? 2 : 0);
+                }
+            }
+            const uint32_t b1 = __ballot_sync(FULL, code == 1);
+            const uint32_t b0 = __ballot_sync(FULL, code == 2);
+            if (lane == 0) { x1[cell * W + w] = b1; x0[cell * W + w] = b0; }
+            c1 += __popc(b1); c0 += __popc(b0);
+        }
+        if (lane == 0) { n1[cell] = c1; n0[cell] = c0; }
+    }
+}
+
+// =============================================================================
+// random numbers (production mode)
+// =============================================================================
+__global__ void fill_uniform_kernel(double* __restrict__ out, long long n, uint64_t seed,
+                                    uint64_t stream_id, int n_levels) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // pair index
+    if (2 * i >= n) return;
+    Philox g(seed);
+    const uint4 r = g((uint64_t)i, stream_id);
+    double a = u01(r.x, r.y), b = u01(r.z, r.w);
+    if (n_levels > 0) { a = floor(a * n_levels); b = floor(b * n_levels); }
+    out[2 * i] = a;
+    if (2 * i + 1 < n) out[2 * i + 1] = b;
+}
+
+__device__ __forceinline__ uint32_t feistel_round(uint32_t r, uint32_t k) {
+    uint32_t h = r * 0x9E3779B1u + k;
+    h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13; h *= 0xC2B2AE3Du; h ^= h >> 16;
+    return h;
+}
+__global__ void fill_permutation_kernel(int32_t* __restrict__ out, int n, uint64_t seed,
+                                        uint64_t stream_id, int half_bits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Philox g(seed);
+    const uint4 k0 = g(0xFE157E1ull, stream_id), k1 = g(0xFE157E2ull, stream_id);
+    const uint32_t keys[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    const uint32_t mask = (1u << half_bits) - 1u;
+    uint32_t x = (uint32_t)i;
+    do {                                      // cycle walking keeps the image inside [0,n)
+        uint32_t l = x >> half_bits, r = x & mask;
+#pragma unroll
+        for (int rd = 0; rd < 8; ++rd) {
+            const uint32_t t = l ^ (feistel_round(r, keys[rd]) & mask);
+            l = r; r = t;
+        }
+        x = (l << half_bits) | r;
+    } while (x >= (uint32_t)n);
+    out[i] = (int32_t)x;
+}
+
+// =============================================================================
+// likelihood
+// =============================================================================
+__global__ void logprob_tables_kernel(const float* __restrict__ theta, const int32_t* __restrict__ ids,
+                                      int R, int M, double FN, double FP, double2* __restrict__ lp) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)R * M) return;
+    const int r = (int)(i / M), m = (int)(i % M);
+    const long long row = ids ? ids[r] : r;
+    double a, b;
+    log_p1_p0(theta[row * M + m], FN, FP, a, b);
+    lp[i] = make_double2(a, b);
+}
+
+// ll[r][k0+kk] for a tile of 128 cells x LL_KT clusters.  One thread per cell keeps LL_KT
+// FP64 accumulators; the (log p1, log p0) pairs of 128 mutations x LL_KT clusters are staged
+// in shared memory and read as 16-byte broadcasts.  Algorithmic work: 2 FMA per
+// (cell, mutation, cluster); bits select exact 0.0/1.0 multipliers so the sum equals the
+// reference's masked sum.
+#define LL_KT 8
+#define LL_MT 128
+#define LL_THREADS 128
+__global__ void __launch_bounds__(LL_THREADS)
+ll_matrix_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
+                 const int32_t* __restrict__ cells, int cell_stride, int C,
+                 const double2* __restrict__ lp, int K, double* __restrict__ ll, int ldk) {
+    __shared__ double2 tile[LL_MT][LL_KT];
+    const int r = blockIdx.x * LL_THREADS + threadIdx.x;
+    const int k0 = blockIdx.y * LL_KT;
+    const bool live = r < C;
+    const long long cell = live ? (cells ? cells[(long long)r * cell_stride] : r) : 0;
+    const uint4* p1 = reinterpret_cast<const uint4*>(x1 + cell * W);
+    const uint4* p0 = reinterpret_cast<const uint4*>(x0 + cell * W);
+    double acc[LL_KT];
+#pragma unroll
+    for (int kk = 0; kk < LL_KT; ++kk) acc[kk] = 0.0;
+
+    for (int m0 = 0; m0 < M; m0 += LL_MT) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < LL_MT * LL_KT; i += LL_THREADS) {
+            const int kk = i / LL_MT, mm = i % LL_MT;      // coalesced along mutations
+            double2 v = make_double2(0.0, 0.0);
+            if (k0 + kk < K && m0 + mm < M) v = lp[(long long)(k0 + kk) * M + m0 + mm];
+            tile[mm][kk] = v;
+        }
+        __syncthreads();
+        if (live) {
+            const uint4 a = p1[m0 >> 7], b = p0[m0 >> 7];
+            const uint32_t w1[4] = {a.x, a.y, a.z, a.w}, w0[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t u1 = w1[q], u0 = w0[q];
+                if ((u1 | u0) == 0u) continue;
+#pragma unroll 4
+                for (int bit = 0; bit < 32; ++bit) {
+                    const double f1 = (double)((u1 >> bit) & 1u), f0 = (double)((u0 >> bit) & 1u);
+                    const double2* t = tile[q * 32 + bit];
+#pragma unroll
+                    for (int kk = 0; kk < LL_KT; ++kk) {
+                        const double2 v = t[kk];
+                        acc[kk] = fma(f1, v.x, fma(f0, v.y, acc[kk]));
+                    }
+                }
+            }
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int kk = 0; kk < LL_KT; ++kk)
+            if (k0 + kk < K) ll[(long long)r * ldk + k0 + kk] = acc[kk];
+    }
+}
+
+// log-likelihood of one cell under one (log p1, log p0) row; same arithmetic as above
+__device__ __forceinline__ double cell_row_ll(const uint32_t* __restrict__ r1,
+                                              const uint32_t* __restrict__ r0, int W,
+                                              const double2* __restrict__ lp) {
+    double acc = 0.0;
+    for (int w = 0; w < W; ++w) {
+        const uint32_t u1 = r1[w], u0 = r0[w];
+        if ((u1 | u0) == 0u) continue;
+        const double2* t = lp + w * 32;
+#pragma unroll 4
+        for (int bit = 0; bit < 32; ++bit) {
+            const double f1 = (double)((u1 >> bit) & 1u), f0 = (double)((u0 >> bit) & 1u);
+            if ((u1 | u0) >> bit & 1u) {
+                const double2 v = t[bit];
+                acc = fma(f1, v.x, fma(f0, v.y, acc));
+            }
+        }
+    }
+    return acc;
+}
+
+// =============================================================================
+// Gibbs sweep
+// =============================================================================
+__global__ void gibbs_prepare_kernel(const int32_t* __restrict__ perm, const double* __restrict__ u,
+                                     const int32_t* __restrict__ assign, const int32_t* __restrict__ n1,
+                                     const int32_t* __restrict__ n0, int N, double c1, double c0,
+                                     double lnew_prior, bnpc_visit_t* __restrict__ visit) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    const int c = perm[t];
+    bnpc_visit_t v;
+    v.u = u[t];
+    // popcount form of libs/CRP.py:230-234: every observed 1 contributes c1, every 0 c0
+    v.lnew = ((double)n1[c] * c1 + (double)n0[c] * c0) + lnew_prior;
+    v.cell = c;
+    v.old = assign[c];
+    v.pad[0] = v.pad[1] = 0;
+    visit[t] = v;
+}
+
+__global__ void gibbs_epoch_begin_kernel(const int32_t* __restrict__ live, int K, int32_t* lst,
+                                         int32_t* cnt, int32_t* col_of_id, int idcap, int32_t* st,
+                                         int first) {
+    for (int i = threadIdx.x; i < idcap; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        const int id = live[2 * j];
+        lst[j] = id;
+        cnt[id] = live[2 * j + 1];
+        col_of_id[id] = j;
+    }
+    if (threadIdx.x == 0) {
+        st[BNPC_ST_K] = K;
+        st[BNPC_ST_NEXTRA] = 0;
+        st[BNPC_ST_FLAGS] = 0;
+        if (first) {
+            st[BNPC_ST_TDONE] = 0; st[BNPC_ST_BIRTHS] = 0; st[BNPC_ST_MOVED] = 0; st[BNPC_ST_SLOW] = 0;
+        }
+    }
+}
+
+// ---- bulk async copy (TMA engine, 1-D) + mbarrier -----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+#define SW_STAGE_CELLS 32
+#define SW_NSTAGE 4
+#define SW_MAXCOL 32
+
+struct SweepShared {
+    alignas(128) double ll_stage[SW_NSTAGE][SW_STAGE_CELLS * SW_MAXCOL];
+    alignas(128) bnpc_visit_t vis_stage[SW_NSTAGE][SW_STAGE_CELLS];
+    alignas(8) uint64_t bar[SW_NSTAGE];
+    double red[40];
+    int L, t, pending, stop;
+    int birth_cell, birth_t;
+    int n_extra, births, moved, slow;
+    int tmp_i, pick;
+    int hang;
+};
+
+// One exact categorical draw for the warp-resident list (libs/CRP.py:88-100 + numpy choice,
+// libs/CRP.py:274-277).  Lanes [0,L) hold live clusters, lane L the new-cluster option.
+__device__ __forceinline__ int warp_categorical(double l, int L, double u, int lane) {
+    const bool in = lane <= L;
+    const double lmax = warp_max(in ? l : -BNPC_INF);
+    const double d = l - lmax;
+    const double e = in ? exp(d) : 0.0;
+    double S = warp_sum(e) - 1.0;                  // sum over all but (one copy of) the max
+    if (S < 0.0) S = 0.0;
+    double z = d - log1p(S);
+    z = fmin(fmax(z, kLogEps), 0.0);
+    const double p = in ? exp(z) : 0.0;
+    const double cdf = warp_scan_incl(p, lane);
+    const double total = __shfl_sync(FULL, cdf, L);
+    const unsigned gt = __ballot_sync(FULL, in && (cdf / total > u));
+    return gt ? (__ffs(gt) - 1) : L;
+}
+
+__device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
+    const int lane = threadIdx.x;
+    int L = sh.L;
+    const int t0 = sh.t;
+    const int ldk = a.ldk;
+    int moved = 0, slow = 0;
+
+    // the live list lives in registers: lane j <-> list position j
+    int id = -1, cnt = 0, src = -1;
+    double lc = 0.0, lcm1 = 0.0;
+    if (lane < L) {
+        id = a.lst[lane];
+        cnt = a.cnt[id];
+        src = a.col_of_id[id];
+        lc = a.logn[cnt] - a.c_norm;
+        lcm1 = a.logn[cnt - 1] - a.c_norm;
+    }
+
+    if (lane == 0) {
+        for (int s = 0; s < SW_NSTAGE; ++s) mbar_init(&sh.bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int n_stages = (a.t_end - t0 + SW_STAGE_CELLS - 1) / SW_STAGE_CELLS;
+    auto issue = [&](int g) {                      // lane 0 only
+        const int slot = g % SW_NSTAGE;
+        const int ts = t0 + g * SW_STAGE_CELLS;
+        const int nc = min(SW_STAGE_CELLS, a.t_end - ts);
+        const uint32_t b_ll = (uint32_t)(nc * ldk * 8), b_v = (uint32_t)(nc * sizeof(bnpc_visit_t));
+        mbar_expect_tx(&sh.bar[slot], b_ll + b_v);
+        bulk_g2s(sh.ll_stage[slot], a.ll + (long long)(ts - a.t_epoch0) * ldk, b_ll, &sh.bar[slot]);
+        bulk_g2s(sh.vis_stage[slot], a.visit + ts, b_v, &sh.bar[slot]);
+    };
+    int issued = 0;
+    if (lane == 0)
+        for (; issued < n_stages && issued < SW_NSTAGE; ++issued) issue(issued);
+    issued = __shfl_sync(FULL, issued, 0);
+
+    int waited = 0;
+    bool leave = false;
+    int next_t = a.t_end;
+    for (int g = 0; g < n_stages && !leave; ++g) {
+        const int slot = g % SW_NSTAGE;
+        const uint32_t parity = (uint32_t)((g / SW_NSTAGE) & 1);
+        {
+            long long spins = 0;
+            while (!mbar_try_wait(&sh.bar[slot], parity)) {
+                if (++spins > (1ll << 24)) { sh.hang = 1; break; }
+            }
+        }
+        waited = g + 1;
+        const int ts = t0 + g * SW_STAGE_CELLS;
+        const int nc = min(SW_STAGE_CELLS, a.t_end - ts);
+        const double* rows = sh.ll_stage[slot];
+        for (int i = 0; i < nc; ++i) {
+            const int t = ts + i;
+            const bnpc_visit_t v = sh.vis_stage[slot][i];
+            const int old = v.old;
+
+            // take the cell out of its cluster (libs/CRP.py:262-266)
+            const unsigned om = __ballot_sync(FULL, lane < L && id == old);
+            int lo = __ffs(om) - 1;
+            const int ocnt = __shfl_sync(FULL, cnt, lo < 0 ? 0 : lo);
+            bool died = false;
+            if (lo >= 0 && ocnt == 1) {
+                // cluster dies: close the gap so list order stays insertion order
+                const int id2 = __shfl_down_sync(FULL, id, 1), cnt2 = __shfl_down_sync(FULL, cnt, 1),
+                          src2 = __shfl_down_sync(FULL, src, 1);
+                const double lc2 = __shfl_down_sync(FULL, lc, 1), lcm2 = __shfl_down_sync(FULL, lcm1, 1);
+                if (lane == lo) a.cnt[old] = 0;
+                if (lane >= lo && lane < L - 1) {
+                    id = id2; cnt = cnt2; src = src2; lc = lc2; lcm1 = lcm2;
+                    a.lst[lane] = id;
+                } else if (lane == L - 1) {
+                    id = -1; cnt = 0; src = -1;
+                }
+                --L;
+                died = true;
+                lo = -1;
+            }
+
+            double l = -BNPC_INF;
+            if (lane < L) {
+                const double val = (src >= 0) ? rows[i * ldk + src]
+                                              : a.llx[(long long)(-src - 2) * a.ldx + (t - a.t_epoch0)];
+                l = val + ((lane == lo) ? lcm1 : lc);
+            } else if (lane == L) {
+                l = v.lnew;
+            }
+
+            int pick;
+            bool fast = false;
+            if (!died && lo >= 0) {
+                // every rival at least 40 nats below the current cluster => all rivals sit on
+                // the 1e-15 floor and the draw returns the current cluster unless u is within
+                // 32e-15 of 0 or 1: skip the transcendental path, result is identical.
+                const double lold = __shfl_sync(FULL, l, lo);
+                const bool rival = (lane <= L) && (lane != lo) && (l > lold - 40.0);
+                if (!__any_sync(FULL, rival) && v.u > 1e-12 && v.u < 1.0 - 1e-12) {
+                    fast = true;
+                    pick = lo;
+                }
+            }
+            if (!fast) {
+                ++slow;
+                pick = warp_categorical(l, L, v.u, lane);
+            }
+            if (pick == lo) continue;               // stays where it was
+
+            ++moved;
+            if (lo >= 0 && lane == lo) {            // leave the old cluster
+                --cnt;
+                lc = a.logn[cnt] - a.c_norm;
+                lcm1 = a.logn[cnt - 1] - a.c_norm;
+                a.cnt[id] = cnt;
+            }
+            if (pick == L) {                        // open a new cluster: CTA-wide work
+                if (lane == 0) {
+                    sh.pending = 1; sh.birth_cell = v.cell; sh.birth_t = t;
+                }
+                next_t = t + 1;
+                leave = true;
+                break;
+            }
+            if (lane == pick) {
+                ++cnt;
+                lc = a.logn[cnt] - a.c_norm;
+                lcm1 = a.logn[cnt - 1] - a.c_norm;
+                a.cnt[id] = cnt;
+                a.assign[v.cell] = id;
+            }
+        }
+        __syncwarp();
+        if (!leave && lane == 0 && issued < n_stages) issue(issued);
+        if (!leave && issued < n_stages) ++issued;
+    }
+    // drain copies still in flight before shared memory is reused or the kernel ends
+    for (int g = waited; g < issued; ++g) {
+        long long spins = 0;
+        while (!mbar_try_wait(&sh.bar[g % SW_NSTAGE], (uint32_t)((g / SW_NSTAGE) & 1))) {
+            if (++spins > (1ll << 24)) { sh.hang = 1; break; }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        sh.L = L;
+        sh.t = next_t;
+        sh.moved += moved;
+        sh.slow += slow;
+    }
+}
+
+// one cell with the whole CTA (list longer than a warp)
+__device__ void sweep_block_cell(const bnpc_sweep_args_t& a, SweepShared& sh, int t, int L) {
+    const int tid = threadIdx.x, B = blockDim.x;
+    const bnpc_visit_t v = a.visit[t];
+    int old = v.old;
+    const bool died = (a.cnt[old] == 1);
+    __syncthreads();
+    if (died) {
+        if (tid == 0) sh.tmp_i = -1;
+        __syncthreads();
+        for (int j = tid; j < L; j += B)
+            if (a.lst[j] == old) sh.tmp_i = j;
+        __syncthreads();
+        const int pos = sh.tmp_i;
+        for (int base = pos; base < L - 1; base += B) {
+            const int j = base + tid;
+            int nv = 0;
+            if (j < L - 1) nv = a.lst[j + 1];
+            __syncthreads();
+            if (j < L - 1) a.lst[j] = nv;
+            __syncthreads();
+        }
+        if (tid == 0) a.cnt[old] = 0;
+        --L;
+        old = -1;
+        __syncthreads();
+    }
+    const long long tx = t - a.t_epoch0;
+    const double* rowp = a.ll + tx * a.ldk;
+    double m_all = -BNPC_INF, m_riv = -BNPC_INF, l_old = -BNPC_INF;
+    for (int j = tid; j <= L; j += B) {
+        double l;
+        if (j < L) {
+            const int id = a.lst[j];
+            int n = a.cnt[id];
+            if (id == old) --n;
+            const int col = a.col_of_id[id];
+            const double val = (col >= 0) ? rowp[col] : a.llx[(long long)(-col - 2) * a.ldx + tx];
+            l = val + (a.logn[n] - a.c_norm);
+            if (id == old) l_old = l; else m_riv = fmax(m_riv, l);
+        } else {
+            l = v.lnew;
+            m_riv = fmax(m_riv, l);
+        }
+        a.scratch[j] = l;
+        m_all = fmax(m_all, l);
+    }
+    const double lmax = block_max(m_all, sh.red);
+    const double lriv = block_max(m_riv, sh.red);
+    const double lold = block_max(l_old, sh.red);
+    if (!died && lriv <= lold - 40.0 && v.u > 1e-8 && v.u < 1.0 - 1e-8) {
+        if (tid == 0) sh.t = t + 1;
+        __syncthreads();
+        return;
+    }
+    double s = 0.0;
+    for (int j = tid; j <= L; j += B) s += exp(a.scratch[j] - lmax);
+    double S = block_sum(s, sh.red) - 1.0;
+    if (S < 0.0) S = 0.0;
+    const double lse = log1p(S);
+    const int seg = (L + 1 + B - 1) / B;
+    const int j0 = tid * seg, j1 = min(j0 + seg, L + 1);
+    double T = 0.0;
+    for (int j = j0; j < j1; ++j) {
+        const double z = fmin(fmax(a.scratch[j] - lmax - lse, kLogEps), 0.0);
+        const double p = exp(z);
+        a.scratch[j] = p;
+        T += p;
+    }
+    double total;
+    const double inc = block_scan_incl(T, sh.red, &total);
+    if (tid == 0) sh.tmp_i = 0x7fffffff;
+    __syncthreads();
+    if (j0 < j1 && inc / total > v.u) atomicMin(&sh.tmp_i, tid);
+    __syncthreads();
+    if (tid == sh.tmp_i) {
+        double cdf = inc - T;
+        int pick = j1 - 1;
+        for (int j = j0; j < j1; ++j) {
+            cdf += a.scratch[j];
+            if (cdf / total > v.u) { pick = j; break; }
+        }
+        sh.pick = pick;
+    }
+    if (sh.tmp_i == 0x7fffffff && tid == 0) sh.pick = L;
+    __syncthreads();
+    if (tid == 0) {
+        const int pick = sh.pick;
+        sh.slow += 1;
+        if (pick == L) {
+            if (!died) a.cnt[old] -= 1;
+            sh.pending = 1; sh.birth_cell = v.cell; sh.birth_t = t;
+            sh.moved += 1;
+        } else {
+            const int idp = a.lst[pick];
+            if (idp != old) {
+                if (!died) a.cnt[old] -= 1;
+                a.cnt[idp] += 1;
+                a.assign[v.cell] = idp;
+                sh.moved += 1;
+            }
+        }
+        sh.t = t + 1;
+        sh.L = L;
+    }
+    __syncthreads();
+}
+
+// a cell opened a new cluster (libs/CRP.py:281-282,291-299,183-188): pick the smallest free
+// id, draw its theta row, build its log-prob row and its ll column for the rest of the epoch
+__device__ void sweep_birth(const bnpc_sweep_args_t& a, SweepShared& sh) {
+    const int tid = threadIdx.x, B = blockDim.x;
+    const int cell = sh.birth_cell, t = sh.birth_t, L = sh.L, e = sh.n_extra, b = sh.births;
+    const int M = a.M, W = a.W;
+    if (a.beta_rows && b >= a.n_beta_rows) {
+        if (tid == 0) { sh.stop |= BNPC_STOP_TAPE_EMPTY; sh.pending = 0; }
+        __syncthreads();
+        return;
+    }
+    if (tid == 0) sh.tmp_i = 0x7fffffff;
+    __syncthreads();
+    for (int i = tid; i <= L && i < a.idcap; i += B)
+        if (a.cnt[i] == 0) atomicMin(&sh.tmp_i, i);
+    __syncthreads();
+    const int nid = sh.tmp_i;
+    if (nid >= a.idcap) {
+        if (tid == 0) { sh.stop |= BNPC_STOP_CAPACITY; sh.pending = 0; }
+        __syncthreads();
+        return;
+    }
+    double2* lpx = reinterpret_cast<double2*>(a.lpx) + (long long)e * M;
+    const uint32_t* r1 = a.x1 + (long long)cell * W;
+    const uint32_t* r0 = a.x0 + (long long)cell * W;
+    for (int m = tid; m < M; m += B) {
+        const int b1 = (r1[m >> 5] >> (m & 31)) & 1, b0 = (r0[m >> 5] >> (m & 31)) & 1;
+        double val;
+        if (a.beta_rows) {
+            val = a.beta_rows[(long long)b * M + m];
+        } else {
+            PhiloxStream rs(a.seed, a.stream_id + 0x1000000ull * (uint64_t)(b + 1), (uint64_t)m);
+            val = beta_sample(a.p + b1, a.q + b0, rs);
+        }
+        const float th = clip_theta(val);
+        a.theta[(long long)nid * M + m] = th;
+        double p1, p0;
+        log_p1_p0(th, a.FN, a.FP, p1, p0);
+        lpx[m] = make_double2(p1, p0);
+    }
+    __syncthreads();
+    double* col = a.llx + (long long)e * a.ldx;
+    for (int tt = t + 1 + tid; tt < a.t_end; tt += B) {
+        const long long c2 = a.visit[tt].cell;
+        col[tt - a.t_epoch0] = cell_row_ll(a.x1 + c2 * W, a.x0 + c2 * W, (M + 31) >> 5, lpx);
+    }
+    if (tid == 0) {
+        a.lst[L] = nid;
+        a.cnt[nid] = 1;
+        a.col_of_id[nid] = -(e + 2);
+        a.assign[cell] = nid;
+        sh.L = L + 1;
+        sh.n_extra = e + 1;
+        sh.births = b + 1;
+        sh.pending = 0;
+        if (e + 1 >= BNPC_MAX_EXTRA) sh.stop |= BNPC_STOP_EXTRA_FULL;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024, 1)
+gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
+    __shared__ SweepShared sh;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        sh.L = a.st[BNPC_ST_K];
+        sh.t = a.t_begin;
+        sh.pending = 0;
+        sh.stop = a.st[BNPC_ST_FLAGS];
+        sh.n_extra = a.st[BNPC_ST_NEXTRA];
+        sh.births = a.st[BNPC_ST_BIRTHS];
+        sh.moved = a.st[BNPC_ST_MOVED];
+        sh.slow = a.st[BNPC_ST_SLOW];
+        sh.hang = 0;
+    }
+    __syncthreads();
+    if (sh.stop) return;                            // an earlier launch of this sweep stopped
+
+    for (;;) {
+        const int t = sh.t, L = sh.L, stop = sh.stop | sh.hang;
+        __syncthreads();
+        if (t >= a.t_end || stop) break;
+        if (L + 1 + BNPC_MAX_EXTRA >= a.idcap) {
+            if (tid == 0) sh.stop |= BNPC_STOP_CAPACITY;
+            __syncthreads();
+            continue;
+        }
+        if (L <= 31) {
+            if (a.ldk > SW_MAXCOL) {
+                if (tid == 0) sh.stop |= BNPC_STOP_REPACK;
+                __syncthreads();
+                continue;
+            }
+            if (tid < 32) sweep_warp_regime(a, sh);
+            __syncthreads();
+        } else {
+            sweep_block_cell(a, sh, t, L);
+        }
+        if (sh.pending) sweep_birth(a, sh);
+    }
+    __syncthreads();
+    const int L = sh.L;
+    for (int j = tid; j < L; j += blockDim.x) {
+        const int id = a.lst[j];
+        a.live_out[2 * j] = id;
+        a.live_out[2 * j + 1] = a.cnt[id];
+    }
+    if (tid == 0) {
+        a.st[BNPC_ST_K] = L;
+        a.st[BNPC_ST_TDONE] = sh.t;
+        a.st[BNPC_ST_FLAGS] = sh.stop | (sh.hang ? 0x100 : 0);
+        a.st[BNPC_ST_NEXTRA] = sh.n_extra;
+        a.st[BNPC_ST_BIRTHS] = sh.births;
+        a.st[BNPC_ST_MOVED] = sh.moved;
+        a.st[BNPC_ST_SLOW] = sh.slow;
+    }
+}
+
+// =============================================================================
+// sufficient statistics
+// =============================================================================
+__global__ void set_ranks_kernel(const int32_t* __restrict__ ids, int K, int32_t* rank_of_id) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < K) rank_of_id[ids[j]] = j;
+}
+
+__global__ void group_members_kernel(const int32_t* __restrict__ assign, int N,
+                                     const int32_t* __restrict__ rank_of_id,
+                                     const int32_t* __restrict__ seg_off, int32_t* cursor,
+                                     int32_t* __restrict__ members) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    const int r = rank_of_id[assign[n]];
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, r);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[r], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    members[seg_off[r] + base + __popc(peers & ((1u << lane) - 1u))] = n;
+}
+
+#define SS_CHUNK 1024
+// grid (chunks, R): a CTA counts ones/zeros per mutation over up to SS_CHUNK members of one
+// segment; lane <-> bit of a 32-mutation word, each warp strides over the words of a row.
+__global__ void __launch_bounds__(256)
+suffstat_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
+                const int32_t* __restrict__ members, const int32_t* __restrict__ seg_off,
+                int32_t* __restrict__ S1, int32_t* __restrict__ S0) {
+    const int r = blockIdx.y;
+    const int beg = seg_off[r] + blockIdx.x * SS_CHUNK;
+    const int end = min(seg_off[r + 1], beg + SS_CHUNK);
+    if (beg >= end) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int Wm = (M + 31) >> 5;
+    for (int w = warp; w < Wm; w += nw) {
+        int c1 = 0, c0 = 0;
+        int i = beg;
+        for (; i + 4 <= end; i += 4) {
+            const long long a0 = members[i], a1 = members[i + 1], a2 = members[i + 2], a3 = members[i + 3];
+            const uint32_t p0 = x1[a0 * W + w], p1 = x1[a1 * W + w], p2 = x1[a2 * W + w], p3 = x1[a3 * W + w];
+            const uint32_t q0 = x0[a0 * W + w], q1 = x0[a1 * W + w], q2 = x0[a2 * W + w], q3 = x0[a3 * W + w];
+            c1 += ((p0 >> lane) & 1) + ((p1 >> lane) & 1) + ((p2 >> lane) & 1) + ((p3 >> lane) & 1);
+            c0 += ((q0 >> lane) & 1) + ((q1 >> lane) & 1) + ((q2 >> lane) & 1) + ((q3 >> lane) & 1);
+        }
+        for (; i < end; ++i) {
+            const long long a0 = members[i];
+            c1 += (x1[a0 * W + w] >> lane) & 1;
+            c0 += (x0[a0 * W + w] >> lane) & 1;
+        }
+        const int m = w * 32 + lane;
+        if (m < M) {
+            if (c1) atomicAdd(&S1[(long long)r * M + m], c1);
+            if (c0) atomicAdd(&S0[(long long)r * M + m], c0);
+        }
+    }
+}
+
+// =============================================================================
+// theta draws and Metropolis-Hastings
+// =============================================================================
+__global__ void beta_rows_kernel(const int32_t* __restrict__ S1, const int32_t* __restrict__ S0, int R,
+                                 int M, double p, double q, const double* __restrict__ tape,
+                                 uint64_t seed, uint64_t stream_id, float* __restrict__ theta_out,
+                                 const int32_t* __restrict__ out_ids) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)R * M) return;
+    const int r = (int)(i / M), m = (int)(i % M);
+    double val;
+    if (tape) {
+        val = tape[i];
+    } else {
+        PhiloxStream rs(seed, stream_id, (uint64_t)i);
+        val = beta_sample(p + (double)S1[i], q + (double)S0[i], rs);
+    }
+    const long long row = out_ids ? out_ids[r] : r;
+    theta_out[row * M + m] = clip_theta(val);
+}
+
+__global__ void theta_from_uniform_kernel(const double* __restrict__ u, int R, int M,
+                                          float* __restrict__ theta_out,
+                                          const int32_t* __restrict__ out_ids) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)R * M) return;
+    const int r = (int)(i / M), m = (int)(i % M);
+    const long long row = out_ids ? out_ids[r] : r;
+    theta_out[row * M + m] = clip_theta(u[i]);
+}
+
+struct MhConst {
+    double FN, FP, p, q, betaln;
+    int flat;
+};
+
+// log acceptance ratio of libs/CRP.py:347-383 for one (row, mutation)
+__device__ __forceinline__ double theta_log_A(float th_new, float th_old, int s1, int s0, double lo,
+                                              double hi, double sd, const MhConst& c, bool clip) {
+    const float lo_f = (float)kThetaLo, hi_f = (float)kThetaHi;
+    const double lsd = log(sd);
+    const double y = (double)(th_new - th_old) / sd;
+    const double fwd = truncnorm_logpdf_std(y, lo, hi) - lsd;
+    const double rlo = (double)(lo_f - th_new) / sd, rhi = (double)(hi_f - th_new) / sd;
+    const double yr = (double)(th_old - th_new) / sd;
+    const double rev = truncnorm_logpdf_std(yr, rlo, rhi) - lsd;
+    double n1, n0, o1, o0;
+    log_p1_p0(th_new, c.FN, c.FP, n1, n0);
+    log_p1_p0(th_old, c.FN, c.FP, o1, o0);
+    const double ll_new = (double)s1 * n1 + (double)s0 * n0;
+    const double ll_old = (double)s1 * o1 + (double)s0 * o0;
+    double pr_new = 0.0, pr_old = 0.0;
+    if (!c.flat) {
+        pr_new = beta_logpdf((double)th_new, c.p, c.q, c.betaln);
+        pr_old = beta_logpdf((double)th_old, c.p, c.q, c.betaln);
+    }
+    double A = ll_new + pr_new - ll_old - pr_old + rev - fwd;
+    if (clip) A = fmin(A, 0.0);
+    return A;
+}
+
+__device__ __constant__ const double kStepSd[3] = {0.1, 0.25, 0.5};   // libs/CRP.py:65
+
+__global__ void mh_theta_kernel(float* theta, const int32_t* __restrict__ ids, int R, int M,
+                                const int32_t* __restrict__ S1, const int32_t* __restrict__ S0,
+                                const double* __restrict__ rnd, MhConst c, int flags,
+                                double* __restrict__ logq, int32_t* declined) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long RM = (long long)R * M;
+    if (i >= RM) return;
+    const int r = (int)(i / M), m = (int)(i % M);
+    const long long row = ids ? ids[r] : r;
+    const float old = theta[row * M + m];
+    const double sd = kStepSd[(int)rnd[i]];
+    const double ut = rnd[RM + i], ua = rnd[2 * RM + i];
+    const float lo_f = (float)kThetaLo, hi_f = (float)kThetaHi;
+    const double lo = (double)(lo_f - old) / sd, hi = (double)(hi_f - old) / sd;
+    const double x = truncnorm_ppf_std(ut, lo, hi);
+    const float prop = (float)(x * sd + (double)old);
+    const bool want_logq = flags & 1;
+    const double A = theta_log_A(prop, old, S1[i], S0[i], lo, hi, sd, c, want_logq);
+    const bool rej = log(ua) >= A;
+    if (!rej) theta[row * M + m] = prop;
+    else atomicAdd(&declined[r], 1);
+    if (want_logq) logq[i] = rej ? log(-1.0 * expm1(A)) : A;
+}
+
+__global__ void theta_log_ratio_kernel(const float* __restrict__ th_new, const float* __restrict__ th_old,
+                                       int R, int M, const int32_t* __restrict__ S1,
+                                       const int32_t* __restrict__ S0, const double* __restrict__ sd_idx,
+                                       float blo, float bhi, MhConst c, double* __restrict__ A) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)R * M) return;
+    const float old = th_old[i];
+    const double sd = kStepSd[(int)sd_idx[i]];
+    const double lo = (double)(blo - old) / sd, hi = (double)(bhi - old) / sd;
+    A[i] = theta_log_A(th_new[i], old, S1[i], S0[i], lo, hi, sd, c, true);
+}
+
+// =============================================================================
+// deterministic reductions over [R][M]
+// =============================================================================
+#define RL_MAXE 4
+struct RlArgs {
+    double fn[RL_MAXE], fp[RL_MAXE];
+    int E;
+    double p, q, betaln;
+};
+__global__ void __launch_bounds__(256)
+row_loglik_kernel(const float* __restrict__ theta, const int32_t* __restrict__ ids, int R, int M,
+                  const int32_t* __restrict__ S1, const int32_t* __restrict__ S0, RlArgs g,
+                  double* __restrict__ out, double* __restrict__ prior_out) {
+    __shared__ double red[40];
+    const int r = blockIdx.x;
+    const long long row = ids ? ids[r] : r;
+    double acc[RL_MAXE] = {0.0, 0.0, 0.0, 0.0};
+    double pr = 0.0;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const float th = theta[row * M + m];
+        const double s1 = (double)S1[(long long)r * M + m], s0 = (double)S0[(long long)r * M + m];
+#pragma unroll
+        for (int e = 0; e < RL_MAXE; ++e) {
+            if (e < g.E) {
+                double a, b;
+                log_p1_p0(th, g.fn[e], g.fp[e], a, b);
+                acc[e] += s1 * a + s0 * b;
+            }
+        }
+        if (prior_out) pr += beta_logpdf((double)th, g.p, g.q, g.betaln);
+    }
+    for (int e = 0; e < g.E; ++e) {
+        const double s = block_sum(acc[e], red);
+        if (threadIdx.x == 0) out[(long long)e * R + r] = s;
+    }
+    if (prior_out) {
+        const double s = block_sum(pr, red);
+        if (threadIdx.x == 0) prior_out[r] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+row_sum_kernel(const double* __restrict__ v, int R, int M, double* __restrict__ out) {
+    __shared__ double red[40];
+    const int r = blockIdx.x;
+    double acc = 0.0;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) acc += v[(long long)r * M + m];
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) out[r] = s;
+}
+
+// =============================================================================
+// split-merge support
+// =============================================================================
+__global__ void __launch_bounds__(1024)
+gather_count_kernel(const int32_t* __restrict__ assign, int N, int id_a, int id_b, int32_t* blk) {
+    __shared__ int ca, cb;
+    if (threadIdx.x == 0) { ca = 0; cb = 0; }
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = (n < N) ? assign[n] : -1;
+    const unsigned ma = __ballot_sync(FULL, v == id_a && n < N);
+    const unsigned mb = __ballot_sync(FULL, id_b >= 0 && v == id_b && n < N);
+    if ((threadIdx.x & 31) == 0) {
+        if (ma) atomicAdd(&ca, __popc(ma));
+        if (mb) atomicAdd(&cb, __popc(mb));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { blk[2 * blockIdx.x] = ca; blk[2 * blockIdx.x + 1] = cb; }
+}
+__global__ void gather_scan_kernel(int32_t* blk, int nb) {
+    // single thread: exclusive scans; the id_b region starts after all of id_a
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int ta = 0;
+    for (int b = 0; b < nb; ++b) { const int c = blk[2 * b]; blk[2 * b] = ta; ta += c; }
+    int tb = ta;
+    for (int b = 0; b < nb; ++b) { const int c = blk[2 * b + 1]; blk[2 * b + 1] = tb; tb += c; }
+    blk[2 * nb] = ta;
+    blk[2 * nb + 1] = tb;
+}
+__global__ void __launch_bounds__(1024)
+gather_scatter_kernel(const int32_t* __restrict__ assign, int N, int id_a, int id_b,
+                      const int32_t* __restrict__ blk, int32_t* __restrict__ cells_out) {
+    __shared__ int wa[32], wb[32];
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int v = (n < N) ? assign[n] : -1;
+    const bool ia = (n < N) && v == id_a, ib = (n < N) && id_b >= 0 && v == id_b;
+    const unsigned ma = __ballot_sync(FULL, ia), mb = __ballot_sync(FULL, ib);
+    if (lane == 0) { wa[w] = __popc(ma); wb[w] = __popc(mb); }
+    __syncthreads();
+    if (w == 0) {
+        int a = wa[lane], b = wb[lane];
+        int sa = a, sb = b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ta = __shfl_up_sync(FULL, sa, o), tb = __shfl_up_sync(FULL, sb, o);
+            if (lane >= o) { sa += ta; sb += tb; }
+        }
+        wa[lane] = sa - a; wb[lane] = sb - b;
+    }
+    __syncthreads();
+    const unsigned lt = (1u << lane) - 1u;
+    if (ia) cells_out[blk[2 * blockIdx.x] + wa[w] + __popc(ma & lt)] = n;
+    if (ib) cells_out[blk[2 * blockIdx.x + 1] + wb[w] + __popc(mb & lt)] = n;
+}
+
+__global__ void anchor_swaps_kernel(int32_t* cells, int n, int n_a, int idx_i, int idx_j, int is_merge) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (!is_merge) {                       // libs/CRP.py:449-450
+        int t = cells[0]; cells[0] = cells[idx_i]; cells[idx_i] = t;
+        t = cells[n - 1]; cells[n - 1] = cells[idx_j]; cells[idx_j] = t;
+    } else {                               // libs/CRP.py:496,500 (each half swapped on its own)
+        int t = cells[0]; cells[0] = cells[idx_i]; cells[idx_i] = t;
+        t = cells[n - 1]; cells[n - 1] = cells[n_a + idx_j]; cells[n_a + idx_j] = t;
+    }
+}
+
+struct K6 { double k[6]; };
+__global__ void rg_launch_halves_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0,
+                                        int W, const int32_t* __restrict__ cells, int n, K6 k6,
+                                        int32_t* __restrict__ half) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n - 2) return;
+    const long long c = cells[s + 1], ci = cells[0], cj = cells[n - 1];
+    int ci_[6] = {0, 0, 0, 0, 0, 0}, cj_[6] = {0, 0, 0, 0, 0, 0};
+    for (int w = 0; w < W; ++w) {
+        const uint32_t s1 = x1[c * W + w], s0 = x0[c * W + w];
+        uint32_t a1 = x1[ci * W + w], a0 = x0[ci * W + w], am = ~(a1 | a0);
+        ci_[0] += __popc(a1 & s1); ci_[1] += __popc(a1 & s0);
+        ci_[2] += __popc(a0 & s1); ci_[3] += __popc(a0 & s0);
+        ci_[4] += __popc(am & s1); ci_[5] += __popc(am & s0);
+        a1 = x1[cj * W + w]; a0 = x0[cj * W + w]; am = ~(a1 | a0);
+        cj_[0] += __popc(a1 & s1); cj_[1] += __popc(a1 & s0);
+        cj_[2] += __popc(a0 & s1); cj_[3] += __popc(a0 & s0);
+        cj_[4] += __popc(am & s1); cj_[5] += __popc(am & s0);
+    }
+    double li = 0.0, lj = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { li += (double)ci_[q] * k6.k[q]; lj += (double)cj_[q] * k6.k[q]; }
+    half[s] = (lj > li) ? 1 : 0;
+}
+
+__global__ void rg_count_kernel(const int32_t* __restrict__ half, int nfree, int32_t* seg_off) {
+    // seg_off[3] accumulates the number of side-1 free cells; seg_off[4..5] are cursors
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = (s < nfree) ? half[s] : 0;
+    const unsigned m = __ballot_sync(FULL, v == 1);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&seg_off[3], __popc(m));
+}
+__global__ void rg_sides_kernel(const int32_t* __restrict__ cells, int n, const int32_t* __restrict__ half,
+                                int32_t* __restrict__ members, int32_t* seg_off) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int n_i = (n - 2 - seg_off[3]) + 1;
+    const int side = (s == 0) ? 0 : ((s == n - 1) ? 1 : half[s - 1]);
+    const int pos = atomicAdd(&seg_off[4 + side], 1);
+    members[(side ? n_i : 0) + pos] = cells[s];
+    if (s == 0) { seg_off[0] = 0; seg_off[1] = n_i; seg_off[2] = n; }
+}
+
+// restricted Gibbs scan, one warp (libs/CRP.py:609-632 / :806-818).  The scan is a strictly
+// sequential 2-way draw per free cell; lanes prefetch 32 steps of inputs at a time and the
+// serial arithmetic is replicated across lanes.
+__global__ void __launch_bounds__(32)
+rg_scan_kernel(const double* __restrict__ ll2, int ldk, int n, const int32_t* __restrict__ perm,
+               const double* __restrict__ u, int32_t* half, double alpha, int mode,
+               const int32_t* __restrict__ cells, const int32_t* __restrict__ assign, int id_i,
+               double* __restrict__ lq) {
+    const int lane = threadIdx.x;
+    const int nf = n - 2;
+    int ones = 0;
+    for (int s = lane; s < nf; s += 32) ones += half[s];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ones += __shfl_xor_sync(FULL, ones, o);
+    const double cn = log((double)n - 1.0 + alpha);
+    for (int base = 0; base < nf; base += 32) {
+        const int step = base + lane;
+        int c = 0, hc = 0, forced = 0;
+        double l0 = 0.0, l1 = 0.0, uu = 0.5;
+        if (step < nf) {
+            c = (mode == 0) ? perm[step] : step;
+            l0 = ll2[(long long)c * ldk];
+            l1 = ll2[(long long)c * ldk + 1];
+            hc = half[c];
+            if (mode == 0) uu = u[step];
+            else forced = (assign[cells[c + 1]] == id_i) ? 0 : 1;
+        }
+        const int cntb = min(32, nf - base);
+        for (int i = 0; i < cntb; ++i) {
+            const int ci = __shfl_sync(FULL, c, i), hci = __shfl_sync(FULL, hc, i);
+            const double a0 = __shfl_sync(FULL, l0, i), a1 = __shfl_sync(FULL, l1, i);
+            const double ui = __shfl_sync(FULL, uu, i);
+            const int fi = __shfl_sync(FULL, forced, i);
+            const int ones_ex = ones - hci;
+            const int n_j = ones_ex + 1, n_i = n - n_j - 1;
+            int side;
+            double lp_side = 0.0;
+            const double gap = a1 - a0;
+            if (mode == 0 && lq == nullptr && fabs(gap) > 60.0 && ui > 1e-12 && ui < 1.0 - 1e-12) {
+                // |log n_j - log n_i| < 21, so the loser's probability is < e^-39: the draw
+                // cannot land on it for u in (1e-12, 1-1e-12)
+                side = gap > 0.0 ? 1 : 0;
+            } else {
+                const double p0 = a0 + (log((double)n_i) - cn);
+                const double p1 = a1 + (log((double)n_j) - cn);
+                const int top = (p1 > p0) ? 1 : 0;
+                const double other = (top ? p0 : p1) - (top ? p1 : p0);
+                const double lse = log1p(exp(other));
+                const double lpt = 0.0 - lse, lpo = other - lse;
+                const double lp0 = top ? lpo : lpt, lp1 = top ? lpt : lpo;
+                if (mode == 0) {
+                    const double e0 = exp(lp0), e1 = exp(lp1);
+                    side = (ui < e0 / (e0 + e1)) ? 0 : 1;
+                } else {
+                    side = fi;
+                }
+                lp_side = side ? lp1 : lp0;
+            }
+            if (lane == 0) {
+                half[ci] = side;
+                if (lq) lq[ci] = lp_side;
+            }
+            ones = ones_ex + side;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void apply_split_kernel(const int32_t* __restrict__ cells, int n, const int32_t* __restrict__ half,
+                                   int new_id, int32_t* assign) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const bool mv = (s == n - 1) || (s > 0 && half[s - 1] == 1);
+    if (mv) assign[cells[s]] = new_id;
+}
+__global__ void apply_merge_kernel(const int32_t* __restrict__ cells, int n_a, int n, int id, int32_t* assign) {
+    const int s = n_a + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) assign[cells[s]] = id;
+}
+
+// =============================================================================
+// C ABI
+// =============================================================================
+extern "C" {
+
+int bnpc_abi_version(void) { return BNPC_ABI_VERSION; }
+const char* bnpc_last_error(void) { return g_err; }
+
+int bnpc_pack_planes(const double* x_f64, const int8_t* x_i8, int N, int M, int W, uint32_t* x1,
+                     uint32_t* x0, int32_t* n1, int32_t* n0, void* stream) {
+    if ((x_f64 == nullptr) == (x_i8 == nullptr)) return bad_arg("exactly one of x_f64 / x_i8");
+    if (W % 4 != 0 || W * 32 < M) return bad_arg("W must be a multiple of 4 with 32*W >= M");
+    if (N <= 0) return 0;
+    const int blocks = (int)min((long long)cdiv((long long)N * 32, 256), 148ll * 64);
+    pack_planes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x_f64, x_i8, N, M, W, x1, x0, n1, n0);
+    LAUNCH_CHECK("pack_planes");
+    return 0;
+}
+
+int bnpc_fill_uniform(double* out, int64_t n, uint64_t seed, uint64_t stream_id, int n_levels,
+                      void* stream) {
+    if (n <= 0) return 0;
+    const long long pairs = (n + 1) / 2;
+    fill_uniform_kernel<<<cdiv(pairs, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, stream_id, n_levels);
+    LAUNCH_CHECK("fill_uniform");
+    return 0;
+}
+
+int bnpc_fill_permutation(int32_t* out, int n, uint64_t seed, uint64_t stream_id, void* stream) {
+    if (n <= 0) return 0;
+    int bits = 2;
+    while ((1ll << bits) < n) ++bits;
+    if (bits & 1) ++bits;
+    fill_permutation_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, stream_id, bits / 2);
+    LAUNCH_CHECK("fill_permutation");
+    return 0;
+}
+
+int bnpc_logprob_tables(const float* theta, const int32_t* ids, int R, int M, double FN, double FP,
+                        double* lp, void* stream) {
+    if (R <= 0) return 0;
+    logprob_tables_kernel<<<cdiv((long long)R * M, 256), 256, 0, (cudaStream_t)stream>>>(
+        theta, ids, R, M, FN, FP, reinterpret_cast<double2*>(lp));
+    LAUNCH_CHECK("logprob_tables");
+    return 0;
+}
+
+int bnpc_ll_matrix(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
+                   int cell_stride, int C, const double* lp, int K, double* ll, int ldk, void* stream) {
+    if (C <= 0 || K <= 0) return 0;
+    if (ldk < K) return bad_arg("ldk < K");
+    if (W % 4 != 0) return bad_arg("W must be a multiple of 4");
+    dim3 grid(cdiv(C, LL_THREADS), cdiv(K, LL_KT));
+    if (grid.y > 65535) return bad_arg("too many clusters for one ll_matrix launch");
+    ll_matrix_kernel<<<grid, LL_THREADS, 0, (cudaStream_t)stream>>>(
+        x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const double2*>(lp), K, ll, ldk);
+    LAUNCH_CHECK("ll_matrix");
+    return 0;
+}
+
+int bnpc_gibbs_prepare(const int32_t* perm, const double* u, const int32_t* assign, const int32_t* n1,
+                       const int32_t* n0, int N, double c1, double c0, double lnew_prior,
+                       bnpc_visit_t* visit, void* stream) {
+    if (N <= 0) return 0;
+    gibbs_prepare_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(perm, u, assign, n1, n0, N, c1, c0,
+                                                                        lnew_prior, visit);
+    LAUNCH_CHECK("gibbs_prepare");
+    return 0;
+}
+
+int bnpc_gibbs_epoch_begin(const int32_t* live, int K, int32_t* lst, int32_t* cnt, int32_t* col_of_id,
+                           int idcap, int32_t* st, int first, void* stream) {
+    if (K > idcap) return bad_arg("K > idcap");
+    gibbs_epoch_begin_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(live, K, lst, cnt, col_of_id, idcap, st,
+                                                                  first);
+    LAUNCH_CHECK("gibbs_epoch_begin");
+    return 0;
+}
+
+int bnpc_gibbs_sweep(const bnpc_sweep_args_t* a, int block_threads, void* stream) {
+    if (!a) return bad_arg("args");
+    if (block_threads < 32 || block_threads > 1024 || block_threads % 32) return bad_arg("block_threads");
+    if (a->ldk % 2) return bad_arg("ldk must be even (16-byte rows)");
+    if (a->t_begin < a->t_epoch0 || a->t_end - a->t_epoch0 > a->ldx) return bad_arg("sweep range vs ldx");
+    gibbs_sweep_kernel<<<1, block_threads, 0, (cudaStream_t)stream>>>(*a);
+    LAUNCH_CHECK("gibbs_sweep");
+    return 0;
+}
+
+int bnpc_set_ranks(const int32_t* ids, int K, int32_t* rank_of_id, void* stream) {
+    if (K <= 0) return 0;
+    set_ranks_kernel<<<cdiv(K, 256), 256, 0, (cudaStream_t)stream>>>(ids, K, rank_of_id);
+    LAUNCH_CHECK("set_ranks");
+    return 0;
+}
+
+int bnpc_group_members(const int32_t* assign, int N, const int32_t* rank_of_id, const int32_t* seg_off,
+                       int32_t* cursor, int K, int32_t* members, void* stream) {
+    if (N <= 0) return 0;
+    cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)K, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("group_members memset", e);
+    group_members_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(assign, N, rank_of_id, seg_off,
+                                                                        cursor, members);
+    LAUNCH_CHECK("group_members");
+    return 0;
+}
+
+int bnpc_suffstat(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* members,
+                  const int32_t* seg_off, int R, int max_len, int32_t* S1, int32_t* S0, void* stream) {
+    if (R <= 0) return 0;
+    cudaError_t e = cudaMemsetAsync(S1, 0, sizeof(int32_t) * (size_t)R * M, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(S0, 0, sizeof(int32_t) * (size_t)R * M, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("suffstat memset", e);
+    if (max_len <= 0) return 0;
+    // grid.y is limited to 65535: tile the segment axis
+    for (int r0 = 0; r0 < R; r0 += 65535) {
+        const int rr = min(65535, R - r0);
+        dim3 grid(cdiv(max_len, SS_CHUNK), rr);
+        suffstat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x1, x0, W, M, members, seg_off + r0,
+                                                               S1 + (size_t)r0 * M, S0 + (size_t)r0 * M);
+        LAUNCH_CHECK("suffstat");
+    }
+    return 0;
+}
+
+int bnpc_beta_rows(const int32_t* S1, const int32_t* S0, int R, int M, double p, double q,
+                   const double* tape, uint64_t seed, uint64_t stream_id, float* theta_out,
+                   const int32_t* out_ids, void* stream) {
+    if (R <= 0) return 0;
+    beta_rows_kernel<<<cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream>>>(
+        S1, S0, R, M, p, q, tape, seed, stream_id, theta_out, out_ids);
+    LAUNCH_CHECK("beta_rows");
+    return 0;
+}
+
+int bnpc_theta_from_uniform(const double* u, int R, int M, float* theta_out, const int32_t* out_ids,
+                            void* stream) {
+    if (R <= 0) return 0;
+    theta_from_uniform_kernel<<<cdiv((long long)R * M, 256), 256, 0, (cudaStream_t)stream>>>(u, R, M, theta_out,
+                                                                                           out_ids);
+    LAUNCH_CHECK("theta_from_uniform");
+    return 0;
+}
+
+static MhConst make_mh_const(double FN, double FP, double p, double q) {
+    MhConst c;
+    c.FN = FN; c.FP = FP; c.p = p; c.q = q;
+    c.flat = (p == 1.0 && q == 1.0);
+    c.betaln = lgamma(p) + lgamma(q) - lgamma(p + q);
+    return c;
+}
+
+int bnpc_mh_theta(float* theta, const int32_t* ids, int R, int M, const int32_t* S1, const int32_t* S0,
+                  const double* rnd, double FN, double FP, double p, double q, int flags, double* logq,
+                  int32_t* declined, void* stream) {
+    if (R <= 0) return 0;
+    if ((flags & 1) && !logq) return bad_arg("logq required when flags&1");
+    mh_theta_kernel<<<cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream>>>(
+        theta, ids, R, M, S1, S0, rnd, make_mh_const(FN, FP, p, q), flags, logq, declined);
+    LAUNCH_CHECK("mh_theta");
+    return 0;
+}
+
+int bnpc_theta_log_ratio(const float* th_new, const float* th_old, int R, int M, const int32_t* S1,
+                         const int32_t* S0, const double* sd_idx, float blo, float bhi, double FN,
+                         double FP, double p, double q, double* A, void* stream) {
+    if (R <= 0) return 0;
+    theta_log_ratio_kernel<<<cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream>>>(
+        th_new, th_old, R, M, S1, S0, sd_idx, blo, bhi, make_mh_const(FN, FP, p, q), A);
+    LAUNCH_CHECK("theta_log_ratio");
+    return 0;
+}
+
+int bnpc_row_loglik(const float* theta, const int32_t* ids, int R, int M, const int32_t* S1,
+                    const int32_t* S0, const double* fn_h, const double* fp_h, int E, double p,
+                    double q, double* out, double* prior_out, void* stream) {
+    if (R <= 0) return 0;
+    if (E < 0 || E > RL_MAXE) return bad_arg("E must be in [0,4]");
+    RlArgs g;
+    memset(&g, 0, sizeof(g));
+    g.E = E;
+    for (int e = 0; e < E; ++e) { g.fn[e] = fn_h[e]; g.fp[e] = fp_h[e]; }
+    g.p = p; g.q = q;
+    g.betaln = lgamma(p) + lgamma(q) - lgamma(p + q);
+    row_loglik_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(theta, ids, R, M, S1, S0, g, out, prior_out);
+    LAUNCH_CHECK("row_loglik");
+    return 0;
+}
+
+int bnpc_row_sum(const double* v, int R, int M, double* out, void* stream) {
+    if (R <= 0) return 0;
+    row_sum_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(v, R, M, out);
+    LAUNCH_CHECK("row_sum");
+    return 0;
+}
+
+int bnpc_gather_members(const int32_t* assign, int N, int id_a, int id_b, int32_t* cells_out,
+                        int32_t* blk, void* stream) {
+    if (N <= 0) return 0;
+    const int nb = cdiv(N, 1024);
+    gather_count_kernel<<<nb, 1024, 0, (cudaStream_t)stream>>>(assign, N, id_a, id_b, blk);
+    LAUNCH_CHECK("gather_count");
+    gather_scan_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(blk, nb);
+    LAUNCH_CHECK("gather_scan");
+    gather_scatter_kernel<<<nb, 1024, 0, (cudaStream_t)stream>>>(assign, N, id_a, id_b, blk, cells_out);
+    LAUNCH_CHECK("gather_scatter");
+    return 0;
+}
+
+int bnpc_anchor_swaps(int32_t* cells, int n, int n_a, int idx_i, int idx_j, int is_merge, void* stream) {
+    if (n < 2) return bad_arg("n < 2");
+    anchor_swaps_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(cells, n, n_a, idx_i, idx_j, is_merge);
+    LAUNCH_CHECK("anchor_swaps");
+    return 0;
+}
+
+int bnpc_rg_launch_halves(const uint32_t* x1, const uint32_t* x0, int W, const int32_t* cells, int n,
+                          const double* k6_h, int32_t* half, void* stream) {
+    if (n <= 2) return 0;
+    K6 k;
+    for (int i = 0; i < 6; ++i) k.k[i] = k6_h[i];
+    rg_launch_halves_kernel<<<cdiv(n - 2, 128), 128, 0, (cudaStream_t)stream>>>(x1, x0, W, cells, n, k, half);
+    LAUNCH_CHECK("rg_launch_halves");
+    return 0;
+}
+
+int bnpc_rg_sides(const int32_t* cells, int n, const int32_t* half, int32_t* members, int32_t* seg_off,
+                  void* stream) {
+    if (n < 2) return bad_arg("n < 2");
+    cudaError_t e = cudaMemsetAsync(seg_off, 0, sizeof(int32_t) * 8, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("rg_sides memset", e);
+    if (n > 2) {
+        rg_count_kernel<<<cdiv(n - 2, 256), 256, 0, (cudaStream_t)stream>>>(half, n - 2, seg_off);
+        LAUNCH_CHECK("rg_count");
+    }
+    rg_sides_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(cells, n, half, members, seg_off);
+    LAUNCH_CHECK("rg_sides");
+    return 0;
+}
+
+int bnpc_rg_scan(const double* ll2, int ldk, int n, const int32_t* perm, const double* u, int32_t* half,
+                 double alpha, int mode, const int32_t* cells, const int32_t* assign, int id_i,
+                 double* lq, void* stream) {
+    if (n <= 2) return 0;
+    if (mode == 0 && (!perm || !u)) return bad_arg("perm/u required for a sampled scan");
+    if (mode == 1 && (!cells || !assign || !lq)) return bad_arg("cells/assign/lq required for replay");
+    rg_scan_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ll2, ldk, n, perm, u, half, alpha, mode, cells, assign,
+                                                       id_i, lq);
+    LAUNCH_CHECK("rg_scan");
+    return 0;
+}
+
+int bnpc_apply_split(const int32_t* cells, int n, const int32_t* half, int new_id, int32_t* assign,
+                     void* stream) {
+    apply_split_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(cells, n, half, new_id, assign);
+    LAUNCH_CHECK("apply_split");
+    return 0;
+}
+
+int bnpc_apply_merge(const int32_t* cells, int n_a, int n, int id, int32_t* assign, void* stream) {
+    if (n <= n_a) return 0;
+    apply_merge_kernel<<<cdiv(n - n_a, 256), 256, 0, (cudaStream_t)stream>>>(cells, n_a, n, id, assign);
+    LAUNCH_CHECK("apply_merge");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+/*
+ * bnpc_b200.h -- C ABI of the B200-native BnpC MCMC hot path.
+ *
+ * The reference (cbg-ethz/BnpC v0.2.1) is pure Python: it has no FFI of its own.
+ * Its boundary for this path is the duck-typed class contract consumed by
+ * libs/MCMC.py:320-342 (Chain.do_step) and libs/MCMC.py:242-282
+ * (Chain.update_results).  The entry points below are the device-side pieces
+ * of that contract; each one cites the reference function(s) whose arithmetic
+ * it replaces.  Host orchestration (which entry point is called when) mirrors
+ * the reference methods one-to-one and lives in bnpc_b200/engine.py behind
+ * libs/CRP.py / libs/CRP_learning_errors.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure;
+ *     bnpc_last_error() then returns a static, thread-local message;
+ *   - all pointers are DEVICE pointers owned by the caller (allocated by
+ *     PyTorch on the current device) unless the name ends in _h; the library
+ *     allocates nothing and keeps no state between calls;
+ *   - `stream` is a cudaStream_t passed as void*; every launch is asynchronous
+ *     on that stream; no entry point synchronises;
+ *   - data layout: two bit-planes per matrix, cell-major.  x1[n*W + w] bit b is
+ *     set iff data[n][32*w+b] == 1, x0 likewise for == 0; a missing entry has
+ *     neither bit; W is a multiple of 4 (rows are 16-byte aligned) and bits
+ *     beyond M are zero;
+ *   - cluster parameters theta are float32 [idcap][M], indexed by the
+ *     reference's cluster id (smallest unused non-negative integer,
+ *     libs/CRP.py:297-299);
+ *   - "list order" is the insertion order of the reference's
+ *     cells_per_cluster dict (libs/CRP.py:268).
+ */
+#ifndef BNPC_B200_H
+#define BNPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNPC_ABI_VERSION 1
+
+/* capacity of clusters born since the ll matrix of the current epoch was built */
+#define BNPC_MAX_EXTRA 32
+
+/* ints in the sweep status block `st` */
+#define BNPC_ST_K        0   /* live clusters (length of the list)            */
+#define BNPC_ST_TDONE    1   /* sweep position reached (cells [0,t) processed) */
+#define BNPC_ST_FLAGS    2   /* BNPC_STOP_* bits                               */
+#define BNPC_ST_NEXTRA   3   /* clusters born in this epoch                    */
+#define BNPC_ST_BIRTHS   4   /* clusters born in this sweep (tape rows used)   */
+#define BNPC_ST_MOVED    5   /* cells whose cluster changed in this sweep      */
+#define BNPC_ST_SLOW     6   /* cells that took the exact (slow) path          */
+#define BNPC_ST_WORDS    16
+
+#define BNPC_STOP_EXTRA_FULL  1  /* BNPC_MAX_EXTRA births: start a new epoch      */
+#define BNPC_STOP_REPACK      2  /* list shrank below a warp but ll rows are wide */
+#define BNPC_STOP_TAPE_EMPTY  4  /* parity mode: more births than taped rows      */
+#define BNPC_STOP_CAPACITY    8  /* list/id capacity reached: grow and relaunch   */
+
+/* per-cell record of a sweep, in visiting order (32 bytes) */
+typedef struct {
+    double  u;      /* uniform for the categorical draw (libs/CRP.py:277)             */
+    double  lnew;   /* new-cluster log posterior of this cell (libs/CRP.py:230-234)   */
+    int32_t cell;   /* cell index = permutation[t] (libs/CRP.py:260)                  */
+    int32_t old;    /* its cluster id before the sweep                                 */
+    int32_t pad[2];
+} bnpc_visit_t;
+
+int         bnpc_abi_version(void);
+const char* bnpc_last_error(void);
+
+/* ---- input path: libs/dpmmIO.py:27-98 produces float64 {0,1,NaN}; this packs it.
+ * x_f64 [N][M] row-major (NaN or any value other than 0/1 = missing), or
+ * x_i8 [N][M] (0, 1, anything else = missing).  Exactly one of the two is non-NULL.
+ * Outputs: x1,x0 [N][W]; n1,n0 [N] = per-cell counts of ones / zeros.            */
+int bnpc_pack_planes(const double* x_f64, const int8_t* x_i8, int N, int M, int W,
+                     uint32_t* x1, uint32_t* x0, int32_t* n1, int32_t* n0, void* stream);
+
+/* ---- counter-based random numbers (production mode; parity mode injects a tape).
+ * out[i] = U[0,1) from Philox4x32-10(key=seed, counter=(i, stream_id)); if
+ * n_levels > 0 the value is floor(u * n_levels) instead (numpy randint stand-in,
+ * libs/CRP.py:328).                                                              */
+int bnpc_fill_uniform(double* out, int64_t n, uint64_t seed, uint64_t stream_id,
+                      int n_levels, void* stream);
+/* out = a pseudo-random permutation of 0..n-1 (keyed Feistel network with cycle
+ * walking); stands in for np.random.permutation (libs/CRP.py:260,616).           */
+int bnpc_fill_permutation(int32_t* out, int n, uint64_t seed, uint64_t stream_id,
+                          void* stream);
+
+/* ---- likelihood, libs/CRP.py:197-212 (_calc_ll, _Bernoulli_FN, _Bernoulli_FP).
+ * lp[r][m] = { log(th*(1-FN) + (1-th)*FP), log(th*FN + (1-th)*(1-FP)) } for
+ * th = theta[ids[r]][m] (ids==NULL: row r), with (1-th) rounded in float32 as
+ * the reference does.                                                            */
+int bnpc_logprob_tables(const float* theta, const int32_t* ids, int R, int M,
+                        double FN, double FP, double* lp /* [R][M][2] */, void* stream);
+/* ll[r][k] = sum_m x1[c][m]*lp[k][m][0] + x0[c][m]*lp[k][m][1], c = cells[r]
+ * (cells==NULL: c = r; cells may point into bnpc_visit_t records: pass
+ * cell_stride = 8 ints, else 1).  FP64 accumulation in mutation order.          */
+int bnpc_ll_matrix(const uint32_t* x1, const uint32_t* x0, int W, int M,
+                   const int32_t* cells, int cell_stride, int C,
+                   const double* lp, int K, double* ll, int ldk, void* stream);
+
+/* ---- Gibbs sweep, libs/CRP.py:254-299 (+ :88-100, :183-188, :223-234).
+ * bnpc_gibbs_prepare builds the visit records for a whole sweep:
+ *   visit[t] = {u[t], n1[c]*c1 + n0[c]*c0 + lnew_prior, c = perm[t], assign[c]}.  */
+int bnpc_gibbs_prepare(const int32_t* perm, const double* u, const int32_t* assign,
+                       const int32_t* n1, const int32_t* n0, int N,
+                       double c1, double c0, double lnew_prior,
+                       bnpc_visit_t* visit, void* stream);
+/* Start of an epoch: rebuild cnt[] from the host-authoritative list
+ * live[2*j] = id, live[2*j+1] = size (list order), set col_of_id[id] = j and
+ * clear the epoch's extra-cluster bookkeeping.  first != 0 also resets the
+ * per-sweep counters in st.                                                       */
+int bnpc_gibbs_epoch_begin(const int32_t* live, int K, int32_t* lst, int32_t* cnt,
+                           int32_t* col_of_id, int idcap, int32_t* st, int first,
+                           void* stream);
+typedef struct {
+    /* data */
+    const uint32_t* x1; const uint32_t* x0; int32_t W; int32_t N; int32_t M;
+    /* chain state */
+    int32_t* assign; int32_t* cnt; int32_t* lst; int32_t* col_of_id; float* theta;
+    int32_t idcap; int32_t* st; int32_t* live_out /* [2*idcap] (id,size) at exit */;
+    /* epoch */
+    const double* ll; int32_t ldk; int32_t t_epoch0;
+    double* lpx /* [MAX_EXTRA][M][2] */; double* llx /* [MAX_EXTRA][ldx] */; int32_t ldx;
+    double* scratch /* [idcap+1] */;
+    /* sweep inputs */
+    const bnpc_visit_t* visit; int32_t t_begin; int32_t t_end;
+    const double* beta_rows /* parity tape [n_beta_rows][M] or NULL */; int32_t n_beta_rows;
+    uint64_t seed; uint64_t stream_id;
+    /* constants */
+    const double* logn /* [N+1], logn[n] = log(n) as numpy computes it */;
+    double c_norm /* log(N-1+alpha) */; double FN; double FP; double p; double q;
+} bnpc_sweep_args_t;
+int bnpc_gibbs_sweep(const bnpc_sweep_args_t* args_h, int block_threads, void* stream);
+
+/* ---- sufficient statistics: S1[r][m], S0[r][m] = number of cells of segment r
+ * with a 1 / a 0 at mutation m.  Segment r = members[seg_off[r] .. seg_off[r+1]).
+ * Replaces the data[cells] gathers of libs/CRP.py:308,360-367 and the [N,M]
+ * passes of libs/CRP.py:237-238, libs/CRP_learning_errors.py:58-63.              */
+int bnpc_group_members(const int32_t* assign, int N, const int32_t* rank_of_id,
+                       const int32_t* seg_off, int32_t* cursor, int K,
+                       int32_t* members, void* stream);
+int bnpc_set_ranks(const int32_t* ids, int K, int32_t* rank_of_id, void* stream);
+int bnpc_suffstat(const uint32_t* x1, const uint32_t* x0, int W, int M,
+                  const int32_t* members, const int32_t* seg_off, int R, int max_len,
+                  int32_t* S1, int32_t* S0, void* stream);
+
+/* ---- Beta draws for cluster parameters, libs/CRP.py:172-175,183-188:
+ * theta_out[r][m] = float32(clip(Beta(p + S1[r][m], q + S0[r][m]), 1e-5, 1-1e-5)).
+ * tape != NULL: tape[r][m] holds the Beta variates (parity mode).                */
+int bnpc_beta_rows(const int32_t* S1, const int32_t* S0, int R, int M, double p, double q,
+                   const double* tape, uint64_t seed, uint64_t stream_id,
+                   float* theta_out, const int32_t* out_ids, void* stream);
+/* theta_out[ids[r]][m] = float32(clip(u[r][m], 1e-5, 1-1e-5)), libs/CRP.py:176-180 */
+int bnpc_theta_from_uniform(const double* u, int R, int M, float* theta_out,
+                            const int32_t* out_ids, void* stream);
+
+/* ---- Metropolis-Hastings on cluster parameters, libs/CRP.py:314-383
+ * (MH_cluster_params, _get_log_A).  Row r updates theta[ids[r]] (ids==NULL: row
+ * r) in place from S1/S0 row r.  rnd = [3][R][M]: proposal-sd index, truncnorm
+ * uniform, acceptance uniform.  flags: bit0 = want transition log-probabilities
+ * (trans_prob=True): logq[r][m] is written and A is clipped at 0.
+ * declined[r] is incremented by the number of rejected proposals of row r.       */
+int bnpc_mh_theta(float* theta, const int32_t* ids, int R, int M,
+                  const int32_t* S1, const int32_t* S0, const double* rnd,
+                  double FN, double FP, double p, double q, int flags,
+                  double* logq, int32_t* declined, void* stream);
+/* A[r][m] of libs/CRP.py:347-383 for given (new, old) rows without a draw (used
+ * by libs/CRP.py:674-681 and :777-797): bounds are lo=(blo-old)/sd, hi=(bhi-old)/sd
+ * with the subtraction rounded in float32; A clipped at 0.                        */
+int bnpc_theta_log_ratio(const float* th_new, const float* th_old, int R, int M,
+                         const int32_t* S1, const int32_t* S0, const double* sd_idx,
+                         float blo, float bhi, double FN, double FP, double p, double q,
+                         double* A, void* stream);
+
+/* ---- reductions over [R][M]: libs/CRP.py:237-251, 716-733,
+ * libs/CRP_learning_errors.py:58-63.  For each of the E (FN,FP) pairs
+ * out[e*R + r] = sum_m S1*log p1 + S0*log p0 for row r (theta[ids[r]]);
+ * if prior_out != NULL, prior_out[r] = sum_m Beta(p,q).logpdf(theta[ids[r]][m]).
+ * Deterministic (fixed summation order).                                          */
+int bnpc_row_loglik(const float* theta, const int32_t* ids, int R, int M,
+                    const int32_t* S1, const int32_t* S0,
+                    const double* fn_h, const double* fp_h, int E,
+                    double p, double q, double* out, double* prior_out, void* stream);
+/* out[r] = sum_m v[r][m] (fixed order) */
+int bnpc_row_sum(const double* v, int R, int M, double* out, void* stream);
+
+/* ---- split-merge support, libs/CRP.py:434-567,609-638,777-820 ---------------- */
+/* ordered member lists: cells_out = [cells of id_a ascending..., cells of id_b
+ * ascending...] (id_b < 0: only id_a).  blk is scratch [ceil(N/1024)*2+2].        */
+int bnpc_gather_members(const int32_t* assign, int N, int id_a, int id_b,
+                        int32_t* cells_out, int32_t* blk, void* stream);
+/* the anchor swaps of libs/CRP.py:449-450 (split: n_a = n) and :496,:500 (merge) */
+int bnpc_anchor_swaps(int32_t* cells, int n, int n_a, int idx_i, int idx_j, int is_merge,
+                      void* stream);
+/* libs/CRP.py:547-561: half[s] = 1 if the j anchor's raw row explains free cell s
+ * better than the i anchor's.  k6 = log-likelihood constants for (anchor,cell) =
+ * (1,1),(1,0),(0,1),(0,0),(missing,1),(missing,0).                                */
+int bnpc_rg_launch_halves(const uint32_t* x1, const uint32_t* x0, int W,
+                          const int32_t* cells, int n, const double* k6_h,
+                          int32_t* half, void* stream);
+/* split `cells` by half into members = [side i..., side j...]; seg_off[0..2]      */
+int bnpc_rg_sides(const int32_t* cells, int n, const int32_t* half,
+                  int32_t* members, int32_t* seg_off, void* stream);
+/* one restricted Gibbs scan over the n-2 free cells, libs/CRP.py:609-632
+ * (mode 0: sampled, order = perm, uniforms u) or the forced replay of
+ * libs/CRP.py:806-818 (mode 1: side = (assign[cell] != id_i), natural order).
+ * ll2 [n-2][ldk>=2] from bnpc_ll_matrix.  lq[c] = log-probability of the side
+ * taken.  half is updated in place.                                               */
+int bnpc_rg_scan(const double* ll2, int ldk, int n, const int32_t* perm, const double* u,
+                 int32_t* half, double alpha, int mode, const int32_t* cells,
+                 const int32_t* assign, int id_i, double* lq, void* stream);
+/* accepted split (libs/CRP.py:471-474): assign[cell] = new_id for side-j cells;
+ * accepted merge (libs/CRP.py:517): assign[cells[n_a..n)] = id.                   */
+int bnpc_apply_split(const int32_t* cells, int n, const int32_t* half, int new_id,
+                     int32_t* assign, void* stream);
+int bnpc_apply_merge(const int32_t* cells, int n_a, int n, int id, int32_t* assign,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNPC_B200_H */
