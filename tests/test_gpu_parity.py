@@ -1,0 +1,124 @@
+"""GPU parity tests proper: the CUDA-backed classes (through libs.CRP /
+libs.CRP_learning_errors and the C ABI) replay recorded random tapes and must make the
+SAME decisions as the reference (golden fixtures) / the oracle (larger seeded cases):
+identical assignments, cluster lists, sizes and float32 parameters after every step;
+log-likelihood and log-posterior within 1e-9 relative (north star: 1e-5)."""
+import numpy as np
+import pytest
+
+from helpers import Golden, assert_state, golden_names
+from oracle.crp_oracle import (DEFAULT_MOVES, OracleCRP, OracleCRPLearnErrors, do_step, simulate,
+                               snapshot)
+from oracle.rng_tape import LegacyRandom, Tape
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+RTOL = 1e-9
+
+
+def cuda_model(learning, data, kwargs, tape_arrays):
+    from bnpc_b200.rng import Tape as PTape
+    from bnpc_b200.rng import TapeRandom
+    import libs.CRP as crp
+    import libs.CRP_learning_errors as crple
+    rnd = TapeRandom(PTape(*tape_arrays))
+    if learning:
+        m = crple.CRP_errors_learning(data, rnd=rnd, **kwargs)
+        assert m.__module__ == 'libs.CRP_learning_errors'
+    else:
+        m = crp.CRP(data, rnd=rnd, **kwargs)
+    return m, rnd
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_cuda_replays_reference_tape(name):
+    g = Golden(name)
+    m, rnd = cuda_model(g.meta['learning'], g.data, g.meta['kwargs'], g.tape_arrays)
+    m.init(assign=g.meta['init_assign'] if g.meta['init'] == 'assign' else None)
+    assert rnd.tape.pos == g.tape_pos[1]
+    assert_state(snapshot(m), g.state(0), f'{name} init', exact_float=False, rtol=RTOL)
+    for s in range(g.meta['steps']):
+        log = do_step(m, rnd, g.meta['moves'], g.meta['learning'])
+        assert log == g.steplog[s], f'{name} step {s + 1}: {log} vs {g.steplog[s]}'
+        assert rnd.tape.pos == g.tape_pos[s + 2], f'{name} step {s + 1}: tape position'
+        assert_state(snapshot(m), g.state(s + 1), f'{name} step {s + 1}', exact_float=False, rtol=RTOL)
+    assert rnd.tape.exhausted()
+
+
+def _oracle_run(data, learning, kwargs, moves, steps, seed, assign):
+    tape = Tape()
+    rnd = LegacyRandom(record=tape)
+    np.random.seed(seed)
+    cls = OracleCRPLearnErrors if learning else OracleCRP
+    o = cls(data.copy(), rnd=rnd, **kwargs)
+    o.init(assign=assign)
+    snaps, logs, pos = [snapshot(o)], [], [len(tape.records)]
+    for _ in range(steps):
+        logs.append(do_step(o, rnd, moves, learning))
+        snaps.append(snapshot(o))
+        pos.append(len(tape.records))
+    return tape, snaps, logs, pos
+
+
+CASES = [
+    # name, N, M, k_true, miss, learning, pp, init, steps, moves
+    ('mid_learn', 2000, 300, 8, 0.10, True, [0.25, 0.25], 'assign', 6, dict(DEFAULT_MOVES, sm_prob=0.5)),
+    ('mid_fixed_sm', 1500, 640, 6, 0.10, False, [1, 1], 'assign', 6, dict(DEFAULT_MOVES, sm_prob=0.75)),
+    ('panel_learn', 6000, 50, 5, 0.30, True, [1, 1], 'assign', 5, dict(DEFAULT_MOVES, sm_prob=0.4)),
+    ('random_init_bigK', 900, 120, 5, 0.10, True, [0.25, 0.25], 'random', 3, dict(DEFAULT_MOVES, sm_prob=0.0)),
+    ('random_init_sm', 300, 64, 4, 0.10, False, [0.25, 0.25], 'random', 8, dict(DEFAULT_MOVES, sm_prob=0.5)),
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_cuda_matches_oracle_on_seeded_data(case):
+    name, N, M, k, miss, learning, pp, init, steps, moves = case
+    data, z = simulate(N, M, k_true=k, miss=miss, seed=sum(map(ord, name)) % 1000)
+    if learning:
+        kwargs = dict(DP_alpha=[-1, -1], param_beta=pp, FP_mean=0.01, FP_sd=0.01, FN_mean=0.2, FN_sd=0.1)
+    else:
+        kwargs = dict(DP_alpha=[-1, -1], param_beta=pp, FN_error=0.2, FP_error=0.01)
+    assign = None
+    if init == 'assign':
+        rng = np.random.default_rng(1)
+        a = z.copy()
+        scat = rng.random(N) < 0.05
+        a[scat] = rng.integers(0, k + 2, scat.sum())
+        assign = [int(v) for v in a]
+    tape, snaps, logs, pos = _oracle_run(data, learning, kwargs, moves, steps, 17, assign)
+    m, rnd = cuda_model(learning, data, kwargs, tape.to_arrays())
+    m.init(assign=assign)
+    assert rnd.tape.pos == pos[0]
+    assert_state(snapshot(m), snaps[0], f'{name} init', exact_float=False, rtol=RTOL)
+    for s in range(steps):
+        log = do_step(m, rnd, moves, learning)
+        assert log == logs[s], f'{name} step {s + 1}: {log} vs {logs[s]}'
+        assert rnd.tape.pos == pos[s + 1], f'{name} step {s + 1}: tape position'
+        assert_state(snapshot(m), snaps[s + 1], f'{name} step {s + 1}', exact_float=False, rtol=RTOL)
+
+
+def test_production_mode_recovers_clusters_and_is_deterministic():
+    """No tape: device Philox draws.  Same seed -> identical trace; the chain finds the
+    simulated clusters (ARI vs truth) from a random start."""
+    from sklearn.metrics import adjusted_rand_score
+    from bnpc_b200.rng import PhiloxRandom
+    import libs.CRP_learning_errors as crple
+    data, z = simulate(1200, 200, k_true=6, miss=0.1, seed=12)
+    kwargs = dict(DP_alpha=[-1, -1], param_beta=[0.25, 0.25], FP_mean=0.01, FP_sd=0.01,
+                  FN_mean=0.2, FN_sd=0.1)
+    traces = []
+    for rep in range(2):
+        rnd = PhiloxRandom(2024)
+        m = crple.CRP_errors_learning(data, rnd=rnd, **kwargs)
+        m.init()
+        ll = []
+        for _ in range(40):
+            do_step(m, rnd, DEFAULT_MOVES, True)
+            ll.append(m.get_ll_full())
+        traces.append((np.array(ll), m.assignment.copy(), m.FN, m.FP))
+    np.testing.assert_array_equal(traces[0][0], traces[1][0])
+    np.testing.assert_array_equal(traces[0][1], traces[1][1])
+    assert adjusted_rand_score(z, traces[0][1]) > 0.95
+    assert 0.1 < traces[0][2] < 0.3 and traces[0][3] < 0.05
+    assert traces[0][0][-1] > traces[0][0][0]
