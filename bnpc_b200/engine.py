@@ -14,6 +14,7 @@ fallback: without the library or a CUDA device every method raises.
 Method docstrings cite the reference lines (cbg-ethz/BnpC v0.2.1) they replace.
 """
 import ctypes as C
+import threading
 from collections import OrderedDict
 
 import numpy as np
@@ -31,6 +32,7 @@ EPS = np.finfo(np.float64).resolution            # libs/CRP.py:11
 THETA_LO = 1e-5                                   # libs/CRP.py:12-13
 THETA_HI = 1 - THETA_LO
 LL_BUDGET_BYTES = 1 << 30                         # largest ll matrix built per epoch
+_PACK_LOCK = threading.Lock()                     # chains of one model pack the input once
 
 
 class _Shared:
@@ -74,7 +76,7 @@ class _ThetaView:
         scalar = np.ndim(ids) == 0
         idx = torch.as_tensor(np.atleast_1d(np.asarray(ids, dtype=np.int64)), device=o.device)
         with torch.cuda.stream(o.stream):
-            rows = o.theta.index_select(0, idx).cpu().numpy()
+            rows = o._down(o.theta.index_select(0, idx))
         return rows[0] if scalar else rows
 
 
@@ -108,6 +110,10 @@ class DeviceCRP:
         self._shared = {}            # device -> _Shared, shared between deep copies
         self._dev_ready = False
         self.sweep_stats = {}
+        self.profile = False
+        self._events = []
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
 
     def __str__(self):
         return ('\nDPMM with:\n'
@@ -125,6 +131,7 @@ class DeviceCRP:
         new = self.__class__.__new__(self.__class__)
         new.__dict__.update(self.__dict__)
         new.sweep_stats = {}
+        new._events = []
         return new
 
     # ------------------------------------------------------------------ plumbing
@@ -139,7 +146,41 @@ class DeviceCRP:
         return t
 
     def _up(self, arr, dtype):
-        return torch.as_tensor(np.ascontiguousarray(arr), dtype=dtype, device=self.device)
+        t = torch.as_tensor(np.ascontiguousarray(arr), dtype=dtype, device=self.device)
+        self.h2d_bytes += t.numel() * t.element_size()
+        return t
+
+    def _down(self, t):
+        """device -> host read (synchronises this chain's stream)"""
+        self.d2h_bytes += t.numel() * t.element_size()
+        return t.cpu().numpy()
+
+    class _Timed:
+        """CUDA-event bracket around one launch on the chain's stream (bench.py roofline)."""
+
+        def __init__(self, owner, name):
+            self.o, self.name = owner, name
+
+        def __enter__(self):
+            if self.o.profile:
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.b = torch.cuda.Event(enable_timing=True)
+                self.a.record(self.o.stream)
+
+        def __exit__(self, *exc):
+            if self.o.profile:
+                self.b.record(self.o.stream)
+                self.o._events.append((self.name, self.a, self.b))
+            return False
+
+    def kernel_times_ms(self):
+        """name -> list of durations of the bracketed launches since the last call."""
+        self.stream.synchronize()
+        out = {}
+        for name, a, b in self._events:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        self._events = []
+        return out
 
     def _setup_device(self):
         if not torch.cuda.is_available():
@@ -155,8 +196,9 @@ class DeviceCRP:
         self.rnd.bind(self.device)
         with torch.cuda.stream(self.stream):
             key = str(self.device)
-            if key not in self._shared:
-                self._shared[key] = _Shared(self.data, self.device)
+            with _PACK_LOCK:
+                if key not in self._shared:
+                    self._shared[key] = _Shared(self.data, self.device)
             self.sh = self._shared[key]
             self._bufs = {}
             N = self.cells_total
@@ -202,7 +244,12 @@ class DeviceCRP:
     @property
     def assignment(self):
         with torch.cuda.stream(self.stream):
-            return self.assign_d.cpu().numpy().astype(np.int64)
+            return self._down(self.assign_d).astype(np.int64)
+
+    def copy_assignment_to(self, row):
+        """device-side trace: row (int32 [N] device tensor) <- current assignment."""
+        with torch.cuda.stream(self.stream):
+            row.copy_(self.assign_d, non_blocking=True)
 
     @property
     def parameters(self):
@@ -292,7 +339,7 @@ class DeviceCRP:
                           fn_a, fp_a, E, float(self.p), float(self.q), out.data_ptr(), pr_ptr, sp)
         rows = E + (1 if want_prior else 0)
         self.L.row_sum(out.data_ptr(), rows, R, tot.data_ptr(), sp)
-        return tot[:rows].cpu().numpy()
+        return self._down(tot[:rows])
 
     def _trace_scalars(self):
         if self._trace_cache is None:
@@ -362,9 +409,10 @@ class DeviceCRP:
                 scratch = self._buf('scratch', self.idcap + 1, torch.float64)
                 L.logprob_tables(self.theta.data_ptr(), self.lst.data_ptr(), K, M, FN, FP, lp.data_ptr(), sp)
                 # cell indices are read straight out of the visit records (int32 #4 of 8)
-                L.ll_matrix(sh.x1.data_ptr(), sh.x0.data_ptr(), sh.W, M,
-                            self.visit.data_ptr() + t * _lib.VISIT_BYTES + 16, 8, rows,
-                            lp.data_ptr(), K, ll.data_ptr(), ldk, sp)
+                with self._Timed(self, 'll_matrix'):
+                    L.ll_matrix(sh.x1.data_ptr(), sh.x0.data_ptr(), sh.W, M,
+                                self.visit.data_ptr() + t * _lib.VISIT_BYTES + 16, 8, rows,
+                                lp.data_ptr(), K, ll.data_ptr(), ldk, sp)
                 a = _lib.SweepArgs(
                     x1=sh.x1.data_ptr(), x0=sh.x0.data_ptr(), W=sh.W, N=N, M=M,
                     assign=self.assign_d.data_ptr(), cnt=self.cnt.data_ptr(), lst=self.lst.data_ptr(),
@@ -377,13 +425,14 @@ class DeviceCRP:
                     n_beta_rows=n_tape, seed=seed, stream_id=stream_id,
                     logn=sh.logn.data_ptr(), c_norm=c_norm, FN=FN, FP=FP,
                     p=float(self.p), q=float(self.q))
-                L.gibbs_sweep(C.byref(a), 1024, sp)
-                st = self.st.cpu().numpy()                     # synchronises the stream
+                with self._Timed(self, 'gibbs_sweep'):
+                    L.gibbs_sweep(C.byref(a), 1024, sp)
+                st = self._down(self.st)                       # synchronises the stream
                 flags = int(st[_lib.ST_FLAGS])
                 if flags & (_lib.STOP_TAPE_EMPTY | _lib.STOP_HANG):
                     raise RuntimeError(f'gibbs_sweep stopped with flags {flags:#x} at t={st[_lib.ST_TDONE]}')
                 K = int(st[_lib.ST_K])
-                pairs = self.live_io[:2 * K].cpu().numpy()
+                pairs = self._down(self.live_io[:2 * K])
                 self.cells_per_cluster = OrderedDict(
                     (int(pairs[2 * j]), int(pairs[2 * j + 1])) for j in range(K))
                 t_new = int(st[_lib.ST_TDONE])
@@ -619,7 +668,7 @@ class DeviceCRP:
         self.L.row_loglik(self.rg_theta.data_ptr(), None, 3, self.muts_total, self.rg_S1.data_ptr(),
                           self.rg_S0.data_ptr(), fn, fp, 1, float(self.p), float(self.q),
                           out.data_ptr(), None, self._sp())
-        return out[:3].cpu().numpy()
+        return self._down(out[:3])
 
     def _decide_split(self, n, size_term, cl_i):
         """libs/CRP.py:641-653 with :668-682, :695-733, :757-764."""

@@ -34,8 +34,10 @@ def pack(L, data):
     x0 = torch.zeros((N, W), dtype=torch.int32, device='cuda')
     n1 = torch.zeros(N, dtype=torch.int32, device='cuda')
     n0 = torch.zeros(N, dtype=torch.int32, device='cuda')
-    L.pack_planes(None, dev(code, torch.int8).data_ptr(), N, M, W, x1.data_ptr(), x0.data_ptr(),
+    code_d = dev(code, torch.int8)
+    L.pack_planes(None, code_d.data_ptr(), N, M, W, x1.data_ptr(), x0.data_ptr(),
                   n1.data_ptr(), n0.data_ptr(), sp())
+    torch.cuda.synchronize()
     return W, x1, x0, n1, n0
 
 
@@ -62,7 +64,8 @@ def test_pack_planes(L, shape):
     N, M = shape
     y1 = torch.zeros_like(x1)
     y0 = torch.zeros_like(x0)
-    L.pack_planes(dev(data, torch.float64).data_ptr(), None, N, M, W, y1.data_ptr(), y0.data_ptr(),
+    data_d = dev(data, torch.float64)
+    L.pack_planes(data_d.data_ptr(), None, N, M, W, y1.data_ptr(), y0.data_ptr(),
                   n1.data_ptr(), n0.data_ptr(), sp())
     assert torch.equal(x1, y1) and torch.equal(x0, y0)
 
@@ -104,8 +107,8 @@ def test_ll_matrix_matches_reference_arithmetic(L, shape, K):
     ids = rng.permutation(K + 3)[:K].astype(np.int32)
     W, x1, x0, _, _ = pack(L, data)
     lp = torch.empty(K * M * 2, dtype=torch.float64, device='cuda')
-    L.logprob_tables(dev(theta, torch.float32).data_ptr(), dev(ids, torch.int32).data_ptr(), K, M,
-                     0.17, 0.013, lp.data_ptr(), sp())
+    theta_d, ids_d = dev(theta, torch.float32), dev(ids, torch.int32)
+    L.logprob_tables(theta_d.data_ptr(), ids_d.data_ptr(), K, M, 0.17, 0.013, lp.data_ptr(), sp())
     th = theta[ids]
     t64 = th.astype(np.float64)
     omt = (np.float32(1) - th).astype(np.float64)
@@ -117,7 +120,8 @@ def test_ll_matrix_matches_reference_arithmetic(L, shape, K):
     cells = rng.permutation(N).astype(np.int32)
     ldk = K + (K & 1)
     ll = torch.zeros(N * ldk, dtype=torch.float64, device='cuda')
-    L.ll_matrix(x1.data_ptr(), x0.data_ptr(), W, M, dev(cells, torch.int32).data_ptr(), 1, N,
+    cells_d = dev(cells, torch.int32)
+    L.ll_matrix(x1.data_ptr(), x0.data_ptr(), W, M, cells_d.data_ptr(), 1, N,
                 lp.data_ptr(), K, ll.data_ptr(), ldk, sp())
     got = ll.cpu().numpy().reshape(N, ldk)[:, :K]
     want = np.stack([orc.loglik(data[cells], th[k]) for k in range(K)], axis=1)
@@ -183,8 +187,8 @@ def test_mh_theta_matches_scipy_path(L, pp, want_logq):
     th_d = dev(theta, torch.float32)
     logq = torch.zeros(rows * M, dtype=torch.float64, device='cuda')
     dec = torch.zeros(rows, dtype=torch.int32, device='cuda')
-    L.mh_theta(th_d.data_ptr(), None, rows, M, dev(S1, torch.int32).data_ptr(),
-               dev(S0, torch.int32).data_ptr(), dev(draws, torch.float64).data_ptr(), 0.2, 0.01,
+    S1_d, S0_d, draws_d = dev(S1, torch.int32), dev(S0, torch.int32), dev(draws, torch.float64)
+    L.mh_theta(th_d.data_ptr(), None, rows, M, S1_d.data_ptr(), S0_d.data_ptr(), draws_d.data_ptr(), 0.2, 0.01,
                float(pp[0]), float(pp[1]), 1 if want_logq else 0,
                logq.data_ptr() if want_logq else None, dec.data_ptr(), sp())
     got = th_d.cpu().numpy()
