@@ -324,7 +324,7 @@ def run_gpu(args, cfg):
     e2e = total_chains * K / (ms_e2e / 1e3)
     peak, peak_src = measured_peaks()
     # roofline of the dominant kernel among the bracketed launches
-    ldk = max(2, k_live + (k_live & 1))
+    ldk = max(3, k_live | 1)
     alg_bytes = {
         'll_matrix': N * M / 4 + 16.0 * k_live * M + 8.0 * N * k_live,
         'gibbs_sweep': N * (8.0 * ldk + 32.0) + 8.0 * N,

@@ -9,4 +9,10 @@ The drop-in module paths of the reference (`libs.CRP.CRP`,
 `libs.CRP_learning_errors.CRP_errors_learning`, `libs.MCMC.MCMC`) live in the top-level
 `libs/` package and delegate here.
 """
+import os as _os
+
+# chains run concurrently on one stream each; with the default 8 hardware queues short kernels
+# of one chain would queue behind another chain's long sweep (must be set before CUDA starts)
+_os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
 __version__ = '0.1.0'

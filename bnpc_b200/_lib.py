@@ -88,7 +88,7 @@ SIGNATURES = {
     'bnpc_anchor_swaps': [_P, _I, _I, _I, _I, _I, _P],
     'bnpc_rg_launch_halves': [_P, _P, _I, _P, _I, C.POINTER(_D), _P, _P],
     'bnpc_rg_sides': [_P, _I, _P, _P, _P, _P],
-    'bnpc_rg_scan': [_P, _I, _I, _P, _P, _P, _D, _I, _P, _P, _I, _P, _P],
+    'bnpc_rg_scan': [_P, _I, _I, _P, _P, _P, _D, _I, _P, _P, _I, _P, _P, _P],
     'bnpc_apply_split': [_P, _I, _P, _I, _P, _P],
     'bnpc_apply_merge': [_P, _I, _I, _I, _P, _P],
 }
@@ -98,7 +98,7 @@ _lib = None
 launch_count = 0          # kernels launched through this binding (bench.py reports it)
 
 # kernels launched per entry point (memset nodes are not counted)
-_KERNELS_PER_CALL = {'bnpc_gather_members': 3, 'bnpc_rg_sides': 2}
+_KERNELS_PER_CALL = {'bnpc_gather_members': 3, 'bnpc_rg_sides': 2, 'bnpc_rg_scan': 3}
 
 
 class _Lib:

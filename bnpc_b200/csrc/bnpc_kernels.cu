@@ -300,9 +300,9 @@ __global__ void gibbs_prepare_kernel(const int32_t* __restrict__ perm, const dou
     v.u = u[t];
     // popcount form of libs/CRP.py:230-234: every observed 1 contributes c1, every 0 c0
     v.lnew = ((double)n1[c] * c1 + (double)n0[c] * c0) + lnew_prior;
+    v.logit = log1p(-v.u) - log(v.u);
     v.cell = c;
     v.old = assign[c];
-    v.pad[0] = v.pad[1] = 0;
     visit[t] = v;
 }
 
@@ -359,13 +359,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 #define SW_STAGE_CELLS 32
 #define SW_NSTAGE 4
-#define SW_MAXCOL 32
+#define SW_MAXCOL 33          /* odd row stride: lanes reading different rows hit different banks */
 
 struct SweepShared {
     alignas(128) double ll_stage[SW_NSTAGE][SW_STAGE_CELLS * SW_MAXCOL];
     alignas(128) bnpc_visit_t vis_stage[SW_NSTAGE][SW_STAGE_CELLS];
     alignas(8) uint64_t bar[SW_NSTAGE];
     double red[40];
+    // the live list while it fits a warp: position j <-> insertion order
+    double s_lc[32], s_lcm1[32];          // log CRP weight at the current size / at size-1
+    int s_id[32], s_cnt[32], s_src[32];   // cluster id, size, ll column (>=0) or -(extra+2)
     int L, t, pending, stop;
     int birth_cell, birth_t;
     int n_extra, births, moved, slow;
@@ -391,6 +394,89 @@ __device__ __forceinline__ int warp_categorical(double l, int L, double u, int l
     return gt ? (__ffs(gt) - 1) : L;
 }
 
+// Exact treatment of one cell by the whole warp, lanes <-> clusters (libs/CRP.py:262-288).
+// Returns 0: the cell stayed, 1: list/sizes changed, 2: it opens a new cluster (CTA-wide work).
+__device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, const bnpc_visit_t& v,
+                                const double* row, int t, int& L) {
+    const int lane = threadIdx.x;
+    int id = -1, cnt = 0, src = -1;
+    double lc = 0.0, lcm1 = 0.0;
+    if (lane < L) {
+        id = sh.s_id[lane]; cnt = sh.s_cnt[lane]; src = sh.s_src[lane];
+        lc = sh.s_lc[lane]; lcm1 = sh.s_lcm1[lane];
+    }
+    const int old = v.old;
+    const unsigned om = __ballot_sync(FULL, lane < L && id == old);
+    int lo = __ffs(om) - 1;
+    const int ocnt = __shfl_sync(FULL, cnt, lo < 0 ? 0 : lo);
+    bool died = false;
+    if (lo >= 0 && ocnt == 1) {
+        // the cluster dies with its last cell: close the gap, list order stays insertion order
+        const int id2 = __shfl_down_sync(FULL, id, 1), cnt2 = __shfl_down_sync(FULL, cnt, 1),
+                  src2 = __shfl_down_sync(FULL, src, 1);
+        const double lc2 = __shfl_down_sync(FULL, lc, 1), lcm2 = __shfl_down_sync(FULL, lcm1, 1);
+        if (lane == lo) a.cnt[old] = 0;
+        if (lane >= lo && lane < L - 1) {
+            id = id2; cnt = cnt2; src = src2; lc = lc2; lcm1 = lcm2;
+            a.lst[lane] = id;
+        } else if (lane == L - 1) {
+            id = -1; cnt = 0; src = -1;
+        }
+        --L;
+        died = true;
+        lo = -1;
+        __syncwarp();
+        if (lane <= L) {
+            sh.s_id[lane] = id; sh.s_cnt[lane] = cnt; sh.s_src[lane] = src;
+            sh.s_lc[lane] = lc; sh.s_lcm1[lane] = lcm1;
+        }
+        __syncwarp();
+    }
+    double l = -BNPC_INF;
+    if (lane < L) {
+        const double val = (src >= 0) ? row[src] : a.llx[(long long)(-src - 2) * a.ldx + (t - a.t_epoch0)];
+        l = val + ((lane == lo) ? lcm1 : lc);
+    } else if (lane == L) {
+        l = v.lnew;
+    }
+    const int pick = warp_categorical(l, L, v.u, lane);
+    if (pick == lo) return 0;
+    if (lo >= 0 && lane == lo) {                    // leave the old cluster
+        --cnt;
+        lc = a.logn[cnt] - a.c_norm;
+        lcm1 = a.logn[cnt - 1] - a.c_norm;
+        a.cnt[id] = cnt;
+        sh.s_cnt[lane] = cnt; sh.s_lc[lane] = lc; sh.s_lcm1[lane] = lcm1;
+    }
+    if (pick == L) {
+        if (lane == 0) { sh.pending = 1; sh.birth_cell = v.cell; sh.birth_t = t; }
+        __syncwarp();
+        return 2;
+    }
+    if (lane == pick) {
+        ++cnt;
+        lc = a.logn[cnt] - a.c_norm;
+        lcm1 = a.logn[cnt - 1] - a.c_norm;
+        a.cnt[id] = cnt;
+        a.assign[v.cell] = id;
+        sh.s_cnt[lane] = cnt; sh.s_lc[lane] = lc; sh.s_lcm1[lane] = lcm1;
+    }
+    __syncwarp();
+    return 1;
+}
+
+#define OUT_STAY 0
+#define OUT_MOVE 1
+#define OUT_COMPLEX 2
+
+// Warp regime (list of at most 31 clusters).  The sweep is sequential, but a cell that ends
+// up where it was leaves every size unchanged, so 32 consecutive cells are scored in parallel
+// (lane <-> cell) against the current sizes; everything before the first cell that does not
+// provably stay is then exact, that cell is resolved, and only the cells after it are scored
+// again.  A cell provably stays when all rivals sit 40 nats below its own cluster (they are all
+// on the reference's 1e-15 floor) and u is away from 0 and 1; with a single rival the draw is a
+// two-way draw decided by comparing log-odds with logit(u), with a 1e-3 guard band; anything
+// else goes through the exact warp-cooperative draw.
 __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
     const int lane = threadIdx.x;
     int L = sh.L;
@@ -398,17 +484,13 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
     const int ldk = a.ldk;
     int moved = 0, slow = 0;
 
-    // the live list lives in registers: lane j <-> list position j
-    int id = -1, cnt = 0, src = -1;
-    double lc = 0.0, lcm1 = 0.0;
     if (lane < L) {
-        id = a.lst[lane];
-        cnt = a.cnt[id];
-        src = a.col_of_id[id];
-        lc = a.logn[cnt] - a.c_norm;
-        lcm1 = a.logn[cnt - 1] - a.c_norm;
+        const int id = a.lst[lane];
+        const int c = a.cnt[id];
+        sh.s_id[lane] = id; sh.s_cnt[lane] = c; sh.s_src[lane] = a.col_of_id[id];
+        sh.s_lc[lane] = a.logn[c] - a.c_norm;
+        sh.s_lcm1[lane] = a.logn[c - 1] - a.c_norm;
     }
-
     if (lane == 0) {
         for (int s = 0; s < SW_NSTAGE; ++s) mbar_init(&sh.bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -416,15 +498,20 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
     }
     __syncwarp();
 
-    const int n_stages = (a.t_end - t0 + SW_STAGE_CELLS - 1) / SW_STAGE_CELLS;
+    // stages cover 32 consecutive sweep positions, aligned to the epoch start so that every
+    // bulk copy starts on a 256-byte boundary of the ll matrix
+    const int s_first = (t0 - a.t_epoch0) / SW_STAGE_CELLS;
+    const int s_last = (a.t_end - 1 - a.t_epoch0) / SW_STAGE_CELLS;
+    const int n_stages = s_last - s_first + 1;
     auto issue = [&](int g) {                      // lane 0 only
         const int slot = g % SW_NSTAGE;
-        const int ts = t0 + g * SW_STAGE_CELLS;
-        const int nc = min(SW_STAGE_CELLS, a.t_end - ts);
-        const uint32_t b_ll = (uint32_t)(nc * ldk * 8), b_v = (uint32_t)(nc * sizeof(bnpc_visit_t));
+        const int sp = (s_first + g) * SW_STAGE_CELLS;            // position relative to the epoch
+        const int nc = min(SW_STAGE_CELLS, a.t_end - a.t_epoch0 - sp);
+        const uint32_t b_ll = ((uint32_t)(nc * ldk * 8) + 15u) & ~15u;
+        const uint32_t b_v = (uint32_t)(nc * sizeof(bnpc_visit_t));
         mbar_expect_tx(&sh.bar[slot], b_ll + b_v);
-        bulk_g2s(sh.ll_stage[slot], a.ll + (long long)(ts - a.t_epoch0) * ldk, b_ll, &sh.bar[slot]);
-        bulk_g2s(sh.vis_stage[slot], a.visit + ts, b_v, &sh.bar[slot]);
+        bulk_g2s(sh.ll_stage[slot], a.ll + (long long)sp * ldk, b_ll, &sh.bar[slot]);
+        bulk_g2s(sh.vis_stage[slot], a.visit + a.t_epoch0 + sp, b_v, &sh.bar[slot]);
     };
     int issued = 0;
     if (lane == 0)
@@ -444,86 +531,94 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
             }
         }
         waited = g + 1;
-        const int ts = t0 + g * SW_STAGE_CELLS;
+        const int ts = a.t_epoch0 + (s_first + g) * SW_STAGE_CELLS;
         const int nc = min(SW_STAGE_CELLS, a.t_end - ts);
         const double* rows = sh.ll_stage[slot];
-        for (int i = 0; i < nc; ++i) {
-            const int t = ts + i;
-            const bnpc_visit_t v = sh.vis_stage[slot][i];
-            const int old = v.old;
+        const bnpc_visit_t* vis = sh.vis_stage[slot];
+        const bnpc_visit_t v = vis[lane < nc ? lane : 0];
+        const double* row = rows + (lane < nc ? lane : 0) * ldk;
+        const int tx = ts + lane - a.t_epoch0;
 
-            // take the cell out of its cluster (libs/CRP.py:262-266)
-            const unsigned om = __ballot_sync(FULL, lane < L && id == old);
-            int lo = __ffs(om) - 1;
-            const int ocnt = __shfl_sync(FULL, cnt, lo < 0 ? 0 : lo);
-            bool died = false;
-            if (lo >= 0 && ocnt == 1) {
-                // cluster dies: close the gap so list order stays insertion order
-                const int id2 = __shfl_down_sync(FULL, id, 1), cnt2 = __shfl_down_sync(FULL, cnt, 1),
-                          src2 = __shfl_down_sync(FULL, src, 1);
-                const double lc2 = __shfl_down_sync(FULL, lc, 1), lcm2 = __shfl_down_sync(FULL, lcm1, 1);
-                if (lane == lo) a.cnt[old] = 0;
-                if (lane >= lo && lane < L - 1) {
-                    id = id2; cnt = cnt2; src = src2; lc = lc2; lcm1 = lcm2;
-                    a.lst[lane] = id;
-                } else if (lane == L - 1) {
-                    id = -1; cnt = 0; src = -1;
+        int lo_lane = max(0, t0 - ts);
+        bool need_eval = true;
+        int outcome = OUT_STAY, k_old = -1, r1 = -1;
+        while (lo_lane < nc) {
+            if (need_eval) {
+                outcome = OUT_STAY;
+                if (lane >= lo_lane && lane < nc) {
+                    double l_old = -BNPC_INF, m1 = -BNPC_INF, m2 = -BNPC_INF;
+                    k_old = -1; r1 = -1;
+                    for (int k = 0; k < L; ++k) {
+                        const int src = sh.s_src[k];
+                        const double val = (src >= 0) ? row[src]
+                                                      : a.llx[(long long)(-src - 2) * a.ldx + tx];
+                        if (sh.s_id[k] == v.old) {
+                            l_old = val + sh.s_lcm1[k];
+                            k_old = k;
+                        } else {
+                            const double l = val + sh.s_lc[k];
+                            if (l > m1) { m2 = m1; m1 = l; r1 = k; }
+                            else if (l > m2) m2 = l;
+                        }
+                    }
+                    {
+                        const double l = v.lnew;
+                        if (l > m1) { m2 = m1; m1 = l; r1 = L; }
+                        else if (l > m2) m2 = l;
+                    }
+                    const double cut = l_old - 40.0;
+                    if (k_old < 0 || sh.s_cnt[k_old] == 1) {
+                        outcome = OUT_COMPLEX;
+                    } else if (!(m1 > cut)) {
+                        outcome = (v.u > 1e-12 && v.u < 1.0 - 1e-12) ? OUT_STAY : OUT_COMPLEX;
+                    } else if (!(m2 > cut) && r1 != L && v.u > 1e-9 && v.u < 1.0 - 1e-9) {
+                        // log-odds of the later list position over the earlier one
+                        const double d_ab = (r1 > k_old) ? (m1 - l_old) : (l_old - m1);
+                        if (fabs(d_ab - v.logit) > 1e-3) {
+                            const int pick = (d_ab < v.logit) ? min(k_old, r1) : max(k_old, r1);
+                            outcome = (pick == k_old) ? OUT_STAY : OUT_MOVE;
+                        } else {
+                            outcome = OUT_COMPLEX;
+                        }
+                    } else {
+                        outcome = OUT_COMPLEX;
+                    }
                 }
-                --L;
-                died = true;
-                lo = -1;
             }
-
-            double l = -BNPC_INF;
-            if (lane < L) {
-                const double val = (src >= 0) ? rows[i * ldk + src]
-                                              : a.llx[(long long)(-src - 2) * a.ldx + (t - a.t_epoch0)];
-                l = val + ((lane == lo) ? lcm1 : lc);
-            } else if (lane == L) {
-                l = v.lnew;
-            }
-
-            int pick;
-            bool fast = false;
-            if (!died && lo >= 0) {
-                // every rival at least 40 nats below the current cluster => all rivals sit on
-                // the 1e-15 floor and the draw returns the current cluster unless u is within
-                // 32e-15 of 0 or 1: skip the transcendental path, result is identical.
-                const double lold = __shfl_sync(FULL, l, lo);
-                const bool rival = (lane <= L) && (lane != lo) && (l > lold - 40.0);
-                if (!__any_sync(FULL, rival) && v.u > 1e-12 && v.u < 1.0 - 1e-12) {
-                    fast = true;
-                    pick = lo;
-                }
-            }
-            if (!fast) {
-                ++slow;
-                pick = warp_categorical(l, L, v.u, lane);
-            }
-            if (pick == lo) continue;               // stays where it was
-
-            ++moved;
-            if (lo >= 0 && lane == lo) {            // leave the old cluster
-                --cnt;
-                lc = a.logn[cnt] - a.c_norm;
-                lcm1 = a.logn[cnt - 1] - a.c_norm;
-                a.cnt[id] = cnt;
-            }
-            if (pick == L) {                        // open a new cluster: CTA-wide work
+            const unsigned pend = __ballot_sync(FULL, lane >= lo_lane && lane < nc && outcome != OUT_STAY);
+            if (!pend) break;
+            const int f = __ffs(pend) - 1;
+            const int of = __shfl_sync(FULL, outcome, f);
+            int status;
+            if (of == OUT_MOVE) {
+                const int kf = __shfl_sync(FULL, k_old, f), rf = __shfl_sync(FULL, r1, f);
                 if (lane == 0) {
-                    sh.pending = 1; sh.birth_cell = v.cell; sh.birth_t = t;
+                    const int c_old = sh.s_cnt[kf] - 1, c_new = sh.s_cnt[rf] + 1;
+                    sh.s_cnt[kf] = c_old;
+                    sh.s_lc[kf] = a.logn[c_old] - a.c_norm;
+                    sh.s_lcm1[kf] = a.logn[c_old - 1] - a.c_norm;
+                    a.cnt[sh.s_id[kf]] = c_old;
+                    sh.s_cnt[rf] = c_new;
+                    sh.s_lc[rf] = a.logn[c_new] - a.c_norm;
+                    sh.s_lcm1[rf] = a.logn[c_new - 1] - a.c_norm;
+                    a.cnt[sh.s_id[rf]] = c_new;
+                    a.assign[vis[f].cell] = sh.s_id[rf];
                 }
-                next_t = t + 1;
-                leave = true;
-                break;
+                __syncwarp();
+                ++moved;
+                status = 1;
+            } else {
+                ++slow;
+                status = sweep_exact_cell(a, sh, vis[f], rows + f * ldk, ts + f, L);
+                if (status) ++moved;
+                if (status == 2) {
+                    next_t = ts + f + 1;
+                    leave = true;
+                    break;
+                }
             }
-            if (lane == pick) {
-                ++cnt;
-                lc = a.logn[cnt] - a.c_norm;
-                lcm1 = a.logn[cnt - 1] - a.c_norm;
-                a.cnt[id] = cnt;
-                a.assign[v.cell] = id;
-            }
+            lo_lane = f + 1;
+            need_eval = (status != 0);
         }
         __syncwarp();
         if (!leave && lane == 0 && issued < n_stages) issue(issued);
@@ -1092,71 +1187,126 @@ __global__ void rg_sides_kernel(const int32_t* __restrict__ cells, int n, const 
     if (s == 0) { seg_off[0] = 0; seg_off[1] = n_i; seg_off[2] = n; }
 }
 
-// restricted Gibbs scan, one warp (libs/CRP.py:609-632 / :806-818).  The scan is a strictly
-// sequential 2-way draw per free cell; lanes prefetch 32 steps of inputs at a time and the
-// serial arithmetic is replicated across lanes.
-__global__ void __launch_bounds__(32)
-rg_scan_kernel(const double* __restrict__ ll2, int ldk, int n, const int32_t* __restrict__ perm,
-               const double* __restrict__ u, int32_t* half, double alpha, int mode,
-               const int32_t* __restrict__ cells, const int32_t* __restrict__ assign, int id_i,
-               double* __restrict__ lq) {
-    const int lane = threadIdx.x;
+// ---- restricted Gibbs scan (libs/CRP.py:609-632 / :806-818) -------------------------------
+// The two-way draw of a free cell depends on the scan history only through n_j, the current size
+// of side j, and the probability of side j grows with n_j.  So for a given uniform the draw is
+// "side j iff n_j - 1 >= tau" for an integer threshold tau that can be found for all cells IN
+// PARALLEL (closed form, then corrected with the reference's own arithmetic, rg_side below).
+// The sequential part of the scan is then integer-only: ex = ones - own; side = ex >= tau.
+__device__ __forceinline__ void rg_pair_logprob(double a0, double a1, int n_i, int n_j, double cn,
+                                                double& lp0, double& lp1) {
+    // libs/CRP.py:622-623 with _normalize_log (libs/CRP.py:103-116)
+    const double p0 = a0 + (log((double)n_i) - cn);
+    const double p1 = a1 + (log((double)n_j) - cn);
+    const int top = (p1 > p0) ? 1 : 0;
+    const double other = (top ? p0 : p1) - (top ? p1 : p0);
+    const double lse = log1p(exp(other));
+    const double lpt = 0.0 - lse, lpo = other - lse;
+    lp0 = top ? lpo : lpt;
+    lp1 = top ? lpt : lpo;
+}
+__device__ __forceinline__ int rg_side(double a0, double a1, int ex, int n, double cn, double u) {
+    // np.random.choice([0,1], p=exp(log_probs)) with `ex` other free cells on side j
+    const int n_j = ex + 1, n_i = n - n_j - 1;
+    double lp0, lp1;
+    rg_pair_logprob(a0, a1, n_i, n_j, cn, lp0, lp1);
+    const double e0 = exp(lp0), e1 = exp(lp1);
+    return (u < e0 / (e0 + e1)) ? 0 : 1;
+}
+
+#define RG_FORCE_1 0
+#define RG_FORCE_0 (1 << 29)
+
+__global__ void rg_prepare_kernel(const double* __restrict__ ll2, int ldk, int n,
+                                  const int32_t* __restrict__ perm, const double* __restrict__ u,
+                                  const int32_t* __restrict__ half, double alpha, int mode,
+                                  const int32_t* __restrict__ cells, const int32_t* __restrict__ assign,
+                                  int id_i, int32_t* __restrict__ work) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int nf = n - 2;
+    if (s >= nf) return;
+    const int c = (mode == 0) ? perm[s] : s;
+    int tau;
+    if (mode != 0) {
+        tau = (assign[cells[c + 1]] == id_i) ? RG_FORCE_0 : RG_FORCE_1;
+    } else {
+        const double a0 = ll2[(long long)c * ldk], a1 = ll2[(long long)c * ldk + 1];
+        const double uu = u[s];
+        const double cn = log((double)n - 1.0 + alpha);
+        // side j iff n_j/(n-1) >= sigmoid(logit(1-u) - (a1-a0)); n_j = ex + 1
+        const double x = (log1p(-uu) - log(uu)) - (a1 - a0);
+        double guess = ceil(((double)n - 1.0) / (1.0 + exp(-x)) - 1.0);
+        if (!(guess >= 0.0)) guess = 0.0;
+        if (guess > (double)nf) guess = (double)nf;
+        tau = (int)guess;
+        for (int it = 0; it < 64 && tau > 0 && rg_side(a0, a1, tau - 1, n, cn, uu) == 1; ++it) --tau;
+        for (int it = 0; it < 64 && tau < nf && rg_side(a0, a1, tau, n, cn, uu) == 0; ++it) ++tau;
+    }
+    work[s] = tau * 2 + half[c];
+}
+
+#define RG_CHUNK 1024
+// the sequential integer pass: one thread, inputs streamed through shared memory by bulk copies
+__global__ void __launch_bounds__(32)
+rg_serial_kernel(const int32_t* __restrict__ half, int nf, int32_t* __restrict__ work, int out_off) {
+    __shared__ alignas(128) int32_t buf[2][RG_CHUNK];
+    __shared__ alignas(8) uint64_t bar[2];
+    const int lane = threadIdx.x;
     int ones = 0;
     for (int s = lane; s < nf; s += 32) ones += half[s];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ones += __shfl_xor_sync(FULL, ones, o);
-    const double cn = log((double)n - 1.0 + alpha);
-    for (int base = 0; base < nf; base += 32) {
-        const int step = base + lane;
-        int c = 0, hc = 0, forced = 0;
-        double l0 = 0.0, l1 = 0.0, uu = 0.5;
-        if (step < nf) {
-            c = (mode == 0) ? perm[step] : step;
-            l0 = ll2[(long long)c * ldk];
-            l1 = ll2[(long long)c * ldk + 1];
-            hc = half[c];
-            if (mode == 0) uu = u[step];
-            else forced = (assign[cells[c + 1]] == id_i) ? 0 : 1;
+    if (lane != 0) return;
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int n_chunks = (nf + RG_CHUNK - 1) / RG_CHUNK;
+    auto issue = [&](int g) {
+        const int cnt = min(RG_CHUNK, nf - g * RG_CHUNK);
+        const uint32_t bytes = ((uint32_t)cnt * 4u + 15u) & ~15u;
+        mbar_expect_tx(&bar[g & 1], bytes);
+        bulk_g2s(buf[g & 1], work + (long long)g * RG_CHUNK, bytes, &bar[g & 1]);
+    };
+    if (n_chunks > 0) issue(0);
+    int32_t* out = work + out_off;
+    for (int g = 0; g < n_chunks; ++g) {
+        if (g + 1 < n_chunks) issue(g + 1);
+        long long spins = 0;
+        while (!mbar_try_wait(&bar[g & 1], (uint32_t)((g >> 1) & 1))) {
+            if (++spins > (1ll << 24)) return;
         }
-        const int cntb = min(32, nf - base);
-        for (int i = 0; i < cntb; ++i) {
-            const int ci = __shfl_sync(FULL, c, i), hci = __shfl_sync(FULL, hc, i);
-            const double a0 = __shfl_sync(FULL, l0, i), a1 = __shfl_sync(FULL, l1, i);
-            const double ui = __shfl_sync(FULL, uu, i);
-            const int fi = __shfl_sync(FULL, forced, i);
-            const int ones_ex = ones - hci;
-            const int n_j = ones_ex + 1, n_i = n - n_j - 1;
-            int side;
-            double lp_side = 0.0;
-            const double gap = a1 - a0;
-            if (mode == 0 && lq == nullptr && fabs(gap) > 60.0 && ui > 1e-12 && ui < 1.0 - 1e-12) {
-                // |log n_j - log n_i| < 21, so the loser's probability is < e^-39: the draw
-                // cannot land on it for u in (1e-12, 1-1e-12)
-                side = gap > 0.0 ? 1 : 0;
-            } else {
-                const double p0 = a0 + (log((double)n_i) - cn);
-                const double p1 = a1 + (log((double)n_j) - cn);
-                const int top = (p1 > p0) ? 1 : 0;
-                const double other = (top ? p0 : p1) - (top ? p1 : p0);
-                const double lse = log1p(exp(other));
-                const double lpt = 0.0 - lse, lpo = other - lse;
-                const double lp0 = top ? lpo : lpt, lp1 = top ? lpt : lpo;
-                if (mode == 0) {
-                    const double e0 = exp(lp0), e1 = exp(lp1);
-                    side = (ui < e0 / (e0 + e1)) ? 0 : 1;
-                } else {
-                    side = fi;
-                }
-                lp_side = side ? lp1 : lp0;
-            }
-            if (lane == 0) {
-                half[ci] = side;
-                if (lq) lq[ci] = lp_side;
-            }
-            ones = ones_ex + side;
+        const int cnt = min(RG_CHUNK, nf - g * RG_CHUNK);
+        const int32_t* b = buf[g & 1];
+        int32_t* o = out + (long long)g * RG_CHUNK;
+#pragma unroll 8
+        for (int i = 0; i < cnt; ++i) {
+            const int v = b[i];
+            const int ex = ones - (v & 1);
+            const int side = (ex >= (v >> 1)) ? 1 : 0;
+            ones = ex + side;
+            o[i] = ex * 2 + side;
         }
-        __syncwarp();
+    }
+}
+
+__global__ void rg_finish_kernel(const double* __restrict__ ll2, int ldk, int n,
+                                 const int32_t* __restrict__ perm, int32_t* __restrict__ half,
+                                 double alpha, int mode, const int32_t* __restrict__ work, int out_off,
+                                 double* __restrict__ lq) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nf = n - 2;
+    if (s >= nf) return;
+    const int c = (mode == 0) ? perm[s] : s;
+    const int o = work[out_off + s];
+    const int side = o & 1, ex = o >> 1;
+    half[c] = side;
+    if (lq) {
+        const double cn = log((double)n - 1.0 + alpha);
+        double lp0, lp1;
+        rg_pair_logprob(ll2[(long long)c * ldk], ll2[(long long)c * ldk + 1], n - (ex + 1) - 1, ex + 1, cn,
+                        lp0, lp1);
+        lq[c] = side ? lp1 : lp0;
     }
 }
 
@@ -1254,7 +1404,6 @@ int bnpc_gibbs_epoch_begin(const int32_t* live, int K, int32_t* lst, int32_t* cn
 int bnpc_gibbs_sweep(const bnpc_sweep_args_t* a, int block_threads, void* stream) {
     if (!a) return bad_arg("args");
     if (block_threads < 32 || block_threads > 1024 || block_threads % 32) return bad_arg("block_threads");
-    if (a->ldk % 2) return bad_arg("ldk must be even (16-byte rows)");
     if (a->t_begin < a->t_epoch0 || a->t_end - a->t_epoch0 > a->ldx) return bad_arg("sweep range vs ldx");
     gibbs_sweep_kernel<<<1, block_threads, 0, (cudaStream_t)stream>>>(*a);
     LAUNCH_CHECK("gibbs_sweep");
@@ -1414,13 +1563,21 @@ int bnpc_rg_sides(const int32_t* cells, int n, const int32_t* half, int32_t* mem
 
 int bnpc_rg_scan(const double* ll2, int ldk, int n, const int32_t* perm, const double* u, int32_t* half,
                  double alpha, int mode, const int32_t* cells, const int32_t* assign, int id_i,
-                 double* lq, void* stream) {
+                 double* lq, int32_t* work, void* stream) {
     if (n <= 2) return 0;
     if (mode == 0 && (!perm || !u)) return bad_arg("perm/u required for a sampled scan");
-    if (mode == 1 && (!cells || !assign || !lq)) return bad_arg("cells/assign/lq required for replay");
-    rg_scan_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ll2, ldk, n, perm, u, half, alpha, mode, cells, assign,
-                                                       id_i, lq);
-    LAUNCH_CHECK("rg_scan");
+    if (mode == 1 && (!cells || !assign)) return bad_arg("cells/assign required for replay");
+    if (!work) return bad_arg("work");
+    const int nf = n - 2;
+    const int out_off = (nf + 3) & ~3;
+    cudaStream_t st = (cudaStream_t)stream;
+    rg_prepare_kernel<<<cdiv(nf, 128), 128, 0, st>>>(ll2, ldk, n, perm, u, half, alpha, mode, cells, assign,
+                                                     id_i, work);
+    LAUNCH_CHECK("rg_prepare");
+    rg_serial_kernel<<<1, 32, 0, st>>>(half, nf, work, out_off);
+    LAUNCH_CHECK("rg_serial");
+    rg_finish_kernel<<<cdiv(nf, 128), 128, 0, st>>>(ll2, ldk, n, perm, half, alpha, mode, work, out_off, lq);
+    LAUNCH_CHECK("rg_finish");
     return 0;
 }
 

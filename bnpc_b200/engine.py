@@ -209,6 +209,7 @@ class DeviceCRP:
             self.half = torch.zeros(N + 8, dtype=torch.int32, device=self.device)
             self.gblk = torch.empty(2 * ((N + 1023) // 1024) + 2, dtype=torch.int32, device=self.device)
             self.seg3 = torch.zeros(8, dtype=torch.int32, device=self.device)
+            self.rg_work = torch.zeros(2 * N + 16, dtype=torch.int32, device=self.device)
             self.st = torch.zeros(_lib.ST_WORDS, dtype=torch.int32, device=self.device)
             self.rg_theta = torch.zeros((3, self.muts_total), dtype=torch.float32, device=self.device)
             self.rg_S1 = torch.zeros((3, self.muts_total), dtype=torch.int32, device=self.device)
@@ -400,18 +401,19 @@ class DeviceCRP:
                 self.live_io[:2 * K].copy_(self._up(live, torch.int32))
                 L.gibbs_epoch_begin(self.live_io.data_ptr(), K, self.lst.data_ptr(), self.cnt.data_ptr(),
                                     self.col_of_id.data_ptr(), self.idcap, self.st.data_ptr(), first, sp)
-                ldk = max(2, K + (K & 1))
+                # odd row stride (bank-conflict-free per-lane row reads in the warp regime)
+                ldk = max(3, K | 1)
                 rows = int(min(N - t, max(1, LL_BUDGET_BYTES // (8 * ldk))))
                 lp = self._buf('lp', 2 * K * M, torch.float64)
-                ll = self._buf('ll', rows * ldk, torch.float64)
+                ll = self._buf('ll', rows * ldk + 2, torch.float64)
                 lpx = self._buf('lpx', 2 * _lib.MAX_EXTRA * M, torch.float64)
                 llx = self._buf('llx', _lib.MAX_EXTRA * rows, torch.float64)
                 scratch = self._buf('scratch', self.idcap + 1, torch.float64)
                 L.logprob_tables(self.theta.data_ptr(), self.lst.data_ptr(), K, M, FN, FP, lp.data_ptr(), sp)
-                # cell indices are read straight out of the visit records (int32 #4 of 8)
+                # cell indices are read straight out of the visit records (int32 #6 of 8)
                 with self._Timed(self, 'll_matrix'):
                     L.ll_matrix(sh.x1.data_ptr(), sh.x0.data_ptr(), sh.W, M,
-                                self.visit.data_ptr() + t * _lib.VISIT_BYTES + 16, 8, rows,
+                                self.visit.data_ptr() + t * _lib.VISIT_BYTES + 24, 8, rows,
                                 lp.data_ptr(), K, ll.data_ptr(), ldk, sp)
                 a = _lib.SweepArgs(
                     x1=sh.x1.data_ptr(), x0=sh.x0.data_ptr(), W=sh.W, N=N, M=M,
@@ -604,7 +606,8 @@ class DeviceCRP:
             perm, u = self.rnd.scan_draws(nf)
             lq = self._buf('rg_lq', nf, torch.float64)
             L.rg_scan(ll2.data_ptr(), 2, n, perm.data_ptr(), u.data_ptr(), self.half.data_ptr(),
-                      float(self.DP_a), 0, None, None, -1, lq.data_ptr() if want_logq else None, sp)
+                      float(self.DP_a), 0, None, None, -1, lq.data_ptr() if want_logq else None,
+                      self.rg_work.data_ptr(), sp)
             if want_logq:
                 lq_assign = float(self._rg_sum_rows(lq, 1, nf)[0].item())
         self._rg_side_stats(n)
@@ -722,7 +725,8 @@ class DeviceCRP:
             ll2 = self._rg_pair_ll(orig, None, n)
             lq = self._buf('rg_lq', nf, torch.float64)
             L.rg_scan(ll2.data_ptr(), 2, n, None, None, self.half.data_ptr(), float(self.DP_a), 1,
-                      self.cells_d.data_ptr(), self.assign_d.data_ptr(), cl_i, lq.data_ptr(), sp)
+                      self.cells_d.data_ptr(), self.assign_d.data_ptr(), cl_i, lq.data_ptr(),
+                      self.rg_work.data_ptr(), sp)
             back += float(self._rg_sum_rows(lq, 1, nf)[0].item())
         logq_ratio = back - fwd
         # `half` now equals the original split (reference quirk)

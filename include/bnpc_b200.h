@@ -61,9 +61,10 @@ extern "C" {
 typedef struct {
     double  u;      /* uniform for the categorical draw (libs/CRP.py:277)             */
     double  lnew;   /* new-cluster log posterior of this cell (libs/CRP.py:230-234)   */
+    double  logit;  /* log((1-u)/u): a two-way draw picks the first option iff the
+                       log-odds of the second over the first are below this           */
     int32_t cell;   /* cell index = permutation[t] (libs/CRP.py:260)                  */
     int32_t old;    /* its cluster id before the sweep                                 */
-    int32_t pad[2];
 } bnpc_visit_t;
 
 int         bnpc_abi_version(void);
@@ -207,10 +208,13 @@ int bnpc_rg_sides(const int32_t* cells, int n, const int32_t* half,
  * (mode 0: sampled, order = perm, uniforms u) or the forced replay of
  * libs/CRP.py:806-818 (mode 1: side = (assign[cell] != id_i), natural order).
  * ll2 [n-2][ldk>=2] from bnpc_ll_matrix.  lq[c] = log-probability of the side
- * taken.  half is updated in place.                                               */
+ * taken (NULL: not wanted).  half is updated in place.  work is scratch of
+ * 2*(n-2)+8 int32.  Three launches: per-cell count thresholds in parallel (the
+ * two-way draw is monotone in the running side-j count), a serial integer
+ * pass, and a parallel write-back.                                                */
 int bnpc_rg_scan(const double* ll2, int ldk, int n, const int32_t* perm, const double* u,
                  int32_t* half, double alpha, int mode, const int32_t* cells,
-                 const int32_t* assign, int id_i, double* lq, void* stream);
+                 const int32_t* assign, int id_i, double* lq, int32_t* work, void* stream);
 /* accepted split (libs/CRP.py:471-474): assign[cell] = new_id for side-j cells;
  * accepted merge (libs/CRP.py:517): assign[cells[n_a..n)] = id.                   */
 int bnpc_apply_split(const int32_t* cells, int n, const int32_t* half, int new_id,
