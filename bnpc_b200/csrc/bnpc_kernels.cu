@@ -301,9 +301,41 @@ __global__ void gibbs_prepare_kernel(const int32_t* __restrict__ perm, const dou
     // popcount form of libs/CRP.py:230-234: every observed 1 contributes c1, every 0 c0
     v.lnew = ((double)n1[c] * c1 + (double)n0[c] * c0) + lnew_prior;
     v.logit = log1p(-v.u) - log(v.u);
+    v.v_old = 0.0; v.v1 = 0.0; v.v2 = 0.0;
     v.cell = c;
     v.old = assign[c];
+    v.cols = 3 << 24;                 // "unknown rivals" until bnpc_gibbs_candidates has run
+    v.pad = 0;
     visit[t] = v;
+}
+
+// static rival candidates of every visited cell (see include/bnpc_b200.h)
+__global__ void gibbs_candidates_kernel(const double* __restrict__ ll, int ldk, int K,
+                                        const int32_t* __restrict__ col_of_id,
+                                        bnpc_visit_t* __restrict__ visit, int C, double slack) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= C) return;
+    const double* row = ll + (long long)r * ldk;
+    const int c_old = col_of_id[visit[r].old];
+    int c1 = 0, c2 = 0, n = 3;
+    double v_old = 0.0, v1 = -BNPC_INF, v2 = -BNPC_INF;
+    if (c_old >= 0 && c_old < K) {
+        v_old = row[c_old];
+        const double thr = v_old - 40.0 - slack;
+        n = 0;
+        for (int k = 0; k < K; ++k) {
+            if (k == c_old) continue;
+            const double v = row[k];
+            if (v > thr) ++n;
+            if (v > v1) { v2 = v1; c2 = c1; v1 = v; c1 = k; }
+            else if (v > v2) { v2 = v; c2 = k; }
+        }
+        if (n > 3) n = 3;
+    }
+    visit[r].v_old = v_old;
+    visit[r].v1 = v1;
+    visit[r].v2 = v2;
+    visit[r].cols = (c_old & 255) | (c1 << 8) | (c2 << 16) | (n << 24);
 }
 
 __global__ void gibbs_epoch_begin_kernel(const int32_t* __restrict__ live, int K, int32_t* lst,
@@ -359,16 +391,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 #define SW_STAGE_CELLS 32
 #define SW_NSTAGE 4
-#define SW_MAXCOL 33          /* odd row stride: lanes reading different rows hit different banks */
+#define SW_MAXCOL 64          /* ll columns addressable from the packed candidate record */
 
 struct SweepShared {
-    alignas(128) double ll_stage[SW_NSTAGE][SW_STAGE_CELLS * SW_MAXCOL];
     alignas(128) bnpc_visit_t vis_stage[SW_NSTAGE][SW_STAGE_CELLS];
     alignas(8) uint64_t bar[SW_NSTAGE];
     double red[40];
     // the live list while it fits a warp: position j <-> insertion order
     double s_lc[32], s_lcm1[32];          // log CRP weight at the current size / at size-1
     int s_id[32], s_cnt[32], s_src[32];   // cluster id, size, ll column (>=0) or -(extra+2)
+    int s_pos_of_col[SW_MAXCOL];          // ll column -> list position, -1 once the cluster died
+    int s_xpos[BNPC_MAX_EXTRA];           // cluster born in this epoch -> list position or -1
     int L, t, pending, stop;
     int birth_cell, birth_t;
     int n_extra, births, moved, slow;
@@ -394,8 +427,23 @@ __device__ __forceinline__ int warp_categorical(double l, int L, double u, int l
     return gt ? (__ffs(gt) - 1) : L;
 }
 
+// column / extra -> list position maps, rebuilt after every structural change (rare)
+__device__ __forceinline__ void sweep_rebuild_maps(SweepShared& sh, int L) {
+    const int lane = threadIdx.x;
+    for (int c = lane; c < SW_MAXCOL; c += 32) sh.s_pos_of_col[c] = -1;
+    for (int e = lane; e < BNPC_MAX_EXTRA; e += 32) sh.s_xpos[e] = -1;
+    __syncwarp();
+    if (lane < L) {
+        const int src = sh.s_src[lane];
+        if (src >= 0) { if (src < SW_MAXCOL) sh.s_pos_of_col[src] = lane; }
+        else if (src <= -2) sh.s_xpos[-src - 2] = lane;
+    }
+    __syncwarp();
+}
+
 // Exact treatment of one cell by the whole warp, lanes <-> clusters (libs/CRP.py:262-288).
-// Returns 0: the cell stayed, 1: list/sizes changed, 2: it opens a new cluster (CTA-wide work).
+// `row` is the cell's ll row in GLOBAL memory.  Returns 0: the cell stayed, 1: list/sizes
+// changed, 2: it opens a new cluster (CTA-wide work, the caller leaves the warp regime).
 __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, const bnpc_visit_t& v,
                                 const double* row, int t, int& L) {
     const int lane = threadIdx.x;
@@ -409,7 +457,6 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
     const unsigned om = __ballot_sync(FULL, lane < L && id == old);
     int lo = __ffs(om) - 1;
     const int ocnt = __shfl_sync(FULL, cnt, lo < 0 ? 0 : lo);
-    bool died = false;
     if (lo >= 0 && ocnt == 1) {
         // the cluster dies with its last cell: close the gap, list order stays insertion order
         const int id2 = __shfl_down_sync(FULL, id, 1), cnt2 = __shfl_down_sync(FULL, cnt, 1),
@@ -423,7 +470,6 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
             id = -1; cnt = 0; src = -1;
         }
         --L;
-        died = true;
         lo = -1;
         __syncwarp();
         if (lane <= L) {
@@ -431,6 +477,7 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
             sh.s_lc[lane] = lc; sh.s_lcm1[lane] = lcm1;
         }
         __syncwarp();
+        sweep_rebuild_maps(sh, L);
     }
     double l = -BNPC_INF;
     if (lane < L) {
@@ -469,14 +516,63 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
 #define OUT_MOVE 1
 #define OUT_COMPLEX 2
 
+// Lane-local draw of one cell among its own cluster (option 0) and up to three rivals, every
+// other cluster sitting on the reference's 1e-15 floor.  Same arithmetic as
+// _normalize_log_probs + numpy choice, restricted to the options that are not on the floor.
+// Returns the list position picked, or -1 if u falls on a floored entry (exact path decides).
+__device__ __forceinline__ int local_draw(const int* pos, const double* l, int n_opt, int L, double u) {
+    double lmax = l[0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) if (i < n_opt) lmax = fmax(lmax, l[i]);
+    double S = -1.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (i < n_opt) S += exp(l[i] - lmax);
+    if (S < 0.0) S = 0.0;
+    const double lse = log1p(S);
+    const double eps = exp(kLogEps);
+    double p[4];
+    double total = (double)(L + 1 - n_opt) * eps;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        p[i] = 0.0;
+        if (i < n_opt) {
+            p[i] = exp(fmin(fmax(l[i] - lmax - lse, kLogEps), 0.0));
+            total += p[i];
+        }
+    }
+    // walk the options in list order; floored entries between them take eps each
+    double cdf = 0.0;
+    int prev = -1;
+#pragma unroll
+    for (int step = 0; step < 4; ++step) {
+        if (step < n_opt) {
+            int best = -1, bpos = 0x7fffffff;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < n_opt && pos[i] > prev && pos[i] < bpos) { bpos = pos[i]; best = i; }
+            cdf += (double)(bpos - prev - 1) * eps;
+            if (cdf / total > u) return -1;
+            double pb = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (i == best) pb = p[i];
+            cdf += pb;
+            if (cdf / total > u) return bpos;
+            prev = bpos;
+        }
+    }
+    return -1;
+}
+
 // Warp regime (list of at most 31 clusters).  The sweep is sequential, but a cell that ends
 // up where it was leaves every size unchanged, so 32 consecutive cells are scored in parallel
 // (lane <-> cell) against the current sizes; everything before the first cell that does not
 // provably stay is then exact, that cell is resolved, and only the cells after it are scored
-// again.  A cell provably stays when all rivals sit 40 nats below its own cluster (they are all
-// on the reference's 1e-15 floor) and u is away from 0 and 1; with a single rival the draw is a
-// two-way draw decided by comparing log-odds with logit(u), with a 1e-3 guard band; anything
-// else goes through the exact warp-cooperative draw.
+// again.  Scoring looks only at the cell's static rival candidates (bnpc_gibbs_candidates)
+// plus clusters born in this epoch: no rival within 40 nats => the draw returns the current
+// cluster unless u is within 32e-15 of 0 or 1; one rival => two-way draw by comparing log-odds
+// with logit(u) (1e-3 guard band); up to three rivals => lane-local draw; anything else
+// (cluster death, a new cluster, more rivals, u on a floored entry) goes through the exact
+// warp-cooperative draw over the whole list.
 __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
     const int lane = threadIdx.x;
     int L = sh.L;
@@ -497,9 +593,10 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
+    sweep_rebuild_maps(sh, L);
+    const int n_extra = sh.n_extra;
 
-    // stages cover 32 consecutive sweep positions, aligned to the epoch start so that every
-    // bulk copy starts on a 256-byte boundary of the ll matrix
+    // stages = 32 consecutive visit records, streamed into shared memory by bulk async copies
     const int s_first = (t0 - a.t_epoch0) / SW_STAGE_CELLS;
     const int s_last = (a.t_end - 1 - a.t_epoch0) / SW_STAGE_CELLS;
     const int n_stages = s_last - s_first + 1;
@@ -507,10 +604,8 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
         const int slot = g % SW_NSTAGE;
         const int sp = (s_first + g) * SW_STAGE_CELLS;            // position relative to the epoch
         const int nc = min(SW_STAGE_CELLS, a.t_end - a.t_epoch0 - sp);
-        const uint32_t b_ll = ((uint32_t)(nc * ldk * 8) + 15u) & ~15u;
         const uint32_t b_v = (uint32_t)(nc * sizeof(bnpc_visit_t));
-        mbar_expect_tx(&sh.bar[slot], b_ll + b_v);
-        bulk_g2s(sh.ll_stage[slot], a.ll + (long long)sp * ldk, b_ll, &sh.bar[slot]);
+        mbar_expect_tx(&sh.bar[slot], b_v);
         bulk_g2s(sh.vis_stage[slot], a.visit + a.t_epoch0 + sp, b_v, &sh.bar[slot]);
     };
     int issued = 0;
@@ -533,55 +628,71 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
         waited = g + 1;
         const int ts = a.t_epoch0 + (s_first + g) * SW_STAGE_CELLS;
         const int nc = min(SW_STAGE_CELLS, a.t_end - ts);
-        const double* rows = sh.ll_stage[slot];
         const bnpc_visit_t* vis = sh.vis_stage[slot];
         const bnpc_visit_t v = vis[lane < nc ? lane : 0];
-        const double* row = rows + (lane < nc ? lane : 0) * ldk;
-        const int tx = ts + lane - a.t_epoch0;
+        const long long tx = ts + lane - a.t_epoch0;
 
         int lo_lane = max(0, t0 - ts);
         bool need_eval = true;
-        int outcome = OUT_STAY, k_old = -1, r1 = -1;
+        int outcome = OUT_STAY, to_pos = -1, p_old = -1;
         while (lo_lane < nc) {
             if (need_eval) {
                 outcome = OUT_STAY;
                 if (lane >= lo_lane && lane < nc) {
-                    double l_old = -BNPC_INF, m1 = -BNPC_INF, m2 = -BNPC_INF;
-                    k_old = -1; r1 = -1;
-                    for (int k = 0; k < L; ++k) {
-                        const int src = sh.s_src[k];
-                        const double val = (src >= 0) ? row[src]
-                                                      : a.llx[(long long)(-src - 2) * a.ldx + tx];
-                        if (sh.s_id[k] == v.old) {
-                            l_old = val + sh.s_lcm1[k];
-                            k_old = k;
-                        } else {
-                            const double l = val + sh.s_lc[k];
-                            if (l > m1) { m2 = m1; m1 = l; r1 = k; }
-                            else if (l > m2) m2 = l;
-                        }
-                    }
-                    {
-                        const double l = v.lnew;
-                        if (l > m1) { m2 = m1; m1 = l; r1 = L; }
-                        else if (l > m2) m2 = l;
-                    }
-                    const double cut = l_old - 40.0;
-                    if (k_old < 0 || sh.s_cnt[k_old] == 1) {
+                    const int cols = v.cols;
+                    const int n_static = cols >> 24;
+                    p_old = sh.s_pos_of_col[cols & 63];
+                    if (n_static > 2 || p_old < 0 || sh.s_cnt[p_old] == 1 || sh.s_id[p_old] != v.old) {
                         outcome = OUT_COMPLEX;
-                    } else if (!(m1 > cut)) {
-                        outcome = (v.u > 1e-12 && v.u < 1.0 - 1e-12) ? OUT_STAY : OUT_COMPLEX;
-                    } else if (!(m2 > cut) && r1 != L && v.u > 1e-9 && v.u < 1.0 - 1e-9) {
-                        // log-odds of the later list position over the earlier one
-                        const double d_ab = (r1 > k_old) ? (m1 - l_old) : (l_old - m1);
-                        if (fabs(d_ab - v.logit) > 1e-3) {
-                            const int pick = (d_ab < v.logit) ? min(k_old, r1) : max(k_old, r1);
-                            outcome = (pick == k_old) ? OUT_STAY : OUT_MOVE;
-                        } else {
-                            outcome = OUT_COMPLEX;
-                        }
                     } else {
-                        outcome = OUT_COMPLEX;
+                        int pos[4];
+                        double l[4];
+                        int n_opt = 1;
+                        pos[0] = p_old;
+                        l[0] = v.v_old + sh.s_lcm1[p_old];
+                        pos[1] = pos[2] = pos[3] = -1;
+                        l[1] = l[2] = l[3] = -BNPC_INF;
+                        const double cut = l[0] - 40.0;
+                        bool over = false;
+                        auto add = [&](int p, double lv) {
+                            if (lv > cut) {
+                                if (n_opt == 1) { pos[1] = p; l[1] = lv; }
+                                else if (n_opt == 2) { pos[2] = p; l[2] = lv; }
+                                else if (n_opt == 3) { pos[3] = p; l[3] = lv; }
+                                else over = true;
+                                ++n_opt;
+                            }
+                        };
+                        if (n_static >= 1) {
+                            const int p1 = sh.s_pos_of_col[(cols >> 8) & 63];
+                            if (p1 >= 0) add(p1, v.v1 + sh.s_lc[p1]);
+                        }
+                        if (n_static >= 2) {
+                            const int p2 = sh.s_pos_of_col[(cols >> 16) & 63];
+                            if (p2 >= 0) add(p2, v.v2 + sh.s_lc[p2]);
+                        }
+                        for (int e = 0; e < n_extra; ++e) {       // clusters born in this epoch
+                            const int pe = sh.s_xpos[e];
+                            if (pe >= 0) add(pe, a.llx[(long long)e * a.ldx + tx] + sh.s_lc[pe]);
+                        }
+                        add(L, v.lnew);
+                        if (over) {
+                            outcome = OUT_COMPLEX;
+                        } else if (n_opt == 1) {
+                            outcome = (v.u > 1e-12 && v.u < 1.0 - 1e-12) ? OUT_STAY : OUT_COMPLEX;
+                        } else {
+                            int pick = -1;
+                            if (n_opt == 2 && v.u > 1e-9 && v.u < 1.0 - 1e-9) {
+                                // log-odds of the later list position over the earlier one
+                                const double d_ab = (pos[1] > p_old) ? (l[1] - l[0]) : (l[0] - l[1]);
+                                if (fabs(d_ab - v.logit) > 1e-3)
+                                    pick = (d_ab < v.logit) ? min(p_old, pos[1]) : max(p_old, pos[1]);
+                            }
+                            if (pick < 0) pick = local_draw(pos, l, n_opt, L, v.u);
+                            if (pick == p_old) outcome = OUT_STAY;
+                            else if (pick < 0 || pick >= L) outcome = OUT_COMPLEX;
+                            else { outcome = OUT_MOVE; to_pos = pick; }
+                        }
                     }
                 }
             }
@@ -591,7 +702,7 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
             const int of = __shfl_sync(FULL, outcome, f);
             int status;
             if (of == OUT_MOVE) {
-                const int kf = __shfl_sync(FULL, k_old, f), rf = __shfl_sync(FULL, r1, f);
+                const int kf = __shfl_sync(FULL, p_old, f), rf = __shfl_sync(FULL, to_pos, f);
                 if (lane == 0) {
                     const int c_old = sh.s_cnt[kf] - 1, c_new = sh.s_cnt[rf] + 1;
                     sh.s_cnt[kf] = c_old;
@@ -609,7 +720,8 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
                 status = 1;
             } else {
                 ++slow;
-                status = sweep_exact_cell(a, sh, vis[f], rows + f * ldk, ts + f, L);
+                status = sweep_exact_cell(a, sh, vis[f], a.ll + (long long)(ts + f - a.t_epoch0) * ldk,
+                                          ts + f, L);
                 if (status) ++moved;
                 if (status == 2) {
                     next_t = ts + f + 1;
@@ -808,7 +920,8 @@ __device__ void sweep_birth(const bnpc_sweep_args_t& a, SweepShared& sh) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024, 1)
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
     __shared__ SweepShared sh;
     const int tid = threadIdx.x;
@@ -1392,6 +1505,16 @@ int bnpc_gibbs_prepare(const int32_t* perm, const double* u, const int32_t* assi
     return 0;
 }
 
+int bnpc_gibbs_candidates(const double* ll, int ldk, int K, const int32_t* col_of_id,
+                          bnpc_visit_t* visit_t0, int C, double slack, void* stream) {
+    if (C <= 0) return 0;
+    if (K > SW_MAXCOL) return bad_arg("candidates need K <= 64");
+    gibbs_candidates_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(ll, ldk, K, col_of_id, visit_t0, C,
+                                                                          slack);
+    LAUNCH_CHECK("gibbs_candidates");
+    return 0;
+}
+
 int bnpc_gibbs_epoch_begin(const int32_t* live, int K, int32_t* lst, int32_t* cnt, int32_t* col_of_id,
                            int idcap, int32_t* st, int first, void* stream) {
     if (K > idcap) return bad_arg("K > idcap");
@@ -1405,7 +1528,11 @@ int bnpc_gibbs_sweep(const bnpc_sweep_args_t* a, int block_threads, void* stream
     if (!a) return bad_arg("args");
     if (block_threads < 32 || block_threads > 1024 || block_threads % 32) return bad_arg("block_threads");
     if (a->t_begin < a->t_epoch0 || a->t_end - a->t_epoch0 > a->ldx) return bad_arg("sweep range vs ldx");
-    gibbs_sweep_kernel<<<1, block_threads, 0, (cudaStream_t)stream>>>(*a);
+    // 256 threads leave the full register budget to the warp regime; long lists want 1024
+    if (block_threads <= 256)
+        gibbs_sweep_kernel<256><<<1, block_threads, 0, (cudaStream_t)stream>>>(*a);
+    else
+        gibbs_sweep_kernel<1024><<<1, block_threads, 0, (cudaStream_t)stream>>>(*a);
     LAUNCH_CHECK("gibbs_sweep");
     return 0;
 }

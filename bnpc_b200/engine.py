@@ -410,11 +410,15 @@ class DeviceCRP:
                 llx = self._buf('llx', _lib.MAX_EXTRA * rows, torch.float64)
                 scratch = self._buf('scratch', self.idcap + 1, torch.float64)
                 L.logprob_tables(self.theta.data_ptr(), self.lst.data_ptr(), K, M, FN, FP, lp.data_ptr(), sp)
-                # cell indices are read straight out of the visit records (int32 #6 of 8)
+                # cell indices are read straight out of the visit records
                 with self._Timed(self, 'll_matrix'):
                     L.ll_matrix(sh.x1.data_ptr(), sh.x0.data_ptr(), sh.W, M,
-                                self.visit.data_ptr() + t * _lib.VISIT_BYTES + 24, 8, rows,
-                                lp.data_ptr(), K, ll.data_ptr(), ldk, sp)
+                                self.visit.data_ptr() + t * _lib.VISIT_BYTES + _lib.VISIT_CELL_OFFSET,
+                                _lib.VISIT_BYTES // 4, rows, lp.data_ptr(), K, ll.data_ptr(), ldk, sp)
+                if ldk <= 64:
+                    L.gibbs_candidates(ll.data_ptr(), ldk, K, self.col_of_id.data_ptr(),
+                                       self.visit.data_ptr() + t * _lib.VISIT_BYTES, rows,
+                                       float(np.log(N)), sp)
                 a = _lib.SweepArgs(
                     x1=sh.x1.data_ptr(), x0=sh.x0.data_ptr(), W=sh.W, N=N, M=M,
                     assign=self.assign_d.data_ptr(), cnt=self.cnt.data_ptr(), lst=self.lst.data_ptr(),
@@ -428,7 +432,7 @@ class DeviceCRP:
                     logn=sh.logn.data_ptr(), c_norm=c_norm, FN=FN, FP=FP,
                     p=float(self.p), q=float(self.q))
                 with self._Timed(self, 'gibbs_sweep'):
-                    L.gibbs_sweep(C.byref(a), 1024, sp)
+                    L.gibbs_sweep(C.byref(a), 256 if K <= 48 else 1024, sp)
                 st = self._down(self.st)                       # synchronises the stream
                 flags = int(st[_lib.ST_FLAGS])
                 if flags & (_lib.STOP_TAPE_EMPTY | _lib.STOP_HANG):

@@ -57,14 +57,20 @@ extern "C" {
 #define BNPC_STOP_TAPE_EMPTY  4  /* parity mode: more births than taped rows      */
 #define BNPC_STOP_CAPACITY    8  /* list/id capacity reached: grow and relaunch   */
 
-/* per-cell record of a sweep, in visiting order (32 bytes) */
+/* per-cell record of a sweep, in visiting order (64 bytes) */
 typedef struct {
     double  u;      /* uniform for the categorical draw (libs/CRP.py:277)             */
     double  lnew;   /* new-cluster log posterior of this cell (libs/CRP.py:230-234)   */
     double  logit;  /* log((1-u)/u): a two-way draw picks the first option iff the
                        log-odds of the second over the first are below this           */
+    double  v_old;  /* ll of the cell under its current cluster ...                   */
+    double  v1, v2; /* ... and under its two best rival clusters (epoch columns)      */
     int32_t cell;   /* cell index = permutation[t] (libs/CRP.py:260)                  */
     int32_t old;    /* its cluster id before the sweep                                 */
+    int32_t cols;   /* c_old | c1<<8 | c2<<16 | n<<24: ll columns of the above and the
+                       number n (saturating at 3) of clusters that can come within 40
+                       nats of the current one for ANY cluster sizes                   */
+    int32_t pad;
 } bnpc_visit_t;
 
 int         bnpc_abi_version(void);
@@ -108,6 +114,13 @@ int bnpc_gibbs_prepare(const int32_t* perm, const double* u, const int32_t* assi
                        const int32_t* n1, const int32_t* n0, int N,
                        double c1, double c0, double lnew_prior,
                        bnpc_visit_t* visit, void* stream);
+/* After bnpc_ll_matrix of an epoch with at most 64 columns: fill v_old, v1, v2, cols of
+ * the visit records [t0, t0+C).  A cluster k can rival the current cluster o of a cell
+ * (come within 40 nats of it once the CRP weights log n_k are added) only if
+ * ll_k > ll_o - 40 - slack with slack = log N, whatever the sizes are; the sequential
+ * sweep then only looks at these candidates.                                        */
+int bnpc_gibbs_candidates(const double* ll, int ldk, int K, const int32_t* col_of_id,
+                          bnpc_visit_t* visit_t0, int C, double slack, void* stream);
 /* Start of an epoch: rebuild cnt[] from the host-authoritative list
  * live[2*j] = id, live[2*j+1] = size (list order), set col_of_id[id] = j and
  * clear the epoch's extra-cluster bookkeeping.  first != 0 also resets the
