@@ -703,17 +703,24 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
             int status;
             if (of == OUT_MOVE) {
                 const int kf = __shfl_sync(FULL, p_old, f), rf = __shfl_sync(FULL, to_pos, f);
+                // sizes n_old-1 and n_new+1: one of the two log weights of each cluster is the
+                // other one's previous value; the two new ones are computed by two lanes at once
+                // (log() instead of a dependent table fetch from global memory)
                 if (lane == 0) {
-                    const int c_old = sh.s_cnt[kf] - 1, c_new = sh.s_cnt[rf] + 1;
+                    const int c_old = sh.s_cnt[kf] - 1;
+                    const double w = sh.s_lcm1[kf];
                     sh.s_cnt[kf] = c_old;
-                    sh.s_lc[kf] = a.logn[c_old] - a.c_norm;
-                    sh.s_lcm1[kf] = a.logn[c_old - 1] - a.c_norm;
+                    sh.s_lc[kf] = w;
+                    sh.s_lcm1[kf] = log((double)(c_old - 1)) - a.c_norm;
                     a.cnt[sh.s_id[kf]] = c_old;
-                    sh.s_cnt[rf] = c_new;
-                    sh.s_lc[rf] = a.logn[c_new] - a.c_norm;
-                    sh.s_lcm1[rf] = a.logn[c_new - 1] - a.c_norm;
-                    a.cnt[sh.s_id[rf]] = c_new;
                     a.assign[vis[f].cell] = sh.s_id[rf];
+                } else if (lane == 1) {
+                    const int c_new = sh.s_cnt[rf] + 1;
+                    const double w = sh.s_lc[rf];
+                    sh.s_cnt[rf] = c_new;
+                    sh.s_lcm1[rf] = w;
+                    sh.s_lc[rf] = log((double)c_new) - a.c_norm;
+                    a.cnt[sh.s_id[rf]] = c_new;
                 }
                 __syncwarp();
                 ++moved;
@@ -925,7 +932,11 @@ __global__ void __launch_bounds__(MAXT, 1)
 gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
     __shared__ SweepShared sh;
     const int tid = threadIdx.x;
+    long long clk0 = 0;
+    unsigned long long ns0 = 0;
     if (tid == 0) {
+        clk0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
         sh.L = a.st[BNPC_ST_K];
         sh.t = a.t_begin;
         sh.pending = 0;
@@ -976,6 +987,11 @@ gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
         a.st[BNPC_ST_BIRTHS] = sh.births;
         a.st[BNPC_ST_MOVED] = sh.moved;
         a.st[BNPC_ST_SLOW] = sh.slow;
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        const long long dc = clock64() - clk0;
+        a.st[BNPC_ST_CYCLES] = (int)(dc >> 10);          // kilo-cycles of this launch
+        a.st[BNPC_ST_NANOS] = (int)((ns1 - ns0) >> 10);   // ~microseconds of this launch
     }
 }
 

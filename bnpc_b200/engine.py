@@ -454,7 +454,9 @@ class DeviceCRP:
                     raise RuntimeError(f'parity tape held {n_tape} cluster births, sweep made '
                                        f'{int(st[_lib.ST_BIRTHS])}')
             self.sweep_stats = dict(epochs=epochs, births=int(st[_lib.ST_BIRTHS]),
-                                    moved=int(st[_lib.ST_MOVED]), slow=int(st[_lib.ST_SLOW]))
+                                    moved=int(st[_lib.ST_MOVED]), slow=int(st[_lib.ST_SLOW]),
+                                    kcycles=int(st[8]), us=int(st[9]) * 1.024,
+                                    sm_mhz=(int(st[8]) / max(1, int(st[9]))) * 1e3)
         self._touch()
 
     # ----------------------------------------------------------------- MH theta

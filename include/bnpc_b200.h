@@ -50,6 +50,8 @@ extern "C" {
 #define BNPC_ST_BIRTHS   4   /* clusters born in this sweep (tape rows used)   */
 #define BNPC_ST_MOVED    5   /* cells whose cluster changed in this sweep      */
 #define BNPC_ST_SLOW     6   /* cells that took the exact (slow) path          */
+#define BNPC_ST_CYCLES   8   /* SM clock cycles of the last sweep launch, / 1024 */
+#define BNPC_ST_NANOS    9   /* globaltimer ns of the last sweep launch, / 1024  */
 #define BNPC_ST_WORDS    16
 
 #define BNPC_STOP_EXTRA_FULL  1  /* BNPC_MAX_EXTRA births: start a new epoch      */
