@@ -24,7 +24,9 @@ ST_K, ST_TDONE, ST_FLAGS, ST_NEXTRA, ST_BIRTHS, ST_MOVED, ST_SLOW = range(7)
 ST_WORDS = 16
 STOP_EXTRA_FULL, STOP_REPACK, STOP_TAPE_EMPTY, STOP_CAPACITY, STOP_HANG = 1, 2, 4, 8, 0x100
 VISIT_BYTES = 64
-VISIT_CELL_OFFSET = 48
+VISIT_CELL_OFFSET = 32
+CAND_BYTES = 80
+MAX_LIST = 1024          # longest cluster list the sequencer regime of the sweep handles
 
 
 def _stale():
@@ -56,7 +58,7 @@ class SweepArgs(C.Structure):
         ('ll', C.c_void_p), ('ldk', C.c_int32), ('t_epoch0', C.c_int32),
         ('lpx', C.c_void_p), ('llx', C.c_void_p), ('ldx', C.c_int32),
         ('scratch', C.c_void_p),
-        ('visit', C.c_void_p), ('t_begin', C.c_int32), ('t_end', C.c_int32),
+        ('visit', C.c_void_p), ('cand', C.c_void_p), ('t_begin', C.c_int32), ('t_end', C.c_int32),
         ('beta_rows', C.c_void_p), ('n_beta_rows', C.c_int32),
         ('seed', C.c_uint64), ('stream_id', C.c_uint64),
         ('logn', C.c_void_p),
@@ -74,7 +76,7 @@ SIGNATURES = {
     'bnpc_logprob_tables': [_P, _P, _I, _I, _D, _D, _P, _P],
     'bnpc_ll_matrix': [_P, _P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _P],
     'bnpc_gibbs_prepare': [_P, _P, _P, _P, _P, _I, _D, _D, _D, _P, _P],
-    'bnpc_gibbs_candidates': [_P, _I, _I, _P, _P, _I, _D, _P],
+    'bnpc_gibbs_candidates': [_P, _I, _I, _P, _P, _P, _I, _D, _P],
     'bnpc_gibbs_epoch_begin': [_P, _I, _P, _P, _P, _I, _P, _I, _P],
     'bnpc_gibbs_sweep': [C.POINTER(SweepArgs), _I, _P],
     'bnpc_group_members': [_P, _I, _P, _P, _P, _I, _P, _P],

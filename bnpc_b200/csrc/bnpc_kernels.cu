@@ -301,41 +301,58 @@ __global__ void gibbs_prepare_kernel(const int32_t* __restrict__ perm, const dou
     // popcount form of libs/CRP.py:230-234: every observed 1 contributes c1, every 0 c0
     v.lnew = ((double)n1[c] * c1 + (double)n0[c] * c0) + lnew_prior;
     v.logit = log1p(-v.u) - log(v.u);
-    v.v_old = 0.0; v.v1 = 0.0; v.v2 = 0.0;
+    v.v_old = 0.0;
     v.cell = c;
     v.old = assign[c];
-    v.cols = 3 << 24;                 // "unknown rivals" until bnpc_gibbs_candidates has run
-    v.pad = 0;
+    v.c_old = -1;
+    v.n_cand = BNPC_MAX_CAND + 1;     // "unknown rivals" until bnpc_gibbs_candidates has run
+    v.pad[0] = v.pad[1] = v.pad[2] = v.pad[3] = 0;
     visit[t] = v;
 }
 
 // static rival candidates of every visited cell (see include/bnpc_b200.h)
 __global__ void gibbs_candidates_kernel(const double* __restrict__ ll, int ldk, int K,
                                         const int32_t* __restrict__ col_of_id,
-                                        bnpc_visit_t* __restrict__ visit, int C, double slack) {
+                                        bnpc_visit_t* __restrict__ visit, bnpc_cand_t* __restrict__ cand,
+                                        int C, double slack) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= C) return;
     const double* row = ll + (long long)r * ldk;
     const int c_old = col_of_id[visit[r].old];
-    int c1 = 0, c2 = 0, n = 3;
-    double v_old = 0.0, v1 = -BNPC_INF, v2 = -BNPC_INF;
+    double val[BNPC_MAX_CAND];
+    int col[BNPC_MAX_CAND];
+#pragma unroll
+    for (int i = 0; i < BNPC_MAX_CAND; ++i) { val[i] = -BNPC_INF; col[i] = 0; }
+    int n = BNPC_MAX_CAND + 1;
+    double v_old = 0.0;
     if (c_old >= 0 && c_old < K) {
         v_old = row[c_old];
         const double thr = v_old - 40.0 - slack;
         n = 0;
         for (int k = 0; k < K; ++k) {
-            if (k == c_old) continue;
             const double v = row[k];
-            if (v > thr) ++n;
-            if (v > v1) { v2 = v1; c2 = c1; v1 = v; c1 = k; }
-            else if (v > v2) { v2 = v; c2 = k; }
+            if (k == c_old || !(v > thr)) continue;
+            ++n;
+            // insert into the best-first list (registers; fully unrolled bubble)
+            double cv = v;
+            int cc = k;
+#pragma unroll
+            for (int i = 0; i < BNPC_MAX_CAND; ++i) {
+                if (cv > val[i]) {
+                    const double tv = val[i]; const int tc = col[i];
+                    val[i] = cv; col[i] = cc; cv = tv; cc = tc;
+                }
+            }
         }
-        if (n > 3) n = 3;
+        if (n > BNPC_MAX_CAND) n = BNPC_MAX_CAND + 1;
     }
     visit[r].v_old = v_old;
-    visit[r].v1 = v1;
-    visit[r].v2 = v2;
-    visit[r].cols = (c_old & 255) | (c1 << 8) | (c2 << 16) | (n << 24);
+    visit[r].c_old = c_old;
+    visit[r].n_cand = n;
+    bnpc_cand_t out;
+#pragma unroll
+    for (int i = 0; i < BNPC_MAX_CAND; ++i) { out.val[i] = val[i]; out.col[i] = (uint16_t)col[i]; }
+    cand[r] = out;
 }
 
 __global__ void gibbs_epoch_begin_kernel(const int32_t* __restrict__ live, int K, int32_t* lst,
@@ -391,17 +408,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 #define SW_STAGE_CELLS 32
 #define SW_NSTAGE 4
-#define SW_MAXCOL 64          /* ll columns addressable from the packed candidate record */
+#define SW_MAXL 1024          /* longest list / widest ll matrix the sequencer regime handles */
+#define SW_NOPT (BNPC_MAX_CAND + 2)   /* own cluster + candidates + one more (new cluster / newborn) */
 
 struct SweepShared {
     alignas(128) bnpc_visit_t vis_stage[SW_NSTAGE][SW_STAGE_CELLS];
+    alignas(128) bnpc_cand_t cand_stage[SW_NSTAGE][SW_STAGE_CELLS];
     alignas(8) uint64_t bar[SW_NSTAGE];
     double red[40];
-    // the live list while it fits a warp: position j <-> insertion order
-    double s_lc[32], s_lcm1[32];          // log CRP weight at the current size / at size-1
-    int s_id[32], s_cnt[32], s_src[32];   // cluster id, size, ll column (>=0) or -(extra+2)
-    int s_pos_of_col[SW_MAXCOL];          // ll column -> list position, -1 once the cluster died
-    int s_xpos[BNPC_MAX_EXTRA];           // cluster born in this epoch -> list position or -1
+    // the live list (position j <-> insertion order) while it has at most SW_MAXL entries
+    double s_lc[SW_MAXL], s_lcm1[SW_MAXL];      // log CRP weight at the current size / at size-1
+    int s_id[SW_MAXL], s_cnt[SW_MAXL], s_src[SW_MAXL];   // id, size, ll column (>=0) or -(extra+2)
+    int s_pos_of_col[SW_MAXL];                  // ll column -> list position, -1 once the cluster died
+    int s_xpos[BNPC_MAX_EXTRA];                 // cluster born in this epoch -> list position or -1
     int L, t, pending, stop;
     int birth_cell, birth_t;
     int n_extra, births, moved, slow;
@@ -409,7 +428,7 @@ struct SweepShared {
     int hang;
 };
 
-// One exact categorical draw for the warp-resident list (libs/CRP.py:88-100 + numpy choice,
+// One exact categorical draw for a list that fits a warp (libs/CRP.py:88-100 + numpy choice,
 // libs/CRP.py:274-277).  Lanes [0,L) hold live clusters, lane L the new-cluster option.
 __device__ __forceinline__ int warp_categorical(double l, int L, double u, int lane) {
     const bool in = lane <= L;
@@ -430,20 +449,20 @@ __device__ __forceinline__ int warp_categorical(double l, int L, double u, int l
 // column / extra -> list position maps, rebuilt after every structural change (rare)
 __device__ __forceinline__ void sweep_rebuild_maps(SweepShared& sh, int L) {
     const int lane = threadIdx.x;
-    for (int c = lane; c < SW_MAXCOL; c += 32) sh.s_pos_of_col[c] = -1;
+    for (int c = lane; c < SW_MAXL; c += 32) sh.s_pos_of_col[c] = -1;
     for (int e = lane; e < BNPC_MAX_EXTRA; e += 32) sh.s_xpos[e] = -1;
     __syncwarp();
-    if (lane < L) {
-        const int src = sh.s_src[lane];
-        if (src >= 0) { if (src < SW_MAXCOL) sh.s_pos_of_col[src] = lane; }
-        else if (src <= -2) sh.s_xpos[-src - 2] = lane;
+    for (int j = lane; j < L; j += 32) {
+        const int src = sh.s_src[j];
+        if (src >= 0) { if (src < SW_MAXL) sh.s_pos_of_col[src] = j; }
+        else if (src <= -2) sh.s_xpos[-src - 2] = j;
     }
     __syncwarp();
 }
 
-// Exact treatment of one cell by the whole warp, lanes <-> clusters (libs/CRP.py:262-288).
-// `row` is the cell's ll row in GLOBAL memory.  Returns 0: the cell stayed, 1: list/sizes
-// changed, 2: it opens a new cluster (CTA-wide work, the caller leaves the warp regime).
+// Exact treatment of one cell by one warp, lanes <-> clusters, for lists of at most 31 clusters
+// (libs/CRP.py:262-288).  `row` is the cell's ll row in GLOBAL memory.  Returns 0: the cell
+// stayed, 1: list/sizes changed, 2: it opens a new cluster (CTA-wide work follows).
 __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, const bnpc_visit_t& v,
                                 const double* row, int t, int& L) {
     const int lane = threadIdx.x;
@@ -490,8 +509,8 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
     if (pick == lo) return 0;
     if (lo >= 0 && lane == lo) {                    // leave the old cluster
         --cnt;
-        lc = a.logn[cnt] - a.c_norm;
-        lcm1 = a.logn[cnt - 1] - a.c_norm;
+        lc = log((double)cnt) - a.c_norm;
+        lcm1 = log((double)(cnt - 1)) - a.c_norm;
         a.cnt[id] = cnt;
         sh.s_cnt[lane] = cnt; sh.s_lc[lane] = lc; sh.s_lcm1[lane] = lcm1;
     }
@@ -502,8 +521,8 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
     }
     if (lane == pick) {
         ++cnt;
-        lc = a.logn[cnt] - a.c_norm;
-        lcm1 = a.logn[cnt - 1] - a.c_norm;
+        lc = log((double)cnt) - a.c_norm;
+        lcm1 = log((double)(cnt - 1)) - a.c_norm;
         a.cnt[id] = cnt;
         a.assign[v.cell] = id;
         sh.s_cnt[lane] = cnt; sh.s_lc[lane] = lc; sh.s_lcm1[lane] = lcm1;
@@ -516,24 +535,24 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
 #define OUT_MOVE 1
 #define OUT_COMPLEX 2
 
-// Lane-local draw of one cell among its own cluster (option 0) and up to three rivals, every
-// other cluster sitting on the reference's 1e-15 floor.  Same arithmetic as
-// _normalize_log_probs + numpy choice, restricted to the options that are not on the floor.
+// Lane-local draw of one cell among its own cluster (option 0) and its rivals, every other
+// cluster sitting on the reference's 1e-15 floor.  Same arithmetic as _normalize_log_probs +
+// numpy choice (libs/CRP.py:88-100, 277), restricted to the options that are not on the floor.
 // Returns the list position picked, or -1 if u falls on a floored entry (exact path decides).
 __device__ __forceinline__ int local_draw(const int* pos, const double* l, int n_opt, int L, double u) {
     double lmax = l[0];
 #pragma unroll
-    for (int i = 1; i < 4; ++i) if (i < n_opt) lmax = fmax(lmax, l[i]);
+    for (int i = 1; i < SW_NOPT; ++i) if (i < n_opt) lmax = fmax(lmax, l[i]);
     double S = -1.0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) if (i < n_opt) S += exp(l[i] - lmax);
+    for (int i = 0; i < SW_NOPT; ++i) if (i < n_opt) S += exp(l[i] - lmax);
     if (S < 0.0) S = 0.0;
     const double lse = log1p(S);
     const double eps = exp(kLogEps);
-    double p[4];
+    double p[SW_NOPT];
     double total = (double)(L + 1 - n_opt) * eps;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < SW_NOPT; ++i) {
         p[i] = 0.0;
         if (i < n_opt) {
             p[i] = exp(fmin(fmax(l[i] - lmax - lse, kLogEps), 0.0));
@@ -543,49 +562,45 @@ __device__ __forceinline__ int local_draw(const int* pos, const double* l, int n
     // walk the options in list order; floored entries between them take eps each
     double cdf = 0.0;
     int prev = -1;
+    for (int step = 0; step < n_opt; ++step) {
+        int bpos = 0x7fffffff;
+        double pb = 0.0;
 #pragma unroll
-    for (int step = 0; step < 4; ++step) {
-        if (step < n_opt) {
-            int best = -1, bpos = 0x7fffffff;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (i < n_opt && pos[i] > prev && pos[i] < bpos) { bpos = pos[i]; best = i; }
-            cdf += (double)(bpos - prev - 1) * eps;
-            if (cdf / total > u) return -1;
-            double pb = 0.0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) if (i == best) pb = p[i];
-            cdf += pb;
-            if (cdf / total > u) return bpos;
-            prev = bpos;
-        }
+        for (int i = 0; i < SW_NOPT; ++i)
+            if (i < n_opt && pos[i] > prev && pos[i] < bpos) { bpos = pos[i]; pb = p[i]; }
+        cdf += (double)(bpos - prev - 1) * eps;
+        if (cdf / total > u) return -1;
+        cdf += pb;
+        if (cdf / total > u) return bpos;
+        prev = bpos;
     }
     return -1;
 }
 
-// Warp regime (list of at most 31 clusters).  The sweep is sequential, but a cell that ends
-// up where it was leaves every size unchanged, so 32 consecutive cells are scored in parallel
-// (lane <-> cell) against the current sizes; everything before the first cell that does not
-// provably stay is then exact, that cell is resolved, and only the cells after it are scored
-// again.  Scoring looks only at the cell's static rival candidates (bnpc_gibbs_candidates)
-// plus clusters born in this epoch: no rival within 40 nats => the draw returns the current
-// cluster unless u is within 32e-15 of 0 or 1; one rival => two-way draw by comparing log-odds
-// with logit(u) (1e-3 guard band); up to three rivals => lane-local draw; anything else
-// (cluster death, a new cluster, more rivals, u on a floored entry) goes through the exact
-// warp-cooperative draw over the whole list.
-__device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
+// Sequencer regime (lists of at most SW_MAXL clusters), run by warp 0.  The sweep is
+// sequential, but a cell that ends up where it was leaves every size unchanged, so 32
+// consecutive cells are scored in parallel (lane <-> cell) against the current sizes;
+// everything before the first cell that does not provably stay is then exact, that cell is
+// resolved, and only the cells after it are scored again.  Scoring looks only at the cell's
+// static rival candidates (bnpc_gibbs_candidates) plus clusters born in this epoch: no rival
+// within 40 nats => the draw returns the current cluster unless u is within 1e-12 of 0 or 1;
+// one rival => two-way draw by comparing log-odds with logit(u) (1e-3 guard band); otherwise a
+// lane-local draw over the rivals.  Cluster death, a new cluster, too many rivals or u on a
+// floored entry go through the exact draw over the whole list (warp-cooperative for lists of
+// up to 31 clusters, CTA-wide otherwise).
+__device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
     const int lane = threadIdx.x;
     int L = sh.L;
     const int t0 = sh.t;
     const int ldk = a.ldk;
     int moved = 0, slow = 0;
 
-    if (lane < L) {
-        const int id = a.lst[lane];
+    for (int j = lane; j < L; j += 32) {
+        const int id = a.lst[j];
         const int c = a.cnt[id];
-        sh.s_id[lane] = id; sh.s_cnt[lane] = c; sh.s_src[lane] = a.col_of_id[id];
-        sh.s_lc[lane] = a.logn[c] - a.c_norm;
-        sh.s_lcm1[lane] = a.logn[c - 1] - a.c_norm;
+        sh.s_id[j] = id; sh.s_cnt[j] = c; sh.s_src[j] = a.col_of_id[id];
+        sh.s_lc[j] = a.logn[c] - a.c_norm;
+        sh.s_lcm1[j] = a.logn[c - 1] - a.c_norm;
     }
     if (lane == 0) {
         for (int s = 0; s < SW_NSTAGE; ++s) mbar_init(&sh.bar[s], 1);
@@ -596,7 +611,8 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
     sweep_rebuild_maps(sh, L);
     const int n_extra = sh.n_extra;
 
-    // stages = 32 consecutive visit records, streamed into shared memory by bulk async copies
+    // stages = 32 consecutive visit + candidate records, streamed into shared memory by bulk
+    // async copies (TMA engine) NSTAGE ahead of the sequencer
     const int s_first = (t0 - a.t_epoch0) / SW_STAGE_CELLS;
     const int s_last = (a.t_end - 1 - a.t_epoch0) / SW_STAGE_CELLS;
     const int n_stages = s_last - s_first + 1;
@@ -605,8 +621,10 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
         const int sp = (s_first + g) * SW_STAGE_CELLS;            // position relative to the epoch
         const int nc = min(SW_STAGE_CELLS, a.t_end - a.t_epoch0 - sp);
         const uint32_t b_v = (uint32_t)(nc * sizeof(bnpc_visit_t));
-        mbar_expect_tx(&sh.bar[slot], b_v);
+        const uint32_t b_c = (uint32_t)(nc * sizeof(bnpc_cand_t));
+        mbar_expect_tx(&sh.bar[slot], b_v + b_c);
         bulk_g2s(sh.vis_stage[slot], a.visit + a.t_epoch0 + sp, b_v, &sh.bar[slot]);
+        bulk_g2s(sh.cand_stage[slot], a.cand + a.t_epoch0 + sp, b_c, &sh.bar[slot]);
     };
     int issued = 0;
     if (lane == 0)
@@ -629,7 +647,9 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
         const int ts = a.t_epoch0 + (s_first + g) * SW_STAGE_CELLS;
         const int nc = min(SW_STAGE_CELLS, a.t_end - ts);
         const bnpc_visit_t* vis = sh.vis_stage[slot];
-        const bnpc_visit_t v = vis[lane < nc ? lane : 0];
+        const int my = lane < nc ? lane : 0;
+        const bnpc_visit_t v = vis[my];
+        const bnpc_cand_t* cd = &sh.cand_stage[slot][my];
         const long long tx = ts + lane - a.t_epoch0;
 
         int lo_lane = max(0, t0 - ts);
@@ -639,37 +659,36 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
             if (need_eval) {
                 outcome = OUT_STAY;
                 if (lane >= lo_lane && lane < nc) {
-                    const int cols = v.cols;
-                    const int n_static = cols >> 24;
-                    p_old = sh.s_pos_of_col[cols & 63];
-                    if (n_static > 2 || p_old < 0 || sh.s_cnt[p_old] == 1 || sh.s_id[p_old] != v.old) {
+                    const int n_static = v.n_cand;
+                    p_old = (v.c_old >= 0 && v.c_old < SW_MAXL) ? sh.s_pos_of_col[v.c_old] : -1;
+                    if (n_static > BNPC_MAX_CAND || p_old < 0 || sh.s_cnt[p_old] == 1 ||
+                        sh.s_id[p_old] != v.old) {
                         outcome = OUT_COMPLEX;
                     } else {
-                        int pos[4];
-                        double l[4];
+                        int pos[SW_NOPT];
+                        double l[SW_NOPT];
+#pragma unroll
+                        for (int i = 0; i < SW_NOPT; ++i) { pos[i] = -1; l[i] = -BNPC_INF; }
                         int n_opt = 1;
                         pos[0] = p_old;
                         l[0] = v.v_old + sh.s_lcm1[p_old];
-                        pos[1] = pos[2] = pos[3] = -1;
-                        l[1] = l[2] = l[3] = -BNPC_INF;
                         const double cut = l[0] - 40.0;
                         bool over = false;
                         auto add = [&](int p, double lv) {
                             if (lv > cut) {
-                                if (n_opt == 1) { pos[1] = p; l[1] = lv; }
-                                else if (n_opt == 2) { pos[2] = p; l[2] = lv; }
-                                else if (n_opt == 3) { pos[3] = p; l[3] = lv; }
-                                else over = true;
+                                if (n_opt >= SW_NOPT) over = true;
+#pragma unroll
+                                for (int i = 1; i < SW_NOPT; ++i)
+                                    if (i == n_opt) { pos[i] = p; l[i] = lv; }
                                 ++n_opt;
                             }
                         };
-                        if (n_static >= 1) {
-                            const int p1 = sh.s_pos_of_col[(cols >> 8) & 63];
-                            if (p1 >= 0) add(p1, v.v1 + sh.s_lc[p1]);
-                        }
-                        if (n_static >= 2) {
-                            const int p2 = sh.s_pos_of_col[(cols >> 16) & 63];
-                            if (p2 >= 0) add(p2, v.v2 + sh.s_lc[p2]);
+#pragma unroll
+                        for (int i = 0; i < BNPC_MAX_CAND; ++i) {
+                            if (i < n_static) {
+                                const int pi = sh.s_pos_of_col[cd->col[i]];
+                                if (pi >= 0) add(pi, cd->val[i] + sh.s_lc[pi]);
+                            }
                         }
                         for (int e = 0; e < n_extra; ++e) {       // clusters born in this epoch
                             const int pe = sh.s_xpos[e];
@@ -705,7 +724,6 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
                 const int kf = __shfl_sync(FULL, p_old, f), rf = __shfl_sync(FULL, to_pos, f);
                 // sizes n_old-1 and n_new+1: one of the two log weights of each cluster is the
                 // other one's previous value; the two new ones are computed by two lanes at once
-                // (log() instead of a dependent table fetch from global memory)
                 if (lane == 0) {
                     const int c_old = sh.s_cnt[kf] - 1;
                     const double w = sh.s_lcm1[kf];
@@ -727,6 +745,12 @@ __device__ void sweep_warp_regime(const bnpc_sweep_args_t& a, SweepShared& sh) {
                 status = 1;
             } else {
                 ++slow;
+                if (L > 31) {                       // CTA-wide exact draw, then come back
+                    if (lane == 0) sh.pending = 2;
+                    next_t = ts + f;
+                    leave = true;
+                    break;
+                }
                 status = sweep_exact_cell(a, sh, vis[f], a.ll + (long long)(ts + f - a.t_epoch0) * ldk,
                                           ts + f, L);
                 if (status) ++moved;
@@ -930,7 +954,8 @@ __device__ void sweep_birth(const bnpc_sweep_args_t& a, SweepShared& sh) {
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
-    __shared__ SweepShared sh;
+    extern __shared__ __align__(128) unsigned char sweep_smem[];
+    SweepShared& sh = *reinterpret_cast<SweepShared*>(sweep_smem);
     const int tid = threadIdx.x;
     long long clk0 = 0;
     unsigned long long ns0 = 0;
@@ -951,7 +976,7 @@ gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
     if (sh.stop) return;                            // an earlier launch of this sweep stopped
 
     for (;;) {
-        const int t = sh.t, L = sh.L, stop = sh.stop | sh.hang;
+        const int t = sh.t, L = sh.L, stop = sh.stop | sh.hang, pending = sh.pending;
         __syncthreads();
         if (t >= a.t_end || stop) break;
         if (L + 1 + BNPC_MAX_EXTRA >= a.idcap) {
@@ -959,18 +984,24 @@ gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
             __syncthreads();
             continue;
         }
-        if (L <= 31) {
-            if (a.ldk > SW_MAXCOL) {
-                if (tid == 0) sh.stop |= BNPC_STOP_REPACK;
-                __syncthreads();
-                continue;
-            }
-            if (tid < 32) sweep_warp_regime(a, sh);
+        if (pending == 2) {
+            // the sequencer handed this cell to the CTA-wide exact draw
+            if (tid == 0) sh.pending = 0;
             __syncthreads();
+            sweep_block_cell(a, sh, t, L);
+        } else if (L < SW_MAXL && a.ldk <= SW_MAXL) {
+            if (tid < 32) sweep_sequencer(a, sh);
+            __syncthreads();
+        } else if (L < SW_MAXL / 2) {
+            // the list shrank far below the width of this epoch's ll matrix: let the host
+            // start a narrower epoch so that the sequencer regime can take over
+            if (tid == 0) sh.stop |= BNPC_STOP_REPACK;
+            __syncthreads();
+            continue;
         } else {
             sweep_block_cell(a, sh, t, L);
         }
-        if (sh.pending) sweep_birth(a, sh);
+        if (sh.pending == 1) sweep_birth(a, sh);
     }
     __syncthreads();
     const int L = sh.L;
@@ -1522,11 +1553,11 @@ int bnpc_gibbs_prepare(const int32_t* perm, const double* u, const int32_t* assi
 }
 
 int bnpc_gibbs_candidates(const double* ll, int ldk, int K, const int32_t* col_of_id,
-                          bnpc_visit_t* visit_t0, int C, double slack, void* stream) {
+                          bnpc_visit_t* visit_t0, bnpc_cand_t* cand_t0, int C, double slack, void* stream) {
     if (C <= 0) return 0;
-    if (K > SW_MAXCOL) return bad_arg("candidates need K <= 64");
-    gibbs_candidates_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(ll, ldk, K, col_of_id, visit_t0, C,
-                                                                          slack);
+    if (K > SW_MAXL) return bad_arg("candidates need K <= 1024");
+    gibbs_candidates_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(ll, ldk, K, col_of_id, visit_t0,
+                                                                          cand_t0, C, slack);
     LAUNCH_CHECK("gibbs_candidates");
     return 0;
 }
@@ -1544,11 +1575,20 @@ int bnpc_gibbs_sweep(const bnpc_sweep_args_t* a, int block_threads, void* stream
     if (!a) return bad_arg("args");
     if (block_threads < 32 || block_threads > 1024 || block_threads % 32) return bad_arg("block_threads");
     if (a->t_begin < a->t_epoch0 || a->t_end - a->t_epoch0 > a->ldx) return bad_arg("sweep range vs ldx");
-    // 256 threads leave the full register budget to the warp regime; long lists want 1024
+    // 256 threads leave the full register budget to the sequencer warp; long lists want 1024
+    const size_t smem = sizeof(SweepShared);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e1 = cudaFuncSetAttribute(gibbs_sweep_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e2 = cudaFuncSetAttribute(gibbs_sweep_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e1 != cudaSuccess) return fail("gibbs_sweep smem attribute", e1);
+        if (e2 != cudaSuccess) return fail("gibbs_sweep smem attribute", e2);
+        attr_done = true;
+    }
     if (block_threads <= 256)
-        gibbs_sweep_kernel<256><<<1, block_threads, 0, (cudaStream_t)stream>>>(*a);
+        gibbs_sweep_kernel<256><<<1, block_threads, smem, (cudaStream_t)stream>>>(*a);
     else
-        gibbs_sweep_kernel<1024><<<1, block_threads, 0, (cudaStream_t)stream>>>(*a);
+        gibbs_sweep_kernel<1024><<<1, block_threads, smem, (cudaStream_t)stream>>>(*a);
     LAUNCH_CHECK("gibbs_sweep");
     return 0;
 }

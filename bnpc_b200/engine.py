@@ -204,6 +204,7 @@ class DeviceCRP:
             N = self.cells_total
             self.assign_d = torch.zeros(N, dtype=torch.int32, device=self.device)
             self.visit = torch.empty(N * _lib.VISIT_BYTES, dtype=torch.uint8, device=self.device)
+            self.cand = torch.empty(N * _lib.CAND_BYTES, dtype=torch.uint8, device=self.device)
             self.members = torch.empty(N, dtype=torch.int32, device=self.device)
             self.cells_d = torch.empty(N + 8, dtype=torch.int32, device=self.device)
             self.half = torch.zeros(N + 8, dtype=torch.int32, device=self.device)
@@ -415,9 +416,10 @@ class DeviceCRP:
                     L.ll_matrix(sh.x1.data_ptr(), sh.x0.data_ptr(), sh.W, M,
                                 self.visit.data_ptr() + t * _lib.VISIT_BYTES + _lib.VISIT_CELL_OFFSET,
                                 _lib.VISIT_BYTES // 4, rows, lp.data_ptr(), K, ll.data_ptr(), ldk, sp)
-                if ldk <= 64:
+                if ldk <= _lib.MAX_LIST:
                     L.gibbs_candidates(ll.data_ptr(), ldk, K, self.col_of_id.data_ptr(),
-                                       self.visit.data_ptr() + t * _lib.VISIT_BYTES, rows,
+                                       self.visit.data_ptr() + t * _lib.VISIT_BYTES,
+                                       self.cand.data_ptr() + t * _lib.CAND_BYTES, rows,
                                        float(np.log(N)), sp)
                 a = _lib.SweepArgs(
                     x1=sh.x1.data_ptr(), x0=sh.x0.data_ptr(), W=sh.W, N=N, M=M,
@@ -426,13 +428,13 @@ class DeviceCRP:
                     st=self.st.data_ptr(), live_out=self.live_io.data_ptr(),
                     ll=ll.data_ptr(), ldk=ldk, t_epoch0=t,
                     lpx=lpx.data_ptr(), llx=llx.data_ptr(), ldx=rows, scratch=scratch.data_ptr(),
-                    visit=self.visit.data_ptr(), t_begin=t, t_end=t + rows,
+                    visit=self.visit.data_ptr(), cand=self.cand.data_ptr(), t_begin=t, t_end=t + rows,
                     beta_rows=beta_tape.data_ptr() if beta_tape is not None else None,
                     n_beta_rows=n_tape, seed=seed, stream_id=stream_id,
                     logn=sh.logn.data_ptr(), c_norm=c_norm, FN=FN, FP=FP,
                     p=float(self.p), q=float(self.q))
                 with self._Timed(self, 'gibbs_sweep'):
-                    L.gibbs_sweep(C.byref(a), 256 if K <= 48 else 1024, sp)
+                    L.gibbs_sweep(C.byref(a), 256 if K <= 256 else 1024, sp)
                 st = self._down(self.st)                       # synchronises the stream
                 flags = int(st[_lib.ST_FLAGS])
                 if flags & (_lib.STOP_TAPE_EMPTY | _lib.STOP_HANG):

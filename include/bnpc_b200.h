@@ -65,15 +65,21 @@ typedef struct {
     double  lnew;   /* new-cluster log posterior of this cell (libs/CRP.py:230-234)   */
     double  logit;  /* log((1-u)/u): a two-way draw picks the first option iff the
                        log-odds of the second over the first are below this           */
-    double  v_old;  /* ll of the cell under its current cluster ...                   */
-    double  v1, v2; /* ... and under its two best rival clusters (epoch columns)      */
+    double  v_old;  /* ll of the cell under its current cluster                       */
     int32_t cell;   /* cell index = permutation[t] (libs/CRP.py:260)                  */
     int32_t old;    /* its cluster id before the sweep                                 */
-    int32_t cols;   /* c_old | c1<<8 | c2<<16 | n<<24: ll columns of the above and the
-                       number n (saturating at 3) of clusters that can come within 40
-                       nats of the current one for ANY cluster sizes                   */
-    int32_t pad;
+    int32_t c_old;  /* ll column of that cluster in the current epoch                  */
+    int32_t n_cand; /* rival candidates (see bnpc_cand_t); BNPC_MAX_CAND+1 = too many  */
+    int32_t pad[4];
 } bnpc_visit_t;
+
+/* rival candidates of one visited cell (80 bytes): the clusters that can come within 40
+ * nats of the cell's current cluster for ANY cluster sizes, best first                 */
+#define BNPC_MAX_CAND 8
+typedef struct {
+    double   val[BNPC_MAX_CAND];   /* ll of the cell under the candidate cluster       */
+    uint16_t col[BNPC_MAX_CAND];   /* its ll column in the current epoch               */
+} bnpc_cand_t;
 
 int         bnpc_abi_version(void);
 const char* bnpc_last_error(void);
@@ -116,13 +122,14 @@ int bnpc_gibbs_prepare(const int32_t* perm, const double* u, const int32_t* assi
                        const int32_t* n1, const int32_t* n0, int N,
                        double c1, double c0, double lnew_prior,
                        bnpc_visit_t* visit, void* stream);
-/* After bnpc_ll_matrix of an epoch with at most 64 columns: fill v_old, v1, v2, cols of
- * the visit records [t0, t0+C).  A cluster k can rival the current cluster o of a cell
- * (come within 40 nats of it once the CRP weights log n_k are added) only if
- * ll_k > ll_o - 40 - slack with slack = log N, whatever the sizes are; the sequential
- * sweep then only looks at these candidates.                                        */
+/* After bnpc_ll_matrix of an epoch with at most 1024 columns: fill v_old, c_old, n_cand of
+ * the visit records [t0, t0+C) and their candidate records.  A cluster k can rival the
+ * current cluster o of a cell (come within 40 nats of it once the CRP weights log n_k are
+ * added) only if ll_k > ll_o - 40 - slack with slack = log N, whatever the sizes are; the
+ * sequential sweep then only looks at these candidates.                              */
 int bnpc_gibbs_candidates(const double* ll, int ldk, int K, const int32_t* col_of_id,
-                          bnpc_visit_t* visit_t0, int C, double slack, void* stream);
+                          bnpc_visit_t* visit_t0, bnpc_cand_t* cand_t0, int C, double slack,
+                          void* stream);
 /* Start of an epoch: rebuild cnt[] from the host-authoritative list
  * live[2*j] = id, live[2*j+1] = size (list order), set col_of_id[id] = j and
  * clear the epoch's extra-cluster bookkeeping.  first != 0 also resets the
@@ -141,7 +148,7 @@ typedef struct {
     double* lpx /* [MAX_EXTRA][M][2] */; double* llx /* [MAX_EXTRA][ldx] */; int32_t ldx;
     double* scratch /* [idcap+1] */;
     /* sweep inputs */
-    const bnpc_visit_t* visit; int32_t t_begin; int32_t t_end;
+    const bnpc_visit_t* visit; const bnpc_cand_t* cand; int32_t t_begin; int32_t t_end;
     const double* beta_rows /* parity tape [n_beta_rows][M] or NULL */; int32_t n_beta_rows;
     uint64_t seed; uint64_t stream_id;
     /* constants */

@@ -55,6 +55,8 @@ def timed(name, fn, n):
 
 def dev_step(i):
     ch.do_step()
+    if i % 5 == 0:
+        print('step', i, m.sweep_stats, 'K', len(m.cells_per_cluster))
     m.get_ll_full()
     m.get_lprior_full()
 
@@ -66,4 +68,5 @@ def host_step(i):
 
 timed('device-trace step', dev_step, args.steps)
 timed('host-trace step', host_step, args.steps)
-print('sweep stats', m.sweep_stats)
+print('sweep stats', m.sweep_stats, 'K', len(m.cells_per_cluster), 'FN', m.FN, 'FP', m.FP, 'alpha', m.DP_a)
+print('sizes', sorted(m.cells_per_cluster.values()))
