@@ -310,7 +310,9 @@ __global__ void gibbs_prepare_kernel(const int32_t* __restrict__ perm, const dou
     visit[t] = v;
 }
 
-// static rival candidates of every visited cell (see include/bnpc_b200.h)
+// static rival candidates of every visited cell (see include/bnpc_b200.h), kept in column order:
+// columns follow the list order at the start of the epoch and deaths preserve relative order,
+// so a walk over the candidates is a walk in list order.
 __global__ void gibbs_candidates_kernel(const double* __restrict__ ll, int ldk, int K,
                                         const int32_t* __restrict__ col_of_id,
                                         bnpc_visit_t* __restrict__ visit, bnpc_cand_t* __restrict__ cand,
@@ -319,10 +321,9 @@ __global__ void gibbs_candidates_kernel(const double* __restrict__ ll, int ldk, 
     if (r >= C) return;
     const double* row = ll + (long long)r * ldk;
     const int c_old = col_of_id[visit[r].old];
-    double val[BNPC_MAX_CAND];
-    int col[BNPC_MAX_CAND];
+    bnpc_cand_t out;
 #pragma unroll
-    for (int i = 0; i < BNPC_MAX_CAND; ++i) { val[i] = -BNPC_INF; col[i] = 0; }
+    for (int i = 0; i < BNPC_MAX_CAND; ++i) { out.val[i] = -BNPC_INF; out.col[i] = 0; }
     int n = BNPC_MAX_CAND + 1;
     double v_old = 0.0;
     if (c_old >= 0 && c_old < K) {
@@ -332,26 +333,16 @@ __global__ void gibbs_candidates_kernel(const double* __restrict__ ll, int ldk, 
         for (int k = 0; k < K; ++k) {
             const double v = row[k];
             if (k == c_old || !(v > thr)) continue;
-            ++n;
-            // insert into the best-first list (registers; fully unrolled bubble)
-            double cv = v;
-            int cc = k;
 #pragma unroll
-            for (int i = 0; i < BNPC_MAX_CAND; ++i) {
-                if (cv > val[i]) {
-                    const double tv = val[i]; const int tc = col[i];
-                    val[i] = cv; col[i] = cc; cv = tv; cc = tc;
-                }
-            }
+            for (int i = 0; i < BNPC_MAX_CAND; ++i)
+                if (i == n) { out.val[i] = v; out.col[i] = (uint16_t)k; }
+            ++n;
         }
         if (n > BNPC_MAX_CAND) n = BNPC_MAX_CAND + 1;
     }
     visit[r].v_old = v_old;
     visit[r].c_old = c_old;
     visit[r].n_cand = n;
-    bnpc_cand_t out;
-#pragma unroll
-    for (int i = 0; i < BNPC_MAX_CAND; ++i) { out.val[i] = val[i]; out.col[i] = (uint16_t)col[i]; }
     cand[r] = out;
 }
 
@@ -407,7 +398,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 #define SW_STAGE_CELLS 32
-#define SW_NSTAGE 4
+#define SW_NSTAGE 16
 #define SW_MAXL 1024          /* longest list / widest ll matrix the sequencer regime handles */
 #define SW_NOPT (BNPC_MAX_CAND + 2)   /* own cluster + candidates + one more (new cluster / newborn) */
 
@@ -426,6 +417,8 @@ struct SweepShared {
     int n_extra, births, moved, slow;
     int tmp_i, pick;
     int hang;
+    double d_move;                              // log-weight change of the last move (validity margins)
+    int mv_a, mv_b;                             // list positions touched by the last move
 };
 
 // One exact categorical draw for a list that fits a warp (libs/CRP.py:88-100 + numpy choice,
@@ -535,58 +528,64 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
 #define OUT_MOVE 1
 #define OUT_COMPLEX 2
 
-// Lane-local draw of one cell among its own cluster (option 0) and its rivals, every other
-// cluster sitting on the reference's 1e-15 floor.  Same arithmetic as _normalize_log_probs +
-// numpy choice (libs/CRP.py:88-100, 277), restricted to the options that are not on the floor.
-// Returns the list position picked, or -1 if u falls on a floored entry (exact path decides).
-__device__ __forceinline__ int local_draw(const int* pos, const double* l, int n_opt, int L, double u) {
+// Lane-local draw of one cell among `n_opt` options given IN LIST ORDER (its own cluster, its
+// rivals, possibly the new-cluster option last), every other cluster sitting on the reference's
+// 1e-15 floor: the arithmetic of _normalize_log_probs + numpy choice (libs/CRP.py:88-100, 277)
+// restricted to the options that are not on the floor.  Returns the index of the option picked
+// and *margin = distance of u from the nearer edge of the picked interval (in probability);
+// -1 if u falls on a floored entry.  Callers send margins below 1e-12 to the exact draw.
+__device__ __forceinline__ int local_draw(const int* pos, const double* l, int n_opt, int L, double u,
+                                          double* margin) {
     double lmax = l[0];
 #pragma unroll
     for (int i = 1; i < SW_NOPT; ++i) if (i < n_opt) lmax = fmax(lmax, l[i]);
-    double S = -1.0;
-#pragma unroll
-    for (int i = 0; i < SW_NOPT; ++i) if (i < n_opt) S += exp(l[i] - lmax);
-    if (S < 0.0) S = 0.0;
-    const double lse = log1p(S);
-    const double eps = exp(kLogEps);
-    double p[SW_NOPT];
-    double total = (double)(L + 1 - n_opt) * eps;
+    double e[SW_NOPT];
+    double Z = 0.0;
 #pragma unroll
     for (int i = 0; i < SW_NOPT; ++i) {
-        p[i] = 0.0;
-        if (i < n_opt) {
-            p[i] = exp(fmin(fmax(l[i] - lmax - lse, kLogEps), 0.0));
-            total += p[i];
+        e[i] = 0.0;
+        if (i < n_opt) { e[i] = exp(l[i] - lmax); Z += e[i]; }
+    }
+    const double eps = exp(kLogEps);
+    const double rz = 1.0 / Z;
+    double total = (double)(L + 1 - n_opt) * eps;
+#pragma unroll
+    for (int i = 0; i < SW_NOPT; ++i)
+        if (i < n_opt) { e[i] = fmin(fmax(e[i] * rz, eps), 1.0); total += e[i]; }
+    const double ut = u * total;
+    double cdf = 0.0;
+    int prev = -1, pick = -1;
+    *margin = 0.0;
+#pragma unroll
+    for (int i = 0; i < SW_NOPT; ++i) {
+        if (i < n_opt && pick == -1) {
+            cdf += (double)(pos[i] - prev - 1) * eps;          // floored entries before option i
+            if (cdf > ut) { pick = -2; }
+            else {
+                const double lo = cdf;
+                cdf += e[i];
+                if (cdf > ut) { pick = i; *margin = fmin(ut - lo, cdf - ut) / total; }
+            }
+            prev = pos[i];
         }
     }
-    // walk the options in list order; floored entries between them take eps each
-    double cdf = 0.0;
-    int prev = -1;
-    for (int step = 0; step < n_opt; ++step) {
-        int bpos = 0x7fffffff;
-        double pb = 0.0;
-#pragma unroll
-        for (int i = 0; i < SW_NOPT; ++i)
-            if (i < n_opt && pos[i] > prev && pos[i] < bpos) { bpos = pos[i]; pb = p[i]; }
-        cdf += (double)(bpos - prev - 1) * eps;
-        if (cdf / total > u) return -1;
-        cdf += pb;
-        if (cdf / total > u) return bpos;
-        prev = bpos;
-    }
-    return -1;
+    return pick < 0 ? -1 : pick;
 }
 
 // Sequencer regime (lists of at most SW_MAXL clusters), run by warp 0.  The sweep is
 // sequential, but a cell that ends up where it was leaves every size unchanged, so 32
 // consecutive cells are scored in parallel (lane <-> cell) against the current sizes;
-// everything before the first cell that does not provably stay is then exact, that cell is
-// resolved, and only the cells after it are scored again.  Scoring looks only at the cell's
-// static rival candidates (bnpc_gibbs_candidates) plus clusters born in this epoch: no rival
-// within 40 nats => the draw returns the current cluster unless u is within 1e-12 of 0 or 1;
-// one rival => two-way draw by comparing log-odds with logit(u) (1e-3 guard band); otherwise a
-// lane-local draw over the rivals.  Cluster death, a new cluster, too many rivals or u on a
-// floored entry go through the exact draw over the whole list (warp-cooperative for lists of
+// everything before the first cell that does not provably stay is then exact and that cell is
+// resolved.  A move changes two sizes by one, i.e. two log weights by d ~ 1/n: every later
+// lane keeps a conservative validity margin for its own decision (in nats for "no rival" and
+// two-way decisions, in probability for multi-way draws), decrements it by the worst-case
+// effect of the move if the moved clusters are among its options, and is scored again only
+// when the margin is used up.  Scoring looks only at the cell's static rival candidates
+// (bnpc_gibbs_candidates) plus clusters born in this epoch: no rival within 40 nats => the
+// draw returns the current cluster unless u is within 1e-12 of 0 or 1; one rival => two-way
+// draw by comparing log-odds with logit(u) (1e-3 guard band); otherwise a lane-local draw.
+// Cluster death, a new cluster, too many rivals, u on a floored entry or within 1e-12 of an
+// interval edge go through the exact draw over the whole list (warp-cooperative for lists of
 // up to 31 clusters, CTA-wide otherwise).
 __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
     const int lane = threadIdx.x;
@@ -653,64 +652,95 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
         const long long tx = ts + lane - a.t_epoch0;
 
         int lo_lane = max(0, t0 - ts);
-        bool need_eval = true;
+        bool need_eval = lane >= lo_lane && lane < nc;      // per lane
         int outcome = OUT_STAY, to_pos = -1, p_old = -1;
+        double slack_nat = BNPC_INF, slack_p = BNPC_INF;    // validity margins of `outcome`
+        unsigned long long bloom = 0ull;                    // list positions (mod 64) it depends on
         while (lo_lane < nc) {
             if (need_eval) {
+                need_eval = false;
                 outcome = OUT_STAY;
-                if (lane >= lo_lane && lane < nc) {
-                    const int n_static = v.n_cand;
-                    p_old = (v.c_old >= 0 && v.c_old < SW_MAXL) ? sh.s_pos_of_col[v.c_old] : -1;
-                    if (n_static > BNPC_MAX_CAND || p_old < 0 || sh.s_cnt[p_old] == 1 ||
-                        sh.s_id[p_old] != v.old) {
+                slack_nat = BNPC_INF; slack_p = BNPC_INF; bloom = 0ull;
+                const int n_static = v.n_cand;
+                p_old = (v.c_old >= 0 && v.c_old < SW_MAXL) ? sh.s_pos_of_col[v.c_old] : -1;
+                if (n_static > BNPC_MAX_CAND || p_old < 0 || sh.s_cnt[p_old] == 1 ||
+                    sh.s_id[p_old] != v.old) {
+                    outcome = OUT_COMPLEX;
+                } else {
+                    // options in list order: candidates are in column order, the own cluster is
+                    // slotted in by its column, newborn clusters and the new-cluster option follow
+                    int pos[SW_NOPT];
+                    double l[SW_NOPT];
+#pragma unroll
+                    for (int i = 0; i < SW_NOPT; ++i) { pos[i] = -1; l[i] = -BNPC_INF; }
+                    int n_opt = 0, i_old = 0;
+                    const double l_old = v.v_old + sh.s_lcm1[p_old];
+                    const double cut = l_old - 40.0;
+                    double best_below = -BNPC_INF;            // best rival that is NOT within 40 nats
+                    bool over = false, own_in = false;
+                    bloom = 1ull << (p_old & 63);
+                    auto put = [&](int p, double lv) {
+                        if (n_opt >= SW_NOPT) over = true;
+#pragma unroll
+                        for (int i = 0; i < SW_NOPT; ++i)
+                            if (i == n_opt) { pos[i] = p; l[i] = lv; }
+                        ++n_opt;
+                    };
+                    auto rival = [&](int p, double lv) {
+                        if (lv > cut) put(p, lv);
+                        else best_below = fmax(best_below, lv);
+                    };
+#pragma unroll
+                    for (int i = 0; i < BNPC_MAX_CAND; ++i) {
+                        if (i < n_static) {
+                            const int ci = cd->col[i];
+                            if (!own_in && ci > v.c_old) { i_old = n_opt; put(p_old, l_old); own_in = true; }
+                            const int pi = sh.s_pos_of_col[ci];
+                            if (pi >= 0) {
+                                bloom |= 1ull << (pi & 63);
+                                rival(pi, cd->val[i] + sh.s_lc[pi]);
+                            }
+                        }
+                    }
+                    if (!own_in) { i_old = n_opt; put(p_old, l_old); }
+                    for (int e = 0; e < n_extra; ++e) {       // clusters born in this epoch
+                        const int pe = sh.s_xpos[e];
+                        if (pe >= 0) {
+                            bloom |= 1ull << (pe & 63);
+                            rival(pe, a.llx[(long long)e * a.ldx + tx] + sh.s_lc[pe]);
+                        }
+                    }
+                    rival(L, v.lnew);
+                    if (over) {
                         outcome = OUT_COMPLEX;
+                    } else if (n_opt == 1) {
+                        outcome = (v.u > 1e-12 && v.u < 1.0 - 1e-12) ? OUT_STAY : OUT_COMPLEX;
+                        slack_nat = cut - best_below;
                     } else {
-                        int pos[SW_NOPT];
-                        double l[SW_NOPT];
-#pragma unroll
-                        for (int i = 0; i < SW_NOPT; ++i) { pos[i] = -1; l[i] = -BNPC_INF; }
-                        int n_opt = 1;
-                        pos[0] = p_old;
-                        l[0] = v.v_old + sh.s_lcm1[p_old];
-                        const double cut = l[0] - 40.0;
-                        bool over = false;
-                        auto add = [&](int p, double lv) {
-                            if (lv > cut) {
-                                if (n_opt >= SW_NOPT) over = true;
-#pragma unroll
-                                for (int i = 1; i < SW_NOPT; ++i)
-                                    if (i == n_opt) { pos[i] = p; l[i] = lv; }
-                                ++n_opt;
-                            }
-                        };
-#pragma unroll
-                        for (int i = 0; i < BNPC_MAX_CAND; ++i) {
-                            if (i < n_static) {
-                                const int pi = sh.s_pos_of_col[cd->col[i]];
-                                if (pi >= 0) add(pi, cd->val[i] + sh.s_lc[pi]);
+                        int pick = -1;
+                        if (n_opt == 2 && pos[1] < L && v.u > 1e-9 && v.u < 1.0 - 1e-9) {
+                            // two-way draw: log-odds of the later position over the earlier one
+                            const double gap = fabs((l[1] - l[0]) - v.logit);
+                            if (gap > 1e-3) {
+                                pick = ((l[1] - l[0]) < v.logit) ? 0 : 1;
+                                slack_nat = fmin(gap - 1e-3, cut - best_below);
                             }
                         }
-                        for (int e = 0; e < n_extra; ++e) {       // clusters born in this epoch
-                            const int pe = sh.s_xpos[e];
-                            if (pe >= 0) add(pe, a.llx[(long long)e * a.ldx + tx] + sh.s_lc[pe]);
+                        if (pick < 0) {
+                            double mg;
+                            pick = local_draw(pos, l, n_opt, L, v.u, &mg);
+                            slack_p = mg - 1e-12;
+                            slack_nat = cut - best_below;
+                            if (slack_p <= 0.0) pick = -1;
                         }
-                        add(L, v.lnew);
-                        if (over) {
-                            outcome = OUT_COMPLEX;
-                        } else if (n_opt == 1) {
-                            outcome = (v.u > 1e-12 && v.u < 1.0 - 1e-12) ? OUT_STAY : OUT_COMPLEX;
-                        } else {
-                            int pick = -1;
-                            if (n_opt == 2 && v.u > 1e-9 && v.u < 1.0 - 1e-9) {
-                                // log-odds of the later list position over the earlier one
-                                const double d_ab = (pos[1] > p_old) ? (l[1] - l[0]) : (l[0] - l[1]);
-                                if (fabs(d_ab - v.logit) > 1e-3)
-                                    pick = (d_ab < v.logit) ? min(p_old, pos[1]) : max(p_old, pos[1]);
-                            }
-                            if (pick < 0) pick = local_draw(pos, l, n_opt, L, v.u);
-                            if (pick == p_old) outcome = OUT_STAY;
-                            else if (pick < 0 || pick >= L) outcome = OUT_COMPLEX;
-                            else { outcome = OUT_MOVE; to_pos = pick; }
+                        if (pick < 0) outcome = OUT_COMPLEX;
+                        else if (pick == i_old) outcome = OUT_STAY;
+                        else {
+                            int pp = -1;
+#pragma unroll
+                            for (int i = 0; i < SW_NOPT; ++i) if (i == pick) pp = pos[i];
+                            if (pp >= L) outcome = OUT_COMPLEX;      // opens a new cluster
+                            else { outcome = OUT_MOVE; to_pos = pp; }
                         }
                     }
                 }
@@ -719,7 +749,6 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
             if (!pend) break;
             const int f = __ffs(pend) - 1;
             const int of = __shfl_sync(FULL, outcome, f);
-            int status;
             if (of == OUT_MOVE) {
                 const int kf = __shfl_sync(FULL, p_old, f), rf = __shfl_sync(FULL, to_pos, f);
                 // sizes n_old-1 and n_new+1: one of the two log weights of each cluster is the
@@ -727,22 +756,32 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
                 if (lane == 0) {
                     const int c_old = sh.s_cnt[kf] - 1;
                     const double w = sh.s_lcm1[kf];
+                    const double w2 = log((double)(c_old - 1)) - a.c_norm;
                     sh.s_cnt[kf] = c_old;
                     sh.s_lc[kf] = w;
-                    sh.s_lcm1[kf] = log((double)(c_old - 1)) - a.c_norm;
+                    sh.s_lcm1[kf] = w2;
+                    sh.d_move = w - w2;                     // largest weight change of the shrinking cluster
                     a.cnt[sh.s_id[kf]] = c_old;
                     a.assign[vis[f].cell] = sh.s_id[rf];
                 } else if (lane == 1) {
                     const int c_new = sh.s_cnt[rf] + 1;
                     const double w = sh.s_lc[rf];
+                    const double w0 = sh.s_lcm1[rf];
                     sh.s_cnt[rf] = c_new;
                     sh.s_lcm1[rf] = w;
                     sh.s_lc[rf] = log((double)c_new) - a.c_norm;
-                    a.cnt[sh.s_id[rf]] = c_new;
+                    sh.red[39] = w - w0;                    // largest weight change of the growing cluster
                 }
                 __syncwarp();
                 ++moved;
-                status = 1;
+                // validity of the decisions of the lanes still to come
+                const double d = sh.d_move + sh.red[39];
+                if (lane > f && lane < nc && ((bloom >> (kf & 63)) | (bloom >> (rf & 63))) & 1ull) {
+                    slack_nat -= d;
+                    slack_p -= expm1(2.0 * d);
+                    if (!(slack_nat > 0.0) || !(slack_p > 0.0)) need_eval = true;
+                }
+                lo_lane = f + 1;
             } else {
                 ++slow;
                 if (L > 31) {                       // CTA-wide exact draw, then come back
@@ -751,17 +790,17 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
                     leave = true;
                     break;
                 }
-                status = sweep_exact_cell(a, sh, vis[f], a.ll + (long long)(ts + f - a.t_epoch0) * ldk,
-                                          ts + f, L);
+                const int status = sweep_exact_cell(a, sh, vis[f],
+                                                    a.ll + (long long)(ts + f - a.t_epoch0) * ldk, ts + f, L);
                 if (status) ++moved;
                 if (status == 2) {
                     next_t = ts + f + 1;
                     leave = true;
                     break;
                 }
+                lo_lane = f + 1;
+                if (status != 0) need_eval = lane >= lo_lane && lane < nc;   // structure may have changed
             }
-            lo_lane = f + 1;
-            need_eval = (status != 0);
         }
         __syncwarp();
         if (!leave && lane == 0 && issued < n_stages) issue(issued);

@@ -434,7 +434,7 @@ class DeviceCRP:
                     logn=sh.logn.data_ptr(), c_norm=c_norm, FN=FN, FP=FP,
                     p=float(self.p), q=float(self.q))
                 with self._Timed(self, 'gibbs_sweep'):
-                    L.gibbs_sweep(C.byref(a), 256 if K <= 256 else 1024, sp)
+                    L.gibbs_sweep(C.byref(a), 256 if K < 1000 else 1024, sp)
                 st = self._down(self.st)                       # synchronises the stream
                 flags = int(st[_lib.ST_FLAGS])
                 if flags & (_lib.STOP_TAPE_EMPTY | _lib.STOP_HANG):
