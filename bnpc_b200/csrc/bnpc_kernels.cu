@@ -770,7 +770,8 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
                     sh.s_cnt[rf] = c_new;
                     sh.s_lcm1[rf] = w;
                     sh.s_lc[rf] = log((double)c_new) - a.c_norm;
-                    sh.red[39] = w - w0;                    // largest weight change of the growing cluster
+                    a.cnt[sh.s_id[rf]] = c_new;
+                    sh.red[39] = w - w0;                   // largest weight change of the growing cluster
                 }
                 __syncwarp();
                 ++moved;
