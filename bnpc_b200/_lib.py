@@ -25,7 +25,7 @@ ST_WORDS = 16
 STOP_EXTRA_FULL, STOP_REPACK, STOP_TAPE_EMPTY, STOP_CAPACITY, STOP_HANG = 1, 2, 4, 8, 0x100
 VISIT_BYTES = 64
 VISIT_CELL_OFFSET = 32
-CAND_BYTES = 80
+CAND_BYTES = 96
 MAX_LIST = 1024          # longest cluster list the sequencer regime of the sweep handles
 
 
@@ -76,7 +76,7 @@ SIGNATURES = {
     'bnpc_logprob_tables': [_P, _P, _I, _I, _D, _D, _P, _P],
     'bnpc_ll_matrix': [_P, _P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _P],
     'bnpc_gibbs_prepare': [_P, _P, _P, _P, _P, _I, _D, _D, _D, _P, _P],
-    'bnpc_gibbs_candidates': [_P, _I, _I, _P, _P, _P, _I, _D, _P],
+    'bnpc_gibbs_candidates': [_P, _I, _I, _P, _P, _P, _I, _D, _D, _P],
     'bnpc_gibbs_epoch_begin': [_P, _I, _P, _P, _P, _I, _P, _I, _P],
     'bnpc_gibbs_sweep': [C.POINTER(SweepArgs), _I, _P],
     'bnpc_group_members': [_P, _I, _P, _P, _P, _I, _P, _P],

@@ -300,49 +300,65 @@ __global__ void gibbs_prepare_kernel(const int32_t* __restrict__ perm, const dou
     v.u = u[t];
     // popcount form of libs/CRP.py:230-234: every observed 1 contributes c1, every 0 c0
     v.lnew = ((double)n1[c] * c1 + (double)n0[c] * c0) + lnew_prior;
-    v.logit = log1p(-v.u) - log(v.u);
-    v.v_old = 0.0;
+    v.e_new = 0.0;
+    v.ref = 0.0;
     v.cell = c;
     v.old = assign[c];
     v.c_old = -1;
-    v.n_cand = BNPC_MAX_CAND + 1;     // "unknown rivals" until bnpc_gibbs_candidates has run
-    v.pad[0] = v.pad[1] = v.pad[2] = v.pad[3] = 0;
+    v.n_opt = BNPC_MAX_OPT + 1;       // "unknown rivals" until bnpc_gibbs_candidates has run
+    v.i_old = 0;
+    v.pad[0] = v.pad[1] = v.pad[2] = 0;
     visit[t] = v;
 }
 
-// static rival candidates of every visited cell (see include/bnpc_b200.h), kept in column order:
-// columns follow the list order at the start of the epoch and deaths preserve relative order,
-// so a walk over the candidates is a walk in list order.
+// static options of every visited cell (see include/bnpc_b200.h), kept in column order: columns
+// follow the list order at the start of the epoch and deaths preserve relative order, so a walk
+// over the options is a walk in list order.
 __global__ void gibbs_candidates_kernel(const double* __restrict__ ll, int ldk, int K,
                                         const int32_t* __restrict__ col_of_id,
                                         bnpc_visit_t* __restrict__ visit, bnpc_cand_t* __restrict__ cand,
-                                        int C, double slack) {
+                                        int C, double slack, double c_norm) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= C) return;
     const double* row = ll + (long long)r * ldk;
     const int c_old = col_of_id[visit[r].old];
+    const double lnew_ll = visit[r].lnew + c_norm;          // ll_new + log(alpha)
     bnpc_cand_t out;
+    double val[BNPC_MAX_OPT];
 #pragma unroll
-    for (int i = 0; i < BNPC_MAX_CAND; ++i) { out.val[i] = -BNPC_INF; out.col[i] = 0; }
-    int n = BNPC_MAX_CAND + 1;
-    double v_old = 0.0;
+    for (int i = 0; i < BNPC_MAX_OPT; ++i) { out.e[i] = 0.0; out.col[i] = 0; val[i] = -BNPC_INF; }
+    out.pad[0] = out.pad[1] = out.pad[2] = 0;
+    int n = BNPC_MAX_OPT + 1, i_old = 0;
+    double ref = 0.0, e_new = 0.0;
     if (c_old >= 0 && c_old < K) {
-        v_old = row[c_old];
+        const double v_old = row[c_old];
         const double thr = v_old - 40.0 - slack;
         n = 0;
+        ref = fmax(v_old, lnew_ll);
         for (int k = 0; k < K; ++k) {
             const double v = row[k];
-            if (k == c_old || !(v > thr)) continue;
+            if (k != c_old && !(v > thr)) continue;
+            if (k == c_old) i_old = n;
 #pragma unroll
-            for (int i = 0; i < BNPC_MAX_CAND; ++i)
-                if (i == n) { out.val[i] = v; out.col[i] = (uint16_t)k; }
+            for (int i = 0; i < BNPC_MAX_OPT; ++i)
+                if (i == n) { val[i] = v; out.col[i] = (uint16_t)k; }
+            ref = fmax(ref, v);
             ++n;
         }
-        if (n > BNPC_MAX_CAND) n = BNPC_MAX_CAND + 1;
+        if (n > BNPC_MAX_OPT) {
+            n = BNPC_MAX_OPT + 1;
+        } else {
+#pragma unroll
+            for (int i = 0; i < BNPC_MAX_OPT; ++i)
+                if (i < n) out.e[i] = exp(val[i] - ref);
+            e_new = exp(lnew_ll - ref);
+        }
     }
-    visit[r].v_old = v_old;
+    visit[r].e_new = e_new;
+    visit[r].ref = ref;
     visit[r].c_old = c_old;
-    visit[r].n_cand = n;
+    visit[r].n_opt = n;
+    visit[r].i_old = i_old;
     cand[r] = out;
 }
 
@@ -400,7 +416,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 #define SW_STAGE_CELLS 32
 #define SW_NSTAGE 16
 #define SW_MAXL 1024          /* longest list / widest ll matrix the sequencer regime handles */
-#define SW_NOPT (BNPC_MAX_CAND + 2)   /* own cluster + candidates + one more (new cluster / newborn) */
 
 struct SweepShared {
     alignas(128) bnpc_visit_t vis_stage[SW_NSTAGE][SW_STAGE_CELLS];
@@ -408,7 +423,6 @@ struct SweepShared {
     alignas(8) uint64_t bar[SW_NSTAGE];
     double red[40];
     // the live list (position j <-> insertion order) while it has at most SW_MAXL entries
-    double s_lc[SW_MAXL], s_lcm1[SW_MAXL];      // log CRP weight at the current size / at size-1
     int s_id[SW_MAXL], s_cnt[SW_MAXL], s_src[SW_MAXL];   // id, size, ll column (>=0) or -(extra+2)
     int s_pos_of_col[SW_MAXL];                  // ll column -> list position, -1 once the cluster died
     int s_xpos[BNPC_MAX_EXTRA];                 // cluster born in this epoch -> list position or -1
@@ -417,8 +431,6 @@ struct SweepShared {
     int n_extra, births, moved, slow;
     int tmp_i, pick;
     int hang;
-    double d_move;                              // log-weight change of the last move (validity margins)
-    int mv_a, mv_b;                             // list positions touched by the last move
 };
 
 // One exact categorical draw for a list that fits a warp (libs/CRP.py:88-100 + numpy choice,
@@ -460,11 +472,7 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
                                 const double* row, int t, int& L) {
     const int lane = threadIdx.x;
     int id = -1, cnt = 0, src = -1;
-    double lc = 0.0, lcm1 = 0.0;
-    if (lane < L) {
-        id = sh.s_id[lane]; cnt = sh.s_cnt[lane]; src = sh.s_src[lane];
-        lc = sh.s_lc[lane]; lcm1 = sh.s_lcm1[lane];
-    }
+    if (lane < L) { id = sh.s_id[lane]; cnt = sh.s_cnt[lane]; src = sh.s_src[lane]; }
     const int old = v.old;
     const unsigned om = __ballot_sync(FULL, lane < L && id == old);
     int lo = __ffs(om) - 1;
@@ -473,10 +481,9 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
         // the cluster dies with its last cell: close the gap, list order stays insertion order
         const int id2 = __shfl_down_sync(FULL, id, 1), cnt2 = __shfl_down_sync(FULL, cnt, 1),
                   src2 = __shfl_down_sync(FULL, src, 1);
-        const double lc2 = __shfl_down_sync(FULL, lc, 1), lcm2 = __shfl_down_sync(FULL, lcm1, 1);
         if (lane == lo) a.cnt[old] = 0;
         if (lane >= lo && lane < L - 1) {
-            id = id2; cnt = cnt2; src = src2; lc = lc2; lcm1 = lcm2;
+            id = id2; cnt = cnt2; src = src2;
             a.lst[lane] = id;
         } else if (lane == L - 1) {
             id = -1; cnt = 0; src = -1;
@@ -484,17 +491,15 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
         --L;
         lo = -1;
         __syncwarp();
-        if (lane <= L) {
-            sh.s_id[lane] = id; sh.s_cnt[lane] = cnt; sh.s_src[lane] = src;
-            sh.s_lc[lane] = lc; sh.s_lcm1[lane] = lcm1;
-        }
+        if (lane <= L) { sh.s_id[lane] = id; sh.s_cnt[lane] = cnt; sh.s_src[lane] = src; }
         __syncwarp();
         sweep_rebuild_maps(sh, L);
     }
     double l = -BNPC_INF;
     if (lane < L) {
         const double val = (src >= 0) ? row[src] : a.llx[(long long)(-src - 2) * a.ldx + (t - a.t_epoch0)];
-        l = val + ((lane == lo) ? lcm1 : lc);
+        // CRP weight log n - log(N-1+alpha) with the cell itself taken out (libs/CRP.py:83-85,262-270)
+        l = val + (a.logn[(lane == lo) ? cnt - 1 : cnt] - a.c_norm);
     } else if (lane == L) {
         l = v.lnew;
     }
@@ -502,10 +507,8 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
     if (pick == lo) return 0;
     if (lo >= 0 && lane == lo) {                    // leave the old cluster
         --cnt;
-        lc = log((double)cnt) - a.c_norm;
-        lcm1 = log((double)(cnt - 1)) - a.c_norm;
         a.cnt[id] = cnt;
-        sh.s_cnt[lane] = cnt; sh.s_lc[lane] = lc; sh.s_lcm1[lane] = lcm1;
+        sh.s_cnt[lane] = cnt;
     }
     if (pick == L) {
         if (lane == 0) { sh.pending = 1; sh.birth_cell = v.cell; sh.birth_t = t; }
@@ -514,11 +517,9 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
     }
     if (lane == pick) {
         ++cnt;
-        lc = log((double)cnt) - a.c_norm;
-        lcm1 = log((double)(cnt - 1)) - a.c_norm;
         a.cnt[id] = cnt;
         a.assign[v.cell] = id;
-        sh.s_cnt[lane] = cnt; sh.s_lc[lane] = lc; sh.s_lcm1[lane] = lcm1;
+        sh.s_cnt[lane] = cnt;
     }
     __syncwarp();
     return 1;
@@ -527,66 +528,24 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
 #define OUT_STAY 0
 #define OUT_MOVE 1
 #define OUT_COMPLEX 2
-
-// Lane-local draw of one cell among `n_opt` options given IN LIST ORDER (its own cluster, its
-// rivals, possibly the new-cluster option last), every other cluster sitting on the reference's
-// 1e-15 floor: the arithmetic of _normalize_log_probs + numpy choice (libs/CRP.py:88-100, 277)
-// restricted to the options that are not on the floor.  Returns the index of the option picked
-// and *margin = distance of u from the nearer edge of the picked interval (in probability);
-// -1 if u falls on a floored entry.  Callers send margins below 1e-12 to the exact draw.
-__device__ __forceinline__ int local_draw(const int* pos, const double* l, int n_opt, int L, double u,
-                                          double* margin) {
-    double lmax = l[0];
-#pragma unroll
-    for (int i = 1; i < SW_NOPT; ++i) if (i < n_opt) lmax = fmax(lmax, l[i]);
-    double e[SW_NOPT];
-    double Z = 0.0;
-#pragma unroll
-    for (int i = 0; i < SW_NOPT; ++i) {
-        e[i] = 0.0;
-        if (i < n_opt) { e[i] = exp(l[i] - lmax); Z += e[i]; }
-    }
-    const double eps = exp(kLogEps);
-    const double rz = 1.0 / Z;
-    double total = (double)(L + 1 - n_opt) * eps;
-#pragma unroll
-    for (int i = 0; i < SW_NOPT; ++i)
-        if (i < n_opt) { e[i] = fmin(fmax(e[i] * rz, eps), 1.0); total += e[i]; }
-    const double ut = u * total;
-    double cdf = 0.0;
-    int prev = -1, pick = -1;
-    *margin = 0.0;
-#pragma unroll
-    for (int i = 0; i < SW_NOPT; ++i) {
-        if (i < n_opt && pick == -1) {
-            cdf += (double)(pos[i] - prev - 1) * eps;          // floored entries before option i
-            if (cdf > ut) { pick = -2; }
-            else {
-                const double lo = cdf;
-                cdf += e[i];
-                if (cdf > ut) { pick = i; *margin = fmin(ut - lo, cdf - ut) / total; }
-            }
-            prev = pos[i];
-        }
-    }
-    return pick < 0 ? -1 : pick;
-}
+#define SW_GUARD 1e-10        /* draws closer than this (in probability) to an interval edge go exact */
 
 // Sequencer regime (lists of at most SW_MAXL clusters), run by warp 0.  The sweep is
 // sequential, but a cell that ends up where it was leaves every size unchanged, so 32
 // consecutive cells are scored in parallel (lane <-> cell) against the current sizes;
-// everything before the first cell that does not provably stay is then exact and that cell is
-// resolved.  A move changes two sizes by one, i.e. two log weights by d ~ 1/n: every later
-// lane keeps a conservative validity margin for its own decision (in nats for "no rival" and
-// two-way decisions, in probability for multi-way draws), decrements it by the worst-case
-// effect of the move if the moved clusters are among its options, and is scored again only
-// when the margin is used up.  Scoring looks only at the cell's static rival candidates
-// (bnpc_gibbs_candidates) plus clusters born in this epoch: no rival within 40 nats => the
-// draw returns the current cluster unless u is within 1e-12 of 0 or 1; one rival => two-way
-// draw by comparing log-odds with logit(u) (1e-3 guard band); otherwise a lane-local draw.
-// Cluster death, a new cluster, too many rivals, u on a floored entry or within 1e-12 of an
-// interval edge go through the exact draw over the whole list (warp-cooperative for lists of
-// up to 31 clusters, CTA-wide otherwise).
+// everything before the first cell that does not stay is then exact and that cell is resolved.
+// Scoring looks only at the cell's static options (bnpc_gibbs_candidates) plus clusters born in
+// this epoch; every other cluster sits on the reference's 1e-15 probability floor.  Restricted to
+// the options the draw of _normalize_log_probs + numpy choice (libs/CRP.py:88-100, 277) is LINEAR
+// in the cluster sizes: weight_i = n_i * exp(ll_i - ref), the new-cluster option weighs
+// alpha * exp(ll_new - ref), and the pick is the first option whose running sum exceeds
+// u * total -- integer sizes times per-cell constants, no transcendental in the sequential part.
+// A move changes two sizes; later lanes are scored again only if one of their options was
+// touched.  The linear form and the reference's log-space arithmetic differ by rounding
+// (~1e-13) and by the floored entries (<= 1024e-15): whenever u is within SW_GUARD of an
+// interval edge, and for cluster death, a new cluster, or more than BNPC_MAX_CAND rivals, the
+// cell goes through the exact draw over the whole list in the reference's own arithmetic
+// (warp-cooperative for lists of up to 31 clusters, CTA-wide otherwise).
 __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
     const int lane = threadIdx.x;
     int L = sh.L;
@@ -596,10 +555,7 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
 
     for (int j = lane; j < L; j += 32) {
         const int id = a.lst[j];
-        const int c = a.cnt[id];
-        sh.s_id[j] = id; sh.s_cnt[j] = c; sh.s_src[j] = a.col_of_id[id];
-        sh.s_lc[j] = a.logn[c] - a.c_norm;
-        sh.s_lcm1[j] = a.logn[c - 1] - a.c_norm;
+        sh.s_id[j] = id; sh.s_cnt[j] = a.cnt[id]; sh.s_src[j] = a.col_of_id[id];
     }
     if (lane == 0) {
         for (int s = 0; s < SW_NSTAGE; ++s) mbar_init(&sh.bar[s], 1);
@@ -610,7 +566,7 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
     sweep_rebuild_maps(sh, L);
     const int n_extra = sh.n_extra;
 
-    // stages = 32 consecutive visit + candidate records, streamed into shared memory by bulk
+    // stages = 32 consecutive visit + option records, streamed into shared memory by bulk
     // async copies (TMA engine) NSTAGE ahead of the sequencer
     const int s_first = (t0 - a.t_epoch0) / SW_STAGE_CELLS;
     const int s_last = (a.t_end - 1 - a.t_epoch0) / SW_STAGE_CELLS;
@@ -648,100 +604,96 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
         const bnpc_visit_t* vis = sh.vis_stage[slot];
         const int my = lane < nc ? lane : 0;
         const bnpc_visit_t v = vis[my];
-        const bnpc_cand_t* cd = &sh.cand_stage[slot][my];
         const long long tx = ts + lane - a.t_epoch0;
+        // the lane's options live in registers for the whole stage
+        double e[BNPC_MAX_OPT];
+        int col[BNPC_MAX_OPT];
+        {
+            const bnpc_cand_t* cd = &sh.cand_stage[slot][my];
+#pragma unroll
+            for (int i = 0; i < BNPC_MAX_OPT; ++i) { e[i] = cd->e[i]; col[i] = cd->col[i]; }
+        }
+        const int n_opt = v.n_opt, i_old = v.i_old;
+        // warp-uniform bound of the option loops; largest option weight of the lane
+        int n_max = (lane < nc && n_opt <= BNPC_MAX_OPT) ? n_opt : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(FULL, n_max, o));
+        double e_max = 0.0;
+#pragma unroll
+        for (int i = 0; i < BNPC_MAX_OPT; ++i) e_max = fmax(e_max, e[i]);
 
         int lo_lane = max(0, t0 - ts);
         bool need_eval = lane >= lo_lane && lane < nc;      // per lane
         int outcome = OUT_STAY, to_pos = -1, p_old = -1;
-        double slack_nat = BNPC_INF, slack_p = BNPC_INF;    // validity margins of `outcome`
         unsigned long long bloom = 0ull;                    // list positions (mod 64) it depends on
+        double slack = 0.0;                                 // validity margin of `outcome` (weight units)
+        double e_lim = e_max;                               // largest weight among all its options
         while (lo_lane < nc) {
             if (need_eval) {
                 need_eval = false;
-                outcome = OUT_STAY;
-                slack_nat = BNPC_INF; slack_p = BNPC_INF; bloom = 0ull;
-                const int n_static = v.n_cand;
-                p_old = (v.c_old >= 0 && v.c_old < SW_MAXL) ? sh.s_pos_of_col[v.c_old] : -1;
-                if (n_static > BNPC_MAX_CAND || p_old < 0 || sh.s_cnt[p_old] == 1 ||
-                    sh.s_id[p_old] != v.old) {
-                    outcome = OUT_COMPLEX;
-                } else {
-                    // options in list order: candidates are in column order, the own cluster is
-                    // slotted in by its column, newborn clusters and the new-cluster option follow
-                    int pos[SW_NOPT];
-                    double l[SW_NOPT];
+                outcome = OUT_COMPLEX;
+                bloom = 0ull;
+                to_pos = -1;
+                slack = 0.0;
+                p_old = (n_opt <= BNPC_MAX_OPT) ? sh.s_pos_of_col[v.c_old] : -1;
+                if (p_old >= 0 && sh.s_cnt[p_old] > 1 && sh.s_id[p_old] == v.old) {
+                    double cum[BNPC_MAX_OPT];
+                    int pos[BNPC_MAX_OPT];
+                    double S = 0.0;
 #pragma unroll
-                    for (int i = 0; i < SW_NOPT; ++i) { pos[i] = -1; l[i] = -BNPC_INF; }
-                    int n_opt = 0, i_old = 0;
-                    const double l_old = v.v_old + sh.s_lcm1[p_old];
-                    const double cut = l_old - 40.0;
-                    double best_below = -BNPC_INF;            // best rival that is NOT within 40 nats
-                    bool over = false, own_in = false;
-                    bloom = 1ull << (p_old & 63);
-                    auto put = [&](int p, double lv) {
-                        if (n_opt >= SW_NOPT) over = true;
+                    for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+                        cum[i] = 0.0; pos[i] = -1;
+                    }
 #pragma unroll
-                        for (int i = 0; i < SW_NOPT; ++i)
-                            if (i == n_opt) { pos[i] = p; l[i] = lv; }
-                        ++n_opt;
-                    };
-                    auto rival = [&](int p, double lv) {
-                        if (lv > cut) put(p, lv);
-                        else best_below = fmax(best_below, lv);
-                    };
-#pragma unroll
-                    for (int i = 0; i < BNPC_MAX_CAND; ++i) {
-                        if (i < n_static) {
-                            const int ci = cd->col[i];
-                            if (!own_in && ci > v.c_old) { i_old = n_opt; put(p_old, l_old); own_in = true; }
-                            const int pi = sh.s_pos_of_col[ci];
-                            if (pi >= 0) {
-                                bloom |= 1ull << (pi & 63);
-                                rival(pi, cd->val[i] + sh.s_lc[pi]);
-                            }
+                    for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+                        if (i >= n_max) break;                // warp-uniform
+                        if (i < n_opt) {
+                            const int p = sh.s_pos_of_col[col[i]];
+                            int c = 0;
+                            if (p >= 0) { c = sh.s_cnt[p]; bloom |= 1ull << (p & 63); }
+                            if (i == i_old) --c;
+                            pos[i] = p;
+                            S += (double)c * e[i];
+                            cum[i] = S;
                         }
                     }
-                    if (!own_in) { i_old = n_opt; put(p_old, l_old); }
-                    for (int e = 0; e < n_extra; ++e) {       // clusters born in this epoch
-                        const int pe = sh.s_xpos[e];
+                    double Sx = 0.0;
+                    for (int x = 0; x < n_extra; ++x) {       // clusters born in this epoch
+                        const int pe = sh.s_xpos[x];
                         if (pe >= 0) {
                             bloom |= 1ull << (pe & 63);
-                            rival(pe, a.llx[(long long)e * a.ldx + tx] + sh.s_lc[pe]);
+                            const double ex = exp(a.llx[(long long)x * a.ldx + tx] - v.ref);
+                            e_lim = fmax(e_lim, ex);
+                            Sx += (double)sh.s_cnt[pe] * ex;
                         }
                     }
-                    rival(L, v.lnew);
-                    if (over) {
-                        outcome = OUT_COMPLEX;
-                    } else if (n_opt == 1) {
-                        outcome = (v.u > 1e-12 && v.u < 1.0 - 1e-12) ? OUT_STAY : OUT_COMPLEX;
-                        slack_nat = cut - best_below;
-                    } else {
-                        int pick = -1;
-                        if (n_opt == 2 && pos[1] < L && v.u > 1e-9 && v.u < 1.0 - 1e-9) {
-                            // two-way draw: log-odds of the later position over the earlier one
-                            const double gap = fabs((l[1] - l[0]) - v.logit);
-                            if (gap > 1e-3) {
-                                pick = ((l[1] - l[0]) < v.logit) ? 0 : 1;
-                                slack_nat = fmin(gap - 1e-3, cut - best_below);
+                    const double total = (S + Sx) + v.e_new;
+                    const double target = v.u * total;
+                    double lo = 0.0, hi = 0.0;
+                    int pick = -1;
+#pragma unroll
+                    for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+                        if (i >= n_max) break;                // warp-uniform
+                        if (i < n_opt && pick < 0) {
+                            if (cum[i] > target) { pick = i; hi = cum[i]; to_pos = pos[i]; }
+                            else lo = cum[i];
+                        }
+                    }
+                    if (pick < 0) {
+                        double run = S;
+                        for (int x = 0; x < n_extra && pick < 0; ++x) {
+                            const int pe = sh.s_xpos[x];
+                            if (pe >= 0) {
+                                lo = run;
+                                run += (double)sh.s_cnt[pe] * exp(a.llx[(long long)x * a.ldx + tx] - v.ref);
+                                if (run > target) { pick = BNPC_MAX_OPT + x; hi = run; to_pos = pe; }
                             }
                         }
-                        if (pick < 0) {
-                            double mg;
-                            pick = local_draw(pos, l, n_opt, L, v.u, &mg);
-                            slack_p = mg - 1e-12;
-                            slack_nat = cut - best_below;
-                            if (slack_p <= 0.0) pick = -1;
-                        }
-                        if (pick < 0) outcome = OUT_COMPLEX;
-                        else if (pick == i_old) outcome = OUT_STAY;
-                        else {
-                            int pp = -1;
-#pragma unroll
-                            for (int i = 0; i < SW_NOPT; ++i) if (i == pick) pp = pos[i];
-                            if (pp >= L) outcome = OUT_COMPLEX;      // opens a new cluster
-                            else { outcome = OUT_MOVE; to_pos = pp; }
-                        }
+                    }
+                    // pick < 0: the new-cluster option (or rounding at the top edge) -> exact draw
+                    if (pick >= 0 && to_pos >= 0) {
+                        slack = fmin(target - lo, hi - target) - 2.0 * SW_GUARD * total;
+                        if (slack > 0.0) outcome = (pick == i_old) ? OUT_STAY : OUT_MOVE;
                     }
                 }
             }
@@ -751,36 +703,25 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
             const int of = __shfl_sync(FULL, outcome, f);
             if (of == OUT_MOVE) {
                 const int kf = __shfl_sync(FULL, p_old, f), rf = __shfl_sync(FULL, to_pos, f);
-                // sizes n_old-1 and n_new+1: one of the two log weights of each cluster is the
-                // other one's previous value; the two new ones are computed by two lanes at once
                 if (lane == 0) {
-                    const int c_old = sh.s_cnt[kf] - 1;
-                    const double w = sh.s_lcm1[kf];
-                    const double w2 = log((double)(c_old - 1)) - a.c_norm;
-                    sh.s_cnt[kf] = c_old;
-                    sh.s_lc[kf] = w;
-                    sh.s_lcm1[kf] = w2;
-                    sh.d_move = w - w2;                     // largest weight change of the shrinking cluster
-                    a.cnt[sh.s_id[kf]] = c_old;
+                    const int c = sh.s_cnt[kf] - 1;
+                    sh.s_cnt[kf] = c;
+                    a.cnt[sh.s_id[kf]] = c;
                     a.assign[vis[f].cell] = sh.s_id[rf];
                 } else if (lane == 1) {
-                    const int c_new = sh.s_cnt[rf] + 1;
-                    const double w = sh.s_lc[rf];
-                    const double w0 = sh.s_lcm1[rf];
-                    sh.s_cnt[rf] = c_new;
-                    sh.s_lcm1[rf] = w;
-                    sh.s_lc[rf] = log((double)c_new) - a.c_norm;
-                    a.cnt[sh.s_id[rf]] = c_new;
-                    sh.red[39] = w - w0;                   // largest weight change of the growing cluster
+                    const int c = sh.s_cnt[rf] + 1;
+                    sh.s_cnt[rf] = c;
+                    a.cnt[sh.s_id[rf]] = c;
                 }
                 __syncwarp();
                 ++moved;
-                // validity of the decisions of the lanes still to come
-                const double d = sh.d_move + sh.red[39];
-                if (lane > f && lane < nc && ((bloom >> (kf & 63)) | (bloom >> (rf & 63))) & 1ull) {
-                    slack_nat -= d;
-                    slack_p -= expm1(2.0 * d);
-                    if (!(slack_nat > 0.0) || !(slack_p > 0.0)) need_eval = true;
+                // A move shifts two sizes by one: every interval edge and u*total of a later lane
+                // that has one of the two clusters among its options move by at most 2*e_lim each.
+                // Such a lane keeps its decision while its margin lasts and is scored again when
+                // the margin is used up -- or at once if the shrunk cluster is down to one cell.
+                if (lane > f && lane < nc && (((bloom >> (kf & 63)) | (bloom >> (rf & 63))) & 1ull)) {
+                    slack -= 4.0 * e_lim;
+                    if (!(slack > 0.0) || sh.s_cnt[kf] <= 1) need_eval = true;
                 }
                 lo_lane = f + 1;
             } else {
@@ -1091,38 +1032,71 @@ __global__ void group_members_kernel(const int32_t* __restrict__ assign, int N,
     members[seg_off[r] + base + __popc(peers & ((1u << lane) - 1u))] = n;
 }
 
-#define SS_CHUNK 1024
-// grid (chunks, R): a CTA counts ones/zeros per mutation over up to SS_CHUNK members of one
-// segment; lane <-> bit of a 32-mutation word, each warp strides over the words of a row.
+#define SS_CHUNK 512
+// grid (chunks, R, word blocks): a CTA counts ones/zeros per mutation over up to SS_CHUNK members
+// of one segment for a block of 32 mutation words.  A thread owns one word column and strides
+// over the rows, so that a warp reads whole 128-byte row pieces (coalesced); the 32 per-bit
+// counters of a word are kept as 8 registers of four byte-wide counters each
+// (acc[j] += (x >> j) & 0x01010101 counts bits j, j+8, j+16, j+24), at most 255 rows per thread.
 __global__ void __launch_bounds__(256)
 suffstat_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
                 const int32_t* __restrict__ members, const int32_t* __restrict__ seg_off,
-                int32_t* __restrict__ S1, int32_t* __restrict__ S0) {
+                int32_t* __restrict__ S1, int32_t* __restrict__ S0, int wc_log2) {
+    __shared__ int cnt[2][32][32];
     const int r = blockIdx.y;
     const int beg = seg_off[r] + blockIdx.x * SS_CHUNK;
     const int end = min(seg_off[r + 1], beg + SS_CHUNK);
     if (beg >= end) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int Wm = (M + 31) >> 5;
-    for (int w = warp; w < Wm; w += nw) {
-        int c1 = 0, c0 = 0;
-        int i = beg;
-        for (; i + 4 <= end; i += 4) {
-            const long long a0 = members[i], a1 = members[i + 1], a2 = members[i + 2], a3 = members[i + 3];
-            const uint32_t p0 = x1[a0 * W + w], p1 = x1[a1 * W + w], p2 = x1[a2 * W + w], p3 = x1[a3 * W + w];
-            const uint32_t q0 = x0[a0 * W + w], q1 = x0[a1 * W + w], q2 = x0[a2 * W + w], q3 = x0[a3 * W + w];
-            c1 += ((p0 >> lane) & 1) + ((p1 >> lane) & 1) + ((p2 >> lane) & 1) + ((p3 >> lane) & 1);
-            c0 += ((q0 >> lane) & 1) + ((q1 >> lane) & 1) + ((q2 >> lane) & 1) + ((q3 >> lane) & 1);
+    const int wc = 1 << wc_log2;
+    const int col = threadIdx.x & (wc - 1), rsub = threadIdx.x >> wc_log2, rstep = 256 >> wc_log2;
+    const int w = blockIdx.z * 32 + col;
+    for (int i = threadIdx.x; i < 2 * 32 * 32; i += 256) (&cnt[0][0][0])[i] = 0;
+    __syncthreads();
+    if (w < W) {
+        uint32_t a1[8], a0[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a1[j] = 0u; a0[j] = 0u; }
+        int i = beg + rsub;
+        for (; i + 3 * rstep < end; i += 4 * rstep) {
+            const long long c0 = members[i], c1 = members[i + rstep], c2 = members[i + 2 * rstep],
+                            c3 = members[i + 3 * rstep];
+            const uint32_t p0 = x1[c0 * W + w], p1 = x1[c1 * W + w], p2 = x1[c2 * W + w], p3 = x1[c3 * W + w];
+            const uint32_t q0 = x0[c0 * W + w], q1 = x0[c1 * W + w], q2 = x0[c2 * W + w], q3 = x0[c3 * W + w];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a1[j] += ((p0 >> j) & 0x01010101u) + ((p1 >> j) & 0x01010101u) + ((p2 >> j) & 0x01010101u) +
+                         ((p3 >> j) & 0x01010101u);
+                a0[j] += ((q0 >> j) & 0x01010101u) + ((q1 >> j) & 0x01010101u) + ((q2 >> j) & 0x01010101u) +
+                         ((q3 >> j) & 0x01010101u);
+            }
         }
-        for (; i < end; ++i) {
-            const long long a0 = members[i];
-            c1 += (x1[a0 * W + w] >> lane) & 1;
-            c0 += (x0[a0 * W + w] >> lane) & 1;
+        for (; i < end; i += rstep) {
+            const long long c0 = members[i];
+            const uint32_t p0 = x1[c0 * W + w], q0 = x0[c0 * W + w];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a1[j] += (p0 >> j) & 0x01010101u;
+                a0[j] += (q0 >> j) & 0x01010101u;
+            }
         }
-        const int m = w * 32 + lane;
-        if (m < M) {
-            if (c1) atomicAdd(&S1[(long long)r * M + m], c1);
-            if (c0) atomicAdd(&S0[(long long)r * M + m], c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int v1 = (a1[j] >> (8 * b)) & 0xff, v0 = (a0[j] >> (8 * b)) & 0xff;
+                if (v1) atomicAdd(&cnt[0][col][j + 8 * b], v1);
+                if (v0) atomicAdd(&cnt[1][col][j + 8 * b], v0);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+        const int c = i >> 5, bit = i & 31;
+        const int m = (blockIdx.z * 32 + c) * 32 + bit;
+        if (c < wc && m < M) {
+            const int v1 = cnt[0][c][bit], v0 = cnt[1][c][bit];
+            if (v1) atomicAdd(&S1[(long long)r * M + m], v1);
+            if (v0) atomicAdd(&S0[(long long)r * M + m], v0);
         }
     }
 }
@@ -1593,11 +1567,12 @@ int bnpc_gibbs_prepare(const int32_t* perm, const double* u, const int32_t* assi
 }
 
 int bnpc_gibbs_candidates(const double* ll, int ldk, int K, const int32_t* col_of_id,
-                          bnpc_visit_t* visit_t0, bnpc_cand_t* cand_t0, int C, double slack, void* stream) {
+                          bnpc_visit_t* visit_t0, bnpc_cand_t* cand_t0, int C, double slack,
+                          double c_norm, void* stream) {
     if (C <= 0) return 0;
     if (K > SW_MAXL) return bad_arg("candidates need K <= 1024");
     gibbs_candidates_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(ll, ldk, K, col_of_id, visit_t0,
-                                                                          cand_t0, C, slack);
+                                                                          cand_t0, C, slack, c_norm);
     LAUNCH_CHECK("gibbs_candidates");
     return 0;
 }
@@ -1658,12 +1633,14 @@ int bnpc_suffstat(const uint32_t* x1, const uint32_t* x0, int W, int M, const in
     if (e == cudaSuccess) e = cudaMemsetAsync(S0, 0, sizeof(int32_t) * (size_t)R * M, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail("suffstat memset", e);
     if (max_len <= 0) return 0;
+    int wc_log2 = 2;                       // word columns per CTA row group: 4, 8, 16 or 32
+    while ((1 << wc_log2) < W && wc_log2 < 5) ++wc_log2;
     // grid.y is limited to 65535: tile the segment axis
     for (int r0 = 0; r0 < R; r0 += 65535) {
         const int rr = min(65535, R - r0);
-        dim3 grid(cdiv(max_len, SS_CHUNK), rr);
+        dim3 grid(cdiv(max_len, SS_CHUNK), rr, cdiv(W, 32));
         suffstat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x1, x0, W, M, members, seg_off + r0,
-                                                               S1 + (size_t)r0 * M, S0 + (size_t)r0 * M);
+                                                               S1 + (size_t)r0 * M, S0 + (size_t)r0 * M, wc_log2);
         LAUNCH_CHECK("suffstat");
     }
     return 0;

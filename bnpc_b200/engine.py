@@ -420,7 +420,7 @@ class DeviceCRP:
                     L.gibbs_candidates(ll.data_ptr(), ldk, K, self.col_of_id.data_ptr(),
                                        self.visit.data_ptr() + t * _lib.VISIT_BYTES,
                                        self.cand.data_ptr() + t * _lib.CAND_BYTES, rows,
-                                       float(np.log(N)), sp)
+                                       float(np.log(N)), c_norm, sp)
                 a = _lib.SweepArgs(
                     x1=sh.x1.data_ptr(), x0=sh.x0.data_ptr(), W=sh.W, N=N, M=M,
                     assign=self.assign_d.data_ptr(), cnt=self.cnt.data_ptr(), lst=self.lst.data_ptr(),

@@ -63,22 +63,27 @@ extern "C" {
 typedef struct {
     double  u;      /* uniform for the categorical draw (libs/CRP.py:277)             */
     double  lnew;   /* new-cluster log posterior of this cell (libs/CRP.py:230-234)   */
-    double  logit;  /* log((1-u)/u): a two-way draw picks the first option iff the
-                       log-odds of the second over the first are below this           */
-    double  v_old;  /* ll of the cell under its current cluster                       */
+    double  e_new;  /* weight of the new-cluster option: alpha * exp(ll_new - ref)    */
+    double  ref;    /* reference level of the option weights (largest ll among them)  */
     int32_t cell;   /* cell index = permutation[t] (libs/CRP.py:260)                  */
     int32_t old;    /* its cluster id before the sweep                                 */
     int32_t c_old;  /* ll column of that cluster in the current epoch                  */
-    int32_t n_cand; /* rival candidates (see bnpc_cand_t); BNPC_MAX_CAND+1 = too many  */
-    int32_t pad[4];
+    int32_t n_opt;  /* options (own cluster + rivals); BNPC_MAX_OPT+1 = too many/unknown */
+    int32_t i_old;  /* index of the own cluster among the options                      */
+    int32_t pad[3];
 } bnpc_visit_t;
 
-/* rival candidates of one visited cell (80 bytes): the clusters that can come within 40
- * nats of the cell's current cluster for ANY cluster sizes, best first                 */
+/* options of one visited cell (96 bytes): its own cluster and the rivals that can come
+ * within 40 nats of it for ANY cluster sizes, in ll-column order (= list order).  The
+ * draw of libs/CRP.py:274-277 restricted to these options is linear in the cluster
+ * sizes: P(option i) = n_i * e[i] / (sum_j n_j * e[j] + e_new), n_own counted without
+ * the cell itself.                                                                    */
 #define BNPC_MAX_CAND 8
+#define BNPC_MAX_OPT  (BNPC_MAX_CAND + 1)
 typedef struct {
-    double   val[BNPC_MAX_CAND];   /* ll of the cell under the candidate cluster       */
-    uint16_t col[BNPC_MAX_CAND];   /* its ll column in the current epoch               */
+    double   e[BNPC_MAX_OPT];     /* exp(ll - ref) of the option                        */
+    uint16_t col[BNPC_MAX_OPT];   /* its ll column in the current epoch                 */
+    uint16_t pad[3];
 } bnpc_cand_t;
 
 int         bnpc_abi_version(void);
@@ -122,14 +127,14 @@ int bnpc_gibbs_prepare(const int32_t* perm, const double* u, const int32_t* assi
                        const int32_t* n1, const int32_t* n0, int N,
                        double c1, double c0, double lnew_prior,
                        bnpc_visit_t* visit, void* stream);
-/* After bnpc_ll_matrix of an epoch with at most 1024 columns: fill v_old, c_old, n_cand of
- * the visit records [t0, t0+C) and their candidate records.  A cluster k can rival the
+/* After bnpc_ll_matrix of an epoch with at most 1024 columns: fill ref, e_new, c_old, n_opt,
+ * i_old of the visit records [t0, t0+C) and their option records.  A cluster k can rival the
  * current cluster o of a cell (come within 40 nats of it once the CRP weights log n_k are
  * added) only if ll_k > ll_o - 40 - slack with slack = log N, whatever the sizes are; the
- * sequential sweep then only looks at these candidates.                              */
+ * sequential sweep then only looks at these options.  c_norm = log(N-1+alpha).         */
 int bnpc_gibbs_candidates(const double* ll, int ldk, int K, const int32_t* col_of_id,
                           bnpc_visit_t* visit_t0, bnpc_cand_t* cand_t0, int C, double slack,
-                          void* stream);
+                          double c_norm, void* stream);
 /* Start of an epoch: rebuild cnt[] from the host-authoritative list
  * live[2*j] = id, live[2*j+1] = size (list order), set col_of_id[id] = j and
  * clear the epoch's extra-cluster bookkeeping.  first != 0 also resets the
