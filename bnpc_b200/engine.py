@@ -20,7 +20,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 from scipy.special import gamma as _gamma_fn
-from scipy.special import gammaln
+from scipy.special import gammaln, xlogy
 from scipy.stats import beta as _beta_dist
 from scipy.stats import gamma as _gamma_dist
 from scipy.stats import truncnorm as _truncnorm
@@ -33,6 +33,34 @@ THETA_LO = 1e-5                                   # libs/CRP.py:12-13
 THETA_HI = 1 - THETA_LO
 LL_BUDGET_BYTES = 1 << 30                         # largest ll matrix built per epoch
 _PACK_LOCK = threading.Lock()                     # chains of one model pack the input once
+_NORM_LOGC = np.log(np.sqrt(2 * np.pi))           # scipy _norm_pdf_logC
+
+
+def _tn_logpdf(x, lo, hi, loc, scale):
+    """scipy.stats.truncnorm.logpdf(x, lo, hi, loc, scale) for scalars, without the frozen /
+    argument-checking machinery (same private formulas: _norm_logpdf - _log_gauss_mass)."""
+    y = (x - loc) / scale
+    if not (lo <= y <= hi):
+        return -np.inf
+    return float(_truncnorm._logpdf(np.float64(y), np.float64(lo), np.float64(hi))) - np.log(scale)
+
+
+class _TruncNormPrior:
+    """Frozen truncated normal on [0,1] (libs/CRP_learning_errors.py:24,30): logpdf with the
+    log mass of the interval computed once."""
+
+    def __init__(self, mean, sd):
+        self.mean, self.sd = mean, sd
+        self.lo, self.hi = (0 - mean) / sd, (1 - mean) / sd
+        self.args = (self.lo, self.hi, mean, sd)
+        # _logpdf(0) = -log(sqrt(2 pi)) - log(mass of [lo, hi])
+        self._const = float(_truncnorm._logpdf(np.float64(0.0), np.float64(self.lo), np.float64(self.hi)))
+
+    def logpdf(self, x):
+        y = (x - self.mean) / self.sd
+        if not (self.lo <= y <= self.hi):
+            return -np.inf
+        return (-y ** 2 / 2.0 + self._const) - np.log(self.sd)
 
 
 class _Shared:
@@ -155,6 +183,21 @@ class DeviceCRP:
         self.d2h_bytes += t.numel() * t.element_size()
         return t.cpu().numpy()
 
+    def _down_small(self, *tensors):
+        """One synchronisation for several small device -> host reads (pinned staging)."""
+        out, off = [], 0
+        for t in tensors:
+            nb = t.numel() * t.element_size()
+            if off + nb > self._pin.numel():
+                raise RuntimeError('pinned staging buffer too small')
+            view = self._pin[off:off + nb].view(t.dtype)
+            view.copy_(t.reshape(-1), non_blocking=True)
+            out.append(view)
+            off += (nb + 15) & ~15
+            self.d2h_bytes += nb
+        self.stream.synchronize()
+        return [v.numpy().copy() for v in out]
+
     class _Timed:
         """CUDA-event bracket around one launch on the chain's stream (bench.py roofline)."""
 
@@ -216,6 +259,8 @@ class DeviceCRP:
             self.rg_S1 = torch.zeros((3, self.muts_total), dtype=torch.int32, device=self.device)
             self.rg_S0 = torch.zeros((3, self.muts_total), dtype=torch.int32, device=self.device)
             self.rg_dec = torch.zeros(4, dtype=torch.int32, device=self.device)
+            self.rg_scal = torch.zeros(32, dtype=torch.float64, device=self.device)
+            self._pin = torch.empty(1 << 16, dtype=torch.uint8).pin_memory()
             self.idcap = 0
         self._dev_ready = True
         self._version = 0
@@ -364,7 +409,11 @@ class DeviceCRP:
     def get_lprior_full(self):
         """libs/CRP.py:241-251."""
         _, sizes = self._ids_sizes()
-        lp = self.DP_a_prior.logpdf(self.DP_a) + np.nansum(self._crp_table_at(sizes))
+        # scipy gamma(a, loc=b).logpdf: xlogy(a-1, y) - y - gammaln(a) at y = x - loc (scale 1)
+        a0, loc = self.DP_a_gamma
+        y = self.DP_a - loc
+        lp_alpha = float(xlogy(a0 - 1.0, y) - y - gammaln(a0)) if y > 0 else -np.inf
+        lp = lp_alpha + np.nansum(self._crp_table_at(sizes))
         if not self.beta_prior_uniform:
             lp += self._trace_scalars()[1]
         return lp
@@ -435,12 +484,16 @@ class DeviceCRP:
                     p=float(self.p), q=float(self.q))
                 with self._Timed(self, 'gibbs_sweep'):
                     L.gibbs_sweep(C.byref(a), 256 if K < 1000 else 1024, sp)
-                st = self._down(self.st)                       # synchronises the stream
+                # status block and live list in one read (at most MAX_EXTRA births per epoch)
+                k_cap = K + _lib.MAX_EXTRA + 2
+                if 8 * k_cap + 256 <= self._pin.numel():
+                    st, pairs = self._down_small(self.st, self.live_io[:2 * k_cap])   # synchronises
+                else:
+                    st, pairs = self._down(self.st), self._down(self.live_io[:2 * k_cap])
                 flags = int(st[_lib.ST_FLAGS])
                 if flags & (_lib.STOP_TAPE_EMPTY | _lib.STOP_HANG):
                     raise RuntimeError(f'gibbs_sweep stopped with flags {flags:#x} at t={st[_lib.ST_TDONE]}')
                 K = int(st[_lib.ST_K])
-                pairs = self._down(self.live_io[:2 * K])
                 self.cells_per_cluster = OrderedDict(
                     (int(pairs[2 * j]), int(pairs[2 * j + 1])) for j in range(K))
                 t_new = int(st[_lib.ST_TDONE])
@@ -567,6 +620,11 @@ class DeviceCRP:
         return [1, 0]
 
     # -- restricted Gibbs machinery (libs/CRP.py:527-638) -----------------------
+    # Everything a split-merge move computes on the device is enqueued without waiting; the
+    # scalars the Metropolis-Hastings decision needs are reduced into slots of `rg_scal` and
+    # read back ONCE (one stream synchronisation per move).
+    SL_FWD_ASSIGN, SL_FWD_THETA, SL_BACK, SL_BACK_LQ, SL_PRIOR_NEW, SL_PRIOR_OLD, SL_LL3 = 0, 1, 2, 3, 4, 6, 8
+
     def _rg_side_stats(self, n):
         """rg_S[0], rg_S[1] = sufficient statistics of the two halves (anchors
         included) for the current `half`; returns nothing (device only)."""
@@ -577,23 +635,23 @@ class DeviceCRP:
                    self.seg3.data_ptr(), 2, n, self.rg_S1.data_ptr(), self.rg_S0.data_ptr(), sp)
         self._stats_version = -1          # `members` was reused
 
-    def _rg_sum_rows(self, v, rows, m):
-        tot = self._buf('rg_tot', 8, torch.float64)
-        self.L.row_sum(v.data_ptr(), rows, m, tot.data_ptr(), self._sp())
-        return tot
+    def _rg_sum_to(self, v, rows, m, slot):
+        """rg_scal[slot + r] = sum of row r of v[rows][m] (fixed order)."""
+        self.L.row_sum(v.data_ptr(), rows, m, self.rg_scal.data_ptr() + 8 * slot, self._sp())
 
-    def _rg_mh(self, row0, rows, want_logq):
-        """MH_cluster_params on rg_theta[row0:row0+rows] (libs/CRP.py:583,601)."""
+    def _rg_mh(self, row0, rows, slot=None):
+        """MH_cluster_params on rg_theta[row0:row0+rows] (libs/CRP.py:583,601); with a slot the
+        transition log-probability (trans_prob=True) is summed into rg_scal[slot]."""
         M = self.muts_total
         rnd = self.rnd.mh_theta_draws(rows, M)
+        want = slot is not None
         logq = self._buf('rg_logq', 3 * M, torch.float64)
         self.L.mh_theta(self.rg_theta[row0:].data_ptr(), None, rows, M, self.rg_S1[row0:].data_ptr(),
                         self.rg_S0[row0:].data_ptr(), rnd.data_ptr(), float(self.FN), float(self.FP),
-                        float(self.p), float(self.q), 1 if want_logq else 0,
-                        logq.data_ptr() if want_logq else None, self.rg_dec.data_ptr(), self._sp())
-        if want_logq:
-            return float(self._rg_sum_rows(logq, 1, rows * M)[0].item())
-        return None
+                        float(self.p), float(self.q), 1 if want else 0,
+                        logq.data_ptr() if want else None, self.rg_dec.data_ptr(), self._sp())
+        if want:
+            self._rg_sum_to(logq, 1, rows * M, slot)
 
     def _rg_pair_ll(self, theta, ids_ptr, n):
         """ll of the n-2 free cells under two theta rows (libs/CRP.py:635-638)."""
@@ -608,7 +666,6 @@ class DeviceCRP:
     def _scan_split(self, n, want_logq=False):
         """libs/CRP.py:570-578, 590-632."""
         L, sp, nf = self.L, self._sp(), n - 2
-        lq_assign = 0.0
         if n > 2:
             ll2 = self._rg_pair_ll(self.rg_theta, None, n)
             perm, u = self.rnd.scan_draws(nf)
@@ -617,23 +674,21 @@ class DeviceCRP:
                       float(self.DP_a), 0, None, None, -1, lq.data_ptr() if want_logq else None,
                       self.rg_work.data_ptr(), sp)
             if want_logq:
-                lq_assign = float(self._rg_sum_rows(lq, 1, nf)[0].item())
+                self._rg_sum_to(lq, 1, nf, self.SL_FWD_ASSIGN)
         self._rg_side_stats(n)
         # both halves in one launch; draws are taken side 0 first, as the reference does
-        lq_theta = self._rg_mh(0, 2, want_logq)
-        if want_logq:
-            return lq_assign + lq_theta
-        return None
+        self._rg_mh(0, 2, self.SL_FWD_THETA if want_logq else None)
 
     def _scan_merged(self, want_logq=False):
         """libs/CRP.py:581-587."""
-        return self._rg_mh(2, 1, want_logq)
+        self._rg_mh(2, 1, self.SL_FWD_THETA if want_logq else None)
 
     def _restricted_gibbs(self, move, n, n_a, size_term, scans, cl_i, cl_j):
         """libs/CRP.py:527-567.  Returns (accepted, number of free cells on side j)."""
         L, sp, M = self.L, self._sp(), self.muts_total
         FN, FP = float(self.FN), float(self.FP)
         mix0 = self._beta_mix_const[0]
+        self.rg_scal.zero_()
         # launch state: free cells go to the anchor whose raw row explains them better
         if n > 2:
             k6 = (C.c_double * 6)(
@@ -661,39 +716,39 @@ class DeviceCRP:
             return self._decide_split(n, size_term, cl_i)
         return self._decide_merge(n, n_a, size_term, cl_i, cl_j)
 
-    def _count_ones(self, n):
-        """free cells currently on side j (seg3[3] after rg_sides)."""
-        return int(self.seg3[3].item()) if n > 2 else 0
+    def _prior_sum_to(self, theta, rows, slot):
+        """rg_scal[slot + r] = sum_m Beta(p,q).logpdf(theta[r][m]) (device reduction)."""
+        self.L.row_loglik(theta.data_ptr(), None, rows, self.muts_total, self.rg_S1.data_ptr(),
+                          self.rg_S0.data_ptr(), None, None, 0, float(self.p), float(self.q),
+                          self.rg_scal.data_ptr(), self.rg_scal.data_ptr() + 8 * slot, self._sp())
 
-    def _prior_sum(self, theta, rows):
-        """sum of Beta(p,q).logpdf over `rows` rows of theta (device reduction)."""
-        r = self._row_loglik(theta, None, rows, self.rg_S1, self.rg_S0, [], [], True)
-        return float(r[0])
-
-    def _ll_three(self):
+    def _ll_three_to(self, slot):
         """flat ll of side i, side j (under rg_theta[0:2]) and of all cells (under
         rg_theta[2]) from the three statistics rows (libs/CRP.py:726-728)."""
-        out = self._buf('rl_out', 16, torch.float64)
         fn = (C.c_double * 1)(float(self.FN))
         fp = (C.c_double * 1)(float(self.FP))
         self.L.row_loglik(self.rg_theta.data_ptr(), None, 3, self.muts_total, self.rg_S1.data_ptr(),
                           self.rg_S0.data_ptr(), fn, fp, 1, float(self.p), float(self.q),
-                          out.data_ptr(), None, self._sp())
-        return self._down(out[:3])
+                          self.rg_scal.data_ptr() + 8 * slot, None, self._sp())
 
     def _decide_split(self, n, size_term, cl_i):
         """libs/CRP.py:641-653 with :668-682, :695-733, :757-764."""
         L, sp, M = self.L, self._sp(), self.muts_total
-        fwd = self._scan_split(n, want_logq=True)
+        self._scan_split(n, want_logq=True)
         sd = self.rnd.step_sd_index(1, M)
         A = self._buf('rg_A', 2 * M, torch.float64)
         L.theta_log_ratio(self.theta[cl_i].data_ptr(), self.rg_theta[2].data_ptr(), 1, M,
                           self.rg_S1[2].data_ptr(), self.rg_S0[2].data_ptr(), sd.data_ptr(),
                           THETA_LO, THETA_HI, float(self.FN), float(self.FP),
                           float(self.p), float(self.q), A.data_ptr(), sp)
-        back = float(self._rg_sum_rows(A, 1, M)[0].item())
-        logq_ratio = back - fwd
-        ones = self._count_ones(n)
+        self._rg_sum_to(A, 1, M, self.SL_BACK)
+        if not self.beta_prior_uniform:
+            self._prior_sum_to(self.rg_theta, 2, self.SL_PRIOR_NEW)
+            self._prior_sum_to(self.theta[cl_i:cl_i + 1], 1, self.SL_PRIOR_OLD)
+        self._ll_three_to(self.SL_LL3)
+        sc, seg = self._down_small(self.rg_scal[:16], self.seg3)
+        ones = int(seg[3]) if n > 2 else 0                  # free cells on side j (rg_sides)
+        logq_ratio = sc[self.SL_BACK] - (sc[self.SL_FWD_ASSIGN] + sc[self.SL_FWD_THETA])
         # eq. 7: prior ratio (libs/CRP.py:695-713)
         n_j = ones + 1
         n_i = n - n_j
@@ -703,22 +758,20 @@ class DeviceCRP:
         if n_j > 0:
             r += gammaln(n_i)
         if not self.beta_prior_uniform:
-            r += self._prior_sum(self.rg_theta, 2) - self._prior_sum(self.theta[cl_i:cl_i + 1], 1)
-        ll3 = self._ll_three()
-        ll_ratio = ll3[0] + ll3[1] - ll3[2]
+            r += (sc[self.SL_PRIOR_NEW] + sc[self.SL_PRIOR_NEW + 1]) - sc[self.SL_PRIOR_OLD]
+        ll_ratio = sc[self.SL_LL3] + sc[self.SL_LL3 + 1] - sc[self.SL_LL3 + 2]
         lq_pick, others = size_term
         norm = np.nansum(1 / np.append(others, [n_i, n_j]))
         size_ratio = (np.log(1 / n_i / norm) + np.log(1 / n_j / norm)) - lq_pick
         total = logq_ratio + r + ll_ratio + size_ratio
-        u = self.rnd.random() if not (n > 2 and (ones == 0 or ones == n - 2)) else None
-        if u is None:
+        if n > 2 and (ones == 0 or ones == n - 2):
             return False, ones              # np.unique(rg_assignment).size == 1
-        return bool(np.log(u) < total), ones
+        return bool(np.log(self.rnd.random()) < total), ones
 
     def _decide_merge(self, n, n_a, size_term, cl_i, cl_j):
         """libs/CRP.py:656-665 with :685-692, :736-754, :767-820."""
         L, sp, M, nf = self.L, self._sp(), self.muts_total, n - 2
-        fwd = self._scan_merged(want_logq=True)
+        self._scan_merged(want_logq=True)
         # probability of walking from the launch split back to the original split
         sd = self.rnd.step_sd_index(2, M)
         orig = self._buf('rg_orig', 2 * M, torch.float32)
@@ -728,16 +781,22 @@ class DeviceCRP:
         L.theta_log_ratio(orig.data_ptr(), self.rg_theta.data_ptr(), 2, M, self.rg_S1.data_ptr(),
                           self.rg_S0.data_ptr(), sd.data_ptr(), 0.0, 1.0,
                           float(self.FN), float(self.FP), float(self.p), float(self.q), A.data_ptr(), sp)
-        back = float(self._rg_sum_rows(A, 1, 2 * M)[0].item())
+        self._rg_sum_to(A, 1, 2 * M, self.SL_BACK)
         if n > 2:
             ll2 = self._rg_pair_ll(orig, None, n)
             lq = self._buf('rg_lq', nf, torch.float64)
             L.rg_scan(ll2.data_ptr(), 2, n, None, None, self.half.data_ptr(), float(self.DP_a), 1,
                       self.cells_d.data_ptr(), self.assign_d.data_ptr(), cl_i, lq.data_ptr(),
                       self.rg_work.data_ptr(), sp)
-            back += float(self._rg_sum_rows(lq, 1, nf)[0].item())
-        logq_ratio = back - fwd
+            self._rg_sum_to(lq, 1, nf, self.SL_BACK_LQ)
+        if not self.beta_prior_uniform:
+            self._prior_sum_to(self.rg_theta[2:3], 1, self.SL_PRIOR_NEW)
+            self._prior_sum_to(orig, 2, self.SL_PRIOR_OLD)
         # `half` now equals the original split (reference quirk)
+        self._rg_side_stats(n)
+        self._ll_three_to(self.SL_LL3)
+        sc, = self._down_small(self.rg_scal[:16])
+        logq_ratio = (sc[self.SL_BACK] + sc[self.SL_BACK_LQ]) - sc[self.SL_FWD_THETA]
         n_j = (n - n_a - 1) + 1
         n_i = n - n_j
         r = gammaln(n) - np.log(self.DP_a)
@@ -746,10 +805,8 @@ class DeviceCRP:
         if n_j > 0:
             r -= gammaln(n_j)
         if not self.beta_prior_uniform:
-            r += self._prior_sum(self.rg_theta[2:3], 1) - self._prior_sum(orig, 2)
-        self._rg_side_stats(n)
-        ll3 = self._ll_three()
-        ll_ratio = ll3[2] - ll3[0] - ll3[1]
+            r += sc[self.SL_PRIOR_NEW] - (sc[self.SL_PRIOR_OLD] + sc[self.SL_PRIOR_OLD + 1])
+        ll_ratio = sc[self.SL_LL3 + 2] - sc[self.SL_LL3] - sc[self.SL_LL3 + 1]
         if nf - 1 > 0:
             back_size = -np.log(self.cells_total) - np.log(nf - 1)
         else:
@@ -768,9 +825,9 @@ class DeviceCRPLearnErrors(DeviceCRP):
     def __init__(self, data, DP_alpha=(-1, -1), param_beta=(1, 1), FP_mean=0.001, FP_sd=0.0005,
                  FN_mean=0.25, FN_sd=0.05, device=None, rnd=None):
         super().__init__(data, DP_alpha, param_beta, FN_mean, FP_mean, device=device, rnd=rnd)
-        self.FP_prior = _truncnorm((0 - FP_mean) / FP_sd, (1 - FP_mean) / FP_sd, FP_mean, FP_sd)
+        self.FP_prior = _TruncNormPrior(FP_mean, FP_sd)
         self.FP_sd = np.array([FP_sd * 0.5, FP_sd, FP_sd * 1.5])
-        self.FN_prior = _truncnorm((0 - FN_mean) / FN_sd, (1 - FN_mean) / FN_sd, FN_mean, FN_sd)
+        self.FN_prior = _TruncNormPrior(FN_mean, FN_sd)
         self.FN_sd = np.array([FN_sd * 0.5, FN_sd, FN_sd * 1.5])
 
     def __str__(self):
@@ -819,9 +876,9 @@ class DeviceCRPLearnErrors(DeviceCRP):
                 prop = float(_truncnorm._ppf(np.float64(u), np.float64(lo), np.float64(hi)) * sd + cur)
             except FloatingPointError:
                 prop = float(_truncnorm._ppf(np.float64(u), np.float64(lo), np.float64(np.inf)) * sd + cur)
-        fwd = _truncnorm.logpdf(prop, lo, hi, loc=cur, scale=sd)
+        fwd = _tn_logpdf(prop, lo, hi, cur, sd)
         lo_r, hi_r = (0 - prop) / sd, (1 - prop) / sd
-        rev = _truncnorm.logpdf(cur, lo_r, hi_r, loc=prop, scale=sd)
+        rev = _tn_logpdf(cur, lo_r, hi_r, prop, sd)
         if which == 'FP':
             ll_new, ll_old = self._ll_at([(prop, self.FN), (cur, self.FN)])
         else:
