@@ -21,6 +21,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
 
 MAX_EXTRA = 32
 ST_K, ST_TDONE, ST_FLAGS, ST_NEXTRA, ST_BIRTHS, ST_MOVED, ST_SLOW = range(7)
+ST_NUNC = 10
 ST_WORDS = 16
 STOP_EXTRA_FULL, STOP_REPACK, STOP_TAPE_EMPTY, STOP_CAPACITY, STOP_HANG = 1, 2, 4, 8, 0x100
 VISIT_BYTES = 64
@@ -59,6 +60,7 @@ class SweepArgs(C.Structure):
         ('lpx', C.c_void_p), ('llx', C.c_void_p), ('ldx', C.c_int32),
         ('scratch', C.c_void_p),
         ('visit', C.c_void_p), ('cand', C.c_void_p), ('t_begin', C.c_int32), ('t_end', C.c_int32),
+        ('visit_c', C.c_void_p), ('cand_c', C.c_void_p),
         ('beta_rows', C.c_void_p), ('n_beta_rows', C.c_int32),
         ('seed', C.c_uint64), ('stream_id', C.c_uint64),
         ('logn', C.c_void_p),
@@ -76,7 +78,8 @@ SIGNATURES = {
     'bnpc_logprob_tables': [_P, _P, _I, _I, _D, _D, _P, _P],
     'bnpc_ll_matrix': [_P, _P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _P],
     'bnpc_gibbs_prepare': [_P, _P, _P, _P, _P, _I, _D, _D, _D, _P, _P],
-    'bnpc_gibbs_candidates': [_P, _I, _I, _P, _P, _P, _I, _D, _D, _P],
+    'bnpc_gibbs_candidates': [_P, _I, _I, _P, _P, _P, _I, _D, _D, _P, _P],
+    'bnpc_gibbs_compact': [_P, _P, _I, _P, _P, _P, _P, _P],
     'bnpc_gibbs_epoch_begin': [_P, _I, _P, _P, _P, _I, _P, _I, _P],
     'bnpc_gibbs_sweep': [C.POINTER(SweepArgs), _I, _P],
     'bnpc_group_members': [_P, _I, _P, _P, _P, _I, _P, _P],
@@ -102,7 +105,7 @@ _lib = None
 launch_count = 0          # kernels launched through this binding (bench.py reports it)
 
 # kernels launched per entry point (memset nodes are not counted)
-_KERNELS_PER_CALL = {'bnpc_gather_members': 3, 'bnpc_rg_sides': 2, 'bnpc_rg_scan': 3}
+_KERNELS_PER_CALL = {'bnpc_gather_members': 3, 'bnpc_rg_sides': 2, 'bnpc_rg_scan': 3, 'bnpc_gibbs_compact': 2}
 
 
 class _Lib:

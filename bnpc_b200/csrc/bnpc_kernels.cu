@@ -307,59 +307,131 @@ __global__ void gibbs_prepare_kernel(const int32_t* __restrict__ perm, const dou
     v.c_old = -1;
     v.n_opt = BNPC_MAX_OPT + 1;       // "unknown rivals" until bnpc_gibbs_candidates has run
     v.i_old = 0;
-    v.pad[0] = v.pad[1] = v.pad[2] = 0;
+    v.t = t;
+    v.flags = 0;
+    v.e_max = 1.0f;
     visit[t] = v;
 }
 
 // static options of every visited cell (see include/bnpc_b200.h), kept in column order: columns
 // follow the list order at the start of the epoch and deaths preserve relative order, so a walk
 // over the options is a walk in list order.
-__global__ void gibbs_candidates_kernel(const double* __restrict__ ll, int ldk, int K,
-                                        const int32_t* __restrict__ col_of_id,
-                                        bnpc_visit_t* __restrict__ visit, bnpc_cand_t* __restrict__ cand,
-                                        int C, double slack, double c_norm) {
+#define CAND_THREADS 128
+__global__ void __launch_bounds__(CAND_THREADS)
+gibbs_candidates_kernel(const double* __restrict__ ll, int ldk, int K,
+                        const int32_t* __restrict__ col_of_id,
+                        bnpc_visit_t* __restrict__ visit, bnpc_cand_t* __restrict__ cand,
+                        int C, double slack, double c_norm, int32_t* __restrict__ blk) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= C) return;
-    const double* row = ll + (long long)r * ldk;
-    const int c_old = col_of_id[visit[r].old];
-    const double lnew_ll = visit[r].lnew + c_norm;          // ll_new + log(alpha)
-    bnpc_cand_t out;
-    double val[BNPC_MAX_OPT];
+    int uncertain = 0;
+    if (r < C) {
+        const double* row = ll + (long long)r * ldk;
+        const int c_old = col_of_id[visit[r].old];
+        const double lnew_ll = visit[r].lnew + c_norm;          // ll_new + log(alpha)
+        const double u = visit[r].u;
+        bnpc_cand_t out;
+        double val[BNPC_MAX_OPT];
 #pragma unroll
-    for (int i = 0; i < BNPC_MAX_OPT; ++i) { out.e[i] = 0.0; out.col[i] = 0; val[i] = -BNPC_INF; }
-    out.pad[0] = out.pad[1] = out.pad[2] = 0;
-    int n = BNPC_MAX_OPT + 1, i_old = 0;
-    double ref = 0.0, e_new = 0.0;
-    if (c_old >= 0 && c_old < K) {
-        const double v_old = row[c_old];
-        const double thr = v_old - 40.0 - slack;
-        n = 0;
-        ref = fmax(v_old, lnew_ll);
-        for (int k = 0; k < K; ++k) {
-            const double v = row[k];
-            if (k != c_old && !(v > thr)) continue;
-            if (k == c_old) i_old = n;
+        for (int i = 0; i < BNPC_MAX_OPT; ++i) { out.e[i] = 0.0; out.col[i] = 0; val[i] = -BNPC_INF; }
+        out.pad[0] = out.pad[1] = out.pad[2] = 0;
+        int n = BNPC_MAX_OPT + 1, i_old = 0, flags = 0;
+        double ref = 0.0, e_new = 0.0, e_max = 1.0;
+        if (c_old >= 0 && c_old < K) {
+            const double v_old = row[c_old];
+            const double thr = v_old - 40.0 - slack;
+            n = 0;
+            ref = fmax(v_old, lnew_ll);
+            for (int k = 0; k < K; ++k) {
+                const double v = row[k];
+                if (k != c_old && !(v > thr)) continue;
+                if (k == c_old) i_old = n;
 #pragma unroll
-            for (int i = 0; i < BNPC_MAX_OPT; ++i)
-                if (i == n) { val[i] = v; out.col[i] = (uint16_t)k; }
-            ref = fmax(ref, v);
-            ++n;
+                for (int i = 0; i < BNPC_MAX_OPT; ++i)
+                    if (i == n) { val[i] = v; out.col[i] = (uint16_t)k; }
+                ref = fmax(ref, v);
+                ++n;
+            }
+            if (n > BNPC_MAX_OPT) {
+                n = BNPC_MAX_OPT + 1;
+            } else {
+                e_max = 0.0;
+#pragma unroll
+                for (int i = 0; i < BNPC_MAX_OPT; ++i)
+                    if (i < n) { out.e[i] = exp(val[i] - ref); e_max = fmax(e_max, out.e[i]); }
+                e_new = exp(lnew_ll - ref);
+                if (n == 1 && lnew_ll < v_old - 40.0 && u > 3e-10 && u < 1.0 - 3e-10)
+                    flags = BNPC_VISIT_CERTAIN;
+            }
         }
-        if (n > BNPC_MAX_OPT) {
-            n = BNPC_MAX_OPT + 1;
-        } else {
-#pragma unroll
-            for (int i = 0; i < BNPC_MAX_OPT; ++i)
-                if (i < n) out.e[i] = exp(val[i] - ref);
-            e_new = exp(lnew_ll - ref);
-        }
+        visit[r].e_new = e_new;
+        visit[r].ref = ref;
+        visit[r].c_old = c_old;
+        visit[r].n_opt = n;
+        visit[r].i_old = i_old;
+        visit[r].flags = flags;
+        visit[r].e_max = __double2float_ru(e_max);
+        cand[r] = out;
+        uncertain = !(flags & BNPC_VISIT_CERTAIN);
     }
-    visit[r].e_new = e_new;
-    visit[r].ref = ref;
-    visit[r].c_old = c_old;
-    visit[r].n_opt = n;
-    visit[r].i_old = i_old;
-    cand[r] = out;
+    const int cnt = __syncthreads_count(uncertain);
+    if (threadIdx.x == 0) blk[blockIdx.x] = cnt;
+}
+
+// exclusive scan of the per-block counts (one CTA); blk[nb] and st[BNPC_ST_NUNC] = total
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int32_t* blk, int nb, int32_t* st) {
+    __shared__ int wsum[33];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int per = (nb + 1023) / 1024;
+    const int j0 = tid * per, j1 = min(j0 + per, nb);
+    int s = 0;
+    for (int j = j0; j < j1; ++j) s += blk[j];
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const int x = wsum[lane];
+        int si = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, si, o);
+            if (lane >= o) si += t;
+        }
+        wsum[lane] = si - x;
+        if (lane == 31) wsum[32] = si;
+    }
+    __syncthreads();
+    int run = wsum[w] + inc - s;
+    for (int j = j0; j < j1; ++j) { const int c = blk[j]; blk[j] = run; run += c; }
+    if (tid == 0) { blk[nb] = wsum[32]; st[BNPC_ST_NUNC] = wsum[32]; }
+}
+
+__global__ void __launch_bounds__(CAND_THREADS)
+compact_scatter_kernel(const bnpc_visit_t* __restrict__ visit, const bnpc_cand_t* __restrict__ cand,
+                       int C, const int32_t* __restrict__ blk, bnpc_visit_t* __restrict__ visit_c,
+                       bnpc_cand_t* __restrict__ cand_c) {
+    __shared__ int wcnt[CAND_THREADS / 32];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool take = r < C && !(visit[r].flags & BNPC_VISIT_CERTAIN);
+    const unsigned m = __ballot_sync(FULL, take);
+    if (lane == 0) wcnt[w] = __popc(m);
+    __syncthreads();
+    if (!take) return;
+    int pos = blk[blockIdx.x] + __popc(m & ((1u << lane) - 1u));
+    for (int i = 0; i < w; ++i) pos += wcnt[i];
+    const uint4* sv = reinterpret_cast<const uint4*>(visit + r);
+    uint4* dv = reinterpret_cast<uint4*>(visit_c + pos);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(bnpc_visit_t) / 16); ++i) dv[i] = sv[i];
+    const uint4* sc = reinterpret_cast<const uint4*>(cand + r);
+    uint4* dc = reinterpret_cast<uint4*>(cand_c + pos);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(bnpc_cand_t) / 16); ++i) dc[i] = sc[i];
 }
 
 __global__ void gibbs_epoch_begin_kernel(const int32_t* __restrict__ live, int K, int32_t* lst,
@@ -431,6 +503,7 @@ struct SweepShared {
     int n_extra, births, moved, slow;
     int tmp_i, pick;
     int hang;
+    int compact, crec;                          // compact mode on / next compacted record
 };
 
 // One exact categorical draw for a list that fits a warp (libs/CRP.py:88-100 + numpy choice,
@@ -531,32 +604,46 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
 #define SW_GUARD 1e-10        /* draws closer than this (in probability) to an interval edge go exact */
 
 // Sequencer regime (lists of at most SW_MAXL clusters), run by warp 0.  The sweep is
-// sequential, but a cell that ends up where it was leaves every size unchanged, so 32
-// consecutive cells are scored in parallel (lane <-> cell) against the current sizes;
-// everything before the first cell that does not stay is then exact and that cell is resolved.
-// Scoring looks only at the cell's static options (bnpc_gibbs_candidates) plus clusters born in
-// this epoch; every other cluster sits on the reference's 1e-15 probability floor.  Restricted to
-// the options the draw of _normalize_log_probs + numpy choice (libs/CRP.py:88-100, 277) is LINEAR
-// in the cluster sizes: weight_i = n_i * exp(ll_i - ref), the new-cluster option weighs
-// alpha * exp(ll_new - ref), and the pick is the first option whose running sum exceeds
-// u * total -- integer sizes times per-cell constants, no transcendental in the sequential part.
-// A move changes two sizes; later lanes are scored again only if one of their options was
-// touched.  The linear form and the reference's log-space arithmetic differ by rounding
-// (~1e-13) and by the floored entries (<= 1024e-15): whenever u is within SW_GUARD of an
-// interval edge, and for cluster death, a new cluster, or more than BNPC_MAX_CAND rivals, the
-// cell goes through the exact draw over the whole list in the reference's own arithmetic
-// (warp-cooperative for lists of up to 31 clusters, CTA-wide otherwise).
+// sequential, but only through the cluster sizes.  32 consecutive records are scored in
+// parallel (lane <-> visit) against the current sizes, looking only at the cell's static
+// options (bnpc_gibbs_candidates) plus clusters born in this epoch; every other cluster sits
+// on the reference's 1e-15 probability floor.  Restricted to the options the draw of
+// _normalize_log_probs + numpy choice (libs/CRP.py:88-100, 277) is LINEAR in the cluster sizes:
+// weight_i = n_i * exp(ll_i - ref), the new-cluster option weighs alpha * exp(ll_new - ref), and
+// the pick is the first option whose running sum exceeds u * total -- integer sizes times
+// per-cell constants, no transcendental in the sequential part.
+//
+// Each lane keeps the margin of its decision in weight units.  One move shifts every interval
+// edge and u*total of another cell by at most 2*e_lim, so a lane's decision survives nb earlier
+// moves while margin > 4*e_lim*nb: all movers of the stage up to the first lane whose margin (or
+// cluster size) does not allow that are applied AT ONCE; the rest is scored again.  The linear
+// form and the reference's log-space arithmetic differ by rounding (~1e-13) and by the floored
+// entries (<= 1024e-15): whenever u is within SW_GUARD of an interval edge, and for cluster
+// death, a new cluster, or more than BNPC_MAX_CAND rivals, the cell goes through the exact draw
+// over the whole list in the reference's own arithmetic (warp-cooperative for lists of up to 31
+// clusters, CTA-wide otherwise).
+//
+// Compact mode: while no cluster was born in the epoch and every cluster has at least two cells,
+// visits flagged BNPC_VISIT_CERTAIN stay whatever the sizes are; the sequencer then walks only
+// the compacted records of the other visits (bnpc_gibbs_compact).  The first event that could
+// invalidate this (a birth, a cluster down to one cell) sends the rest of the epoch through the
+// dense records.
 __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
     const int lane = threadIdx.x;
+    const unsigned lt_mask = (1u << lane) - 1u;
     int L = sh.L;
-    const int t0 = sh.t;
     const int ldk = a.ldk;
     int moved = 0, slow = 0;
 
+    int cmin = 0x7fffffff;
     for (int j = lane; j < L; j += 32) {
         const int id = a.lst[j];
-        sh.s_id[j] = id; sh.s_cnt[j] = a.cnt[id]; sh.s_src[j] = a.col_of_id[id];
+        const int c = a.cnt[id];
+        sh.s_id[j] = id; sh.s_cnt[j] = c; sh.s_src[j] = a.col_of_id[id];
+        cmin = min(cmin, c);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmin = min(cmin, __shfl_xor_sync(FULL, cmin, o));
     if (lane == 0) {
         for (int s = 0; s < SW_NSTAGE; ++s) mbar_init(&sh.bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -565,21 +652,27 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
     __syncwarp();
     sweep_rebuild_maps(sh, L);
     const int n_extra = sh.n_extra;
+    const bool compact = sh.compact && cmin >= 2 && n_extra == 0;
+    const int need_cnt = compact ? 2 : 1;       // cells a cluster keeps after a batched move
+
+    const bnpc_visit_t* vbase = compact ? a.visit_c : a.visit + a.t_epoch0;
+    const bnpc_cand_t* cbase = compact ? a.cand_c : a.cand + a.t_epoch0;
+    const int n_rec = compact ? a.st[BNPC_ST_NUNC] : a.t_end - a.t_epoch0;
+    const int first_rec = compact ? sh.crec : sh.t - a.t_epoch0;
 
     // stages = 32 consecutive visit + option records, streamed into shared memory by bulk
     // async copies (TMA engine) NSTAGE ahead of the sequencer
-    const int s_first = (t0 - a.t_epoch0) / SW_STAGE_CELLS;
-    const int s_last = (a.t_end - 1 - a.t_epoch0) / SW_STAGE_CELLS;
-    const int n_stages = s_last - s_first + 1;
+    const int s_first = first_rec / SW_STAGE_CELLS;
+    const int n_stages = (first_rec < n_rec) ? (n_rec - 1) / SW_STAGE_CELLS - s_first + 1 : 0;
     auto issue = [&](int g) {                      // lane 0 only
         const int slot = g % SW_NSTAGE;
-        const int sp = (s_first + g) * SW_STAGE_CELLS;            // position relative to the epoch
-        const int nc = min(SW_STAGE_CELLS, a.t_end - a.t_epoch0 - sp);
+        const int sp = (s_first + g) * SW_STAGE_CELLS;
+        const int nc = min(SW_STAGE_CELLS, n_rec - sp);
         const uint32_t b_v = (uint32_t)(nc * sizeof(bnpc_visit_t));
         const uint32_t b_c = (uint32_t)(nc * sizeof(bnpc_cand_t));
         mbar_expect_tx(&sh.bar[slot], b_v + b_c);
-        bulk_g2s(sh.vis_stage[slot], a.visit + a.t_epoch0 + sp, b_v, &sh.bar[slot]);
-        bulk_g2s(sh.cand_stage[slot], a.cand + a.t_epoch0 + sp, b_c, &sh.bar[slot]);
+        bulk_g2s(sh.vis_stage[slot], vbase + sp, b_v, &sh.bar[slot]);
+        bulk_g2s(sh.cand_stage[slot], cbase + sp, b_c, &sh.bar[slot]);
     };
     int issued = 0;
     if (lane == 0)
@@ -588,7 +681,7 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
 
     int waited = 0;
     bool leave = false;
-    int next_t = a.t_end;
+    int next_t = a.t_end, next_rec = n_rec;
     for (int g = 0; g < n_stages && !leave; ++g) {
         const int slot = g % SW_NSTAGE;
         const uint32_t parity = (uint32_t)((g / SW_NSTAGE) & 1);
@@ -599,12 +692,12 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
             }
         }
         waited = g + 1;
-        const int ts = a.t_epoch0 + (s_first + g) * SW_STAGE_CELLS;
-        const int nc = min(SW_STAGE_CELLS, a.t_end - ts);
+        const int rec0 = (s_first + g) * SW_STAGE_CELLS;
+        const int nc = min(SW_STAGE_CELLS, n_rec - rec0);
         const bnpc_visit_t* vis = sh.vis_stage[slot];
         const int my = lane < nc ? lane : 0;
         const bnpc_visit_t v = vis[my];
-        const long long tx = ts + lane - a.t_epoch0;
+        const long long tx = v.t - a.t_epoch0;
         // the lane's options live in registers for the whole stage
         double e[BNPC_MAX_OPT];
         int col[BNPC_MAX_OPT];
@@ -614,29 +707,26 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
             for (int i = 0; i < BNPC_MAX_OPT; ++i) { e[i] = cd->e[i]; col[i] = cd->col[i]; }
         }
         const int n_opt = v.n_opt, i_old = v.i_old;
-        // warp-uniform bound of the option loops; largest option weight of the lane
+        // warp-uniform bound of the option loops
         int n_max = (lane < nc && n_opt <= BNPC_MAX_OPT) ? n_opt : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(FULL, n_max, o));
-        double e_max = 0.0;
-#pragma unroll
-        for (int i = 0; i < BNPC_MAX_OPT; ++i) e_max = fmax(e_max, e[i]);
 
-        int lo_lane = max(0, t0 - ts);
+        int lo_lane = max(0, first_rec - rec0);
         bool need_eval = lane >= lo_lane && lane < nc;      // per lane
-        int outcome = OUT_STAY, to_pos = -1, p_old = -1;
-        unsigned long long bloom = 0ull;                    // list positions (mod 64) it depends on
+        int outcome = OUT_STAY, to_pos = -1, p_old = -1, c_own = 0;
         double slack = 0.0;                                 // validity margin of `outcome` (weight units)
-        double e_lim = e_max;                               // largest weight among all its options
+        double e_lim = (double)v.e_max;                     // largest weight among all its options
         while (lo_lane < nc) {
             if (need_eval) {
                 need_eval = false;
                 outcome = OUT_COMPLEX;
-                bloom = 0ull;
                 to_pos = -1;
                 slack = 0.0;
+                c_own = 0;
                 p_old = (n_opt <= BNPC_MAX_OPT) ? sh.s_pos_of_col[v.c_old] : -1;
-                if (p_old >= 0 && sh.s_cnt[p_old] > 1 && sh.s_id[p_old] == v.old) {
+                if (p_old >= 0) c_own = sh.s_cnt[p_old];
+                if (p_old >= 0 && c_own > 1 && sh.s_id[p_old] == v.old) {
                     double cum[BNPC_MAX_OPT];
                     int pos[BNPC_MAX_OPT];
                     double S = 0.0;
@@ -650,7 +740,7 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
                         if (i < n_opt) {
                             const int p = sh.s_pos_of_col[col[i]];
                             int c = 0;
-                            if (p >= 0) { c = sh.s_cnt[p]; bloom |= 1ull << (p & 63); }
+                            if (p >= 0) c = sh.s_cnt[p];
                             if (i == i_old) --c;
                             pos[i] = p;
                             S += (double)c * e[i];
@@ -661,7 +751,6 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
                     for (int x = 0; x < n_extra; ++x) {       // clusters born in this epoch
                         const int pe = sh.s_xpos[x];
                         if (pe >= 0) {
-                            bloom |= 1ull << (pe & 63);
                             const double ex = exp(a.llx[(long long)x * a.ldx + tx] - v.ref);
                             e_lim = fmax(e_lim, ex);
                             Sx += (double)sh.s_cnt[pe] * ex;
@@ -697,52 +786,56 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
                     }
                 }
             }
-            const unsigned pend = __ballot_sync(FULL, lane >= lo_lane && lane < nc && outcome != OUT_STAY);
+            const bool act = lane >= lo_lane && lane < nc;
+            const unsigned pend = __ballot_sync(FULL, act && outcome != OUT_STAY);
             if (!pend) break;
-            const int f = __ffs(pend) - 1;
-            const int of = __shfl_sync(FULL, outcome, f);
-            if (of == OUT_MOVE) {
-                const int kf = __shfl_sync(FULL, p_old, f), rf = __shfl_sync(FULL, to_pos, f);
-                if (lane == 0) {
-                    const int c = sh.s_cnt[kf] - 1;
-                    sh.s_cnt[kf] = c;
-                    a.cnt[sh.s_id[kf]] = c;
-                    a.assign[vis[f].cell] = sh.s_id[rf];
-                } else if (lane == 1) {
-                    const int c = sh.s_cnt[rf] + 1;
-                    sh.s_cnt[rf] = c;
-                    a.cnt[sh.s_id[rf]] = c;
-                }
-                __syncwarp();
-                ++moved;
-                // A move shifts two sizes by one: every interval edge and u*total of a later lane
-                // that has one of the two clusters among its options move by at most 2*e_lim each.
-                // Such a lane keeps its decision while its margin lasts and is scored again when
-                // the margin is used up -- or at once if the shrunk cluster is down to one cell.
-                if (lane > f && lane < nc && (((bloom >> (kf & 63)) | (bloom >> (rf & 63))) & 1ull)) {
-                    slack -= 4.0 * e_lim;
-                    if (!(slack > 0.0) || sh.s_cnt[kf] <= 1) need_eval = true;
-                }
-                lo_lane = f + 1;
-            } else {
-                ++slow;
-                if (L > 31) {                       // CTA-wide exact draw, then come back
-                    if (lane == 0) sh.pending = 2;
-                    next_t = ts + f;
-                    leave = true;
-                    break;
-                }
-                const int status = sweep_exact_cell(a, sh, vis[f],
-                                                    a.ll + (long long)(ts + f - a.t_epoch0) * ldk, ts + f, L);
-                if (status) ++moved;
-                if (status == 2) {
-                    next_t = ts + f + 1;
-                    leave = true;
-                    break;
-                }
-                lo_lane = f + 1;
-                if (status != 0) need_eval = lane >= lo_lane && lane < nc;   // structure may have changed
+            // would this lane's decision survive if every earlier pending lane moved a cell?
+            const int nb = __popc(pend & lt_mask);
+            bool ok = true;
+            if (act) {
+                if (outcome == OUT_COMPLEX) ok = false;
+                else if (nb > 0) ok = (slack - 4.0 * e_lim * (double)nb > 0.0) &&
+                                      (c_own - nb > ((outcome == OUT_MOVE) ? need_cnt : 1));
+                else ok = (outcome == OUT_STAY) || (c_own > need_cnt);
             }
+            const unsigned bad = __ballot_sync(FULL, !ok);
+            const int fb = bad ? (__ffs(bad) - 1) : 32;
+            const unsigned batch = pend & ((fb >= 32) ? FULL : ((1u << fb) - 1u));
+            if (batch) {
+                // all pending lanes before the first doubtful one are movers: apply them at once
+                if ((batch >> lane) & 1u) {
+                    atomicSub(&sh.s_cnt[p_old], 1);
+                    atomicAdd(&sh.s_cnt[to_pos], 1);
+                    a.assign[v.cell] = sh.s_id[to_pos];
+                }
+                moved += __popc(batch);
+                __syncwarp();
+                if (fb >= nc) break;
+                lo_lane = fb;                               // score the rest against the new sizes
+                need_eval = lane >= lo_lane && lane < nc;
+                continue;
+            }
+            // the first pending lane cannot take the linear form: exact draw
+            const int f = fb;
+            const int t_f = __shfl_sync(FULL, v.t, f);
+            ++slow;
+            if (L > 31) {                           // CTA-wide exact draw, then come back
+                if (lane == 0) sh.pending = 2;
+                next_t = t_f; next_rec = rec0 + f + 1;
+                leave = true;
+                break;
+            }
+            const int status = sweep_exact_cell(a, sh, vis[f], a.ll + (long long)(t_f - a.t_epoch0) * ldk, t_f, L);
+            if (status) ++moved;
+            if (status == 2 || (compact && status != 0)) {
+                // a birth, or (compact mode) sizes changed outside the batched bookkeeping:
+                // re-enter and decide again whether the compacted records may be used
+                next_t = t_f + 1; next_rec = rec0 + f + 1;
+                leave = true;
+                break;
+            }
+            lo_lane = f + 1;
+            if (status != 0) need_eval = lane >= lo_lane && lane < nc;   // structure may have changed
         }
         __syncwarp();
         if (!leave && lane == 0 && issued < n_stages) issue(issued);
@@ -756,9 +849,12 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
         }
     }
     __syncwarp();
+    // sizes changed by batched moves live in shared memory only: publish them
+    for (int j = lane; j < L; j += 32) a.cnt[sh.s_id[j]] = sh.s_cnt[j];
     if (lane == 0) {
         sh.L = L;
         sh.t = next_t;
+        if (compact) sh.crec = next_rec; else sh.compact = 0;
         sh.moved += moved;
         sh.slow += slow;
     }
@@ -952,6 +1048,9 @@ gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
         sh.moved = a.st[BNPC_ST_MOVED];
         sh.slow = a.st[BNPC_ST_SLOW];
         sh.hang = 0;
+        sh.compact = (a.visit_c != nullptr && a.cand_c != nullptr && a.t_begin == a.t_epoch0 &&
+                      sh.n_extra == 0) ? 1 : 0;
+        sh.crec = 0;
     }
     __syncthreads();
     if (sh.stop) return;                            // an earlier launch of this sweep stopped
@@ -1568,12 +1667,26 @@ int bnpc_gibbs_prepare(const int32_t* perm, const double* u, const int32_t* assi
 
 int bnpc_gibbs_candidates(const double* ll, int ldk, int K, const int32_t* col_of_id,
                           bnpc_visit_t* visit_t0, bnpc_cand_t* cand_t0, int C, double slack,
-                          double c_norm, void* stream) {
+                          double c_norm, int32_t* blk, void* stream) {
     if (C <= 0) return 0;
     if (K > SW_MAXL) return bad_arg("candidates need K <= 1024");
-    gibbs_candidates_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(ll, ldk, K, col_of_id, visit_t0,
-                                                                          cand_t0, C, slack, c_norm);
+    if (!blk) return bad_arg("blk");
+    gibbs_candidates_kernel<<<cdiv(C, CAND_THREADS), CAND_THREADS, 0, (cudaStream_t)stream>>>(
+        ll, ldk, K, col_of_id, visit_t0, cand_t0, C, slack, c_norm, blk);
     LAUNCH_CHECK("gibbs_candidates");
+    return 0;
+}
+
+int bnpc_gibbs_compact(const bnpc_visit_t* visit_t0, const bnpc_cand_t* cand_t0, int C, int32_t* blk,
+                       bnpc_visit_t* visit_c, bnpc_cand_t* cand_c, int32_t* st, void* stream) {
+    if (C <= 0) return 0;
+    if (!blk || !visit_c || !cand_c || !st) return bad_arg("compact buffers");
+    const int nb = cdiv(C, CAND_THREADS);
+    compact_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(blk, nb, st);
+    LAUNCH_CHECK("compact_scan");
+    compact_scatter_kernel<<<nb, CAND_THREADS, 0, (cudaStream_t)stream>>>(visit_t0, cand_t0, C, blk, visit_c,
+                                                                         cand_c);
+    LAUNCH_CHECK("compact_scatter");
     return 0;
 }
 

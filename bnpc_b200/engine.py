@@ -248,6 +248,9 @@ class DeviceCRP:
             self.assign_d = torch.zeros(N, dtype=torch.int32, device=self.device)
             self.visit = torch.empty(N * _lib.VISIT_BYTES, dtype=torch.uint8, device=self.device)
             self.cand = torch.empty(N * _lib.CAND_BYTES, dtype=torch.uint8, device=self.device)
+            self.visit_c = torch.empty(N * _lib.VISIT_BYTES, dtype=torch.uint8, device=self.device)
+            self.cand_c = torch.empty(N * _lib.CAND_BYTES, dtype=torch.uint8, device=self.device)
+            self.cblk = torch.empty((N + 127) // 128 + 2, dtype=torch.int32, device=self.device)
             self.members = torch.empty(N, dtype=torch.int32, device=self.device)
             self.cells_d = torch.empty(N + 8, dtype=torch.int32, device=self.device)
             self.half = torch.zeros(N + 8, dtype=torch.int32, device=self.device)
@@ -465,11 +468,16 @@ class DeviceCRP:
                     L.ll_matrix(sh.x1.data_ptr(), sh.x0.data_ptr(), sh.W, M,
                                 self.visit.data_ptr() + t * _lib.VISIT_BYTES + _lib.VISIT_CELL_OFFSET,
                                 _lib.VISIT_BYTES // 4, rows, lp.data_ptr(), K, ll.data_ptr(), ldk, sp)
-                if ldk <= _lib.MAX_LIST:
+                compacted = ldk <= _lib.MAX_LIST
+                if compacted:
                     L.gibbs_candidates(ll.data_ptr(), ldk, K, self.col_of_id.data_ptr(),
                                        self.visit.data_ptr() + t * _lib.VISIT_BYTES,
                                        self.cand.data_ptr() + t * _lib.CAND_BYTES, rows,
-                                       float(np.log(N)), c_norm, sp)
+                                       float(np.log(N)), c_norm, self.cblk.data_ptr(), sp)
+                    L.gibbs_compact(self.visit.data_ptr() + t * _lib.VISIT_BYTES,
+                                    self.cand.data_ptr() + t * _lib.CAND_BYTES, rows,
+                                    self.cblk.data_ptr(), self.visit_c.data_ptr(),
+                                    self.cand_c.data_ptr(), self.st.data_ptr(), sp)
                 a = _lib.SweepArgs(
                     x1=sh.x1.data_ptr(), x0=sh.x0.data_ptr(), W=sh.W, N=N, M=M,
                     assign=self.assign_d.data_ptr(), cnt=self.cnt.data_ptr(), lst=self.lst.data_ptr(),
@@ -478,6 +486,8 @@ class DeviceCRP:
                     ll=ll.data_ptr(), ldk=ldk, t_epoch0=t,
                     lpx=lpx.data_ptr(), llx=llx.data_ptr(), ldx=rows, scratch=scratch.data_ptr(),
                     visit=self.visit.data_ptr(), cand=self.cand.data_ptr(), t_begin=t, t_end=t + rows,
+                    visit_c=self.visit_c.data_ptr() if compacted else None,
+                    cand_c=self.cand_c.data_ptr() if compacted else None,
                     beta_rows=beta_tape.data_ptr() if beta_tape is not None else None,
                     n_beta_rows=n_tape, seed=seed, stream_id=stream_id,
                     logn=sh.logn.data_ptr(), c_norm=c_norm, FN=FN, FP=FP,
@@ -510,6 +520,7 @@ class DeviceCRP:
                                        f'{int(st[_lib.ST_BIRTHS])}')
             self.sweep_stats = dict(epochs=epochs, births=int(st[_lib.ST_BIRTHS]),
                                     moved=int(st[_lib.ST_MOVED]), slow=int(st[_lib.ST_SLOW]),
+                                    uncertain=int(st[_lib.ST_NUNC]),
                                     kcycles=int(st[8]), us=int(st[9]) * 1.024,
                                     sm_mhz=(int(st[8]) / max(1, int(st[9]))) * 1e3)
         self._touch()

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BNPC_ABI_VERSION 1
+#define BNPC_ABI_VERSION 2
 
 /* capacity of clusters born since the ll matrix of the current epoch was built */
 #define BNPC_MAX_EXTRA 32
@@ -52,6 +52,7 @@ extern "C" {
 #define BNPC_ST_SLOW     6   /* cells that took the exact (slow) path          */
 #define BNPC_ST_CYCLES   8   /* SM clock cycles of the last sweep launch, / 1024 */
 #define BNPC_ST_NANOS    9   /* globaltimer ns of the last sweep launch, / 1024  */
+#define BNPC_ST_NUNC     10  /* visits of the epoch that are not statically certain (bnpc_gibbs_compact) */
 #define BNPC_ST_WORDS    16
 
 #define BNPC_STOP_EXTRA_FULL  1  /* BNPC_MAX_EXTRA births: start a new epoch      */
@@ -70,8 +71,15 @@ typedef struct {
     int32_t c_old;  /* ll column of that cluster in the current epoch                  */
     int32_t n_opt;  /* options (own cluster + rivals); BNPC_MAX_OPT+1 = too many/unknown */
     int32_t i_old;  /* index of the own cluster among the options                      */
-    int32_t pad[3];
+    int32_t t;      /* position of the visit in the sweep                              */
+    int32_t flags;  /* BNPC_VISIT_CERTAIN                                              */
+    float   e_max;  /* largest option weight e[i], rounded up                          */
 } bnpc_visit_t;
+/* The cell stays where it is whatever the cluster sizes are (as long as its cluster keeps a
+ * second member and no cluster was born since the options were listed): its own cluster is its
+ * only option, the new-cluster option is more than 40 nats below it, and u is farther than
+ * 3e-10 from 0 and 1.  The sequential part of the sweep may skip such visits.               */
+#define BNPC_VISIT_CERTAIN 1
 
 /* options of one visited cell (96 bytes): its own cluster and the rivals that can come
  * within 40 nats of it for ANY cluster sizes, in ll-column order (= list order).  The
@@ -134,7 +142,14 @@ int bnpc_gibbs_prepare(const int32_t* perm, const double* u, const int32_t* assi
  * sequential sweep then only looks at these options.  c_norm = log(N-1+alpha).         */
 int bnpc_gibbs_candidates(const double* ll, int ldk, int K, const int32_t* col_of_id,
                           bnpc_visit_t* visit_t0, bnpc_cand_t* cand_t0, int C, double slack,
-                          double c_norm, void* stream);
+                          double c_norm, int32_t* blk, void* stream);
+/* blk (scratch, [ceil(C/128)+1] ints) receives per-block counts of the visits that are not
+ * BNPC_VISIT_CERTAIN.  bnpc_gibbs_compact then copies those visit and option records, in
+ * visiting order, to visit_c / cand_c and writes their number to st[BNPC_ST_NUNC]: the
+ * sequential sweep walks only them while no cluster is born and every cluster keeps two cells. */
+int bnpc_gibbs_compact(const bnpc_visit_t* visit_t0, const bnpc_cand_t* cand_t0, int C,
+                       int32_t* blk, bnpc_visit_t* visit_c, bnpc_cand_t* cand_c, int32_t* st,
+                       void* stream);
 /* Start of an epoch: rebuild cnt[] from the host-authoritative list
  * live[2*j] = id, live[2*j+1] = size (list order), set col_of_id[id] = j and
  * clear the epoch's extra-cluster bookkeeping.  first != 0 also resets the
@@ -154,6 +169,8 @@ typedef struct {
     double* scratch /* [idcap+1] */;
     /* sweep inputs */
     const bnpc_visit_t* visit; const bnpc_cand_t* cand; int32_t t_begin; int32_t t_end;
+    /* compacted records of the epoch's uncertain visits (bnpc_gibbs_compact) or NULL */
+    const bnpc_visit_t* visit_c; const bnpc_cand_t* cand_c;
     const double* beta_rows /* parity tape [n_beta_rows][M] or NULL */; int32_t n_beta_rows;
     uint64_t seed; uint64_t stream_id;
     /* constants */

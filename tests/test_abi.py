@@ -30,7 +30,7 @@ def test_library_exports_header_symbols():
 def test_ctypes_signatures_match_header():
     declared = set(_declared()) - {'bnpc_abi_version', 'bnpc_last_error'}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.lib().abi_version() == 1
+    assert _lib.lib().abi_version() == 2
 
 
 def test_sweep_args_layout_matches_c():

@@ -68,6 +68,10 @@ CASES = [
     ('panel_learn', 6000, 50, 5, 0.30, True, [1, 1], 'assign', 5, dict(DEFAULT_MOVES, sm_prob=0.4)),
     ('random_init_bigK', 900, 120, 5, 0.10, True, [0.25, 0.25], 'random', 3, dict(DEFAULT_MOVES, sm_prob=0.0)),
     ('random_init_sm', 300, 64, 4, 0.10, False, [0.25, 0.25], 'random', 8, dict(DEFAULT_MOVES, sm_prob=0.5)),
+    # short rows: most cells have several rivals and many move per sweep (batched movers of the sweep)
+    ('noisy_many_movers', 12000, 40, 4, 0.20, True, [0.25, 0.25], 'assign', 5, dict(DEFAULT_MOVES, sm_prob=0.2)),
+    # long rows: most visits are statically certain (compacted records of the sweep)
+    ('mostly_certain', 30000, 300, 10, 0.10, True, [0.25, 0.25], 'assign', 4, dict(DEFAULT_MOVES, sm_prob=0.25)),
 ]
 
 
