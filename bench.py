@@ -278,7 +278,7 @@ def run_gpu(args, cfg):
         torch.cuda.synchronize()
         sampler = ClockSampler(local) if rank == 0 else None
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = _lib.launch_count
+        launches0 = _lib.launch_count()
         start.record()
         bar.wait()
         [t.join() for t in ths]
@@ -288,7 +288,7 @@ def run_gpu(args, cfg):
         if errs:
             raise errs[0]
         ms = torch.tensor([start.elapsed_time(end)], device=dev, dtype=torch.float64)
-        launches = torch.tensor([_lib.launch_count - launches0], device=dev, dtype=torch.float64)
+        launches = torch.tensor([_lib.launch_count() - launches0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.barrier()
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_HERE, 'libbnpc_b200.so')
 SOURCES = [os.path.join(_HERE, 'csrc', 'bnpc_kernels.cu')]
-HEADERS = [os.path.join(_HERE, 'csrc', 'bnpc_math.cuh'),
+HEADERS = [os.path.join(_HERE, 'csrc', 'bnpc_math.cuh'), os.path.join(_HERE, 'csrc', 'bnpc_chain.cuh'),
            os.path.join(_ROOT, 'include', 'bnpc_b200.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
@@ -70,6 +70,39 @@ class SweepArgs(C.Structure):
 
 _P, _I, _D, _U64, _I64, _F = C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_int64, C.c_float
 
+
+class ChainWs(C.Structure):
+    """bnpc_chain_t: device (and pinned host) buffers of one chain."""
+    _fields_ = [(n, C.c_void_p) for n in ('x1', 'x0', 'n1', 'n0', 'logn')] + \
+        [(n, C.c_int32) for n in ('W', 'N', 'M', 'idcap')] + \
+        [(n, C.c_void_p) for n in (
+            'assign', 'theta', 'cnt', 'lst', 'col_of_id', 'rank_of_id', 'live_io', 'st',
+            'visit', 'cand', 'visit_c', 'cand_c', 'cblk', 'perm', 'u',
+            'lp', 'll', 'lpx', 'llx', 'scratch',
+            'ids', 'seg', 'cursor', 'members', 'S1', 'S0', 'rnd', 'declined', 'rl_out', 'rl_tot',
+            'cells', 'half', 'gblk', 'seg3', 'rg_work', 'rg_theta', 'rg_S1', 'rg_S0', 'rg_dec', 'rg_scal',
+            'rg_lp', 'rg_ll2', 'rg_lq', 'rg_logq', 'rg_A', 'rg_orig', 'rg_perm', 'rg_u', 'rg_rnd', 'rg_sd',
+            'rg_beta', 'h_in', 'h_out', 'h_scal')]
+
+
+class Epoch(C.Structure):
+    """bnpc_epoch_t"""
+    _fields_ = [(n, C.c_int32) for n in ('first', 'K', 't', 'rows', 'ldk', 'rand_ready')] + \
+        [(n, C.c_double) for n in ('c1', 'c0', 'lnew_prior', 'c_norm', 'log_n', 'FN', 'FP', 'p', 'q')] + \
+        [('seed', C.c_uint64), ('stream_id', C.c_uint64), ('beta_rows', C.c_void_p),
+         ('n_beta_rows', C.c_int32)] + \
+        [(n, C.c_void_p) for n in ('ev_ll0', 'ev_ll1', 'ev_sw0', 'ev_sw1')]
+
+
+class RgMove(C.Structure):
+    """bnpc_rg_t"""
+    _fields_ = [(n, C.c_int32) for n in ('n', 'n_a', 'cl_i', 'cl_j', 'a_i', 'a_j', 'is_merge', 'rand_ready')] + \
+        [(n, C.c_double) for n in ('alpha', 'FN', 'FP', 'p', 'q')] + [('k6', C.c_double * 6)] + \
+        [('seed', C.c_uint64), ('stream_id', C.c_uint64)]
+
+
+_WS, _EP, _RG = C.POINTER(ChainWs), C.POINTER(Epoch), C.POINTER(RgMove)
+
 # name -> argument ctypes, exactly as declared in include/bnpc_b200.h
 SIGNATURES = {
     'bnpc_pack_planes': [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
@@ -98,14 +131,25 @@ SIGNATURES = {
     'bnpc_rg_scan': [_P, _I, _I, _P, _P, _P, _D, _I, _P, _P, _I, _P, _P, _P],
     'bnpc_apply_split': [_P, _I, _P, _I, _P, _P],
     'bnpc_apply_merge': [_P, _I, _I, _I, _P, _P],
+    'bnpc_chain_gibbs_epoch': [_WS, _EP, _P],
+    'bnpc_chain_stats': [_WS, _I, _I, _P],
+    'bnpc_chain_mh_theta': [_WS, _I, _I, _U64, _U64, _D, _D, _D, _D, _P],
+    'bnpc_chain_loglik': [_WS, _I, C.POINTER(_D), C.POINTER(_D), _I, _I, _D, _D, _P],
+    'bnpc_chain_rg_setup': [_WS, _RG, _P],
+    'bnpc_chain_rg_scan_split': [_WS, _RG, _I, _P],
+    'bnpc_chain_rg_scan_merged': [_WS, _RG, _I, _P],
+    'bnpc_chain_rg_decide_split': [_WS, _RG, _I, _P],
+    'bnpc_chain_rg_decide_merge': [_WS, _RG, _I, _P],
+    'bnpc_chain_rg_apply': [_WS, _RG, _I, _P],
 }
 
 _lock = threading.Lock()
 _lib = None
-launch_count = 0          # kernels launched through this binding (bench.py reports it)
 
-# kernels launched per entry point (memset nodes are not counted)
-_KERNELS_PER_CALL = {'bnpc_gather_members': 3, 'bnpc_rg_sides': 2, 'bnpc_rg_scan': 3, 'bnpc_gibbs_compact': 2}
+
+def launch_count():
+    """kernels launched through the library since it was loaded (bench.py reports it)"""
+    return int(lib()._dll.bnpc_launch_count())
 
 
 class _Lib:
@@ -113,6 +157,7 @@ class _Lib:
         self._dll = C.CDLL(path)
         self._dll.bnpc_last_error.restype = C.c_char_p
         self._dll.bnpc_abi_version.restype = C.c_int
+        self._dll.bnpc_launch_count.restype = C.c_int64
         for name, args in SIGNATURES.items():
             fn = getattr(self._dll, name)
             fn.argtypes = args
@@ -120,15 +165,11 @@ class _Lib:
             setattr(self, name[len('bnpc_'):], self._wrap(name, fn))
 
     def _wrap(self, name, fn):
-        n_k = _KERNELS_PER_CALL.get(name, 1)
-
         def call(*args):
-            global launch_count
             rc = fn(*args)
             if rc != 0:
                 raise RuntimeError(f'{name} failed ({rc}): '
                                    f'{self._dll.bnpc_last_error().decode()}')
-            launch_count += n_k
         call.__name__ = name
         return call
 

@@ -18,6 +18,7 @@
 //   row_loglik_kernel / row_sum_kernel         deterministic [R][M] reductions
 //   gather_* / anchor_swaps / rg_*             split-merge restricted Gibbs support
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -37,10 +38,12 @@ static int bad_arg(const char* what) {
     snprintf(g_err, sizeof(g_err), "invalid argument: %s", what);
     return 2;
 }
+static std::atomic<long long> g_launches{0};
 #define LAUNCH_CHECK(name)                                        \
     do {                                                          \
         cudaError_t e__ = cudaGetLastError();                     \
         if (e__ != cudaSuccess) return fail(name, e__);           \
+        g_launches.fetch_add(1, std::memory_order_relaxed);       \
     } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -1602,6 +1605,7 @@ extern "C" {
 
 int bnpc_abi_version(void) { return BNPC_ABI_VERSION; }
 const char* bnpc_last_error(void) { return g_err; }
+int64_t bnpc_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 int bnpc_pack_planes(const double* x_f64, const int8_t* x_i8, int N, int M, int W, uint32_t* x1,
                      uint32_t* x0, int32_t* n1, int32_t* n0, void* stream) {
@@ -1907,5 +1911,7 @@ int bnpc_apply_merge(const int32_t* cells, int n_a, int n, int id, int32_t* assi
     LAUNCH_CHECK("apply_merge");
     return 0;
 }
+
+#include "bnpc_chain.cuh"
 
 }  // extern "C"

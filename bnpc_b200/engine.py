@@ -166,40 +166,30 @@ class DeviceCRP:
     def _sp(self):
         return self.stream.cuda_stream
 
-    def _buf(self, name, numel, dtype):
-        t = self._bufs.get(name)
-        if t is None or t.numel() < numel or t.dtype != dtype:
-            t = torch.empty(max(int(numel), 1), dtype=dtype, device=self.device)
-            self._bufs[name] = t
+    def _dev(self, name, shape, dtype, zero=False):
+        """(Re)allocate the named workspace buffer and publish its address in the C workspace."""
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+        self._t[name] = t
+        if hasattr(self.ws, name):
+            setattr(self.ws, name, t.data_ptr())
         return t
 
-    def _up(self, arr, dtype):
-        t = torch.as_tensor(np.ascontiguousarray(arr), dtype=dtype, device=self.device)
-        self.h2d_bytes += t.numel() * t.element_size()
-        return t
+    def _put(self, dst, arr):
+        """host array -> the head of a device workspace buffer (parity tapes, init)"""
+        src = torch.from_numpy(np.ascontiguousarray(arr)).to(dst.dtype).reshape(-1)
+        dst.view(-1)[:src.numel()].copy_(src)
+        self.h2d_bytes += src.numel() * src.element_size()
 
     def _down(self, t):
         """device -> host read (synchronises this chain's stream)"""
         self.d2h_bytes += t.numel() * t.element_size()
         return t.cpu().numpy()
 
-    def _down_small(self, *tensors):
-        """One synchronisation for several small device -> host reads (pinned staging)."""
-        out, off = [], 0
-        for t in tensors:
-            nb = t.numel() * t.element_size()
-            if off + nb > self._pin.numel():
-                raise RuntimeError('pinned staging buffer too small')
-            view = self._pin[off:off + nb].view(t.dtype)
-            view.copy_(t.reshape(-1), non_blocking=True)
-            out.append(view)
-            off += (nb + 15) & ~15
-            self.d2h_bytes += nb
+    def _sync(self):
         self.stream.synchronize()
-        return [v.numpy().copy() for v in out]
 
     class _Timed:
-        """CUDA-event bracket around one launch on the chain's stream (bench.py roofline)."""
+        """CUDA-event bracket around launches on the chain's stream (bench.py roofline)."""
 
         def __init__(self, owner, name):
             self.o, self.name = owner, name
@@ -237,55 +227,97 @@ class DeviceCRP:
         if self.rnd is None:
             self.rnd = PhiloxRandom(np.random.SeedSequence().entropy & 0xFFFFFFFFFFFFFFFF)
         self.rnd.bind(self.device)
+        N, M = self.cells_total, self.muts_total
+        i32, f64, f32, u8 = torch.int32, torch.float64, torch.float32, torch.uint8
         with torch.cuda.stream(self.stream):
             key = str(self.device)
             with _PACK_LOCK:
                 if key not in self._shared:
                     self._shared[key] = _Shared(self.data, self.device)
-            self.sh = self._shared[key]
-            self._bufs = {}
-            N = self.cells_total
-            self.assign_d = torch.zeros(N, dtype=torch.int32, device=self.device)
-            self.visit = torch.empty(N * _lib.VISIT_BYTES, dtype=torch.uint8, device=self.device)
-            self.cand = torch.empty(N * _lib.CAND_BYTES, dtype=torch.uint8, device=self.device)
-            self.visit_c = torch.empty(N * _lib.VISIT_BYTES, dtype=torch.uint8, device=self.device)
-            self.cand_c = torch.empty(N * _lib.CAND_BYTES, dtype=torch.uint8, device=self.device)
-            self.cblk = torch.empty((N + 127) // 128 + 2, dtype=torch.int32, device=self.device)
-            self.members = torch.empty(N, dtype=torch.int32, device=self.device)
-            self.cells_d = torch.empty(N + 8, dtype=torch.int32, device=self.device)
-            self.half = torch.zeros(N + 8, dtype=torch.int32, device=self.device)
-            self.gblk = torch.empty(2 * ((N + 1023) // 1024) + 2, dtype=torch.int32, device=self.device)
-            self.seg3 = torch.zeros(8, dtype=torch.int32, device=self.device)
-            self.rg_work = torch.zeros(2 * N + 16, dtype=torch.int32, device=self.device)
-            self.st = torch.zeros(_lib.ST_WORDS, dtype=torch.int32, device=self.device)
-            self.rg_theta = torch.zeros((3, self.muts_total), dtype=torch.float32, device=self.device)
-            self.rg_S1 = torch.zeros((3, self.muts_total), dtype=torch.int32, device=self.device)
-            self.rg_S0 = torch.zeros((3, self.muts_total), dtype=torch.int32, device=self.device)
-            self.rg_dec = torch.zeros(4, dtype=torch.int32, device=self.device)
-            self.rg_scal = torch.zeros(32, dtype=torch.float64, device=self.device)
-            self._pin = torch.empty(1 << 16, dtype=torch.uint8).pin_memory()
+            self.sh = sh = self._shared[key]
+            self.ws = ws = _lib.ChainWs()
+            self.ep = _lib.Epoch()
+            self.rg = _lib.RgMove()
+            self._t = {}
+            ws.x1, ws.x0, ws.n1, ws.n0 = (sh.x1.data_ptr(), sh.x0.data_ptr(), sh.n1.data_ptr(),
+                                          sh.n0.data_ptr())
+            ws.logn = sh.logn.data_ptr()
+            ws.W, ws.N, ws.M = sh.W, N, M
+            self.assign_d = self._dev('assign', N, i32, zero=True)
+            self.st = self._dev('st', _lib.ST_WORDS, i32, zero=True)
+            for name, nbytes in (('visit', _lib.VISIT_BYTES), ('cand', _lib.CAND_BYTES),
+                                 ('visit_c', _lib.VISIT_BYTES), ('cand_c', _lib.CAND_BYTES)):
+                self._dev(name, N * nbytes, u8)
+            self._dev('cblk', (N + 127) // 128 + 2, i32)
+            self._dev('perm', N, i32)
+            self._dev('u', N, f64)
+            self._dev('lpx', 2 * _lib.MAX_EXTRA * M, f64)
+            self.members = self._dev('members', N, i32)
+            self._dev('rl_tot', 8, f64)
+            # split-merge
+            self._dev('cells', N + 8, i32)
+            self._dev('half', N + 8, i32, zero=True)
+            self._dev('gblk', 2 * ((N + 1023) // 1024) + 2, i32)
+            self.seg3 = self._dev('seg3', 8, i32, zero=True)
+            self._dev('rg_work', 2 * N + 16, i32, zero=True)
+            self.rg_theta = self._dev('rg_theta', (3, M), f32, zero=True)
+            self.rg_S1 = self._dev('rg_S1', (3, M), i32, zero=True)
+            self.rg_S0 = self._dev('rg_S0', (3, M), i32, zero=True)
+            self._dev('rg_dec', 4, i32, zero=True)
+            self._dev('rg_scal', 32, f64, zero=True)
+            self._dev('rg_lp', 4 * M, f64)
+            self._dev('rg_ll2', 2 * N, f64)
+            self._dev('rg_lq', N, f64)
+            self._dev('rg_logq', 3 * M, f64)
+            self._dev('rg_A', 2 * M, f64)
+            self._dev('rg_orig', 2 * M, f32)
+            self._dev('rg_perm', N, i32)
+            self._dev('rg_u', N, f64)
+            self._dev('rg_rnd', 6 * M, f64)
+            self._dev('rg_sd', 2 * M, f64)
+            self._dev('rg_beta', 3 * M, f64)
             self.idcap = 0
+            self._ll_cap = 0
+            self._llx_cap = 0
         self._dev_ready = True
         self._version = 0
         self._stats_version = -1
         self._trace_cache = None
 
     def _grow_ids(self, need):
-        """Make room for cluster ids < need (theta rows, counters, maps)."""
+        """Make room for cluster ids < need: theta rows, counters, maps and every buffer whose
+        size follows the number of live clusters (K <= idcap)."""
         if need <= self.idcap:
             return
-        cap = max(need, 2 * self.idcap, 64)
+        cap = max(need, 2 * self.idcap, 256)
         M = self.muts_total
-        theta = torch.zeros((cap, M), dtype=torch.float32, device=self.device)
-        if self.idcap:
-            theta[:self.idcap] = self.theta
-        self.theta = theta
-        self.cnt = torch.zeros(cap, dtype=torch.int32, device=self.device)
-        self.lst = torch.zeros(cap, dtype=torch.int32, device=self.device)
-        self.col_of_id = torch.full((cap,), -1, dtype=torch.int32, device=self.device)
-        self.rank_of_id = torch.zeros(cap, dtype=torch.int32, device=self.device)
-        self.live_io = torch.zeros(2 * cap, dtype=torch.int32, device=self.device)
+        i32, f64 = torch.int32, torch.float64
+        old = self._t.get('theta')
+        self.theta = self._dev('theta', (cap, M), torch.float32, zero=True)
+        if old is not None:
+            self.theta[:self.idcap] = old
+        for name in ('cnt', 'lst', 'rank_of_id', 'ids', 'cursor', 'declined'):
+            self._dev(name, cap + 2, i32, zero=True)
+        self._dev('seg', cap + 2, i32, zero=True)
+        t = self._dev('col_of_id', cap, i32)
+        t.fill_(-1)
+        self._dev('live_io', 2 * cap, i32, zero=True)
+        self._dev('scratch', cap + 1, f64)
+        self._dev('lp', 2 * cap * M, f64)
+        self.S1 = self._dev('S1', cap * M, i32)
+        self.S0 = self._dev('S0', cap * M, i32)
+        self._dev('rnd', 3 * cap * M, f64)
+        self._dev('rl_out', 5 * cap, f64)
+        # pinned host staging
+        self._h_in = torch.empty(4 * cap + 16, dtype=i32).pin_memory()
+        self._h_out = torch.empty(_lib.ST_WORDS + 2 * cap + 16, dtype=i32).pin_memory()
+        self._h_scal = torch.empty(32, dtype=f64).pin_memory()
+        self.h_in, self.h_out, self.h_scal = self._h_in.numpy(), self._h_out.numpy(), self._h_scal.numpy()
+        self.ws.h_in, self.ws.h_out, self.ws.h_scal = (self._h_in.data_ptr(), self._h_out.data_ptr(),
+                                                       self._h_scal.data_ptr())
         self.idcap = cap
+        self.ws.idcap = cap
+        self._stats_version = -1
 
     def _touch(self):
         self._version += 1
@@ -317,6 +349,10 @@ class DeviceCRP:
             i += 1
         return i
 
+    def _streams(self, n):
+        """n fresh random stream ids of this chain (production mode)"""
+        return self.rnd.reserve(n)
+
     # --------------------------------------------------------------------- init
     def init(self, mode='random', assign=False):
         """libs/CRP.py:119-152, 155-180."""
@@ -336,21 +372,25 @@ class DeviceCRP:
             K = labels.size
             self.cells_per_cluster = OrderedDict((i, int(sizes[i])) for i in range(K))
             self._grow_ids(K + _lib.MAX_EXTRA + 2)
-            self.assign_d.copy_(self._up(a, torch.int32))
+            self._put(self.assign_d, a.astype(np.int32))
             self._touch()
-            ids_d = self._up(np.arange(K), torch.int32)
+            ids_d = torch.arange(K, dtype=torch.int32, device=self.device)
             if given:
                 self._refresh_stats()
                 tape = self.rnd.beta_rows(K, M)
+                tape_d = None
+                if tape is not None:
+                    tape_d = torch.as_tensor(tape, dtype=torch.float64, device=self.device)
                 self.L.beta_rows(self.S1.data_ptr(), self.S0.data_ptr(), K, M, float(self.p),
-                                 float(self.q), tape.data_ptr() if tape is not None else None,
-                                 self.rnd.device_seed, self.rnd.next_stream(),
+                                 float(self.q), tape_d.data_ptr() if tape_d is not None else None,
+                                 self.rnd.device_seed, self._streams(1) + 1,
                                  self.theta.data_ptr(), ids_d.data_ptr(), self._sp())
             else:
                 u = self.rnd.uniform_rows(K, M)
+                u = torch.as_tensor(u, dtype=torch.float64, device=self.device)
                 self.L.theta_from_uniform(u.data_ptr(), K, M, self.theta.data_ptr(),
                                           ids_d.data_ptr(), self._sp())
-            self.stream.synchronize()
+            self._sync()
         self._touch()
 
     # ------------------------------------------------------- sufficient statistics
@@ -359,45 +399,38 @@ class DeviceCRP:
         data[cells] gathers of libs/CRP.py:308,360-367)."""
         if self._stats_version == self._version:
             return
-        ids, sizes = self._ids_sizes()
-        K, M, N = ids.size, self.muts_total, self.cells_total
-        seg = np.concatenate(([0], np.cumsum(sizes))).astype(np.int32)
-        self.ids_d = self._up(ids, torch.int32)
-        seg_d = self._up(seg, torch.int32)
-        cur = self._buf('cursor', K, torch.int32)
-        self.S1 = self._buf('S1', K * M, torch.int32)
-        self.S0 = self._buf('S0', K * M, torch.int32)
-        sp = self._sp()
-        self.L.set_ranks(self.ids_d.data_ptr(), K, self.rank_of_id.data_ptr(), sp)
-        self.L.group_members(self.assign_d.data_ptr(), N, self.rank_of_id.data_ptr(), seg_d.data_ptr(),
-                             cur.data_ptr(), K, self.members.data_ptr(), sp)
-        self.L.suffstat(self.sh.x1.data_ptr(), self.sh.x0.data_ptr(), self.sh.W, M,
-                        self.members.data_ptr(), seg_d.data_ptr(), K, int(sizes.max()),
-                        self.S1.data_ptr(), self.S0.data_ptr(), sp)
+        K = len(self.cells_per_cluster)
+        h = self.h_in
+        h[:K] = np.fromiter(self.cells_per_cluster.keys(), dtype=np.int32, count=K)
+        sizes = np.fromiter(self.cells_per_cluster.values(), dtype=np.int32, count=K)
+        h[K] = 0
+        np.cumsum(sizes, out=h[K + 1:2 * K + 1])
+        # (h_in is consumed before it is written again: every method synchronises the stream
+        # after its last call)
+        self.L.chain_stats(self.ws, K, int(sizes.max()), self._sp())
+        self.h2d_bytes += 4 * (2 * K + 1)
         self._stats_version = self._version
 
     # ----------------------------------------------------------------- traces
-    def _row_loglik(self, theta, ids_ptr, R, S1, S0, fn, fp, want_prior):
+    def _loglik(self, fn, fp, want_prior):
+        """full-data log-likelihood at each (FN, FP) pair [+ the Beta prior of theta], from the
+        [K][M] sufficient statistics"""
+        self._refresh_stats()
         E = len(fn)
-        out = self._buf('rl_out', 4 * R + R, torch.float64)
-        tot = self._buf('rl_tot', 8, torch.float64)
-        fn_a = (C.c_double * E)(*fn) if E else None
-        fp_a = (C.c_double * E)(*fp) if E else None
-        pr_ptr = out.data_ptr() + 8 * E * R if want_prior else None
-        sp = self._sp()
-        self.L.row_loglik(theta.data_ptr(), ids_ptr, R, self.muts_total, S1.data_ptr(), S0.data_ptr(),
-                          fn_a, fp_a, E, float(self.p), float(self.q), out.data_ptr(), pr_ptr, sp)
+        K = len(self.cells_per_cluster)
+        fn_a = (C.c_double * max(E, 1))(*fn)
+        fp_a = (C.c_double * max(E, 1))(*fp)
+        self.L.chain_loglik(self.ws, K, fn_a, fp_a, E, 1 if want_prior else 0, float(self.p),
+                            float(self.q), self._sp())
+        self._sync()
         rows = E + (1 if want_prior else 0)
-        self.L.row_sum(out.data_ptr(), rows, R, tot.data_ptr(), sp)
-        return self._down(tot[:rows])
+        self.d2h_bytes += 8 * rows
+        return self.h_scal[:rows].copy()
 
     def _trace_scalars(self):
         if self._trace_cache is None:
             with torch.cuda.stream(self.stream):
-                self._refresh_stats()
-                K = len(self.cells_per_cluster)
-                r = self._row_loglik(self.theta, self.ids_d.data_ptr(), K, self.S1, self.S0,
-                                     [float(self.FN)], [float(self.FP)], not self.beta_prior_uniform)
+                r = self._loglik([float(self.FN)], [float(self.FP)], not self.beta_prior_uniform)
             self._trace_cache = (float(r[0]), float(r[1]) if not self.beta_prior_uniform else 0.0)
         return self._trace_cache
 
@@ -426,86 +459,69 @@ class DeviceCRP:
         """libs/CRP.py:254-299.  The sweep runs in epochs: for the clusters alive
         at the start of an epoch the cells x clusters log-likelihood matrix is
         built by one dense kernel, then one persistent CTA walks the permutation;
-        clusters born inside an epoch get their column computed on the spot."""
+        clusters born inside an epoch get their column computed on the spot.
+        One C call and one stream synchronisation per epoch."""
         N, M = self.cells_total, self.muts_total
-        L, sh = self.L, self.sh
+        L, ep = self.L, self.ep
         with torch.cuda.stream(self.stream):
             sp = self._sp()
-            perm, u, beta_tape, n_tape = self.rnd.gibbs_draws(N, M)
             mix0, mix1 = self._beta_mix_const
             FN, FP = float(self.FN), float(self.FP)
             # popcount form of get_lpost_single_new_cluster (libs/CRP.py:230-234)
-            c1 = float(np.log(mix1 * (1 - FN) + mix0 * FP))
-            c0 = float(np.log(mix1 * FN + mix0 * (1 - FP)))
-            c_norm = float(np.log(N - 1 + self.DP_a))
-            lnew_prior = float(np.log(self.DP_a) - np.log(N - 1 + self.DP_a))
-            L.gibbs_prepare(perm.data_ptr(), u.data_ptr(), self.assign_d.data_ptr(), sh.n1.data_ptr(),
-                            sh.n0.data_ptr(), N, c1, c0, lnew_prior, self.visit.data_ptr(), sp)
-            seed, stream_id = self.rnd.device_seed, self.rnd.next_stream()
-            t, first, epochs = 0, 1, 0
-            stall = 0
+            ep.c1 = float(np.log(mix1 * (1 - FN) + mix0 * FP))
+            ep.c0 = float(np.log(mix1 * FN + mix0 * (1 - FP)))
+            ep.c_norm = float(np.log(N - 1 + self.DP_a))
+            ep.lnew_prior = float(np.log(self.DP_a) - np.log(N - 1 + self.DP_a))
+            ep.log_n = float(np.log(N))
+            ep.FN, ep.FP, ep.p, ep.q = FN, FP, float(self.p), float(self.q)
+            n_tape = 0
+            if self.rnd.is_tape:
+                perm, u, beta, n_tape = self.rnd.gibbs_draws(N, M)
+                self._put(self._t['perm'], perm)
+                self._put(self._t['u'], u)
+                beta_d = torch.as_tensor(beta, dtype=torch.float64, device=self.device)
+                ep.rand_ready, ep.beta_rows, ep.n_beta_rows = 1, beta_d.data_ptr(), n_tape
+                ep.seed, ep.stream_id = 0, 0
+            else:
+                ep.rand_ready, ep.beta_rows, ep.n_beta_rows = 0, None, 0
+                ep.seed, ep.stream_id = self.rnd.device_seed, self._streams(3)
+            t, first, epochs, stall = 0, 1, 0, 0
             while t < N:
-                ids, sizes = self._ids_sizes()
-                K = ids.size
+                K = len(self.cells_per_cluster)
                 self._grow_ids(K + _lib.MAX_EXTRA + 2)
-                live = np.empty(2 * K, dtype=np.int32)
-                live[0::2] = ids
-                live[1::2] = sizes
-                self.live_io[:2 * K].copy_(self._up(live, torch.int32))
-                L.gibbs_epoch_begin(self.live_io.data_ptr(), K, self.lst.data_ptr(), self.cnt.data_ptr(),
-                                    self.col_of_id.data_ptr(), self.idcap, self.st.data_ptr(), first, sp)
+                h = self.h_in
+                h[0:2 * K:2] = np.fromiter(self.cells_per_cluster.keys(), dtype=np.int32, count=K)
+                h[1:2 * K:2] = np.fromiter(self.cells_per_cluster.values(), dtype=np.int32, count=K)
                 # odd row stride (bank-conflict-free per-lane row reads in the warp regime)
                 ldk = max(3, K | 1)
                 rows = int(min(N - t, max(1, LL_BUDGET_BYTES // (8 * ldk))))
-                lp = self._buf('lp', 2 * K * M, torch.float64)
-                ll = self._buf('ll', rows * ldk + 2, torch.float64)
-                lpx = self._buf('lpx', 2 * _lib.MAX_EXTRA * M, torch.float64)
-                llx = self._buf('llx', _lib.MAX_EXTRA * rows, torch.float64)
-                scratch = self._buf('scratch', self.idcap + 1, torch.float64)
-                L.logprob_tables(self.theta.data_ptr(), self.lst.data_ptr(), K, M, FN, FP, lp.data_ptr(), sp)
-                # cell indices are read straight out of the visit records
-                with self._Timed(self, 'll_matrix'):
-                    L.ll_matrix(sh.x1.data_ptr(), sh.x0.data_ptr(), sh.W, M,
-                                self.visit.data_ptr() + t * _lib.VISIT_BYTES + _lib.VISIT_CELL_OFFSET,
-                                _lib.VISIT_BYTES // 4, rows, lp.data_ptr(), K, ll.data_ptr(), ldk, sp)
-                compacted = ldk <= _lib.MAX_LIST
-                if compacted:
-                    L.gibbs_candidates(ll.data_ptr(), ldk, K, self.col_of_id.data_ptr(),
-                                       self.visit.data_ptr() + t * _lib.VISIT_BYTES,
-                                       self.cand.data_ptr() + t * _lib.CAND_BYTES, rows,
-                                       float(np.log(N)), c_norm, self.cblk.data_ptr(), sp)
-                    L.gibbs_compact(self.visit.data_ptr() + t * _lib.VISIT_BYTES,
-                                    self.cand.data_ptr() + t * _lib.CAND_BYTES, rows,
-                                    self.cblk.data_ptr(), self.visit_c.data_ptr(),
-                                    self.cand_c.data_ptr(), self.st.data_ptr(), sp)
-                a = _lib.SweepArgs(
-                    x1=sh.x1.data_ptr(), x0=sh.x0.data_ptr(), W=sh.W, N=N, M=M,
-                    assign=self.assign_d.data_ptr(), cnt=self.cnt.data_ptr(), lst=self.lst.data_ptr(),
-                    col_of_id=self.col_of_id.data_ptr(), theta=self.theta.data_ptr(), idcap=self.idcap,
-                    st=self.st.data_ptr(), live_out=self.live_io.data_ptr(),
-                    ll=ll.data_ptr(), ldk=ldk, t_epoch0=t,
-                    lpx=lpx.data_ptr(), llx=llx.data_ptr(), ldx=rows, scratch=scratch.data_ptr(),
-                    visit=self.visit.data_ptr(), cand=self.cand.data_ptr(), t_begin=t, t_end=t + rows,
-                    visit_c=self.visit_c.data_ptr() if compacted else None,
-                    cand_c=self.cand_c.data_ptr() if compacted else None,
-                    beta_rows=beta_tape.data_ptr() if beta_tape is not None else None,
-                    n_beta_rows=n_tape, seed=seed, stream_id=stream_id,
-                    logn=sh.logn.data_ptr(), c_norm=c_norm, FN=FN, FP=FP,
-                    p=float(self.p), q=float(self.q))
-                with self._Timed(self, 'gibbs_sweep'):
-                    L.gibbs_sweep(C.byref(a), 256 if K < 1000 else 1024, sp)
-                # status block and live list in one read (at most MAX_EXTRA births per epoch)
-                k_cap = K + _lib.MAX_EXTRA + 2
-                if 8 * k_cap + 256 <= self._pin.numel():
-                    st, pairs = self._down_small(self.st, self.live_io[:2 * k_cap])   # synchronises
+                if rows * ldk + 2 > self._ll_cap:
+                    self._ll_cap = rows * ldk + 2
+                    self._dev('ll', self._ll_cap, torch.float64)
+                if _lib.MAX_EXTRA * rows > self._llx_cap:
+                    self._llx_cap = _lib.MAX_EXTRA * rows
+                    self._dev('llx', self._llx_cap, torch.float64)
+                ep.first, ep.K, ep.t, ep.rows, ep.ldk = first, K, t, rows, ldk
+                if self.profile:
+                    # CUDA events recorded by the library around the two dominant launches
+                    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                    for e in evs:
+                        e.record(self.stream)            # creates the underlying event
+                    ep.ev_ll0, ep.ev_ll1, ep.ev_sw0, ep.ev_sw1 = [e.cuda_event for e in evs]
+                    self._events += [('ll_matrix', evs[0], evs[1]), ('gibbs_sweep', evs[2], evs[3])]
                 else:
-                    st, pairs = self._down(self.st), self._down(self.live_io[:2 * k_cap])
+                    ep.ev_ll0 = ep.ev_ll1 = ep.ev_sw0 = ep.ev_sw1 = None
+                L.chain_gibbs_epoch(self.ws, ep, sp)
+                self._sync()
+                self.h2d_bytes += 8 * K
+                st = self.h_out[:_lib.ST_WORDS]
                 flags = int(st[_lib.ST_FLAGS])
                 if flags & (_lib.STOP_TAPE_EMPTY | _lib.STOP_HANG):
                     raise RuntimeError(f'gibbs_sweep stopped with flags {flags:#x} at t={st[_lib.ST_TDONE]}')
                 K = int(st[_lib.ST_K])
-                self.cells_per_cluster = OrderedDict(
-                    (int(pairs[2 * j]), int(pairs[2 * j + 1])) for j in range(K))
+                self.d2h_bytes += 4 * _lib.ST_WORDS + 8 * K
+                pairs = self.h_out[_lib.ST_WORDS:_lib.ST_WORDS + 2 * K].tolist()
+                self.cells_per_cluster = OrderedDict(zip(pairs[0::2], pairs[1::2]))
                 t_new = int(st[_lib.ST_TDONE])
                 stall = stall + 1 if t_new == t else 0
                 if stall > 2:
@@ -514,10 +530,9 @@ class DeviceCRP:
                     self._grow_ids(2 * self.idcap)
                 t, first = t_new, 0
                 epochs += 1
-            if getattr(self.rnd, 'is_tape', False):
-                if int(st[_lib.ST_BIRTHS]) != n_tape:
-                    raise RuntimeError(f'parity tape held {n_tape} cluster births, sweep made '
-                                       f'{int(st[_lib.ST_BIRTHS])}')
+            if self.rnd.is_tape and int(st[_lib.ST_BIRTHS]) != n_tape:
+                raise RuntimeError(f'parity tape held {n_tape} cluster births, sweep made '
+                                   f'{int(st[_lib.ST_BIRTHS])}')
             self.sweep_stats = dict(epochs=epochs, births=int(st[_lib.ST_BIRTHS]),
                                     moved=int(st[_lib.ST_MOVED]), slow=int(st[_lib.ST_SLOW]),
                                     uncertain=int(st[_lib.ST_NUNC]),
@@ -532,13 +547,16 @@ class DeviceCRP:
         with torch.cuda.stream(self.stream):
             self._refresh_stats()
             K, M = len(self.cells_per_cluster), self.muts_total
-            rnd = self.rnd.mh_theta_draws(K, M)
-            dec = self._buf('declined', K, torch.int32)
-            dec[:K].zero_()
-            self.L.mh_theta(self.theta.data_ptr(), self.ids_d.data_ptr(), K, M, self.S1.data_ptr(),
-                            self.S0.data_ptr(), rnd.data_ptr(), float(self.FN), float(self.FP),
-                            float(self.p), float(self.q), 0, None, dec.data_ptr(), self._sp())
-            declined = int(dec[:K].sum().item())
+            if self.rnd.is_tape:
+                self._put(self._t['rnd'], self.rnd.mh_theta_draws(K, M))
+                ready, seed, sid = 1, 0, 0
+            else:
+                ready, seed, sid = 0, self.rnd.device_seed, self._streams(2)
+            self.L.chain_mh_theta(self.ws, K, ready, seed, sid, float(self.FN), float(self.FP),
+                                  float(self.p), float(self.q), self._sp())
+            self._sync()
+            declined = int(self.h_out[0])
+            self.d2h_bytes += 4
         self._trace_cache = None
         return declined, K * M - declined
 
@@ -571,9 +589,30 @@ class DeviceCRP:
                 return (self._try_split(step_no), move)
             return (self._try_merge(step_no), move)
 
+    def _rg_begin(self, n, n_a, cl_i, cl_j, a_i, a_j, is_merge):
+        g = self.rg
+        g.n, g.n_a, g.cl_i, g.cl_j, g.a_i, g.a_j, g.is_merge = n, n_a, cl_i, cl_j, a_i, a_j, is_merge
+        g.rand_ready = 1 if self.rnd.is_tape else 0
+        g.seed = self.rnd.device_seed
+        FN, FP = float(self.FN), float(self.FP)
+        g.alpha, g.FN, g.FP, g.p, g.q = float(self.DP_a), FN, FP, float(self.p), float(self.q)
+        mix0 = self._beta_mix_const[0]
+        with np.errstate(divide='ignore'):
+            k6 = (np.log(1.0 * (1 - FN) + 0.0 * FP), np.log(1.0 * FN + 0.0 * (1 - FP)),
+                  np.log(0.0 * (1 - FN) + 1.0 * FP), np.log(0.0 * FN + 1.0 * (1 - FP)),
+                  np.log(mix0 * (1 - FN) + (1 - mix0) * FP), np.log(mix0 * FN + (1 - mix0) * (1 - FP)))
+        for i in range(6):
+            g.k6[i] = float(k6[i])
+        self._stats_version = -1          # `members` is reused by the move
+        return g
+
+    def _rg_rand(self, n_streams):
+        """production: reserve the streams of the next composite call"""
+        if not self.rnd.is_tape:
+            self.rg.stream_id = self._streams(n_streams)
+
     def _try_split(self, scans):
         """libs/CRP.py:434-481."""
-        L, sp, N = self.L, self._sp(), self.cells_total
         ids, sizes = self._ids_sizes()
         weight = sizes / sizes.sum()
         while True:
@@ -583,9 +622,7 @@ class DeviceCRP:
             if n != 1:
                 break
         a_i, a_j = self.rnd.first_two_of_permutation(n)
-        L.gather_members(self.assign_d.data_ptr(), N, target, -1, self.cells_d.data_ptr(),
-                         self.gblk.data_ptr(), sp)
-        L.anchor_swaps(self.cells_d.data_ptr(), n, n, a_i, a_j, 0, sp)
+        g = self._rg_begin(n, n, target, -1, a_i, a_j, 0)
         lq_pick = np.log(weight[where]) - np.log(n) - np.log(n - 1)
         others = np.delete(sizes, where)
         ok, ones = self._restricted_gibbs('split', n, n, (lq_pick, others), scans, target, -1)
@@ -593,10 +630,7 @@ class DeviceCRP:
             return [0, 1]
         new_id = self.get_empty_cluster()
         self._grow_ids(new_id + _lib.MAX_EXTRA + 2)
-        self.theta[target].copy_(self.rg_theta[0])
-        self.theta[new_id].copy_(self.rg_theta[1])
-        L.apply_split(self.cells_d.data_ptr(), n, self.half.data_ptr(), new_id,
-                      self.assign_d.data_ptr(), sp)
+        self.L.chain_rg_apply(self.ws, g, new_id, self._sp())
         moved = ones + 1
         self.cells_per_cluster[target] -= moved
         self.cells_per_cluster[new_id] = moved
@@ -605,7 +639,6 @@ class DeviceCRP:
 
     def _try_merge(self, scans):
         """libs/CRP.py:484-524."""
-        L, sp, N = self.L, self._sp(), self.cells_total
         ids, sizes = self._ids_sizes()
         inv = 1 / sizes
         weight = inv / inv.sum()
@@ -615,111 +648,54 @@ class DeviceCRP:
         a_i = self.rnd.randint(n_a)
         a_j = self.rnd.randint(n_b)
         n = n_a + n_b
-        L.gather_members(self.assign_d.data_ptr(), N, cl_i, cl_j, self.cells_d.data_ptr(),
-                         self.gblk.data_ptr(), sp)
-        L.anchor_swaps(self.cells_d.data_ptr(), n, n_a, a_i, a_j, 1, sp)
+        g = self._rg_begin(n, n_a, cl_i, cl_j, a_i, a_j, 1)
         both = np.argwhere((ids == cl_j) | (ids == cl_i)).flatten()
         lq_pick = np.nansum(np.log(weight[both])) - np.nansum(np.log(sizes[both]))
         ok, _ = self._restricted_gibbs('merge', n, n_a, lq_pick, scans, cl_i, cl_j)
         if not ok:
             return [0, 1]
-        self.theta[cl_i].copy_(self.rg_theta[2])
-        L.apply_merge(self.cells_d.data_ptr(), n_a, n, cl_i, self.assign_d.data_ptr(), sp)
+        self.L.chain_rg_apply(self.ws, g, -1, self._sp())
         self.cells_per_cluster[cl_i] += n_b
         del self.cells_per_cluster[cl_j]
         self._touch()
         return [1, 0]
 
     # -- restricted Gibbs machinery (libs/CRP.py:527-638) -----------------------
-    # Everything a split-merge move computes on the device is enqueued without waiting; the
-    # scalars the Metropolis-Hastings decision needs are reduced into slots of `rg_scal` and
-    # read back ONCE (one stream synchronisation per move).
+    # Everything a split-merge move computes on the device is enqueued without waiting (one C call
+    # per scan); the scalars the Metropolis-Hastings decision needs are reduced into slots of
+    # `rg_scal` and read back ONCE (one stream synchronisation per move).
     SL_FWD_ASSIGN, SL_FWD_THETA, SL_BACK, SL_BACK_LQ, SL_PRIOR_NEW, SL_PRIOR_OLD, SL_LL3 = 0, 1, 2, 3, 4, 6, 8
-
-    def _rg_side_stats(self, n):
-        """rg_S[0], rg_S[1] = sufficient statistics of the two halves (anchors
-        included) for the current `half`; returns nothing (device only)."""
-        L, sp, M = self.L, self._sp(), self.muts_total
-        L.rg_sides(self.cells_d.data_ptr(), n, self.half.data_ptr(), self.members.data_ptr(),
-                   self.seg3.data_ptr(), sp)
-        L.suffstat(self.sh.x1.data_ptr(), self.sh.x0.data_ptr(), self.sh.W, M, self.members.data_ptr(),
-                   self.seg3.data_ptr(), 2, n, self.rg_S1.data_ptr(), self.rg_S0.data_ptr(), sp)
-        self._stats_version = -1          # `members` was reused
-
-    def _rg_sum_to(self, v, rows, m, slot):
-        """rg_scal[slot + r] = sum of row r of v[rows][m] (fixed order)."""
-        self.L.row_sum(v.data_ptr(), rows, m, self.rg_scal.data_ptr() + 8 * slot, self._sp())
-
-    def _rg_mh(self, row0, rows, slot=None):
-        """MH_cluster_params on rg_theta[row0:row0+rows] (libs/CRP.py:583,601); with a slot the
-        transition log-probability (trans_prob=True) is summed into rg_scal[slot]."""
-        M = self.muts_total
-        rnd = self.rnd.mh_theta_draws(rows, M)
-        want = slot is not None
-        logq = self._buf('rg_logq', 3 * M, torch.float64)
-        self.L.mh_theta(self.rg_theta[row0:].data_ptr(), None, rows, M, self.rg_S1[row0:].data_ptr(),
-                        self.rg_S0[row0:].data_ptr(), rnd.data_ptr(), float(self.FN), float(self.FP),
-                        float(self.p), float(self.q), 1 if want else 0,
-                        logq.data_ptr() if want else None, self.rg_dec.data_ptr(), self._sp())
-        if want:
-            self._rg_sum_to(logq, 1, rows * M, slot)
-
-    def _rg_pair_ll(self, theta, ids_ptr, n):
-        """ll of the n-2 free cells under two theta rows (libs/CRP.py:635-638)."""
-        L, sp, M, nf = self.L, self._sp(), self.muts_total, n - 2
-        lp = self._buf('rg_lp', 4 * M, torch.float64)
-        ll2 = self._buf('rg_ll2', 2 * nf, torch.float64)
-        L.logprob_tables(theta.data_ptr(), ids_ptr, 2, M, float(self.FN), float(self.FP), lp.data_ptr(), sp)
-        L.ll_matrix(self.sh.x1.data_ptr(), self.sh.x0.data_ptr(), self.sh.W, M,
-                    self.cells_d.data_ptr() + 4, 1, nf, lp.data_ptr(), 2, ll2.data_ptr(), 2, sp)
-        return ll2
 
     def _scan_split(self, n, want_logq=False):
         """libs/CRP.py:570-578, 590-632."""
-        L, sp, nf = self.L, self._sp(), n - 2
-        if n > 2:
-            ll2 = self._rg_pair_ll(self.rg_theta, None, n)
-            perm, u = self.rnd.scan_draws(nf)
-            lq = self._buf('rg_lq', nf, torch.float64)
-            L.rg_scan(ll2.data_ptr(), 2, n, perm.data_ptr(), u.data_ptr(), self.half.data_ptr(),
-                      float(self.DP_a), 0, None, None, -1, lq.data_ptr() if want_logq else None,
-                      self.rg_work.data_ptr(), sp)
-            if want_logq:
-                self._rg_sum_to(lq, 1, nf, self.SL_FWD_ASSIGN)
-        self._rg_side_stats(n)
-        # both halves in one launch; draws are taken side 0 first, as the reference does
-        self._rg_mh(0, 2, self.SL_FWD_THETA if want_logq else None)
+        M, nf = self.muts_total, n - 2
+        if self.rnd.is_tape:
+            if n > 2:
+                perm, u = self.rnd.scan_draws(nf)
+                self._put(self._t['rg_perm'], perm)
+                self._put(self._t['rg_u'], u)
+            self._put(self._t['rg_rnd'], self.rnd.mh_theta_draws(2, M))
+        else:
+            self._rg_rand(4)
+        self.L.chain_rg_scan_split(self.ws, self.rg, 1 if want_logq else 0, self._sp())
 
     def _scan_merged(self, want_logq=False):
         """libs/CRP.py:581-587."""
-        self._rg_mh(2, 1, self.SL_FWD_THETA if want_logq else None)
+        if self.rnd.is_tape:
+            self._put(self._t['rg_rnd'], self.rnd.mh_theta_draws(1, self.muts_total))
+        else:
+            self._rg_rand(2)
+        self.L.chain_rg_scan_merged(self.ws, self.rg, 1 if want_logq else 0, self._sp())
 
     def _restricted_gibbs(self, move, n, n_a, size_term, scans, cl_i, cl_j):
         """libs/CRP.py:527-567.  Returns (accepted, number of free cells on side j)."""
-        L, sp, M = self.L, self._sp(), self.muts_total
-        FN, FP = float(self.FN), float(self.FP)
-        mix0 = self._beta_mix_const[0]
-        self.rg_scal.zero_()
+        M = self.muts_total
         # launch state: free cells go to the anchor whose raw row explains them better
-        if n > 2:
-            k6 = (C.c_double * 6)(
-                np.log(1.0 * (1 - FN) + 0.0 * FP), np.log(1.0 * FN + 0.0 * (1 - FP)),
-                np.log(0.0 * (1 - FN) + 1.0 * FP), np.log(0.0 * FN + 1.0 * (1 - FP)),
-                np.log(mix0 * (1 - FN) + (1 - mix0) * FP), np.log(mix0 * FN + (1 - mix0) * (1 - FP)))
-            L.rg_launch_halves(self.sh.x1.data_ptr(), self.sh.x0.data_ptr(), self.sh.W,
-                               self.cells_d.data_ptr(), n, k6, self.half.data_ptr(), sp)
-        self._rg_side_stats(n)
-        tape = self.rnd.beta_rows(2, M)
-        L.beta_rows(self.rg_S1.data_ptr(), self.rg_S0.data_ptr(), 2, M, float(self.p), float(self.q),
-                    tape.data_ptr() if tape is not None else None, self.rnd.device_seed,
-                    self.rnd.next_stream(), self.rg_theta.data_ptr(), None, sp)
-        # statistics of all cells of the move never change: S_all = S_i + S_j
-        torch.add(self.rg_S1[0], self.rg_S1[1], out=self.rg_S1[2])
-        torch.add(self.rg_S0[0], self.rg_S0[1], out=self.rg_S0[2])
-        tape = self.rnd.beta_rows(1, M)
-        L.beta_rows(self.rg_S1[2].data_ptr(), self.rg_S0[2].data_ptr(), 1, M, float(self.p), float(self.q),
-                    tape.data_ptr() if tape is not None else None, self.rnd.device_seed,
-                    self.rnd.next_stream(), self.rg_theta[2].data_ptr(), None, sp)
+        if self.rnd.is_tape:
+            self._put(self._t['rg_beta'], np.concatenate([self.rnd.beta_rows(2, M), self.rnd.beta_rows(1, M)]))
+        else:
+            self._rg_rand(2)
+        self.L.chain_rg_setup(self.ws, self.rg, self._sp())
         for _ in range(scans):
             self._scan_split(n)
             self._scan_merged()
@@ -727,38 +703,19 @@ class DeviceCRP:
             return self._decide_split(n, size_term, cl_i)
         return self._decide_merge(n, n_a, size_term, cl_i, cl_j)
 
-    def _prior_sum_to(self, theta, rows, slot):
-        """rg_scal[slot + r] = sum_m Beta(p,q).logpdf(theta[r][m]) (device reduction)."""
-        self.L.row_loglik(theta.data_ptr(), None, rows, self.muts_total, self.rg_S1.data_ptr(),
-                          self.rg_S0.data_ptr(), None, None, 0, float(self.p), float(self.q),
-                          self.rg_scal.data_ptr(), self.rg_scal.data_ptr() + 8 * slot, self._sp())
-
-    def _ll_three_to(self, slot):
-        """flat ll of side i, side j (under rg_theta[0:2]) and of all cells (under
-        rg_theta[2]) from the three statistics rows (libs/CRP.py:726-728)."""
-        fn = (C.c_double * 1)(float(self.FN))
-        fp = (C.c_double * 1)(float(self.FP))
-        self.L.row_loglik(self.rg_theta.data_ptr(), None, 3, self.muts_total, self.rg_S1.data_ptr(),
-                          self.rg_S0.data_ptr(), fn, fp, 1, float(self.p), float(self.q),
-                          self.rg_scal.data_ptr() + 8 * slot, None, self._sp())
-
     def _decide_split(self, n, size_term, cl_i):
         """libs/CRP.py:641-653 with :668-682, :695-733, :757-764."""
-        L, sp, M = self.L, self._sp(), self.muts_total
+        M = self.muts_total
         self._scan_split(n, want_logq=True)
-        sd = self.rnd.step_sd_index(1, M)
-        A = self._buf('rg_A', 2 * M, torch.float64)
-        L.theta_log_ratio(self.theta[cl_i].data_ptr(), self.rg_theta[2].data_ptr(), 1, M,
-                          self.rg_S1[2].data_ptr(), self.rg_S0[2].data_ptr(), sd.data_ptr(),
-                          THETA_LO, THETA_HI, float(self.FN), float(self.FP),
-                          float(self.p), float(self.q), A.data_ptr(), sp)
-        self._rg_sum_to(A, 1, M, self.SL_BACK)
-        if not self.beta_prior_uniform:
-            self._prior_sum_to(self.rg_theta, 2, self.SL_PRIOR_NEW)
-            self._prior_sum_to(self.theta[cl_i:cl_i + 1], 1, self.SL_PRIOR_OLD)
-        self._ll_three_to(self.SL_LL3)
-        sc, seg = self._down_small(self.rg_scal[:16], self.seg3)
-        ones = int(seg[3]) if n > 2 else 0                  # free cells on side j (rg_sides)
+        if self.rnd.is_tape:
+            self._put(self._t['rg_sd'], self.rnd.step_sd_index(1, M))
+        else:
+            self._rg_rand(1)
+        self.L.chain_rg_decide_split(self.ws, self.rg, 1 if self.beta_prior_uniform else 0, self._sp())
+        self._sync()
+        self.d2h_bytes += 8 * 16 + 32
+        sc = self.h_scal[:16].copy()
+        ones = int(self.h_out[3]) if n > 2 else 0           # free cells on side j (rg_sides)
         logq_ratio = sc[self.SL_BACK] - (sc[self.SL_FWD_ASSIGN] + sc[self.SL_FWD_THETA])
         # eq. 7: prior ratio (libs/CRP.py:695-713)
         n_j = ones + 1
@@ -781,32 +738,16 @@ class DeviceCRP:
 
     def _decide_merge(self, n, n_a, size_term, cl_i, cl_j):
         """libs/CRP.py:656-665 with :685-692, :736-754, :767-820."""
-        L, sp, M, nf = self.L, self._sp(), self.muts_total, n - 2
+        M, nf = self.muts_total, n - 2
         self._scan_merged(want_logq=True)
-        # probability of walking from the launch split back to the original split
-        sd = self.rnd.step_sd_index(2, M)
-        orig = self._buf('rg_orig', 2 * M, torch.float32)
-        orig[:M].copy_(self.theta[cl_i])
-        orig[M:2 * M].copy_(self.theta[cl_j])
-        A = self._buf('rg_A', 2 * M, torch.float64)
-        L.theta_log_ratio(orig.data_ptr(), self.rg_theta.data_ptr(), 2, M, self.rg_S1.data_ptr(),
-                          self.rg_S0.data_ptr(), sd.data_ptr(), 0.0, 1.0,
-                          float(self.FN), float(self.FP), float(self.p), float(self.q), A.data_ptr(), sp)
-        self._rg_sum_to(A, 1, 2 * M, self.SL_BACK)
-        if n > 2:
-            ll2 = self._rg_pair_ll(orig, None, n)
-            lq = self._buf('rg_lq', nf, torch.float64)
-            L.rg_scan(ll2.data_ptr(), 2, n, None, None, self.half.data_ptr(), float(self.DP_a), 1,
-                      self.cells_d.data_ptr(), self.assign_d.data_ptr(), cl_i, lq.data_ptr(),
-                      self.rg_work.data_ptr(), sp)
-            self._rg_sum_to(lq, 1, nf, self.SL_BACK_LQ)
-        if not self.beta_prior_uniform:
-            self._prior_sum_to(self.rg_theta[2:3], 1, self.SL_PRIOR_NEW)
-            self._prior_sum_to(orig, 2, self.SL_PRIOR_OLD)
-        # `half` now equals the original split (reference quirk, SURVEY Appendix C.6)
-        self._rg_side_stats(n)
-        self._ll_three_to(self.SL_LL3)
-        sc, = self._down_small(self.rg_scal[:16])
+        if self.rnd.is_tape:
+            self._put(self._t['rg_sd'], self.rnd.step_sd_index(2, M))
+        else:
+            self._rg_rand(1)
+        self.L.chain_rg_decide_merge(self.ws, self.rg, 1 if self.beta_prior_uniform else 0, self._sp())
+        self._sync()
+        self.d2h_bytes += 8 * 16
+        sc = self.h_scal[:16].copy()
         logq_ratio = (sc[self.SL_BACK] + sc[self.SL_BACK_LQ]) - sc[self.SL_FWD_THETA]
         n_j = (n - n_a - 1) + 1
         n_i = n - n_j
@@ -865,10 +806,7 @@ class DeviceCRPLearnErrors(DeviceCRP):
         """full-data log-likelihood at each (FP, FN) pair, from the [K][M] sufficient
         statistics (libs/CRP_learning_errors.py:58-63 without the [N,M] pass)."""
         with torch.cuda.stream(self.stream):
-            self._refresh_stats()
-            K = len(self.cells_per_cluster)
-            r = self._row_loglik(self.theta, self.ids_d.data_ptr(), K, self.S1, self.S0,
-                                 [float(fn) for _, fn in pairs], [float(fp) for fp, _ in pairs], False)
+            r = self._loglik([float(fn) for _, fn in pairs], [float(fp) for fp, _ in pairs], False)
         return [float(x) for x in r]
 
     def _mh_error(self, which):

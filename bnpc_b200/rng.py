@@ -123,17 +123,16 @@ class TapeRandom(_Base):
     def init_labels(self, n):
         return self.tape.take('int', n).astype(np.int64)
 
-    # bulk, device
+    # bulk: host arrays, uploaded by the model into its workspace buffers
     def uniform_rows(self, rows, m):
-        return self._up(self.tape.take('u', rows * m), torch.float64)
+        return self.tape.take('u', rows * m).copy()
 
     def beta_rows(self, rows, m):
         """`rows` consecutive Beta draws of length m (libs/CRP.py:172,184)."""
-        v = np.concatenate([self.tape.take('beta', m) for _ in range(rows)])
-        return self._up(v, torch.float64)
+        return np.concatenate([self.tape.take('beta', m) for _ in range(rows)])
 
     def step_sd_index(self, rows, m):
-        return self._up(self.tape.take('int', rows * m), torch.float64)
+        return self.tape.take('int', rows * m).copy()
 
     def mh_theta_draws(self, rows, m):
         """Per row: proposal-sd indices, truncnorm uniforms, acceptance uniforms
@@ -143,7 +142,7 @@ class TapeRandom(_Base):
             out[0, r] = self.tape.take('int', m)
             out[1, r] = self.tape.take('u', m)
             out[2, r] = self.tape.take('u', m)
-        return self._up(out, torch.float64)
+        return out
 
     def gibbs_draws(self, n, m):
         """permutation(N), then per visited cell one uniform and -- when that cell
@@ -156,18 +155,18 @@ class TapeRandom(_Base):
             if self.tape.next_is('beta'):
                 rows.append(self.tape.take('beta', m))
         # a non-NULL (dummy) pointer keeps the kernel in tape mode when no cluster was born
-        beta = self._up(np.stack(rows) if rows else np.zeros(1), torch.float64)
-        return self._up(perm, torch.int32), self._up(u, torch.float64), beta, len(rows)
+        beta = np.stack(rows) if rows else np.zeros(1)
+        return perm, u, beta, len(rows)
 
     def scan_draws(self, nf):
         """permutation(n-2) and one uniform per free cell (libs/CRP.py:616,625)."""
         perm = self.tape.take('perm', nf).astype(np.int32)
         u = np.concatenate([self.tape.take('u', 1) for _ in range(nf)]) if nf else np.zeros(0)
-        return self._up(perm, torch.int32), self._up(u, torch.float64)
+        return perm, u
 
     device_seed = 0
 
-    def next_stream(self):
+    def reserve(self, n):
         return 0
 
 
@@ -183,6 +182,12 @@ class PhiloxRandom(_Base):
     def next_stream(self):
         self.calls += 1
         return self.calls
+
+    def reserve(self, n):
+        """n consecutive device stream ids; returns the id BEFORE the first (ids base+1..base+n)"""
+        base = self.calls
+        self.calls += n
+        return base
 
     def _stream_ptr(self):
         return torch.cuda.current_stream(self.device).cuda_stream

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BNPC_ABI_VERSION 2
+#define BNPC_ABI_VERSION 3
 
 /* capacity of clusters born since the ll matrix of the current epoch was built */
 #define BNPC_MAX_EXTRA 32
@@ -96,6 +96,8 @@ typedef struct {
 
 int         bnpc_abi_version(void);
 const char* bnpc_last_error(void);
+/* kernels launched through this library since it was loaded (all threads) */
+int64_t     bnpc_launch_count(void);
 
 /* ---- input path: libs/dpmmIO.py:27-98 produces float64 {0,1,NaN}; this packs it.
  * x_f64 [N][M] row-major (NaN or any value other than 0/1 = missing), or
@@ -265,6 +267,89 @@ int bnpc_apply_split(const int32_t* cells, int n, const int32_t* half, int new_i
                      int32_t* assign, void* stream);
 int bnpc_apply_merge(const int32_t* cells, int n_a, int n, int id, int32_t* assign,
                      void* stream);
+
+/* ==== chain workspace: one C call per model method ================================
+ * The entry points above launch one kernel each.  The ones below enqueue, in one call, every
+ * launch a method of the reference's model classes needs (libs/MCMC.py:320-342 calls them once
+ * per step), reading their buffers from a workspace the caller fills once.  All device buffers
+ * are still allocated and owned by the caller; h_* are PINNED HOST buffers used for the small
+ * per-call inputs/outputs (copied asynchronously on `stream`; the caller synchronises the
+ * stream before reading h_out / h_scal).  Nothing is allocated, nothing synchronises.        */
+typedef struct {
+    /* read-only data shared by the chains of one device */
+    const uint32_t* x1; const uint32_t* x0; const int32_t* n1; const int32_t* n0; const double* logn;
+    int32_t W; int32_t N; int32_t M; int32_t idcap;
+    /* chain state */
+    int32_t* assign; float* theta /* [idcap][M] */; int32_t* cnt; int32_t* lst; int32_t* col_of_id;
+    int32_t* rank_of_id; int32_t* live_io /* [2*idcap] */; int32_t* st /* [BNPC_ST_WORDS] */;
+    /* Gibbs sweep */
+    bnpc_visit_t* visit; bnpc_cand_t* cand; bnpc_visit_t* visit_c; bnpc_cand_t* cand_c /* [N] each */;
+    int32_t* cblk /* [N/128+2] */; int32_t* perm /* [N] */; double* u /* [N] */;
+    double* lp /* [K][M][2] */; double* ll /* [rows][ldk] */; double* lpx /* [MAX_EXTRA][M][2] */;
+    double* llx /* [MAX_EXTRA][rows] */; double* scratch /* [idcap+1] */;
+    /* sufficient statistics of the live clusters, list order */
+    int32_t* ids; int32_t* seg; int32_t* cursor /* [K+1] each */; int32_t* members /* [N] */;
+    int32_t* S1; int32_t* S0 /* [K][M] */; double* rnd /* [3][K][M] */; int32_t* declined /* [K+1] */;
+    double* rl_out /* [5][K] */; double* rl_tot /* [8] */;
+    /* split-merge */
+    int32_t* cells /* [N+8] */; int32_t* half /* [N+8] */; int32_t* gblk; int32_t* seg3 /* [8] */;
+    int32_t* rg_work /* [2N+16] */; float* rg_theta /* [3][M] */; int32_t* rg_S1; int32_t* rg_S0 /* [3][M] */;
+    int32_t* rg_dec /* [4] */; double* rg_scal /* [32] */; double* rg_lp /* [2][M][2] */;
+    double* rg_ll2 /* [N][2] */; double* rg_lq /* [N] */; double* rg_logq /* [3][M] */; double* rg_A /* [2][M] */;
+    float* rg_orig /* [2][M] */; int32_t* rg_perm /* [N] */; double* rg_u /* [N] */; double* rg_rnd /* [3][2][M] */;
+    double* rg_sd /* [2][M] */; double* rg_beta /* [3][M], parity tape */;
+    /* pinned host staging */
+    int32_t* h_in; int32_t* h_out; double* h_scal;
+} bnpc_chain_t;
+
+/* One epoch of a Gibbs sweep (libs/CRP.py:254-299) over visits [t, t+rows): the live list
+ * (id, size pairs in list order) is read from h_in[0..2K); on return h_out holds the status
+ * block st[BNPC_ST_WORDS] followed by the live list after the epoch.  first != 0 starts a sweep:
+ * visiting order and uniforms are drawn (streams stream_id+1, +2 of `seed`) unless rand_ready
+ * says perm/u already hold them (parity tape), and the visit records are built.  Cluster births
+ * use stream_id + 2^24*(b+1) or the rows of beta_rows.                                       */
+typedef struct {
+    int32_t first; int32_t K; int32_t t; int32_t rows; int32_t ldk; int32_t rand_ready;
+    double c1; double c0; double lnew_prior; double c_norm; double log_n;
+    double FN; double FP; double p; double q;
+    uint64_t seed; uint64_t stream_id;
+    const double* beta_rows; int32_t n_beta_rows;
+    /* optional cudaEvent_t handles recorded around the ll matrix and the sweep launch (NULL: none) */
+    void* ev_ll0; void* ev_ll1; void* ev_sw0; void* ev_sw1;
+} bnpc_epoch_t;
+int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* stream);
+
+/* S1/S0 of the K live clusters (libs/CRP.py:308,360-367): h_in = ids[K], seg[K+1] (segment
+ * offsets = running sum of the sizes), max_len = largest size.                              */
+int bnpc_chain_stats(const bnpc_chain_t* w, int K, int max_len, void* stream);
+/* update_parameters (libs/CRP.py:302-344) for the K live clusters; draws from streams
+ * stream_id+1, +2 unless rand_ready (rnd already filled); h_out[0] = proposals declined.    */
+int bnpc_chain_mh_theta(const bnpc_chain_t* w, int K, int rand_ready, uint64_t seed, uint64_t stream_id,
+                        double FN, double FP, double p, double q, void* stream);
+/* h_scal[e] = full-data log-likelihood at (fn_h[e], fp_h[e]), e < E <= 4 (libs/CRP.py:237-238,
+ * libs/CRP_learning_errors.py:58-63); want_prior: h_scal[E] = sum of Beta(p,q).logpdf(theta)  */
+int bnpc_chain_loglik(const bnpc_chain_t* w, int K, const double* fn_h, const double* fp_h, int E,
+                      int want_prior, double p, double q, void* stream);
+
+/* A split-merge move (libs/CRP.py:434-567).  n cells of cluster cl_i (split: cl_j = -1) or of
+ * cl_i then cl_j (merge, n_a cells in cl_i); a_i, a_j = anchor positions.  Random streams
+ * stream_id+1.. of `seed` per call (at most 4) unless rand_ready (rg_perm, rg_u, rg_rnd, rg_sd,
+ * rg_beta filled from the parity tape).  rg_scal slots: 0 forward assignment log-prob, 1 forward
+ * theta log-prob, 2 backward theta, 3 backward assignment, 4-5 prior of the new rows, 6-7 of the
+ * old rows, 8-10 log-likelihood of side i, side j, all cells.                                */
+typedef struct {
+    int32_t n; int32_t n_a; int32_t cl_i; int32_t cl_j; int32_t a_i; int32_t a_j; int32_t is_merge;
+    int32_t rand_ready;
+    double alpha; double FN; double FP; double p; double q; double k6[6];
+    uint64_t seed; uint64_t stream_id;
+} bnpc_rg_t;
+int bnpc_chain_rg_setup(const bnpc_chain_t* w, const bnpc_rg_t* g, void* stream);
+int bnpc_chain_rg_scan_split(const bnpc_chain_t* w, const bnpc_rg_t* g, int want_logq, void* stream);
+int bnpc_chain_rg_scan_merged(const bnpc_chain_t* w, const bnpc_rg_t* g, int want_logq, void* stream);
+/* decision scalars -> h_scal[0..16) (= rg_scal), split also seg3 -> h_out[0..8)             */
+int bnpc_chain_rg_decide_split(const bnpc_chain_t* w, const bnpc_rg_t* g, int flat_prior, void* stream);
+int bnpc_chain_rg_decide_merge(const bnpc_chain_t* w, const bnpc_rg_t* g, int flat_prior, void* stream);
+int bnpc_chain_rg_apply(const bnpc_chain_t* w, const bnpc_rg_t* g, int new_id, void* stream);
 
 #ifdef __cplusplus
 }

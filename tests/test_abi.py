@@ -28,19 +28,40 @@ def test_library_exports_header_symbols():
 
 
 def test_ctypes_signatures_match_header():
-    declared = set(_declared()) - {'bnpc_abi_version', 'bnpc_last_error'}
+    declared = set(_declared()) - {'bnpc_abi_version', 'bnpc_last_error', 'bnpc_launch_count'}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.lib().abi_version() == 2
+    assert _lib.lib().abi_version() == 3
 
 
-def test_sweep_args_layout_matches_c():
-    # field order/size of the ctypes mirror of bnpc_sweep_args_t
+def _struct_fields(name):
     src = open(os.path.join(ROOT, 'include', 'bnpc_b200.h')).read()
-    body = re.search(r'typedef struct \{((?:(?!typedef struct).)*?)\} bnpc_sweep_args_t;', src, flags=re.S).group(1)
+    body = re.search(r'typedef struct \{((?:(?!typedef struct).)*?)\} ' + name + ';', src, flags=re.S).group(1)
     body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
-    fields = re.findall(r'(?:const\s+)?[a-z0-9_]+\s*\*?\s*([A-Za-z0-9_]+)\s*;', body)
-    assert fields == [f for f, _ in _lib.SweepArgs._fields_]
-    assert ctypes.sizeof(_lib.SweepArgs) % 8 == 0
+    return re.findall(r'(?:const\s+)?[a-z0-9_]+\s*\*?\s*([A-Za-z0-9_]+)\s*(?:\[\d+\])?\s*;', body)
+
+
+@pytest.mark.parametrize('c_name,mirror', [('bnpc_sweep_args_t', 'SweepArgs'), ('bnpc_chain_t', 'ChainWs'),
+                                           ('bnpc_epoch_t', 'Epoch'), ('bnpc_rg_t', 'RgMove')])
+def test_struct_layouts_match_c(c_name, mirror):
+    # field order of the ctypes mirrors of the structs declared in the header
+    cls = getattr(_lib, mirror)
+    assert _struct_fields(c_name) == [f[0] for f in cls._fields_]
+    assert ctypes.sizeof(cls) % 8 == 0
+
+
+def test_struct_sizes_match_c(tmp_path):
+    # compile a tiny C program against the header and compare sizeof() with the mirrors
+    import subprocess
+    src = tmp_path / 'sizes.c'
+    src.write_text('#include <stdio.h>\n#include "bnpc_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(bnpc_sweep_args_t),sizeof(bnpc_chain_t),sizeof(bnpc_epoch_t),sizeof(bnpc_rg_t),'
+                   'sizeof(bnpc_visit_t),sizeof(bnpc_cand_t));return 0;}\n')
+    exe = tmp_path / 'sizes'
+    subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(_lib.SweepArgs), ctypes.sizeof(_lib.ChainWs), ctypes.sizeof(_lib.Epoch),
+            ctypes.sizeof(_lib.RgMove), _lib.VISIT_BYTES, _lib.CAND_BYTES]
+    assert got == want
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -45,12 +45,12 @@ def wrap(obj, name):
 
     def timed(*a, **k):
         torch.cuda.synchronize()
-        l0 = _lib.launch_count
+        l0 = _lib.launch_count()
         t0 = time.perf_counter()
         r = fn(*a, **k)
         torch.cuda.synchronize()
         acc[name].append(time.perf_counter() - t0)
-        launches[name].append(_lib.launch_count - l0)
+        launches[name].append(_lib.launch_count() - l0)
         return r
     setattr(obj, name, timed)
 
