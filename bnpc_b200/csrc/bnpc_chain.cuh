@@ -68,24 +68,39 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
     TRY(bnpc_gibbs_epoch_begin(w->live_io, K, w->lst, w->cnt, w->col_of_id, w->idcap, w->st, e->first, stream));
     TRY(bnpc_logprob_tables(w->theta, w->lst, K, M, e->FN, e->FP, w->lp, stream));
     // cell indices are read straight out of the visit records
-    TRY(record_event(e->ev_ll0, stream));
-    TRY(bnpc_ll_matrix(w->x1, w->x0, w->W, M, &w->visit[t].cell, (int)(sizeof(bnpc_visit_t) / 4), rows, w->lp,
-                       K, w->ll, ldk, stream));
-    TRY(record_event(e->ev_ll1, stream));
-    const bool compacted = ldk <= SW_MAXL;
-    if (compacted) {
-        TRY(bnpc_gibbs_candidates(w->ll, ldk, K, w->col_of_id, w->visit + t, w->cand + t, rows, e->log_n,
-                                  e->c_norm, w->cblk, stream));
-        TRY(bnpc_gibbs_compact(w->visit + t, w->cand + t, rows, w->cblk, w->visit_c, w->cand_c, w->st, stream));
+    const int32_t* cells = &w->visit[t].cell;
+    const int cstride = (int)(sizeof(bnpc_visit_t) / 4);
+    const bool lean = e->lean != 0;
+    const bool compacted = lean || ldk <= SW_MAXL;
+    if (lean) {
+        // approximate rows pick the options; FP64 only for the options of the uncertain visits
+        if (K > BNPC_LEAN_MAXK) return bad_arg("lean epoch with K > BNPC_LEAN_MAXK");
+        const int ldf = (K + 7) & ~7;
+        TRY(record_event(e->ev_ll0, stream));
+        TRY(bnpc_ll_matrix_f32(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp, w->lpf, K, w->llf, ldf, stream));
+        TRY(record_event(e->ev_ll1, stream));
+        TRY(bnpc_gibbs_options(w->llf, ldf, K, w->col_of_id, w->visit + t, w->opt + t, w->n_cert, rows, e->log_n,
+                               e->c_norm, 2 * M, stream));
+        TRY(bnpc_gibbs_exact(w->x1, w->x0, w->W, M, w->lp, K, w->visit + t, w->opt + t, w->n_cert, rows, w->cblk,
+                             w->idx_c, w->st, w->visit_c, w->cand_c, e->log_n, e->c_norm, stream));
+    } else {
+        TRY(record_event(e->ev_ll0, stream));
+        TRY(bnpc_ll_matrix(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp, K, w->ll, ldk, stream));
+        TRY(record_event(e->ev_ll1, stream));
+        if (compacted) {
+            TRY(bnpc_gibbs_candidates(w->ll, ldk, K, w->col_of_id, w->visit + t, w->cand + t, rows, e->log_n,
+                                      e->c_norm, w->cblk, stream));
+            TRY(bnpc_gibbs_compact(w->visit + t, w->cand + t, rows, w->cblk, w->visit_c, w->cand_c, w->st, stream));
+        }
     }
     bnpc_sweep_args_t a;
     memset(&a, 0, sizeof(a));
     a.x1 = w->x1; a.x0 = w->x0; a.W = w->W; a.N = N; a.M = M;
     a.assign = w->assign; a.cnt = w->cnt; a.lst = w->lst; a.col_of_id = w->col_of_id; a.theta = w->theta;
     a.idcap = w->idcap; a.st = w->st; a.live_out = w->live_io;
-    a.ll = w->ll; a.ldk = ldk; a.t_epoch0 = t;
+    a.ll = lean ? nullptr : w->ll; a.ldk = ldk; a.t_epoch0 = t; a.lp = w->lp;
     a.lpx = w->lpx; a.llx = w->llx; a.ldx = rows; a.scratch = w->scratch;
-    a.visit = w->visit; a.cand = w->cand; a.t_begin = t; a.t_end = t + rows;
+    a.visit = w->visit; a.cand = lean ? nullptr : w->cand; a.t_begin = t; a.t_end = t + rows;
     a.visit_c = compacted ? w->visit_c : nullptr;
     a.cand_c = compacted ? w->cand_c : nullptr;
     a.beta_rows = e->beta_rows; a.n_beta_rows = e->n_beta_rows;

@@ -437,6 +437,8 @@ compact_scatter_kernel(const bnpc_visit_t* __restrict__ visit, const bnpc_cand_t
     for (int i = 0; i < (int)(sizeof(bnpc_cand_t) / 16); ++i) dc[i] = sc[i];
 }
 
+#include "bnpc_lean.cuh"
+
 __global__ void gibbs_epoch_begin_kernel(const int32_t* __restrict__ live, int K, int32_t* lst,
                                          int32_t* cnt, int32_t* col_of_id, int idcap, int32_t* st,
                                          int first) {
@@ -452,6 +454,7 @@ __global__ void gibbs_epoch_begin_kernel(const int32_t* __restrict__ live, int K
         st[BNPC_ST_K] = K;
         st[BNPC_ST_NEXTRA] = 0;
         st[BNPC_ST_FLAGS] = 0;
+        st[BNPC_ST_NMANY] = 0;
         if (first) {
             st[BNPC_ST_TDONE] = 0; st[BNPC_ST_BIRTHS] = 0; st[BNPC_ST_MOVED] = 0; st[BNPC_ST_SLOW] = 0;
         }
@@ -507,6 +510,7 @@ struct SweepShared {
     int tmp_i, pick;
     int hang;
     int compact, crec;                          // compact mode on / next compacted record
+    double s_row[BNPC_LEAN_MAXK];               // lean epochs: exact ll row of the cell in hand, by column
 };
 
 // One exact categorical draw for a list that fits a warp (libs/CRP.py:88-100 + numpy choice,
@@ -655,8 +659,11 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
     __syncwarp();
     sweep_rebuild_maps(sh, L);
     const int n_extra = sh.n_extra;
-    const bool compact = sh.compact && cmin >= 2 && n_extra == 0;
-    const int need_cnt = compact ? 2 : 1;       // cells a cluster keeps after a batched move
+    // lean epochs: a cluster never holds a single certain visit (gibbs_finalize_kernel), so the
+    // compacted records stay valid whatever the sizes do; dense epochs check the sizes instead
+    const bool lean = a.ll == nullptr;
+    const bool compact = lean || (sh.compact && cmin >= 2 && n_extra == 0);
+    const int need_cnt = (compact && !lean) ? 2 : 1;   // cells a cluster keeps after a batched move
 
     const bnpc_visit_t* vbase = compact ? a.visit_c : a.visit + a.t_epoch0;
     const bnpc_cand_t* cbase = compact ? a.cand_c : a.cand + a.t_epoch0;
@@ -822,8 +829,8 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
             const int f = fb;
             const int t_f = __shfl_sync(FULL, v.t, f);
             ++slow;
-            if (L > 31) {                           // CTA-wide exact draw, then come back
-                if (lane == 0) sh.pending = 2;
+            if (lean || L > 31) {                   // CTA-wide work (exact row / exact draw), then come back
+                if (lane == 0) sh.pending = lean ? 3 : 2;
                 next_t = t_f; next_rec = rec0 + f + 1;
                 leave = true;
                 break;
@@ -864,7 +871,8 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
 }
 
 // one cell with the whole CTA (list longer than a warp)
-__device__ void sweep_block_cell(const bnpc_sweep_args_t& a, SweepShared& sh, int t, int L) {
+__device__ void sweep_block_cell(const bnpc_sweep_args_t& a, SweepShared& sh, int t, int L,
+                                 const double* rowp) {
     const int tid = threadIdx.x, B = blockDim.x;
     const bnpc_visit_t v = a.visit[t];
     int old = v.old;
@@ -891,7 +899,6 @@ __device__ void sweep_block_cell(const bnpc_sweep_args_t& a, SweepShared& sh, in
         __syncthreads();
     }
     const long long tx = t - a.t_epoch0;
-    const double* rowp = a.ll + tx * a.ldk;
     double m_all = -BNPC_INF, m_riv = -BNPC_INF, l_old = -BNPC_INF;
     for (int j = tid; j <= L; j += B) {
         double l;
@@ -993,7 +1000,8 @@ __device__ void sweep_birth(const bnpc_sweep_args_t& a, SweepShared& sh) {
         __syncthreads();
         return;
     }
-    double2* lpx = reinterpret_cast<double2*>(a.lpx) + (long long)e * M;
+    const bool lean = a.ll == nullptr;         // lean epochs end at a birth: no ll column is built
+    double2* lpx = lean ? nullptr : reinterpret_cast<double2*>(a.lpx) + (long long)e * M;
     const uint32_t* r1 = a.x1 + (long long)cell * W;
     const uint32_t* r0 = a.x0 + (long long)cell * W;
     for (int m = tid; m < M; m += B) {
@@ -1007,15 +1015,19 @@ __device__ void sweep_birth(const bnpc_sweep_args_t& a, SweepShared& sh) {
         }
         const float th = clip_theta(val);
         a.theta[(long long)nid * M + m] = th;
-        double p1, p0;
-        log_p1_p0(th, a.FN, a.FP, p1, p0);
-        lpx[m] = make_double2(p1, p0);
+        if (!lean) {
+            double p1, p0;
+            log_p1_p0(th, a.FN, a.FP, p1, p0);
+            lpx[m] = make_double2(p1, p0);
+        }
     }
     __syncthreads();
-    double* col = a.llx + (long long)e * a.ldx;
-    for (int tt = t + 1 + tid; tt < a.t_end; tt += B) {
-        const long long c2 = a.visit[tt].cell;
-        col[tt - a.t_epoch0] = cell_row_ll(a.x1 + c2 * W, a.x0 + c2 * W, (M + 31) >> 5, lpx);
+    if (!lean) {
+        double* col = a.llx + (long long)e * a.ldx;
+        for (int tt = t + 1 + tid; tt < a.t_end; tt += B) {
+            const long long c2 = a.visit[tt].cell;
+            col[tt - a.t_epoch0] = cell_row_ll(a.x1 + c2 * W, a.x0 + c2 * W, (M + 31) >> 5, lpx);
+        }
     }
     if (tid == 0) {
         a.lst[L] = nid;
@@ -1026,7 +1038,7 @@ __device__ void sweep_birth(const bnpc_sweep_args_t& a, SweepShared& sh) {
         sh.n_extra = e + 1;
         sh.births = b + 1;
         sh.pending = 0;
-        if (e + 1 >= BNPC_MAX_EXTRA) sh.stop |= BNPC_STOP_EXTRA_FULL;
+        if (lean || e + 1 >= BNPC_MAX_EXTRA) sh.stop |= BNPC_STOP_EXTRA_FULL;
     }
     __syncthreads();
 }
@@ -1071,7 +1083,32 @@ gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
             // the sequencer handed this cell to the CTA-wide exact draw
             if (tid == 0) sh.pending = 0;
             __syncthreads();
-            sweep_block_cell(a, sh, t, L);
+            sweep_block_cell(a, sh, t, L, a.ll + (long long)(t - a.t_epoch0) * a.ldk);
+        } else if (pending == 3) {
+            // lean epoch: the exact FP64 row of this cell, one thread per live cluster in the
+            // arithmetic of ll_matrix_kernel, then the exact draw
+            if (tid == 0) sh.pending = 0;
+            const long long cell = a.visit[t].cell;
+            if (tid < L) {
+                const int col = a.col_of_id[a.lst[tid]];
+                sh.s_row[col] = cell_row_ll(a.x1 + cell * a.W, a.x0 + cell * a.W, (a.M + 31) >> 5,
+                                            reinterpret_cast<const double2*>(a.lp) + (long long)col * a.M);
+            }
+            __syncthreads();
+            if (L <= 31) {
+                if (tid < 32) {
+                    int L2 = L;
+                    const int status = sweep_exact_cell(a, sh, a.visit[t], sh.s_row, t, L2);
+                    if (tid == 0) {
+                        sh.L = L2;
+                        sh.t = t + 1;
+                        if (status) sh.moved += 1;
+                    }
+                }
+                __syncthreads();
+            } else {
+                sweep_block_cell(a, sh, t, L, sh.s_row);
+            }
         } else if (L < SW_MAXL && a.ldk <= SW_MAXL) {
             if (tid < 32) sweep_sequencer(a, sh);
             __syncthreads();
@@ -1082,7 +1119,7 @@ gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
             __syncthreads();
             continue;
         } else {
-            sweep_block_cell(a, sh, t, L);
+            sweep_block_cell(a, sh, t, L, a.ll + (long long)(t - a.t_epoch0) * a.ldk);
         }
         if (sh.pending == 1) sweep_birth(a, sh);
     }
@@ -1691,6 +1728,60 @@ int bnpc_gibbs_compact(const bnpc_visit_t* visit_t0, const bnpc_cand_t* cand_t0,
     compact_scatter_kernel<<<nb, CAND_THREADS, 0, (cudaStream_t)stream>>>(visit_t0, cand_t0, C, blk, visit_c,
                                                                          cand_c);
     LAUNCH_CHECK("compact_scatter");
+    return 0;
+}
+
+int bnpc_ll_matrix_f32(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
+                       int cell_stride, int C, const double* lp, float* lpf, int K, float* llf, int ldf,
+                       void* stream) {
+    if (C <= 0 || K <= 0) return 0;
+    if (ldf < K) return bad_arg("ldf < K");
+    if (W % 4 != 0) return bad_arg("W must be a multiple of 4");
+    const long long n = (long long)K * M;
+    lp_to_f32_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double2*>(lp), n,
+                                                                     reinterpret_cast<float2*>(lpf));
+    LAUNCH_CHECK("lp_to_f32");
+    dim3 grid(cdiv(C, LL_THREADS), cdiv(K, LLF_KT));
+    ll_matrix_f32_kernel<<<grid, LL_THREADS, 0, (cudaStream_t)stream>>>(
+        x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const float2*>(lpf), K, llf, ldf);
+    LAUNCH_CHECK("ll_matrix_f32");
+    return 0;
+}
+
+int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_id,
+                       const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, int32_t* n_cert, int C,
+                       double log_n, double c_norm, int terms, void* stream) {
+    if (C <= 0) return 0;
+    if (K <= 0 || K > BNPC_LEAN_MAXK) return bad_arg("lean epochs need K <= BNPC_LEAN_MAXK");
+    cudaError_t ce = cudaMemsetAsync(n_cert, 0, sizeof(int32_t) * BNPC_LEAN_MAXK, (cudaStream_t)stream);
+    if (ce != cudaSuccess) return fail("gibbs_options memset", ce);
+    const float err_rel = (float)terms * 2.384185791015625e-07f;      // terms * 2^-22
+    gibbs_options_kernel<<<cdiv(C, CAND_THREADS), CAND_THREADS, 0, (cudaStream_t)stream>>>(
+        llf, ldf, K, col_of_id, visit_t0, opt_t0, n_cert, C, (float)log_n, c_norm, err_rel);
+    LAUNCH_CHECK("gibbs_options");
+    return 0;
+}
+
+int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const double* lp, int K,
+                     const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, const int32_t* n_cert, int C,
+                     int32_t* blk, int32_t* idx_c, int32_t* st, bnpc_visit_t* visit_c,
+                     bnpc_cand_t* cand_c, double log_n, double c_norm, void* stream) {
+    if (C <= 0) return 0;
+    if (K <= 0 || K > BNPC_LEAN_MAXK) return bad_arg("lean epochs need K <= BNPC_LEAN_MAXK");
+    const int nb = cdiv(C, CAND_THREADS);
+    cudaStream_t s = (cudaStream_t)stream;
+    gibbs_finalize_kernel<<<nb, CAND_THREADS, 0, s>>>(opt_t0, n_cert, C, blk);
+    LAUNCH_CHECK("gibbs_finalize");
+    compact_scan_kernel<<<1, 1024, 0, s>>>(blk, nb, st);
+    LAUNCH_CHECK("compact_scan");
+    compact_index_kernel<<<nb, CAND_THREADS, 0, s>>>(opt_t0, C, blk, idx_c);
+    LAUNCH_CHECK("compact_index");
+    const size_t smem = sizeof(double2) * 32 * (size_t)K;
+    // the number of uncertain visits lives on the device: blocks beyond it exit at once
+    gibbs_exact_kernel<<<cdiv(C, EX_THREADS), EX_THREADS, smem, s>>>(
+        x1, x0, W, M, reinterpret_cast<const double2*>(lp), K, visit_t0, opt_t0, idx_c, st, visit_c, cand_c,
+        log_n, c_norm);
+    LAUNCH_CHECK("gibbs_exact");
     return 0;
 }
 

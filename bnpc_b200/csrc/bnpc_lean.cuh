@@ -1,0 +1,262 @@
+// "Lean" epoch of the Gibbs sweep for lists of at most BNPC_LEAN_MAXK clusters.
+//
+// The sweep needs exact (FP64) log-likelihoods only where a decision depends on them.  An
+// APPROXIMATE cells x clusters matrix (FP32 accumulation: FP32 FMA here, bf16-split operands on
+// the tcgen05 tensor cores in bnpc_tc.cuh) is enough to prove, with its rounding error bounded,
+// that a cluster cannot come within 40 + log N nats of the cell's own cluster for ANY cluster
+// sizes -- such clusters sit on the reference's 1e-15 probability floor (libs/CRP.py:88-100).
+// Only the surviving (cell, cluster) pairs of the visits that are not statically certain are
+// then evaluated in FP64, in exactly the arithmetic of ll_matrix_kernel.
+//
+//   lp_to_f32_kernel        (log p1, log p0) table in float
+//   ll_matrix_f32_kernel    approximate ll rows, FP32 FMA (reference for / fallback of the TC kernel)
+//   gibbs_options_kernel    per visit: option columns from the approximate row, provisional
+//                           "certain" flag, per-cluster counts of certain visits
+//   gibbs_finalize_kernel   a cluster with a single certain visit loses it (the cluster could
+//                           shrink to that one cell); per-block counts of uncertain visits
+//   compact_index_kernel    visit indices of the uncertain visits, in visiting order
+//   gibbs_exact_kernel      FP64 log-likelihoods of their options -> compacted visit/option records
+
+__global__ void lp_to_f32_kernel(const double2* __restrict__ lp, long long n, float2* __restrict__ lpf) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const double2 v = lp[i]; lpf[i] = make_float2((float)v.x, (float)v.y); }
+}
+
+#define LLF_KT 16
+__global__ void __launch_bounds__(LL_THREADS)
+ll_matrix_f32_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
+                     const int32_t* __restrict__ cells, int cell_stride, int C,
+                     const float2* __restrict__ lp, int K, float* __restrict__ ll, int ldk) {
+    __shared__ float2 tile[LL_MT][LLF_KT];
+    const int r = blockIdx.x * LL_THREADS + threadIdx.x;
+    const int k0 = blockIdx.y * LLF_KT;
+    const bool live = r < C;
+    const long long cell = live ? (cells ? cells[(long long)r * cell_stride] : r) : 0;
+    const uint4* p1 = reinterpret_cast<const uint4*>(x1 + cell * W);
+    const uint4* p0 = reinterpret_cast<const uint4*>(x0 + cell * W);
+    float acc[LLF_KT];
+#pragma unroll
+    for (int kk = 0; kk < LLF_KT; ++kk) acc[kk] = 0.0f;
+    for (int m0 = 0; m0 < M; m0 += LL_MT) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < LL_MT * LLF_KT; i += LL_THREADS) {
+            const int kk = i / LL_MT, mm = i % LL_MT;
+            float2 v = make_float2(0.0f, 0.0f);
+            if (k0 + kk < K && m0 + mm < M) v = lp[(long long)(k0 + kk) * M + m0 + mm];
+            tile[mm][kk] = v;
+        }
+        __syncthreads();
+        if (live) {
+            const uint4 a = p1[m0 >> 7], b = p0[m0 >> 7];
+            const uint32_t w1[4] = {a.x, a.y, a.z, a.w}, w0[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t u1 = w1[q], u0 = w0[q];
+                if ((u1 | u0) == 0u) continue;
+#pragma unroll 4
+                for (int bit = 0; bit < 32; ++bit) {
+                    const float f1 = (float)((u1 >> bit) & 1u), f0 = (float)((u0 >> bit) & 1u);
+                    const float2* t = tile[q * 32 + bit];
+#pragma unroll
+                    for (int kk = 0; kk < LLF_KT; ++kk) {
+                        const float2 v = t[kk];
+                        acc[kk] = fmaf(f1, v.x, fmaf(f0, v.y, acc[kk]));
+                    }
+                }
+            }
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int kk = 0; kk < LLF_KT; ++kk)
+            if (k0 + kk < K) ll[(long long)r * ldk + k0 + kk] = acc[kk];
+    }
+}
+
+// err_rel = (number of summed terms) * 2^-22: every term of a row sum is <= 0, so partial sums
+// never exceed the total in magnitude and FP32 accumulation (rounded or truncated, in any order)
+// is off by at most terms * 2^-23 * |sum|; the factor 2 and the constant are head-room.
+__global__ void __launch_bounds__(CAND_THREADS)
+gibbs_options_kernel(const float* __restrict__ llf, int ldf, int K, const int32_t* __restrict__ col_of_id,
+                     const bnpc_visit_t* __restrict__ visit, bnpc_opt_t* __restrict__ opt,
+                     int32_t* __restrict__ n_cert, int C, float slack, double c_norm, float err_rel) {
+    __shared__ int s_cert[BNPC_LEAN_MAXK];
+    if (threadIdx.x < BNPC_LEAN_MAXK) s_cert[threadIdx.x] = 0;
+    __syncthreads();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < C) {
+        const float* row = llf + (long long)r * ldf;
+        const int c_old = col_of_id[visit[r].old];
+        bnpc_opt_t o;
+#pragma unroll
+        for (int i = 0; i < BNPC_MAX_OPT; ++i) o.col[i] = 0;
+        o.n_opt = BNPC_MAX_OPT + 1; o.i_old = 0; o.flags = BNPC_OPT_MANY; o.pad = 0;
+        if (c_old >= 0 && c_old < K) {
+            const float v_old = row[c_old];
+            const float err = err_rel * (fabsf(v_old) + 64.0f) + 0.05f;
+            const float thr = v_old - 40.0f - slack - 2.0f * err;
+            int n = 0, i_old = 0;
+            for (int k = 0; k < K; ++k) {
+                const float v = row[k];
+                if (k != c_old && !(v > thr)) continue;
+                if (k == c_old) i_old = n;
+#pragma unroll
+                for (int i = 0; i < BNPC_MAX_OPT; ++i)
+                    if (i == n) o.col[i] = (uint8_t)k;
+                ++n;
+            }
+            if (n <= BNPC_MAX_OPT) {
+                o.n_opt = (uint8_t)n; o.i_old = (uint8_t)i_old; o.flags = 0;
+                const double lnew_ll = visit[r].lnew + c_norm;
+                const double u = visit[r].u;
+                if (n == 1 && lnew_ll < (double)(v_old - 40.0f - err) && u > 3e-10 && u < 1.0 - 3e-10) {
+                    o.flags = BNPC_VISIT_CERTAIN;
+                    atomicAdd(&s_cert[c_old], 1);
+                }
+            }
+        }
+        opt[r] = o;
+    }
+    __syncthreads();
+    if (threadIdx.x < K && s_cert[threadIdx.x]) atomicAdd(&n_cert[threadIdx.x], s_cert[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(CAND_THREADS)
+gibbs_finalize_kernel(bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ n_cert, int C,
+                      int32_t* __restrict__ blk) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int uncertain = 0;
+    if (r < C) {
+        const uint8_t flags = opt[r].flags;
+        bool certain = (flags & BNPC_VISIT_CERTAIN) != 0;
+        if (certain && n_cert[opt[r].col[0]] < 2) {
+            certain = false;
+            opt[r].flags = flags & ~BNPC_VISIT_CERTAIN;
+        }
+        uncertain = !certain;
+    }
+    const int cnt = __syncthreads_count(uncertain);
+    if (threadIdx.x == 0) blk[blockIdx.x] = cnt;
+}
+
+__global__ void __launch_bounds__(CAND_THREADS)
+compact_index_kernel(const bnpc_opt_t* __restrict__ opt, int C, const int32_t* __restrict__ blk,
+                     int32_t* __restrict__ idx_c) {
+    __shared__ int wcnt[CAND_THREADS / 32];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool take = r < C && !(opt[r].flags & BNPC_VISIT_CERTAIN);
+    const unsigned m = __ballot_sync(FULL, take);
+    if (lane == 0) wcnt[w] = __popc(m);
+    __syncthreads();
+    if (!take) return;
+    int pos = blk[blockIdx.x] + __popc(m & ((1u << lane) - 1u));
+    for (int i = 0; i < w; ++i) pos += wcnt[i];
+    idx_c[pos] = r;
+}
+
+#define EX_THREADS 256
+// One thread per uncertain visit: FP64 log-likelihood of each of its options in the arithmetic
+// of ll_matrix_kernel (mutation order, fma(f1, lp1, fma(f0, lp0, acc))), then the option weights
+// exactly as gibbs_candidates_kernel derives them from the FP64 matrix.
+__global__ void __launch_bounds__(EX_THREADS)
+gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
+                   const double2* __restrict__ lp, int K, const bnpc_visit_t* __restrict__ visit,
+                   const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ idx_c,
+                   int32_t* __restrict__ st, bnpc_visit_t* __restrict__ visit_c,
+                   bnpc_cand_t* __restrict__ cand_c, double slack, double c_norm) {
+    extern __shared__ __align__(16) unsigned char ex_smem[];
+    double2* tile = reinterpret_cast<double2*>(ex_smem);          // [32][K]
+    const int n_unc = st[BNPC_ST_NUNC];
+    if (blockIdx.x * EX_THREADS >= n_unc) return;
+    const int j = blockIdx.x * EX_THREADS + threadIdx.x;
+    const bool live = j < n_unc;
+    const int r = live ? idx_c[j] : idx_c[0];
+    bnpc_visit_t v = visit[r];
+    const bnpc_opt_t o = opt[r];
+    const int nn = (live && o.n_opt <= BNPC_MAX_OPT) ? o.n_opt : 0;
+    int col[BNPC_MAX_OPT];
+    double acc[BNPC_MAX_OPT];
+#pragma unroll
+    for (int i = 0; i < BNPC_MAX_OPT; ++i) { col[i] = (i < nn) ? o.col[i] : 0; acc[i] = 0.0; }
+    int n_max = nn;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) n_max = max(n_max, __shfl_xor_sync(FULL, n_max, s));
+    const uint32_t* p1 = x1 + (long long)v.cell * W;
+    const uint32_t* p0 = x0 + (long long)v.cell * W;
+    const int words = (M + 31) >> 5;
+    for (int w = 0; w < words; ++w) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * K; i += EX_THREADS) {
+            const int kk = i >> 5, mm = i & 31, m = w * 32 + mm;       // coalesced along mutations
+            tile[mm * K + kk] = (m < M) ? lp[(long long)kk * M + m] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        if (n_max == 0) continue;
+        const uint32_t u1 = p1[w], u0 = p0[w];
+        if (nn == 0 || (u1 | u0) == 0u) continue;
+#pragma unroll 2
+        for (int bit = 0; bit < 32; ++bit) {
+            const double f1 = (double)((u1 >> bit) & 1u), f0 = (double)((u0 >> bit) & 1u);
+            const double2* t = tile + bit * K;
+#pragma unroll
+            for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+                if (i >= n_max) break;                               // warp-uniform
+                if (i < nn) {
+                    const double2 q = t[col[i]];
+                    acc[i] = fma(f1, q.x, fma(f0, q.y, acc[i]));
+                }
+            }
+        }
+    }
+    if (!live) return;
+    // same selection and weights as gibbs_candidates_kernel, on the exact values
+    const double lnew_ll = v.lnew + c_norm;
+    bnpc_cand_t out;
+    double val[BNPC_MAX_OPT];
+#pragma unroll
+    for (int i = 0; i < BNPC_MAX_OPT; ++i) { out.e[i] = 0.0; out.col[i] = 0; val[i] = -BNPC_INF; }
+    out.pad[0] = out.pad[1] = out.pad[2] = 0;
+    int n = BNPC_MAX_OPT + 1, i_old = 0;
+    double ref = 0.0, e_new = 0.0, e_max = 1.0;
+    int c_old = -1;
+    if (nn > 0) {
+        double v_old = 0.0;
+#pragma unroll
+        for (int i = 0; i < BNPC_MAX_OPT; ++i)
+            if (i == o.i_old) { v_old = acc[i]; c_old = col[i]; }
+        const double thr = v_old - 40.0 - slack;
+        n = 0;
+        ref = fmax(v_old, lnew_ll);
+#pragma unroll
+        for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+            if (i < nn) {
+                const bool own = (i == o.i_old);
+                if (own || acc[i] > thr) {
+                    if (own) i_old = n;
+#pragma unroll
+                    for (int s = 0; s < BNPC_MAX_OPT; ++s)
+                        if (s == n) { val[s] = acc[i]; out.col[s] = (uint16_t)col[i]; }
+                    ref = fmax(ref, acc[i]);
+                    ++n;
+                }
+            }
+        }
+        e_max = 0.0;
+#pragma unroll
+        for (int i = 0; i < BNPC_MAX_OPT; ++i)
+            if (i < n) { out.e[i] = exp(val[i] - ref); e_max = fmax(e_max, out.e[i]); }
+        e_new = exp(lnew_ll - ref);
+    } else {
+        atomicAdd(&st[BNPC_ST_NMANY], 1);
+    }
+    v.e_new = e_new;
+    v.ref = ref;
+    v.c_old = c_old;
+    v.n_opt = n;
+    v.i_old = i_old;
+    v.flags = 0;
+    v.e_max = __double2float_ru(e_max);
+    visit_c[j] = v;
+    cand_c[j] = out;
+}

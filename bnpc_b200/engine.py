@@ -112,6 +112,7 @@ class DeviceCRP:
     """Fixed error rates (reference class `CRP`, libs/CRP.py:17-66)."""
 
     learning = False
+    lean_enabled = True           # class-wide switch (tests force the dense FP64 matrix with False)
 
     def __init__(self, data, DP_alpha=(-1, -1), param_beta=(1, 1), FN_error=EPS, FP_error=EPS,
                  device=None, rnd=None):
@@ -252,6 +253,12 @@ class DeviceCRP:
             self._dev('perm', N, i32)
             self._dev('u', N, f64)
             self._dev('lpx', 2 * _lib.MAX_EXTRA * M, f64)
+            self._dev('lpf', 2 * _lib.LEAN_MAXK * M, f32)
+            self._dev('llf', N * _lib.LEAN_MAXK, f32)
+            self._dev('opt', N * _lib.OPT_BYTES, u8)
+            self._dev('n_cert', _lib.LEAN_MAXK, i32, zero=True)
+            self._dev('idx_c', N, i32)
+            self._lean_ok = True
             self.members = self._dev('members', N, i32)
             self._dev('rl_tot', 8, f64)
             # split-merge
@@ -494,11 +501,15 @@ class DeviceCRP:
                 h[1:2 * K:2] = np.fromiter(self.cells_per_cluster.values(), dtype=np.int32, count=K)
                 # odd row stride (bank-conflict-free per-lane row reads in the warp regime)
                 ldk = max(3, K | 1)
-                rows = int(min(N - t, max(1, LL_BUDGET_BYTES // (8 * ldk))))
-                if rows * ldk + 2 > self._ll_cap:
+                # lean epoch: approximate rows select the options, FP64 only where a decision
+                # needs it; dense FP64 matrix for longer lists (or when many cells have > 8 rivals)
+                lean = K <= _lib.LEAN_MAXK and self._lean_ok and self.lean_enabled
+                rows = N - t if lean else int(min(N - t, max(1, LL_BUDGET_BYTES // (8 * ldk))))
+                ep.lean = 1 if lean else 0
+                if not lean and rows * ldk + 2 > self._ll_cap:
                     self._ll_cap = rows * ldk + 2
                     self._dev('ll', self._ll_cap, torch.float64)
-                if _lib.MAX_EXTRA * rows > self._llx_cap:
+                if not lean and _lib.MAX_EXTRA * rows > self._llx_cap:
                     self._llx_cap = _lib.MAX_EXTRA * rows
                     self._dev('llx', self._llx_cap, torch.float64)
                 ep.first, ep.K, ep.t, ep.rows, ep.ldk = first, K, t, rows, ldk
@@ -523,6 +534,10 @@ class DeviceCRP:
                 pairs = self.h_out[_lib.ST_WORDS:_lib.ST_WORDS + 2 * K].tolist()
                 self.cells_per_cluster = OrderedDict(zip(pairs[0::2], pairs[1::2]))
                 t_new = int(st[_lib.ST_TDONE])
+                if lean and int(st[_lib.ST_NMANY]) > max(64, rows // 50):
+                    self._lean_ok = False          # too many cells with > 8 rivals: dense rows pay
+                elif not lean and K <= _lib.LEAN_MAXK:
+                    self._lean_ok = True           # try again next time
                 stall = stall + 1 if t_new == t else 0
                 if stall > 2:
                     raise RuntimeError(f'gibbs_sweep made no progress at t={t} (flags {flags:#x})')

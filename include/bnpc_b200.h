@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BNPC_ABI_VERSION 3
+#define BNPC_ABI_VERSION 4
 
 /* capacity of clusters born since the ll matrix of the current epoch was built */
 #define BNPC_MAX_EXTRA 32
@@ -53,6 +53,7 @@ extern "C" {
 #define BNPC_ST_CYCLES   8   /* SM clock cycles of the last sweep launch, / 1024 */
 #define BNPC_ST_NANOS    9   /* globaltimer ns of the last sweep launch, / 1024  */
 #define BNPC_ST_NUNC     10  /* visits of the epoch that are not statically certain (bnpc_gibbs_compact) */
+#define BNPC_ST_NMANY    11  /* lean epochs: uncertain visits with more than BNPC_MAX_CAND rivals         */
 #define BNPC_ST_WORDS    16
 
 #define BNPC_STOP_EXTRA_FULL  1  /* BNPC_MAX_EXTRA births: start a new epoch      */
@@ -93,6 +94,19 @@ typedef struct {
     uint16_t col[BNPC_MAX_OPT];   /* its ll column in the current epoch                 */
     uint16_t pad[3];
 } bnpc_cand_t;
+
+/* Lean epochs (lists of at most BNPC_LEAN_MAXK clusters): options of a visit as selected from
+ * the APPROXIMATE log-likelihood row (16 bytes): a superset of the clusters that can come within
+ * 40 + log N nats of the cell's own cluster.                                                    */
+#define BNPC_LEAN_MAXK 64
+#define BNPC_OPT_MANY  2     /* more than BNPC_MAX_CAND rivals (or unknown own column)            */
+typedef struct {
+    uint8_t col[BNPC_MAX_OPT];  /* ll columns in list order                                       */
+    uint8_t n_opt;              /* own cluster + rivals; BNPC_MAX_OPT+1: too many                  */
+    uint8_t i_old;              /* index of the own cluster among them                             */
+    uint8_t flags;              /* BNPC_VISIT_CERTAIN | BNPC_OPT_MANY                              */
+    int32_t pad;
+} bnpc_opt_t;
 
 int         bnpc_abi_version(void);
 const char* bnpc_last_error(void);
@@ -152,6 +166,24 @@ int bnpc_gibbs_candidates(const double* ll, int ldk, int K, const int32_t* col_o
 int bnpc_gibbs_compact(const bnpc_visit_t* visit_t0, const bnpc_cand_t* cand_t0, int C,
                        int32_t* blk, bnpc_visit_t* visit_c, bnpc_cand_t* cand_c, int32_t* st,
                        void* stream);
+/* ---- lean epoch (see bnpc_opt_t): approximate rows -> options -> FP64 only for the options of
+ * the uncertain visits.  bnpc_ll_matrix_f32: float copy of lp (lpf [K][M][2] is written first)
+ * and FP32-FMA rows llf[r][k], r < C.  bnpc_gibbs_options: opt[r], certain-visit counts per
+ * column in n_cert[K] (zeroed inside); terms = number of summed terms of a row (2*M) for the
+ * error bound of the approximate rows.  bnpc_gibbs_exact: finalises the certain flags (a
+ * cluster never keeps a single certain visit), compacts the uncertain visits in visiting order
+ * (idx_c, st[BNPC_ST_NUNC]) and writes their visit / option records with FP64 log-likelihoods in
+ * the arithmetic of bnpc_ll_matrix.                                                            */
+int bnpc_ll_matrix_f32(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
+                       int cell_stride, int C, const double* lp, float* lpf, int K, float* llf,
+                       int ldf, void* stream);
+int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_id,
+                       const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, int32_t* n_cert, int C,
+                       double log_n, double c_norm, int terms, void* stream);
+int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const double* lp, int K,
+                     const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, const int32_t* n_cert, int C,
+                     int32_t* blk, int32_t* idx_c, int32_t* st, bnpc_visit_t* visit_c,
+                     bnpc_cand_t* cand_c, double log_n, double c_norm, void* stream);
 /* Start of an epoch: rebuild cnt[] from the host-authoritative list
  * live[2*j] = id, live[2*j+1] = size (list order), set col_of_id[id] = j and
  * clear the epoch's extra-cluster bookkeeping.  first != 0 also resets the
@@ -166,7 +198,8 @@ typedef struct {
     int32_t* assign; int32_t* cnt; int32_t* lst; int32_t* col_of_id; float* theta;
     int32_t idcap; int32_t* st; int32_t* live_out /* [2*idcap] (id,size) at exit */;
     /* epoch */
-    const double* ll; int32_t ldk; int32_t t_epoch0;
+    const double* ll /* NULL: lean epoch, exact rows are computed on demand from lp */; int32_t ldk;
+    int32_t t_epoch0; const double* lp /* [K][M][2] of the epoch (lean epochs) */;
     double* lpx /* [MAX_EXTRA][M][2] */; double* llx /* [MAX_EXTRA][ldx] */; int32_t ldx;
     double* scratch /* [idcap+1] */;
     /* sweep inputs */
@@ -287,6 +320,9 @@ typedef struct {
     int32_t* cblk /* [N/128+2] */; int32_t* perm /* [N] */; double* u /* [N] */;
     double* lp /* [K][M][2] */; double* ll /* [rows][ldk] */; double* lpx /* [MAX_EXTRA][M][2] */;
     double* llx /* [MAX_EXTRA][rows] */; double* scratch /* [idcap+1] */;
+    /* lean epochs */
+    float* lpf /* [K][M][2] */; float* llf /* [N][ldf] */; bnpc_opt_t* opt /* [N] */;
+    int32_t* n_cert /* [BNPC_LEAN_MAXK] */; int32_t* idx_c /* [N] */;
     /* sufficient statistics of the live clusters, list order */
     int32_t* ids; int32_t* seg; int32_t* cursor /* [K+1] each */; int32_t* members /* [N] */;
     int32_t* S1; int32_t* S0 /* [K][M] */; double* rnd /* [3][K][M] */; int32_t* declined /* [K+1] */;
@@ -310,6 +346,7 @@ typedef struct {
  * use stream_id + 2^24*(b+1) or the rows of beta_rows.                                       */
 typedef struct {
     int32_t first; int32_t K; int32_t t; int32_t rows; int32_t ldk; int32_t rand_ready;
+    int32_t lean /* 1: lean epoch (K <= BNPC_LEAN_MAXK), 0: dense FP64 matrix */; int32_t pad0;
     double c1; double c0; double lnew_prior; double c_norm; double log_n;
     double FN; double FP; double p; double q;
     uint64_t seed; uint64_t stream_id;

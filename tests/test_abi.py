@@ -30,7 +30,7 @@ def test_library_exports_header_symbols():
 def test_ctypes_signatures_match_header():
     declared = set(_declared()) - {'bnpc_abi_version', 'bnpc_last_error', 'bnpc_launch_count'}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.lib().abi_version() == 3
+    assert _lib.lib().abi_version() == _lib.ABI_VERSION
 
 
 def _struct_fields(name):

@@ -75,6 +75,18 @@ CASES = [
 ]
 
 
+@pytest.fixture
+def dense_rows(monkeypatch):
+    """force the dense FP64 cells x clusters matrix (the path of lists longer than 64 clusters)"""
+    from bnpc_b200.engine import DeviceCRP
+    monkeypatch.setattr(DeviceCRP, 'lean_enabled', False)
+
+
+@pytest.mark.parametrize('case', [CASES[0], CASES[5]], ids=[CASES[0][0], CASES[5][0]])
+def test_cuda_matches_oracle_dense_rows(case, dense_rows):
+    test_cuda_matches_oracle_on_seeded_data(case)
+
+
 @pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
 def test_cuda_matches_oracle_on_seeded_data(case):
     name, N, M, k, miss, learning, pp, init, steps, moves = case
