@@ -14,13 +14,13 @@ _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_HERE, 'libbnpc_b200.so')
 SOURCES = [os.path.join(_HERE, 'csrc', 'bnpc_kernels.cu')]
 HEADERS = [os.path.join(_HERE, 'csrc', 'bnpc_math.cuh'), os.path.join(_HERE, 'csrc', 'bnpc_chain.cuh'),
-           os.path.join(_HERE, 'csrc', 'bnpc_lean.cuh'),
+           os.path.join(_HERE, 'csrc', 'bnpc_lean.cuh'), os.path.join(_HERE, 'csrc', 'bnpc_tc.cuh'),
            os.path.join(_ROOT, 'include', 'bnpc_b200.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-fmad=false', '-std=c++17', '-shared', '-Xcompiler', '-fPIC']
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_EXTRA = 32
 ST_K, ST_TDONE, ST_FLAGS, ST_NEXTRA, ST_BIRTHS, ST_MOVED, ST_SLOW = range(7)
 ST_NUNC = 10
@@ -83,7 +83,7 @@ class ChainWs(C.Structure):
         [(n, C.c_void_p) for n in (
             'assign', 'theta', 'cnt', 'lst', 'col_of_id', 'rank_of_id', 'live_io', 'st',
             'visit', 'cand', 'visit_c', 'cand_c', 'cblk', 'perm', 'u',
-            'lp', 'll', 'lpx', 'llx', 'scratch', 'lpf', 'llf', 'opt', 'n_cert', 'idx_c',
+            'lp', 'll', 'lpx', 'llx', 'scratch', 'lpf', 'llf', 'opt', 'n_cert', 'idx_c', 'bsplit',
             'ids', 'seg', 'cursor', 'members', 'S1', 'S0', 'rnd', 'declined', 'rl_out', 'rl_tot',
             'cells', 'half', 'gblk', 'seg3', 'rg_work', 'rg_theta', 'rg_S1', 'rg_S0', 'rg_dec', 'rg_scal',
             'rg_lp', 'rg_ll2', 'rg_lq', 'rg_logq', 'rg_A', 'rg_orig', 'rg_perm', 'rg_u', 'rg_rnd', 'rg_sd',
@@ -119,6 +119,7 @@ SIGNATURES = {
     'bnpc_gibbs_candidates': [_P, _I, _I, _P, _P, _P, _I, _D, _D, _P, _P],
     'bnpc_gibbs_compact': [_P, _P, _I, _P, _P, _P, _P, _P],
     'bnpc_ll_matrix_f32': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P],
+    'bnpc_ll_matrix_tc': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P],
     'bnpc_gibbs_options': [_P, _I, _I, _P, _P, _P, _P, _I, _D, _D, _I, _P],
     'bnpc_gibbs_exact': [_P, _P, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _D, _D, _P],
     'bnpc_gibbs_epoch_begin': [_P, _I, _P, _P, _P, _I, _P, _I, _P],

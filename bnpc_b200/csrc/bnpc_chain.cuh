@@ -75,9 +75,14 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
     if (lean) {
         // approximate rows pick the options; FP64 only for the options of the uncertain visits
         if (K > BNPC_LEAN_MAXK) return bad_arg("lean epoch with K > BNPC_LEAN_MAXK");
-        const int ldf = (K + 7) & ~7;
+        const int ldf = (K + 15) & ~15;
         TRY(record_event(e->ev_ll0, stream));
-        TRY(bnpc_ll_matrix_f32(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp, w->lpf, K, w->llf, ldf, stream));
+        if (e->lean == 2)
+            TRY(bnpc_ll_matrix_tc(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp, w->bsplit, K, w->llf, ldf,
+                                  stream));
+        else
+            TRY(bnpc_ll_matrix_f32(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp, w->lpf, K, w->llf, ldf,
+                                   stream));
         TRY(record_event(e->ev_ll1, stream));
         TRY(bnpc_gibbs_options(w->llf, ldf, K, w->col_of_id, w->visit + t, w->opt + t, w->n_cert, rows, e->log_n,
                                e->c_norm, 2 * M, stream));

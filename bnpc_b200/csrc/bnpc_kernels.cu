@@ -437,8 +437,6 @@ compact_scatter_kernel(const bnpc_visit_t* __restrict__ visit, const bnpc_cand_t
     for (int i = 0; i < (int)(sizeof(bnpc_cand_t) / 16); ++i) dc[i] = sc[i];
 }
 
-#include "bnpc_lean.cuh"
-
 __global__ void gibbs_epoch_begin_kernel(const int32_t* __restrict__ live, int K, int32_t* lst,
                                          int32_t* cnt, int32_t* col_of_id, int idcap, int32_t* st,
                                          int first) {
@@ -490,6 +488,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+
+#include "bnpc_lean.cuh"
+#include "bnpc_tc.cuh"
 
 #define SW_STAGE_CELLS 32
 #define SW_NSTAGE 16
@@ -1746,6 +1747,26 @@ int bnpc_ll_matrix_f32(const uint32_t* x1, const uint32_t* x0, int W, int M, con
         x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const float2*>(lpf), K, llf, ldf);
     LAUNCH_CHECK("ll_matrix_f32");
     return 0;
+}
+
+int bnpc_ll_matrix_tc(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
+                      int cell_stride, int C, const double* lp, uint16_t* bsplit, int K, float* llf, int ldf,
+                      void* stream) {
+    if (C <= 0 || K <= 0) return 0;
+    if (K > BNPC_LEAN_MAXK) return bad_arg("tensor-core rows need K <= BNPC_LEAN_MAXK");
+    if (W % 4 != 0) return bad_arg("W must be a multiple of 4");
+    const int kpad = (K + 15) & ~15;
+    if (ldf < kpad || ldf % 4 != 0) return bad_arg("ldf must be a multiple of 4, >= K rounded up to 16");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long total = (long long)W * 2 * kpad * 64;
+    lp_split_bf16_kernel<<<cdiv(total, 256), 256, 0, s>>>(reinterpret_cast<const double2*>(lp), K, M, W, kpad, bsplit);
+    LAUNCH_CHECK("lp_split_bf16");
+    switch (kpad) {
+        case 16: return launch_ll_tc<16>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
+        case 32: return launch_ll_tc<32>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
+        case 48: return launch_ll_tc<48>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
+        default: return launch_ll_tc<64>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
+    }
 }
 
 int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_id,

@@ -1,0 +1,259 @@
+// Approximate cells x clusters log-likelihood rows on the 5th-generation tensor cores
+// (tcgen05.mma, sm_100a), used by lean Gibbs epochs to select each visit's options.
+//
+//   llf[r][k] = sum_m x1[c][m] * LP1[k][m] + x0[c][m] * LP0[k][m],   c = cell of visit r
+//
+// as one GEMM  D[128 visits x N] += A[128 x 64] * B[N x 64]^T  per 64-bit slice of a bit-plane:
+//   A  the 0/1 data of the slice, expanded by the producer warps from the bit-planes straight
+//      into TENSOR MEMORY (tcgen05.st; one TMEM lane per visit, two bf16 per 32-bit column).
+//      A set bit becomes bf16 2.0 = 0x4000 -- a single bit, so a rotate and an AND expand two
+//      matrix elements -- and B carries the factor 0.5 (exact).
+//   B  the (log p1 | log p0) table split into S = 2 bf16 terms (hi, lo: 16 significant bits) as
+//      separate output columns n = s*KPAD + k, prepared once per epoch in the K-major
+//      128-byte-swizzled UMMA layout so that a stage is one bulk async copy (cp.async.bulk).
+//   D  FP32 accumulators in TMEM; the epilogue adds the S column groups and writes floats.
+// Warp roles: warps 0-3 produce A and run the epilogue (TMEM lane quarter = warp), warp 4 issues
+// the MMAs (one thread), warp 5 streams B.  4-stage pipeline on mbarriers; tcgen05.commit frees
+// a stage.  The order of the 64 reduction indices inside a stage is a fixed permutation of the
+// bit order (element 2p+h <-> bit p+16h), the same for A and B.
+#include <cuda_bf16.h>
+
+#define TC_NST 4
+#define TC_THREADS 192
+#define TC_A_COL0 128            /* first TMEM column of the A stages (D uses [0, N), N <= 128) */
+#define TC_TMEM_COLS 256
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    long long spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1ll << 26)) asm volatile("trap;");      // a protocol bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem_d] (+)= A[tmem_a] * B[smem desc]: kind::f16 (bf16 x bf16 -> f32), A from tensor memory
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// B table: chunk kc (64 reduction indices of one plane) x N rows x 64 bf16, each chunk stored
+// exactly as its shared-memory stage (K-major, 128-byte swizzle: 8-row groups of 1024 bytes, the
+// 16-byte piece c of row n at piece position c ^ (n & 7)).
+__global__ void lp_split_bf16_kernel(const double2* __restrict__ lp, int K, int M, int W, int KPAD,
+                                     uint16_t* __restrict__ Bg) {
+    const int N = 2 * KPAD;
+    const long long total = (long long)W * N * 64;          // W chunks: W/2 per plane
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int e = (int)(idx & 63);
+    const int n = (int)((idx >> 6) % N);
+    const int kc = (int)(idx / (64ll * N));
+    const int s = n / KPAD, k = n % KPAD;
+    const int plane = kc >= W / 2;
+    const int j = plane ? kc - W / 2 : kc;
+    const int word = e >> 5, q = e & 31, p = q >> 1, h = q & 1;
+    const int m = (2 * j + word) * 32 + p + 16 * h;
+    double v = 0.0;
+    if (k < K && m < M) {
+        const double2 t = lp[(long long)k * M + m];
+        v = 0.5 * (plane ? t.y : t.x);
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn((float)v);
+    const double rest = v - (double)__bfloat162float(hi);
+    const __nv_bfloat16 lo = __float2bfloat16_rn((float)rest);
+    const __nv_bfloat16 out = s == 0 ? hi : lo;
+    const long long off = (long long)kc * N * 64 + (n >> 3) * 512 + (n & 7) * 64 + (((e >> 3) ^ (n & 7)) << 3) + (e & 7);
+    Bg[off] = __bfloat16_as_ushort(out);
+}
+
+template <int KPAD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W,
+                    const int32_t* __restrict__ cells, int cell_stride, int C,
+                    const uint16_t* __restrict__ Bg, float* __restrict__ llf, int ldf) {
+    constexpr int N = 2 * KPAD;
+    constexpr uint32_t B_STAGE_BYTES = (uint32_t)N * 128u;
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(tc_smem + TC_NST * B_STAGE_BYTES);
+    uint64_t* empty = full + TC_NST;
+    uint64_t* acc_full = empty + TC_NST;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stages_per_plane = W / 2;                    // 64 bits of a row per stage
+    const int n_stages = 2 * stages_per_plane;
+    const int n_tiles = (C + 127) / 128;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_NST; ++s) { mbar_init(&full[s], 5); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        // ---- A producers (one TMEM lane = one visit each), then the epilogue of the tile ----
+        const int row = threadIdx.x;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        uint32_t it = 0, tile_count = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_count) {
+            const int r = tile * 128 + row;
+            const bool live = r < C;
+            const long long cell = cells ? cells[(long long)(live ? r : 0) * cell_stride] : (live ? r : 0);
+            const uint32_t* p1 = x1 + cell * W;
+            const uint32_t* p0 = x0 + cell * W;
+            for (int sidx = 0; sidx < n_stages; ++sidx, ++it) {
+                const int slot = it % TC_NST;
+                const uint32_t* src = (sidx < stages_per_plane) ? p1 + 2 * sidx : p0 + 2 * (sidx - stages_per_plane);
+                uint2 wv = *reinterpret_cast<const uint2*>(src);
+                if (!live) wv = make_uint2(0u, 0u);
+                uint32_t regs[32];
+#pragma unroll
+                for (int p = 0; p < 16; ++p) {
+                    regs[p] = __funnelshift_l(wv.x, wv.x, (14 - p) & 31) & 0x40004000u;
+                    regs[16 + p] = __funnelshift_l(wv.y, wv.y, (14 - p) & 31) & 0x40004000u;
+                }
+                if (it >= TC_NST) mbar_wait(&empty[slot], ((it / TC_NST) - 1) & 1);
+                tc_fence_after();
+                tc_st32(tmem + TC_A_COL0 + slot * 32 + lane_base, regs);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[slot]);
+            }
+            // epilogue: D lane `row`, columns [0, N): add the split groups, write the row
+            mbar_wait(acc_full, tile_count & 1);
+            tc_fence_after();
+            float acc[KPAD];
+#pragma unroll
+            for (int c = 0; c < KPAD / 16; ++c) {
+                uint32_t v0[16], v1[16];
+                tc_ld16(tmem + lane_base + c * 16, v0);
+                tc_ld16(tmem + lane_base + KPAD + c * 16, v1);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[c * 16 + i] = __uint_as_float(v0[i]) + __uint_as_float(v1[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+            if (live) {
+                float4* dst = reinterpret_cast<float4*>(llf + (long long)r * ldf);
+#pragma unroll
+                for (int i = 0; i < KPAD / 4; ++i)
+                    dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+            }
+        }
+    } else if (warp == 4) {
+        // ---- MMA issuer ----
+        if (lane == 0) {
+            // instruction descriptor: D f32, A/B bf16, both K-major, N, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+            uint32_t it = 0, tile_count = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_count) {
+                if (tile_count > 0) mbar_wait(acc_empty, (tile_count - 1) & 1);
+                tc_fence_after();
+                for (int sidx = 0; sidx < n_stages; ++sidx, ++it) {
+                    const int slot = it % TC_NST;
+                    mbar_wait(&full[slot], (it / TC_NST) & 1);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(tc_smem + slot * B_STAGE_BYTES);
+                    // K-major, 128B swizzle: LBO 1, SBO 1024 B, version 1, layout type 2
+                    const uint64_t desc0 = (uint64_t)((b_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) |
+                                           (1ull << 46) | (2ull << 61);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        tc_mma_ts(tmem, tmem + TC_A_COL0 + slot * 32 + j * 8, desc0 + (uint64_t)(2 * j), idesc,
+                                  (sidx | j) != 0 ? 1u : 0u);
+                    tc_commit(&empty[slot]);
+                }
+                tc_commit(acc_full);
+            }
+        }
+    } else {
+        // ---- B loader ----
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int sidx = 0; sidx < n_stages; ++sidx, ++it) {
+                    const int slot = it % TC_NST;
+                    if (it >= TC_NST) mbar_wait(&empty[slot], ((it / TC_NST) - 1) & 1);
+                    mbar_expect_tx(&full[slot], B_STAGE_BYTES);
+                    bulk_g2s(tc_smem + slot * B_STAGE_BYTES, Bg + (long long)sidx * N * 64, B_STAGE_BYTES, &full[slot]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+template <int KPAD>
+static int launch_ll_tc(const uint32_t* x1, const uint32_t* x0, int W, const int32_t* cells, int cell_stride,
+                        int C, const uint16_t* Bg, float* llf, int ldf, cudaStream_t s) {
+    const size_t smem = (size_t)TC_NST * (2 * KPAD) * 128 + 128;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(ll_matrix_tc_kernel<KPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return fail("ll_matrix_tc smem attribute", e);
+        attr_done = true;
+    }
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int tiles = cdiv(C, 128);
+    ll_matrix_tc_kernel<KPAD><<<tiles < sms ? tiles : sms, TC_THREADS, smem, s>>>(x1, x0, W, cells, cell_stride, C,
+                                                                                 Bg, llf, ldf);
+    LAUNCH_CHECK("ll_matrix_tc");
+    return 0;
+}
+

@@ -113,6 +113,7 @@ class DeviceCRP:
 
     learning = False
     lean_enabled = True           # class-wide switch (tests force the dense FP64 matrix with False)
+    lean_rows = 2                 # approximate rows of lean epochs: 2 tcgen05 tensor cores, 1 FP32 FMA
 
     def __init__(self, data, DP_alpha=(-1, -1), param_beta=(1, 1), FN_error=EPS, FP_error=EPS,
                  device=None, rnd=None):
@@ -258,6 +259,7 @@ class DeviceCRP:
             self._dev('opt', N * _lib.OPT_BYTES, u8)
             self._dev('n_cert', _lib.LEAN_MAXK, i32, zero=True)
             self._dev('idx_c', N, i32)
+            self._dev('bsplit', sh.W * 2 * _lib.LEAN_MAXK * 64, torch.int16)
             self._lean_ok = True
             self.members = self._dev('members', N, i32)
             self._dev('rl_tot', 8, f64)
@@ -505,7 +507,7 @@ class DeviceCRP:
                 # needs it; dense FP64 matrix for longer lists (or when many cells have > 8 rivals)
                 lean = K <= _lib.LEAN_MAXK and self._lean_ok and self.lean_enabled
                 rows = N - t if lean else int(min(N - t, max(1, LL_BUDGET_BYTES // (8 * ldk))))
-                ep.lean = 1 if lean else 0
+                ep.lean = self.lean_rows if lean else 0
                 if not lean and rows * ldk + 2 > self._ll_cap:
                     self._ll_cap = rows * ldk + 2
                     self._dev('ll', self._ll_cap, torch.float64)

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BNPC_ABI_VERSION 4
+#define BNPC_ABI_VERSION 5
 
 /* capacity of clusters born since the ll matrix of the current epoch was built */
 #define BNPC_MAX_EXTRA 32
@@ -177,6 +177,12 @@ int bnpc_gibbs_compact(const bnpc_visit_t* visit_t0, const bnpc_cand_t* cand_t0,
 int bnpc_ll_matrix_f32(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
                        int cell_stride, int C, const double* lp, float* lpf, int K, float* llf,
                        int ldf, void* stream);
+/* The same rows on the tcgen05 tensor cores: lp split into two bf16 terms (bsplit: scratch of
+ * W * 2*Kp * 64 bf16, Kp = K rounded up to 16), 0/1 data expanded from the bit-planes into
+ * tensor memory, FP32 accumulation; llf[r][0..Kp) is written, ldf >= Kp, ldf % 4 == 0.        */
+int bnpc_ll_matrix_tc(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
+                      int cell_stride, int C, const double* lp, uint16_t* bsplit, int K, float* llf,
+                      int ldf, void* stream);
 int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_id,
                        const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, int32_t* n_cert, int C,
                        double log_n, double c_norm, int terms, void* stream);
@@ -323,6 +329,7 @@ typedef struct {
     /* lean epochs */
     float* lpf /* [K][M][2] */; float* llf /* [N][ldf] */; bnpc_opt_t* opt /* [N] */;
     int32_t* n_cert /* [BNPC_LEAN_MAXK] */; int32_t* idx_c /* [N] */;
+    uint16_t* bsplit /* [W][2*BNPC_LEAN_MAXK][64] bf16 */;
     /* sufficient statistics of the live clusters, list order */
     int32_t* ids; int32_t* seg; int32_t* cursor /* [K+1] each */; int32_t* members /* [N] */;
     int32_t* S1; int32_t* S0 /* [K][M] */; double* rnd /* [3][K][M] */; int32_t* declined /* [K+1] */;
@@ -346,7 +353,8 @@ typedef struct {
  * use stream_id + 2^24*(b+1) or the rows of beta_rows.                                       */
 typedef struct {
     int32_t first; int32_t K; int32_t t; int32_t rows; int32_t ldk; int32_t rand_ready;
-    int32_t lean /* 1: lean epoch (K <= BNPC_LEAN_MAXK), 0: dense FP64 matrix */; int32_t pad0;
+    int32_t lean /* 0: dense FP64 matrix; lean epoch (K <= BNPC_LEAN_MAXK) with approximate rows
+                    from 1: FP32 FMA, 2: tcgen05 tensor cores */; int32_t pad0;
     double c1; double c0; double lnew_prior; double c_norm; double log_n;
     double FN; double FP; double p; double q;
     uint64_t seed; uint64_t stream_id;
