@@ -75,7 +75,7 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
     if (lean) {
         // approximate rows pick the options; FP64 only for the options of the uncertain visits
         if (K > BNPC_LEAN_MAXK) return bad_arg("lean epoch with K > BNPC_LEAN_MAXK");
-        const int ldf = (K + 15) & ~15;
+        const int ldf = (K + 7) & ~7;
         TRY(record_event(e->ev_ll0, stream));
         if (e->lean == 2)
             TRY(bnpc_ll_matrix_tc(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp, w->bsplit, K, w->llf, ldf,

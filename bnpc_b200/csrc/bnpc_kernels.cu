@@ -21,6 +21,7 @@
 #include <atomic>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/bnpc_b200.h"
@@ -1755,16 +1756,20 @@ int bnpc_ll_matrix_tc(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
     if (C <= 0 || K <= 0) return 0;
     if (K > BNPC_LEAN_MAXK) return bad_arg("tensor-core rows need K <= BNPC_LEAN_MAXK");
     if (W % 4 != 0) return bad_arg("W must be a multiple of 4");
-    const int kpad = (K + 15) & ~15;
-    if (ldf < kpad || ldf % 4 != 0) return bad_arg("ldf must be a multiple of 4, >= K rounded up to 16");
+    const int kpad = (K + 7) & ~7;
+    if (ldf < kpad || ldf % 4 != 0) return bad_arg("ldf must be a multiple of 4, >= K rounded up to 8");
     cudaStream_t s = (cudaStream_t)stream;
     const long long total = (long long)W * 2 * kpad * 64;
     lp_split_bf16_kernel<<<cdiv(total, 256), 256, 0, s>>>(reinterpret_cast<const double2*>(lp), K, M, W, kpad, bsplit);
     LAUNCH_CHECK("lp_split_bf16");
     switch (kpad) {
+        case 8: return launch_ll_tc<8>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
         case 16: return launch_ll_tc<16>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
+        case 24: return launch_ll_tc<24>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
         case 32: return launch_ll_tc<32>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
+        case 40: return launch_ll_tc<40>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
         case 48: return launch_ll_tc<48>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
+        case 56: return launch_ll_tc<56>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
         default: return launch_ll_tc<64>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
     }
 }

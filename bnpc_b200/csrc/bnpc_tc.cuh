@@ -12,16 +12,21 @@
 //      separate output columns n = s*KPAD + k, prepared once per epoch in the K-major
 //      128-byte-swizzled UMMA layout so that a stage is one bulk async copy (cp.async.bulk).
 //   D  FP32 accumulators in TMEM; the epilogue adds the S column groups and writes floats.
-// Warp roles: warps 0-3 produce A and run the epilogue (TMEM lane quarter = warp), warp 4 issues
-// the MMAs (one thread), warp 5 streams B.  4-stage pipeline on mbarriers; tcgen05.commit frees
-// a stage.  The order of the 64 reduction indices inside a stage is a fixed permutation of the
+// Warp roles: warps 0-7 produce A (TMEM lane quarter = warp % 4; warps 0-3 expand the first half
+// of every stage and run the epilogue, warps 4-7 the second half), warp 8 issues the MMAs (one
+// thread), warp 9 streams B.  A stage is 256 reduction indices (16 MMAs) so that the barrier round
+// trip of a stage is amortised; 2-stage pipeline on mbarriers; tcgen05.commit frees a stage.
+// Measured (B200, 100k x 1k x 24): 56 us; ~90 cycles per MMA whatever N is -- with N = 2*Kp <= 128
+// output columns the instruction is bound by reading its 4 KB A operand from tensor memory, not
+// by the tensor pipe (62 cycles per MMA at N = 128).  Next lever: 8-bit A (kind::f8f6f4).  The order of the 64 reduction indices inside a stage is a fixed permutation of the
 // bit order (element 2p+h <-> bit p+16h), the same for A and B.
 #include <cuda_bf16.h>
 
-#define TC_NST 4
-#define TC_THREADS 192
-#define TC_A_COL0 128            /* first TMEM column of the A stages (D uses [0, N), N <= 128) */
-#define TC_TMEM_COLS 256
+#define TC_NST 2
+#define TC_CPS 4              /* 64-bit chunks of the row per pipeline stage */
+#define TC_THREADS 320
+#define TC_A_COL0 256            /* first TMEM column of the A stages (accumulators use [0, 256)) */
+#define TC_TMEM_COLS 512
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -70,6 +75,13 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
         : "memory");
 }
 
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
 // B table: chunk kc (64 reduction indices of one plane) x N rows x 64 bf16, each chunk stored
 // exactly as its shared-memory stage (K-major, 128-byte swizzle: 8-row groups of 1024 bytes, the
 // 16-byte piece c of row n at piece position c ^ (n & 7)).
@@ -106,7 +118,11 @@ ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                     const int32_t* __restrict__ cells, int cell_stride, int C,
                     const uint16_t* __restrict__ Bg, float* __restrict__ llf, int ldf) {
     constexpr int N = 2 * KPAD;
-    constexpr uint32_t B_STAGE_BYTES = (uint32_t)N * 128u;
+    // consecutive MMAs go to NACC independent accumulator tiles, summed in the epilogue (no
+    // read-after-write chain on one TMEM tile between back-to-back instructions)
+    constexpr int NACC = (N <= 64) ? 4 : 2;
+    constexpr uint32_t B_CHUNK_BYTES = (uint32_t)N * 128u;          // 64 reduction indices
+    constexpr uint32_t B_STAGE_BYTES = TC_CPS * B_CHUNK_BYTES;
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(tc_smem + TC_NST * B_STAGE_BYTES);
     uint64_t* empty = full + TC_NST;
@@ -114,18 +130,19 @@ ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
     uint64_t* acc_empty = acc_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int stages_per_plane = W / 2;                    // 64 bits of a row per stage
-    const int n_stages = 2 * stages_per_plane;
+    // the row of a visit is 2 planes x W words = W chunks of 64 bits; a stage is TC_CPS chunks
+    const int half = W / 2;                                 // chunks per plane
+    const int n_stages = (W + TC_CPS - 1) / TC_CPS;
     const int n_tiles = (C + 127) / 128;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_NST; ++s) { mbar_init(&full[s], 5); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < TC_NST; ++s) { mbar_init(&full[s], 9); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"((uint32_t)TC_TMEM_COLS)
                      : "memory");
@@ -136,10 +153,12 @@ ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 4) {
-        // ---- A producers (one TMEM lane = one visit each), then the epilogue of the tile ----
-        const int row = threadIdx.x;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    if (warp < 8) {
+        // ---- A producers: one TMEM lane = one visit; group g = warp / 4 expands chunks
+        // [2g, 2g+2) of every stage; group 0 also runs the epilogue of the tile ----
+        const int g = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         uint32_t it = 0, tile_count = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_count) {
             const int r = tile * 128 + row;
@@ -147,37 +166,55 @@ ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
             const long long cell = cells ? cells[(long long)(live ? r : 0) * cell_stride] : (live ? r : 0);
             const uint32_t* p1 = x1 + cell * W;
             const uint32_t* p0 = x0 + cell * W;
+            // words of chunk c (64 bits of plane 1, then of plane 0); zero beyond the row
+            auto fetch = [&](int c) -> uint2 {
+                if (!live || c >= W) return make_uint2(0u, 0u);
+                const uint32_t* src = (c < half) ? p1 + 2 * c : p0 + 2 * (c - half);
+                return __ldg(reinterpret_cast<const uint2*>(src));
+            };
+            // this group's chunks of the next stage are in flight while the current ones are expanded
+            uint2 nxt0 = fetch(2 * g), nxt1 = fetch(2 * g + 1);
             for (int sidx = 0; sidx < n_stages; ++sidx, ++it) {
+                const uint2 w0 = nxt0, w1 = nxt1;
+                nxt0 = fetch((sidx + 1) * TC_CPS + 2 * g);
+                nxt1 = fetch((sidx + 1) * TC_CPS + 2 * g + 1);
                 const int slot = it % TC_NST;
-                const uint32_t* src = (sidx < stages_per_plane) ? p1 + 2 * sidx : p0 + 2 * (sidx - stages_per_plane);
-                uint2 wv = *reinterpret_cast<const uint2*>(src);
-                if (!live) wv = make_uint2(0u, 0u);
-                uint32_t regs[32];
+                uint32_t regs[64];
 #pragma unroll
                 for (int p = 0; p < 16; ++p) {
-                    regs[p] = __funnelshift_l(wv.x, wv.x, (14 - p) & 31) & 0x40004000u;
-                    regs[16 + p] = __funnelshift_l(wv.y, wv.y, (14 - p) & 31) & 0x40004000u;
+                    regs[p] = __funnelshift_l(w0.x, w0.x, (14 - p) & 31) & 0x40004000u;
+                    regs[16 + p] = __funnelshift_l(w0.y, w0.y, (14 - p) & 31) & 0x40004000u;
+                    regs[32 + p] = __funnelshift_l(w1.x, w1.x, (14 - p) & 31) & 0x40004000u;
+                    regs[48 + p] = __funnelshift_l(w1.y, w1.y, (14 - p) & 31) & 0x40004000u;
                 }
                 if (it >= TC_NST) mbar_wait(&empty[slot], ((it / TC_NST) - 1) & 1);
                 tc_fence_after();
-                tc_st32(tmem + TC_A_COL0 + slot * 32 + lane_base, regs);
+                const uint32_t dst = tmem + TC_A_COL0 + slot * (TC_CPS * 32) + g * 64 + lane_base;
+                tc_st32(dst, regs);
+                tc_st32(dst + 32, regs + 32);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[slot]);
             }
+            if (g != 0) continue;
             // epilogue: D lane `row`, columns [0, N): add the split groups, write the row
             mbar_wait(acc_full, tile_count & 1);
             tc_fence_after();
             float acc[KPAD];
 #pragma unroll
-            for (int c = 0; c < KPAD / 16; ++c) {
-                uint32_t v0[16], v1[16];
-                tc_ld16(tmem + lane_base + c * 16, v0);
-                tc_ld16(tmem + lane_base + KPAD + c * 16, v1);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int c = 0; c < KPAD / 8; ++c) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) acc[c * 16 + i] = __uint_as_float(v0[i]) + __uint_as_float(v1[i]);
+                for (int i = 0; i < 8; ++i) acc[c * 8 + i] = 0.0f;
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) {
+                    uint32_t v0[8], v1[8];
+                    tc_ld8(tmem + lane_base + a * N + c * 8, v0);
+                    tc_ld8(tmem + lane_base + a * N + KPAD + c * 8, v1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[c * 8 + i] += __uint_as_float(v0[i]) + __uint_as_float(v1[i]);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -189,7 +226,7 @@ ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                     dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ---- MMA issuer ----
         if (lane == 0) {
             // instruction descriptor: D f32, A/B bf16, both K-major, N, M = 128
@@ -203,13 +240,17 @@ ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                     mbar_wait(&full[slot], (it / TC_NST) & 1);
                     tc_fence_after();
                     const uint32_t b_addr = smem_u32(tc_smem + slot * B_STAGE_BYTES);
-                    // K-major, 128B swizzle: LBO 1, SBO 1024 B, version 1, layout type 2
-                    const uint64_t desc0 = (uint64_t)((b_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) |
-                                           (1ull << 46) | (2ull << 61);
+                    const uint32_t a_addr = tmem + TC_A_COL0 + slot * (TC_CPS * 32);
+                    const int chunks = min(TC_CPS, W - sidx * TC_CPS);
+                    for (int cc = 0; cc < chunks; ++cc) {
+                        // K-major, 128B swizzle: LBO 1, SBO 1024 B, version 1, layout type 2
+                        const uint64_t desc0 = (uint64_t)(((b_addr + cc * B_CHUNK_BYTES) >> 4) & 0x3FFFu) |
+                                               (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        tc_mma_ts(tmem, tmem + TC_A_COL0 + slot * 32 + j * 8, desc0 + (uint64_t)(2 * j), idesc,
-                                  (sidx | j) != 0 ? 1u : 0u);
+                        for (int j = 0; j < 4; ++j)
+                            tc_mma_ts(tmem + (j % NACC) * N, a_addr + cc * 32 + j * 8, desc0 + (uint64_t)(2 * j), idesc,
+                                      ((sidx | cc) != 0 || j >= NACC) ? 1u : 0u);
+                    }
                     tc_commit(&empty[slot]);
                 }
                 tc_commit(acc_full);
@@ -223,15 +264,17 @@ ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                 for (int sidx = 0; sidx < n_stages; ++sidx, ++it) {
                     const int slot = it % TC_NST;
                     if (it >= TC_NST) mbar_wait(&empty[slot], ((it / TC_NST) - 1) & 1);
-                    mbar_expect_tx(&full[slot], B_STAGE_BYTES);
-                    bulk_g2s(tc_smem + slot * B_STAGE_BYTES, Bg + (long long)sidx * N * 64, B_STAGE_BYTES, &full[slot]);
+                    const uint32_t bytes = (uint32_t)min(TC_CPS, W - sidx * TC_CPS) * B_CHUNK_BYTES;
+                    mbar_expect_tx(&full[slot], bytes);
+                    bulk_g2s(tc_smem + slot * B_STAGE_BYTES, Bg + (long long)sidx * TC_CPS * N * 64, bytes,
+                             &full[slot]);
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_TMEM_COLS)
                      : "memory");
     }
@@ -240,7 +283,7 @@ ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
 template <int KPAD>
 static int launch_ll_tc(const uint32_t* x1, const uint32_t* x0, int W, const int32_t* cells, int cell_stride,
                         int C, const uint16_t* Bg, float* llf, int ldf, cudaStream_t s) {
-    const size_t smem = (size_t)TC_NST * (2 * KPAD) * 128 + 128;
+    const size_t smem = (size_t)TC_NST * TC_CPS * (2 * KPAD) * 128 + 256;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(ll_matrix_tc_kernel<KPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,

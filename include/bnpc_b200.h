@@ -178,7 +178,7 @@ int bnpc_ll_matrix_f32(const uint32_t* x1, const uint32_t* x0, int W, int M, con
                        int cell_stride, int C, const double* lp, float* lpf, int K, float* llf,
                        int ldf, void* stream);
 /* The same rows on the tcgen05 tensor cores: lp split into two bf16 terms (bsplit: scratch of
- * W * 2*Kp * 64 bf16, Kp = K rounded up to 16), 0/1 data expanded from the bit-planes into
+ * W * 2*Kp * 64 bf16, Kp = K rounded up to 8), 0/1 data expanded from the bit-planes into
  * tensor memory, FP32 accumulation; llf[r][0..Kp) is written, ldf >= Kp, ldf % 4 == 0.        */
 int bnpc_ll_matrix_tc(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
                       int cell_stride, int C, const double* lp, uint16_t* bsplit, int K, float* llf,

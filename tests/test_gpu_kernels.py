@@ -230,3 +230,41 @@ def test_gather_members_and_anchor_swaps(L):
         w[-1], w[j] = w[j], w[-1]
         L.anchor_swaps(out.data_ptr(), c3.size, c3.size, i, j, 0, sp())
         np.testing.assert_array_equal(out.cpu().numpy()[:c3.size], w)
+
+
+@pytest.mark.parametrize('shape', [(300, 128, 5), (5000, 1000, 24), (4096, 640, 64), (777, 50, 40)])
+@pytest.mark.parametrize('rows', ['tcgen05', 'fp32_fma'])
+def test_approximate_rows_within_their_error_bound(L, shape, rows):
+    """The approximate log-likelihood rows of lean epochs (tcgen05 tensor cores, bf16-split
+    operands, FP32 accumulation; FP32-FMA reference kernel) against the FP64 matrix.  The bound
+    the option selection relies on is terms * 2^-22 * (|ll| + 64) + 0.05 (bnpc_gibbs_options);
+    measured errors are ~1e-6 relative."""
+    N, M, K = shape
+    rng = np.random.default_rng(N + M + K)
+    data = rng.integers(0, 2, (N, M)).astype(np.float64)
+    data[rng.random((N, M)) < 0.1] = np.nan
+    W, x1, x0, n1, n0 = pack(L, data)
+    theta = dev(np.clip(rng.random((K, M)), 1e-5, 1 - 1e-5).astype(np.float32), torch.float32)
+    lp = torch.zeros(2 * K * M, dtype=torch.float64, device='cuda')
+    L.logprob_tables(theta.data_ptr(), None, K, M, 0.2, 0.01, lp.data_ptr(), sp())
+    cells = dev(rng.permutation(N).astype(np.int32), torch.int32)
+    ldk = K | 1
+    ll = torch.zeros(N * ldk, dtype=torch.float64, device='cuda')
+    L.ll_matrix(x1.data_ptr(), x0.data_ptr(), W, M, cells.data_ptr(), 1, N, lp.data_ptr(), K, ll.data_ptr(), ldk, sp())
+    kp = (K + 7) & ~7
+    llf = torch.full((N, kp), float('nan'), dtype=torch.float32, device='cuda')
+    if rows == 'tcgen05':
+        scratch = torch.zeros(W * 2 * kp * 64, dtype=torch.int16, device='cuda')
+        L.ll_matrix_tc(x1.data_ptr(), x0.data_ptr(), W, M, cells.data_ptr(), 1, N, lp.data_ptr(),
+                       scratch.data_ptr(), K, llf.data_ptr(), kp, sp())
+    else:
+        scratch = torch.zeros(2 * K * M, dtype=torch.float32, device='cuda')
+        L.ll_matrix_f32(x1.data_ptr(), x0.data_ptr(), W, M, cells.data_ptr(), 1, N, lp.data_ptr(),
+                        scratch.data_ptr(), K, llf.data_ptr(), kp, sp())
+    torch.cuda.synchronize()
+    want = ll.cpu().numpy().reshape(N, ldk)[:, :K]
+    got = llf.cpu().numpy()[:, :K].astype(np.float64)
+    assert not np.isnan(got).any()
+    bound = 2 * M * 2.0 ** -22 * (np.abs(want) + 64) + 0.05
+    assert (np.abs(got - want) <= bound).all()
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max() + 1e-3

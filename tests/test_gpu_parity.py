@@ -87,6 +87,17 @@ def test_cuda_matches_oracle_dense_rows(case, dense_rows):
     test_cuda_matches_oracle_on_seeded_data(case)
 
 
+@pytest.fixture
+def fma_rows(monkeypatch):
+    """lean epochs with the FP32-FMA rows instead of the tcgen05 kernel"""
+    from bnpc_b200.engine import DeviceCRP
+    monkeypatch.setattr(DeviceCRP, 'lean_rows', 1)
+
+
+def test_cuda_matches_oracle_fma_rows(fma_rows):
+    test_cuda_matches_oracle_on_seeded_data(CASES[0])
+
+
 @pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
 def test_cuda_matches_oracle_on_seeded_data(case):
     name, N, M, k, miss, learning, pp, init, steps, moves = case

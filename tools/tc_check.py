@@ -26,7 +26,7 @@ for (N, M, K) in [(300, 128, 5), (1000, 200, 16), (5000, 1000, 24), (100000, 100
     ldk = K | 1
     ll = torch.zeros(N * ldk, dtype=torch.float64, device=dev)
     L.ll_matrix(x1.data_ptr(), x0.data_ptr(), W, M, cells.data_ptr(), 1, N, lp.data_ptr(), K, ll.data_ptr(), ldk, sp())
-    kp = (K + 15) & ~15
+    kp = (K + 7) & ~7
     llf = torch.full((N, kp), float('nan'), dtype=torch.float32, device=dev)
     bs = torch.zeros(W * 2 * kp * 64, dtype=torch.int16, device=dev)
     torch.cuda.synchronize()
