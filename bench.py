@@ -184,11 +184,25 @@ class ClockSampler:
 
 
 def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s sustained, source): the driver-written measurements of this
+    pool's B200s, else the fallback of B200_PROFILING.md."""
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
-            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+            d = json.load(f)
+        return float(d['hbm_gbs']), float(d.get('bf16_tflops_sustained', d['bf16_tflops'])), \
+            'measured (MEASURED_PEAKS.json; bf16 = sustained figure, the kernel runs inside a long step)'
     except Exception:
-        return 6650.0, 'fallback (B200_PROFILING.md)'
+        return 6650.0, 1400.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the profiled kernels (ncu --set full captures summarised under
+    profiles/): {kernel: bytes} or {}."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def run_gpu(args, cfg):
@@ -309,7 +323,7 @@ def run_gpu(args, cfg):
     for ch in chains:
         ch.results = {}
         ch.init_results(2 * K + 8)
-    ms_e2e, _, _ = leg(step_e2e, 1, K, False)
+    ms_e2e, _, _ = leg(step_e2e, min(W, 3), K, False)
     h2d = sum(ch.model.h2d_bytes for ch in chains) / (len(chains) * K)
     d2h = sum(ch.model.d2h_bytes for ch in chains) / (len(chains) * K)
     # the host-side int64 trace row is read back as int32 [N] + the theta snapshot + scalars
@@ -322,32 +336,44 @@ def run_gpu(args, cfg):
 
     value = total_chains * K / (ms_dev / 1e3)
     e2e = total_chains * K / (ms_e2e / 1e3)
-    peak, peak_src = measured_peaks()
-    # roofline of the dominant kernel among the bracketed launches
-    ldk = max(3, k_live | 1)
-    alg_bytes = {
-        'll_matrix': N * M / 4 + 16.0 * k_live * M + 8.0 * N * k_live,
-        'gibbs_sweep': N * (8.0 * ldk + 32.0) + 8.0 * N,
-    }
+    hbm_peak, bf16_peak, peak_src = measured_peaks()
+    traffic = ncu_traffic()
     tot = {k: float(np.sum(v)) for k, v in ktimes.items()}
-    roof = None
-    if tot:
-        dom = max(tot, key=tot.get)
-        avg_ms = float(np.mean(ktimes[dom]))
-        ach = alg_bytes[dom] / (avg_ms * 1e-3) / 1e9
-        roof = dict(kernel=dom, bound='hbm', achieved=ach, peak=peak, unit='GB/s', frac=ach / peak,
-                    traffic=None, peak_source=peak_src, avg_launch_ms=avg_ms,
-                    algorithmic_bytes_per_launch=alg_bytes[dom],
-                    note='the sweep is a sequential chain of N dependent categorical draws: '
-                         'latency-bound by construction, HBM fraction reported for information')
+    n_unc = float(sweep_stats.get('uncertain', N))
+    # algorithmic work per launch:
+    #   likelihood rows  4*N*M*K flop (2 planes x multiply-add), N*M/4 + 16*K*M + 4*N*K bytes
+    #   sweep            the records of the uncertain visits (160 B each) + 4 B per visit of output
+    alg = {
+        'll_matrix': dict(flops=4.0 * N * M * k_live, bytes=N * M / 4 + 16.0 * k_live * M + 4.0 * N * k_live),
+        'gibbs_sweep': dict(flops=0.0, bytes=160.0 * n_unc + 4.0 * N),
+    }
+
+    def roof_of(name):
+        if name not in ktimes:
+            return None
+        avg_ms = float(np.mean(ktimes[name]))
+        if name == 'll_matrix':
+            ach = alg[name]['flops'] / (avg_ms * 1e-3) / 1e12
+            return dict(kernel='ll_matrix_tc_kernel (tcgen05 likelihood rows)', bound='tensor', achieved=ach,
+                        peak=bf16_peak, unit='TFLOP/s', frac=ach / bf16_peak,
+                        traffic=traffic.get('ll_matrix_tc_kernel'), peak_source=peak_src, avg_launch_ms=avg_ms,
+                        algorithmic_flops_per_launch=alg[name]['flops'],
+                        algorithmic_bytes_per_launch=alg[name]['bytes'],
+                        hbm_frac=alg[name]['bytes'] / (avg_ms * 1e-3) / 1e9 / hbm_peak,
+                        note='algorithmic flops 4*N*M*K; the kernel executes 2 bf16 split terms per '
+                             'log-probability and pads K to a multiple of 8')
+        ach = alg[name]['bytes'] / (avg_ms * 1e-3) / 1e9
+        return dict(kernel='gibbs_sweep_kernel', bound='hbm', achieved=ach, peak=hbm_peak, unit='GB/s',
+                    frac=ach / hbm_peak, traffic=traffic.get('gibbs_sweep_kernel'), peak_source=peak_src,
+                    avg_launch_ms=avg_ms, algorithmic_bytes_per_launch=alg[name]['bytes'],
+                    note='the sweep is a sequential chain of dependent categorical draws, one CTA per '
+                         'chain: latency-bound by construction; the HBM fraction is reported for information')
+
+    roof = roof_of(max(tot, key=tot.get)) if tot else None
+    roof_ll = roof_of('ll_matrix')
     kernels = {k: dict(launches=len(v), avg_ms=float(np.mean(v)),
                        share_of_step=float(np.sum(v)) / (len(chains) * ms_dev))
                for k, v in ktimes.items()}
-    if 'll_matrix' in ktimes:
-        avg = float(np.mean(ktimes['ll_matrix']))
-        kernels['ll_matrix'].update(
-            algorithmic_gbs=alg_bytes['ll_matrix'] / (avg * 1e-3) / 1e9,
-            algorithmic_tflops=4.0 * N * M * k_live / (avg * 1e-3) / 1e12, pipe='fp64 fma')
     out = dict(
         metric=METRIC, value=value, unit='chain-steps/s', n_gpus=n_gpus, steps=K, warmup=W,
         ms_per_step=ms_dev / K, higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -357,14 +383,15 @@ def run_gpu(args, cfg):
                              f'{"learned" if cfg["learning"] else "fixed"} error rates, start = true assignment',
                     chains_per_gpu=cpg, chains_total=total_chains, moves=moves_of(cfg),
                     live_clusters=k_live,
-                    l2='no explicit flush: per-step streams (ll matrix, visit records, draws) of the '
-                       f'{cpg} concurrent chains plus the bit-planes exceed the 126 MB L2 '
-                       f'({cpg * (8 * ldk + 48) * N / 1e6 + N * M / 4e6:.0f} MB)'),
+                    l2='no explicit flush: every step streams its own visit records, approximate rows, '
+                       'option records and draws (about 130 B per cell per chain) besides the bit-planes: '
+                       f'{cpg * 130 * N / 1e6 + N * M / 4e6:.0f} MB for the {cpg} concurrent chains vs 126 MB of L2'),
         steps_per_sec_per_chain=K / (ms_dev / 1e3),
         e2e=dict(value=e2e, unit='chain-steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  steps_per_sec_per_chain=K / (ms_e2e / 1e3), ms_per_step=ms_e2e / K,
                  api='libs.MCMC.Chain_steps.do_step + update_results (host traces)'),
-        gpu_launches=launches, roofline=roof, kernels=kernels, sweep=sweep_stats, clocks=clocks)
+        gpu_launches=launches, roofline=roof, roofline_likelihood=roof_ll, kernels=kernels,
+        sweep=sweep_stats, clocks=clocks)
     if not args.no_cpu_baseline and n_gpus == 1:
         out['cpu_baseline'] = run_cpu(cfg, 1, 2, 1, 25.0, args.cpu_sample_cells)
     if world > 1:

@@ -102,9 +102,15 @@ class _ThetaView:
     def __getitem__(self, ids):
         o = self._o
         scalar = np.ndim(ids) == 0
-        idx = torch.as_tensor(np.atleast_1d(np.asarray(ids, dtype=np.int64)), device=o.device)
+        idx = np.atleast_1d(np.asarray(ids, dtype=np.int64))
+        n, M = idx.size, o.muts_total
         with torch.cuda.stream(o.stream):
-            rows = o._down(o.theta.index_select(0, idx))
+            pin = o._pinned('theta_rows', n * M, torch.float32)
+            rows_d = o.theta.index_select(0, torch.as_tensor(idx, device=o.device))
+            pin[:n * M].copy_(rows_d.view(-1), non_blocking=True)
+            o._sync()
+        o.d2h_bytes += 4 * n * M
+        rows = pin[:n * M].numpy().reshape(n, M).copy()
         return rows[0] if scalar else rows
 
 
@@ -190,6 +196,14 @@ class DeviceCRP:
     def _sync(self):
         self.stream.synchronize()
 
+    def _pinned(self, name, numel, dtype):
+        """a pinned host staging buffer of at least numel elements (grown on demand)"""
+        t = self._pins.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(max(int(numel), 1), dtype=dtype).pin_memory()
+            self._pins[name] = t
+        return t
+
     class _Timed:
         """CUDA-event bracket around launches on the chain's stream (bench.py roofline)."""
 
@@ -241,6 +255,7 @@ class DeviceCRP:
             self.ep = _lib.Epoch()
             self.rg = _lib.RgMove()
             self._t = {}
+            self._pins = {}
             ws.x1, ws.x0, ws.n1, ws.n0 = (sh.x1.data_ptr(), sh.x0.data_ptr(), sh.n1.data_ptr(),
                                           sh.n0.data_ptr())
             ws.logn = sh.logn.data_ptr()
@@ -332,10 +347,22 @@ class DeviceCRP:
         self._version += 1
         self._trace_cache = None
 
+    def _assignment_pinned(self):
+        N = self.cells_total
+        with torch.cuda.stream(self.stream):
+            pin = self._pinned('assign', N, torch.int32)
+            pin[:N].copy_(self.assign_d, non_blocking=True)
+            self._sync()
+        self.d2h_bytes += 4 * N
+        return pin[:N].numpy()
+
     @property
     def assignment(self):
-        with torch.cuda.stream(self.stream):
-            return self._down(self.assign_d).astype(np.int64)
+        return self._assignment_pinned().astype(np.int64)
+
+    def assignment_into(self, row):
+        """trace row (any integer numpy array of length N) <- current assignment, one pass"""
+        np.copyto(row, self._assignment_pinned(), casting='unsafe')
 
     def copy_assignment_to(self, row):
         """device-side trace: row (int32 [N] device tensor) <- current assignment."""

@@ -313,7 +313,10 @@ class Chain:
         r['DP_alpha'][step] = self.model.DP_a
         r['FN'][step] = self.model.FN
         r['FP'][step] = self.model.FP
-        r['assignments'][step] = self.model.assignment
+        if hasattr(self.model, 'assignment_into'):
+            self.model.assignment_into(r['assignments'][step])
+        else:
+            r['assignments'][step] = self.model.assignment
         if burn_in:
             return
         clusters = np.sort(np.fromiter(self.model.cells_per_cluster.keys(), dtype=int))

@@ -46,7 +46,8 @@ WANT = [
     'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
     'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
     'smsp__inst_executed.sum', 'sm__cycles_elapsed.max', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
-    'lts__t_sector_hit_rate.pct',
+    'lts__t_sector_hit_rate.pct', 'sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active',
+    'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active',
 ]
 
 
