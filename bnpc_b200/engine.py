@@ -99,9 +99,8 @@ class _ThetaView:
     def __init__(self, owner):
         self._o = owner
 
-    def __getitem__(self, ids):
+    def _fetch(self, ids):
         o = self._o
-        scalar = np.ndim(ids) == 0
         idx = np.atleast_1d(np.asarray(ids, dtype=np.int64))
         n, M = idx.size, o.muts_total
         with torch.cuda.stream(o.stream):
@@ -110,8 +109,11 @@ class _ThetaView:
             pin[:n * M].copy_(rows_d.view(-1), non_blocking=True)
             o._sync()
         o.d2h_bytes += 4 * n * M
-        rows = pin[:n * M].numpy().reshape(n, M).copy()
-        return rows[0] if scalar else rows
+        return pin[:n * M].numpy().reshape(n, M)
+
+    def __getitem__(self, ids):
+        rows = self._fetch(ids).copy()
+        return rows[0] if np.ndim(ids) == 0 else rows
 
 
 class DeviceCRP:
@@ -336,6 +338,9 @@ class DeviceCRP:
         self._h_in = torch.empty(4 * cap + 16, dtype=i32).pin_memory()
         self._h_out = torch.empty(_lib.ST_WORDS + 2 * cap + 16, dtype=i32).pin_memory()
         self._h_scal = torch.empty(32, dtype=f64).pin_memory()
+        # trace staging is sized once per capacity: pinned allocations synchronise the device
+        self._pinned('theta_rows', cap * M, torch.float32)
+        self._pinned('assign', self.cells_total, i32)
         self.h_in, self.h_out, self.h_scal = self._h_in.numpy(), self._h_out.numpy(), self._h_scal.numpy()
         self.ws.h_in, self.ws.h_out, self.ws.h_scal = (self._h_in.data_ptr(), self._h_out.data_ptr(),
                                                        self._h_scal.data_ptr())
@@ -372,6 +377,10 @@ class DeviceCRP:
     @property
     def parameters(self):
         return _ThetaView(self)
+
+    def parameters_into(self, ids, out):
+        """out[:len(ids)] <- theta rows of the given cluster ids (trace recording, one copy)"""
+        out[:len(ids)] = _ThetaView(self)._fetch(ids)
 
     def _ids_sizes(self):
         ids = np.fromiter(self.cells_per_cluster.keys(), dtype=np.int64)

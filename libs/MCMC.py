@@ -295,10 +295,35 @@ class Chain:
         return self.results
 
     def init_results(self, steps):
+        """libs/MCMC.py:231-239.  The assignment trace is int32 (the reference's `int` is 64-bit:
+        twice the host memory, 4 GB per chain at 100k cells x 5000 steps) and is touched once here so
+        that recording a step never page-faults."""
         n = self.model.cells_total
         self.results = dict(ML=np.zeros(steps), MAP=np.zeros(steps), DP_alpha=np.zeros(steps),
                             FN=np.empty(steps), FP=np.empty(steps),
-                            assignments=np.zeros((steps, n), dtype=int))
+                            assignments=np.empty((steps, n), dtype=np.int32))
+        self.results['assignments'].fill(0)
+        self._par_buf = None          # [kept steps, cluster capacity, M]; results['params'] views it
+        self._par_k = 0
+
+    def _params_row(self, step, room, k):
+        """Row of the theta trace for this step with room for k clusters.  The reference pads the
+        whole [steps, K, M] array by one cluster whenever K grows (libs/MCMC.py:271-276); here the
+        cluster axis has spare capacity and results['params'] is a view of the columns in use."""
+        r = self.results
+        if self._par_buf is None:
+            cap = max(8, 2 * k)
+            self._par_buf = np.zeros((room, cap, self.model.muts_total), dtype=np.float32)
+        if k > self._par_buf.shape[1]:
+            grown = np.zeros((self._par_buf.shape[0], max(k, 2 * self._par_buf.shape[1]),
+                              self.model.muts_total), dtype=np.float32)
+            grown[:, :self._par_buf.shape[1]] = self._par_buf
+            self._par_buf = grown
+        if k > self._par_k or 'params' not in r or r['params'].base is not self._par_buf:
+            self._par_k = max(self._par_k, k)
+            r['params'] = self._par_buf[:, :self._par_k]
+        first_kept = r['ML'].size - self._par_buf.shape[0]
+        return self._par_buf[step - first_kept]
 
     def update_results(self, step, burn_in=True):
         """libs/MCMC.py:242-282: one trace row per step; theta rows of the SORTED live
@@ -320,25 +345,24 @@ class Chain:
         if burn_in:
             return
         clusters = np.sort(np.fromiter(self.model.cells_per_cluster.keys(), dtype=int))
-        if 'params' not in r:
-            r['params'] = np.zeros((room, clusters.size, self.model.muts_total), dtype=np.float32)
-        first_kept = r['ML'].size - r['params'].shape[0]
-        grow = clusters.size - r['params'].shape[1]
-        if grow > 0:
-            r['params'] = np.pad(r['params'], [(0, 0), (0, grow), (0, 0)], mode='constant')
-        r['params'][step - first_kept][:clusters.size] = self.model.parameters[clusters]
+        row = self._params_row(step, room, clusters.size)
+        if hasattr(self.model, 'parameters_into'):
+            self.model.parameters_into(clusters, row)
+        else:
+            row[:clusters.size] = self.model.parameters[clusters]
 
     def _extend_results(self, add_size=None, burn_in=True):
         r = self.results
         if not add_size:
             add_size = min(200, r['ML'].size)
-        if not burn_in and 'params' in r:
-            r['params'] = np.concatenate(
-                [r['params'], np.zeros((add_size,) + r['params'].shape[1:], dtype=np.float32)])
+        if not burn_in and self._par_buf is not None:
+            self._par_buf = np.concatenate(
+                [self._par_buf, np.zeros((add_size,) + self._par_buf.shape[1:], dtype=np.float32)])
+            r['params'] = self._par_buf[:, :self._par_k]
         for key in ('ML', 'MAP', 'DP_alpha', 'FN', 'FP'):
             r[key] = np.append(r[key], np.zeros(add_size))
         r['assignments'] = np.concatenate(
-            [r['assignments'], np.zeros((add_size, self.model.cells_total), dtype=int)])
+            [r['assignments'], np.zeros((add_size, self.model.cells_total), dtype=np.int32)])
 
     def stdout_progress(self):
         def show(counter, name, tabs=2):
