@@ -144,6 +144,9 @@ SIGNATURES = {
     'bnpc_chain_stats': [_WS, _I, _I, _P],
     'bnpc_chain_mh_theta': [_WS, _I, _I, _U64, _U64, _D, _D, _D, _D, _P],
     'bnpc_chain_loglik': [_WS, _I, C.POINTER(_D), C.POINTER(_D), _I, _I, _D, _D, _P],
+    'bnpc_chain_theta_rows': [_WS, _I, _P, _P],
+    'bnpc_copy_async': [_P, _P, _I64, _I, _P],
+    'bnpc_stream_sync': [_P],
     'bnpc_chain_rg_setup': [_WS, _RG, _P],
     'bnpc_chain_rg_scan_split': [_WS, _RG, _I, _P],
     'bnpc_chain_rg_scan_merged': [_WS, _RG, _I, _P],

@@ -51,6 +51,40 @@ __global__ void sum_int_kernel(const int32_t* __restrict__ v, int n, int32_t* ou
     }
 }
 
+__global__ void gather_rows_kernel(const float* __restrict__ theta, const int32_t* __restrict__ ids, int n, int M,
+                                   float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n * M) return;
+    const int r = (int)(i / M), m = (int)(i % M);
+    out[i] = theta[(long long)ids[r] * M + m];
+}
+
+int bnpc_copy_async(void* dst, const void* src, int64_t bytes, int kind, void* stream) {
+    if (bytes <= 0) return 0;
+    const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice
+                             : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    return copy_async(dst, src, (size_t)bytes, k, stream);
+}
+
+int bnpc_stream_sync(void* stream) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("cudaStreamSynchronize", e);
+    return 0;
+}
+
+// theta rows of the n cluster ids in h_in[0..n) -> dst_h (pinned host, [n][M] float); uses the
+// `cursor` and `rnd` scratch buffers of the workspace
+int bnpc_chain_theta_rows(const bnpc_chain_t* w, int n, float* dst_h, void* stream) {
+    if (!w || n <= 0 || n > w->idcap) return bad_arg("workspace/n");
+    TRY(copy_async(w->cursor, w->h_in, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, stream));
+    float* stage = reinterpret_cast<float*>(w->rnd);
+    gather_rows_kernel<<<cdiv((long long)n * w->M, 256), 256, 0, (cudaStream_t)stream>>>(w->theta, w->cursor, n,
+                                                                                      w->M, stage);
+    LAUNCH_CHECK("gather_rows");
+    TRY(copy_async(dst_h, stage, sizeof(float) * (size_t)n * w->M, cudaMemcpyDeviceToHost, stream));
+    return 0;
+}
+
 int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* stream) {
     if (!w || !e) return bad_arg("workspace/epoch");
     const int N = w->N, M = w->M, K = e->K, t = e->t, rows = e->rows, ldk = e->ldk;

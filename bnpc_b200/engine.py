@@ -101,13 +101,13 @@ class _ThetaView:
 
     def _fetch(self, ids):
         o = self._o
-        idx = np.atleast_1d(np.asarray(ids, dtype=np.int64))
+        idx = np.atleast_1d(np.asarray(ids, dtype=np.int32))
         n, M = idx.size, o.muts_total
-        with torch.cuda.stream(o.stream):
-            pin = o._pinned('theta_rows', n * M, torch.float32)
-            rows_d = o.theta.index_select(0, torch.as_tensor(idx, device=o.device))
-            pin[:n * M].copy_(rows_d.view(-1), non_blocking=True)
-            o._sync()
+        pin = o._pinned('theta_rows', n * M, torch.float32)
+        o.h_in[:n] = idx
+        o.L.chain_theta_rows(o.ws, n, pin.data_ptr(), o._sp())
+        o._sync()
+        o.h2d_bytes += 4 * n
         o.d2h_bytes += 4 * n * M
         return pin[:n * M].numpy().reshape(n, M)
 
@@ -174,11 +174,12 @@ class DeviceCRP:
 
     # ------------------------------------------------------------------ plumbing
     def _sp(self):
-        return self.stream.cuda_stream
+        return self._stream_ptr
 
     def _dev(self, name, shape, dtype, zero=False):
         """(Re)allocate the named workspace buffer and publish its address in the C workspace."""
-        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+        with torch.cuda.stream(self.stream):      # the fill of torch.zeros runs on the chain's stream
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
         self._t[name] = t
         if hasattr(self.ws, name):
             setattr(self.ws, name, t.data_ptr())
@@ -187,7 +188,8 @@ class DeviceCRP:
     def _put(self, dst, arr):
         """host array -> the head of a device workspace buffer (parity tapes, init)"""
         src = torch.from_numpy(np.ascontiguousarray(arr)).to(dst.dtype).reshape(-1)
-        dst.view(-1)[:src.numel()].copy_(src)
+        with torch.cuda.stream(self.stream):
+            dst.view(-1)[:src.numel()].copy_(src)
         self.h2d_bytes += src.numel() * src.element_size()
 
     def _down(self, t):
@@ -196,7 +198,7 @@ class DeviceCRP:
         return t.cpu().numpy()
 
     def _sync(self):
-        self.stream.synchronize()
+        self.L.stream_sync(self._sp())
 
     def _pinned(self, name, numel, dtype):
         """a pinned host staging buffer of at least numel elements (grown on demand)"""
@@ -242,6 +244,7 @@ class DeviceCRP:
         self.device = torch.device(self.device)
         torch.cuda.set_device(self.device)
         self.stream = torch.cuda.Stream(self.device)
+        self._stream_ptr = self.stream.cuda_stream
         if self.rnd is None:
             self.rnd = PhiloxRandom(np.random.SeedSequence().entropy & 0xFFFFFFFFFFFFFFFF)
         self.rnd.bind(self.device)
@@ -321,12 +324,14 @@ class DeviceCRP:
         old = self._t.get('theta')
         self.theta = self._dev('theta', (cap, M), torch.float32, zero=True)
         if old is not None:
-            self.theta[:self.idcap] = old
+            with torch.cuda.stream(self.stream):
+                self.theta[:self.idcap] = old
         for name in ('cnt', 'lst', 'rank_of_id', 'ids', 'cursor', 'declined'):
             self._dev(name, cap + 2, i32, zero=True)
         self._dev('seg', cap + 2, i32, zero=True)
         t = self._dev('col_of_id', cap, i32)
-        t.fill_(-1)
+        with torch.cuda.stream(self.stream):
+            t.fill_(-1)
         self._dev('live_io', 2 * cap, i32, zero=True)
         self._dev('scratch', cap + 1, f64)
         self._dev('lp', 2 * cap * M, f64)
@@ -354,10 +359,9 @@ class DeviceCRP:
 
     def _assignment_pinned(self):
         N = self.cells_total
-        with torch.cuda.stream(self.stream):
-            pin = self._pinned('assign', N, torch.int32)
-            pin[:N].copy_(self.assign_d, non_blocking=True)
-            self._sync()
+        pin = self._pinned('assign', N, torch.int32)
+        self.L.copy_async(pin.data_ptr(), self.assign_d.data_ptr(), 4 * N, 2, self._sp())
+        self._sync()
         self.d2h_bytes += 4 * N
         return pin[:N].numpy()
 
@@ -371,8 +375,7 @@ class DeviceCRP:
 
     def copy_assignment_to(self, row):
         """device-side trace: row (int32 [N] device tensor) <- current assignment."""
-        with torch.cuda.stream(self.stream):
-            row.copy_(self.assign_d, non_blocking=True)
+        self.L.copy_async(row.data_ptr(), self.assign_d.data_ptr(), 4 * self.cells_total, 3, self._sp())
 
     @property
     def parameters(self):
@@ -474,8 +477,7 @@ class DeviceCRP:
 
     def _trace_scalars(self):
         if self._trace_cache is None:
-            with torch.cuda.stream(self.stream):
-                r = self._loglik([float(self.FN)], [float(self.FP)], not self.beta_prior_uniform)
+            r = self._loglik([float(self.FN)], [float(self.FP)], not self.beta_prior_uniform)
             self._trace_cache = (float(r[0]), float(r[1]) if not self.beta_prior_uniform else 0.0)
         return self._trace_cache
 
@@ -508,108 +510,107 @@ class DeviceCRP:
         One C call and one stream synchronisation per epoch."""
         N, M = self.cells_total, self.muts_total
         L, ep = self.L, self.ep
-        with torch.cuda.stream(self.stream):
-            sp = self._sp()
-            mix0, mix1 = self._beta_mix_const
-            FN, FP = float(self.FN), float(self.FP)
-            # popcount form of get_lpost_single_new_cluster (libs/CRP.py:230-234)
-            ep.c1 = float(np.log(mix1 * (1 - FN) + mix0 * FP))
-            ep.c0 = float(np.log(mix1 * FN + mix0 * (1 - FP)))
-            ep.c_norm = float(np.log(N - 1 + self.DP_a))
-            ep.lnew_prior = float(np.log(self.DP_a) - np.log(N - 1 + self.DP_a))
-            ep.log_n = float(np.log(N))
-            ep.FN, ep.FP, ep.p, ep.q = FN, FP, float(self.p), float(self.q)
-            n_tape = 0
-            if self.rnd.is_tape:
-                perm, u, beta, n_tape = self.rnd.gibbs_draws(N, M)
-                self._put(self._t['perm'], perm)
-                self._put(self._t['u'], u)
+        sp = self._sp()
+        mix0, mix1 = self._beta_mix_const
+        FN, FP = float(self.FN), float(self.FP)
+        # popcount form of get_lpost_single_new_cluster (libs/CRP.py:230-234)
+        ep.c1 = float(np.log(mix1 * (1 - FN) + mix0 * FP))
+        ep.c0 = float(np.log(mix1 * FN + mix0 * (1 - FP)))
+        ep.c_norm = float(np.log(N - 1 + self.DP_a))
+        ep.lnew_prior = float(np.log(self.DP_a) - np.log(N - 1 + self.DP_a))
+        ep.log_n = float(np.log(N))
+        ep.FN, ep.FP, ep.p, ep.q = FN, FP, float(self.p), float(self.q)
+        n_tape = 0
+        if self.rnd.is_tape:
+            perm, u, beta, n_tape = self.rnd.gibbs_draws(N, M)
+            self._put(self._t['perm'], perm)
+            self._put(self._t['u'], u)
+            with torch.cuda.stream(self.stream):
                 beta_d = torch.as_tensor(beta, dtype=torch.float64, device=self.device)
-                ep.rand_ready, ep.beta_rows, ep.n_beta_rows = 1, beta_d.data_ptr(), n_tape
-                ep.seed, ep.stream_id = 0, 0
+            ep.rand_ready, ep.beta_rows, ep.n_beta_rows = 1, beta_d.data_ptr(), n_tape
+            ep.seed, ep.stream_id = 0, 0
+        else:
+            ep.rand_ready, ep.beta_rows, ep.n_beta_rows = 0, None, 0
+            ep.seed, ep.stream_id = self.rnd.device_seed, self._streams(3)
+        t, first, epochs, stall = 0, 1, 0, 0
+        while t < N:
+            K = len(self.cells_per_cluster)
+            self._grow_ids(K + _lib.MAX_EXTRA + 2)
+            h = self.h_in
+            h[0:2 * K:2] = np.fromiter(self.cells_per_cluster.keys(), dtype=np.int32, count=K)
+            h[1:2 * K:2] = np.fromiter(self.cells_per_cluster.values(), dtype=np.int32, count=K)
+            # odd row stride (bank-conflict-free per-lane row reads in the warp regime)
+            ldk = max(3, K | 1)
+            # lean epoch: approximate rows select the options, FP64 only where a decision
+            # needs it; dense FP64 matrix for longer lists (or when many cells have > 8 rivals)
+            lean = K <= _lib.LEAN_MAXK and self._lean_ok and self.lean_enabled
+            rows = N - t if lean else int(min(N - t, max(1, LL_BUDGET_BYTES // (8 * ldk))))
+            ep.lean = self.lean_rows if lean else 0
+            if not lean and rows * ldk + 2 > self._ll_cap:
+                self._ll_cap = rows * ldk + 2
+                self._dev('ll', self._ll_cap, torch.float64)
+            if not lean and _lib.MAX_EXTRA * rows > self._llx_cap:
+                self._llx_cap = _lib.MAX_EXTRA * rows
+                self._dev('llx', self._llx_cap, torch.float64)
+            ep.first, ep.K, ep.t, ep.rows, ep.ldk = first, K, t, rows, ldk
+            if self.profile:
+                # CUDA events recorded by the library around the two dominant launches
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                for e in evs:
+                    e.record(self.stream)            # creates the underlying event
+                ep.ev_ll0, ep.ev_ll1, ep.ev_sw0, ep.ev_sw1 = [e.cuda_event for e in evs]
+                self._events += [('ll_matrix', evs[0], evs[1]), ('gibbs_sweep', evs[2], evs[3])]
             else:
-                ep.rand_ready, ep.beta_rows, ep.n_beta_rows = 0, None, 0
-                ep.seed, ep.stream_id = self.rnd.device_seed, self._streams(3)
-            t, first, epochs, stall = 0, 1, 0, 0
-            while t < N:
-                K = len(self.cells_per_cluster)
-                self._grow_ids(K + _lib.MAX_EXTRA + 2)
-                h = self.h_in
-                h[0:2 * K:2] = np.fromiter(self.cells_per_cluster.keys(), dtype=np.int32, count=K)
-                h[1:2 * K:2] = np.fromiter(self.cells_per_cluster.values(), dtype=np.int32, count=K)
-                # odd row stride (bank-conflict-free per-lane row reads in the warp regime)
-                ldk = max(3, K | 1)
-                # lean epoch: approximate rows select the options, FP64 only where a decision
-                # needs it; dense FP64 matrix for longer lists (or when many cells have > 8 rivals)
-                lean = K <= _lib.LEAN_MAXK and self._lean_ok and self.lean_enabled
-                rows = N - t if lean else int(min(N - t, max(1, LL_BUDGET_BYTES // (8 * ldk))))
-                ep.lean = self.lean_rows if lean else 0
-                if not lean and rows * ldk + 2 > self._ll_cap:
-                    self._ll_cap = rows * ldk + 2
-                    self._dev('ll', self._ll_cap, torch.float64)
-                if not lean and _lib.MAX_EXTRA * rows > self._llx_cap:
-                    self._llx_cap = _lib.MAX_EXTRA * rows
-                    self._dev('llx', self._llx_cap, torch.float64)
-                ep.first, ep.K, ep.t, ep.rows, ep.ldk = first, K, t, rows, ldk
-                if self.profile:
-                    # CUDA events recorded by the library around the two dominant launches
-                    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-                    for e in evs:
-                        e.record(self.stream)            # creates the underlying event
-                    ep.ev_ll0, ep.ev_ll1, ep.ev_sw0, ep.ev_sw1 = [e.cuda_event for e in evs]
-                    self._events += [('ll_matrix', evs[0], evs[1]), ('gibbs_sweep', evs[2], evs[3])]
-                else:
-                    ep.ev_ll0 = ep.ev_ll1 = ep.ev_sw0 = ep.ev_sw1 = None
-                L.chain_gibbs_epoch(self.ws, ep, sp)
-                self._sync()
-                self.h2d_bytes += 8 * K
-                st = self.h_out[:_lib.ST_WORDS]
-                flags = int(st[_lib.ST_FLAGS])
-                if flags & (_lib.STOP_TAPE_EMPTY | _lib.STOP_HANG):
-                    raise RuntimeError(f'gibbs_sweep stopped with flags {flags:#x} at t={st[_lib.ST_TDONE]}')
-                K = int(st[_lib.ST_K])
-                self.d2h_bytes += 4 * _lib.ST_WORDS + 8 * K
-                pairs = self.h_out[_lib.ST_WORDS:_lib.ST_WORDS + 2 * K].tolist()
-                self.cells_per_cluster = OrderedDict(zip(pairs[0::2], pairs[1::2]))
-                t_new = int(st[_lib.ST_TDONE])
-                if lean and int(st[_lib.ST_NMANY]) > max(64, rows // 50):
-                    self._lean_ok = False          # too many cells with > 8 rivals: dense rows pay
-                elif not lean and K <= _lib.LEAN_MAXK:
-                    self._lean_ok = True           # try again next time
-                stall = stall + 1 if t_new == t else 0
-                if stall > 2:
-                    raise RuntimeError(f'gibbs_sweep made no progress at t={t} (flags {flags:#x})')
-                if flags & _lib.STOP_CAPACITY:
-                    self._grow_ids(2 * self.idcap)
-                t, first = t_new, 0
-                epochs += 1
-            if self.rnd.is_tape and int(st[_lib.ST_BIRTHS]) != n_tape:
-                raise RuntimeError(f'parity tape held {n_tape} cluster births, sweep made '
-                                   f'{int(st[_lib.ST_BIRTHS])}')
-            self.sweep_stats = dict(epochs=epochs, births=int(st[_lib.ST_BIRTHS]),
-                                    moved=int(st[_lib.ST_MOVED]), slow=int(st[_lib.ST_SLOW]),
-                                    uncertain=int(st[_lib.ST_NUNC]),
-                                    kcycles=int(st[8]), us=int(st[9]) * 1.024,
-                                    sm_mhz=(int(st[8]) / max(1, int(st[9]))) * 1e3)
+                ep.ev_ll0 = ep.ev_ll1 = ep.ev_sw0 = ep.ev_sw1 = None
+            L.chain_gibbs_epoch(self.ws, ep, sp)
+            self._sync()
+            self.h2d_bytes += 8 * K
+            st = self.h_out[:_lib.ST_WORDS]
+            flags = int(st[_lib.ST_FLAGS])
+            if flags & (_lib.STOP_TAPE_EMPTY | _lib.STOP_HANG):
+                raise RuntimeError(f'gibbs_sweep stopped with flags {flags:#x} at t={st[_lib.ST_TDONE]}')
+            K = int(st[_lib.ST_K])
+            self.d2h_bytes += 4 * _lib.ST_WORDS + 8 * K
+            pairs = self.h_out[_lib.ST_WORDS:_lib.ST_WORDS + 2 * K].tolist()
+            self.cells_per_cluster = OrderedDict(zip(pairs[0::2], pairs[1::2]))
+            t_new = int(st[_lib.ST_TDONE])
+            if lean and int(st[_lib.ST_NMANY]) > max(64, rows // 50):
+                self._lean_ok = False          # too many cells with > 8 rivals: dense rows pay
+            elif not lean and K <= _lib.LEAN_MAXK:
+                self._lean_ok = True           # try again next time
+            stall = stall + 1 if t_new == t else 0
+            if stall > 2:
+                raise RuntimeError(f'gibbs_sweep made no progress at t={t} (flags {flags:#x})')
+            if flags & _lib.STOP_CAPACITY:
+                self._grow_ids(2 * self.idcap)
+            t, first = t_new, 0
+            epochs += 1
+        if self.rnd.is_tape and int(st[_lib.ST_BIRTHS]) != n_tape:
+            raise RuntimeError(f'parity tape held {n_tape} cluster births, sweep made '
+                               f'{int(st[_lib.ST_BIRTHS])}')
+        self.sweep_stats = dict(epochs=epochs, births=int(st[_lib.ST_BIRTHS]),
+                                moved=int(st[_lib.ST_MOVED]), slow=int(st[_lib.ST_SLOW]),
+                                uncertain=int(st[_lib.ST_NUNC]),
+                                kcycles=int(st[8]), us=int(st[9]) * 1.024,
+                                sm_mhz=(int(st[8]) / max(1, int(st[9]))) * 1e3)
         self._touch()
 
     # ----------------------------------------------------------------- MH theta
     def update_parameters(self, step_no=None):
         """libs/CRP.py:302-311, 314-344 for all live clusters in one launch.
         Returns (declined, accepted) summed over clusters x mutations."""
-        with torch.cuda.stream(self.stream):
-            self._refresh_stats()
-            K, M = len(self.cells_per_cluster), self.muts_total
-            if self.rnd.is_tape:
-                self._put(self._t['rnd'], self.rnd.mh_theta_draws(K, M))
-                ready, seed, sid = 1, 0, 0
-            else:
-                ready, seed, sid = 0, self.rnd.device_seed, self._streams(2)
-            self.L.chain_mh_theta(self.ws, K, ready, seed, sid, float(self.FN), float(self.FP),
-                                  float(self.p), float(self.q), self._sp())
-            self._sync()
-            declined = int(self.h_out[0])
-            self.d2h_bytes += 4
+        self._refresh_stats()
+        K, M = len(self.cells_per_cluster), self.muts_total
+        if self.rnd.is_tape:
+            self._put(self._t['rnd'], self.rnd.mh_theta_draws(K, M))
+            ready, seed, sid = 1, 0, 0
+        else:
+            ready, seed, sid = 0, self.rnd.device_seed, self._streams(2)
+        self.L.chain_mh_theta(self.ws, K, ready, seed, sid, float(self.FN), float(self.FP),
+                              float(self.p), float(self.q), self._sp())
+        self._sync()
+        declined = int(self.h_out[0])
+        self.d2h_bytes += 4
         self._trace_cache = None
         return declined, K * M - declined
 
@@ -632,15 +633,14 @@ class DeviceCRP:
     def update_assignments_split_merge(self, ratios=(.75, .25), step_no=5):
         """libs/CRP.py:417-431.  Returns ([accepted, declined], move)."""
         k = len(self.cells_per_cluster)
-        with torch.cuda.stream(self.stream):
-            if k == 1:
-                return (self._try_split(step_no), 0)
-            if k == self.cells_total:
-                return (self._try_merge(step_no), 1)
-            move = self.rnd.pick_weighted(ratios)
-            if move == 0:
-                return (self._try_split(step_no), move)
-            return (self._try_merge(step_no), move)
+        if k == 1:
+            return (self._try_split(step_no), 0)
+        if k == self.cells_total:
+            return (self._try_merge(step_no), 1)
+        move = self.rnd.pick_weighted(ratios)
+        if move == 0:
+            return (self._try_split(step_no), move)
+        return (self._try_merge(step_no), move)
 
     def _rg_begin(self, n, n_a, cl_i, cl_j, a_i, a_j, is_merge):
         g = self.rg
@@ -858,8 +858,7 @@ class DeviceCRPLearnErrors(DeviceCRP):
     def _ll_at(self, pairs):
         """full-data log-likelihood at each (FP, FN) pair, from the [K][M] sufficient
         statistics (libs/CRP_learning_errors.py:58-63 without the [N,M] pass)."""
-        with torch.cuda.stream(self.stream):
-            r = self._loglik([float(fn) for _, fn in pairs], [float(fp) for fp, _ in pairs], False)
+        r = self._loglik([float(fn) for _, fn in pairs], [float(fp) for fp, _ in pairs], False)
         return [float(x) for x in r]
 
     def _mh_error(self, which):

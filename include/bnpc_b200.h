@@ -376,6 +376,14 @@ int bnpc_chain_mh_theta(const bnpc_chain_t* w, int K, int rand_ready, uint64_t s
 int bnpc_chain_loglik(const bnpc_chain_t* w, int K, const double* fn_h, const double* fp_h, int E,
                       int want_prior, double p, double q, void* stream);
 
+/* theta rows of the n cluster ids in h_in[0..n) -> dst_h (pinned host [n][M] float): the trace
+ * read of libs/MCMC.py:281-282 (`model.parameters[clusters]`)                                 */
+int bnpc_chain_theta_rows(const bnpc_chain_t* w, int n, float* dst_h, void* stream);
+/* plumbing for hosts without their own CUDA runtime binding: asynchronous copy on the stream
+ * (kind 1 host->device, 2 device->host, 3 device->device) and stream synchronisation           */
+int bnpc_copy_async(void* dst, const void* src, int64_t bytes, int kind, void* stream);
+int bnpc_stream_sync(void* stream);
+
 /* A split-merge move (libs/CRP.py:434-567).  n cells of cluster cl_i (split: cl_j = -1) or of
  * cl_i then cl_j (merge, n_a cells in cl_i); a_i, a_j = anchor positions.  Random streams
  * stream_id+1.. of `seed` per call (at most 4) unless rand_ready (rg_perm, rg_u, rg_rnd, rg_sd,
