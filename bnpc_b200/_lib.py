@@ -20,7 +20,7 @@ HEADERS = [os.path.join(_HERE, 'csrc', 'bnpc_math.cuh'), os.path.join(_HERE, 'cs
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-fmad=false', '-std=c++17', '-shared', '-Xcompiler', '-fPIC']
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_EXTRA = 32
 ST_K, ST_TDONE, ST_FLAGS, ST_NEXTRA, ST_BIRTHS, ST_MOVED, ST_SLOW = range(7)
 ST_NUNC = 10
@@ -61,7 +61,7 @@ class SweepArgs(C.Structure):
         ('x1', C.c_void_p), ('x0', C.c_void_p), ('W', C.c_int32), ('N', C.c_int32), ('M', C.c_int32),
         ('assign', C.c_void_p), ('cnt', C.c_void_p), ('lst', C.c_void_p), ('col_of_id', C.c_void_p),
         ('theta', C.c_void_p), ('idcap', C.c_int32), ('st', C.c_void_p), ('live_out', C.c_void_p),
-        ('ll', C.c_void_p), ('ldk', C.c_int32), ('t_epoch0', C.c_int32), ('lp', C.c_void_p),
+        ('ll', C.c_void_p), ('ldk', C.c_int32), ('t_epoch0', C.c_int32), ('lp', C.c_void_p), ('comp', C.c_void_p),
         ('lpx', C.c_void_p), ('llx', C.c_void_p), ('ldx', C.c_int32),
         ('scratch', C.c_void_p),
         ('visit', C.c_void_p), ('cand', C.c_void_p), ('t_begin', C.c_int32), ('t_end', C.c_int32),
@@ -83,7 +83,7 @@ class ChainWs(C.Structure):
         [(n, C.c_void_p) for n in (
             'assign', 'theta', 'cnt', 'lst', 'col_of_id', 'rank_of_id', 'live_io', 'st',
             'visit', 'cand', 'visit_c', 'cand_c', 'cblk', 'perm', 'u',
-            'lp', 'll', 'lpx', 'llx', 'scratch', 'lpf', 'llf', 'opt', 'n_cert', 'idx_c', 'bsplit',
+            'lp', 'll', 'lpx', 'llx', 'scratch', 'lpf', 'llf', 'opt', 'n_cert', 'idx_c', 'bsplit', 'comp',
             'ids', 'seg', 'cursor', 'members', 'S1', 'S0', 'rnd', 'declined', 'rl_out', 'rl_tot',
             'cells', 'half', 'gblk', 'seg3', 'rg_work', 'rg_theta', 'rg_S1', 'rg_S0', 'rg_dec', 'rg_scal',
             'rg_lp', 'rg_ll2', 'rg_lq', 'rg_logq', 'rg_A', 'rg_orig', 'rg_perm', 'rg_u', 'rg_rnd', 'rg_sd',
@@ -92,7 +92,7 @@ class ChainWs(C.Structure):
 
 class Epoch(C.Structure):
     """bnpc_epoch_t"""
-    _fields_ = [(n, C.c_int32) for n in ('first', 'K', 't', 'rows', 'ldk', 'rand_ready', 'lean', 'pad0')] + \
+    _fields_ = [(n, C.c_int32) for n in ('first', 'K', 't', 'rows', 'ldk', 'rand_ready', 'lean', 'serial_sweep')] + \
         [(n, C.c_double) for n in ('c1', 'c0', 'lnew_prior', 'c_norm', 'log_n', 'FN', 'FP', 'p', 'q')] + \
         [('seed', C.c_uint64), ('stream_id', C.c_uint64), ('beta_rows', C.c_void_p),
          ('n_beta_rows', C.c_int32)] + \
@@ -121,7 +121,7 @@ SIGNATURES = {
     'bnpc_ll_matrix_f32': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P],
     'bnpc_ll_matrix_tc': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P],
     'bnpc_gibbs_options': [_P, _I, _I, _P, _P, _P, _P, _I, _D, _D, _I, _P],
-    'bnpc_gibbs_exact': [_P, _P, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _D, _D, _P],
+    'bnpc_gibbs_exact': [_P, _P, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _D, _D, _P, _P],
     'bnpc_gibbs_epoch_begin': [_P, _I, _P, _P, _P, _I, _P, _I, _P],
     'bnpc_gibbs_sweep': [C.POINTER(SweepArgs), _I, _P],
     'bnpc_group_members': [_P, _I, _P, _P, _P, _I, _P, _P],

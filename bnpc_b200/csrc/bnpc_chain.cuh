@@ -121,7 +121,7 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
         TRY(bnpc_gibbs_options(w->llf, ldf, K, w->col_of_id, w->visit + t, w->opt + t, w->n_cert, rows, e->log_n,
                                e->c_norm, 2 * M, stream));
         TRY(bnpc_gibbs_exact(w->x1, w->x0, w->W, M, w->lp, K, w->visit + t, w->opt + t, w->n_cert, rows, w->cblk,
-                             w->idx_c, w->st, w->visit_c, w->cand_c, e->log_n, e->c_norm, stream));
+                             w->idx_c, w->st, w->visit_c, w->cand_c, e->log_n, e->c_norm, w->comp, stream));
     } else {
         TRY(record_event(e->ev_ll0, stream));
         TRY(bnpc_ll_matrix(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp, K, w->ll, ldk, stream));
@@ -138,6 +138,7 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
     a.assign = w->assign; a.cnt = w->cnt; a.lst = w->lst; a.col_of_id = w->col_of_id; a.theta = w->theta;
     a.idcap = w->idcap; a.st = w->st; a.live_out = w->live_io;
     a.ll = lean ? nullptr : w->ll; a.ldk = ldk; a.t_epoch0 = t; a.lp = w->lp;
+    a.comp = (lean && !e->serial_sweep) ? w->comp : nullptr;
     a.lpx = w->lpx; a.llx = w->llx; a.ldx = rows; a.scratch = w->scratch;
     a.visit = w->visit; a.cand = lean ? nullptr : w->cand; a.t_begin = t; a.t_end = t + rows;
     a.visit_c = compacted ? w->visit_c : nullptr;

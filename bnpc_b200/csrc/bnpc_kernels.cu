@@ -497,6 +497,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 #define SW_NSTAGE 16
 #define SW_MAXL 1024          /* longest list / widest ll matrix the sequencer regime handles */
 
+#define SW_PAR_WARPS 8
+#define SW_WINDOW 256         /* records per window of the parallel sequencer (= 8 stages) */
+
 struct SweepShared {
     alignas(128) bnpc_visit_t vis_stage[SW_NSTAGE][SW_STAGE_CELLS];
     alignas(128) bnpc_cand_t cand_stage[SW_NSTAGE][SW_STAGE_CELLS];
@@ -513,6 +516,11 @@ struct SweepShared {
     int hang;
     int compact, crec;                          // compact mode on / next compacted record
     double s_row[BNPC_LEAN_MAXK];               // lean epochs: exact ll row of the cell in hand, by column
+    // parallel sequencer (lean epochs): one warp per group of option-graph components
+    int owner_of_col[BNPC_LEAN_MAXK];
+    int abort_idx;                              // window-relative index of the first record that needs the exact path
+    unsigned char own_idx[SW_PAR_WARPS][SW_WINDOW];      // a warp's records of the window, in order
+    unsigned int mlog[SW_PAR_WARPS][SW_WINDOW];           // its moves of the window: idx | from << 8 | to << 16
 };
 
 // One exact categorical draw for a list that fits a warp (libs/CRP.py:88-100 + numpy choice,
@@ -872,6 +880,248 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
     }
 }
 
+// Parallel sequencer of lean epochs (all 8 warps of the CTA).  Two visits interact only through
+// the sizes of clusters both have among their options, so the records split into the connected
+// components of the "option graph" on the clusters (components_kernel); a warp owns a group of
+// components and walks ITS records in visiting order with the batched scoring of
+// sweep_sequencer, while the other warps do the same for theirs.  Records are taken in windows of
+// 256 (bulk-copied into shared memory, double-buffered); all warps meet at the end of a window.
+// A record that needs the exact path (guard band, death, birth, > 8 rivals) must see the state of
+// ALL clusters exactly at its position: the warp that meets it posts its index, every warp undoes
+// the moves it made past that index in this window (they are logged; assignments are only
+// written at the end of a window), and the CTA handles the record before the walk resumes behind it.
+__device__ void sweep_sequencer_par(const bnpc_sweep_args_t& a, SweepShared& sh) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int L = sh.L;
+    if (w == 0) {
+        for (int j = lane; j < L; j += 32) {
+            const int id = a.lst[j];
+            sh.s_id[j] = id; sh.s_cnt[j] = a.cnt[id]; sh.s_src[j] = a.col_of_id[id];
+        }
+        __syncwarp();
+        sweep_rebuild_maps(sh, L);
+    }
+    if (tid < BNPC_LEAN_MAXK) sh.owner_of_col[tid] = a.comp[192 + tid];
+    if (tid == 0) {
+        mbar_init(&sh.bar[0], 1);
+        mbar_init(&sh.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        sh.abort_idx = 0x7fffffff;
+    }
+    __syncthreads();
+    const int n_rec = a.st[BNPC_ST_NUNC];
+    const int first_rec = sh.crec;
+    const int n_win = (first_rec < n_rec) ? (n_rec - first_rec + SW_WINDOW - 1) / SW_WINDOW : 0;
+    bnpc_visit_t* vbuf = &sh.vis_stage[0][0];           // two windows of 256 records
+    bnpc_cand_t* cbuf = &sh.cand_stage[0][0];
+    auto issue = [&](int g) {                            // thread 0 only
+        const int r0 = first_rec + g * SW_WINDOW;
+        const int nw = min(SW_WINDOW, n_rec - r0);
+        const uint32_t b_v = (uint32_t)(nw * sizeof(bnpc_visit_t)), b_c = (uint32_t)(nw * sizeof(bnpc_cand_t));
+        mbar_expect_tx(&sh.bar[g & 1], b_v + b_c);
+        bulk_g2s(vbuf + (g & 1) * SW_WINDOW, a.visit_c + r0, b_v, &sh.bar[g & 1]);
+        bulk_g2s(cbuf + (g & 1) * SW_WINDOW, a.cand_c + r0, b_c, &sh.bar[g & 1]);
+    };
+    int issued = 0;
+    if (tid == 0)
+        for (; issued < n_win && issued < 2; ++issued) issue(issued);
+    int moved = 0, slow = 0;
+    int next_t = a.t_end, next_rec = n_rec;
+    bool leave = false;
+    int waited = 0;
+    for (int g = 0; g < n_win && !leave; ++g) {
+        {
+            long long spins = 0;
+            while (!mbar_try_wait(&sh.bar[g & 1], (uint32_t)((g >> 1) & 1))) {
+                if (++spins > (1ll << 24)) { sh.hang = 1; break; }
+            }
+        }
+        waited = g + 1;
+        const int r0 = first_rec + g * SW_WINDOW;
+        const int nw = min(SW_WINDOW, n_rec - r0);
+        const bnpc_visit_t* vis = vbuf + (g & 1) * SW_WINDOW;
+        const bnpc_cand_t* cnd = cbuf + (g & 1) * SW_WINDOW;
+        // ---- this warp's records of the window, in order ----
+        int own = 0;
+#pragma unroll
+        for (int c = 0; c < SW_WINDOW / 32; ++c) {
+            const int rec = c * 32 + lane;
+            bool mine = false;
+            if (rec < nw) {
+                const int n_opt = vis[rec].n_opt, c_old = vis[rec].c_old;
+                const bool global = n_opt > BNPC_MAX_OPT || c_old < 0 || c_old >= BNPC_LEAN_MAXK;
+                mine = global ? (w == 0) : (sh.owner_of_col[c_old] == w);
+            }
+            const unsigned m = __ballot_sync(FULL, mine);
+            if (mine) sh.own_idx[w][own + __popc(m & lt_mask)] = (unsigned char)rec;
+            own += __popc(m);
+        }
+        __syncwarp();
+        int n_log = 0;
+        bool stopped = false;
+        for (int base = 0; base < own && !stopped; base += 32) {
+            int nc = min(32, own - base);
+            const int rec = sh.own_idx[w][base + (lane < nc ? lane : 0)];
+            const bnpc_visit_t v = vis[rec];
+            double e[BNPC_MAX_OPT];
+            int pos[BNPC_MAX_OPT];
+            {
+                const bnpc_cand_t* cd = &cnd[rec];
+#pragma unroll
+                for (int i = 0; i < BNPC_MAX_OPT; ++i) { e[i] = cd->e[i]; pos[i] = cd->col[i]; }
+            }
+            const int n_opt = v.n_opt, i_old = v.i_old;
+            int n_max = (lane < nc && n_opt <= BNPC_MAX_OPT) ? n_opt : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(FULL, n_max, o));
+            // list positions of the options (columns -> positions change only on the exact path)
+#pragma unroll
+            for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+                if (i >= n_max) break;
+                pos[i] = (i < n_opt && n_opt <= BNPC_MAX_OPT) ? sh.s_pos_of_col[pos[i]] : -1;
+            }
+            const int p_old = (n_opt <= BNPC_MAX_OPT && v.c_old >= 0) ? sh.s_pos_of_col[v.c_old] : -1;
+            const bool own_ok = p_old >= 0 && sh.s_id[p_old] == v.old;
+            const double e_lim = (double)v.e_max;
+            int lo_lane = 0;
+            bool need_eval = lane < nc;
+            int outcome = OUT_STAY, to_pos = -1, c_own = 0;
+            double slack = 0.0;
+            while (lo_lane < nc) {
+                // records at or behind a posted exact-path record are left for the next walk
+                const int ab = *(volatile int*)&sh.abort_idx;
+                if (ab != 0x7fffffff) {
+                    const unsigned keep = __ballot_sync(FULL, lane < nc && rec < ab);
+                    nc = __popc(keep);                   // own_idx is ascending: a prefix survives
+                    stopped = true;
+                    if (lo_lane >= nc) break;
+                }
+                if (need_eval) {
+                    need_eval = false;
+                    outcome = OUT_COMPLEX;
+                    to_pos = -1;
+                    slack = 0.0;
+                    c_own = own_ok ? sh.s_cnt[p_old] : 0;
+                    if (own_ok && c_own > 1) {
+                        double cum[BNPC_MAX_OPT];
+                        double S = 0.0;
+#pragma unroll
+                        for (int i = 0; i < BNPC_MAX_OPT; ++i) cum[i] = 0.0;
+#pragma unroll
+                        for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+                            if (i >= n_max) break;            // warp-uniform
+                            int c = 0;
+                            if (i < n_opt && pos[i] >= 0) c = sh.s_cnt[pos[i]];
+                            if (i == i_old) --c;
+                            S = fma((double)c, e[i], S);      // e[i] = 0 beyond the options
+                            cum[i] = S;
+                        }
+                        const double total = S + v.e_new;
+                        const double target = v.u * total;
+                        int pick = 0;
+                        double dmin = target;                 // distance to the nearest interval edge
+#pragma unroll
+                        for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+                            if (i >= n_max) break;
+                            if (i < n_opt) {
+                                const double d = cum[i] - target;
+                                pick += (d <= 0.0) ? 1 : 0;
+                                dmin = fmin(dmin, fabs(d));
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < BNPC_MAX_OPT; ++i)
+                            if (i == pick) to_pos = pos[i];
+                        // pick == n_opt: the new-cluster option (or rounding at the top edge) -> exact draw
+                        if (pick < n_opt && to_pos >= 0) {
+                            slack = dmin - 2.0 * SW_GUARD * total;
+                            if (slack > 0.0) outcome = (pick == i_old) ? OUT_STAY : OUT_MOVE;
+                        }
+                    }
+                }
+                const bool act = lane >= lo_lane && lane < nc;
+                const unsigned pend = __ballot_sync(FULL, act && outcome != OUT_STAY);
+                if (!pend) break;
+                const int nb = __popc(pend & lt_mask);
+                bool ok = true;
+                if (act) {
+                    if (outcome == OUT_COMPLEX) ok = false;
+                    else if (nb > 0) ok = (slack - 4.0 * e_lim * (double)nb > 0.0) && (c_own - nb > 1);
+                }
+                const unsigned bad = __ballot_sync(FULL, !ok);
+                const int fb = bad ? (__ffs(bad) - 1) : 32;
+                const unsigned batch = pend & ((fb >= 32) ? FULL : ((1u << fb) - 1u));
+                if (batch) {
+                    if ((batch >> lane) & 1u) {
+                        atomicSub(&sh.s_cnt[p_old], 1);
+                        atomicAdd(&sh.s_cnt[to_pos], 1);
+                        sh.mlog[w][n_log + __popc(batch & lt_mask)] =
+                            (unsigned)rec | ((unsigned)p_old << 8) | ((unsigned)to_pos << 16);
+                    }
+                    n_log += __popc(batch);
+                    __syncwarp();
+                    if (fb >= nc) break;
+                    lo_lane = fb;
+                    need_eval = lane >= lo_lane && lane < nc;
+                    continue;
+                }
+                // the first pending record cannot take the linear form: post it, stop this warp here
+                const int rec_f = __shfl_sync(FULL, rec, fb);
+                if (lane == 0) atomicMin(&sh.abort_idx, rec_f);
+                stopped = true;
+                break;
+            }
+        }
+        __syncthreads();
+        // ---- end of the window: commit the moves in front of a posted record, undo the rest ----
+        const int ab = sh.abort_idx;
+        for (int i = lane; i < n_log; i += 32) {
+            const unsigned en = sh.mlog[w][i];
+            const int rec = en & 0xff, from = (en >> 8) & 0xff, to = (en >> 16) & 0xff;
+            if (rec < ab) {
+                a.assign[vis[rec].cell] = sh.s_id[to];
+                ++moved;
+            } else {
+                atomicAdd(&sh.s_cnt[from], 1);
+                atomicSub(&sh.s_cnt[to], 1);
+            }
+        }
+        __syncthreads();
+        if (ab != 0x7fffffff) {
+            // the CTA handles record `ab` exactly, then the walk resumes behind it
+            next_t = vis[ab].t;
+            next_rec = r0 + ab + 1;
+            if (tid == 0) { sh.pending = 3; ++slow; }
+            leave = true;
+        } else if (tid == 0 && issued < n_win) {
+            issue(issued);
+        }
+        if (!leave && issued < n_win) ++issued;      // (uniform: every thread tracks the count)
+    }
+    // drain copies still in flight before shared memory is reused or the kernel ends
+    for (int g = waited; g < ((tid == 0) ? issued : 0); ++g) {
+        long long spins = 0;
+        while (!mbar_try_wait(&sh.bar[g & 1], (uint32_t)((g >> 1) & 1))) {
+            if (++spins > (1ll << 24)) { sh.hang = 1; break; }
+        }
+    }
+    // moves counted per lane: fold into the CTA totals
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) moved += __shfl_xor_sync(FULL, moved, o);
+    if (lane == 0 && moved) atomicAdd(&sh.moved, moved);
+    __syncthreads();
+    for (int j = tid; j < L; j += blockDim.x) a.cnt[sh.s_id[j]] = sh.s_cnt[j];
+    if (tid == 0) {
+        sh.t = next_t;
+        sh.crec = next_rec;
+        sh.slow += slow;
+        sh.abort_idx = 0x7fffffff;
+    }
+    __syncthreads();
+}
+
 // one cell with the whole CTA (list longer than a warp)
 __device__ void sweep_block_cell(const bnpc_sweep_args_t& a, SweepShared& sh, int t, int L,
                                  const double* rowp) {
@@ -1111,6 +1361,8 @@ gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
             } else {
                 sweep_block_cell(a, sh, t, L, sh.s_row);
             }
+        } else if (a.ll == nullptr && a.comp != nullptr && blockDim.x == 32 * SW_PAR_WARPS) {
+            sweep_sequencer_par(a, sh);
         } else if (L < SW_MAXL && a.ldk <= SW_MAXL) {
             if (tid < 32) sweep_sequencer(a, sh);
             __syncthreads();
@@ -1791,11 +2043,14 @@ int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_i
 int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const double* lp, int K,
                      const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, const int32_t* n_cert, int C,
                      int32_t* blk, int32_t* idx_c, int32_t* st, bnpc_visit_t* visit_c,
-                     bnpc_cand_t* cand_c, double log_n, double c_norm, void* stream) {
+                     bnpc_cand_t* cand_c, double log_n, double c_norm, int32_t* comp, void* stream) {
     if (C <= 0) return 0;
     if (K <= 0 || K > BNPC_LEAN_MAXK) return bad_arg("lean epochs need K <= BNPC_LEAN_MAXK");
+    if (!comp) return bad_arg("comp");
     const int nb = cdiv(C, CAND_THREADS);
     cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t ce = cudaMemsetAsync(comp, 0, sizeof(int32_t) * 256, s);
+    if (ce != cudaSuccess) return fail("gibbs_exact memset", ce);
     gibbs_finalize_kernel<<<nb, CAND_THREADS, 0, s>>>(opt_t0, n_cert, C, blk);
     LAUNCH_CHECK("gibbs_finalize");
     compact_scan_kernel<<<1, 1024, 0, s>>>(blk, nb, st);
@@ -1806,8 +2061,10 @@ int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const
     // the number of uncertain visits lives on the device: blocks beyond it exit at once
     gibbs_exact_kernel<<<cdiv(C, EX_THREADS), EX_THREADS, smem, s>>>(
         x1, x0, W, M, reinterpret_cast<const double2*>(lp), K, visit_t0, opt_t0, idx_c, st, visit_c, cand_c,
-        log_n, c_norm);
+        log_n, c_norm, comp);
     LAUNCH_CHECK("gibbs_exact");
+    components_kernel<<<1, BNPC_LEAN_MAXK, 0, s>>>(comp, K, SW_PAR_WARPS);
+    LAUNCH_CHECK("components");
     return 0;
 }
 

@@ -164,11 +164,14 @@ gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__
                    const double2* __restrict__ lp, int K, const bnpc_visit_t* __restrict__ visit,
                    const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ idx_c,
                    int32_t* __restrict__ st, bnpc_visit_t* __restrict__ visit_c,
-                   bnpc_cand_t* __restrict__ cand_c, double slack, double c_norm) {
+                   bnpc_cand_t* __restrict__ cand_c, double slack, double c_norm, int32_t* __restrict__ comp) {
     extern __shared__ __align__(16) unsigned char ex_smem[];
+    __shared__ unsigned long long s_adj[BNPC_LEAN_MAXK];
+    __shared__ int s_num[BNPC_LEAN_MAXK];
     double2* tile = reinterpret_cast<double2*>(ex_smem);          // [32][K]
     const int n_unc = st[BNPC_ST_NUNC];
     if (blockIdx.x * EX_THREADS >= n_unc) return;
+    if (threadIdx.x < BNPC_LEAN_MAXK) { s_adj[threadIdx.x] = 0ull; s_num[threadIdx.x] = 0; }
     const int j = blockIdx.x * EX_THREADS + threadIdx.x;
     const bool live = j < n_unc;
     const int r = live ? idx_c[j] : idx_c[0];
@@ -209,7 +212,7 @@ gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__
             }
         }
     }
-    if (!live) return;
+    // (every thread stays for the block-wide publication of the option graph below)
     // same selection and weights as gibbs_candidates_kernel, on the exact values
     const double lnew_ll = v.lnew + c_norm;
     bnpc_cand_t out;
@@ -247,16 +250,87 @@ gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__
         for (int i = 0; i < BNPC_MAX_OPT; ++i)
             if (i < n) { out.e[i] = exp(val[i] - ref); e_max = fmax(e_max, out.e[i]); }
         e_new = exp(lnew_ll - ref);
-    } else {
+    } else if (live) {
         atomicAdd(&st[BNPC_ST_NMANY], 1);
     }
-    v.e_new = e_new;
-    v.ref = ref;
-    v.c_old = c_old;
-    v.n_opt = n;
-    v.i_old = i_old;
-    v.flags = 0;
-    v.e_max = __double2float_ru(e_max);
-    visit_c[j] = v;
-    cand_c[j] = out;
+    if (live) {
+        v.e_new = e_new;
+        v.ref = ref;
+        v.c_old = c_old;
+        v.n_opt = n;
+        v.i_old = i_old;
+        v.flags = 0;
+        v.e_max = __double2float_ru(e_max);
+        visit_c[j] = v;
+        cand_c[j] = out;
+        // option graph on the columns: the visit links its own cluster with every rival
+        if (nn > 0 && c_old >= 0) {
+            unsigned long long mask = 0ull;
+#pragma unroll
+            for (int i = 0; i < BNPC_MAX_OPT; ++i)
+                if (i < n) mask |= 1ull << out.col[i];
+            atomicOr(&s_adj[c_old], mask);
+            atomicAdd(&s_num[c_old], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        unsigned long long* adj = reinterpret_cast<unsigned long long*>(comp);
+        if (s_adj[threadIdx.x]) atomicOr(&adj[threadIdx.x], s_adj[threadIdx.x]);
+        if (s_num[threadIdx.x]) atomicAdd(&comp[128 + threadIdx.x], s_num[threadIdx.x]);
+    }
+}
+
+// comp layout (int32[256]): [0,128) adjacency masks (64 x uint64), [128,192) uncertain visits per
+// column, [192,256) owner warp per column.  One block of 64 threads: connected components of the
+// option graph, then the components are dealt to `n_warps` warps, heaviest first, each to the
+// warp with the least records so far.
+__global__ void __launch_bounds__(BNPC_LEAN_MAXK)
+components_kernel(int32_t* __restrict__ comp, int K, int n_warps) {
+    __shared__ unsigned long long m[BNPC_LEAN_MAXK];
+    __shared__ int weight[BNPC_LEAN_MAXK], owner[BNPC_LEAN_MAXK], load[32];
+    const int c = threadIdx.x;
+    const unsigned long long* adj = reinterpret_cast<const unsigned long long*>(comp);
+    m[c] = (c < K) ? (adj[c] | (1ull << c)) : (1ull << c);
+    __syncthreads();
+    // make the relation symmetric, then close it
+    {
+        unsigned long long x = m[c];
+        while (x) { const int d = __ffsll((long long)x) - 1; x &= x - 1; atomicOr(&m[d], 1ull << c); }
+    }
+    __syncthreads();
+    for (int it = 0; it < BNPC_LEAN_MAXK; ++it) {
+        unsigned long long x = m[c], acc = m[c];
+        while (x) { const int d = __ffsll((long long)x) - 1; x &= x - 1; acc |= m[d]; }
+        const int changed = __syncthreads_or(acc != m[c]);
+        m[c] = acc;
+        __syncthreads();
+        if (!changed) break;
+    }
+    const int root = __ffsll((long long)m[c]) - 1;
+    int wsum = 0;
+    if (root == c) {
+        unsigned long long x = m[c];
+        while (x) { const int d = __ffsll((long long)x) - 1; x &= x - 1; if (d < K) wsum += comp[128 + d]; }
+    }
+    weight[c] = (root == c) ? wsum : -1;
+    owner[c] = 0;
+    if (c < 32) load[c] = 0;
+    __syncthreads();
+    if (c == 0) {
+        for (;;) {
+            int best = -1, bw = 0;
+            for (int r = 0; r < BNPC_LEAN_MAXK; ++r)
+                if (weight[r] > bw) { bw = weight[r]; best = r; }
+            if (best < 0) break;
+            int wmin = 0;
+            for (int q = 1; q < n_warps; ++q)
+                if (load[q] < load[wmin]) wmin = q;
+            owner[best] = wmin;
+            load[wmin] += bw;
+            weight[best] = -1;
+        }
+    }
+    __syncthreads();
+    comp[192 + c] = owner[root];
 }

@@ -122,6 +122,7 @@ class DeviceCRP:
     learning = False
     lean_enabled = True           # class-wide switch (tests force the dense FP64 matrix with False)
     lean_rows = 2                 # approximate rows of lean epochs: 2 tcgen05 tensor cores, 1 FP32 FMA
+    serial_sweep = False          # lean epochs: one sequencer warp (True) or one per component group
 
     def __init__(self, data, DP_alpha=(-1, -1), param_beta=(1, 1), FN_error=EPS, FP_error=EPS,
                  device=None, rnd=None):
@@ -280,6 +281,7 @@ class DeviceCRP:
             self._dev('n_cert', _lib.LEAN_MAXK, i32, zero=True)
             self._dev('idx_c', N, i32)
             self._dev('bsplit', sh.W * 2 * _lib.LEAN_MAXK * 64, torch.int16)
+            self._dev('comp', 256, i32, zero=True)
             self._lean_ok = True
             self.members = self._dev('members', N, i32)
             self._dev('rl_tot', 8, f64)

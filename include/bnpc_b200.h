@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BNPC_ABI_VERSION 5
+#define BNPC_ABI_VERSION 6
 
 /* capacity of clusters born since the ll matrix of the current epoch was built */
 #define BNPC_MAX_EXTRA 32
@@ -173,7 +173,9 @@ int bnpc_gibbs_compact(const bnpc_visit_t* visit_t0, const bnpc_cand_t* cand_t0,
  * error bound of the approximate rows.  bnpc_gibbs_exact: finalises the certain flags (a
  * cluster never keeps a single certain visit), compacts the uncertain visits in visiting order
  * (idx_c, st[BNPC_ST_NUNC]) and writes their visit / option records with FP64 log-likelihoods in
- * the arithmetic of bnpc_ll_matrix.                                                            */
+ * the arithmetic of bnpc_ll_matrix.  comp (int32[256]) receives the option graph on the columns
+ * (which clusters share a visit), its connected components and the sequencer warp that owns
+ * each column: visits of different components never interact, the sweep walks them in parallel. */
 int bnpc_ll_matrix_f32(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
                        int cell_stride, int C, const double* lp, float* lpf, int K, float* llf,
                        int ldf, void* stream);
@@ -189,7 +191,7 @@ int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_i
 int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const double* lp, int K,
                      const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, const int32_t* n_cert, int C,
                      int32_t* blk, int32_t* idx_c, int32_t* st, bnpc_visit_t* visit_c,
-                     bnpc_cand_t* cand_c, double log_n, double c_norm, void* stream);
+                     bnpc_cand_t* cand_c, double log_n, double c_norm, int32_t* comp, void* stream);
 /* Start of an epoch: rebuild cnt[] from the host-authoritative list
  * live[2*j] = id, live[2*j+1] = size (list order), set col_of_id[id] = j and
  * clear the epoch's extra-cluster bookkeeping.  first != 0 also resets the
@@ -206,6 +208,7 @@ typedef struct {
     /* epoch */
     const double* ll /* NULL: lean epoch, exact rows are computed on demand from lp */; int32_t ldk;
     int32_t t_epoch0; const double* lp /* [K][M][2] of the epoch (lean epochs) */;
+    const int32_t* comp /* lean epochs: option-graph components (bnpc_gibbs_exact) or NULL */;
     double* lpx /* [MAX_EXTRA][M][2] */; double* llx /* [MAX_EXTRA][ldx] */; int32_t ldx;
     double* scratch /* [idcap+1] */;
     /* sweep inputs */
@@ -329,7 +332,7 @@ typedef struct {
     /* lean epochs */
     float* lpf /* [K][M][2] */; float* llf /* [N][ldf] */; bnpc_opt_t* opt /* [N] */;
     int32_t* n_cert /* [BNPC_LEAN_MAXK] */; int32_t* idx_c /* [N] */;
-    uint16_t* bsplit /* [W][2*BNPC_LEAN_MAXK][64] bf16 */;
+    uint16_t* bsplit /* [W][2*BNPC_LEAN_MAXK][64] bf16 */; int32_t* comp /* [256] */;
     /* sufficient statistics of the live clusters, list order */
     int32_t* ids; int32_t* seg; int32_t* cursor /* [K+1] each */; int32_t* members /* [N] */;
     int32_t* S1; int32_t* S0 /* [K][M] */; double* rnd /* [3][K][M] */; int32_t* declined /* [K+1] */;
@@ -354,7 +357,8 @@ typedef struct {
 typedef struct {
     int32_t first; int32_t K; int32_t t; int32_t rows; int32_t ldk; int32_t rand_ready;
     int32_t lean /* 0: dense FP64 matrix; lean epoch (K <= BNPC_LEAN_MAXK) with approximate rows
-                    from 1: FP32 FMA, 2: tcgen05 tensor cores */; int32_t pad0;
+                    from 1: FP32 FMA, 2: tcgen05 tensor cores */;
+    int32_t serial_sweep /* lean epochs: 1 = one sequencer warp instead of one per component group */;
     double c1; double c0; double lnew_prior; double c_norm; double log_n;
     double FN; double FP; double p; double q;
     uint64_t seed; uint64_t stream_id;

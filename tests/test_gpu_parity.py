@@ -98,6 +98,18 @@ def test_cuda_matches_oracle_fma_rows(fma_rows):
     test_cuda_matches_oracle_on_seeded_data(CASES[0])
 
 
+@pytest.fixture
+def serial_sweep(monkeypatch):
+    """lean epochs walked by one sequencer warp instead of one warp per component group"""
+    from bnpc_b200.engine import DeviceCRP
+    monkeypatch.setattr(DeviceCRP, 'serial_sweep', True)
+
+
+@pytest.mark.parametrize('case', [CASES[0], CASES[5], CASES[6]], ids=[CASES[0][0], CASES[5][0], CASES[6][0]])
+def test_cuda_matches_oracle_serial_sweep(case, serial_sweep):
+    test_cuda_matches_oracle_on_seeded_data(case)
+
+
 @pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
 def test_cuda_matches_oracle_on_seeded_data(case):
     name, N, M, k, miss, learning, pp, init, steps, moves = case
