@@ -20,7 +20,7 @@ HEADERS = [os.path.join(_HERE, 'csrc', 'bnpc_math.cuh'), os.path.join(_HERE, 'cs
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-fmad=false', '-std=c++17', '-shared', '-Xcompiler', '-fPIC']
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_EXTRA = 32
 ST_K, ST_TDONE, ST_FLAGS, ST_NEXTRA, ST_BIRTHS, ST_MOVED, ST_SLOW = range(7)
 ST_NUNC = 10
@@ -120,7 +120,8 @@ SIGNATURES = {
     'bnpc_gibbs_compact': [_P, _P, _I, _P, _P, _P, _P, _P],
     'bnpc_ll_matrix_f32': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P],
     'bnpc_ll_matrix_tc': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P],
-    'bnpc_gibbs_options': [_P, _I, _I, _P, _P, _P, _P, _I, _D, _D, _I, _P],
+    'bnpc_ll_matrix_i8': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _D, _P, _I, _P],
+    'bnpc_gibbs_options': [_P, _I, _I, _P, _P, _P, _P, _I, _D, _D, _I, _D, _P],
     'bnpc_gibbs_exact': [_P, _P, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _D, _D, _P, _P],
     'bnpc_gibbs_epoch_begin': [_P, _I, _P, _P, _P, _I, _P, _I, _P],
     'bnpc_gibbs_sweep': [C.POINTER(SweepArgs), _I, _P],

@@ -251,12 +251,15 @@ ll_matrix_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x
                 if ((u1 | u0) == 0u) continue;
 #pragma unroll 4
                 for (int bit = 0; bit < 32; ++bit) {
-                    const double f1 = (double)((u1 >> bit) & 1u), f0 = (double)((u0 >> bit) & 1u);
+                    // an entry selects log p1 (.x), log p0 (.y) or nothing: one addition per
+                    // entry, bit-identical to fma(f1, lp1, fma(f0, lp0, acc)) with 0/1 factors
+                    // and half its chain of dependent operations
+                    const bool b1 = (u1 >> bit) & 1u, b0 = (u0 >> bit) & 1u;
                     const double2* t = tile[q * 32 + bit];
 #pragma unroll
                     for (int kk = 0; kk < LL_KT; ++kk) {
                         const double2 v = t[kk];
-                        acc[kk] = fma(f1, v.x, fma(f0, v.y, acc[kk]));
+                        acc[kk] += b1 ? v.x : (b0 ? v.y : 0.0);
                     }
                 }
             }
@@ -280,10 +283,9 @@ __device__ __forceinline__ double cell_row_ll(const uint32_t* __restrict__ r1,
         const double2* t = lp + w * 32;
 #pragma unroll 4
         for (int bit = 0; bit < 32; ++bit) {
-            const double f1 = (double)((u1 >> bit) & 1u), f0 = (double)((u0 >> bit) & 1u);
             if ((u1 | u0) >> bit & 1u) {
                 const double2 v = t[bit];
-                acc = fma(f1, v.x, fma(f0, v.y, acc));
+                acc += ((u1 >> bit) & 1u) ? v.x : v.y;
             }
         }
     }
@@ -492,6 +494,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 #include "bnpc_lean.cuh"
 #include "bnpc_tc.cuh"
+#include "bnpc_tc_i8.cuh"
 
 #define SW_STAGE_CELLS 32
 #define SW_NSTAGE 16
@@ -2026,16 +2029,46 @@ int bnpc_ll_matrix_tc(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
     }
 }
 
+int bnpc_ll_matrix_i8(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
+                      int cell_stride, int C, const double* lp, uint8_t* bdigits, int K, double vmax,
+                      float* llf, int ldf, void* stream) {
+    if (C <= 0 || K <= 0) return 0;
+    if (K > BNPC_LEAN_MAXK) return bad_arg("tensor-core rows need K <= BNPC_LEAN_MAXK");
+    if (W % 4 != 0) return bad_arg("W must be a multiple of 4");
+    if (!(vmax > 0.0)) return bad_arg("vmax must be positive");
+    if (M >= 32768) return bad_arg("int32 accumulators hold rows of fewer than 32768 mutations");
+    const int kpad = (K + 7) & ~7;
+    if (ldf < kpad || ldf % 4 != 0) return bad_arg("ldf must be a multiple of 4, >= K rounded up to 8");
+    cudaStream_t s = (cudaStream_t)stream;
+    const double q = vmax / 65535.0;
+    const long long total = (long long)(W / 2) * 2 * kpad * 128;
+    lp_split_u8_kernel<<<cdiv(total, 256), 256, 0, s>>>(reinterpret_cast<const double2*>(lp), K, M, W, kpad, 1.0 / q,
+                                                       bdigits);
+    LAUNCH_CHECK("lp_split_u8");
+    const float nq = -(float)q;
+    switch (kpad) {
+        case 8: return launch_ll_i8<8>(x1, x0, W, cells, cell_stride, C, bdigits, nq, llf, ldf, s);
+        case 16: return launch_ll_i8<16>(x1, x0, W, cells, cell_stride, C, bdigits, nq, llf, ldf, s);
+        case 24: return launch_ll_i8<24>(x1, x0, W, cells, cell_stride, C, bdigits, nq, llf, ldf, s);
+        case 32: return launch_ll_i8<32>(x1, x0, W, cells, cell_stride, C, bdigits, nq, llf, ldf, s);
+        case 40: return launch_ll_i8<40>(x1, x0, W, cells, cell_stride, C, bdigits, nq, llf, ldf, s);
+        case 48: return launch_ll_i8<48>(x1, x0, W, cells, cell_stride, C, bdigits, nq, llf, ldf, s);
+        case 56: return launch_ll_i8<56>(x1, x0, W, cells, cell_stride, C, bdigits, nq, llf, ldf, s);
+        default: return launch_ll_i8<64>(x1, x0, W, cells, cell_stride, C, bdigits, nq, llf, ldf, s);
+    }
+}
+
 int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_id,
                        const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, int32_t* n_cert, int C,
-                       double log_n, double c_norm, int terms, void* stream) {
+                       double log_n, double c_norm, int terms, double err_abs, void* stream) {
     if (C <= 0) return 0;
     if (K <= 0 || K > BNPC_LEAN_MAXK) return bad_arg("lean epochs need K <= BNPC_LEAN_MAXK");
     cudaError_t ce = cudaMemsetAsync(n_cert, 0, sizeof(int32_t) * BNPC_LEAN_MAXK, (cudaStream_t)stream);
     if (ce != cudaSuccess) return fail("gibbs_options memset", ce);
     const float err_rel = (float)terms * 2.384185791015625e-07f;      // terms * 2^-22
     gibbs_options_kernel<<<cdiv(C, CAND_THREADS), CAND_THREADS, 0, (cudaStream_t)stream>>>(
-        llf, ldf, K, col_of_id, visit_t0, opt_t0, n_cert, C, (float)log_n, c_norm, err_rel);
+        llf, ldf, K, col_of_id, visit_t0, opt_t0, n_cert, C, (float)log_n, c_norm, err_rel,
+        0.05f + (float)(err_abs > 0.0 ? err_abs : 0.0));
     LAUNCH_CHECK("gibbs_options");
     return 0;
 }
@@ -2057,7 +2090,14 @@ int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const
     LAUNCH_CHECK("compact_scan");
     compact_index_kernel<<<nb, CAND_THREADS, 0, s>>>(opt_t0, C, blk, idx_c);
     LAUNCH_CHECK("compact_index");
-    const size_t smem = sizeof(double2) * 32 * (size_t)K;
+    const size_t smem = sizeof(double2) * 32 * EX_WORDS * (size_t)K;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ce = cudaFuncSetAttribute(gibbs_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(double2) * 32 * EX_WORDS * BNPC_LEAN_MAXK));
+        if (ce != cudaSuccess) return fail("gibbs_exact smem attribute", ce);
+        attr_done = true;
+    }
     // the number of uncertain visits lives on the device: blocks beyond it exit at once
     gibbs_exact_kernel<<<cdiv(C, EX_THREADS), EX_THREADS, smem, s>>>(
         x1, x0, W, M, reinterpret_cast<const double2*>(lp), K, visit_t0, opt_t0, idx_c, st, visit_c, cand_c,

@@ -75,11 +75,13 @@ ll_matrix_f32_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict
 
 // err_rel = (number of summed terms) * 2^-22: every term of a row sum is <= 0, so partial sums
 // never exceed the total in magnitude and FP32 accumulation (rounded or truncated, in any order)
-// is off by at most terms * 2^-23 * |sum|; the factor 2 and the constant are head-room.
+// is off by at most terms * 2^-23 * |sum|; the factor 2 and the constant are head-room.  err_abs
+// = 0.05 + the absolute error of the rows (the quantisation of the integer rows, M * q / 2).
 __global__ void __launch_bounds__(CAND_THREADS)
 gibbs_options_kernel(const float* __restrict__ llf, int ldf, int K, const int32_t* __restrict__ col_of_id,
                      const bnpc_visit_t* __restrict__ visit, bnpc_opt_t* __restrict__ opt,
-                     int32_t* __restrict__ n_cert, int C, float slack, double c_norm, float err_rel) {
+                     int32_t* __restrict__ n_cert, int C, float slack, double c_norm, float err_rel,
+                     float err_abs) {
     __shared__ int s_cert[BNPC_LEAN_MAXK];
     if (threadIdx.x < BNPC_LEAN_MAXK) s_cert[threadIdx.x] = 0;
     __syncthreads();
@@ -93,7 +95,7 @@ gibbs_options_kernel(const float* __restrict__ llf, int ldf, int K, const int32_
         o.n_opt = BNPC_MAX_OPT + 1; o.i_old = 0; o.flags = BNPC_OPT_MANY; o.pad = 0;
         if (c_old >= 0 && c_old < K) {
             const float v_old = row[c_old];
-            const float err = err_rel * (fabsf(v_old) + 64.0f) + 0.05f;
+            const float err = err_rel * (fabsf(v_old) + 64.0f) + err_abs;
             const float thr = v_old - 40.0f - slack - 2.0f * err;
             int n = 0, i_old = 0;
             for (int k = 0; k < K; ++k) {
@@ -155,10 +157,15 @@ compact_index_kernel(const bnpc_opt_t* __restrict__ opt, int C, const int32_t* _
     idx_c[pos] = r;
 }
 
-#define EX_THREADS 256
-// One thread per uncertain visit: FP64 log-likelihood of each of its options in the arithmetic
-// of ll_matrix_kernel (mutation order, fma(f1, lp1, fma(f0, lp0, acc))), then the option weights
-// exactly as gibbs_candidates_kernel derives them from the FP64 matrix.
+#define EX_THREADS 128
+#define EX_WORDS 4            /* words of a row (128 mutations) staged per round */
+// One thread per uncertain visit: FP64 log-likelihood of each of its options, then the option
+// weights exactly as gibbs_candidates_kernel derives them from the FP64 matrix.  The row is summed
+// in four interleaved partial sums per option (word w goes to partial w % 4; the chain of dependent
+// additions is the latency bound of this kernel) that are combined as (s0 + s1) + (s2 + s3); a term
+// is the log-probability selected by the entry (adding it is what fma(1, lp, acc) does in
+// ll_matrix_kernel).  The summation order differs from ll_matrix_kernel's, i.e. values agree to
+// ~1e-13 relative, far inside the guard band of the sweep's fast draws (SW_GUARD).
 __global__ void __launch_bounds__(EX_THREADS)
 gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
                    const double2* __restrict__ lp, int K, const bnpc_visit_t* __restrict__ visit,
@@ -168,7 +175,8 @@ gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__
     extern __shared__ __align__(16) unsigned char ex_smem[];
     __shared__ unsigned long long s_adj[BNPC_LEAN_MAXK];
     __shared__ int s_num[BNPC_LEAN_MAXK];
-    double2* tile = reinterpret_cast<double2*>(ex_smem);          // [32][K]
+    double2* tile = reinterpret_cast<double2*>(ex_smem);          // [32 * EX_WORDS][K]
+    const double* tile_d = reinterpret_cast<const double*>(ex_smem);
     const int n_unc = st[BNPC_ST_NUNC];
     if (blockIdx.x * EX_THREADS >= n_unc) return;
     if (threadIdx.x < BNPC_LEAN_MAXK) { s_adj[threadIdx.x] = 0ull; s_num[threadIdx.x] = 0; }
@@ -179,39 +187,51 @@ gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__
     const bnpc_opt_t o = opt[r];
     const int nn = (live && o.n_opt <= BNPC_MAX_OPT) ? o.n_opt : 0;
     int col[BNPC_MAX_OPT];
-    double acc[BNPC_MAX_OPT];
+    double part[EX_WORDS][BNPC_MAX_OPT];
 #pragma unroll
-    for (int i = 0; i < BNPC_MAX_OPT; ++i) { col[i] = (i < nn) ? o.col[i] : 0; acc[i] = 0.0; }
+    for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+        col[i] = (i < nn) ? 2 * o.col[i] : 0;
+#pragma unroll
+        for (int q = 0; q < EX_WORDS; ++q) part[q][i] = 0.0;
+    }
     int n_max = nn;
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) n_max = max(n_max, __shfl_xor_sync(FULL, n_max, s));
-    const uint32_t* p1 = x1 + (long long)v.cell * W;
-    const uint32_t* p0 = x0 + (long long)v.cell * W;
+    const uint4* p1 = reinterpret_cast<const uint4*>(x1 + (long long)v.cell * W);
+    const uint4* p0 = reinterpret_cast<const uint4*>(x0 + (long long)v.cell * W);
     const int words = (M + 31) >> 5;
-    for (int w = 0; w < words; ++w) {
+    for (int w0 = 0; w0 < words; w0 += EX_WORDS) {
         __syncthreads();
-        for (int i = threadIdx.x; i < 32 * K; i += EX_THREADS) {
-            const int kk = i >> 5, mm = i & 31, m = w * 32 + mm;       // coalesced along mutations
+        for (int i = threadIdx.x; i < 32 * EX_WORDS * K; i += EX_THREADS) {
+            const int kk = i / (32 * EX_WORDS), mm = i % (32 * EX_WORDS), m = w0 * 32 + mm;   // coalesced along mutations
             tile[mm * K + kk] = (m < M) ? lp[(long long)kk * M + m] : make_double2(0.0, 0.0);
         }
         __syncthreads();
-        if (n_max == 0) continue;
-        const uint32_t u1 = p1[w], u0 = p0[w];
-        if (nn == 0 || (u1 | u0) == 0u) continue;
+        if (n_max == 0 || nn == 0) continue;
+        const uint4 a = p1[w0 >> 2], b = p0[w0 >> 2];         // rows are padded with zeros to W words
+        const uint32_t u1[EX_WORDS] = {a.x, a.y, a.z, a.w}, u0[EX_WORDS] = {b.x, b.y, b.z, b.w};
 #pragma unroll 2
         for (int bit = 0; bit < 32; ++bit) {
-            const double f1 = (double)((u1 >> bit) & 1u), f0 = (double)((u0 >> bit) & 1u);
-            const double2* t = tile + bit * K;
 #pragma unroll
-            for (int i = 0; i < BNPC_MAX_OPT; ++i) {
-                if (i >= n_max) break;                               // warp-uniform
-                if (i < nn) {
-                    const double2 q = t[col[i]];
-                    acc[i] = fma(f1, q.x, fma(f0, q.y, acc[i]));
+            for (int q = 0; q < EX_WORDS; ++q) {
+                const uint32_t b1 = (u1[q] >> bit) & 1u, b0 = (u0[q] >> bit) & 1u;
+                // the entry selects log p1 (.x), log p0 (.y) or nothing
+                const double* t = tile_d + (q * 32 + bit) * 2 * K + (b1 ? 0 : 1);
+                const bool any = (b1 | b0) != 0u;
+#pragma unroll
+                for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+                    if (i >= n_max) break;                               // warp-uniform
+                    if (i < nn) {
+                        const double term = t[col[i]];
+                        part[q][i] += any ? term : 0.0;
+                    }
                 }
             }
         }
     }
+    double acc[BNPC_MAX_OPT];
+#pragma unroll
+    for (int i = 0; i < BNPC_MAX_OPT; ++i) acc[i] = (part[0][i] + part[1][i]) + (part[2][i] + part[3][i]);
     // (every thread stays for the block-wide publication of the option graph below)
     // same selection and weights as gibbs_candidates_kernel, on the exact values
     const double lnew_ll = v.lnew + c_norm;

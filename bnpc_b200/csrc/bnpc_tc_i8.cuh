@@ -1,0 +1,287 @@
+// Approximate cells x clusters log-likelihood rows on the tensor cores in EXACT INTEGER
+// arithmetic (tcgen05.mma kind::i8, sm_100a): the production rows of lean Gibbs epochs.
+//
+//   llf[r][k] = sum_m x1[c][m] * LP1[k][m] + x0[c][m] * LP0[k][m],   c = cell of visit r
+//
+// The log-probabilities are quantised once per epoch to 16-bit fixed point,
+//   -LP = q * (256 * hi + lo),   q = vmax / 65535,   hi, lo in [0, 255],
+// and the two base-256 digits are separate output columns n = digit * KPAD + k, so that
+//   D[128 visits x 2*KPAD] += A[128 x 32] * B[2*KPAD x 32]^T      (u8 x u8 -> s32, K = 32)
+// accumulates integers with no rounding at all: the only error of a row is the quantisation,
+// at most (number of observed entries of the cell) * q / 2  (<= M * q / 2; bnpc_gibbs_options
+// gets it as err_abs), plus one float rounding of the result.
+//   A  the 0/1 data, one byte per entry, expanded by the producer warps from the bit-planes
+//      straight into TENSOR MEMORY (tcgen05.st; one TMEM lane per visit, four entries per 32-bit
+//      column): (word >> p) & 0x01010101 makes four matrix elements.
+//   B  the digit table in the K-major 128-byte-swizzled UMMA layout, one bulk async copy
+//      (cp.async.bulk) per stage; a stage is 256 reduction indices = 8 MMAs.
+//   D  int32 accumulators in TMEM, two sets: the epilogue of a tile overlaps the next tile.
+// Warp roles (14 warps): 0-7 produce A (TMEM lane quarter = warp % 4; warps 0-3 expand the first
+// 128 indices of every stage, warps 4-7 the second), 8-11 epilogue (TMEM -> registers -> one
+// float row per visit), 12 issues the MMAs (one thread), 13 streams B.  The 16-byte piece of a
+// visit's row that a producer thread expands per stage is prefetched T8_PF stages ahead (the
+// row gather is the long-latency part: visiting order is a random permutation of the cells),
+// across tile boundaries, with the cell indices two tiles ahead of that.
+// The order of the 32 reduction indices inside a word is a fixed permutation of the bit order
+// (element 4p+b <-> bit p+8b), the same for A and B.
+
+#define T8_NST 4                 /* pipeline stages (A in TMEM, B in shared memory) */
+#define T8_THREADS 448
+#define T8_A_COL0 256            /* first TMEM column of the A stages (accumulators use [0, 256)) */
+#define T8_A_STAGE_COLS 64       /* 256 one-byte entries per visit and stage */
+#define T8_PF 4                  /* row-piece prefetch depth, in stages */
+
+// D[tmem_d] (+)= A[tmem_a] * B[smem desc]: kind::i8 (u8 x u8 -> s32), A from tensor memory
+__device__ __forceinline__ void tc_mma_ts_i8(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Digit table: B chunk kc (128 reduction indices = two 64-bit pieces of one plane) x N rows x 128
+// bytes, each chunk stored exactly as its shared-memory image (K-major, 128-byte swizzle: 8-row
+// groups of 1024 bytes, the 16-byte piece c of row n at piece position c ^ (n & 7)).
+__global__ void lp_split_u8_kernel(const double2* __restrict__ lp, int K, int M, int W, int KPAD, double inv_q,
+                                   uint8_t* __restrict__ Bg) {
+    const int N = 2 * KPAD;
+    const long long total = (long long)(W / 2) * N * 128;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int e = (int)(idx & 127);
+    const int n = (int)((idx >> 7) % N);
+    const int kc = (int)(idx / (128ll * N));
+    const int digit = n / KPAD, k = n % KPAD;
+    const int half = W / 2;                                  // 64-bit pieces per plane
+    const int c0 = 2 * kc;                                   // first 64-bit piece of the chunk
+    const int plane = c0 >= half;
+    const int j = plane ? c0 - half : c0;
+    const int q = e >> 5, p = (e & 31) >> 2, b = e & 3;      // element 32q + 4p + b <-> word q, bit p + 8b
+    const int m = (2 * j + q) * 32 + p + 8 * b;
+    int iv = 0;
+    if (k < K && m < M) {
+        const double2 t = lp[(long long)k * M + m];
+        const double v = plane ? t.y : t.x;                  // <= 0
+        iv = (int)rint(-v * inv_q);
+        iv = iv < 0 ? 0 : (iv > 65535 ? 65535 : iv);
+    }
+    const int out = digit == 0 ? (iv >> 8) : (iv & 255);
+    const long long off = (long long)kc * N * 128 + (n >> 3) * 1024 + (n & 7) * 128 + (((e >> 4) ^ (n & 7)) << 4) + (e & 15);
+    Bg[off] = (uint8_t)out;
+}
+
+template <int KPAD>
+__global__ void __launch_bounds__(T8_THREADS, 1)
+ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W,
+                    const int32_t* __restrict__ cells, int cell_stride, int C,
+                    const uint8_t* __restrict__ Bg, float neg_q, float* __restrict__ llf, int ldf) {
+    constexpr int N = 2 * KPAD;
+    constexpr uint32_t B_CHUNK_BYTES = (uint32_t)N * 128u;          // 128 reduction indices
+    constexpr uint32_t B_STAGE_BYTES = 2u * B_CHUNK_BYTES;
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(tc_smem + T8_NST * B_STAGE_BYTES);
+    uint64_t* empty = full + T8_NST;
+    uint64_t* acc_full = empty + T8_NST;                    // [2]
+    uint64_t* acc_empty = acc_full + 2;                     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the row of a visit is 2 planes x W words = W pieces of 64 bits; a stage is 4 pieces
+    const int half = W / 2;
+    const int n_stages = W / 4;
+    const int n_tiles = (C + 127) / 128;
+    const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T8_NST; ++s) { mbar_init(&full[s], 9); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 8) {
+        // ---- A producers: one TMEM lane = one visit; group g = warp / 4 expands pieces
+        // [2g, 2g+2) of every stage (one aligned 16-byte load) ----
+        const int g = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const long long total = (long long)my_tiles * n_stages;
+        // prefetch cursor: runs T8_PF stages ahead of the stage being expanded
+        long long pf_q = 0;
+        int pf_sidx = 0, pf_tile = blockIdx.x;
+        auto cell_of_tile = [&](int tile) -> long long {     // -1: no such visit
+            const long long r = (long long)tile * 128 + row;
+            if (tile >= n_tiles || r >= C) return -1;
+            return cells ? (long long)__ldg(cells + r * cell_stride) : r;
+        };
+        long long cell_cur = cell_of_tile(pf_tile);
+        long long cell_n1 = cell_of_tile(pf_tile + gridDim.x);
+        long long cell_n2 = cell_of_tile(pf_tile + 2 * gridDim.x);
+        auto pf_load = [&]() -> uint4 {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (pf_q < total) {
+                if (cell_cur >= 0) {
+                    const int c = pf_sidx * 4 + 2 * g;        // first of this thread's two pieces
+                    const uint32_t* src = (c < half) ? x1 + cell_cur * W + 2 * c : x0 + cell_cur * W + 2 * (c - half);
+                    v = __ldg(reinterpret_cast<const uint4*>(src));
+                }
+                ++pf_q;
+                if (++pf_sidx == n_stages) {
+                    pf_sidx = 0;
+                    pf_tile += gridDim.x;
+                    cell_cur = cell_n1;
+                    cell_n1 = cell_n2;
+                    cell_n2 = cell_of_tile(pf_tile + 2 * gridDim.x);
+                }
+            }
+            return v;
+        };
+        uint4 ring[T8_PF];
+#pragma unroll
+        for (int j = 0; j < T8_PF; ++j) ring[j] = pf_load();
+        uint32_t it = 0;
+        for (long long q0 = 0; q0 < total; q0 += T8_PF) {
+#pragma unroll
+            for (int j = 0; j < T8_PF; ++j) {
+                if (q0 + j < total) {
+                    const uint4 w = ring[j];
+                    ring[j] = pf_load();
+                    const int slot = it % T8_NST;
+                    uint32_t regs[32];
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        regs[p] = (w.x >> p) & 0x01010101u;
+                        regs[8 + p] = (w.y >> p) & 0x01010101u;
+                        regs[16 + p] = (w.z >> p) & 0x01010101u;
+                        regs[24 + p] = (w.w >> p) & 0x01010101u;
+                    }
+                    if (it >= T8_NST) mbar_wait(&empty[slot], ((it / T8_NST) - 1) & 1);
+                    tc_fence_after();
+                    const uint32_t dst = tmem + T8_A_COL0 + slot * T8_A_STAGE_COLS + g * 32 + lane_base;
+                    tc_st32(dst, regs);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[slot]);
+                    ++it;
+                }
+            }
+        }
+    } else if (warp < 12) {
+        // ---- epilogue: D lane `row`, columns [0, N) of the tile's accumulator set ----
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t tile_count = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_count) {
+            const uint32_t set = tile_count & 1u;
+            mbar_wait(&acc_full[set], (tile_count >> 1) & 1);
+            tc_fence_after();
+            float acc[KPAD];
+#pragma unroll
+            for (int c = 0; c < KPAD / 8; ++c) {
+                uint32_t hi[8], lo[8];
+                tc_ld8(tmem + lane_base + set * N + c * 8, hi);
+                tc_ld8(tmem + lane_base + set * N + KPAD + c * 8, lo);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    acc[c * 8 + i] = neg_q * (float)(int)((hi[i] << 8) + lo[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[set]);
+            const long long r = (long long)tile * 128 + row;
+            if (r < C) {
+                float4* dst = reinterpret_cast<float4*>(llf + r * ldf);
+#pragma unroll
+                for (int i = 0; i < KPAD / 4; ++i)
+                    dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+            }
+        }
+    } else if (warp == 12) {
+        // ---- MMA issuer ----
+        if (lane == 0) {
+            // instruction descriptor: D s32, A/B u8, both K-major, N, M = 128
+            const uint32_t idesc = (2u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+            uint32_t it = 0, tile_count = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_count) {
+                const uint32_t set = tile_count & 1u;
+                if (tile_count >= 2) mbar_wait(&acc_empty[set], ((tile_count >> 1) - 1) & 1);
+                tc_fence_after();
+                for (int sidx = 0; sidx < n_stages; ++sidx, ++it) {
+                    const int slot = it % T8_NST;
+                    mbar_wait(&full[slot], (it / T8_NST) & 1);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(tc_smem + slot * B_STAGE_BYTES);
+                    const uint32_t a_addr = tmem + T8_A_COL0 + slot * T8_A_STAGE_COLS;
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        // K-major, 128B swizzle: LBO 1, SBO 1024 B, version 1, layout type 2
+                        const uint64_t desc0 = (uint64_t)(((b_addr + cc * B_CHUNK_BYTES) >> 4) & 0x3FFFu) |
+                                               (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            tc_mma_ts_i8(tmem + set * N, a_addr + cc * 32 + j * 8, desc0 + (uint64_t)(2 * j), idesc,
+                                         (sidx | cc | j) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&empty[slot]);
+                }
+                tc_commit(&acc_full[set]);
+            }
+        }
+    } else {
+        // ---- B loader ----
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int sidx = 0; sidx < n_stages; ++sidx, ++it) {
+                    const int slot = it % T8_NST;
+                    if (it >= T8_NST) mbar_wait(&empty[slot], ((it / T8_NST) - 1) & 1);
+                    mbar_expect_tx(&full[slot], B_STAGE_BYTES);
+                    bulk_g2s(tc_smem + slot * B_STAGE_BYTES, Bg + (long long)sidx * B_STAGE_BYTES, B_STAGE_BYTES,
+                             &full[slot]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+template <int KPAD>
+static int launch_ll_i8(const uint32_t* x1, const uint32_t* x0, int W, const int32_t* cells, int cell_stride,
+                        int C, const uint8_t* Bg, float neg_q, float* llf, int ldf, cudaStream_t s) {
+    const size_t smem = (size_t)T8_NST * 2 * (2 * KPAD) * 128 + 256;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(ll_matrix_i8_kernel<KPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return fail("ll_matrix_i8 smem attribute", e);
+        attr_done = true;
+    }
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int tiles = cdiv(C, 128);
+    ll_matrix_i8_kernel<KPAD><<<tiles < sms ? tiles : sms, T8_THREADS, smem, s>>>(x1, x0, W, cells, cell_stride, C,
+                                                                                 Bg, neg_q, llf, ldf);
+    LAUNCH_CHECK("ll_matrix_i8");
+    return 0;
+}

@@ -121,7 +121,7 @@ class DeviceCRP:
 
     learning = False
     lean_enabled = True           # class-wide switch (tests force the dense FP64 matrix with False)
-    lean_rows = 2                 # approximate rows of lean epochs: 2 tcgen05 tensor cores, 1 FP32 FMA
+    lean_rows = 3                 # approximate rows of lean epochs: 3 tcgen05 integer digits, 2 tcgen05 bf16-split, 1 FP32 FMA
     serial_sweep = False          # lean epochs: one sequencer warp (True) or one per component group
 
     def __init__(self, data, DP_alpha=(-1, -1), param_beta=(1, 1), FN_error=EPS, FP_error=EPS,

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BNPC_ABI_VERSION 6
+#define BNPC_ABI_VERSION 7
 
 /* capacity of clusters born since the ll matrix of the current epoch was built */
 #define BNPC_MAX_EXTRA 32
@@ -185,9 +185,19 @@ int bnpc_ll_matrix_f32(const uint32_t* x1, const uint32_t* x0, int W, int M, con
 int bnpc_ll_matrix_tc(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
                       int cell_stride, int C, const double* lp, uint16_t* bsplit, int K, float* llf,
                       int ldf, void* stream);
+/* The same rows on the tensor cores in exact integer arithmetic (tcgen05.mma kind::i8): -lp is
+ * quantised to 16-bit fixed point with step q = vmax / 65535 (the caller guarantees |lp| <= vmax;
+ * larger entries are clamped), the two base-256 digits are separate columns (bdigits: scratch of
+ * W * Kp * 128 bytes), int32 accumulators.  A row is off by at most (observed entries) * q / 2
+ * (<= M * q / 2: pass it to bnpc_gibbs_options as err_abs) plus one float rounding.  M < 32768. */
+int bnpc_ll_matrix_i8(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
+                      int cell_stride, int C, const double* lp, uint8_t* bdigits, int K, double vmax,
+                      float* llf, int ldf, void* stream);
+/* err_abs: absolute error of the approximate rows on top of the FP32 accumulation bound (0 for the
+ * float rows). */
 int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_id,
                        const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, int32_t* n_cert, int C,
-                       double log_n, double c_norm, int terms, void* stream);
+                       double log_n, double c_norm, int terms, double err_abs, void* stream);
 int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const double* lp, int K,
                      const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, const int32_t* n_cert, int C,
                      int32_t* blk, int32_t* idx_c, int32_t* st, bnpc_visit_t* visit_c,
@@ -357,7 +367,7 @@ typedef struct {
 typedef struct {
     int32_t first; int32_t K; int32_t t; int32_t rows; int32_t ldk; int32_t rand_ready;
     int32_t lean /* 0: dense FP64 matrix; lean epoch (K <= BNPC_LEAN_MAXK) with approximate rows
-                    from 1: FP32 FMA, 2: tcgen05 tensor cores */;
+                    from 1: FP32 FMA, 2: tcgen05 bf16-split, 3: tcgen05 integer digits */;
     int32_t serial_sweep /* lean epochs: 1 = one sequencer warp instead of one per component group */;
     double c1; double c0; double lnew_prior; double c_norm; double log_n;
     double FN; double FP; double p; double q;

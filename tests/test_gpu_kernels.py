@@ -233,7 +233,7 @@ def test_gather_members_and_anchor_swaps(L):
 
 
 @pytest.mark.parametrize('shape', [(300, 128, 5), (5000, 1000, 24), (4096, 640, 64), (777, 50, 40)])
-@pytest.mark.parametrize('rows', ['tcgen05', 'fp32_fma'])
+@pytest.mark.parametrize('rows', ['tcgen05', 'tcgen05_i8', 'fp32_fma'])
 def test_approximate_rows_within_their_error_bound(L, shape, rows):
     """The approximate log-likelihood rows of lean epochs (tcgen05 tensor cores, bf16-split
     operands, FP32 accumulation; FP32-FMA reference kernel) against the FP64 matrix.  The bound
@@ -257,6 +257,12 @@ def test_approximate_rows_within_their_error_bound(L, shape, rows):
         scratch = torch.zeros(W * 2 * kp * 64, dtype=torch.int16, device='cuda')
         L.ll_matrix_tc(x1.data_ptr(), x0.data_ptr(), W, M, cells.data_ptr(), 1, N, lp.data_ptr(),
                        scratch.data_ptr(), K, llf.data_ptr(), kp, sp())
+    elif rows == 'tcgen05_i8':
+        # integer digits: exact accumulation, the error is the 16-bit quantisation of the table
+        vmax = float(lp.abs().max().item()) * 1.0001
+        scratch = torch.zeros(W * kp * 128, dtype=torch.uint8, device='cuda')
+        L.ll_matrix_i8(x1.data_ptr(), x0.data_ptr(), W, M, cells.data_ptr(), 1, N, lp.data_ptr(),
+                       scratch.data_ptr(), K, vmax, llf.data_ptr(), kp, sp())
     else:
         scratch = torch.zeros(2 * K * M, dtype=torch.float32, device='cuda')
         L.ll_matrix_f32(x1.data_ptr(), x0.data_ptr(), W, M, cells.data_ptr(), 1, N, lp.data_ptr(),
@@ -266,5 +272,12 @@ def test_approximate_rows_within_their_error_bound(L, shape, rows):
     got = llf.cpu().numpy()[:, :K].astype(np.float64)
     assert not np.isnan(got).any()
     bound = 2 * M * 2.0 ** -22 * (np.abs(want) + 64) + 0.05
+    if rows == 'tcgen05_i8':
+        # what bnpc_chain_gibbs_epoch passes as err_abs, and the sharper statement: at most half a
+        # quantisation step per observed entry plus the float rounding of the result
+        bound = bound + M * (vmax / 65535) / 2
+        observed = (~np.isnan(data)).sum(axis=1)[cells.cpu().numpy()][:, None]
+        sharp = observed * (vmax / 65535) / 2 + 2.0 ** -22 * np.abs(want) + 1e-9
+        assert (np.abs(got - want) <= sharp).all()
     assert (np.abs(got - want) <= bound).all()
-    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max() + 1e-3
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max() + 1e-3 + (0.02 if rows == 'tcgen05_i8' else 0)

@@ -99,6 +99,18 @@ def test_cuda_matches_oracle_fma_rows(fma_rows):
 
 
 @pytest.fixture
+def bf16_rows(monkeypatch):
+    """lean epochs with the bf16-split tcgen05 rows instead of the integer-digit rows"""
+    from bnpc_b200.engine import DeviceCRP
+    monkeypatch.setattr(DeviceCRP, 'lean_rows', 2)
+
+
+@pytest.mark.parametrize('case', [CASES[0], CASES[6]], ids=[CASES[0][0], CASES[6][0]])
+def test_cuda_matches_oracle_bf16_rows(case, bf16_rows):
+    test_cuda_matches_oracle_on_seeded_data(case)
+
+
+@pytest.fixture
 def serial_sweep(monkeypatch):
     """lean epochs walked by one sequencer warp instead of one warp per component group"""
     from bnpc_b200.engine import DeviceCRP
