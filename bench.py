@@ -354,14 +354,17 @@ def run_gpu(args, cfg):
         avg_ms = float(np.mean(ktimes[name]))
         if name == 'll_matrix':
             ach = alg[name]['flops'] / (avg_ms * 1e-3) / 1e12
-            return dict(kernel='ll_matrix_tc_kernel (tcgen05 likelihood rows)', bound='tensor', achieved=ach,
+            return dict(kernel='ll_matrix_i8_kernel (tcgen05 kind::i8 likelihood rows) + its digit-table kernel',
+                        bound='tensor', achieved=ach,
                         peak=bf16_peak, unit='TFLOP/s', frac=ach / bf16_peak,
-                        traffic=traffic.get('ll_matrix_tc_kernel'), peak_source=peak_src, avg_launch_ms=avg_ms,
+                        traffic=traffic.get('ll_matrix_i8_kernel'), peak_source=peak_src, avg_launch_ms=avg_ms,
                         algorithmic_flops_per_launch=alg[name]['flops'],
                         algorithmic_bytes_per_launch=alg[name]['bytes'],
                         hbm_frac=alg[name]['bytes'] / (avg_ms * 1e-3) / 1e9 / hbm_peak,
-                        note='algorithmic flops 4*N*M*K; the kernel executes 2 bf16 split terms per '
-                             'log-probability and pads K to a multiple of 8')
+                        note='algorithmic flops 4*N*M*K; the kernel executes two base-256 digits per '
+                             'log-probability on the int8 tensor pipe (nominal peak 2 x bf16) and pads K to a '
+                             'multiple of 8: algorithmic flops / measured bf16 peak = executed int8 ops / '
+                             '(2 x measured bf16 peak)')
         ach = alg[name]['bytes'] / (avg_ms * 1e-3) / 1e9
         return dict(kernel='gibbs_sweep_kernel', bound='hbm', achieved=ach, peak=hbm_peak, unit='GB/s',
                     frac=ach / hbm_peak, traffic=traffic.get('gibbs_sweep_kernel'), peak_source=peak_src,

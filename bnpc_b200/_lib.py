@@ -120,6 +120,7 @@ SIGNATURES = {
     'bnpc_gibbs_compact': [_P, _P, _I, _P, _P, _P, _P, _P],
     'bnpc_ll_matrix_f32': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P],
     'bnpc_ll_matrix_tc': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P],
+    'bnpc_debug_set_trace': [_P],
     'bnpc_ll_matrix_i8': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _D, _P, _I, _P],
     'bnpc_gibbs_options': [_P, _I, _I, _P, _P, _P, _P, _I, _D, _D, _I, _D, _P],
     'bnpc_gibbs_exact': [_P, _P, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _D, _D, _P, _P],

@@ -618,6 +618,93 @@ __device__ int sweep_exact_cell(const bnpc_sweep_args_t& a, SweepShared& sh, con
     return 1;
 }
 
+// The same for lists of 32..63 clusters: every lane holds list positions `lane` and `lane + 32`
+// (the live list itself stays in shared memory).  Panel-like data (short rows, many plausible
+// clusters per cell) sends most visits here.
+__device__ int sweep_exact_cell2(const bnpc_sweep_args_t& a, SweepShared& sh, const bnpc_visit_t& v,
+                                 const double* row, int t, int& L) {
+    const int lane = threadIdx.x;
+    const int old = v.old;
+    int lo = -1;
+    {
+        const unsigned m0 = __ballot_sync(FULL, lane < L && sh.s_id[lane] == old);
+        const unsigned m1 = __ballot_sync(FULL, lane + 32 < L && sh.s_id[lane + 32] == old);
+        lo = m0 ? (__ffs(m0) - 1) : (m1 ? 32 + __ffs(m1) - 1 : -1);
+    }
+    if (lo >= 0 && sh.s_cnt[lo] == 1) {
+        // the cluster dies with its last cell: close the gap, list order stays insertion order
+        int id_[2], cnt_[2], src_[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int p = lane + 32 * h;
+            const bool mv = p >= lo && p < L - 1;
+            id_[h] = mv ? sh.s_id[p + 1] : 0; cnt_[h] = mv ? sh.s_cnt[p + 1] : 0; src_[h] = mv ? sh.s_src[p + 1] : 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int p = lane + 32 * h;
+            if (p >= lo && p < L - 1) {
+                sh.s_id[p] = id_[h]; sh.s_cnt[p] = cnt_[h]; sh.s_src[p] = src_[h];
+                a.lst[p] = id_[h];
+            } else if (p == L - 1) {
+                sh.s_id[p] = -1; sh.s_cnt[p] = 0; sh.s_src[p] = -1;
+            }
+        }
+        if (lane == 0) a.cnt[old] = 0;
+        --L;
+        lo = -1;
+        __syncwarp();
+        sweep_rebuild_maps(sh, L);
+    }
+    double l[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int p = lane + 32 * h;
+        l[h] = -BNPC_INF;
+        if (p < L) {
+            const int src = sh.s_src[p], cnt = sh.s_cnt[p];
+            const double val = (src >= 0) ? row[src] : a.llx[(long long)(-src - 2) * a.ldx + (t - a.t_epoch0)];
+            l[h] = val + (a.logn[(p == lo) ? cnt - 1 : cnt] - a.c_norm);
+        } else if (p == L) {
+            l[h] = v.lnew;
+        }
+    }
+    // libs/CRP.py:88-100 + numpy choice over L + 1 entries
+    const bool in0 = lane <= L, in1 = lane + 32 <= L;
+    const double lmax = warp_max(fmax(in0 ? l[0] : -BNPC_INF, in1 ? l[1] : -BNPC_INF));
+    const double d0 = l[0] - lmax, d1 = l[1] - lmax;
+    double S = warp_sum((in0 ? exp(d0) : 0.0) + (in1 ? exp(d1) : 0.0)) - 1.0;
+    if (S < 0.0) S = 0.0;
+    const double lse = log1p(S);
+    const double p0 = in0 ? exp(fmin(fmax(d0 - lse, kLogEps), 0.0)) : 0.0;
+    const double p1 = in1 ? exp(fmin(fmax(d1 - lse, kLogEps), 0.0)) : 0.0;
+    const double cdf0 = warp_scan_incl(p0, lane);
+    const double cdf1 = warp_scan_incl(p1, lane) + __shfl_sync(FULL, cdf0, 31);
+    const double total = (L < 32) ? __shfl_sync(FULL, cdf0, L & 31) : __shfl_sync(FULL, cdf1, (L - 32) & 31);
+    const unsigned g0 = __ballot_sync(FULL, in0 && (cdf0 / total > v.u));
+    const unsigned g1 = __ballot_sync(FULL, in1 && (cdf1 / total > v.u));
+    const int pick = g0 ? (__ffs(g0) - 1) : (g1 ? 32 + __ffs(g1) - 1 : L);
+    if (pick == lo) return 0;
+    if (lane == 0) {
+        if (lo >= 0) {                                  // leave the old cluster
+            const int c = sh.s_cnt[lo] - 1;
+            sh.s_cnt[lo] = c;
+            a.cnt[old] = c;
+        }
+        if (pick == L) {
+            sh.pending = 1; sh.birth_cell = v.cell; sh.birth_t = t;
+        } else {
+            const int c = sh.s_cnt[pick] + 1, idp = sh.s_id[pick];
+            sh.s_cnt[pick] = c;
+            a.cnt[idp] = c;
+            a.assign[v.cell] = idp;
+        }
+    }
+    __syncwarp();
+    return pick == L ? 2 : 1;
+}
+
 #define OUT_STAY 0
 #define OUT_MOVE 1
 #define OUT_COMPLEX 2
@@ -842,13 +929,15 @@ __device__ void sweep_sequencer(const bnpc_sweep_args_t& a, SweepShared& sh) {
             const int f = fb;
             const int t_f = __shfl_sync(FULL, v.t, f);
             ++slow;
-            if (lean || L > 31) {                   // CTA-wide work (exact row / exact draw), then come back
+            if (lean || L > 63) {                   // CTA-wide work (exact row / exact draw), then come back
                 if (lane == 0) sh.pending = lean ? 3 : 2;
                 next_t = t_f; next_rec = rec0 + f + 1;
                 leave = true;
                 break;
             }
-            const int status = sweep_exact_cell(a, sh, vis[f], a.ll + (long long)(t_f - a.t_epoch0) * ldk, t_f, L);
+            const double* row_f = a.ll + (long long)(t_f - a.t_epoch0) * ldk;
+            const int status = (L > 31) ? sweep_exact_cell2(a, sh, vis[f], row_f, t_f, L)
+                                        : sweep_exact_cell(a, sh, vis[f], row_f, t_f, L);
             if (status) ++moved;
             if (status == 2 || (compact && status != 0)) {
                 // a birth, or (compact mode) sizes changed outside the batched bookkeeping:
@@ -1350,10 +1439,11 @@ gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
                                             reinterpret_cast<const double2*>(a.lp) + (long long)col * a.M);
             }
             __syncthreads();
-            if (L <= 31) {
+            if (L <= 63) {
                 if (tid < 32) {
                     int L2 = L;
-                    const int status = sweep_exact_cell(a, sh, a.visit[t], sh.s_row, t, L2);
+                    const int status = (L > 31) ? sweep_exact_cell2(a, sh, a.visit[t], sh.s_row, t, L2)
+                                                : sweep_exact_cell(a, sh, a.visit[t], sh.s_row, t, L2);
                     if (tid == 0) {
                         sh.L = L2;
                         sh.t = t + 1;
@@ -1816,47 +1906,83 @@ __global__ void rg_prepare_kernel(const double* __restrict__ ll2, int ldk, int n
 }
 
 #define RG_CHUNK 1024
-// the sequential integer pass: one thread, inputs streamed through shared memory by bulk copies
+#define RG_NEUTRAL (RG_FORCE_0 * 2)     /* padding record: the cell is on side 0 and stays there */
+// The sequential integer pass x -> x - b + [x - b >= tau] over the cells of a scan, by one warp
+// in chunks of 1024 cells.  Lane l walks cells [32 l, 32 l + 32) of the chunk from a GUESS of
+// the running count at its first cell and records how far the count could have been off without
+// changing any of its 32 decisions (a step is monotone in x, so a segment is a pure shift on that
+// interval).  A prefix sum of the segments' net changes then gives every lane its true start as
+// long as all lanes before it were inside their intervals; the lanes up to the first one that
+// was not are final, the others walk again from the corrected starts.  Every round finalises at
+// least one lane (the first open lane starts from an exact value), typically all 32.
 __global__ void __launch_bounds__(32)
 rg_serial_kernel(const int32_t* __restrict__ half, int nf, int32_t* __restrict__ work, int out_off) {
-    __shared__ alignas(128) int32_t buf[2][RG_CHUNK];
-    __shared__ alignas(8) uint64_t bar[2];
+    __shared__ int32_t pin[32 * 33], pout[32 * 33];
     const int lane = threadIdx.x;
     int ones = 0;
     for (int s = lane; s < nf; s += 32) ones += half[s];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ones += __shfl_xor_sync(FULL, ones, o);
-    if (lane != 0) return;
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const int n_chunks = (nf + RG_CHUNK - 1) / RG_CHUNK;
-    auto issue = [&](int g) {
-        const int cnt = min(RG_CHUNK, nf - g * RG_CHUNK);
-        const uint32_t bytes = ((uint32_t)cnt * 4u + 15u) & ~15u;
-        mbar_expect_tx(&bar[g & 1], bytes);
-        bulk_g2s(buf[g & 1], work + (long long)g * RG_CHUNK, bytes, &bar[g & 1]);
-    };
-    if (n_chunks > 0) issue(0);
     int32_t* out = work + out_off;
-    for (int g = 0; g < n_chunks; ++g) {
-        if (g + 1 < n_chunks) issue(g + 1);
-        long long spins = 0;
-        while (!mbar_try_wait(&bar[g & 1], (uint32_t)((g >> 1) & 1))) {
-            if (++spins > (1ll << 24)) return;
-        }
-        const int cnt = min(RG_CHUNK, nf - g * RG_CHUNK);
-        const int32_t* b = buf[g & 1];
-        int32_t* o = out + (long long)g * RG_CHUNK;
+    int x0 = ones;                                 // the count before the first cell of the chunk
+    for (int base = 0; base < nf; base += RG_CHUNK) {
+        const int cnt = min(RG_CHUNK, nf - base);
 #pragma unroll 8
-        for (int i = 0; i < cnt; ++i) {
-            const int v = b[i];
-            const int ex = ones - (v & 1);
-            const int side = (ex >= (v >> 1)) ? 1 : 0;
-            ones = ex + side;
-            o[i] = ex * 2 + side;
+        for (int i = 0; i < 32; ++i) {             // segment i, position lane (bank-conflict-free both ways)
+            const int e = i * 32 + lane;
+            pin[i * 33 + lane] = (e < cnt) ? work[base + e] : RG_NEUTRAL;
         }
+        __syncwarp();
+        int first = 0, guess = x0, start0 = x0, shift = 0;
+        int x_end = x0;
+        for (int round = 0; round < 33 && first < 32; ++round) {
+            int x = guess, up = 0x3fffffff, dn = 0x3fffffff;
+            if (lane >= first) {
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) {
+                    const int v = pin[lane * 33 + i];
+                    const int ex = x - (v & 1), tau = v >> 1;
+                    const int side = (ex >= tau) ? 1 : 0;
+                    if (side) dn = min(dn, ex - tau); else up = min(up, tau - ex - 1);
+                    x = ex + side;
+                    pout[lane * 33 + i] = ex * 2 + side;
+                }
+            }
+            const int delta = (lane >= first) ? x - guess : 0;
+            int incl = delta;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int start = start0 + incl - delta;          // true start if all open lanes before are valid
+            const int d = start - guess;
+            const bool valid = lane < first || (d >= -dn && d <= up);
+            const unsigned bad = __ballot_sync(FULL, !valid);
+            const int f = bad ? (__ffs(bad) - 1) : 32;
+            if (lane >= first && lane < f) shift = d;          // final: decisions stand, counts move by d
+            // the value after the last final lane = the exact start of lane f
+            const int end_true = start + delta;                // valid for lanes < f
+            const int nxt = __shfl_sync(FULL, end_true, f > 0 ? f - 1 : 0);
+            if (f == 32) { x_end = nxt; }
+            else {
+                if (lane >= f) guess = start;                  // corrected starts (exact for lane f)
+                start0 = __shfl_sync(FULL, start, f);
+            }
+            first = f;
+        }
+        if (shift != 0) {
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) pout[lane * 33 + i] += 2 * shift;
+        }
+        __syncwarp();
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            const int e = i * 32 + lane;
+            if (e < cnt) out[base + e] = pout[i * 33 + lane];
+        }
+        __syncwarp();
+        x0 = x_end;
     }
 }
 
@@ -2027,6 +2153,11 @@ int bnpc_ll_matrix_tc(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
         case 56: return launch_ll_tc<56>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
         default: return launch_ll_tc<64>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
     }
+}
+
+int bnpc_debug_set_trace(void* buf) {
+    g_t8_trace = reinterpret_cast<long long*>(buf);
+    return 0;
 }
 
 int bnpc_ll_matrix_i8(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,

@@ -190,7 +190,7 @@ gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__
     double part[EX_WORDS][BNPC_MAX_OPT];
 #pragma unroll
     for (int i = 0; i < BNPC_MAX_OPT; ++i) {
-        col[i] = (i < nn) ? 2 * o.col[i] : 0;
+        col[i] = (i < nn) ? o.col[i] : 0;
 #pragma unroll
         for (int q = 0; q < EX_WORDS; ++q) part[q][i] = 0.0;
     }
@@ -222,7 +222,7 @@ gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__
                 for (int i = 0; i < BNPC_MAX_OPT; ++i) {
                     if (i >= n_max) break;                               // warp-uniform
                     if (i < nn) {
-                        const double term = t[col[i]];
+                        const double term = t[2 * col[i]];
                         part[q][i] += any ? term : 0.0;
                     }
                 }

@@ -75,11 +75,17 @@ __global__ void lp_split_u8_kernel(const double2* __restrict__ lp, int K, int M,
     Bg[off] = (uint8_t)out;
 }
 
+static long long* g_t8_trace = nullptr;      // debug hook (bnpc_debug_set_trace)
+
 template <int KPAD>
 __global__ void __launch_bounds__(T8_THREADS, 1)
 ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W,
                     const int32_t* __restrict__ cells, int cell_stride, int C,
-                    const uint8_t* __restrict__ Bg, float neg_q, float* __restrict__ llf, int ldf) {
+                    const uint8_t* __restrict__ Bg, float neg_q, float* __restrict__ llf, int ldf,
+                    long long* __restrict__ trace) {
+    // trace (debug, normally NULL): clock64 stamps of CTA 0 -- [0,1024) producer warp 0 (3 per
+    // stage: data expanded, previous store done + slot free, store issued), [1024,2048) MMA thread (4 per stage: stage full, first MMA issued, all issued, committed), [2048,..) epilogue warp 8 (2 per tile)
+    const bool tr = trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
     constexpr int N = 2 * KPAD;
     constexpr uint32_t B_CHUNK_BYTES = (uint32_t)N * 128u;          // 128 reduction indices
     constexpr uint32_t B_STAGE_BYTES = 2u * B_CHUNK_BYTES;
@@ -120,46 +126,59 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const long long total = (long long)my_tiles * n_stages;
-        // prefetch cursor: runs T8_PF stages ahead of the stage being expanded
+        // prefetch cursor: runs T8_PF stages ahead of the stage being expanded.  Every load is
+        // issued unconditionally from a valid address (row 0 stands in for visits that do not
+        // exist) straight into its ring register, and masked when it is consumed: a select or a
+        // branch at the load would make the load's latency part of the iteration.
         long long pf_q = 0;
         int pf_sidx = 0, pf_tile = blockIdx.x;
-        auto cell_of_tile = [&](int tile) -> long long {     // -1: no such visit
+        auto row_of_tile = [&](int tile, bool& ok) -> long long {
             const long long r = (long long)tile * 128 + row;
-            if (tile >= n_tiles || r >= C) return -1;
-            return cells ? (long long)__ldg(cells + r * cell_stride) : r;
+            ok = tile < n_tiles && r < C;
+            return ok ? r : 0;
         };
-        long long cell_cur = cell_of_tile(pf_tile);
-        long long cell_n1 = cell_of_tile(pf_tile + gridDim.x);
-        long long cell_n2 = cell_of_tile(pf_tile + 2 * gridDim.x);
-        auto pf_load = [&]() -> uint4 {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        bool ok_cur, ok_n1, ok_n2;
+        long long r_cur = row_of_tile(pf_tile, ok_cur);
+        long long r_n1 = row_of_tile(pf_tile + gridDim.x, ok_n1);
+        long long r_n2 = row_of_tile(pf_tile + 2 * gridDim.x, ok_n2);
+        // cell of a row: loaded (or the row itself) -- always from a valid address
+        int cell_cur = cells ? __ldg(cells + r_cur * cell_stride) : (int)r_cur;
+        int cell_n1 = cells ? __ldg(cells + r_n1 * cell_stride) : (int)r_n1;
+        int cell_n2 = cells ? __ldg(cells + r_n2 * cell_stride) : (int)r_n2;
+        auto pf_next = [&](bool& ok) -> const uint4* {
+            ok = ok_cur && pf_q < total;
+            const int c = pf_sidx * 4 + 2 * g;               // first of this thread's two pieces
+            const long long base = (long long)cell_cur * W;
+            const uint32_t* src = (c < half) ? x1 + base + 2 * c : x0 + base + 2 * (c - half);
             if (pf_q < total) {
-                if (cell_cur >= 0) {
-                    const int c = pf_sidx * 4 + 2 * g;        // first of this thread's two pieces
-                    const uint32_t* src = (c < half) ? x1 + cell_cur * W + 2 * c : x0 + cell_cur * W + 2 * (c - half);
-                    v = __ldg(reinterpret_cast<const uint4*>(src));
-                }
                 ++pf_q;
                 if (++pf_sidx == n_stages) {
                     pf_sidx = 0;
                     pf_tile += gridDim.x;
-                    cell_cur = cell_n1;
-                    cell_n1 = cell_n2;
-                    cell_n2 = cell_of_tile(pf_tile + 2 * gridDim.x);
+                    cell_cur = cell_n1; ok_cur = ok_n1;
+                    cell_n1 = cell_n2; ok_n1 = ok_n2;
+                    r_n2 = row_of_tile(pf_tile + 2 * gridDim.x, ok_n2);
+                    cell_n2 = cells ? __ldg(cells + r_n2 * cell_stride) : (int)r_n2;
                 }
             }
-            return v;
+            return reinterpret_cast<const uint4*>(src);
         };
         uint4 ring[T8_PF];
+        bool ring_ok[T8_PF];
 #pragma unroll
-        for (int j = 0; j < T8_PF; ++j) ring[j] = pf_load();
+        for (int j = 0; j < T8_PF; ++j) ring[j] = __ldg(pf_next(ring_ok[j]));
+        // The store of stage s (tcgen05.st -> wait::st -> arrive) completes while the data of
+        // stage s + 1 is expanded: `pend` is the slot whose store is still in flight.
         uint32_t it = 0;
+        int pend = -1;
         for (long long q0 = 0; q0 < total; q0 += T8_PF) {
 #pragma unroll
             for (int j = 0; j < T8_PF; ++j) {
+                const uint4 raw = ring[j];
+                const bool ok = ring_ok[j];
+                ring[j] = __ldg(pf_next(ring_ok[j]));
                 if (q0 + j < total) {
-                    const uint4 w = ring[j];
-                    ring[j] = pf_load();
+                    const uint4 w = ok ? raw : make_uint4(0u, 0u, 0u, 0u);
                     const int slot = it % T8_NST;
                     uint32_t regs[32];
 #pragma unroll
@@ -169,17 +188,29 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                         regs[16 + p] = (w.z >> p) & 0x01010101u;
                         regs[24 + p] = (w.w >> p) & 0x01010101u;
                     }
+                    if (tr && warp == 0 && it < 300) trace[it * 3] = clock64();
+                    if (pend >= 0) {
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full[pend]);
+                    }
                     if (it >= T8_NST) mbar_wait(&empty[slot], ((it / T8_NST) - 1) & 1);
                     tc_fence_after();
+                    if (tr && warp == 0 && it < 300) trace[it * 3 + 1] = clock64();
                     const uint32_t dst = tmem + T8_A_COL0 + slot * T8_A_STAGE_COLS + g * 32 + lane_base;
                     tc_st32(dst, regs);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[slot]);
+                    pend = slot;
+                    if (tr && warp == 0 && it < 300) trace[it * 3 + 2] = clock64();
                     ++it;
                 }
             }
+        }
+        if (pend >= 0) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[pend]);
         }
     } else if (warp < 12) {
         // ---- epilogue: D lane `row`, columns [0, N) of the tile's accumulator set ----
@@ -190,6 +221,7 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
             const uint32_t set = tile_count & 1u;
             mbar_wait(&acc_full[set], (tile_count >> 1) & 1);
             tc_fence_after();
+            if (tr && warp == 8 && tile_count < 100) trace[2048 + tile_count * 2] = clock64();
             float acc[KPAD];
 #pragma unroll
             for (int c = 0; c < KPAD / 8; ++c) {
@@ -211,6 +243,7 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                 for (int i = 0; i < KPAD / 4; ++i)
                     dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
             }
+            if (tr && warp == 8 && tile_count < 100) trace[2048 + tile_count * 2 + 1] = clock64();
         }
     } else if (warp == 12) {
         // ---- MMA issuer ----
@@ -226,6 +259,7 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                     const int slot = it % T8_NST;
                     mbar_wait(&full[slot], (it / T8_NST) & 1);
                     tc_fence_after();
+                    if (tr && it < 250) trace[1024 + it * 4] = clock64();
                     const uint32_t b_addr = smem_u32(tc_smem + slot * B_STAGE_BYTES);
                     const uint32_t a_addr = tmem + T8_A_COL0 + slot * T8_A_STAGE_COLS;
 #pragma unroll
@@ -234,11 +268,15 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                         const uint64_t desc0 = (uint64_t)(((b_addr + cc * B_CHUNK_BYTES) >> 4) & 0x3FFFu) |
                                                (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
+                        for (int j = 0; j < 4; ++j) {
                             tc_mma_ts_i8(tmem + set * N, a_addr + cc * 32 + j * 8, desc0 + (uint64_t)(2 * j), idesc,
                                          (sidx | cc | j) != 0 ? 1u : 0u);
+                            if (tr && it < 250 && cc == 0 && j == 0) trace[1024 + it * 4 + 1] = clock64();
+                        }
                     }
+                    if (tr && it < 250) trace[1024 + it * 4 + 2] = clock64();
                     tc_commit(&empty[slot]);
+                    if (tr && it < 250) trace[1024 + it * 4 + 3] = clock64();
                 }
                 tc_commit(&acc_full[set]);
             }
@@ -281,7 +319,7 @@ static int launch_ll_i8(const uint32_t* x1, const uint32_t* x0, int W, const int
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = cdiv(C, 128);
     ll_matrix_i8_kernel<KPAD><<<tiles < sms ? tiles : sms, T8_THREADS, smem, s>>>(x1, x0, W, cells, cell_stride, C,
-                                                                                 Bg, neg_q, llf, ldf);
+                                                                                 Bg, neg_q, llf, ldf, g_t8_trace);
     LAUNCH_CHECK("ll_matrix_i8");
     return 0;
 }

@@ -21,6 +21,11 @@ import numpy as np
 import torch
 from scipy.special import gamma as _gamma_fn
 from scipy.special import gammaln, xlogy
+from scipy.special import log1p as _sc_log1p
+from scipy.special import log_ndtr as _sc_log_ndtr
+from scipy.special import ndtr as _sc_ndtr
+from scipy.special import ndtri_exp as _sc_ndtri_exp
+from scipy.stats._continuous_distns import _log_gauss_mass as _scipy_log_gauss_mass
 from scipy.stats import beta as _beta_dist
 from scipy.stats import gamma as _gamma_dist
 from scipy.stats import truncnorm as _truncnorm
@@ -36,13 +41,39 @@ _PACK_LOCK = threading.Lock()                     # chains of one model pack the
 _NORM_LOGC = np.log(np.sqrt(2 * np.pi))           # scipy _norm_pdf_logC
 
 
+def _log_gauss_mass(lo, hi):
+    """scipy.stats._continuous_distns._log_gauss_mass for scalars.  The interval of an error-rate
+    move straddles 0 (scipy's central case: log1p(-ndtr(a) - ndtr(-b))), evaluated here with the
+    same scalar special functions; the tail cases go through scipy itself."""
+    if lo <= 0 < hi:
+        return _sc_log1p(-_sc_ndtr(np.float64(lo)) - _sc_ndtr(np.float64(-hi)))
+    return np.float64(_scipy_log_gauss_mass(np.float64(lo), np.float64(hi)))
+
+
+def _tn_ppf(q, lo, hi):
+    """scipy.stats.truncnorm._ppf(q, lo, hi) for scalars (ppf_left, the case lo < 0 of an
+    error-rate move): ndtri_exp(logsumexp([log_ndtr(lo), log(q) + log_gauss_mass])) with scipy's
+    two-element logsumexp written out (log1p(exp(min - max)) + log(1) + max)."""
+    if not lo < 0:
+        return np.float64(_truncnorm._ppf(np.float64(q), np.float64(lo), np.float64(hi)))
+    t1 = _sc_log_ndtr(np.float64(lo))
+    t2 = np.log(np.float64(q)) + _log_gauss_mass(lo, hi)
+    if t1 == t2:
+        lphi = np.log1p(np.float64(0.0)) + np.log(np.float64(2.0)) + t1
+    else:
+        top, low = (t1, t2) if t1 > t2 else (t2, t1)
+        lphi = np.log1p(np.exp(low - top)) + np.float64(0.0) + top
+    return _sc_ndtri_exp(lphi)
+
+
 def _tn_logpdf(x, lo, hi, loc, scale):
     """scipy.stats.truncnorm.logpdf(x, lo, hi, loc, scale) for scalars, without the frozen /
     argument-checking machinery (same private formulas: _norm_logpdf - _log_gauss_mass)."""
     y = (x - loc) / scale
     if not (lo <= y <= hi):
         return -np.inf
-    return float(_truncnorm._logpdf(np.float64(y), np.float64(lo), np.float64(hi))) - np.log(scale)
+    y = np.float64(y)
+    return float((-y ** 2 / 2.0 - _NORM_LOGC) - _log_gauss_mass(lo, hi)) - np.log(scale)
 
 
 class _TruncNormPrior:
@@ -876,7 +907,7 @@ class DeviceCRPLearnErrors(DeviceCRP):
         u = self.rnd.random()
         with np.errstate(divide='raise', invalid='raise', over='ignore', under='ignore'):
             try:
-                prop = float(_truncnorm._ppf(np.float64(u), np.float64(lo), np.float64(hi)) * sd + cur)
+                prop = float(_tn_ppf(u, lo, hi) * sd + cur)
             except FloatingPointError:
                 prop = float(_truncnorm._ppf(np.float64(u), np.float64(lo), np.float64(np.inf)) * sd + cur)
         fwd = _tn_logpdf(prop, lo, hi, cur, sd)

@@ -190,6 +190,9 @@ int bnpc_ll_matrix_tc(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
  * larger entries are clamped), the two base-256 digits are separate columns (bdigits: scratch of
  * W * Kp * 128 bytes), int32 accumulators.  A row is off by at most (observed entries) * q / 2
  * (<= M * q / 2: pass it to bnpc_gibbs_options as err_abs) plus one float rounding.  M < 32768. */
+/* Debug hook: buf = device array of 4096 int64 (or NULL) that CTA 0 of bnpc_ll_matrix_i8 fills with
+ * clock64 stamps of its pipeline phases (tools/tc_trace.py). */
+int bnpc_debug_set_trace(void* buf);
 int bnpc_ll_matrix_i8(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
                       int cell_stride, int C, const double* lp, uint8_t* bdigits, int K, double vmax,
                       float* llf, int ldf, void* stream);
