@@ -28,7 +28,7 @@ ST_NMANY = 11
 LEAN_MAXK = 64
 OPT_BYTES = 16
 ST_WORDS = 16
-STOP_EXTRA_FULL, STOP_REPACK, STOP_TAPE_EMPTY, STOP_CAPACITY, STOP_HANG = 1, 2, 4, 8, 0x100
+STOP_EXTRA_FULL, STOP_REPACK, STOP_TAPE_EMPTY, STOP_CAPACITY, STOP_MANY, STOP_HANG = 1, 2, 4, 8, 16, 0x100
 VISIT_BYTES = 64
 VISIT_CELL_OFFSET = 32
 CAND_BYTES = 96
@@ -120,6 +120,8 @@ SIGNATURES = {
     'bnpc_gibbs_compact': [_P, _P, _I, _P, _P, _P, _P, _P],
     'bnpc_ll_matrix_f32': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P],
     'bnpc_ll_matrix_tc': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P],
+    'bnpc_cocluster_counts': [_P, _I, _I, _P, _P],
+    'bnpc_mpear_sums': [_P, _I, _P, _I, _P, _P],
     'bnpc_debug_set_trace': [_P],
     'bnpc_ll_matrix_i8': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _D, _P, _I, _P],
     'bnpc_gibbs_options': [_P, _I, _I, _P, _P, _P, _P, _I, _D, _D, _I, _D, _P],

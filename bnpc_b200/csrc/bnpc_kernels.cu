@@ -495,6 +495,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 #include "bnpc_lean.cuh"
 #include "bnpc_tc.cuh"
 #include "bnpc_tc_i8.cuh"
+#include "bnpc_estimators.cuh"
 
 #define SW_STAGE_CELLS 32
 #define SW_NSTAGE 16
@@ -1410,6 +1411,14 @@ gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
         sh.compact = (a.visit_c != nullptr && a.cand_c != nullptr && a.t_begin == a.t_epoch0 &&
                       sh.n_extra == 0) ? 1 : 0;
         sh.crec = 0;
+        // lean epoch whose visits mostly have more rivals than an option record holds (short rows,
+        // e.g. panel data): every such visit would take the exact path with an on-demand FP64 row;
+        // the dense FP64 matrix is the better route -- tell the host before anything is done
+        if (a.ll == nullptr && a.t_begin == a.t_epoch0 && !sh.stop &&
+            a.st[BNPC_ST_NMANY] > max(64, (a.t_end - a.t_begin) / 50)) {
+            sh.stop = BNPC_STOP_MANY;
+            a.st[BNPC_ST_FLAGS] = BNPC_STOP_MANY;
+        }
     }
     __syncthreads();
     if (sh.stop) return;                            // an earlier launch of this sweep stopped
@@ -2153,6 +2162,30 @@ int bnpc_ll_matrix_tc(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
         case 56: return launch_ll_tc<56>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
         default: return launch_ll_tc<64>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
     }
+}
+
+int bnpc_cocluster_counts(const int32_t* assign, int S, int N, int32_t* counts, void* stream) {
+    if (S <= 0 || N < 2) return bad_arg("cocluster_counts needs S > 0 samples of N >= 2 cells");
+    const int T = cdiv(N, EST_TILE);
+    if (T > 65535) return bad_arg("too many cells for one launch");
+    dim3 grid(T, T);
+    cocluster_counts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(assign, S, N, counts);
+    LAUNCH_CHECK("cocluster_counts");
+    return 0;
+}
+
+int bnpc_mpear_sums(const int32_t* counts, int N, const int32_t* labels, int n_cand, unsigned long long* out,
+                    void* stream) {
+    if (N < 2 || n_cand < 0) return bad_arg("mpear_sums needs N >= 2");
+    const int T = cdiv(N, EST_TILE);
+    if (T > 65535) return bad_arg("too many cells for one launch");
+    cudaError_t ce = cudaMemsetAsync(out, 0, sizeof(unsigned long long) * (1 + 2 * (size_t)n_cand),
+                                     (cudaStream_t)stream);
+    if (ce != cudaSuccess) return fail("mpear_sums memset", ce);
+    dim3 grid(T, T);
+    mpear_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(counts, N, labels, n_cand, out);
+    LAUNCH_CHECK("mpear_sums");
+    return 0;
 }
 
 int bnpc_debug_set_trace(void* buf) {

@@ -246,22 +246,28 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
             if (tr && warp == 8 && tile_count < 100) trace[2048 + tile_count * 2 + 1] = clock64();
         }
     } else if (warp == 12) {
-        // ---- MMA issuer ----
-        if (lane == 0) {
-            // instruction descriptor: D s32, A/B u8, both K-major, N, M = 128
-            const uint32_t idesc = (2u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
-            uint32_t it = 0, tile_count = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_count) {
-                const uint32_t set = tile_count & 1u;
-                if (tile_count >= 2) mbar_wait(&acc_empty[set], ((tile_count >> 1) - 1) & 1);
+        // ---- MMA issuer: the whole warp walks the loops (warp-uniform control flow and operands,
+        // so the descriptors live in uniform registers and an MMA is one instruction instead of a
+        // register-to-uniform waterfall); one elected lane issues ----
+        const uint32_t tmem_u = __shfl_sync(FULL, tmem, 0);
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        // instruction descriptor: D s32, A/B u8, both K-major, N, M = 128
+        const uint32_t idesc = (2u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+        const uint32_t smem_base = smem_u32(tc_smem);
+        uint32_t it = 0, tile_count = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_count) {
+            const uint32_t set = tile_count & 1u;
+            if (tile_count >= 2) mbar_wait(&acc_empty[set], ((tile_count >> 1) - 1) & 1);
+            tc_fence_after();
+            for (int sidx = 0; sidx < n_stages; ++sidx, ++it) {
+                const uint32_t slot = it % T8_NST;
+                mbar_wait(&full[slot], (it / T8_NST) & 1);
                 tc_fence_after();
-                for (int sidx = 0; sidx < n_stages; ++sidx, ++it) {
-                    const int slot = it % T8_NST;
-                    mbar_wait(&full[slot], (it / T8_NST) & 1);
-                    tc_fence_after();
-                    if (tr && it < 250) trace[1024 + it * 4] = clock64();
-                    const uint32_t b_addr = smem_u32(tc_smem + slot * B_STAGE_BYTES);
-                    const uint32_t a_addr = tmem + T8_A_COL0 + slot * T8_A_STAGE_COLS;
+                if (tr && it < 250) trace[1024 + it * 4] = clock64();
+                const uint32_t b_addr = smem_base + slot * B_STAGE_BYTES;
+                const uint32_t a_addr = tmem_u + T8_A_COL0 + slot * T8_A_STAGE_COLS;
+                if (leader) {
 #pragma unroll
                     for (int cc = 0; cc < 2; ++cc) {
                         // K-major, 128B swizzle: LBO 1, SBO 1024 B, version 1, layout type 2
@@ -269,7 +275,7 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                                                (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            tc_mma_ts_i8(tmem + set * N, a_addr + cc * 32 + j * 8, desc0 + (uint64_t)(2 * j), idesc,
+                            tc_mma_ts_i8(tmem_u + set * N, a_addr + cc * 32 + j * 8, desc0 + (uint64_t)(2 * j), idesc,
                                          (sidx | cc | j) != 0 ? 1u : 0u);
                             if (tr && it < 250 && cc == 0 && j == 0) trace[1024 + it * 4 + 1] = clock64();
                         }
@@ -278,8 +284,10 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                     tc_commit(&empty[slot]);
                     if (tr && it < 250) trace[1024 + it * 4 + 3] = clock64();
                 }
-                tc_commit(&acc_full[set]);
+                __syncwarp();
             }
+            if (leader) tc_commit(&acc_full[set]);
+            __syncwarp();
         }
     } else {
         // ---- B loader ----

@@ -314,6 +314,7 @@ class DeviceCRP:
             self._dev('bsplit', sh.W * 2 * _lib.LEAN_MAXK * 64, torch.int16)
             self._dev('comp', 256, i32, zero=True)
             self._lean_ok = True
+            self._lean_cooldown = 0
             self.members = self._dev('members', N, i32)
             self._dev('rl_tot', 8, f64)
             # split-merge
@@ -566,6 +567,12 @@ class DeviceCRP:
             ep.rand_ready, ep.beta_rows, ep.n_beta_rows = 0, None, 0
             ep.seed, ep.stream_id = self.rnd.device_seed, self._streams(3)
         t, first, epochs, stall = 0, 1, 0, 0
+        if not self._lean_ok:
+            # the dense route was chosen because of many-rival visits: try lean rows again after a
+            # few sweeps (the attempt costs the approximate rows only, see BNPC_STOP_MANY)
+            self._lean_cooldown -= 1
+            if self._lean_cooldown <= 0:
+                self._lean_ok = True
         while t < N:
             K = len(self.cells_per_cluster)
             self._grow_ids(K + _lib.MAX_EXTRA + 2)
@@ -602,6 +609,12 @@ class DeviceCRP:
             flags = int(st[_lib.ST_FLAGS])
             if flags & (_lib.STOP_TAPE_EMPTY | _lib.STOP_HANG):
                 raise RuntimeError(f'gibbs_sweep stopped with flags {flags:#x} at t={st[_lib.ST_TDONE]}')
+            if flags & _lib.STOP_MANY:
+                # most visits have more rivals than an option record holds: nothing was done, run
+                # this epoch (and the next sweeps) on the dense FP64 matrix
+                self._lean_ok = False
+                self._lean_cooldown = 8
+                continue
             K = int(st[_lib.ST_K])
             self.d2h_bytes += 4 * _lib.ST_WORDS + 8 * K
             pairs = self.h_out[_lib.ST_WORDS:_lib.ST_WORDS + 2 * K].tolist()
@@ -609,8 +622,7 @@ class DeviceCRP:
             t_new = int(st[_lib.ST_TDONE])
             if lean and int(st[_lib.ST_NMANY]) > max(64, rows // 50):
                 self._lean_ok = False          # too many cells with > 8 rivals: dense rows pay
-            elif not lean and K <= _lib.LEAN_MAXK:
-                self._lean_ok = True           # try again next time
+                self._lean_cooldown = 8
             stall = stall + 1 if t_new == t else 0
             if stall > 2:
                 raise RuntimeError(f'gibbs_sweep made no progress at t={t} (flags {flags:#x})')

@@ -60,6 +60,8 @@ extern "C" {
 #define BNPC_STOP_REPACK      2  /* list shrank below a warp but ll rows are wide */
 #define BNPC_STOP_TAPE_EMPTY  4  /* parity mode: more births than taped rows      */
 #define BNPC_STOP_CAPACITY    8  /* list/id capacity reached: grow and relaunch   */
+#define BNPC_STOP_MANY       16  /* lean epoch: too many visits with more than BNPC_MAX_CAND rivals
+                                    (st[BNPC_ST_NMANY]); nothing was done, run the epoch dense */
 
 /* per-cell record of a sweep, in visiting order (64 bytes) */
 typedef struct {
@@ -190,6 +192,17 @@ int bnpc_ll_matrix_tc(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
  * larger entries are clamped), the two base-256 digits are separate columns (bdigits: scratch of
  * W * Kp * 128 bytes), int32 accumulators.  A row is off by at most (observed entries) * q / 2
  * (<= M * q / 2: pass it to bnpc_gibbs_options as err_abs) plus one float rounding.  M < 32768. */
+/* ---- posterior (MPEAR) estimator, reference libs/utils.py:90-145 -------------------------
+ * bnpc_cocluster_counts: assign int32 [S][N] (posterior samples of the assignment vector) ->
+ * counts int32 [N(N-1)/2], the number of samples in which cells i < j sit in different clusters,
+ * condensed in scipy pdist order; the reference's get_dist is counts / S (libs/utils.py:90-97).
+ * bnpc_mpear_sums: labels int32 [n_cand][N] (candidate cuts of the dendrogram) -> out uint64
+ * [1 + 2 n_cand]: out[0] = sum of all counts, out[1+2c] = pairs with equal labels under c,
+ * out[2+2c] = sum of counts over those pairs (the three sums of libs/utils.py:133-145 as exact
+ * integers).  out is zeroed inside. */
+int bnpc_cocluster_counts(const int32_t* assign, int S, int N, int32_t* counts, void* stream);
+int bnpc_mpear_sums(const int32_t* counts, int N, const int32_t* labels, int n_cand,
+                    unsigned long long* out, void* stream);
 /* Debug hook: buf = device array of 4096 int64 (or NULL) that CTA 0 of bnpc_ll_matrix_i8 fills with
  * clock64 stamps of its pipeline phases (tools/tc_trace.py). */
 int bnpc_debug_set_trace(void* buf);

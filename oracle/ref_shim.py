@@ -116,6 +116,7 @@ def load_reference(with_mcmc=False):
         ns.CRP_learning_errors = importlib.import_module('libs.CRP_learning_errors')
         if with_mcmc:
             ns.MCMC = importlib.import_module('libs.MCMC')
+            ns.utils = importlib.import_module('libs.utils')
     finally:
         sys.path.remove(REF_ROOT)
         for k in list(sys.modules):

@@ -9,7 +9,27 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+    """chain fixtures (tests/golden/make_golden.py)"""
+    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+                  if not n.startswith('estimators_'))
+
+
+def estimator_golden_names():
+    """estimator fixtures (tests/golden/make_golden_estimators.py)"""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, 'estimators_*.npz')))
+
+
+class EstimatorGolden:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'), allow_pickle=False)
+        self.z = z
+        code = z['data']
+        self.data = np.where(code < 0, np.nan, code.astype(np.float64))
+        self.results = []
+        for c in range(int(z['n_chains'])):
+            r = {k: z[f'chain{c}_{k}'] for k in ('assignments', 'params', 'ML', 'MAP', 'DP_alpha', 'FN', 'FP')}
+            r['burn_in'] = int(z[f'chain{c}_burn_in'])
+            self.results.append(r)
 
 
 class Golden:

@@ -1,0 +1,103 @@
+"""GPU: the posterior (MPEAR) estimator through libs.utils and the C ABI (bnpc_cocluster_counts,
+bnpc_mpear_sums) against the fixtures generated from the reference and against the oracle."""
+import numpy as np
+import pytest
+
+from helpers import EstimatorGolden, estimator_golden_names
+from oracle import estimators_oracle as eo
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+
+@pytest.mark.parametrize('name', estimator_golden_names())
+def test_posterior_estimator_matches_reference_fixtures(name):
+    import libs.utils as ut
+    g = EstimatorGolden(name)
+    z = g.z
+    cat = eo.concat_chain_results(g.results)
+    np.testing.assert_array_equal(ut.get_dist(cat['assignments']), z['dist'])       # bit-identical
+    np.testing.assert_array_equal(ut._get_MPEAR(cat['assignments']), z['mpear'])
+    post = ut.get_latents_posterior([dict(r) for r in g.results], g.data)[0]
+    np.testing.assert_array_equal(post['assignment'], z['post_assignment'])
+    np.testing.assert_allclose(post['genotypes'].T.values, z['post_genotypes'], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize('shape', [(7, 2), (40, 65), (33, 200), (64, 1111)])
+def test_pair_kernels_are_exact(shape):
+    """counts and the three pair sums are integers: bit-exact against numpy, ragged tile edges
+    included (N not a multiple of 64, more candidates than one staging round)."""
+    import libs.utils as ut
+    S, N = shape
+    rng = np.random.default_rng(S * N)
+    a = rng.integers(0, 6, (S, N))
+    pc = ut._PairCounts(a)
+    counts = pc.counts.cpu().numpy()
+    np.testing.assert_array_equal(counts, eo.pair_counts(a))
+    labels = np.stack([rng.integers(0, k, N) for k in list(range(1, 8)) + [11] * 30])
+    total, same_pairs, same_counts = pc.sums(labels)
+    iu = np.triu_indices(N, k=1)
+    same = labels[:, iu[0]] == labels[:, iu[1]]
+    assert total == int(counts.sum(dtype=np.int64))
+    np.testing.assert_array_equal(same_pairs, same.sum(axis=1))
+    np.testing.assert_array_equal(same_counts, (same * counts[None, :].astype(np.int64)).sum(axis=1))
+
+
+def test_posterior_estimator_on_a_sampled_chain():
+    """End to end at C2-like scale reduced to 3000 cells: run the CUDA chain, feed its traces to
+    the posterior and MAP estimators; both must recover the simulated clusters (north star: ARI
+    of the estimators; the reference sits at 0.9-1.0 here)."""
+    import libs.utils as ut
+    from libs.MCMC import Chain_steps
+    import libs.CRP_learning_errors as crple
+    from bnpc_b200.rng import PhiloxRandom
+    from oracle.crp_oracle import simulate
+    data, z = simulate(3000, 200, k_true=8, miss=0.1, seed=5)
+    m = crple.CRP_errors_learning(data, DP_alpha=[-1, -1], param_beta=[0.25, 0.25], FP_mean=0.01, FP_sd=0.01,
+                                  FN_mean=0.2, FN_sd=0.1, rnd=PhiloxRandom(99))
+    # start near the truth (a quarter of the cells scattered): the test is about the estimators,
+    # not about how fast a chain collapses from a random start
+    rng = np.random.default_rng(1)
+    start = z.copy()
+    scat = rng.random(z.size) < 0.25
+    start[scat] = rng.integers(0, 11, scat.sum())
+    m.init(assign=[int(v) for v in start])
+    moves = dict(sm_prob=0.33, dpa_prob=0.5, error_prob=0.1, sm_ratios=[0.75, 0.25], sm_steps=3,
+                 param_proposal_sd=np.array([0.1, 0.25, 0.5]))
+    steps, burn = 160, 80
+    ch = Chain_steps(m, 0, steps, burn, moves, 0, False)
+    ch.run()
+    res = ch.get_result()
+    post = ut.get_latents_posterior([res], data)[0]
+    point = ut.get_latents_point([res], 'MAP', data)[0]
+    assert ut.get_ARI(post['assignment'], z) > 0.9
+    assert ut.get_ARI(point['assignment'], z) > 0.9
+    assert post['genotypes'].shape == (200, 3000)
+    assert 0.1 < post['FN'][0] < 0.3
+
+
+def test_command_line_end_to_end(tmp_path):
+    """run_BnpC.py on a generated matrix file: 2 chains, posterior + MAP estimators, text outputs
+    in the reference's formats, ARI against the simulated clusters."""
+    import pandas as pd
+    import run_BnpC
+    from oracle.crp_oracle import simulate
+    data, z = simulate(400, 60, k_true=4, miss=0.1, seed=21)
+    mat = np.where(np.isnan(data), 3, data).astype(int).T                   # file: mutations x cells
+    path = tmp_path / 'data.csv'
+    pd.DataFrame(mat, index=[f'mut{i}' for i in range(mat.shape[0])],
+                 columns=[f'cell{j}' for j in range(mat.shape[1])]).to_csv(path, sep='\t')
+    truth = tmp_path / 'truth.txt'
+    truth.write_text(' '.join(str(int(v)) for v in z))
+    out = tmp_path / 'out'
+    args = run_BnpC.parse_args([str(path), '-n', '2', '-s', '150', '-e', 'posterior', 'MAP', '-o', str(out),
+                                '--seed', '7', '-v', '0', '-np', '-tc', str(truth)])
+    run_BnpC.main(args)
+    files = sorted(p.name for p in out.iterdir())
+    for want in ('ARI.txt', 'V_measure.txt', 'args.txt', 'assignment.txt', 'errors.txt',
+                 'genotypes_MAP_mean.tsv', 'genotypes_posterior_mean.tsv', 'genotypes_cont_posterior_mean.tsv'):
+        assert want in files, (want, files)
+    ari = pd.read_csv(out / 'ARI.txt', sep='\t')
+    assert (ari['ARI'] > 0.8).all(), ari
+    geno = pd.read_csv(out / 'genotypes_posterior_mean.tsv', sep='\t', index_col=0)
+    assert geno.shape == (60, 400) and list(geno.index[:2]) == ['mut0', 'mut1']
