@@ -45,8 +45,8 @@ REF_US_PER_CELL_STEP = 550.0     # planning anchor to size
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='C3', choices=sorted(CONFIGS))
     ap.add_argument('--chains-per-gpu', type=int, default=8)

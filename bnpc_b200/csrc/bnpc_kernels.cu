@@ -272,6 +272,60 @@ ll_matrix_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x
     }
 }
 
+// ll[r][0..K) for K <= 2 rows of log-probabilities (the 2-column matrices of the restricted Gibbs
+// scans, libs/CRP.py:635-638): the cells of a split-merge move are few (one or two clusters), so
+// one thread per cell leaves the GPU idle.  Eight threads share a cell (thread s takes the words
+// w = s, s + 8, ...), the whole table sits in shared memory, partial sums are combined by a fixed
+// butterfly.  Lane s walks the bits of a word rotated by 4 s so that the eight lanes of a cell hit
+// different banks.
+#define LLP_CELLS 32
+__global__ void __launch_bounds__(8 * LLP_CELLS)
+ll_few_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
+              const int32_t* __restrict__ cells, int cell_stride, int C,
+              const double2* __restrict__ lp, int K, double* __restrict__ ll, int ldk) {
+    extern __shared__ __align__(16) unsigned char llp_smem[];
+    double2* tab = reinterpret_cast<double2*>(llp_smem);          // [K][W * 32], zero beyond M
+    const int Mp = W * 32;
+    for (int i = threadIdx.x; i < K * Mp; i += blockDim.x) {
+        const int k = i / Mp, m = i % Mp;
+        tab[i] = (m < M) ? lp[(long long)k * M + m] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    const int sub = threadIdx.x & 7;
+    const int r = blockIdx.x * LLP_CELLS + (threadIdx.x >> 3);
+    const bool live = r < C;
+    const long long cell = live ? (cells ? cells[(long long)r * cell_stride] : r) : 0;
+    const uint32_t* r1 = x1 + cell * W;
+    const uint32_t* r0 = x0 + cell * W;
+    const double* t0 = reinterpret_cast<const double*>(tab);
+    const double* t1 = t0 + 2 * Mp;
+    double a0 = 0.0, a1 = 0.0;
+    if (live) {
+        for (int w = sub; w < W; w += 8) {
+            const uint32_t u1 = r1[w], u0 = r0[w];
+            if ((u1 | u0) == 0u) continue;
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i) {
+                const int bit = (i + 4 * sub) & 31;
+                const uint32_t b1 = (u1 >> bit) & 1u, b0 = (u0 >> bit) & 1u;
+                const int at = 2 * (w * 32 + bit) + (b1 ? 0 : 1);
+                const bool any = (b1 | b0) != 0u;
+                a0 += any ? t0[at] : 0.0;
+                if (K > 1) a1 += any ? t1[at] : 0.0;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        a0 += __shfl_xor_sync(FULL, a0, o);
+        a1 += __shfl_xor_sync(FULL, a1, o);
+    }
+    if (live && sub == 0) {
+        ll[(long long)r * ldk] = a0;
+        if (K > 1) ll[(long long)r * ldk + 1] = a1;
+    }
+}
+
 // log-likelihood of one cell under one (log p1, log p0) row; same arithmetic as above
 __device__ __forceinline__ double cell_row_ll(const uint32_t* __restrict__ r1,
                                               const uint32_t* __restrict__ r0, int W,
@@ -1527,7 +1581,7 @@ __global__ void group_members_kernel(const int32_t* __restrict__ assign, int N,
     members[seg_off[r] + base + __popc(peers & ((1u << lane) - 1u))] = n;
 }
 
-#define SS_CHUNK 512
+#define SS_CHUNK 256
 // grid (chunks, R, word blocks): a CTA counts ones/zeros per mutation over up to SS_CHUNK members
 // of one segment for a block of 32 mutation words.  A thread owns one word column and strides
 // over the rows, so that a warp reads whole 128-byte row pieces (coalesced); the 32 per-bit
@@ -1552,17 +1606,22 @@ suffstat_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0
 #pragma unroll
         for (int j = 0; j < 8; ++j) { a1[j] = 0u; a0[j] = 0u; }
         int i = beg + rsub;
-        for (; i + 3 * rstep < end; i += 4 * rstep) {
-            const long long c0 = members[i], c1 = members[i + rstep], c2 = members[i + 2 * rstep],
-                            c3 = members[i + 3 * rstep];
-            const uint32_t p0 = x1[c0 * W + w], p1 = x1[c1 * W + w], p2 = x1[c2 * W + w], p3 = x1[c3 * W + w];
-            const uint32_t q0 = x0[c0 * W + w], q1 = x0[c1 * W + w], q2 = x0[c2 * W + w], q3 = x0[c3 * W + w];
+        // eight rows in flight per thread: the row gather (member index, then its words) is the
+        // latency of this kernel
+        for (; i + 7 * rstep < end; i += 8 * rstep) {
+            long long c[8];
+            uint32_t p[8], q[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) c[k] = members[i + k * rstep];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { p[k] = x1[c[k] * W + w]; q[k] = x0[c[k] * W + w]; }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                a1[j] += ((p0 >> j) & 0x01010101u) + ((p1 >> j) & 0x01010101u) + ((p2 >> j) & 0x01010101u) +
-                         ((p3 >> j) & 0x01010101u);
-                a0[j] += ((q0 >> j) & 0x01010101u) + ((q1 >> j) & 0x01010101u) + ((q2 >> j) & 0x01010101u) +
-                         ((q3 >> j) & 0x01010101u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    a1[j] += (p[k] >> j) & 0x01010101u;
+                    a0[j] += (q[k] >> j) & 0x01010101u;
+                }
             }
         }
         for (; i < end; i += rstep) {
@@ -2080,6 +2139,19 @@ int bnpc_ll_matrix(const uint32_t* x1, const uint32_t* x0, int W, int M, const i
     if (C <= 0 || K <= 0) return 0;
     if (ldk < K) return bad_arg("ldk < K");
     if (W % 4 != 0) return bad_arg("W must be a multiple of 4");
+    if (K <= 2 && sizeof(double2) * (size_t)K * W * 32 <= 200 * 1024) {
+        const size_t smem = sizeof(double2) * (size_t)K * W * 32;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaError_t ce = cudaFuncSetAttribute(ll_few_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (ce != cudaSuccess) return fail("ll_few smem attribute", ce);
+            attr_done = true;
+        }
+        ll_few_kernel<<<cdiv(C, LLP_CELLS), 8 * LLP_CELLS, smem, (cudaStream_t)stream>>>(
+            x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const double2*>(lp), K, ll, ldk);
+        LAUNCH_CHECK("ll_few");
+        return 0;
+    }
     dim3 grid(cdiv(C, LL_THREADS), cdiv(K, LL_KT));
     if (grid.y > 65535) return bad_arg("too many clusters for one ll_matrix launch");
     ll_matrix_kernel<<<grid, LL_THREADS, 0, (cudaStream_t)stream>>>(
