@@ -312,10 +312,12 @@ def run_gpu(args, cfg):
 
     # ---- leg 1: device-resident traces (value) ------------------------------------------
     ms_dev, launches, clocks = leg(step_device, W, K, True)
-    ktimes = {}
+    ktimes, kwork = {}, {}
     for ch in chains:
         for name, v in ch.model.kernel_times_ms().items():
             ktimes.setdefault(name, []).extend(v)
+        for name, v in ch.model.kernel_work().items():
+            kwork.setdefault(name, []).extend(v)
         ch.model.profile = False
     sweep_stats = chains[0].model.sweep_stats
     k_live = len(chains[0].model.cells_per_cluster)
@@ -343,9 +345,21 @@ def run_gpu(args, cfg):
     # algorithmic work per launch:
     #   likelihood rows  4*N*M*K flop (2 planes x multiply-add), N*M/4 + 16*K*M + 4*N*K bytes
     #   sweep            the records of the uncertain visits (160 B each) + 4 B per visit of output
+    # per launch, from the live clusters / visits / uncertain visits of THAT launch (the list of
+    # clusters grows while the chain runs), averaged over the launches of the timed region
+    def mean_work(name, fn, fallback):
+        w = kwork.get(name) or []
+        return float(np.mean([fn(x) for x in w])) if w and len(w) == len(ktimes.get(name, [])) else fallback
+
     alg = {
-        'll_matrix': dict(flops=4.0 * N * M * k_live, bytes=N * M / 4 + 16.0 * k_live * M + 4.0 * N * k_live),
-        'gibbs_sweep': dict(flops=0.0, bytes=160.0 * n_unc + 4.0 * N),
+        'll_matrix': dict(
+            flops=mean_work('ll_matrix', lambda x: 4.0 * x['rows'] * M * x['K'], 4.0 * N * M * k_live),
+            bytes=mean_work('ll_matrix', lambda x: x['rows'] * M / 4 + 16.0 * x['K'] * M + 4.0 * x['rows'] * x['K'],
+                            N * M / 4 + 16.0 * k_live * M + 4.0 * N * k_live)),
+        'gibbs_sweep': dict(
+            flops=0.0,
+            bytes=mean_work('gibbs_sweep', lambda x: 160.0 * x.get('n_unc', x['rows']) + 4.0 * x['rows'],
+                            160.0 * n_unc + 4.0 * N)),
     }
 
     def roof_of(name):

@@ -20,7 +20,7 @@ HEADERS = [os.path.join(_HERE, 'csrc', 'bnpc_math.cuh'), os.path.join(_HERE, 'cs
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-fmad=false', '-std=c++17', '-shared', '-Xcompiler', '-fPIC']
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_EXTRA = 32
 ST_K, ST_TDONE, ST_FLAGS, ST_NEXTRA, ST_BIRTHS, ST_MOVED, ST_SLOW = range(7)
 ST_NUNC = 10
@@ -70,6 +70,7 @@ class SweepArgs(C.Structure):
         ('seed', C.c_uint64), ('stream_id', C.c_uint64),
         ('logn', C.c_void_p),
         ('c_norm', C.c_double), ('FN', C.c_double), ('FP', C.c_double), ('p', C.c_double), ('q', C.c_double),
+        ('owner_c', C.c_void_p),
     ]
 
 
@@ -125,7 +126,7 @@ SIGNATURES = {
     'bnpc_debug_set_trace': [_P],
     'bnpc_ll_matrix_i8': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _D, _P, _I, _P],
     'bnpc_gibbs_options': [_P, _I, _I, _P, _P, _P, _P, _I, _D, _D, _I, _D, _P],
-    'bnpc_gibbs_exact': [_P, _P, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _D, _D, _P, _P],
+    'bnpc_gibbs_exact': [_P, _P, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _D, _D, _P, _P, _P],
     'bnpc_gibbs_epoch_begin': [_P, _I, _P, _P, _P, _I, _P, _I, _P],
     'bnpc_gibbs_sweep': [C.POINTER(SweepArgs), _I, _P],
     'bnpc_group_members': [_P, _I, _P, _P, _P, _I, _P, _P],

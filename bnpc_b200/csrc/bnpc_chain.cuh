@@ -132,7 +132,7 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
         TRY(bnpc_gibbs_options(w->llf, ldf, K, w->col_of_id, w->visit + t, w->opt + t, w->n_cert, rows, e->log_n,
                                e->c_norm, 2 * M, err_abs, stream));
         TRY(bnpc_gibbs_exact(w->x1, w->x0, w->W, M, w->lp, K, w->visit + t, w->opt + t, w->n_cert, rows, w->cblk,
-                             w->idx_c, w->st, w->visit_c, w->cand_c, e->log_n, e->c_norm, w->comp, stream));
+                             w->idx_c, w->st, w->visit_c, w->cand_c, e->log_n, e->c_norm, w->comp, w->rg_perm, stream));
     } else {
         TRY(record_event(e->ev_ll0, stream));
         TRY(bnpc_ll_matrix(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp, K, w->ll, ldk, stream));
@@ -150,6 +150,7 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
     a.idcap = w->idcap; a.st = w->st; a.live_out = w->live_io;
     a.ll = lean ? nullptr : w->ll; a.ldk = ldk; a.t_epoch0 = t; a.lp = w->lp;
     a.comp = (lean && !e->serial_sweep) ? w->comp : nullptr;
+    a.owner_c = (lean && !e->serial_sweep) ? reinterpret_cast<const uint8_t*>(w->rg_perm) : nullptr;
     a.lpx = w->lpx; a.llx = w->llx; a.ldx = rows; a.scratch = w->scratch;
     a.visit = w->visit; a.cand = lean ? nullptr : w->cand; a.t_begin = t; a.t_end = t + rows;
     a.visit_c = compacted ? w->visit_c : nullptr;
@@ -158,7 +159,7 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
     a.seed = e->seed; a.stream_id = e->stream_id;
     a.logn = w->logn; a.c_norm = e->c_norm; a.FN = e->FN; a.FP = e->FP; a.p = e->p; a.q = e->q;
     TRY(record_event(e->ev_sw0, stream));
-    TRY(bnpc_gibbs_sweep(&a, K < 1000 ? 256 : 1024, stream));
+    TRY(bnpc_gibbs_sweep(&a, (lean && !e->serial_sweep) ? 512 : (K < 1000 ? 256 : 1024), stream));
     TRY(record_event(e->ev_sw1, stream));
     // status block + live list back to the host staging area (the caller synchronises)
     const int k_cap = (K + BNPC_MAX_EXTRA + 2 < w->idcap) ? K + BNPC_MAX_EXTRA + 2 : w->idcap;

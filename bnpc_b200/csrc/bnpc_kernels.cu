@@ -512,6 +512,7 @@ __global__ void gibbs_epoch_begin_kernel(const int32_t* __restrict__ live, int K
         st[BNPC_ST_NMANY] = 0;
         if (first) {
             st[BNPC_ST_TDONE] = 0; st[BNPC_ST_BIRTHS] = 0; st[BNPC_ST_MOVED] = 0; st[BNPC_ST_SLOW] = 0;
+            st[12] = 0; st[13] = 0; st[14] = 0; st[15] = 0;       // phase clocks of the parallel sequencer
         }
     }
 }
@@ -555,12 +556,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 #define SW_NSTAGE 16
 #define SW_MAXL 1024          /* longest list / widest ll matrix the sequencer regime handles */
 
-#define SW_PAR_WARPS 8
-#define SW_WINDOW 256         /* records per window of the parallel sequencer (= 8 stages) */
+#define SW_PAR_WARPS 16
+#define SW_WINDOW 384         /* records per window of the parallel sequencer */
+#define SW_BUF_STAGES 24      /* staging for two windows (768 records) */
 
 struct SweepShared {
-    alignas(128) bnpc_visit_t vis_stage[SW_NSTAGE][SW_STAGE_CELLS];
-    alignas(128) bnpc_cand_t cand_stage[SW_NSTAGE][SW_STAGE_CELLS];
+    alignas(128) bnpc_visit_t vis_stage[SW_BUF_STAGES][SW_STAGE_CELLS];
+    alignas(128) bnpc_cand_t cand_stage[SW_BUF_STAGES][SW_STAGE_CELLS];
     alignas(8) uint64_t bar[SW_NSTAGE];
     double red[40];
     // the live list (position j <-> insertion order) while it has at most SW_MAXL entries
@@ -577,8 +579,9 @@ struct SweepShared {
     // parallel sequencer (lean epochs): one warp per group of option-graph components
     int owner_of_col[BNPC_LEAN_MAXK];
     int abort_idx;                              // window-relative index of the first record that needs the exact path
-    unsigned char own_idx[SW_PAR_WARPS][SW_WINDOW];      // a warp's records of the window, in order
-    unsigned int mlog[SW_PAR_WARPS][SW_WINDOW];           // its moves of the window: idx | from << 8 | to << 16
+    unsigned short own_idx[SW_PAR_WARPS][SW_WINDOW];     // a warp's records of the window, in order
+    unsigned int mlog[SW_PAR_WARPS][SW_WINDOW];           // its moves of the window: idx | from << 9 | to << 17
+    unsigned char own_b[2][SW_WINDOW];                    // owner warp of each record of the window (0xff: warp 0, exact path)
 };
 
 // One exact categorical draw for a list that fits a warp (libs/CRP.py:88-100 + numpy choice,
@@ -1074,10 +1077,21 @@ __device__ void sweep_sequencer_par(const bnpc_sweep_args_t& a, SweepShared& sh)
     int issued = 0;
     if (tid == 0)
         for (; issued < n_win && issued < 2; ++issued) issue(issued);
+    // owner bytes of a window (bnpc_gibbs_exact) travel one window ahead through a register
+    auto owner_of = [&](int g) -> unsigned char {
+        const int r = first_rec + g * SW_WINDOW + tid;
+        return (g < n_win && tid < SW_WINDOW && r < n_rec) ? a.owner_c[r] : (unsigned char)0xfe;
+    };
+    if (tid < SW_WINDOW) sh.own_b[0][tid] = owner_of(0);
+    unsigned char nxt_owner = owner_of(1);
+    __syncthreads();
     int moved = 0, slow = 0;
     int next_t = a.t_end, next_rec = n_rec;
     bool leave = false;
     int waited = 0;
+    // phase clocks of warp 0 (kilo-cycles into st[12..15]: window data wait | ownership pass |
+    // batched walk | window barrier + commit)
+    long long ph[4] = {0, 0, 0, 0}, tk = clock64();
     for (int g = 0; g < n_win && !leave; ++g) {
         {
             long long spins = 0;
@@ -1085,6 +1099,7 @@ __device__ void sweep_sequencer_par(const bnpc_sweep_args_t& a, SweepShared& sh)
                 if (++spins > (1ll << 24)) { sh.hang = 1; break; }
             }
         }
+        { const long long now = clock64(); ph[0] += now - tk; tk = now; }
         waited = g + 1;
         const int r0 = first_rec + g * SW_WINDOW;
         const int nw = min(SW_WINDOW, n_rec - r0);
@@ -1097,15 +1112,15 @@ __device__ void sweep_sequencer_par(const bnpc_sweep_args_t& a, SweepShared& sh)
             const int rec = c * 32 + lane;
             bool mine = false;
             if (rec < nw) {
-                const int n_opt = vis[rec].n_opt, c_old = vis[rec].c_old;
-                const bool global = n_opt > BNPC_MAX_OPT || c_old < 0 || c_old >= BNPC_LEAN_MAXK;
-                mine = global ? (w == 0) : (sh.owner_of_col[c_old] == w);
+                const int o = sh.own_b[g & 1][rec];
+                mine = (o == 0xff) ? (w == 0) : (o == w);
             }
             const unsigned m = __ballot_sync(FULL, mine);
-            if (mine) sh.own_idx[w][own + __popc(m & lt_mask)] = (unsigned char)rec;
+            if (mine) sh.own_idx[w][own + __popc(m & lt_mask)] = (unsigned short)rec;
             own += __popc(m);
         }
         __syncwarp();
+        { const long long now = clock64(); ph[1] += now - tk; tk = now; }
         int n_log = 0;
         bool stopped = false;
         for (int base = 0; base < own && !stopped; base += 32) {
@@ -1205,7 +1220,7 @@ __device__ void sweep_sequencer_par(const bnpc_sweep_args_t& a, SweepShared& sh)
                         atomicSub(&sh.s_cnt[p_old], 1);
                         atomicAdd(&sh.s_cnt[to_pos], 1);
                         sh.mlog[w][n_log + __popc(batch & lt_mask)] =
-                            (unsigned)rec | ((unsigned)p_old << 8) | ((unsigned)to_pos << 16);
+                            (unsigned)rec | ((unsigned)p_old << 9) | ((unsigned)to_pos << 17);
                     }
                     n_log += __popc(batch);
                     __syncwarp();
@@ -1221,12 +1236,15 @@ __device__ void sweep_sequencer_par(const bnpc_sweep_args_t& a, SweepShared& sh)
                 break;
             }
         }
+        { const long long now = clock64(); ph[2] += now - tk; tk = now; }
+        if (tid < SW_WINDOW) sh.own_b[(g + 1) & 1][tid] = nxt_owner;
+        nxt_owner = owner_of(g + 2);
         __syncthreads();
         // ---- end of the window: commit the moves in front of a posted record, undo the rest ----
         const int ab = sh.abort_idx;
         for (int i = lane; i < n_log; i += 32) {
             const unsigned en = sh.mlog[w][i];
-            const int rec = en & 0xff, from = (en >> 8) & 0xff, to = (en >> 16) & 0xff;
+            const int rec = en & 0x1ff, from = (en >> 9) & 0xff, to = (en >> 17) & 0xff;
             if (rec < ab) {
                 a.assign[vis[rec].cell] = sh.s_id[to];
                 ++moved;
@@ -1246,7 +1264,10 @@ __device__ void sweep_sequencer_par(const bnpc_sweep_args_t& a, SweepShared& sh)
             issue(issued);
         }
         if (!leave && issued < n_win) ++issued;      // (uniform: every thread tracks the count)
+        { const long long now = clock64(); ph[3] += now - tk; tk = now; }
     }
+    if (tid == 0)
+        for (int k = 0; k < 4; ++k) a.st[12 + k] += (int)(ph[k] >> 10);
     // drain copies still in flight before shared memory is reused or the kernel ends
     for (int g = waited; g < ((tid == 0) ? issued : 0); ++g) {
         long long spins = 0;
@@ -1517,7 +1538,7 @@ gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
             } else {
                 sweep_block_cell(a, sh, t, L, sh.s_row);
             }
-        } else if (a.ll == nullptr && a.comp != nullptr && blockDim.x == 32 * SW_PAR_WARPS) {
+        } else if (a.ll == nullptr && a.comp != nullptr && a.owner_c != nullptr && blockDim.x == 32 * SW_PAR_WARPS) {
             sweep_sequencer_par(a, sh);
         } else if (L < SW_MAXL && a.ldk <= SW_MAXL) {
             if (tid < 32) sweep_sequencer(a, sh);
@@ -2312,13 +2333,14 @@ int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_i
 int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const double* lp, int K,
                      const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, const int32_t* n_cert, int C,
                      int32_t* blk, int32_t* idx_c, int32_t* st, bnpc_visit_t* visit_c,
-                     bnpc_cand_t* cand_c, double log_n, double c_norm, int32_t* comp, void* stream) {
+                     bnpc_cand_t* cand_c, double log_n, double c_norm, int32_t* comp, int32_t* order,
+                     void* stream) {
     if (C <= 0) return 0;
     if (K <= 0 || K > BNPC_LEAN_MAXK) return bad_arg("lean epochs need K <= BNPC_LEAN_MAXK");
-    if (!comp) return bad_arg("comp");
+    if (!comp || !order) return bad_arg("comp/order");
     const int nb = cdiv(C, CAND_THREADS);
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t ce = cudaMemsetAsync(comp, 0, sizeof(int32_t) * 256, s);
+    cudaError_t ce = cudaMemsetAsync(comp, 0, sizeof(int32_t) * 512, s);
     if (ce != cudaSuccess) return fail("gibbs_exact memset", ce);
     gibbs_finalize_kernel<<<nb, CAND_THREADS, 0, s>>>(opt_t0, n_cert, C, blk);
     LAUNCH_CHECK("gibbs_finalize");
@@ -2334,13 +2356,23 @@ int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const
         if (ce != cudaSuccess) return fail("gibbs_exact smem attribute", ce);
         attr_done = true;
     }
+    // processing order: uncertain visits grouped by their own cluster (see exact_hist_kernel)
+    exact_hist_kernel<<<cdiv(C, 256), 256, 0, s>>>(opt_t0, idx_c, st, comp);
+    LAUNCH_CHECK("exact_hist");
+    exact_scan_kernel<<<1, BNPC_LEAN_MAXK, 0, s>>>(comp);
+    LAUNCH_CHECK("exact_scan");
+    exact_scatter_kernel<<<cdiv(C, 256), 256, 0, s>>>(opt_t0, idx_c, st, comp, order);
+    LAUNCH_CHECK("exact_scatter");
     // the number of uncertain visits lives on the device: blocks beyond it exit at once
     gibbs_exact_kernel<<<cdiv(C, EX_THREADS), EX_THREADS, smem, s>>>(
         x1, x0, W, M, reinterpret_cast<const double2*>(lp), K, visit_t0, opt_t0, idx_c, st, visit_c, cand_c,
-        log_n, c_norm, comp);
+        log_n, c_norm, comp, order);
     LAUNCH_CHECK("gibbs_exact");
     components_kernel<<<1, BNPC_LEAN_MAXK, 0, s>>>(comp, K, SW_PAR_WARPS);
     LAUNCH_CHECK("components");
+    // (the processing order is not needed any more: its buffer receives the owner bytes)
+    owner_bytes_kernel<<<cdiv(C, 256), 256, 0, s>>>(visit_c, st, comp, reinterpret_cast<uint8_t*>(order));
+    LAUNCH_CHECK("owner_bytes");
     return 0;
 }
 
@@ -2363,12 +2395,16 @@ int bnpc_gibbs_sweep(const bnpc_sweep_args_t* a, int block_threads, void* stream
     if (!attr_done) {
         cudaError_t e1 = cudaFuncSetAttribute(gibbs_sweep_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaError_t e2 = cudaFuncSetAttribute(gibbs_sweep_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e3 = cudaFuncSetAttribute(gibbs_sweep_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e3 != cudaSuccess) return fail("gibbs_sweep smem attribute", e3);
         if (e1 != cudaSuccess) return fail("gibbs_sweep smem attribute", e1);
         if (e2 != cudaSuccess) return fail("gibbs_sweep smem attribute", e2);
         attr_done = true;
     }
     if (block_threads <= 256)
         gibbs_sweep_kernel<256><<<1, block_threads, smem, (cudaStream_t)stream>>>(*a);
+    else if (block_threads <= 512)
+        gibbs_sweep_kernel<512><<<1, block_threads, smem, (cudaStream_t)stream>>>(*a);
     else
         gibbs_sweep_kernel<1024><<<1, block_threads, smem, (cudaStream_t)stream>>>(*a);
     LAUNCH_CHECK("gibbs_sweep");

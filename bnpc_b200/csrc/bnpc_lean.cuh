@@ -157,6 +157,57 @@ compact_index_kernel(const bnpc_opt_t* __restrict__ opt, int C, const int32_t* _
     idx_c[pos] = r;
 }
 
+// Processing order of the uncertain visits for gibbs_exact_kernel: grouped by the column of the
+// visit's own cluster (counting sort; comp[256..320) histogram, comp[320..384) bases/cursors).
+// Visits of one cluster mostly share their option set, so the lanes of a warp read the same table
+// entries (shared-memory broadcasts instead of 4-8-way bank conflicts).  The order inside a group
+// is arbitrary -- every visit is computed independently and written to its own slot.
+__global__ void __launch_bounds__(256)
+exact_hist_kernel(const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ idx_c,
+                  const int32_t* __restrict__ st, int32_t* __restrict__ comp) {
+    __shared__ int h[BNPC_LEAN_MAXK];
+    if (threadIdx.x < BNPC_LEAN_MAXK) h[threadIdx.x] = 0;
+    __syncthreads();
+    const int n_unc = st[BNPC_ST_NUNC];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_unc) {
+        const bnpc_opt_t o = opt[idx_c[j]];
+        const int c = (o.n_opt <= BNPC_MAX_OPT) ? (o.col[o.i_old] & (BNPC_LEAN_MAXK - 1)) : 0;
+        atomicAdd(&h[c], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < BNPC_LEAN_MAXK && h[threadIdx.x]) atomicAdd(&comp[256 + threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(BNPC_LEAN_MAXK)
+exact_scan_kernel(int32_t* __restrict__ comp) {
+    __shared__ int v[BNPC_LEAN_MAXK];
+    const int c = threadIdx.x;
+    v[c] = comp[256 + c];
+    __syncthreads();
+    int base = 0;
+    for (int i = 0; i < c; ++i) base += v[i];
+    comp[320 + c] = base;
+}
+
+__global__ void __launch_bounds__(256)
+exact_scatter_kernel(const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ idx_c,
+                     const int32_t* __restrict__ st, int32_t* __restrict__ comp, int32_t* __restrict__ order) {
+    const int n_unc = st[BNPC_ST_NUNC];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_unc) return;
+    const bnpc_opt_t o = opt[idx_c[j]];
+    const int c = (o.n_opt <= BNPC_MAX_OPT) ? (o.col[o.i_old] & (BNPC_LEAN_MAXK - 1)) : 0;
+    // warp-aggregated cursor bump
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, c);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&comp[320 + c], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    order[base + __popc(peers & ((1u << lane) - 1u))] = j;
+}
+
 #define EX_THREADS 128
 #define EX_WORDS 4            /* words of a row (128 mutations) staged per round */
 // One thread per uncertain visit: FP64 log-likelihood of each of its options, then the option
@@ -171,7 +222,8 @@ gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__
                    const double2* __restrict__ lp, int K, const bnpc_visit_t* __restrict__ visit,
                    const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ idx_c,
                    int32_t* __restrict__ st, bnpc_visit_t* __restrict__ visit_c,
-                   bnpc_cand_t* __restrict__ cand_c, double slack, double c_norm, int32_t* __restrict__ comp) {
+                   bnpc_cand_t* __restrict__ cand_c, double slack, double c_norm, int32_t* __restrict__ comp,
+                   const int32_t* __restrict__ order) {
     extern __shared__ __align__(16) unsigned char ex_smem[];
     __shared__ unsigned long long s_adj[BNPC_LEAN_MAXK];
     __shared__ int s_num[BNPC_LEAN_MAXK];
@@ -180,9 +232,10 @@ gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__
     const int n_unc = st[BNPC_ST_NUNC];
     if (blockIdx.x * EX_THREADS >= n_unc) return;
     if (threadIdx.x < BNPC_LEAN_MAXK) { s_adj[threadIdx.x] = 0ull; s_num[threadIdx.x] = 0; }
-    const int j = blockIdx.x * EX_THREADS + threadIdx.x;
-    const bool live = j < n_unc;
-    const int r = live ? idx_c[j] : idx_c[0];
+    const int q = blockIdx.x * EX_THREADS + threadIdx.x;
+    const bool live = q < n_unc;
+    const int j = live ? order[q] : order[0];        // slot of the visit among the compacted records
+    const int r = idx_c[j];
     bnpc_visit_t v = visit[r];
     const bnpc_opt_t o = opt[r];
     const int nn = (live && o.n_opt <= BNPC_MAX_OPT) ? o.n_opt : 0;
@@ -353,4 +406,17 @@ components_kernel(int32_t* __restrict__ comp, int K, int n_warps) {
     }
     __syncthreads();
     comp[192 + c] = owner[root];
+}
+
+// Owner warp of every compacted record (0xff: more options than a record holds or unknown own
+// column -- warp 0 posts it for the exact path), read by the parallel sequencer one byte per
+// record instead of two fields of the 64-byte visit records.
+__global__ void __launch_bounds__(256)
+owner_bytes_kernel(const bnpc_visit_t* __restrict__ visit_c, const int32_t* __restrict__ st,
+                   const int32_t* __restrict__ comp, uint8_t* __restrict__ owner) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= st[BNPC_ST_NUNC]) return;
+    const int n_opt = visit_c[j].n_opt, c_old = visit_c[j].c_old;
+    const bool global = n_opt > BNPC_MAX_OPT || c_old < 0 || c_old >= BNPC_LEAN_MAXK;
+    owner[j] = global ? (uint8_t)0xff : (uint8_t)comp[192 + c_old];
 }

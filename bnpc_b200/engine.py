@@ -182,6 +182,7 @@ class DeviceCRP:
         self.sweep_stats = {}
         self.profile = False
         self._events = []
+        self._event_meta = {}
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -202,6 +203,7 @@ class DeviceCRP:
         new.__dict__.update(self.__dict__)
         new.sweep_stats = {}
         new._events = []
+        new._event_meta = {}
         return new
 
     # ------------------------------------------------------------------ plumbing
@@ -267,6 +269,12 @@ class DeviceCRP:
         self._events = []
         return out
 
+    def kernel_work(self):
+        """name -> per-launch work descriptors (live clusters / rows / uncertain visits) of the
+        library-bracketed launches since the last call, in the order of kernel_times_ms()."""
+        out, self._event_meta = self._event_meta, {}
+        return out
+
     def _setup_device(self):
         if not torch.cuda.is_available():
             raise RuntimeError('bnpc_b200 needs a CUDA device (sm_100a); there is no CPU path')
@@ -312,7 +320,7 @@ class DeviceCRP:
             self._dev('n_cert', _lib.LEAN_MAXK, i32, zero=True)
             self._dev('idx_c', N, i32)
             self._dev('bsplit', sh.W * 2 * _lib.LEAN_MAXK * 64, torch.int16)
-            self._dev('comp', 256, i32, zero=True)
+            self._dev('comp', 512, i32, zero=True)
             self._lean_ok = True
             self._lean_cooldown = 0
             self.members = self._dev('members', N, i32)
@@ -600,6 +608,9 @@ class DeviceCRP:
                     e.record(self.stream)            # creates the underlying event
                 ep.ev_ll0, ep.ev_ll1, ep.ev_sw0, ep.ev_sw1 = [e.cuda_event for e in evs]
                 self._events += [('ll_matrix', evs[0], evs[1]), ('gibbs_sweep', evs[2], evs[3])]
+                meta = dict(K=K, rows=rows, lean=bool(lean))
+                self._event_meta.setdefault('ll_matrix', []).append(meta)
+                self._event_meta.setdefault('gibbs_sweep', []).append(meta)
             else:
                 ep.ev_ll0 = ep.ev_ll1 = ep.ev_sw0 = ep.ev_sw1 = None
             L.chain_gibbs_epoch(self.ws, ep, sp)
@@ -615,6 +626,8 @@ class DeviceCRP:
                 self._lean_ok = False
                 self._lean_cooldown = 8
                 continue
+            if self.profile:
+                meta['n_unc'] = int(st[_lib.ST_NUNC])
             K = int(st[_lib.ST_K])
             self.d2h_bytes += 4 * _lib.ST_WORDS + 8 * K
             pairs = self.h_out[_lib.ST_WORDS:_lib.ST_WORDS + 2 * K].tolist()
@@ -636,7 +649,7 @@ class DeviceCRP:
         self.sweep_stats = dict(epochs=epochs, births=int(st[_lib.ST_BIRTHS]),
                                 moved=int(st[_lib.ST_MOVED]), slow=int(st[_lib.ST_SLOW]),
                                 uncertain=int(st[_lib.ST_NUNC]),
-                                kcycles=int(st[8]), us=int(st[9]) * 1.024,
+                                kcycles=int(st[8]), us=int(st[9]) * 1.024, phases_kcyc=[int(st[12 + k]) for k in range(4)],
                                 sm_mhz=(int(st[8]) / max(1, int(st[9]))) * 1e3)
         self._touch()
 

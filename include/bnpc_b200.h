@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BNPC_ABI_VERSION 7
+#define BNPC_ABI_VERSION 8
 
 /* capacity of clusters born since the ll matrix of the current epoch was built */
 #define BNPC_MAX_EXTRA 32
@@ -175,7 +175,9 @@ int bnpc_gibbs_compact(const bnpc_visit_t* visit_t0, const bnpc_cand_t* cand_t0,
  * error bound of the approximate rows.  bnpc_gibbs_exact: finalises the certain flags (a
  * cluster never keeps a single certain visit), compacts the uncertain visits in visiting order
  * (idx_c, st[BNPC_ST_NUNC]) and writes their visit / option records with FP64 log-likelihoods in
- * the arithmetic of bnpc_ll_matrix.  comp (int32[256]) receives the option graph on the columns
+ * the arithmetic of bnpc_ll_matrix (order: scratch of C ints, the processing order of the uncertain
+ * visits grouped by own cluster; on return its first st[BNPC_ST_NUNC] BYTES hold the owner warp of
+ * every compacted record, bnpc_sweep_args_t.owner_c).  comp (int32[512]) receives the option graph on the columns
  * (which clusters share a visit), its connected components and the sequencer warp that owns
  * each column: visits of different components never interact, the sweep walks them in parallel. */
 int bnpc_ll_matrix_f32(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
@@ -217,7 +219,8 @@ int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_i
 int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const double* lp, int K,
                      const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, const int32_t* n_cert, int C,
                      int32_t* blk, int32_t* idx_c, int32_t* st, bnpc_visit_t* visit_c,
-                     bnpc_cand_t* cand_c, double log_n, double c_norm, int32_t* comp, void* stream);
+                     bnpc_cand_t* cand_c, double log_n, double c_norm, int32_t* comp, int32_t* order,
+                     void* stream);
 /* Start of an epoch: rebuild cnt[] from the host-authoritative list
  * live[2*j] = id, live[2*j+1] = size (list order), set col_of_id[id] = j and
  * clear the epoch's extra-cluster bookkeeping.  first != 0 also resets the
@@ -246,6 +249,7 @@ typedef struct {
     /* constants */
     const double* logn /* [N+1], logn[n] = log(n) as numpy computes it */;
     double c_norm /* log(N-1+alpha) */; double FN; double FP; double p; double q;
+    const uint8_t* owner_c /* lean epochs: owner warp per compacted record (bnpc_gibbs_exact) or NULL */;
 } bnpc_sweep_args_t;
 int bnpc_gibbs_sweep(const bnpc_sweep_args_t* args_h, int block_threads, void* stream);
 
@@ -358,7 +362,7 @@ typedef struct {
     /* lean epochs */
     float* lpf /* [K][M][2] */; float* llf /* [N][ldf] */; bnpc_opt_t* opt /* [N] */;
     int32_t* n_cert /* [BNPC_LEAN_MAXK] */; int32_t* idx_c /* [N] */;
-    uint16_t* bsplit /* [W][2*BNPC_LEAN_MAXK][64] bf16 */; int32_t* comp /* [256] */;
+    uint16_t* bsplit /* [W][2*BNPC_LEAN_MAXK][64] bf16 */; int32_t* comp /* [512] */;
     /* sufficient statistics of the live clusters, list order */
     int32_t* ids; int32_t* seg; int32_t* cursor /* [K+1] each */; int32_t* members /* [N] */;
     int32_t* S1; int32_t* S0 /* [K][M] */; double* rnd /* [3][K][M] */; int32_t* declined /* [K+1] */;

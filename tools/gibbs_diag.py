@@ -52,4 +52,5 @@ for i in range(args.steps):
     ch.update_results(1 + i, False)
 for dt, st, k in rows:
     print(f'{1e3 * dt:8.3f} ms K={k:3d} epochs={st["epochs"]} births={st["births"]} moved={st["moved"]} '
-          f'slow={st["slow"]} unc={st.get("uncertain")} kernel_us={st["us"]:.0f}')
+          f'slow={st["slow"]} unc={st.get("uncertain")} kernel_us={st["us"]:.0f} kcycles={st["kcycles"]} '
+          f'phases(wait|own|walk|barrier)={st.get("phases_kcyc")}')
