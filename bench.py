@@ -243,12 +243,20 @@ def run_gpu(args, cfg):
         m.init(assign=z_list)
         chains.append(Chain_steps(m, rank * cpg + c + 1, W + K + 2, 0, moves, 0, False))
 
-    make_chain(0)                                          # packs the matrix once per device
-    ths = [threading.Thread(target=make_chain, args=(c,)) for c in range(1, cpg)]
-    [t.start() for t in ths]
-    [t.join() for t in ths]
-    torch.cuda.synchronize()
-    dev_trace = [torch.zeros((4, N), dtype=torch.int32, device=dev) for _ in chains]
+    def build_chains():
+        """(re)start all chains of this rank from the true assignment with their own seeds: the
+        two legs then walk the SAME trajectory (the cost of a step depends on the chain state,
+        which drifts while the chain runs)"""
+        chains.clear()
+        make_chain(0)                                      # packs the matrix once per device
+        ths = [threading.Thread(target=make_chain, args=(c,)) for c in range(1, cpg)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        chains.sort(key=lambda ch: ch.no)
+        torch.cuda.synchronize()
+
+    build_chains()
+    dev_trace = [torch.zeros((4, N), dtype=torch.int32, device=dev) for _ in range(cpg)]
 
     def step_device(ch, i, tr):
         """do_step + the per-step trace with the assignment row kept on the device."""
@@ -322,10 +330,8 @@ def run_gpu(args, cfg):
     sweep_stats = chains[0].model.sweep_stats
     k_live = len(chains[0].model.cells_per_cluster)
     # ---- leg 2: public driver API with host traces (e2e) --------------------------------
-    for ch in chains:
-        ch.results = {}
-        ch.init_results(2 * K + 8)
-    ms_e2e, _, _ = leg(step_e2e, min(W, 3), K, False)
+    build_chains()                                         # same seeds: the same K + W steps again
+    ms_e2e, _, _ = leg(step_e2e, W, K, False)
     h2d = sum(ch.model.h2d_bytes for ch in chains) / (len(chains) * K)
     d2h = sum(ch.model.d2h_bytes for ch in chains) / (len(chains) * K)
     # the host-side int64 trace row is read back as int32 [N] + the theta snapshot + scalars
