@@ -20,7 +20,7 @@ HEADERS = [os.path.join(_HERE, 'csrc', 'bnpc_math.cuh'), os.path.join(_HERE, 'cs
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-fmad=false', '-std=c++17', '-shared', '-Xcompiler', '-fPIC']
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_EXTRA = 32
 ST_K, ST_TDONE, ST_FLAGS, ST_NEXTRA, ST_BIRTHS, ST_MOVED, ST_SLOW = range(7)
 ST_NUNC = 10
@@ -70,7 +70,7 @@ class SweepArgs(C.Structure):
         ('seed', C.c_uint64), ('stream_id', C.c_uint64),
         ('logn', C.c_void_p),
         ('c_norm', C.c_double), ('FN', C.c_double), ('FP', C.c_double), ('p', C.c_double), ('q', C.c_double),
-        ('owner_c', C.c_void_p),
+        ('owner_c', C.c_void_p), ('wide', C.c_int32),
     ]
 
 

@@ -104,8 +104,10 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
     // cell indices are read straight out of the visit records
     const int32_t* cells = &w->visit[t].cell;
     const int cstride = (int)(sizeof(bnpc_visit_t) / 4);
-    const bool lean = e->lean != 0;
-    const bool compacted = lean || ldk <= SW_MAXL;
+    const bool lean = e->lean > 0;
+    const bool wide = e->lean < 0;               // dense FP64 matrix turned into option weights (sweep_wide)
+    if (wide && K > 63) return bad_arg("wide epoch with more than 63 clusters");
+    const bool compacted = !wide && (lean || ldk <= SW_MAXL);
     if (lean) {
         // approximate rows pick the options; FP64 only for the options of the uncertain visits
         if (K > BNPC_LEAN_MAXK) return bad_arg("lean epoch with K > BNPC_LEAN_MAXK");
@@ -136,6 +138,11 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
     } else {
         TRY(record_event(e->ev_ll0, stream));
         TRY(bnpc_ll_matrix(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp, K, w->ll, ldk, stream));
+        if (wide) {
+            gibbs_weights_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(w->ll, ldk, K, w->col_of_id,
+                                                                               w->visit + t, rows, e->c_norm);
+            LAUNCH_CHECK("gibbs_weights");
+        }
         TRY(record_event(e->ev_ll1, stream));
         if (compacted) {
             TRY(bnpc_gibbs_candidates(w->ll, ldk, K, w->col_of_id, w->visit + t, w->cand + t, rows, e->log_n,
@@ -151,6 +158,7 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
     a.ll = lean ? nullptr : w->ll; a.ldk = ldk; a.t_epoch0 = t; a.lp = w->lp;
     a.comp = (lean && !e->serial_sweep) ? w->comp : nullptr;
     a.owner_c = (lean && !e->serial_sweep) ? reinterpret_cast<const uint8_t*>(w->rg_perm) : nullptr;
+    a.wide = wide ? 1 : 0;
     a.lpx = w->lpx; a.llx = w->llx; a.ldx = rows; a.scratch = w->scratch;
     a.visit = w->visit; a.cand = lean ? nullptr : w->cand; a.t_begin = t; a.t_end = t + rows;
     a.visit_c = compacted ? w->visit_c : nullptr;

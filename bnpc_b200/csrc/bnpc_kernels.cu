@@ -1290,6 +1290,108 @@ __device__ void sweep_sequencer_par(const bnpc_sweep_args_t& a, SweepShared& sh)
     __syncthreads();
 }
 
+// Wide regime (dense epochs of at most 63 clusters in which most visits have more rivals than an
+// option record holds: short rows, e.g. the panel shape): a.ll holds the WEIGHTS
+// e[t][k] = exp(ll[t][k] - ref_t) (gibbs_weights_kernel), and one warp walks ALL visits with lanes
+// <-> list positions (2 l, 2 l + 1).  Restricted to nothing, the draw of _normalize_log_probs +
+// numpy choice (libs/CRP.py:88-100, 277) is linear in the cluster sizes, as in sweep_sequencer:
+// weight_k = n_k e_k, the new-cluster option weighs e_new; one warp scan of the lane pair sums gives
+// the running sums in list order, the pick is the first position whose running sum exceeds
+// u * total.  Within SW_GUARD of an interval edge, for a cluster that would die, and for the
+// new-cluster option the visit goes to the exact draw (pending = 3: exact FP64 row on demand, then
+// sweep_exact_cell / sweep_exact_cell2); a birth ends the epoch.  Visit fields and the two weights
+// of a lane are prefetched four visits ahead.
+#define WIDE_PF 4
+__device__ void sweep_wide(const bnpc_sweep_args_t& a, SweepShared& sh) {
+    const int lane = threadIdx.x;
+    int L = sh.L;
+    for (int j = lane; j < L; j += 32) {
+        const int id = a.lst[j];
+        sh.s_id[j] = id; sh.s_cnt[j] = a.cnt[id]; sh.s_src[j] = a.col_of_id[id];
+    }
+    __syncwarp();
+    sweep_rebuild_maps(sh, L);
+    const int pa = 2 * lane, pb = 2 * lane + 1;
+    const int src_a = (pa < L) ? sh.s_src[pa] : -1, src_b = (pb < L) ? sh.s_src[pb] : -1;
+    const int ldk = a.ldk, t_end = a.t_end;
+    int t = sh.t, moved = 0;
+    struct Pre { double u, e_new, ea, eb; int cell, old, c_old; };
+    auto fetch = [&](int tt) -> Pre {
+        Pre p;
+        const int tc = (tt < t_end) ? tt : t_end - 1;              // always a valid record
+        const bnpc_visit_t* v = a.visit + tc;
+        p.u = v->u; p.e_new = v->e_new; p.cell = v->cell; p.old = v->old; p.c_old = v->c_old;
+        const double* row = a.ll + (long long)(tc - a.t_epoch0) * ldk;
+        p.ea = (src_a >= 0) ? row[src_a] : 0.0;
+        p.eb = (src_b >= 0) ? row[src_b] : 0.0;
+        return p;
+    };
+    Pre ring[WIDE_PF];
+#pragma unroll
+    for (int k = 0; k < WIDE_PF; ++k) ring[k] = fetch(t + k);
+    bool leave = false;
+    while (t < t_end && !leave) {
+#pragma unroll
+        for (int k = 0; k < WIDE_PF; ++k) {
+            // (the refill is unconditional: a load under a branch would be waited for at once)
+            const Pre c = ring[k];
+            ring[k] = fetch(t + WIDE_PF);
+            if (t < t_end && !leave) {
+                const int po = (c.c_old >= 0 && c.c_old < SW_MAXL) ? sh.s_pos_of_col[c.c_old] : -1;
+                bool exact = po < 0;
+                int c_own = 0;
+                if (!exact) {
+                    c_own = sh.s_cnt[po];
+                    exact = sh.s_id[po] != c.old || c_own <= 1;
+                }
+                if (!exact) {
+                    const int na = (pa < L) ? sh.s_cnt[pa] - (pa == po ? 1 : 0) : 0;
+                    const int nb = (pb < L) ? sh.s_cnt[pb] - (pb == po ? 1 : 0) : 0;
+                    const double wa = (double)na * c.ea, wb = (double)nb * c.eb;
+                    const double cum_b = warp_scan_incl(wa + wb, lane);
+                    const double cum_a = cum_b - wb;
+                    const double total = __shfl_sync(FULL, cum_b, 31) + c.e_new;
+                    const double target = c.u * total;
+                    const unsigned ga = __ballot_sync(FULL, pa < L && cum_a > target);
+                    const unsigned gb = __ballot_sync(FULL, pb < L && cum_b > target);
+                    int pick = 0x7fffffff;
+                    if (ga) pick = 2 * (__ffs(ga) - 1);
+                    if (gb) pick = min(pick, 2 * (__ffs(gb) - 1) + 1);
+                    if (pick >= L) {
+                        exact = true;                              // the new-cluster option
+                    } else {
+                        const double hi = __shfl_sync(FULL, (pick & 1) ? cum_b : cum_a, pick >> 1);
+                        const int q = (pick > 0) ? pick - 1 : 0;
+                        double lo = __shfl_sync(FULL, (q & 1) ? cum_b : cum_a, q >> 1);
+                        if (pick == 0) lo = 0.0;
+                        const double slack = fmin(target - lo, hi - target) - 2.0 * SW_GUARD * total;
+                        if (!(slack > 0.0)) {
+                            exact = true;
+                        } else if (pick != po) {
+                            if (lane == 0) {
+                                sh.s_cnt[po] = c_own - 1;
+                                sh.s_cnt[pick] += 1;
+                                a.assign[c.cell] = sh.s_id[pick];
+                            }
+                            ++moved;
+                            __syncwarp();
+                        }
+                    }
+                }
+                if (exact) leave = true; else ++t;
+            }
+        }
+    }
+    __syncwarp();
+    for (int j = lane; j < L; j += 32) a.cnt[sh.s_id[j]] = sh.s_cnt[j];
+    if (lane == 0) {
+        sh.L = L;
+        sh.t = t;
+        sh.moved += moved;
+        if (leave) { sh.pending = 3; sh.slow += 1; }
+    }
+}
+
 // one cell with the whole CTA (list longer than a warp)
 __device__ void sweep_block_cell(const bnpc_sweep_args_t& a, SweepShared& sh, int t, int L,
                                  const double* rowp) {
@@ -1420,7 +1522,7 @@ __device__ void sweep_birth(const bnpc_sweep_args_t& a, SweepShared& sh) {
         __syncthreads();
         return;
     }
-    const bool lean = a.ll == nullptr;         // lean epochs end at a birth: no ll column is built
+    const bool lean = a.ll == nullptr || a.wide;   // lean and wide epochs end at a birth: no ll column is built
     double2* lpx = lean ? nullptr : reinterpret_cast<double2*>(a.lpx) + (long long)e * M;
     const uint32_t* r1 = a.x1 + (long long)cell * W;
     const uint32_t* r0 = a.x0 + (long long)cell * W;
@@ -1538,6 +1640,14 @@ gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
             } else {
                 sweep_block_cell(a, sh, t, L, sh.s_row);
             }
+        } else if (a.wide) {
+            if (L > 63) {                            // (cannot happen: births end a wide epoch)
+                if (tid == 0) sh.stop |= BNPC_STOP_REPACK;
+                __syncthreads();
+                continue;
+            }
+            if (tid < 32) sweep_wide(a, sh);
+            __syncthreads();
         } else if (a.ll == nullptr && a.comp != nullptr && a.owner_c != nullptr && blockDim.x == 32 * SW_PAR_WARPS) {
             sweep_sequencer_par(a, sh);
         } else if (L < SW_MAXL && a.ldk <= SW_MAXL) {

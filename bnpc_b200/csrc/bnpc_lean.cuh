@@ -420,3 +420,27 @@ owner_bytes_kernel(const bnpc_visit_t* __restrict__ visit_c, const int32_t* __re
     const bool global = n_opt > BNPC_MAX_OPT || c_old < 0 || c_old >= BNPC_LEAN_MAXK;
     owner[j] = global ? (uint8_t)0xff : (uint8_t)comp[192 + c_old];
 }
+
+// Wide epochs: the dense FP64 matrix becomes option WEIGHTS in place, ll[t][k] <- exp(ll[t][k] - ref_t)
+// with ref_t = max(max_k ll[t][k], new-cluster score), and the visit record gets ref, the weight
+// of the new-cluster option and the column of the cell's own cluster.  One warp per visit.
+__global__ void __launch_bounds__(256)
+gibbs_weights_kernel(double* __restrict__ ll, int ldk, int K, const int32_t* __restrict__ col_of_id,
+                     bnpc_visit_t* __restrict__ visit, int C, double c_norm) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= C) return;
+    double* row = ll + (long long)r * ldk;
+    const double lnew_ll = visit[r].lnew + c_norm;
+    double m = lnew_ll;
+    for (int k = lane; k < K; k += 32) m = fmax(m, row[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    for (int k = lane; k < K; k += 32) row[k] = exp(row[k] - m);
+    if (lane == 0) {
+        visit[r].ref = m;
+        visit[r].e_new = exp(lnew_ll - m);
+        visit[r].c_old = col_of_id[visit[r].old];
+        visit[r].n_opt = BNPC_MAX_OPT + 1;
+        visit[r].flags = 0;
+    }
+}

@@ -154,6 +154,8 @@ class DeviceCRP:
     lean_enabled = True           # class-wide switch (tests force the dense FP64 matrix with False)
     lean_rows = 3                 # approximate rows of lean epochs: 3 tcgen05 integer digits, 2 tcgen05 bf16-split, 1 FP32 FMA
     serial_sweep = False          # lean epochs: one sequencer warp (True) or one per component group
+    wide_enabled = True           # many-rival data: dense epochs of <= 63 clusters walk option weights (sweep_wide)
+    force_wide = False            # tests: take the wide route whenever K <= 63
 
     def __init__(self, data, DP_alpha=(-1, -1), param_beta=(1, 1), FN_error=EPS, FP_error=EPS,
                  device=None, rnd=None):
@@ -591,13 +593,17 @@ class DeviceCRP:
             ldk = max(3, K | 1)
             # lean epoch: approximate rows select the options, FP64 only where a decision
             # needs it; dense FP64 matrix for longer lists (or when many cells have > 8 rivals)
-            lean = K <= _lib.LEAN_MAXK and self._lean_ok and self.lean_enabled
+            lean = (K <= _lib.LEAN_MAXK and self._lean_ok and self.lean_enabled
+                    and not (self.force_wide and K <= 63))
+            # wide: the dense matrix becomes option weights and one warp walks all visits with
+            # lanes <-> clusters (data whose visits mostly have more rivals than an option record)
+            wide = (not lean) and self.wide_enabled and K <= 63 and (self.force_wide or not self._lean_ok)
             rows = N - t if lean else int(min(N - t, max(1, LL_BUDGET_BYTES // (8 * ldk))))
-            ep.lean = self.lean_rows if lean else 0
+            ep.lean = self.lean_rows if lean else (-1 if wide else 0)
             if not lean and rows * ldk + 2 > self._ll_cap:
                 self._ll_cap = rows * ldk + 2
                 self._dev('ll', self._ll_cap, torch.float64)
-            if not lean and _lib.MAX_EXTRA * rows > self._llx_cap:
+            if not lean and not wide and _lib.MAX_EXTRA * rows > self._llx_cap:
                 self._llx_cap = _lib.MAX_EXTRA * rows
                 self._dev('llx', self._llx_cap, torch.float64)
             ep.first, ep.K, ep.t, ep.rows, ep.ldk = first, K, t, rows, ldk

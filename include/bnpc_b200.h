@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BNPC_ABI_VERSION 8
+#define BNPC_ABI_VERSION 9
 
 /* capacity of clusters born since the ll matrix of the current epoch was built */
 #define BNPC_MAX_EXTRA 32
@@ -250,6 +250,8 @@ typedef struct {
     const double* logn /* [N+1], logn[n] = log(n) as numpy computes it */;
     double c_norm /* log(N-1+alpha) */; double FN; double FP; double p; double q;
     const uint8_t* owner_c /* lean epochs: owner warp per compacted record (bnpc_gibbs_exact) or NULL */;
+    int32_t wide /* 1: ll holds option weights exp(ll - ref) and visit[].ref / e_new / c_old are set
+                    (dense epoch of at most 63 clusters walked by sweep_wide); 0 otherwise */;
 } bnpc_sweep_args_t;
 int bnpc_gibbs_sweep(const bnpc_sweep_args_t* args_h, int block_threads, void* stream);
 
@@ -387,7 +389,9 @@ typedef struct {
 typedef struct {
     int32_t first; int32_t K; int32_t t; int32_t rows; int32_t ldk; int32_t rand_ready;
     int32_t lean /* 0: dense FP64 matrix; lean epoch (K <= BNPC_LEAN_MAXK) with approximate rows
-                    from 1: FP32 FMA, 2: tcgen05 bf16-split, 3: tcgen05 integer digits */;
+                    from 1: FP32 FMA, 2: tcgen05 bf16-split, 3: tcgen05 integer digits;
+                    -1: dense FP64 matrix turned into option weights, all visits walked by one warp
+                    with lanes <-> clusters (K <= 63; data whose visits mostly have > 8 rivals) */;
     int32_t serial_sweep /* lean epochs: 1 = one sequencer warp instead of one per component group */;
     double c1; double c0; double lnew_prior; double c_norm; double log_n;
     double FN; double FP; double p; double q;

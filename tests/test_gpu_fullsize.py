@@ -2,9 +2,9 @@
 error rates / split-merge heavy, C5 1M x 50 panel with 30 % missing), where the CPU oracle would
 take hours per step.  Size-independent properties instead:
 
-* the five independent CUDA routes of the Gibbs sweep -- integer tcgen05 rows + one sequencer
+* the six independent CUDA routes of the Gibbs sweep -- integer tcgen05 rows + one sequencer
   warp per component group (production), FP32-FMA rows, bf16-split tcgen05 rows, the dense FP64
-  matrix, one sequencer warp -- must
+  matrix, one sequencer warp, option weights walked with lanes <-> clusters -- must
   produce the SAME chain from the same Philox seed (bit-identical assignments, cluster lists and
   float32 parameters; the dense FP64 route is the arithmetic pinned against the oracle);
 * bookkeeping invariants after every step (sizes = bincount of the assignment, ordered ids);
@@ -30,6 +30,7 @@ MODES = {
     'bf16_rows': dict(lean_rows=2),
     'dense_fp64': dict(lean_enabled=False),
     'serial_sweep': dict(serial_sweep=True),
+    'wide': dict(force_wide=True),
 }
 
 
@@ -107,7 +108,7 @@ def test_full_size_routes_agree(cfg, monkeypatch):
     np.testing.assert_allclose(ref_final['ll'], want, rtol=1e-9, err_msg=f'{cfg}: get_ll_full vs host float64')
     assert adjusted_rand_score(z, ref_final['assign']) > 0.9
     assert ref_trace[-1]['stats'].get('uncertain', 0) <= c['cells']
-    for mode in ('fma_rows', 'bf16_rows', 'dense_fp64', 'serial_sweep'):
+    for mode in ('fma_rows', 'bf16_rows', 'dense_fp64', 'serial_sweep', 'wide'):
         trace, final = _run(cfg, data, z, mode, monkeypatch)
         for s, (g, w) in enumerate(zip(trace, ref_trace)):
             where = f'{cfg} {mode} vs production, step {s + 1}'

@@ -111,6 +111,25 @@ def test_cuda_matches_oracle_bf16_rows(case, bf16_rows):
 
 
 @pytest.fixture
+def wide_route(monkeypatch):
+    """dense epochs whose FP64 matrix becomes option weights, all visits walked by one warp with
+    lanes <-> clusters (the route of data whose visits mostly have more than 8 rivals)"""
+    from bnpc_b200.engine import DeviceCRP
+    monkeypatch.setattr(DeviceCRP, 'force_wide', True)
+
+
+@pytest.mark.parametrize('case', [CASES[0], CASES[2], CASES[4], CASES[5]],
+                         ids=[CASES[0][0], CASES[2][0], CASES[4][0], CASES[5][0]])
+def test_cuda_matches_oracle_wide_route(case, wide_route):
+    test_cuda_matches_oracle_on_seeded_data(case)
+
+
+@pytest.mark.parametrize('name', ['learn_pp11_panel_missing30', 'fixed_pp025_ragged70'])
+def test_cuda_replays_reference_tape_wide_route(name, wide_route):
+    test_cuda_replays_reference_tape(name)
+
+
+@pytest.fixture
 def serial_sweep(monkeypatch):
     """lean epochs walked by one sequencer warp instead of one warp per component group"""
     from bnpc_b200.engine import DeviceCRP
