@@ -277,6 +277,7 @@ def run_gpu(args, cfg):
 
         def worker(ch, tr):
             try:
+                torch.cuda.set_device(dev)                 # the current device is per host thread
                 for i in range(n_warm):
                     step_fn(ch, 1 + i, tr)
                 ch.model.stream.synchronize()

@@ -1712,13 +1712,14 @@ __global__ void group_members_kernel(const int32_t* __restrict__ assign, int N,
     members[seg_off[r] + base + __popc(peers & ((1u << lane) - 1u))] = n;
 }
 
-#define SS_CHUNK 256
-// grid (chunks, R, word blocks): a CTA counts ones/zeros per mutation over up to SS_CHUNK members
+#define SS_CHUNK 2040         /* rows per CTA: 64 per thread at the widest rows (byte-wide counters hold 255) */
+#define SS_THREADS 1024
+// grid (chunks, R, word blocks): a CTA of 1024 threads counts ones/zeros per mutation over up to SS_CHUNK members
 // of one segment for a block of 32 mutation words.  A thread owns one word column and strides
 // over the rows, so that a warp reads whole 128-byte row pieces (coalesced); the 32 per-bit
 // counters of a word are kept as 8 registers of four byte-wide counters each
 // (acc[j] += (x >> j) & 0x01010101 counts bits j, j+8, j+16, j+24), at most 255 rows per thread.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SS_THREADS)
 suffstat_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
                 const int32_t* __restrict__ members, const int32_t* __restrict__ seg_off,
                 int32_t* __restrict__ S1, int32_t* __restrict__ S0, int wc_log2) {
@@ -1728,9 +1729,9 @@ suffstat_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0
     const int end = min(seg_off[r + 1], beg + SS_CHUNK);
     if (beg >= end) return;
     const int wc = 1 << wc_log2;
-    const int col = threadIdx.x & (wc - 1), rsub = threadIdx.x >> wc_log2, rstep = 256 >> wc_log2;
+    const int col = threadIdx.x & (wc - 1), rsub = threadIdx.x >> wc_log2, rstep = SS_THREADS >> wc_log2;
     const int w = blockIdx.z * 32 + col;
-    for (int i = threadIdx.x; i < 2 * 32 * 32; i += 256) (&cnt[0][0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 2 * 32 * 32; i += SS_THREADS) (&cnt[0][0][0])[i] = 0;
     __syncthreads();
     if (w < W) {
         uint32_t a1[8], a0[8];
@@ -1775,7 +1776,7 @@ suffstat_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+    for (int i = threadIdx.x; i < 32 * 32; i += SS_THREADS) {
         const int c = i >> 5, bit = i & 31;
         const int m = (blockIdx.z * 32 + c) * 32 + bit;
         if (c < wc && m < M) {
@@ -2552,7 +2553,7 @@ int bnpc_suffstat(const uint32_t* x1, const uint32_t* x0, int W, int M, const in
     for (int r0 = 0; r0 < R; r0 += 65535) {
         const int rr = min(65535, R - r0);
         dim3 grid(cdiv(max_len, SS_CHUNK), rr, cdiv(W, 32));
-        suffstat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x1, x0, W, M, members, seg_off + r0,
+        suffstat_kernel<<<grid, SS_THREADS, 0, (cudaStream_t)stream>>>(x1, x0, W, M, members, seg_off + r0,
                                                                S1 + (size_t)r0 * M, S0 + (size_t)r0 * M, wc_log2);
         LAUNCH_CHECK("suffstat");
     }

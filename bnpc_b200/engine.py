@@ -210,6 +210,13 @@ class DeviceCRP:
 
     # ------------------------------------------------------------------ plumbing
     def _sp(self):
+        # the CUDA "current device" is per host thread and kernel launches go to it: a chain that is
+        # stepped from another thread than the one that initialised it (bench legs, thread pools)
+        # must select its device there first (new threads start on device 0)
+        ident = threading.get_ident()
+        if ident != self._dev_thread:
+            torch.cuda.set_device(self.device)
+            self._dev_thread = ident
         return self._stream_ptr
 
     def _dev(self, name, shape, dtype, zero=False):
@@ -287,6 +294,7 @@ class DeviceCRP:
         torch.cuda.set_device(self.device)
         self.stream = torch.cuda.Stream(self.device)
         self._stream_ptr = self.stream.cuda_stream
+        self._dev_thread = threading.get_ident()
         if self.rnd is None:
             self.rnd = PhiloxRandom(np.random.SeedSequence().entropy & 0xFFFFFFFFFFFFFFFF)
         self.rnd.bind(self.device)

@@ -123,6 +123,14 @@ class MCMC:
             n = 1
 
         rank, world, local = dist_info()
+        if world > 1 and torch is not None and not _dist_ready():
+            # launched by torchrun without a process group: NCCL over the GPUs (gloo on CPU-only
+            # hosts), rendezvous from the MASTER_ADDR / MASTER_PORT of the environment
+            if torch.cuda.is_available():
+                torch.cuda.set_device(local)
+                torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local))
+            else:
+                torch.distributed.init_process_group('gloo')
         mine = chains_of_rank(n, rank, world)
         gpus = max(1, _visible_gpus())
         self.chains = [None] * n
