@@ -423,10 +423,19 @@ def run_gpu(args, cfg):
     return out
 
 
+def _emit(line, fd):
+    os.write(fd, (line + '\n').encode())
+
+
 def main():
     args = parse()
     cfg = workload(args)
     rank = int(os.environ.get('RANK', 0))
+    # stdout carries exactly ONE JSON line: everything libraries print there while the bench runs
+    # (NCCL's version banner, warnings) is sent to stderr instead
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == 'reference':
         if rank != 0:
             return
@@ -442,11 +451,12 @@ def main():
                    steps_per_sec_per_chain=res['per_chain'], cpu_baseline=res,
                    e2e=dict(value=res['value'], unit='chain-steps/s', h2d_bytes_per_step=0,
                             d2h_bytes_per_step=0), gpu_launches=0)
-        print(json.dumps(out))
+        _emit(json.dumps(out), out_fd)
         return
     out = run_gpu(args, cfg)
+    sys.stdout.flush()
     if out is not None:
-        print(json.dumps(out))
+        _emit(json.dumps(out), out_fd)
 
 
 if __name__ == '__main__':

@@ -16,9 +16,9 @@
 //   B  the digit table in the K-major 128-byte-swizzled UMMA layout, one bulk async copy
 //      (cp.async.bulk) per stage; a stage is 256 reduction indices = 8 MMAs.
 //   D  int32 accumulators in TMEM, two sets: the epilogue of a tile overlaps the next tile.
-// Warp roles (14 warps): 0-7 produce A (TMEM lane quarter = warp % 4; warps 0-3 expand the first
-// 128 indices of every stage, warps 4-7 the second), 8-11 epilogue (TMEM -> registers -> one
-// float row per visit), 12 issues the MMAs (one thread), 13 streams B.  The 16-byte piece of a
+// Warp roles (22 warps): 0-15 produce A (TMEM lane quarter = warp % 4; group warp / 4 expands one
+// 64-bit piece = 64 indices of every stage), 16-19 epilogue (TMEM -> registers -> one float row
+// per visit), 20 issues the MMAs (warp-uniform, one elected lane), 21 streams B.  The 8-byte piece of a
 // visit's row that a producer thread expands per stage is prefetched T8_PF stages ahead (the
 // row gather is the long-latency part: visiting order is a random permutation of the cells),
 // across tile boundaries, with the cell indices two tiles ahead of that.
@@ -26,7 +26,9 @@
 // (element 4p+b <-> bit p+8b), the same for A and B.
 
 #define T8_NST 4                 /* pipeline stages (A in TMEM, B in shared memory) */
-#define T8_THREADS 448
+#define T8_GROUPS 4              /* producer groups: each expands one 64-bit piece of every stage */
+#define T8_PWARPS (4 * T8_GROUPS)
+#define T8_THREADS (32 * (T8_PWARPS + 6))   /* producers, 4 epilogue warps, MMA warp, B loader */
 #define T8_A_COL0 256            /* first TMEM column of the A stages (accumulators use [0, 256)) */
 #define T8_A_STAGE_COLS 64       /* 256 one-byte entries per visit and stage */
 #define T8_PF 4                  /* row-piece prefetch depth, in stages */
@@ -41,6 +43,15 @@ __device__ __forceinline__ void tc_mma_ts_i8(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d),
         "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
 
@@ -103,12 +114,12 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
     const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < T8_NST; ++s) { mbar_init(&full[s], 9); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < T8_NST; ++s) { mbar_init(&full[s], T8_PWARPS + 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 12) {
+    if (warp == T8_PWARPS + 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"((uint32_t)TC_TMEM_COLS)
                      : "memory");
@@ -119,9 +130,9 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 8) {
-        // ---- A producers: one TMEM lane = one visit; group g = warp / 4 expands pieces
-        // [2g, 2g+2) of every stage (one aligned 16-byte load) ----
+    if (warp < T8_PWARPS) {
+        // ---- A producers: one TMEM lane = one visit; group g = warp / 4 expands piece g of every
+        // stage (one aligned 8-byte load, 16 TMEM columns) ----
         const int g = warp >> 2;
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -145,9 +156,9 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
         int cell_cur = cells ? __ldg(cells + r_cur * cell_stride) : (int)r_cur;
         int cell_n1 = cells ? __ldg(cells + r_n1 * cell_stride) : (int)r_n1;
         int cell_n2 = cells ? __ldg(cells + r_n2 * cell_stride) : (int)r_n2;
-        auto pf_next = [&](bool& ok) -> const uint4* {
+        auto pf_next = [&](bool& ok) -> const uint2* {
             ok = ok_cur && pf_q < total;
-            const int c = pf_sidx * 4 + 2 * g;               // first of this thread's two pieces
+            const int c = pf_sidx * 4 + g;                   // this thread's piece of the stage
             const long long base = (long long)cell_cur * W;
             const uint32_t* src = (c < half) ? x1 + base + 2 * c : x0 + base + 2 * (c - half);
             if (pf_q < total) {
@@ -161,9 +172,9 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                     cell_n2 = cells ? __ldg(cells + r_n2 * cell_stride) : (int)r_n2;
                 }
             }
-            return reinterpret_cast<const uint4*>(src);
+            return reinterpret_cast<const uint2*>(src);
         };
-        uint4 ring[T8_PF];
+        uint2 ring[T8_PF];
         bool ring_ok[T8_PF];
 #pragma unroll
         for (int j = 0; j < T8_PF; ++j) ring[j] = __ldg(pf_next(ring_ok[j]));
@@ -174,19 +185,17 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
         for (long long q0 = 0; q0 < total; q0 += T8_PF) {
 #pragma unroll
             for (int j = 0; j < T8_PF; ++j) {
-                const uint4 raw = ring[j];
+                const uint2 raw = ring[j];
                 const bool ok = ring_ok[j];
                 ring[j] = __ldg(pf_next(ring_ok[j]));
                 if (q0 + j < total) {
-                    const uint4 w = ok ? raw : make_uint4(0u, 0u, 0u, 0u);
+                    const uint2 w = ok ? raw : make_uint2(0u, 0u);
                     const int slot = it % T8_NST;
-                    uint32_t regs[32];
+                    uint32_t regs[16];
 #pragma unroll
                     for (int p = 0; p < 8; ++p) {
                         regs[p] = (w.x >> p) & 0x01010101u;
                         regs[8 + p] = (w.y >> p) & 0x01010101u;
-                        regs[16 + p] = (w.z >> p) & 0x01010101u;
-                        regs[24 + p] = (w.w >> p) & 0x01010101u;
                     }
                     if (tr && warp == 0 && it < 300) trace[it * 3] = clock64();
                     if (pend >= 0) {
@@ -198,8 +207,8 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                     if (it >= T8_NST) mbar_wait(&empty[slot], ((it / T8_NST) - 1) & 1);
                     tc_fence_after();
                     if (tr && warp == 0 && it < 300) trace[it * 3 + 1] = clock64();
-                    const uint32_t dst = tmem + T8_A_COL0 + slot * T8_A_STAGE_COLS + g * 32 + lane_base;
-                    tc_st32(dst, regs);
+                    const uint32_t dst = tmem + T8_A_COL0 + slot * T8_A_STAGE_COLS + g * 16 + lane_base;
+                    tc_st16(dst, regs);
                     pend = slot;
                     if (tr && warp == 0 && it < 300) trace[it * 3 + 2] = clock64();
                     ++it;
@@ -212,7 +221,7 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[pend]);
         }
-    } else if (warp < 12) {
+    } else if (warp < T8_PWARPS + 4) {
         // ---- epilogue: D lane `row`, columns [0, N) of the tile's accumulator set ----
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -221,31 +230,29 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
             const uint32_t set = tile_count & 1u;
             mbar_wait(&acc_full[set], (tile_count >> 1) & 1);
             tc_fence_after();
-            if (tr && warp == 8 && tile_count < 100) trace[2048 + tile_count * 2] = clock64();
-            float acc[KPAD];
+            if (tr && warp == T8_PWARPS && tile_count < 100) trace[2048 + tile_count * 2] = clock64();
+            const long long r = (long long)tile * 128 + row;
+            float4* dst = reinterpret_cast<float4*>(llf + (r < C ? r : 0) * ldf);
 #pragma unroll
             for (int c = 0; c < KPAD / 8; ++c) {
                 uint32_t hi[8], lo[8];
                 tc_ld8(tmem + lane_base + set * N + c * 8, hi);
                 tc_ld8(tmem + lane_base + set * N + KPAD + c * 8, lo);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float v[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    acc[c * 8 + i] = neg_q * (float)(int)((hi[i] << 8) + lo[i]);
+                for (int i = 0; i < 8; ++i) v[i] = neg_q * (float)(int)((hi[i] << 8) + lo[i]);
+                if (r < C) {
+                    dst[2 * c] = make_float4(v[0], v[1], v[2], v[3]);
+                    dst[2 * c + 1] = make_float4(v[4], v[5], v[6], v[7]);
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[set]);
-            const long long r = (long long)tile * 128 + row;
-            if (r < C) {
-                float4* dst = reinterpret_cast<float4*>(llf + r * ldf);
-#pragma unroll
-                for (int i = 0; i < KPAD / 4; ++i)
-                    dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
-            }
-            if (tr && warp == 8 && tile_count < 100) trace[2048 + tile_count * 2 + 1] = clock64();
+            if (tr && warp == T8_PWARPS && tile_count < 100) trace[2048 + tile_count * 2 + 1] = clock64();
         }
-    } else if (warp == 12) {
+    } else if (warp == T8_PWARPS + 4) {
         // ---- MMA issuer: the whole warp walks the loops (warp-uniform control flow and operands,
         // so the descriptors live in uniform registers and an MMA is one instruction instead of a
         // register-to-uniform waterfall); one elected lane issues ----
@@ -306,7 +313,7 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) {
+    if (warp == T8_PWARPS + 4) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_TMEM_COLS)
                      : "memory");
     }
