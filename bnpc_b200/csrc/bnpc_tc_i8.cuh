@@ -14,23 +14,26 @@
 //      straight into TENSOR MEMORY (tcgen05.st; one TMEM lane per visit, four entries per 32-bit
 //      column): (word >> p) & 0x01010101 makes four matrix elements.
 //   B  the digit table in the K-major 128-byte-swizzled UMMA layout, one bulk async copy
-//      (cp.async.bulk) per stage; a stage is 256 reduction indices = 8 MMAs.
+//      (cp.async.bulk) per stage; a stage is 512 reduction indices = 16 MMAs.
 //   D  int32 accumulators in TMEM, two sets: the epilogue of a tile overlaps the next tile.
-// Warp roles (22 warps): 0-15 produce A (TMEM lane quarter = warp % 4; group warp / 4 expands one
-// 64-bit piece = 64 indices of every stage), 16-19 epilogue (TMEM -> registers -> one float row
-// per visit), 20 issues the MMAs (warp-uniform, one elected lane), 21 streams B.  The 8-byte piece of a
+// Warp roles (22 warps): 0-15 produce A (TMEM lane quarter = warp % 4; group warp / 4 expands two
+// 64-bit pieces = 128 indices of every stage), 16-19 epilogue (TMEM -> registers -> one float row
+// per visit), 20 issues the MMAs (warp-uniform, one elected lane), 21 streams B.  The 16-byte piece of a
 // visit's row that a producer thread expands per stage is prefetched T8_PF stages ahead (the
 // row gather is the long-latency part: visiting order is a random permutation of the cells),
 // across tile boundaries, with the cell indices two tiles ahead of that.
 // The order of the 32 reduction indices inside a word is a fixed permutation of the bit order
 // (element 4p+b <-> bit p+8b), the same for A and B.
 
-#define T8_NST 4                 /* pipeline stages (A in TMEM, B in shared memory) */
-#define T8_GROUPS 4              /* producer groups: each expands one 64-bit piece of every stage */
+#define T8_NST 2                 /* pipeline stages (A in TMEM, B in shared memory) */
+#define T8_GROUPS 4              /* producer groups: each expands two 64-bit pieces of every stage */
+#define T8_PIECES 8              /* 64-bit pieces of a row per stage (512 reduction indices, 16 MMAs):
+                                    tcgen05.st + wait::st + arrive cost ~550 cycles per warp and stage
+                                    whatever the size, so a stage is as large as tensor memory allows */
 #define T8_PWARPS (4 * T8_GROUPS)
 #define T8_THREADS (32 * (T8_PWARPS + 6))   /* producers, 4 epilogue warps, MMA warp, B loader */
 #define T8_A_COL0 256            /* first TMEM column of the A stages (accumulators use [0, 256)) */
-#define T8_A_STAGE_COLS 64       /* 256 one-byte entries per visit and stage */
+#define T8_A_STAGE_COLS 128      /* 512 one-byte entries per visit and stage */
 #define T8_PF 4                  /* row-piece prefetch depth, in stages */
 
 // D[tmem_d] (+)= A[tmem_a] * B[smem desc]: kind::i8 (u8 x u8 -> s32), A from tensor memory
@@ -99,7 +102,7 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
     const bool tr = trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
     constexpr int N = 2 * KPAD;
     constexpr uint32_t B_CHUNK_BYTES = (uint32_t)N * 128u;          // 128 reduction indices
-    constexpr uint32_t B_STAGE_BYTES = 2u * B_CHUNK_BYTES;
+    constexpr uint32_t B_STAGE_BYTES = (T8_PIECES / 2) * B_CHUNK_BYTES;
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(tc_smem + T8_NST * B_STAGE_BYTES);
     uint64_t* empty = full + T8_NST;
@@ -109,7 +112,7 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // the row of a visit is 2 planes x W words = W pieces of 64 bits; a stage is 4 pieces
     const int half = W / 2;
-    const int n_stages = W / 4;
+    const int n_stages = (W + T8_PIECES - 1) / T8_PIECES;           // (W is a multiple of 4: the last stage may be half)
     const int n_tiles = (C + 127) / 128;
     const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -131,8 +134,8 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
     const uint32_t tmem = *tmem_slot;
 
     if (warp < T8_PWARPS) {
-        // ---- A producers: one TMEM lane = one visit; group g = warp / 4 expands piece g of every
-        // stage (one aligned 8-byte load, 16 TMEM columns) ----
+        // ---- A producers: one TMEM lane = one visit; group g = warp / 4 expands pieces 2g, 2g+1 of
+        // every stage (one aligned 16-byte load, 32 TMEM columns) ----
         const int g = warp >> 2;
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -156,11 +159,12 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
         int cell_cur = cells ? __ldg(cells + r_cur * cell_stride) : (int)r_cur;
         int cell_n1 = cells ? __ldg(cells + r_n1 * cell_stride) : (int)r_n1;
         int cell_n2 = cells ? __ldg(cells + r_n2 * cell_stride) : (int)r_n2;
-        auto pf_next = [&](bool& ok) -> const uint2* {
-            ok = ok_cur && pf_q < total;
-            const int c = pf_sidx * 4 + g;                   // this thread's piece of the stage
+        auto pf_next = [&](bool& ok) -> const uint4* {
+            ok = ok_cur && pf_q < total && (pf_sidx * T8_PIECES + 2 * g) < W;    // (a half last stage: zeros)
+            const int c = pf_sidx * T8_PIECES + 2 * g;       // first of this thread's two pieces of the stage
             const long long base = (long long)cell_cur * W;
-            const uint32_t* src = (c < half) ? x1 + base + 2 * c : x0 + base + 2 * (c - half);
+            const int cc = (c < W) ? c : 0;
+            const uint32_t* src = (cc < half) ? x1 + base + 2 * cc : x0 + base + 2 * (cc - half);
             if (pf_q < total) {
                 ++pf_q;
                 if (++pf_sidx == n_stages) {
@@ -172,9 +176,9 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                     cell_n2 = cells ? __ldg(cells + r_n2 * cell_stride) : (int)r_n2;
                 }
             }
-            return reinterpret_cast<const uint2*>(src);
+            return reinterpret_cast<const uint4*>(src);
         };
-        uint2 ring[T8_PF];
+        uint4 ring[T8_PF];
         bool ring_ok[T8_PF];
 #pragma unroll
         for (int j = 0; j < T8_PF; ++j) ring[j] = __ldg(pf_next(ring_ok[j]));
@@ -185,17 +189,19 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
         for (long long q0 = 0; q0 < total; q0 += T8_PF) {
 #pragma unroll
             for (int j = 0; j < T8_PF; ++j) {
-                const uint2 raw = ring[j];
+                const uint4 raw = ring[j];
                 const bool ok = ring_ok[j];
                 ring[j] = __ldg(pf_next(ring_ok[j]));
                 if (q0 + j < total) {
-                    const uint2 w = ok ? raw : make_uint2(0u, 0u);
+                    const uint4 w = ok ? raw : make_uint4(0u, 0u, 0u, 0u);
                     const int slot = it % T8_NST;
-                    uint32_t regs[16];
+                    uint32_t regs[32];
 #pragma unroll
                     for (int p = 0; p < 8; ++p) {
                         regs[p] = (w.x >> p) & 0x01010101u;
                         regs[8 + p] = (w.y >> p) & 0x01010101u;
+                        regs[16 + p] = (w.z >> p) & 0x01010101u;
+                        regs[24 + p] = (w.w >> p) & 0x01010101u;
                     }
                     if (tr && warp == 0 && it < 300) trace[it * 3] = clock64();
                     if (pend >= 0) {
@@ -207,8 +213,8 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                     if (it >= T8_NST) mbar_wait(&empty[slot], ((it / T8_NST) - 1) & 1);
                     tc_fence_after();
                     if (tr && warp == 0 && it < 300) trace[it * 3 + 1] = clock64();
-                    const uint32_t dst = tmem + T8_A_COL0 + slot * T8_A_STAGE_COLS + g * 16 + lane_base;
-                    tc_st16(dst, regs);
+                    const uint32_t dst = tmem + T8_A_COL0 + slot * T8_A_STAGE_COLS + g * 32 + lane_base;
+                    tc_st32(dst, regs);
                     pend = slot;
                     if (tr && warp == 0 && it < 300) trace[it * 3 + 2] = clock64();
                     ++it;
@@ -274,9 +280,11 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                 if (tr && it < 250) trace[1024 + it * 4] = clock64();
                 const uint32_t b_addr = smem_base + slot * B_STAGE_BYTES;
                 const uint32_t a_addr = tmem_u + T8_A_COL0 + slot * T8_A_STAGE_COLS;
+                const int chunks = min(T8_PIECES / 2, W / 2 - sidx * (T8_PIECES / 2));
                 if (leader) {
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
+                    for (int cc = 0; cc < T8_PIECES / 2; ++cc) {
+                        if (cc >= chunks) break;
                         // K-major, 128B swizzle: LBO 1, SBO 1024 B, version 1, layout type 2
                         const uint64_t desc0 = (uint64_t)(((b_addr + cc * B_CHUNK_BYTES) >> 4) & 0x3FFFu) |
                                                (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -304,9 +312,9 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                 for (int sidx = 0; sidx < n_stages; ++sidx, ++it) {
                     const int slot = it % T8_NST;
                     if (it >= T8_NST) mbar_wait(&empty[slot], ((it / T8_NST) - 1) & 1);
-                    mbar_expect_tx(&full[slot], B_STAGE_BYTES);
-                    bulk_g2s(tc_smem + slot * B_STAGE_BYTES, Bg + (long long)sidx * B_STAGE_BYTES, B_STAGE_BYTES,
-                             &full[slot]);
+                    const uint32_t bytes = (uint32_t)min(T8_PIECES / 2, W / 2 - sidx * (T8_PIECES / 2)) * B_CHUNK_BYTES;
+                    mbar_expect_tx(&full[slot], bytes);
+                    bulk_g2s(tc_smem + slot * B_STAGE_BYTES, Bg + (long long)sidx * B_STAGE_BYTES, bytes, &full[slot]);
                 }
             }
         }
@@ -322,7 +330,7 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
 template <int KPAD>
 static int launch_ll_i8(const uint32_t* x1, const uint32_t* x0, int W, const int32_t* cells, int cell_stride,
                         int C, const uint8_t* Bg, float neg_q, float* llf, int ldf, cudaStream_t s) {
-    const size_t smem = (size_t)T8_NST * 2 * (2 * KPAD) * 128 + 256;
+    const size_t smem = (size_t)T8_NST * (T8_PIECES / 2) * (2 * KPAD) * 128 + 256;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(ll_matrix_i8_kernel<KPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
