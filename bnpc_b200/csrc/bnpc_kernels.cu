@@ -1105,18 +1105,20 @@ __device__ void sweep_sequencer_par(const bnpc_sweep_args_t& a, SweepShared& sh)
         const int nw = min(SW_WINDOW, n_rec - r0);
         const bnpc_visit_t* vis = vbuf + (g & 1) * SW_WINDOW;
         const bnpc_cand_t* cnd = cbuf + (g & 1) * SW_WINDOW;
-        // ---- this warp's records of the window, in order ----
-        int own = 0;
+        // ---- this warp's records of the window, in order (all owner bytes first, then the
+        // ballots, then the writes: no chain through the running count) ----
+        unsigned mine_mask[SW_WINDOW / 32];
 #pragma unroll
         for (int c = 0; c < SW_WINDOW / 32; ++c) {
             const int rec = c * 32 + lane;
-            bool mine = false;
-            if (rec < nw) {
-                const int o = sh.own_b[g & 1][rec];
-                mine = (o == 0xff) ? (w == 0) : (o == w);
-            }
-            const unsigned m = __ballot_sync(FULL, mine);
-            if (mine) sh.own_idx[w][own + __popc(m & lt_mask)] = (unsigned short)rec;
+            const int o = (rec < nw) ? sh.own_b[g & 1][rec] : 0xfe;
+            mine_mask[c] = __ballot_sync(FULL, (o == 0xff) ? (w == 0) : (o == w));
+        }
+        int own = 0;
+#pragma unroll
+        for (int c = 0; c < SW_WINDOW / 32; ++c) {
+            const unsigned m = mine_mask[c];
+            if ((m >> lane) & 1u) sh.own_idx[w][own + __popc(m & lt_mask)] = (unsigned short)(c * 32 + lane);
             own += __popc(m);
         }
         __syncwarp();
@@ -1712,9 +1714,10 @@ __global__ void group_members_kernel(const int32_t* __restrict__ assign, int N,
     members[seg_off[r] + base + __popc(peers & ((1u << lane) - 1u))] = n;
 }
 
-#define SS_CHUNK 2040         /* rows per CTA: 64 per thread at the widest rows (byte-wide counters hold 255) */
-#define SS_THREADS 1024
-// grid (chunks, R, word blocks): a CTA of 1024 threads counts ones/zeros per mutation over up to SS_CHUNK members
+#define SS_CHUNK 512          /* rows per CTA (byte-wide counters hold 255 rows per thread) */
+#define SS_THREADS 256        /* 8 row groups at the widest rows: 1024 threads over 2040-row chunks were
+                                 2x slower (32-way contention on the shared-memory counters) */
+// grid (chunks, R, word blocks): a CTA counts ones/zeros per mutation over up to SS_CHUNK members
 // of one segment for a block of 32 mutation words.  A thread owns one word column and strides
 // over the rows, so that a warp reads whole 128-byte row pieces (coalesced); the 32 per-bit
 // counters of a word are kept as 8 registers of four byte-wide counters each
