@@ -281,3 +281,44 @@ def test_approximate_rows_within_their_error_bound(L, shape, rows):
         assert (np.abs(got - want) <= sharp).all()
     assert (np.abs(got - want) <= bound).all()
     assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max() + 1e-3 + (0.02 if rows == 'tcgen05_i8' else 0)
+
+
+@pytest.mark.parametrize('nf', [1, 37, 1024, 1025, 5000, 20000])
+@pytest.mark.parametrize('spread', [0.02, 3.0])
+def test_rg_scan_matches_the_serial_scan(L, nf, spread):
+    """One restricted Gibbs scan (libs/CRP.py:609-632) on random two-column log-likelihoods:
+    the device scan (parallel thresholds + the speculative-segment integer pass + write-back)
+    against the serial scan in the reference's arithmetic.  spread = 0.02: nearly every cell is
+    ambiguous (thresholds all over the range, the speculation is corrected often); 3.0: most
+    cells are decisive."""
+    from oracle.crp_oracle import log_crp_weight, log_normalise_pair
+    rng = np.random.default_rng(nf + int(100 * spread))
+    n = nf + 2
+    alpha = 7.5
+    ll2 = np.stack([rng.normal(-300, 20, nf)] * 2, axis=1) + rng.normal(0, spread, (nf, 2))
+    perm = rng.permutation(nf).astype(np.int32)
+    u = rng.random(nf)
+    half0 = (rng.random(nf) < 0.4).astype(np.int32)
+    # serial model
+    half = half0.astype(np.float64).copy()
+    lq_want = np.zeros(nf)
+    with np.errstate(divide='raise', invalid='raise', over='ignore', under='ignore'):
+        for s in range(nf):
+            c = perm[s]
+            half[c] = -1
+            n_j = np.nansum(half) + 2
+            n_i = n - n_j - 1
+            lprob = log_normalise_pair(ll2[c] + log_crp_weight(np.array([n_i, n_j]), n, alpha))
+            p = np.exp(lprob)
+            side = 0 if u[s] < p[0] / (p[0] + p[1]) else 1
+            half[c] = side
+            lq_want[c] = lprob[side]
+    ll2_d = dev(ll2, torch.float64)
+    perm_d, u_d, half_d = dev(perm, torch.int32), dev(u, torch.float64), dev(half0, torch.int32)
+    lq_d = torch.zeros(nf, dtype=torch.float64, device='cuda')
+    work = torch.zeros(2 * nf + 16, dtype=torch.int32, device='cuda')
+    L.rg_scan(ll2_d.data_ptr(), 2, n, perm_d.data_ptr(), u_d.data_ptr(), half_d.data_ptr(), alpha, 0, None,
+              None, -1, lq_d.data_ptr(), work.data_ptr(), sp())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(half_d.cpu().numpy(), half.astype(np.int32))
+    np.testing.assert_allclose(lq_d.cpu().numpy(), lq_want, rtol=1e-12, atol=1e-300)
