@@ -440,7 +440,7 @@ def main():
         if rank != 0:
             return
         chains = args.chains_per_gpu * max(1, args.gpus)
-        res = run_cpu(cfg, chains, args.steps, min(args.warmup, 1), 150.0, args.cpu_sample_cells)
+        res = run_cpu(cfg, chains, args.steps, min(args.warmup, 1), 100.0, args.cpu_sample_cells)
         out = dict(impl='reference', metric=METRIC, value=res['value'], unit='chain-steps/s',
                    n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                    ms_per_step=1e3 * res['cores'] / res['value'] if res['value'] else None,
