@@ -2463,14 +2463,17 @@ int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const
     LAUNCH_CHECK("compact_scan");
     compact_index_kernel<<<nb, CAND_THREADS, 0, s>>>(opt_t0, C, blk, idx_c);
     LAUNCH_CHECK("compact_index");
-    const size_t smem = sizeof(double2) * 32 * EX_WORDS * (size_t)K;
-    static bool attr_done = false;
-    if (!attr_done) {
-        ce = cudaFuncSetAttribute(gibbs_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    // BNPC_EXACT_STAGING=used: stage only the columns a CTA's visits use (32 KB of shared memory
+    // whatever K is); default: all K columns per round (the variant of the round-1 measurements)
+    static int all_cols = -1;
+    if (all_cols < 0) {
+        const char* env = getenv("BNPC_EXACT_STAGING");
+        all_cols = (env && env[0] == 'u') ? 0 : 1;
+        ce = cudaFuncSetAttribute(gibbs_exact_allcols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(double2) * 32 * EX_WORDS * BNPC_LEAN_MAXK));
         if (ce != cudaSuccess) return fail("gibbs_exact smem attribute", ce);
-        attr_done = true;
     }
+    const size_t smem = all_cols ? sizeof(double2) * 32 * EX_WORDS * (size_t)K : sizeof(double2) * 32 * EX_WORDS * EX_COLS;
     // processing order: uncertain visits grouped by their own cluster (see exact_hist_kernel)
     exact_hist_kernel<<<cdiv(C, 256), 256, 0, s>>>(opt_t0, idx_c, st, comp);
     LAUNCH_CHECK("exact_hist");
@@ -2479,9 +2482,14 @@ int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const
     exact_scatter_kernel<<<cdiv(C, 256), 256, 0, s>>>(opt_t0, idx_c, st, comp, order);
     LAUNCH_CHECK("exact_scatter");
     // the number of uncertain visits lives on the device: blocks beyond it exit at once
-    gibbs_exact_kernel<<<cdiv(C, EX_THREADS), EX_THREADS, smem, s>>>(
-        x1, x0, W, M, reinterpret_cast<const double2*>(lp), K, visit_t0, opt_t0, idx_c, st, visit_c, cand_c,
-        log_n, c_norm, comp, order);
+    if (all_cols)
+        gibbs_exact_allcols_kernel<<<cdiv(C, EX_THREADS), EX_THREADS, smem, s>>>(
+            x1, x0, W, M, reinterpret_cast<const double2*>(lp), K, visit_t0, opt_t0, idx_c, st, visit_c, cand_c,
+            log_n, c_norm, comp, order);
+    else
+        gibbs_exact_kernel<<<cdiv(C, EX_THREADS), EX_THREADS, smem, s>>>(
+            x1, x0, W, M, reinterpret_cast<const double2*>(lp), K, visit_t0, opt_t0, idx_c, st, visit_c, cand_c,
+            log_n, c_norm, comp, order);
     LAUNCH_CHECK("gibbs_exact");
     components_kernel<<<1, BNPC_LEAN_MAXK, 0, s>>>(comp, K, SW_PAR_WARPS);
     LAUNCH_CHECK("components");

@@ -210,6 +210,7 @@ exact_scatter_kernel(const bnpc_opt_t* __restrict__ opt, const int32_t* __restri
 
 #define EX_THREADS 128
 #define EX_WORDS 4            /* words of a row (128 mutations) staged per round */
+#define EX_COLS 16            /* columns staged per pass */
 // One thread per uncertain visit: FP64 log-likelihood of each of its options, then the option
 // weights exactly as gibbs_candidates_kernel derives them from the FP64 matrix.  The row is summed
 // in four interleaved partial sums per option (word w goes to partial w % 4; the chain of dependent
@@ -219,6 +220,175 @@ exact_scatter_kernel(const bnpc_opt_t* __restrict__ opt, const int32_t* __restri
 // ~1e-13 relative, far inside the guard band of the sweep's fast draws (SW_GUARD).
 __global__ void __launch_bounds__(EX_THREADS)
 gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
+                   const double2* __restrict__ lp, int K, const bnpc_visit_t* __restrict__ visit,
+                   const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ idx_c,
+                   int32_t* __restrict__ st, bnpc_visit_t* __restrict__ visit_c,
+                   bnpc_cand_t* __restrict__ cand_c, double slack, double c_norm, int32_t* __restrict__ comp,
+                   const int32_t* __restrict__ order) {
+    extern __shared__ __align__(16) unsigned char ex_smem[];
+    __shared__ unsigned long long s_adj[BNPC_LEAN_MAXK];
+    __shared__ int s_num[BNPC_LEAN_MAXK];
+    __shared__ unsigned long long s_used;
+    __shared__ int s_cols[BNPC_LEAN_MAXK];
+    double2* tile = reinterpret_cast<double2*>(ex_smem);          // [32 * EX_WORDS][EX_COLS]
+    const double* tile_d = reinterpret_cast<const double*>(ex_smem);
+    const int n_unc = st[BNPC_ST_NUNC];
+    if (blockIdx.x * EX_THREADS >= n_unc) return;
+    if (threadIdx.x < BNPC_LEAN_MAXK) { s_adj[threadIdx.x] = 0ull; s_num[threadIdx.x] = 0; }
+    const int q = blockIdx.x * EX_THREADS + threadIdx.x;
+    const bool live = q < n_unc;
+    const int j = live ? order[q] : order[0];        // slot of the visit among the compacted records
+    const int r = idx_c[j];
+    bnpc_visit_t v = visit[r];
+    const bnpc_opt_t o = opt[r];
+    const int nn = (live && o.n_opt <= BNPC_MAX_OPT) ? o.n_opt : 0;
+    int col[BNPC_MAX_OPT];
+    double part[EX_WORDS][BNPC_MAX_OPT];
+#pragma unroll
+    for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+        col[i] = (i < nn) ? o.col[i] : 0;
+#pragma unroll
+        for (int q = 0; q < EX_WORDS; ++q) part[q][i] = 0.0;
+    }
+    int n_max = nn;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) n_max = max(n_max, __shfl_xor_sync(FULL, n_max, s));
+    // Only the columns that occur among the options of THIS CTA's visits are staged (the visits
+    // arrive grouped by own cluster: a handful of columns instead of all K), EX_COLS per pass:
+    // 32 KB of shared memory whatever K is (three CTAs per SM), K/5 of the staging traffic.
+    if (threadIdx.x == 0) s_used = 0ull;
+    __syncthreads();
+    {
+        unsigned long long mask = 0ull;
+#pragma unroll
+        for (int i = 0; i < BNPC_MAX_OPT; ++i)
+            if (i < nn) mask |= 1ull << col[i];
+        if (mask) atomicOr(&s_used, mask);
+    }
+    __syncthreads();
+    const unsigned long long used = s_used;
+    const int n_used = __popcll(used);
+    if (threadIdx.x < BNPC_LEAN_MAXK && ((used >> threadIdx.x) & 1ull))
+        s_cols[__popcll(used & ((1ull << threadIdx.x) - 1ull))] = threadIdx.x;
+    int lcol[BNPC_MAX_OPT];                                    // index of the option's column among the used ones
+#pragma unroll
+    for (int i = 0; i < BNPC_MAX_OPT; ++i) lcol[i] = (i < nn) ? __popcll(used & ((1ull << col[i]) - 1ull)) : -1;
+    const uint4* p1 = reinterpret_cast<const uint4*>(x1 + (long long)v.cell * W);
+    const uint4* p0 = reinterpret_cast<const uint4*>(x0 + (long long)v.cell * W);
+    const int words = (M + 31) >> 5;
+    for (int c0 = 0; c0 < n_used; c0 += EX_COLS) {
+        const int nc = min(EX_COLS, n_used - c0);
+        int off[BNPC_MAX_OPT];                                 // 2 * column slot in this pass, or -1
+#pragma unroll
+        for (int i = 0; i < BNPC_MAX_OPT; ++i)
+            off[i] = (lcol[i] >= c0 && lcol[i] < c0 + nc) ? 2 * (lcol[i] - c0) : -1;
+        for (int w0 = 0; w0 < words; w0 += EX_WORDS) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < 32 * EX_WORDS * nc; i += EX_THREADS) {
+                const int kk = i / (32 * EX_WORDS), mm = i % (32 * EX_WORDS), m = w0 * 32 + mm;   // coalesced along mutations
+                tile[mm * EX_COLS + kk] = (m < M) ? lp[(long long)s_cols[c0 + kk] * M + m] : make_double2(0.0, 0.0);
+            }
+            __syncthreads();
+            if (n_max == 0 || nn == 0) continue;
+            const uint4 a = p1[w0 >> 2], b = p0[w0 >> 2];         // rows are padded with zeros to W words
+            const uint32_t u1[EX_WORDS] = {a.x, a.y, a.z, a.w}, u0[EX_WORDS] = {b.x, b.y, b.z, b.w};
+#pragma unroll 2
+            for (int bit = 0; bit < 32; ++bit) {
+#pragma unroll
+                for (int q = 0; q < EX_WORDS; ++q) {
+                    const uint32_t b1 = (u1[q] >> bit) & 1u, b0 = (u0[q] >> bit) & 1u;
+                    // the entry selects log p1 (.x), log p0 (.y) or nothing
+                    const double* t = tile_d + (q * 32 + bit) * 2 * EX_COLS + (b1 ? 0 : 1);
+                    const bool any = (b1 | b0) != 0u;
+#pragma unroll
+                    for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+                        if (i >= n_max) break;                               // warp-uniform
+                        if (off[i] >= 0) {
+                            const double term = t[off[i]];
+                            part[q][i] += any ? term : 0.0;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    double acc[BNPC_MAX_OPT];
+#pragma unroll
+    for (int i = 0; i < BNPC_MAX_OPT; ++i) acc[i] = (part[0][i] + part[1][i]) + (part[2][i] + part[3][i]);
+    // (every thread stays for the block-wide publication of the option graph below)
+    // same selection and weights as gibbs_candidates_kernel, on the exact values
+    const double lnew_ll = v.lnew + c_norm;
+    bnpc_cand_t out;
+    double val[BNPC_MAX_OPT];
+#pragma unroll
+    for (int i = 0; i < BNPC_MAX_OPT; ++i) { out.e[i] = 0.0; out.col[i] = 0; val[i] = -BNPC_INF; }
+    out.pad[0] = out.pad[1] = out.pad[2] = 0;
+    int n = BNPC_MAX_OPT + 1, i_old = 0;
+    double ref = 0.0, e_new = 0.0, e_max = 1.0;
+    int c_old = -1;
+    if (nn > 0) {
+        double v_old = 0.0;
+#pragma unroll
+        for (int i = 0; i < BNPC_MAX_OPT; ++i)
+            if (i == o.i_old) { v_old = acc[i]; c_old = col[i]; }
+        const double thr = v_old - 40.0 - slack;
+        n = 0;
+        ref = fmax(v_old, lnew_ll);
+#pragma unroll
+        for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+            if (i < nn) {
+                const bool own = (i == o.i_old);
+                if (own || acc[i] > thr) {
+                    if (own) i_old = n;
+#pragma unroll
+                    for (int s = 0; s < BNPC_MAX_OPT; ++s)
+                        if (s == n) { val[s] = acc[i]; out.col[s] = (uint16_t)col[i]; }
+                    ref = fmax(ref, acc[i]);
+                    ++n;
+                }
+            }
+        }
+        e_max = 0.0;
+#pragma unroll
+        for (int i = 0; i < BNPC_MAX_OPT; ++i)
+            if (i < n) { out.e[i] = exp(val[i] - ref); e_max = fmax(e_max, out.e[i]); }
+        e_new = exp(lnew_ll - ref);
+    } else if (live) {
+        atomicAdd(&st[BNPC_ST_NMANY], 1);
+    }
+    if (live) {
+        v.e_new = e_new;
+        v.ref = ref;
+        v.c_old = c_old;
+        v.n_opt = n;
+        v.i_old = i_old;
+        v.flags = 0;
+        v.e_max = __double2float_ru(e_max);
+        visit_c[j] = v;
+        cand_c[j] = out;
+        // option graph on the columns: the visit links its own cluster with every rival
+        if (nn > 0 && c_old >= 0) {
+            unsigned long long mask = 0ull;
+#pragma unroll
+            for (int i = 0; i < BNPC_MAX_OPT; ++i)
+                if (i < n) mask |= 1ull << out.col[i];
+            atomicOr(&s_adj[c_old], mask);
+            atomicAdd(&s_num[c_old], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        unsigned long long* adj = reinterpret_cast<unsigned long long*>(comp);
+        if (s_adj[threadIdx.x]) atomicOr(&adj[threadIdx.x], s_adj[threadIdx.x]);
+        if (s_num[threadIdx.x]) atomicAdd(&comp[128 + threadIdx.x], s_num[threadIdx.x]);
+    }
+}
+
+// The same kernel staging ALL K columns per round (shared memory 2 KB x K per CTA): the variant
+// that ran through the round-1 measurements and the default (BNPC_EXACT_STAGING=used selects the
+// column-selective kernel above).
+__global__ void __launch_bounds__(EX_THREADS)
+gibbs_exact_allcols_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
                    const double2* __restrict__ lp, int K, const bnpc_visit_t* __restrict__ visit,
                    const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ idx_c,
                    int32_t* __restrict__ st, bnpc_visit_t* __restrict__ visit_c,
@@ -353,6 +523,7 @@ gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__
         if (s_num[threadIdx.x]) atomicAdd(&comp[128 + threadIdx.x], s_num[threadIdx.x]);
     }
 }
+
 
 // comp layout (int32[256]): [0,128) adjacency masks (64 x uint64), [128,192) uncertain visits per
 // column, [192,256) owner warp per column.  One block of 64 threads: connected components of the
