@@ -2463,12 +2463,13 @@ int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const
     LAUNCH_CHECK("compact_scan");
     compact_index_kernel<<<nb, CAND_THREADS, 0, s>>>(opt_t0, C, blk, idx_c);
     LAUNCH_CHECK("compact_index");
-    // BNPC_EXACT_STAGING=used: stage only the columns a CTA's visits use (32 KB of shared memory
-    // whatever K is); default: all K columns per round (the variant of the round-1 measurements)
+    // default: stage only the columns a CTA's visits use (32 KB of shared memory whatever K is;
+    // Gibbs step 2.50 -> 2.09 ms at K = 59 with every visit uncertain); BNPC_EXACT_STAGING=all
+    // selects the kernel that stages all K columns per round
     static int all_cols = -1;
     if (all_cols < 0) {
         const char* env = getenv("BNPC_EXACT_STAGING");
-        all_cols = (env && env[0] == 'u') ? 0 : 1;
+        all_cols = (env && env[0] == 'a') ? 1 : 0;
         ce = cudaFuncSetAttribute(gibbs_exact_allcols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(double2) * 32 * EX_WORDS * BNPC_LEAN_MAXK));
         if (ce != cudaSuccess) return fail("gibbs_exact smem attribute", ce);

@@ -385,8 +385,7 @@ gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__
 }
 
 // The same kernel staging ALL K columns per round (shared memory 2 KB x K per CTA): the variant
-// that ran through the round-1 measurements and the default (BNPC_EXACT_STAGING=used selects the
-// column-selective kernel above).
+// of most round-1 measurements, kept selectable (BNPC_EXACT_STAGING=all) for comparison.
 __global__ void __launch_bounds__(EX_THREADS)
 gibbs_exact_allcols_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
                    const double2* __restrict__ lp, int K, const bnpc_visit_t* __restrict__ visit,
