@@ -40,6 +40,21 @@ static int bad_arg(const char* what) {
     return 2;
 }
 static std::atomic<long long> g_launches{0};
+
+// cudaFuncSetAttribute is per device: a process that drives several GPUs (chains spread over the
+// visible devices by one process) must opt every device in to the large dynamic shared memory of
+// a kernel.  `done` is the kernel's bit mask of devices already served.
+template <typename F>
+static int ensure_dyn_smem(F func, int bytes, std::atomic<unsigned long long>& done, const char* what) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return 0;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return fail(what, e);
+    done.fetch_or(bit, std::memory_order_release);
+    return 0;
+}
 #define LAUNCH_CHECK(name)                                        \
     do {                                                          \
         cudaError_t e__ = cudaGetLastError();                     \
@@ -2277,12 +2292,8 @@ int bnpc_ll_matrix(const uint32_t* x1, const uint32_t* x0, int W, int M, const i
     if (W % 4 != 0) return bad_arg("W must be a multiple of 4");
     if (K <= 2 && sizeof(double2) * (size_t)K * W * 32 <= 200 * 1024) {
         const size_t smem = sizeof(double2) * (size_t)K * W * 32;
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaError_t ce = cudaFuncSetAttribute(ll_few_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (ce != cudaSuccess) return fail("ll_few smem attribute", ce);
-            attr_done = true;
-        }
+        static std::atomic<unsigned long long> attr_done{0};
+        if (int rc = ensure_dyn_smem(ll_few_kernel, 200 * 1024, attr_done, "ll_few smem attribute")) return rc;
         ll_few_kernel<<<cdiv(C, LLP_CELLS), 8 * LLP_CELLS, smem, (cudaStream_t)stream>>>(
             x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const double2*>(lp), K, ll, ldk);
         LAUNCH_CHECK("ll_few");
@@ -2470,9 +2481,11 @@ int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const
     if (all_cols < 0) {
         const char* env = getenv("BNPC_EXACT_STAGING");
         all_cols = (env && env[0] == 'a') ? 1 : 0;
-        ce = cudaFuncSetAttribute(gibbs_exact_allcols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(sizeof(double2) * 32 * EX_WORDS * BNPC_LEAN_MAXK));
-        if (ce != cudaSuccess) return fail("gibbs_exact smem attribute", ce);
+    }
+    if (all_cols) {
+        static std::atomic<unsigned long long> attr_done{0};
+        if (int rc = ensure_dyn_smem(gibbs_exact_allcols_kernel, (int)(sizeof(double2) * 32 * EX_WORDS * BNPC_LEAN_MAXK),
+                                     attr_done, "gibbs_exact smem attribute")) return rc;
     }
     const size_t smem = all_cols ? sizeof(double2) * 32 * EX_WORDS * (size_t)K : sizeof(double2) * 32 * EX_WORDS * EX_COLS;
     // processing order: uncertain visits grouped by their own cluster (see exact_hist_kernel)
@@ -2515,16 +2528,10 @@ int bnpc_gibbs_sweep(const bnpc_sweep_args_t* a, int block_threads, void* stream
     if (a->t_begin < a->t_epoch0 || a->t_end - a->t_epoch0 > a->ldx) return bad_arg("sweep range vs ldx");
     // 256 threads leave the full register budget to the sequencer warp; long lists want 1024
     const size_t smem = sizeof(SweepShared);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e1 = cudaFuncSetAttribute(gibbs_sweep_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaError_t e2 = cudaFuncSetAttribute(gibbs_sweep_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaError_t e3 = cudaFuncSetAttribute(gibbs_sweep_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e3 != cudaSuccess) return fail("gibbs_sweep smem attribute", e3);
-        if (e1 != cudaSuccess) return fail("gibbs_sweep smem attribute", e1);
-        if (e2 != cudaSuccess) return fail("gibbs_sweep smem attribute", e2);
-        attr_done = true;
-    }
+    static std::atomic<unsigned long long> done256{0}, done512{0}, done1024{0};
+    if (int rc = ensure_dyn_smem(gibbs_sweep_kernel<256>, (int)smem, done256, "gibbs_sweep smem attribute")) return rc;
+    if (int rc = ensure_dyn_smem(gibbs_sweep_kernel<512>, (int)smem, done512, "gibbs_sweep smem attribute")) return rc;
+    if (int rc = ensure_dyn_smem(gibbs_sweep_kernel<1024>, (int)smem, done1024, "gibbs_sweep smem attribute")) return rc;
     if (block_threads <= 256)
         gibbs_sweep_kernel<256><<<1, block_threads, smem, (cudaStream_t)stream>>>(*a);
     else if (block_threads <= 512)

@@ -18,8 +18,10 @@
 // trip of a stage is amortised; 2-stage pipeline on mbarriers; tcgen05.commit frees a stage.
 // Measured (B200, 100k x 1k x 24): 56 us; ~90 cycles per MMA whatever N is -- with N = 2*Kp <= 128
 // output columns the instruction is bound by reading its 4 KB A operand from tensor memory, not
-// by the tensor pipe (62 cycles per MMA at N = 128).  Next lever: 8-bit A (kind::f8f6f4).  The order of the 64 reduction indices inside a stage is a fixed permutation of the
-// bit order (element 2p+h <-> bit p+16h), the same for A and B.
+// by the tensor pipe (62 cycles per MMA at N = 128).  The production rows are the integer kernel of
+// bnpc_tc_i8.cuh (8-bit A: half the instructions per tile, exact accumulation); this one stays as an
+// independent route (lean = 2) for the parity tests.  The order of the 64 reduction indices inside
+// a stage is a fixed permutation of the bit order (element 2p+h <-> bit p+16h), the same for A and B.
 #include <cuda_bf16.h>
 
 #define TC_NST 2
@@ -284,13 +286,8 @@ template <int KPAD>
 static int launch_ll_tc(const uint32_t* x1, const uint32_t* x0, int W, const int32_t* cells, int cell_stride,
                         int C, const uint16_t* Bg, float* llf, int ldf, cudaStream_t s) {
     const size_t smem = (size_t)TC_NST * TC_CPS * (2 * KPAD) * 128 + 256;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(ll_matrix_tc_kernel<KPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return fail("ll_matrix_tc smem attribute", e);
-        attr_done = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    if (int rc = ensure_dyn_smem(ll_matrix_tc_kernel<KPAD>, (int)smem, attr_done, "ll_matrix_tc smem attribute")) return rc;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = cdiv(C, 128);

@@ -331,13 +331,8 @@ template <int KPAD>
 static int launch_ll_i8(const uint32_t* x1, const uint32_t* x0, int W, const int32_t* cells, int cell_stride,
                         int C, const uint8_t* Bg, float neg_q, float* llf, int ldf, cudaStream_t s) {
     const size_t smem = (size_t)T8_NST * (T8_PIECES / 2) * (2 * KPAD) * 128 + 256;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(ll_matrix_i8_kernel<KPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return fail("ll_matrix_i8 smem attribute", e);
-        attr_done = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    if (int rc = ensure_dyn_smem(ll_matrix_i8_kernel<KPAD>, (int)smem, attr_done, "ll_matrix_i8 smem attribute")) return rc;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = cdiv(C, 128);
