@@ -1,8 +1,12 @@
 #!/usr/bin/env python3
-"""Command line of BnpC on the B200 path: the options of the reference's `run_BnpC.py`
-(cbg-ethz/BnpC v0.2.1, run_BnpC.py:13-196) with the same names, defaults and meaning; chains run as
-host threads + CUDA streams (or one rank per GPU under torchrun) instead of forked processes.
-Plots are not produced (no matplotlib in this build): the run behaves as with `-np`.
+"""Command line of BnpC on the B200 path.
+
+The option names, defaults and meaning are those of the reference's command line (cbg-ethz/BnpC
+v0.2.1, run_BnpC.py:13-196), declared here as one table; the flow of `main` is the reference's
+(run_BnpC.py:244-292): load the matrix, build the model, run the chains, infer the requested
+estimators, write the text outputs.  Chains run as host threads + CUDA streams of one process, or
+one rank per GPU under torchrun, instead of forked processes.  Plots are not part of this build:
+a run behaves as with `-np`.
 
     python run_BnpC.py example.csv -n 8 -s 5000 -e posterior MAP -o out/
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 run_BnpC.py data.csv -n 8
@@ -14,77 +18,88 @@ import libs.dpmmIO as io
 from libs.MCMC import MCMC, dist_info
 
 
-def _in_range(lo, hi, open_ends):
-    def check(val):
-        val = float(val)
-        bad = (val <= lo or val >= hi) if open_ends else (val < lo or val > hi)
-        if bad:
-            brackets = '0 < x < 1' if open_ends else f'{lo} <= x <= {hi}'
-            raise argparse.ArgumentTypeError(f'Invalid value: {val}. Values need to be {brackets}')
-        return val
-    return check
+def _bounded(lo, hi, strict):
+    """argparse type: a float inside (lo, hi) if strict, else inside [lo, hi]"""
+    def convert(text):
+        x = float(text)
+        outside = (x <= lo or x >= hi) if strict else (x < lo or x > hi)
+        if outside:
+            span = f'{lo} < x < {hi}' if strict else f'{lo} <= x <= {hi}'
+            raise argparse.ArgumentTypeError(f'Invalid value: {x}. Values need to be {span}')
+        return x
+    return convert
+
+
+RATIO = _bounded(0, 1, True)
+PERCENT = _bounded(0, 1, False)
+PSRF = _bounded(1, 1.5, False)
+
+# (group, flags, argparse keywords); `None` = top level
+OPTIONS = [
+    (None, ('input',), dict(help='matrix file: mutations x cells (cells x mutations with -t), entries 0|1, '
+                                 'missing as 3 or empty, separated by blanks, tabs or commas')),
+    (None, ('-t', '--transpose'), dict(action='store_false', help='do NOT transpose the input (default: transpose)')),
+    (None, ('--debug',), dict(action='store_true', default=False, help='one chain in the main thread')),
+    ('model', ('-FN', '--falseNegative'), dict(type=float, default=-1, help='fixed FN rate (with -FP: rates are not learned)')),
+    ('model', ('-FP', '--falsePositive'), dict(type=float, default=-1, help='fixed FP rate')),
+    ('model', ('-FN_m', '--falseNegative_mean'), dict(type=RATIO, default=0.2, help='prior mean of FN [0.2]')),
+    ('model', ('-FN_sd', '--falseNegative_std'), dict(type=RATIO, default=0.1, help='prior sd of FN [0.1]')),
+    ('model', ('-FP_m', '--falsePositive_mean'), dict(type=RATIO, default=0.01, help='prior mean of FP [0.01]')),
+    ('model', ('-FP_sd', '--falsePositive_std'), dict(type=RATIO, default=0.01, help='prior sd of FP [0.01]')),
+    ('model', ('-ap', '--DPa_prior'), dict(type=float, nargs=2, default=[-1, -1],
+                                           help='Gamma(a, b) prior of the concentration; negative: (sqrt(cells), 1)')),
+    ('model', ('-pp', '--param_prior'), dict(type=float, nargs=2, default=[.25, .25],
+                                             help='Beta(a, b) prior of the cluster parameters [.25 .25]')),
+    ('model', ('-fa', '--fixed_assignment'), dict(type=str, default='', help='file with an assignment that is kept fixed')),
+    ('MCMC', ('-n', '--chains'), dict(type=int, default=1, help='chains [1]')),
+    ('MCMC', ('-s', '--steps'), dict(type=int, default=5000, help='steps per chain [5000]')),
+    ('MCMC', ('-r', '--runtime'), dict(type=int, default=-1, help='minutes to run (overrides -s)')),
+    ('MCMC', ('-ls', '--lugsail'), dict(type=PSRF, default=-1, help='run until the lugsail PSRF falls below this cutoff')),
+    ('MCMC', ('-b', '--burn_in'), dict(type=PERCENT, default=0.33, help='burn-in fraction [0.33]')),
+    ('MCMC', ('-cup', '--conc_update_prob'), dict(type=PERCENT, default=0.25, help='P(update concentration) per step [0.25]')),
+    ('MCMC', ('-eup', '--error_update_prob'), dict(type=PERCENT, default=0.25, help='P(update error rates) per step [0.25]')),
+    ('MCMC', ('-smp', '--split_merge_prob'), dict(type=PERCENT, default=0.33, help='P(split/merge move) per step [0.33]')),
+    ('MCMC', ('-sms', '--split_merge_steps'), dict(type=int, default=3, help='restricted Gibbs scans per split/merge move [3]')),
+    ('MCMC', ('-smr', '--split_merge_ratios'), dict(type=PERCENT, nargs=2, default=[0.75, 0.25], help='split : merge [0.75 0.25]')),
+    ('MCMC', ('-e', '--estimator'), dict(type=str, default='posterior', nargs='+', choices=['posterior', 'ML', 'MAP'],
+                                         help='estimator(s) of the latent variables [posterior]')),
+    ('MCMC', ('-sc', '--single_chains'), dict(action='store_true', default=False, help='estimators per chain')),
+    ('MCMC', ('--seed',), dict(type=int, default=-1, help='seed of the chain seeds [random]')),
+    ('output', ('-o', '--output'), dict(type=str, default='', help='output directory [next to the input]')),
+    ('output', ('-v', '--verbosity'), dict(type=int, default=1, choices=[0, 1, 2], help='stdout verbosity [1]')),
+    ('output', ('-np', '--no_plots'), dict(action='store_true', default=False, help='accepted; plots are never drawn')),
+    ('output', ('-tr', '--tree'), dict(type=str, default='', help='accepted for compatibility (no tree plots)')),
+    ('output', ('-tc', '--true_clusters'), dict(type=str, default='', help='true assignment: ARI and V-measure are written')),
+    ('output', ('-td', '--true_data'), dict(type=str, default='', help='true genotypes: the Hamming distance is written')),
+]
 
 
 def parse_args(argv=None):
-    ratio, percent, psrf = _in_range(0, 1, True), _in_range(0, 1, False), _in_range(1, 1.5, False)
-    p = argparse.ArgumentParser(prog='BnpC', usage='python3 run_BnpC.py <DATA> [options]',
-                                description='*** Clustering of single cell data based on a Dirichlet process. ***')
-    p.add_argument('--version', action='version', version='0.2.1 (bnpc-b200)')
-    p.add_argument('input', help='Path to the input matrix (n cells x m mutations after the default transpose; '
-                                 '1|0 entries, missing values as 3 or empty; blank-, tab- or comma-separated).')
-    p.add_argument('-t', '--transpose', action='store_false', help='Transpose the input matrix. Default = True.')
-    p.add_argument('--debug', action='store_true', default=False, help='Run a single chain in the main thread.')
+    parser = argparse.ArgumentParser(prog='BnpC', usage='python3 run_BnpC.py <DATA> [options]',
+                                     description='Dirichlet-process clustering of single-cell mutation calls (B200 build)')
+    parser.add_argument('--version', action='version', version='0.2.1 (bnpc-b200)')
+    groups = {None: parser}
+    for group, flags, kw in OPTIONS:
+        if group not in groups:
+            groups[group] = parser.add_argument_group(group)
+        groups[group].add_argument(*flags, **kw)
+    return parser.parse_args(argv)
 
-    m = p.add_argument_group('model')
-    m.add_argument('-FN', '--falseNegative', type=float, default=-1,
-                   help='Fixed false negative rate; if > 0 (together with -FP) error rates are not learned.')
-    m.add_argument('-FP', '--falsePositive', type=float, default=-1, help='Fixed false positive rate.')
-    m.add_argument('-FN_m', '--falseNegative_mean', type=ratio, default=0.2, help='Prior mean of FN. Default = 0.2.')
-    m.add_argument('-FN_sd', '--falseNegative_std', type=ratio, default=0.1, help='Prior sd of FN. Default = 0.1.')
-    m.add_argument('-FP_m', '--falsePositive_mean', type=ratio, default=0.01, help='Prior mean of FP. Default = 0.01.')
-    m.add_argument('-FP_sd', '--falsePositive_std', type=ratio, default=0.01, help='Prior sd of FP. Default = 0.01.')
-    m.add_argument('-ap', '--DPa_prior', type=float, nargs=2, default=[-1, -1],
-                   help='Gamma(a, b) prior of the concentration parameter; negative = (sqrt(cells), 1).')
-    m.add_argument('-pp', '--param_prior', type=float, nargs=2, default=[.25, .25],
-                   help='Beta(a, b) prior of the cluster parameters. Default = [.25, .25].')
-    m.add_argument('-fa', '--fixed_assignment', type=str, default='',
-                   help='File with a fixed assignment (only parameters are sampled).')
 
-    c = p.add_argument_group('MCMC')
-    c.add_argument('-n', '--chains', type=int, default=1, help='Number of chains. Default = 1.')
-    c.add_argument('-s', '--steps', type=int, default=5000, help='Steps per chain. Default = 5000.')
-    c.add_argument('-r', '--runtime', type=int, default=-1, help='Runtime in minutes (overrides -s).')
-    c.add_argument('-ls', '--lugsail', type=psrf, default=-1,
-                   help='Run until the lugsail PSRF of the chains is below this cutoff (1 <= x <= 1.5).')
-    c.add_argument('-b', '--burn_in', type=percent, default=0.33, help='Burn-in fraction. Default = 0.33.')
-    c.add_argument('-cup', '--conc_update_prob', type=percent, default=0.25,
-                   help='Probability of updating the concentration parameter per step. Default = 0.25.')
-    c.add_argument('-eup', '--error_update_prob', type=percent, default=0.25,
-                   help='Probability of updating the error rates per step. Default = 0.25.')
-    c.add_argument('-smp', '--split_merge_prob', type=percent, default=0.33,
-                   help='Probability of a split/merge move per step. Default = 0.33.')
-    c.add_argument('-sms', '--split_merge_steps', type=int, default=3,
-                   help='Restricted Gibbs scans per split/merge move. Default = 3.')
-    c.add_argument('-smr', '--split_merge_ratios', type=percent, nargs=2, default=[0.75, 0.25],
-                   help='Ratio of splits/merges. Default = 0.75:0.25')
-    c.add_argument('-e', '--estimator', type=str, default='posterior', nargs='+', choices=['posterior', 'ML', 'MAP'],
-                   help='Estimator(s) for the inferred latent variables. Default = posterior.')
-    c.add_argument('-sc', '--single_chains', action='store_true', default=False,
-                   help='Infer the latent variables per chain instead of over all chains.')
-    c.add_argument('--seed', type=int, default=-1, help='Seed of the chain seeds. Default = random.')
-
-    o = p.add_argument_group('output')
-    o.add_argument('-o', '--output', type=str, default='', help='Output directory. Default = next to the input.')
-    o.add_argument('-v', '--verbosity', type=int, default=1, choices=[0, 1, 2], help='Stdout verbosity. Default = 1.')
-    o.add_argument('-np', '--no_plots', action='store_true', default=False, help='Accepted; plots are never drawn.')
-    o.add_argument('-tr', '--tree', type=str, default='', help='Accepted for compatibility (tree plots are not drawn).')
-    o.add_argument('-tc', '--true_clusters', type=str, default='', help='True assignment: ARI and V-measure are written.')
-    o.add_argument('-td', '--true_data', type=str, default='', help='True genotypes: the Hamming distance is written.')
-    return p.parse_args(argv)
+def build_model(args, data):
+    """fixed error rates when both -FN and -FP are given, learned otherwise (run_BnpC.py:251-262)"""
+    common = dict(DP_alpha=args.DPa_prior, param_beta=args.param_prior)
+    if args.falsePositive > 0 and args.falseNegative > 0:
+        args.error_update_prob = 0
+        from libs.CRP import CRP
+        return CRP(data, FN_error=args.falseNegative, FP_error=args.falsePositive, **common)
+    from libs.CRP_learning_errors import CRP_errors_learning
+    return CRP_errors_learning(data, FP_mean=args.falsePositive_mean, FP_sd=args.falsePositive_std,
+                               FN_mean=args.falseNegative_mean, FN_sd=args.falseNegative_std, **common)
 
 
 def generate_output(args, results, data_raw, names):
-    """run_BnpC.py:203-241 without the plots."""
+    """estimators and text outputs (run_BnpC.py:203-241 without the plots)"""
     out_dir = io._get_out_dir(args)
     inferred = io._infer_results(args, results, data_raw)
     if args.verbosity > 0:
@@ -99,33 +114,23 @@ def generate_output(args, results, data_raw, names):
         io.save_ARI(inferred, truth, out_dir)
     if args.true_data:
         io.save_hamming_dist(inferred, io.load_data(args.true_data, transpose=args.transpose), out_dir)
-    if not args.no_plots and args.verbosity > 0:
+    if args.verbosity > 0 and not args.no_plots:
         print('(plots are not part of this build: trace, genotype and similarity plots were skipped)')
     return out_dir
 
 
 def main(args):
-    """run_BnpC.py:244-292."""
     io.process_sim_folder(args, suffix='')
     data, names = io.load_data(args.input, transpose=args.transpose, get_names=True)
     assert data.size > 0, f'Could not read data from file: {args.input}'
-    if args.falsePositive > 0 and args.falseNegative > 0:
-        args.error_update_prob = 0
-        import libs.CRP as CRP
-        model = CRP.CRP(data, DP_alpha=args.DPa_prior, param_beta=args.param_prior,
-                        FN_error=args.falseNegative, FP_error=args.falsePositive)
-    else:
-        import libs.CRP_learning_errors as CRP
-        model = CRP.CRP_errors_learning(data, DP_alpha=args.DPa_prior, param_beta=args.param_prior,
-                                        FP_mean=args.falsePositive_mean, FP_sd=args.falsePositive_std,
-                                        FN_mean=args.falseNegative_mean, FN_sd=args.falseNegative_std)
+    model = build_model(args, data)
     args.time = [datetime.now()]
     run_var, run_str = io._get_mcmc_termination(args)
     mcmc = MCMC(model, sm_prob=args.split_merge_prob, dpa_prob=args.conc_update_prob,
                 error_prob=args.error_update_prob, sm_ratios=args.split_merge_ratios,
                 sm_steps=args.split_merge_steps)
     rank = dist_info()[0]
-    if args.verbosity > 0 and rank == 0:
+    if rank == 0 and args.verbosity > 0:
         print(model)
         print(mcmc)
         print(f'Run MCMC with ({args.chains} chains {run_str}):')
@@ -133,7 +138,7 @@ def main(args):
         args.chains = 1
     mcmc.run(run_var, args.seed, args.chains, args.verbosity, args.fixed_assignment, args.debug)
     if rank != 0:
-        return None                                   # under torchrun rank 0 holds the gathered traces
+        return None                     # under torchrun rank 0 holds the gathered traces
     args.chain_seeds = mcmc.get_seeds()
     results = mcmc.get_results()
     args.time.append(datetime.now())
