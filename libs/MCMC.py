@@ -48,7 +48,9 @@ def chains_of_rank(n_chains, rank, world):
 
 def psrf_lugsail(ml_traces, burn_in):
     """Lugsail batch-means potential scale reduction factor over the ML traces of several
-    chains (Vats & Flegal 2018; stands in for libs/utils.py:427-467)."""
+    chains with cube-root batches (Vats & Flegal 2018).  The lugsail run mode uses the reference's
+    own estimator, libs.utils.get_lugsail_batch_means_est (square-root batches); this variant is
+    kept for callers that want one common burn-in."""
     x = np.stack([np.asarray(t[burn_in:], dtype=np.float64) for t in ml_traces])
     m, n = x.shape
     b = max(1, int(np.floor(n ** (1 / 3))))
@@ -178,7 +180,9 @@ class MCMC:
         while True:
             steps_run = local[0].results['ML'].size
             traces = all_gather_objects([c.results['ML'] for c in local])
-            psrf = psrf_lugsail([t for part in traces for t in part], steps_run // 2)
+            # the reference's estimator (libs/utils.py:427-461), restated in libs/utils.py
+            from libs.utils import get_lugsail_batch_means_est
+            psrf = get_lugsail_batch_means_est([(t, steps_run // 2) for part in traces for t in part])
             if verbosity > 1:
                 print(f'\tPSRF at {steps_run}:\t{psrf:.5f}')
             for c in local:
