@@ -104,3 +104,23 @@ def test_command_line_end_to_end(tmp_path):
     assert by_est['posterior'] > 0.9 and by_est['MAP'] > 0.5, ari
     geno = pd.read_csv(out / 'genotypes_posterior_mean.tsv', sep='\t', index_col=0)
     assert geno.shape == (60, 400) and list(geno.index[:2]) == ['mut0', 'mut1']
+
+
+def test_lugsail_run_mode():
+    """`-ls`: chains are extended by 200 steps until the lugsail PSRF of their ML traces falls
+    below the cutoff (libs/MCMC.py:138-171 of the reference); burn-in = half of the steps run."""
+    import libs.CRP_learning_errors as crple
+    from libs.MCMC import MCMC
+    from oracle.crp_oracle import simulate
+    data, z = simulate(300, 50, k_true=3, miss=0.1, seed=8)
+    model = crple.CRP_errors_learning(data, DP_alpha=[-1, -1], param_beta=[0.25, 0.25], FP_mean=0.01, FP_sd=0.01,
+                                      FN_mean=0.2, FN_sd=0.1)
+    mcmc = MCMC(model, sm_prob=0.33, dpa_prob=0.25, error_prob=0.25, sm_ratios=[0.75, 0.25], sm_steps=3)
+    mcmc.run((1.2, 0), 5, n=2, verbosity=0)
+    results = mcmc.get_results()
+    assert len(results) == 2
+    for r in results:
+        steps = r['ML'].size
+        assert steps >= 10 and r['PSRF'][-1][1] <= 1.2 and r['PSRF_cutoff'] == 1.2
+        assert r['burn_in'] == steps // 2 + 1 or r['burn_in'] == r['PSRF'][-1][0] // 2 + 1
+        assert r['assignments'].shape == (steps, 300)
