@@ -10,32 +10,18 @@
         if (rc__ != 0) return rc__; \
     } while (0)
 
-static int copy_async(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, void* stream) {
-    if (bytes == 0) return 0;
-    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, (cudaStream_t)stream);
-    if (e != cudaSuccess) return fail("cudaMemcpyAsync", e);
-    return 0;
-}
-
-static int record_event(void* ev, void* stream) {
-    if (!ev) return 0;
-    cudaError_t e = cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream);
-    if (e != cudaSuccess) return fail("cudaEventRecord", e);
-    return 0;
-}
-
-__global__ void add_rows_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b,
+__device__ __forceinline__ void add_rows_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b,
                                 int32_t* __restrict__ c, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) c[i] = a[i] + b[i];
 }
-__global__ void copy_rows_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
+__device__ __forceinline__ void copy_rows_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
                                  float* __restrict__ dst, int M) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < M) dst[i] = src0[i];
     else if (i < 2 * M && src1) dst[i] = src1[i - M];
 }
-__global__ void sum_int_kernel(const int32_t* __restrict__ v, int n, int32_t* out) {
+__device__ __forceinline__ void sum_int_kernel(const int32_t* __restrict__ v, int n, int32_t* out) {
     __shared__ int red[32];
     int s = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
@@ -51,7 +37,7 @@ __global__ void sum_int_kernel(const int32_t* __restrict__ v, int n, int32_t* ou
     }
 }
 
-__global__ void gather_rows_kernel(const float* __restrict__ theta, const int32_t* __restrict__ ids, int n, int M,
+__device__ __forceinline__ void gather_rows_kernel(const float* __restrict__ theta, const int32_t* __restrict__ ids, int n, int M,
                                    float* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)n * M) return;
@@ -78,9 +64,7 @@ int bnpc_chain_theta_rows(const bnpc_chain_t* w, int n, float* dst_h, void* stre
     if (!w || n <= 0 || n > w->idcap) return bad_arg("workspace/n");
     TRY(copy_async(w->cursor, w->h_in, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, stream));
     float* stage = reinterpret_cast<float*>(w->rnd);
-    gather_rows_kernel<<<cdiv((long long)n * w->M, 256), 256, 0, (cudaStream_t)stream>>>(w->theta, w->cursor, n,
-                                                                                      w->M, stage);
-    LAUNCH_CHECK("gather_rows");
+    BNPC_LAUNCH(gather_rows_kernel, 0, 0, cdiv((long long)n * w->M, 256), 256, 0, (cudaStream_t)stream, w->theta, w->cursor, n, w->M, stage);
     TRY(copy_async(dst_h, stage, sizeof(float) * (size_t)n * w->M, cudaMemcpyDeviceToHost, stream));
     return 0;
 }
@@ -139,9 +123,7 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
         TRY(record_event(e->ev_ll0, stream));
         TRY(bnpc_ll_matrix(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp, K, w->ll, ldk, stream));
         if (wide) {
-            gibbs_weights_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(w->ll, ldk, K, w->col_of_id,
-                                                                               w->visit + t, rows, e->c_norm);
-            LAUNCH_CHECK("gibbs_weights");
+            BNPC_LAUNCH(gibbs_weights_kernel, 256, 0, cdiv(rows, 8), 256, 0, (cudaStream_t)stream, w->ll, ldk, K, w->col_of_id, w->visit + t, rows, e->c_norm);
         }
         TRY(record_event(e->ev_ll1, stream));
         if (compacted) {
@@ -196,12 +178,10 @@ int bnpc_chain_mh_theta(const bnpc_chain_t* w, int K, int rand_ready, uint64_t s
         TRY(bnpc_fill_uniform(w->rnd, RM, seed, stream_id + 1, 3, stream));
         TRY(bnpc_fill_uniform(w->rnd + RM, 2 * RM, seed, stream_id + 2, 0, stream));
     }
-    cudaError_t ce = cudaMemsetAsync(w->declined, 0, sizeof(int32_t) * ((size_t)K + 1), (cudaStream_t)stream);
-    if (ce != cudaSuccess) return fail("mh_theta memset", ce);
+    TRY(zero_async(w->declined, sizeof(int32_t) * ((size_t)K + 1), stream, "mh_theta memset"));
     TRY(bnpc_mh_theta(w->theta, w->ids, K, w->M, w->S1, w->S0, w->rnd, FN, FP, p, q, 0, nullptr, w->declined,
                       stream));
-    sum_int_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(w->declined, K, w->declined + K);
-    LAUNCH_CHECK("sum_int");
+    BNPC_LAUNCH(sum_int_kernel, 0, 0, 1, 256, 0, (cudaStream_t)stream, w->declined, K, w->declined + K);
     TRY(copy_async(w->h_out, w->declined + K, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     return 0;
 }
@@ -245,8 +225,7 @@ static int rg_mh(const bnpc_chain_t* w, const bnpc_rg_t* g, int row0, int rows, 
 int bnpc_chain_rg_setup(const bnpc_chain_t* w, const bnpc_rg_t* g, void* stream) {
     if (!w || !g || g->n < 2) return bad_arg("workspace/move");
     const int n = g->n, M = w->M;
-    cudaError_t ce = cudaMemsetAsync(w->rg_scal, 0, sizeof(double) * 32, (cudaStream_t)stream);
-    if (ce != cudaSuccess) return fail("rg_setup memset", ce);
+    TRY(zero_async(w->rg_scal, sizeof(double) * 32, stream, "rg_setup memset"));
     TRY(bnpc_gather_members(w->assign, w->N, g->cl_i, g->cl_j, w->cells, w->gblk, stream));
     TRY(bnpc_anchor_swaps(w->cells, n, g->n_a, g->a_i, g->a_j, g->is_merge, stream));
     if (n > 2) TRY(bnpc_rg_launch_halves(w->x1, w->x0, w->W, w->cells, n, g->k6, w->half, stream));
@@ -254,10 +233,8 @@ int bnpc_chain_rg_setup(const bnpc_chain_t* w, const bnpc_rg_t* g, void* stream)
     // theta of the two halves, then of all cells of the move (libs/CRP.py:562-566)
     TRY(bnpc_beta_rows(w->rg_S1, w->rg_S0, 2, M, g->p, g->q, g->rand_ready ? w->rg_beta : nullptr, g->seed,
                        g->stream_id + 1, w->rg_theta, nullptr, stream));
-    add_rows_kernel<<<cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(w->rg_S1, w->rg_S1 + M, w->rg_S1 + 2 * M, M);
-    LAUNCH_CHECK("add_rows");
-    add_rows_kernel<<<cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(w->rg_S0, w->rg_S0 + M, w->rg_S0 + 2 * M, M);
-    LAUNCH_CHECK("add_rows");
+    BNPC_LAUNCH(add_rows_kernel, 0, 0, cdiv(M, 256), 256, 0, (cudaStream_t)stream, w->rg_S1, w->rg_S1 + M, w->rg_S1 + 2 * M, M);
+    BNPC_LAUNCH(add_rows_kernel, 0, 0, cdiv(M, 256), 256, 0, (cudaStream_t)stream, w->rg_S0, w->rg_S0 + M, w->rg_S0 + 2 * M, M);
     TRY(bnpc_beta_rows(w->rg_S1 + 2 * M, w->rg_S0 + 2 * M, 1, M, g->p, g->q,
                        g->rand_ready ? w->rg_beta + 2 * (size_t)M : nullptr, g->seed, g->stream_id + 2,
                        w->rg_theta + 2 * (size_t)M, nullptr, stream));
@@ -323,9 +300,7 @@ int bnpc_chain_rg_decide_split(const bnpc_chain_t* w, const bnpc_rg_t* g, int fl
 int bnpc_chain_rg_decide_merge(const bnpc_chain_t* w, const bnpc_rg_t* g, int flat_prior, void* stream) {
     if (!w || !g) return bad_arg("workspace/move");
     const int M = w->M, n = g->n, nf = n - 2;
-    copy_rows_kernel<<<cdiv(2 * M, 256), 256, 0, (cudaStream_t)stream>>>(
-        w->theta + (size_t)g->cl_i * M, w->theta + (size_t)g->cl_j * M, w->rg_orig, M);
-    LAUNCH_CHECK("copy_rows");
+    BNPC_LAUNCH(copy_rows_kernel, 0, 0, cdiv(2 * M, 256), 256, 0, (cudaStream_t)stream,  w->theta + (size_t)g->cl_i * M, w->theta + (size_t)g->cl_j * M, w->rg_orig, M);
     if (!g->rand_ready) TRY(bnpc_fill_uniform(w->rg_sd, 2 * M, g->seed, g->stream_id + 1, 3, stream));
     // probability of walking from the launch split back to the original split
     TRY(bnpc_theta_log_ratio(w->rg_orig, w->rg_theta, 2, M, w->rg_S1, w->rg_S0, w->rg_sd, 0.0f, 1.0f, g->FN,
@@ -359,17 +334,11 @@ int bnpc_chain_rg_apply(const bnpc_chain_t* w, const bnpc_rg_t* g, int new_id, v
     const int M = w->M;
     if (!g->is_merge) {
         if (new_id < 0 || new_id >= w->idcap) return bad_arg("new_id");
-        copy_rows_kernel<<<cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(w->rg_theta, nullptr,
-                                                                         w->theta + (size_t)g->cl_i * M, M);
-        LAUNCH_CHECK("copy_rows");
-        copy_rows_kernel<<<cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(w->rg_theta + M, nullptr,
-                                                                         w->theta + (size_t)new_id * M, M);
-        LAUNCH_CHECK("copy_rows");
+        BNPC_LAUNCH(copy_rows_kernel, 0, 0, cdiv(M, 256), 256, 0, (cudaStream_t)stream, w->rg_theta, nullptr, w->theta + (size_t)g->cl_i * M, M);
+        BNPC_LAUNCH(copy_rows_kernel, 0, 0, cdiv(M, 256), 256, 0, (cudaStream_t)stream, w->rg_theta + M, nullptr, w->theta + (size_t)new_id * M, M);
         TRY(bnpc_apply_split(w->cells, g->n, w->half, new_id, w->assign, stream));
     } else {
-        copy_rows_kernel<<<cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(w->rg_theta + 2 * (size_t)M, nullptr,
-                                                                         w->theta + (size_t)g->cl_i * M, M);
-        LAUNCH_CHECK("copy_rows");
+        BNPC_LAUNCH(copy_rows_kernel, 0, 0, cdiv(M, 256), 256, 0, (cudaStream_t)stream, w->rg_theta + 2 * (size_t)M, nullptr, w->theta + (size_t)g->cl_i * M, M);
         TRY(bnpc_apply_merge(w->cells, g->n_a, g->n, g->cl_i, w->assign, stream));
     }
     return 0;

@@ -23,8 +23,7 @@ __device__ __forceinline__ long long condensed_index(long long i, long long j, l
     return i * N - i * (i + 1) / 2 + (j - i - 1);
 }
 
-__global__ void __launch_bounds__(256)
-cocluster_counts_kernel(const int32_t* __restrict__ assign, int S, int N, int32_t* __restrict__ counts) {
+__device__ __forceinline__ void cocluster_counts_kernel(const int32_t* __restrict__ assign, int S, int N, int32_t* __restrict__ counts) {
     const int tj = blockIdx.x, ti = blockIdx.y;
     if (tj < ti) return;
     __shared__ int32_t sa[EST_SCHUNK][EST_TILE], sb[EST_SCHUNK][EST_TILE];
@@ -71,8 +70,7 @@ cocluster_counts_kernel(const int32_t* __restrict__ assign, int S, int N, int32_
 }
 
 #define EST_CGROUP 32          /* candidate labellings staged per round */
-__global__ void __launch_bounds__(256)
-mpear_sums_kernel(const int32_t* __restrict__ counts, int N, const int32_t* __restrict__ labels, int n_cand,
+__device__ __forceinline__ void mpear_sums_kernel(const int32_t* __restrict__ counts, int N, const int32_t* __restrict__ labels, int n_cand,
                   unsigned long long* __restrict__ out) {
     const int tj = blockIdx.x, ti = blockIdx.y;
     if (tj < ti) return;

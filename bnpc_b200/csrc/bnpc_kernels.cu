@@ -39,30 +39,133 @@ static int bad_arg(const char* what) {
     snprintf(g_err, sizeof(g_err), "invalid argument: %s", what);
     return 2;
 }
-static std::atomic<long long> g_launches{0};
-
-// cudaFuncSetAttribute is per device: a process that drives several GPUs (chains spread over the
-// visible devices by one process) must opt every device in to the large dynamic shared memory of
-// a kernel.  `done` is the kernel's bit mask of devices already served.
-template <typename F>
-static int ensure_dyn_smem(F func, int bytes, std::atomic<unsigned long long>& done, const char* what) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
-    const unsigned long long bit = 1ull << (dev & 63);
-    if (done.load(std::memory_order_acquire) & bit) return 0;
-    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return fail(what, e);
-    done.fetch_or(bit, std::memory_order_release);
-    return 0;
-}
-#define LAUNCH_CHECK(name)                                        \
-    do {                                                          \
-        cudaError_t e__ = cudaGetLastError();                     \
-        if (e__ != cudaSuccess) return fail(name, e__);           \
-        g_launches.fetch_add(1, std::memory_order_relaxed);       \
-    } while (0)
+#include "bnpc_batch.cuh"
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// =============================================================================
+// recordable stream operations (see bnpc_batch.cuh)
+// =============================================================================
+// zero-fill as a kernel body, so that the many small clears of a step merge across chains like
+// every other launch (cudaMemsetAsync nodes cannot be batched)
+__device__ __forceinline__ void zero_words_kernel(uint32_t* __restrict__ p, long long n_words, int vec) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (!vec) {
+        if (i < n_words) p[i] = 0u;
+        return;
+    }
+    const long long n4 = n_words >> 2;
+    if (i < n4) reinterpret_cast<uint4*>(p)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < (n_words & 3)) p[4 * n4 + i] = 0u;
+}
+static int zero_async(void* ptr, size_t bytes, void* stream, const char* what) {
+    if (bytes == 0) return 0;
+    if ((bytes & 3) || ((uintptr_t)ptr & 3)) {
+        if (bnpc::g_rec.on) return bad_arg("recorded clears must be whole aligned words");
+        cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(what, e);
+        return 0;
+    }
+    const long long words = (long long)(bytes >> 2);
+    const int vec = ((uintptr_t)ptr & 15) ? 0 : 1;
+    BNPC_LAUNCH(zero_words_kernel, 0, 0, cdiv(vec ? (words + 3) / 4 : words, 256), 256, 0, stream,
+                reinterpret_cast<uint32_t*>(ptr), words, vec);
+    return 0;
+}
+
+// small word copies between device memory and PINNED host memory (reachable from the device
+// under unified addressing) as a kernel body: the live list in, the status block out
+__device__ __forceinline__ void copy_words_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src,
+                                                  int n_words) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_words) dst[i] = src[i];
+}
+#define BNPC_SMALL_COPY_BYTES 8192
+static int g_uva_copies = -1;      // small host<->device copies as kernels over mapped pinned memory
+static int copy_async(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, void* stream) {
+    if (bytes == 0) return 0;
+    if (g_uva_copies < 0) {
+        const char* env = getenv("BNPC_UVA_COPIES");
+        g_uva_copies = (env && env[0] == '0') ? 0 : 1;
+    }
+    if (g_uva_copies && bnpc::g_rec.on && bytes <= BNPC_SMALL_COPY_BYTES && !(bytes & 3) &&
+        !(((uintptr_t)dst | (uintptr_t)src) & 3)) {
+        BNPC_LAUNCH(copy_words_kernel, 0, 0, cdiv((long long)(bytes >> 2), 256), 256, 0, stream,
+                    reinterpret_cast<uint32_t*>(dst), reinterpret_cast<const uint32_t*>(src), (int)(bytes >> 2));
+        return 0;
+    }
+    if (bnpc::g_rec.on) {
+        bnpc::g_rec.q[bnpc::g_rec.cur].emplace_back();
+        bnpc::Op& op = bnpc::g_rec.q[bnpc::g_rec.cur].back();
+        op.kind = 1; op.name = "memcpy"; op.merged = nullptr;
+        op.dst = dst; op.src = src; op.bytes = bytes; op.mk = kind;
+        return 0;
+    }
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("cudaMemcpyAsync", e);
+    return 0;
+}
+
+static int record_event(void* ev, void* stream) {
+    if (!ev) return 0;
+    if (bnpc::g_rec.on) {
+        bnpc::g_rec.q[bnpc::g_rec.cur].emplace_back();
+        bnpc::Op& op = bnpc::g_rec.q[bnpc::g_rec.cur].back();
+        op.kind = 2; op.name = "event"; op.merged = nullptr; op.dst = ev;
+        return 0;
+    }
+    cudaError_t e = cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("cudaEventRecord", e);
+    return 0;
+}
+
+// Issue the recorded operations of all chain slots on `s`: per chain in recorded order, across
+// chains merged -- the slot with the most operations left leads (a chain that recorded an extra
+// operation catches up alone), every slot whose next operation is the same kernel with the same
+// block size joins its launch.
+static int recorder_flush(cudaStream_t s) {
+    using namespace bnpc;
+    Recorder& R = g_rec;
+    size_t cur[GROUP_MAX];
+    for (int c = 0; c < GROUP_MAX; ++c) cur[c] = 0;
+    int rc = 0;
+    for (;;) {
+        int lead = -1;
+        size_t most = 0;
+        for (int c = 0; c < GROUP_MAX; ++c) {
+            const size_t left = R.q[c].size() - cur[c];
+            if (left > most) { most = left; lead = c; }
+        }
+        if (lead < 0) break;
+        Op& key = R.q[lead][cur[lead]];
+        if (key.kind == 1) {
+            cudaError_t e = cudaMemcpyAsync(key.dst, key.src, key.bytes, key.mk, s);
+            if (e != cudaSuccess) { rc = fail("cudaMemcpyAsync", e); break; }
+            ++cur[lead];
+            continue;
+        }
+        if (key.kind == 2) {
+            cudaError_t e = cudaEventRecord((cudaEvent_t)key.dst, s);
+            if (e != cudaSuccess) { rc = fail("cudaEventRecord", e); break; }
+            ++cur[lead];
+            continue;
+        }
+        Op* ops[BATCH_MAX];
+        int who[BATCH_MAX];
+        int n = 0;
+        ops[n] = &key; who[n++] = lead;
+        for (int c = 0; c < GROUP_MAX && n < BATCH_MAX; ++c) {
+            if (c == lead || cur[c] >= R.q[c].size()) continue;
+            Op& o = R.q[c][cur[c]];
+            if (o.kind == 0 && o.merged == key.merged && o.block == key.block) { ops[n] = &o; who[n++] = c; }
+        }
+        rc = key.merged(ops, n, s);
+        if (rc) break;
+        for (int i = 0; i < n; ++i) ++cur[who[i]];
+    }
+    for (int c = 0; c < GROUP_MAX; ++c) R.q[c].clear();
+    return rc;
+}
 
 // =============================================================================
 // warp / block helpers
@@ -140,13 +243,13 @@ __device__ __forceinline__ double block_scan_incl(double v, double* red, double*
 // =============================================================================
 // input path: bit-plane packing
 // =============================================================================
-__global__ void pack_planes_kernel(const double* __restrict__ xf, const int8_t* __restrict__ xi,
+__device__ __forceinline__ void pack_planes_kernel(const double* __restrict__ xf, const int8_t* __restrict__ xi,
                                    int N, int M, int W, uint32_t* __restrict__ x1,
                                    uint32_t* __restrict__ x0, int32_t* __restrict__ n1,
-                                   int32_t* __restrict__ n0) {
+                                   int32_t* __restrict__ n0, int n_ctas) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nwarps = ((long long)n_ctas * blockDim.x) >> 5;
     for (long long cell = warp; cell < N; cell += nwarps) {
         int c1 = 0, c0 = 0;
         for (int w = 0; w < W; ++w) {
@@ -173,7 +276,7 @@ __global__ void pack_planes_kernel(const double* __restrict__ xf, const int8_t* 
 // =============================================================================
 // random numbers (production mode)
 // =============================================================================
-__global__ void fill_uniform_kernel(double* __restrict__ out, long long n, uint64_t seed,
+__device__ __forceinline__ void fill_uniform_kernel(double* __restrict__ out, long long n, uint64_t seed,
                                     uint64_t stream_id, int n_levels) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // pair index
     if (2 * i >= n) return;
@@ -190,7 +293,7 @@ __device__ __forceinline__ uint32_t feistel_round(uint32_t r, uint32_t k) {
     h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13; h *= 0xC2B2AE3Du; h ^= h >> 16;
     return h;
 }
-__global__ void fill_permutation_kernel(int32_t* __restrict__ out, int n, uint64_t seed,
+__device__ __forceinline__ void fill_permutation_kernel(int32_t* __restrict__ out, int n, uint64_t seed,
                                         uint64_t stream_id, int half_bits) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -214,7 +317,7 @@ __global__ void fill_permutation_kernel(int32_t* __restrict__ out, int n, uint64
 // =============================================================================
 // likelihood
 // =============================================================================
-__global__ void logprob_tables_kernel(const float* __restrict__ theta, const int32_t* __restrict__ ids,
+__device__ __forceinline__ void logprob_tables_kernel(const float* __restrict__ theta, const int32_t* __restrict__ ids,
                                       int R, int M, double FN, double FP, double2* __restrict__ lp) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)R * M) return;
@@ -233,8 +336,7 @@ __global__ void logprob_tables_kernel(const float* __restrict__ theta, const int
 #define LL_KT 8
 #define LL_MT 128
 #define LL_THREADS 128
-__global__ void __launch_bounds__(LL_THREADS)
-ll_matrix_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
+__device__ __forceinline__ void ll_matrix_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
                  const int32_t* __restrict__ cells, int cell_stride, int C,
                  const double2* __restrict__ lp, int K, double* __restrict__ ll, int ldk) {
     __shared__ double2 tile[LL_MT][LL_KT];
@@ -294,8 +396,7 @@ ll_matrix_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x
 // butterfly.  Lane s walks the bits of a word rotated by 4 s so that the eight lanes of a cell hit
 // different banks.
 #define LLP_CELLS 32
-__global__ void __launch_bounds__(8 * LLP_CELLS)
-ll_few_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
+__device__ __forceinline__ void ll_few_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
               const int32_t* __restrict__ cells, int cell_stride, int C,
               const double2* __restrict__ lp, int K, double* __restrict__ ll, int ldk) {
     extern __shared__ __align__(16) unsigned char llp_smem[];
@@ -364,7 +465,7 @@ __device__ __forceinline__ double cell_row_ll(const uint32_t* __restrict__ r1,
 // =============================================================================
 // Gibbs sweep
 // =============================================================================
-__global__ void gibbs_prepare_kernel(const int32_t* __restrict__ perm, const double* __restrict__ u,
+__device__ __forceinline__ void gibbs_prepare_kernel(const int32_t* __restrict__ perm, const double* __restrict__ u,
                                      const int32_t* __restrict__ assign, const int32_t* __restrict__ n1,
                                      const int32_t* __restrict__ n0, int N, double c1, double c0,
                                      double lnew_prior, bnpc_visit_t* __restrict__ visit) {
@@ -392,8 +493,7 @@ __global__ void gibbs_prepare_kernel(const int32_t* __restrict__ perm, const dou
 // follow the list order at the start of the epoch and deaths preserve relative order, so a walk
 // over the options is a walk in list order.
 #define CAND_THREADS 128
-__global__ void __launch_bounds__(CAND_THREADS)
-gibbs_candidates_kernel(const double* __restrict__ ll, int ldk, int K,
+__device__ __forceinline__ void gibbs_candidates_kernel(const double* __restrict__ ll, int ldk, int K,
                         const int32_t* __restrict__ col_of_id,
                         bnpc_visit_t* __restrict__ visit, bnpc_cand_t* __restrict__ cand,
                         int C, double slack, double c_norm, int32_t* __restrict__ blk) {
@@ -453,7 +553,7 @@ gibbs_candidates_kernel(const double* __restrict__ ll, int ldk, int K,
 }
 
 // exclusive scan of the per-block counts (one CTA); blk[nb] and st[BNPC_ST_NUNC] = total
-__global__ void __launch_bounds__(1024) compact_scan_kernel(int32_t* blk, int nb, int32_t* st) {
+__device__ __forceinline__ void compact_scan_kernel(int32_t* blk, int nb, int32_t* st) {
     __shared__ int wsum[33];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int per = (nb + 1023) / 1024;
@@ -485,8 +585,7 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(int32_t* blk, int nb
     if (tid == 0) { blk[nb] = wsum[32]; st[BNPC_ST_NUNC] = wsum[32]; }
 }
 
-__global__ void __launch_bounds__(CAND_THREADS)
-compact_scatter_kernel(const bnpc_visit_t* __restrict__ visit, const bnpc_cand_t* __restrict__ cand,
+__device__ __forceinline__ void compact_scatter_kernel(const bnpc_visit_t* __restrict__ visit, const bnpc_cand_t* __restrict__ cand,
                        int C, const int32_t* __restrict__ blk, bnpc_visit_t* __restrict__ visit_c,
                        bnpc_cand_t* __restrict__ cand_c) {
     __shared__ int wcnt[CAND_THREADS / 32];
@@ -509,7 +608,7 @@ compact_scatter_kernel(const bnpc_visit_t* __restrict__ visit, const bnpc_cand_t
     for (int i = 0; i < (int)(sizeof(bnpc_cand_t) / 16); ++i) dc[i] = sc[i];
 }
 
-__global__ void gibbs_epoch_begin_kernel(const int32_t* __restrict__ live, int K, int32_t* lst,
+__device__ __forceinline__ void gibbs_epoch_begin_kernel(const int32_t* __restrict__ live, int K, int32_t* lst,
                                          int32_t* cnt, int32_t* col_of_id, int idcap, int32_t* st,
                                          int first) {
     for (int i = threadIdx.x; i < idcap; i += blockDim.x) cnt[i] = 0;
@@ -1583,8 +1682,7 @@ __device__ void sweep_birth(const bnpc_sweep_args_t& a, SweepShared& sh) {
 }
 
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 1)
-gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
+__device__ __forceinline__ void gibbs_sweep_kernel(const bnpc_sweep_args_t& a) {
     extern __shared__ __align__(128) unsigned char sweep_smem[];
     SweepShared& sh = *reinterpret_cast<SweepShared*>(sweep_smem);
     const int tid = threadIdx.x;
@@ -1707,12 +1805,12 @@ gibbs_sweep_kernel(const __grid_constant__ bnpc_sweep_args_t a) {
 // =============================================================================
 // sufficient statistics
 // =============================================================================
-__global__ void set_ranks_kernel(const int32_t* __restrict__ ids, int K, int32_t* rank_of_id) {
+__device__ __forceinline__ void set_ranks_kernel(const int32_t* __restrict__ ids, int K, int32_t* rank_of_id) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < K) rank_of_id[ids[j]] = j;
 }
 
-__global__ void group_members_kernel(const int32_t* __restrict__ assign, int N,
+__device__ __forceinline__ void group_members_kernel(const int32_t* __restrict__ assign, int N,
                                      const int32_t* __restrict__ rank_of_id,
                                      const int32_t* __restrict__ seg_off, int32_t* cursor,
                                      int32_t* __restrict__ members) {
@@ -1738,18 +1836,18 @@ __global__ void group_members_kernel(const int32_t* __restrict__ assign, int N,
 // over the rows, so that a warp reads whole 128-byte row pieces (coalesced); the 32 per-bit
 // counters of a word are kept as 8 registers of four byte-wide counters each
 // (acc[j] += (x >> j) & 0x01010101 counts bits j, j+8, j+16, j+24), at most 255 rows per thread.
-__global__ void __launch_bounds__(SS_THREADS)
-suffstat_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
+__device__ __forceinline__ void suffstat_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
                 const int32_t* __restrict__ members, const int32_t* __restrict__ seg_off,
-                int32_t* __restrict__ S1, int32_t* __restrict__ S0, int wc_log2) {
+                int32_t* __restrict__ S1, int32_t* __restrict__ S0, int wc_log2, int n_wblk) {
     __shared__ int cnt[2][32][32];
-    const int r = blockIdx.y;
+    // blockIdx.y = segment * n_wblk + word block (blockIdx.z is the chain of a batched launch)
+    const int r = blockIdx.y / n_wblk, wblk = blockIdx.y % n_wblk;
     const int beg = seg_off[r] + blockIdx.x * SS_CHUNK;
     const int end = min(seg_off[r + 1], beg + SS_CHUNK);
     if (beg >= end) return;
     const int wc = 1 << wc_log2;
     const int col = threadIdx.x & (wc - 1), rsub = threadIdx.x >> wc_log2, rstep = SS_THREADS >> wc_log2;
-    const int w = blockIdx.z * 32 + col;
+    const int w = wblk * 32 + col;
     for (int i = threadIdx.x; i < 2 * 32 * 32; i += SS_THREADS) (&cnt[0][0][0])[i] = 0;
     __syncthreads();
     if (w < W) {
@@ -1797,7 +1895,7 @@ suffstat_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0
     __syncthreads();
     for (int i = threadIdx.x; i < 32 * 32; i += SS_THREADS) {
         const int c = i >> 5, bit = i & 31;
-        const int m = (blockIdx.z * 32 + c) * 32 + bit;
+        const int m = (wblk * 32 + c) * 32 + bit;
         if (c < wc && m < M) {
             const int v1 = cnt[0][c][bit], v0 = cnt[1][c][bit];
             if (v1) atomicAdd(&S1[(long long)r * M + m], v1);
@@ -1809,7 +1907,7 @@ suffstat_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0
 // =============================================================================
 // theta draws and Metropolis-Hastings
 // =============================================================================
-__global__ void beta_rows_kernel(const int32_t* __restrict__ S1, const int32_t* __restrict__ S0, int R,
+__device__ __forceinline__ void beta_rows_kernel(const int32_t* __restrict__ S1, const int32_t* __restrict__ S0, int R,
                                  int M, double p, double q, const double* __restrict__ tape,
                                  uint64_t seed, uint64_t stream_id, float* __restrict__ theta_out,
                                  const int32_t* __restrict__ out_ids) {
@@ -1827,7 +1925,7 @@ __global__ void beta_rows_kernel(const int32_t* __restrict__ S1, const int32_t* 
     theta_out[row * M + m] = clip_theta(val);
 }
 
-__global__ void theta_from_uniform_kernel(const double* __restrict__ u, int R, int M,
+__device__ __forceinline__ void theta_from_uniform_kernel(const double* __restrict__ u, int R, int M,
                                           float* __restrict__ theta_out,
                                           const int32_t* __restrict__ out_ids) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1869,7 +1967,7 @@ __device__ __forceinline__ double theta_log_A(float th_new, float th_old, int s1
 
 __device__ __constant__ const double kStepSd[3] = {0.1, 0.25, 0.5};   // libs/CRP.py:65
 
-__global__ void mh_theta_kernel(float* theta, const int32_t* __restrict__ ids, int R, int M,
+__device__ __forceinline__ void mh_theta_kernel(float* theta, const int32_t* __restrict__ ids, int R, int M,
                                 const int32_t* __restrict__ S1, const int32_t* __restrict__ S0,
                                 const double* __restrict__ rnd, MhConst c, int flags,
                                 double* __restrict__ logq, int32_t* declined) {
@@ -1893,7 +1991,7 @@ __global__ void mh_theta_kernel(float* theta, const int32_t* __restrict__ ids, i
     if (want_logq) logq[i] = rej ? log(-1.0 * expm1(A)) : A;
 }
 
-__global__ void theta_log_ratio_kernel(const float* __restrict__ th_new, const float* __restrict__ th_old,
+__device__ __forceinline__ void theta_log_ratio_kernel(const float* __restrict__ th_new, const float* __restrict__ th_old,
                                        int R, int M, const int32_t* __restrict__ S1,
                                        const int32_t* __restrict__ S0, const double* __restrict__ sd_idx,
                                        float blo, float bhi, MhConst c, double* __restrict__ A) {
@@ -1914,8 +2012,7 @@ struct RlArgs {
     int E;
     double p, q, betaln;
 };
-__global__ void __launch_bounds__(256)
-row_loglik_kernel(const float* __restrict__ theta, const int32_t* __restrict__ ids, int R, int M,
+__device__ __forceinline__ void row_loglik_kernel(const float* __restrict__ theta, const int32_t* __restrict__ ids, int R, int M,
                   const int32_t* __restrict__ S1, const int32_t* __restrict__ S0, RlArgs g,
                   double* __restrict__ out, double* __restrict__ prior_out) {
     __shared__ double red[40];
@@ -1946,8 +2043,7 @@ row_loglik_kernel(const float* __restrict__ theta, const int32_t* __restrict__ i
     }
 }
 
-__global__ void __launch_bounds__(256)
-row_sum_kernel(const double* __restrict__ v, int R, int M, double* __restrict__ out) {
+__device__ __forceinline__ void row_sum_kernel(const double* __restrict__ v, int R, int M, double* __restrict__ out) {
     __shared__ double red[40];
     const int r = blockIdx.x;
     double acc = 0.0;
@@ -1959,8 +2055,7 @@ row_sum_kernel(const double* __restrict__ v, int R, int M, double* __restrict__ 
 // =============================================================================
 // split-merge support
 // =============================================================================
-__global__ void __launch_bounds__(1024)
-gather_count_kernel(const int32_t* __restrict__ assign, int N, int id_a, int id_b, int32_t* blk) {
+__device__ __forceinline__ void gather_count_kernel(const int32_t* __restrict__ assign, int N, int id_a, int id_b, int32_t* blk) {
     __shared__ int ca, cb;
     if (threadIdx.x == 0) { ca = 0; cb = 0; }
     __syncthreads();
@@ -1975,7 +2070,7 @@ gather_count_kernel(const int32_t* __restrict__ assign, int N, int id_a, int id_
     __syncthreads();
     if (threadIdx.x == 0) { blk[2 * blockIdx.x] = ca; blk[2 * blockIdx.x + 1] = cb; }
 }
-__global__ void gather_scan_kernel(int32_t* blk, int nb) {
+__device__ __forceinline__ void gather_scan_kernel(int32_t* blk, int nb) {
     // single thread: exclusive scans; the id_b region starts after all of id_a
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int ta = 0;
@@ -1985,8 +2080,7 @@ __global__ void gather_scan_kernel(int32_t* blk, int nb) {
     blk[2 * nb] = ta;
     blk[2 * nb + 1] = tb;
 }
-__global__ void __launch_bounds__(1024)
-gather_scatter_kernel(const int32_t* __restrict__ assign, int N, int id_a, int id_b,
+__device__ __forceinline__ void gather_scatter_kernel(const int32_t* __restrict__ assign, int N, int id_a, int id_b,
                       const int32_t* __restrict__ blk, int32_t* __restrict__ cells_out) {
     __shared__ int wa[32], wb[32];
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2012,7 +2106,7 @@ gather_scatter_kernel(const int32_t* __restrict__ assign, int N, int id_a, int i
     if (ib) cells_out[blk[2 * blockIdx.x + 1] + wb[w] + __popc(mb & lt)] = n;
 }
 
-__global__ void anchor_swaps_kernel(int32_t* cells, int n, int n_a, int idx_i, int idx_j, int is_merge) {
+__device__ __forceinline__ void anchor_swaps_kernel(int32_t* cells, int n, int n_a, int idx_i, int idx_j, int is_merge) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (!is_merge) {                       // libs/CRP.py:449-450
         int t = cells[0]; cells[0] = cells[idx_i]; cells[idx_i] = t;
@@ -2024,7 +2118,7 @@ __global__ void anchor_swaps_kernel(int32_t* cells, int n, int n_a, int idx_i, i
 }
 
 struct K6 { double k[6]; };
-__global__ void rg_launch_halves_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0,
+__device__ __forceinline__ void rg_launch_halves_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0,
                                         int W, const int32_t* __restrict__ cells, int n, K6 k6,
                                         int32_t* __restrict__ half) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2048,14 +2142,14 @@ __global__ void rg_launch_halves_kernel(const uint32_t* __restrict__ x1, const u
     half[s] = (lj > li) ? 1 : 0;
 }
 
-__global__ void rg_count_kernel(const int32_t* __restrict__ half, int nfree, int32_t* seg_off) {
+__device__ __forceinline__ void rg_count_kernel(const int32_t* __restrict__ half, int nfree, int32_t* seg_off) {
     // seg_off[3] accumulates the number of side-1 free cells; seg_off[4..5] are cursors
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = (s < nfree) ? half[s] : 0;
     const unsigned m = __ballot_sync(FULL, v == 1);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&seg_off[3], __popc(m));
 }
-__global__ void rg_sides_kernel(const int32_t* __restrict__ cells, int n, const int32_t* __restrict__ half,
+__device__ __forceinline__ void rg_sides_kernel(const int32_t* __restrict__ cells, int n, const int32_t* __restrict__ half,
                                 int32_t* __restrict__ members, int32_t* seg_off) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -2096,7 +2190,7 @@ __device__ __forceinline__ int rg_side(double a0, double a1, int ex, int n, doub
 #define RG_FORCE_1 0
 #define RG_FORCE_0 (1 << 29)
 
-__global__ void rg_prepare_kernel(const double* __restrict__ ll2, int ldk, int n,
+__device__ __forceinline__ void rg_prepare_kernel(const double* __restrict__ ll2, int ldk, int n,
                                   const int32_t* __restrict__ perm, const double* __restrict__ u,
                                   const int32_t* __restrict__ half, double alpha, int mode,
                                   const int32_t* __restrict__ cells, const int32_t* __restrict__ assign,
@@ -2134,8 +2228,7 @@ __global__ void rg_prepare_kernel(const double* __restrict__ ll2, int ldk, int n
 // long as all lanes before it were inside their intervals; the lanes up to the first one that
 // was not are final, the others walk again from the corrected starts.  Every round finalises at
 // least one lane (the first open lane starts from an exact value), typically all 32.
-__global__ void __launch_bounds__(32)
-rg_serial_kernel(const int32_t* __restrict__ half, int nf, int32_t* __restrict__ work, int out_off) {
+__device__ __forceinline__ void rg_serial_kernel(const int32_t* __restrict__ half, int nf, int32_t* __restrict__ work, int out_off) {
     __shared__ int32_t pin[32 * 33], pout[32 * 33];
     const int lane = threadIdx.x;
     int ones = 0;
@@ -2205,7 +2298,7 @@ rg_serial_kernel(const int32_t* __restrict__ half, int nf, int32_t* __restrict__
     }
 }
 
-__global__ void rg_finish_kernel(const double* __restrict__ ll2, int ldk, int n,
+__device__ __forceinline__ void rg_finish_kernel(const double* __restrict__ ll2, int ldk, int n,
                                  const int32_t* __restrict__ perm, int32_t* __restrict__ half,
                                  double alpha, int mode, const int32_t* __restrict__ work, int out_off,
                                  double* __restrict__ lq) {
@@ -2225,14 +2318,14 @@ __global__ void rg_finish_kernel(const double* __restrict__ ll2, int ldk, int n,
     }
 }
 
-__global__ void apply_split_kernel(const int32_t* __restrict__ cells, int n, const int32_t* __restrict__ half,
+__device__ __forceinline__ void apply_split_kernel(const int32_t* __restrict__ cells, int n, const int32_t* __restrict__ half,
                                    int new_id, int32_t* assign) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const bool mv = (s == n - 1) || (s > 0 && half[s - 1] == 1);
     if (mv) assign[cells[s]] = new_id;
 }
-__global__ void apply_merge_kernel(const int32_t* __restrict__ cells, int n_a, int n, int id, int32_t* assign) {
+__device__ __forceinline__ void apply_merge_kernel(const int32_t* __restrict__ cells, int n_a, int n, int id, int32_t* assign) {
     const int s = n_a + blockIdx.x * blockDim.x + threadIdx.x;
     if (s < n) assign[cells[s]] = id;
 }
@@ -2252,8 +2345,7 @@ int bnpc_pack_planes(const double* x_f64, const int8_t* x_i8, int N, int M, int 
     if (W % 4 != 0 || W * 32 < M) return bad_arg("W must be a multiple of 4 with 32*W >= M");
     if (N <= 0) return 0;
     const int blocks = (int)min((long long)cdiv((long long)N * 32, 256), 148ll * 64);
-    pack_planes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x_f64, x_i8, N, M, W, x1, x0, n1, n0);
-    LAUNCH_CHECK("pack_planes");
+    BNPC_LAUNCH(pack_planes_kernel, 0, 0, blocks, 256, 0, (cudaStream_t)stream, x_f64, x_i8, N, M, W, x1, x0, n1, n0, blocks);
     return 0;
 }
 
@@ -2261,8 +2353,7 @@ int bnpc_fill_uniform(double* out, int64_t n, uint64_t seed, uint64_t stream_id,
                       void* stream) {
     if (n <= 0) return 0;
     const long long pairs = (n + 1) / 2;
-    fill_uniform_kernel<<<cdiv(pairs, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, stream_id, n_levels);
-    LAUNCH_CHECK("fill_uniform");
+    BNPC_LAUNCH(fill_uniform_kernel, 0, 0, cdiv(pairs, 256), 256, 0, (cudaStream_t)stream, out, n, seed, stream_id, n_levels);
     return 0;
 }
 
@@ -2271,17 +2362,14 @@ int bnpc_fill_permutation(int32_t* out, int n, uint64_t seed, uint64_t stream_id
     int bits = 2;
     while ((1ll << bits) < n) ++bits;
     if (bits & 1) ++bits;
-    fill_permutation_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, stream_id, bits / 2);
-    LAUNCH_CHECK("fill_permutation");
+    BNPC_LAUNCH(fill_permutation_kernel, 0, 0, cdiv(n, 256), 256, 0, (cudaStream_t)stream, out, n, seed, stream_id, bits / 2);
     return 0;
 }
 
 int bnpc_logprob_tables(const float* theta, const int32_t* ids, int R, int M, double FN, double FP,
                         double* lp, void* stream) {
     if (R <= 0) return 0;
-    logprob_tables_kernel<<<cdiv((long long)R * M, 256), 256, 0, (cudaStream_t)stream>>>(
-        theta, ids, R, M, FN, FP, reinterpret_cast<double2*>(lp));
-    LAUNCH_CHECK("logprob_tables");
+    BNPC_LAUNCH(logprob_tables_kernel, 0, 0, cdiv((long long)R * M, 256), 256, 0, (cudaStream_t)stream,  theta, ids, R, M, FN, FP, reinterpret_cast<double2*>(lp));
     return 0;
 }
 
@@ -2292,18 +2380,12 @@ int bnpc_ll_matrix(const uint32_t* x1, const uint32_t* x0, int W, int M, const i
     if (W % 4 != 0) return bad_arg("W must be a multiple of 4");
     if (K <= 2 && sizeof(double2) * (size_t)K * W * 32 <= 200 * 1024) {
         const size_t smem = sizeof(double2) * (size_t)K * W * 32;
-        static std::atomic<unsigned long long> attr_done{0};
-        if (int rc = ensure_dyn_smem(ll_few_kernel, 200 * 1024, attr_done, "ll_few smem attribute")) return rc;
-        ll_few_kernel<<<cdiv(C, LLP_CELLS), 8 * LLP_CELLS, smem, (cudaStream_t)stream>>>(
-            x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const double2*>(lp), K, ll, ldk);
-        LAUNCH_CHECK("ll_few");
+        BNPC_LAUNCH(ll_few_kernel, 8 * LLP_CELLS, 0, cdiv(C, LLP_CELLS), 8 * LLP_CELLS, smem, (cudaStream_t)stream,  x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const double2*>(lp), K, ll, ldk);
         return 0;
     }
     dim3 grid(cdiv(C, LL_THREADS), cdiv(K, LL_KT));
     if (grid.y > 65535) return bad_arg("too many clusters for one ll_matrix launch");
-    ll_matrix_kernel<<<grid, LL_THREADS, 0, (cudaStream_t)stream>>>(
-        x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const double2*>(lp), K, ll, ldk);
-    LAUNCH_CHECK("ll_matrix");
+    BNPC_LAUNCH(ll_matrix_kernel, LL_THREADS, 0, grid, LL_THREADS, 0, (cudaStream_t)stream,  x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const double2*>(lp), K, ll, ldk);
     return 0;
 }
 
@@ -2311,9 +2393,7 @@ int bnpc_gibbs_prepare(const int32_t* perm, const double* u, const int32_t* assi
                        const int32_t* n0, int N, double c1, double c0, double lnew_prior,
                        bnpc_visit_t* visit, void* stream) {
     if (N <= 0) return 0;
-    gibbs_prepare_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(perm, u, assign, n1, n0, N, c1, c0,
-                                                                        lnew_prior, visit);
-    LAUNCH_CHECK("gibbs_prepare");
+    BNPC_LAUNCH(gibbs_prepare_kernel, 0, 0, cdiv(N, 256), 256, 0, (cudaStream_t)stream, perm, u, assign, n1, n0, N, c1, c0, lnew_prior, visit);
     return 0;
 }
 
@@ -2323,9 +2403,7 @@ int bnpc_gibbs_candidates(const double* ll, int ldk, int K, const int32_t* col_o
     if (C <= 0) return 0;
     if (K > SW_MAXL) return bad_arg("candidates need K <= 1024");
     if (!blk) return bad_arg("blk");
-    gibbs_candidates_kernel<<<cdiv(C, CAND_THREADS), CAND_THREADS, 0, (cudaStream_t)stream>>>(
-        ll, ldk, K, col_of_id, visit_t0, cand_t0, C, slack, c_norm, blk);
-    LAUNCH_CHECK("gibbs_candidates");
+    BNPC_LAUNCH(gibbs_candidates_kernel, CAND_THREADS, 0, cdiv(C, CAND_THREADS), CAND_THREADS, 0, (cudaStream_t)stream,  ll, ldk, K, col_of_id, visit_t0, cand_t0, C, slack, c_norm, blk);
     return 0;
 }
 
@@ -2334,11 +2412,8 @@ int bnpc_gibbs_compact(const bnpc_visit_t* visit_t0, const bnpc_cand_t* cand_t0,
     if (C <= 0) return 0;
     if (!blk || !visit_c || !cand_c || !st) return bad_arg("compact buffers");
     const int nb = cdiv(C, CAND_THREADS);
-    compact_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(blk, nb, st);
-    LAUNCH_CHECK("compact_scan");
-    compact_scatter_kernel<<<nb, CAND_THREADS, 0, (cudaStream_t)stream>>>(visit_t0, cand_t0, C, blk, visit_c,
-                                                                         cand_c);
-    LAUNCH_CHECK("compact_scatter");
+    BNPC_LAUNCH(compact_scan_kernel, 1024, 0, 1, 1024, 0, (cudaStream_t)stream, blk, nb, st);
+    BNPC_LAUNCH(compact_scatter_kernel, CAND_THREADS, 0, nb, CAND_THREADS, 0, (cudaStream_t)stream, visit_t0, cand_t0, C, blk, visit_c, cand_c);
     return 0;
 }
 
@@ -2349,13 +2424,9 @@ int bnpc_ll_matrix_f32(const uint32_t* x1, const uint32_t* x0, int W, int M, con
     if (ldf < K) return bad_arg("ldf < K");
     if (W % 4 != 0) return bad_arg("W must be a multiple of 4");
     const long long n = (long long)K * M;
-    lp_to_f32_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double2*>(lp), n,
-                                                                     reinterpret_cast<float2*>(lpf));
-    LAUNCH_CHECK("lp_to_f32");
+    BNPC_LAUNCH(lp_to_f32_kernel, 0, 0, cdiv(n, 256), 256, 0, (cudaStream_t)stream, reinterpret_cast<const double2*>(lp), n, reinterpret_cast<float2*>(lpf));
     dim3 grid(cdiv(C, LL_THREADS), cdiv(K, LLF_KT));
-    ll_matrix_f32_kernel<<<grid, LL_THREADS, 0, (cudaStream_t)stream>>>(
-        x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const float2*>(lpf), K, llf, ldf);
-    LAUNCH_CHECK("ll_matrix_f32");
+    BNPC_LAUNCH(ll_matrix_f32_kernel, LL_THREADS, 0, grid, LL_THREADS, 0, (cudaStream_t)stream,  x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const float2*>(lpf), K, llf, ldf);
     return 0;
 }
 
@@ -2369,8 +2440,7 @@ int bnpc_ll_matrix_tc(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
     if (ldf < kpad || ldf % 4 != 0) return bad_arg("ldf must be a multiple of 4, >= K rounded up to 8");
     cudaStream_t s = (cudaStream_t)stream;
     const long long total = (long long)W * 2 * kpad * 64;
-    lp_split_bf16_kernel<<<cdiv(total, 256), 256, 0, s>>>(reinterpret_cast<const double2*>(lp), K, M, W, kpad, bsplit);
-    LAUNCH_CHECK("lp_split_bf16");
+    BNPC_LAUNCH(lp_split_bf16_kernel, 0, 0, cdiv(total, 256), 256, 0, s, reinterpret_cast<const double2*>(lp), K, M, W, kpad, bsplit);
     switch (kpad) {
         case 8: return launch_ll_tc<8>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
         case 16: return launch_ll_tc<16>(x1, x0, W, cells, cell_stride, C, bsplit, llf, ldf, s);
@@ -2388,8 +2458,7 @@ int bnpc_cocluster_counts(const int32_t* assign, int S, int N, int32_t* counts, 
     const int T = cdiv(N, EST_TILE);
     if (T > 65535) return bad_arg("too many cells for one launch");
     dim3 grid(T, T);
-    cocluster_counts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(assign, S, N, counts);
-    LAUNCH_CHECK("cocluster_counts");
+    BNPC_LAUNCH(cocluster_counts_kernel, 256, 0, grid, 256, 0, (cudaStream_t)stream, assign, S, N, counts);
     return 0;
 }
 
@@ -2402,8 +2471,7 @@ int bnpc_mpear_sums(const int32_t* counts, int N, const int32_t* labels, int n_c
                                      (cudaStream_t)stream);
     if (ce != cudaSuccess) return fail("mpear_sums memset", ce);
     dim3 grid(T, T);
-    mpear_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(counts, N, labels, n_cand, out);
-    LAUNCH_CHECK("mpear_sums");
+    BNPC_LAUNCH(mpear_sums_kernel, 256, 0, grid, 256, 0, (cudaStream_t)stream, counts, N, labels, n_cand, out);
     return 0;
 }
 
@@ -2425,9 +2493,7 @@ int bnpc_ll_matrix_i8(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
     cudaStream_t s = (cudaStream_t)stream;
     const double q = vmax / 65535.0;
     const long long total = (long long)(W / 2) * 2 * kpad * 128;
-    lp_split_u8_kernel<<<cdiv(total, 256), 256, 0, s>>>(reinterpret_cast<const double2*>(lp), K, M, W, kpad, 1.0 / q,
-                                                       bdigits);
-    LAUNCH_CHECK("lp_split_u8");
+    BNPC_LAUNCH(lp_split_u8_kernel, 0, 0, cdiv(total, 256), 256, 0, s, reinterpret_cast<const double2*>(lp), K, M, W, kpad, 1.0 / q, bdigits);
     const float nq = -(float)q;
     switch (kpad) {
         case 8: return launch_ll_i8<8>(x1, x0, W, cells, cell_stride, C, bdigits, nq, llf, ldf, s);
@@ -2446,13 +2512,9 @@ int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_i
                        double log_n, double c_norm, int terms, double err_abs, void* stream) {
     if (C <= 0) return 0;
     if (K <= 0 || K > BNPC_LEAN_MAXK) return bad_arg("lean epochs need K <= BNPC_LEAN_MAXK");
-    cudaError_t ce = cudaMemsetAsync(n_cert, 0, sizeof(int32_t) * BNPC_LEAN_MAXK, (cudaStream_t)stream);
-    if (ce != cudaSuccess) return fail("gibbs_options memset", ce);
+    if (int rc = zero_async(n_cert, sizeof(int32_t) * BNPC_LEAN_MAXK, stream, "gibbs_options memset")) return rc;
     const float err_rel = (float)terms * 2.384185791015625e-07f;      // terms * 2^-22
-    gibbs_options_kernel<<<cdiv(C, CAND_THREADS), CAND_THREADS, 0, (cudaStream_t)stream>>>(
-        llf, ldf, K, col_of_id, visit_t0, opt_t0, n_cert, C, (float)log_n, c_norm, err_rel,
-        0.05f + (float)(err_abs > 0.0 ? err_abs : 0.0));
-    LAUNCH_CHECK("gibbs_options");
+    BNPC_LAUNCH(gibbs_options_kernel, CAND_THREADS, 0, cdiv(C, CAND_THREADS), CAND_THREADS, 0, (cudaStream_t)stream,  llf, ldf, K, col_of_id, visit_t0, opt_t0, n_cert, C, (float)log_n, c_norm, err_rel, 0.05f + (float)(err_abs > 0.0 ? err_abs : 0.0));
     return 0;
 }
 
@@ -2466,14 +2528,10 @@ int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const
     if (!comp || !order) return bad_arg("comp/order");
     const int nb = cdiv(C, CAND_THREADS);
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t ce = cudaMemsetAsync(comp, 0, sizeof(int32_t) * 512, s);
-    if (ce != cudaSuccess) return fail("gibbs_exact memset", ce);
-    gibbs_finalize_kernel<<<nb, CAND_THREADS, 0, s>>>(opt_t0, n_cert, C, blk);
-    LAUNCH_CHECK("gibbs_finalize");
-    compact_scan_kernel<<<1, 1024, 0, s>>>(blk, nb, st);
-    LAUNCH_CHECK("compact_scan");
-    compact_index_kernel<<<nb, CAND_THREADS, 0, s>>>(opt_t0, C, blk, idx_c);
-    LAUNCH_CHECK("compact_index");
+    if (int rc = zero_async(comp, sizeof(int32_t) * 512, stream, "gibbs_exact memset")) return rc;
+    BNPC_LAUNCH(gibbs_finalize_kernel, CAND_THREADS, 0, nb, CAND_THREADS, 0, s, opt_t0, n_cert, C, blk);
+    BNPC_LAUNCH(compact_scan_kernel, 1024, 0, 1, 1024, 0, s, blk, nb, st);
+    BNPC_LAUNCH(compact_index_kernel, CAND_THREADS, 0, nb, CAND_THREADS, 0, s, opt_t0, C, blk, idx_c);
     // default: stage only the columns a CTA's visits use (32 KB of shared memory whatever K is;
     // Gibbs step 2.50 -> 2.09 ms at K = 59 with every visit uncertain); BNPC_EXACT_STAGING=all
     // selects the kernel that stages all K columns per round
@@ -2482,43 +2540,26 @@ int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const
         const char* env = getenv("BNPC_EXACT_STAGING");
         all_cols = (env && env[0] == 'a') ? 1 : 0;
     }
-    if (all_cols) {
-        static std::atomic<unsigned long long> attr_done{0};
-        if (int rc = ensure_dyn_smem(gibbs_exact_allcols_kernel, (int)(sizeof(double2) * 32 * EX_WORDS * BNPC_LEAN_MAXK),
-                                     attr_done, "gibbs_exact smem attribute")) return rc;
-    }
     const size_t smem = all_cols ? sizeof(double2) * 32 * EX_WORDS * (size_t)K : sizeof(double2) * 32 * EX_WORDS * EX_COLS;
     // processing order: uncertain visits grouped by their own cluster (see exact_hist_kernel)
-    exact_hist_kernel<<<cdiv(C, 256), 256, 0, s>>>(opt_t0, idx_c, st, comp);
-    LAUNCH_CHECK("exact_hist");
-    exact_scan_kernel<<<1, BNPC_LEAN_MAXK, 0, s>>>(comp);
-    LAUNCH_CHECK("exact_scan");
-    exact_scatter_kernel<<<cdiv(C, 256), 256, 0, s>>>(opt_t0, idx_c, st, comp, order);
-    LAUNCH_CHECK("exact_scatter");
+    BNPC_LAUNCH(exact_hist_kernel, 256, 0, cdiv(C, 256), 256, 0, s, opt_t0, idx_c, st, comp);
+    BNPC_LAUNCH(exact_scan_kernel, BNPC_LEAN_MAXK, 0, 1, BNPC_LEAN_MAXK, 0, s, comp);
+    BNPC_LAUNCH(exact_scatter_kernel, 256, 0, cdiv(C, 256), 256, 0, s, opt_t0, idx_c, st, comp, order);
     // the number of uncertain visits lives on the device: blocks beyond it exit at once
     if (all_cols)
-        gibbs_exact_allcols_kernel<<<cdiv(C, EX_THREADS), EX_THREADS, smem, s>>>(
-            x1, x0, W, M, reinterpret_cast<const double2*>(lp), K, visit_t0, opt_t0, idx_c, st, visit_c, cand_c,
-            log_n, c_norm, comp, order);
+        BNPC_LAUNCH(gibbs_exact_allcols_kernel, EX_THREADS, 0, cdiv(C, EX_THREADS), EX_THREADS, smem, s,  x1, x0, W, M, reinterpret_cast<const double2*>(lp), K, visit_t0, opt_t0, idx_c, st, visit_c, cand_c, log_n, c_norm, comp, order);
     else
-        gibbs_exact_kernel<<<cdiv(C, EX_THREADS), EX_THREADS, smem, s>>>(
-            x1, x0, W, M, reinterpret_cast<const double2*>(lp), K, visit_t0, opt_t0, idx_c, st, visit_c, cand_c,
-            log_n, c_norm, comp, order);
-    LAUNCH_CHECK("gibbs_exact");
-    components_kernel<<<1, BNPC_LEAN_MAXK, 0, s>>>(comp, K, SW_PAR_WARPS);
-    LAUNCH_CHECK("components");
+        BNPC_LAUNCH(gibbs_exact_kernel, EX_THREADS, 0, cdiv(C, EX_THREADS), EX_THREADS, smem, s,  x1, x0, W, M, reinterpret_cast<const double2*>(lp), K, visit_t0, opt_t0, idx_c, st, visit_c, cand_c, log_n, c_norm, comp, order);
+    BNPC_LAUNCH(components_kernel, BNPC_LEAN_MAXK, 0, 1, BNPC_LEAN_MAXK, 0, s, comp, K, SW_PAR_WARPS);
     // (the processing order is not needed any more: its buffer receives the owner bytes)
-    owner_bytes_kernel<<<cdiv(C, 256), 256, 0, s>>>(visit_c, st, comp, reinterpret_cast<uint8_t*>(order));
-    LAUNCH_CHECK("owner_bytes");
+    BNPC_LAUNCH(owner_bytes_kernel, 256, 0, cdiv(C, 256), 256, 0, s, visit_c, st, comp, reinterpret_cast<uint8_t*>(order));
     return 0;
 }
 
 int bnpc_gibbs_epoch_begin(const int32_t* live, int K, int32_t* lst, int32_t* cnt, int32_t* col_of_id,
                            int idcap, int32_t* st, int first, void* stream) {
     if (K > idcap) return bad_arg("K > idcap");
-    gibbs_epoch_begin_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(live, K, lst, cnt, col_of_id, idcap, st,
-                                                                  first);
-    LAUNCH_CHECK("gibbs_epoch_begin");
+    BNPC_LAUNCH(gibbs_epoch_begin_kernel, 0, 0, 1, 1024, 0, (cudaStream_t)stream, live, K, lst, cnt, col_of_id, idcap, st, first);
     return 0;
 }
 
@@ -2528,54 +2569,44 @@ int bnpc_gibbs_sweep(const bnpc_sweep_args_t* a, int block_threads, void* stream
     if (a->t_begin < a->t_epoch0 || a->t_end - a->t_epoch0 > a->ldx) return bad_arg("sweep range vs ldx");
     // 256 threads leave the full register budget to the sequencer warp; long lists want 1024
     const size_t smem = sizeof(SweepShared);
-    static std::atomic<unsigned long long> done256{0}, done512{0}, done1024{0};
-    if (int rc = ensure_dyn_smem(gibbs_sweep_kernel<256>, (int)smem, done256, "gibbs_sweep smem attribute")) return rc;
-    if (int rc = ensure_dyn_smem(gibbs_sweep_kernel<512>, (int)smem, done512, "gibbs_sweep smem attribute")) return rc;
-    if (int rc = ensure_dyn_smem(gibbs_sweep_kernel<1024>, (int)smem, done1024, "gibbs_sweep smem attribute")) return rc;
     if (block_threads <= 256)
-        gibbs_sweep_kernel<256><<<1, block_threads, smem, (cudaStream_t)stream>>>(*a);
+        BNPC_LAUNCH(gibbs_sweep_kernel<256>, 256, 1, 1, block_threads, smem, (cudaStream_t)stream, *a);
     else if (block_threads <= 512)
-        gibbs_sweep_kernel<512><<<1, block_threads, smem, (cudaStream_t)stream>>>(*a);
+        BNPC_LAUNCH(gibbs_sweep_kernel<512>, 512, 1, 1, block_threads, smem, (cudaStream_t)stream, *a);
     else
-        gibbs_sweep_kernel<1024><<<1, block_threads, smem, (cudaStream_t)stream>>>(*a);
-    LAUNCH_CHECK("gibbs_sweep");
+        BNPC_LAUNCH(gibbs_sweep_kernel<1024>, 1024, 1, 1, block_threads, smem, (cudaStream_t)stream, *a);
     return 0;
 }
 
 int bnpc_set_ranks(const int32_t* ids, int K, int32_t* rank_of_id, void* stream) {
     if (K <= 0) return 0;
-    set_ranks_kernel<<<cdiv(K, 256), 256, 0, (cudaStream_t)stream>>>(ids, K, rank_of_id);
-    LAUNCH_CHECK("set_ranks");
+    BNPC_LAUNCH(set_ranks_kernel, 0, 0, cdiv(K, 256), 256, 0, (cudaStream_t)stream, ids, K, rank_of_id);
     return 0;
 }
 
 int bnpc_group_members(const int32_t* assign, int N, const int32_t* rank_of_id, const int32_t* seg_off,
                        int32_t* cursor, int K, int32_t* members, void* stream) {
     if (N <= 0) return 0;
-    cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)K, (cudaStream_t)stream);
-    if (e != cudaSuccess) return fail("group_members memset", e);
-    group_members_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(assign, N, rank_of_id, seg_off,
-                                                                        cursor, members);
-    LAUNCH_CHECK("group_members");
+    if (int rc = zero_async(cursor, sizeof(int32_t) * (size_t)K, stream, "group_members memset")) return rc;
+    BNPC_LAUNCH(group_members_kernel, 0, 0, cdiv(N, 256), 256, 0, (cudaStream_t)stream, assign, N, rank_of_id, seg_off, cursor, members);
     return 0;
 }
 
 int bnpc_suffstat(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* members,
                   const int32_t* seg_off, int R, int max_len, int32_t* S1, int32_t* S0, void* stream) {
     if (R <= 0) return 0;
-    cudaError_t e = cudaMemsetAsync(S1, 0, sizeof(int32_t) * (size_t)R * M, (cudaStream_t)stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(S0, 0, sizeof(int32_t) * (size_t)R * M, (cudaStream_t)stream);
-    if (e != cudaSuccess) return fail("suffstat memset", e);
+    if (int rc = zero_async(S1, sizeof(int32_t) * (size_t)R * M, stream, "suffstat memset")) return rc;
+    if (int rc = zero_async(S0, sizeof(int32_t) * (size_t)R * M, stream, "suffstat memset")) return rc;
     if (max_len <= 0) return 0;
     int wc_log2 = 2;                       // word columns per CTA row group: 4, 8, 16 or 32
     while ((1 << wc_log2) < W && wc_log2 < 5) ++wc_log2;
-    // grid.y is limited to 65535: tile the segment axis
-    for (int r0 = 0; r0 < R; r0 += 65535) {
-        const int rr = min(65535, R - r0);
-        dim3 grid(cdiv(max_len, SS_CHUNK), rr, cdiv(W, 32));
-        suffstat_kernel<<<grid, SS_THREADS, 0, (cudaStream_t)stream>>>(x1, x0, W, M, members, seg_off + r0,
-                                                               S1 + (size_t)r0 * M, S0 + (size_t)r0 * M, wc_log2);
-        LAUNCH_CHECK("suffstat");
+    // grid.y = segments x word blocks, limited to 65535: tile the segment axis
+    const int n_wblk = cdiv(W, 32);
+    const int r_max = 65535 / n_wblk;
+    for (int r0 = 0; r0 < R; r0 += r_max) {
+        const int rr = min(r_max, R - r0);
+        dim3 grid(cdiv(max_len, SS_CHUNK), rr * n_wblk);
+        BNPC_LAUNCH(suffstat_kernel, SS_THREADS, 0, grid, SS_THREADS, 0, (cudaStream_t)stream, x1, x0, W, M, members, seg_off + r0, S1 + (size_t)r0 * M, S0 + (size_t)r0 * M, wc_log2, n_wblk);
     }
     return 0;
 }
@@ -2584,18 +2615,14 @@ int bnpc_beta_rows(const int32_t* S1, const int32_t* S0, int R, int M, double p,
                    const double* tape, uint64_t seed, uint64_t stream_id, float* theta_out,
                    const int32_t* out_ids, void* stream) {
     if (R <= 0) return 0;
-    beta_rows_kernel<<<cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream>>>(
-        S1, S0, R, M, p, q, tape, seed, stream_id, theta_out, out_ids);
-    LAUNCH_CHECK("beta_rows");
+    BNPC_LAUNCH(beta_rows_kernel, 0, 0, cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream,  S1, S0, R, M, p, q, tape, seed, stream_id, theta_out, out_ids);
     return 0;
 }
 
 int bnpc_theta_from_uniform(const double* u, int R, int M, float* theta_out, const int32_t* out_ids,
                             void* stream) {
     if (R <= 0) return 0;
-    theta_from_uniform_kernel<<<cdiv((long long)R * M, 256), 256, 0, (cudaStream_t)stream>>>(u, R, M, theta_out,
-                                                                                           out_ids);
-    LAUNCH_CHECK("theta_from_uniform");
+    BNPC_LAUNCH(theta_from_uniform_kernel, 0, 0, cdiv((long long)R * M, 256), 256, 0, (cudaStream_t)stream, u, R, M, theta_out, out_ids);
     return 0;
 }
 
@@ -2612,9 +2639,7 @@ int bnpc_mh_theta(float* theta, const int32_t* ids, int R, int M, const int32_t*
                   int32_t* declined, void* stream) {
     if (R <= 0) return 0;
     if ((flags & 1) && !logq) return bad_arg("logq required when flags&1");
-    mh_theta_kernel<<<cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream>>>(
-        theta, ids, R, M, S1, S0, rnd, make_mh_const(FN, FP, p, q), flags, logq, declined);
-    LAUNCH_CHECK("mh_theta");
+    BNPC_LAUNCH(mh_theta_kernel, 0, 0, cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream,  theta, ids, R, M, S1, S0, rnd, make_mh_const(FN, FP, p, q), flags, logq, declined);
     return 0;
 }
 
@@ -2622,9 +2647,7 @@ int bnpc_theta_log_ratio(const float* th_new, const float* th_old, int R, int M,
                          const int32_t* S0, const double* sd_idx, float blo, float bhi, double FN,
                          double FP, double p, double q, double* A, void* stream) {
     if (R <= 0) return 0;
-    theta_log_ratio_kernel<<<cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream>>>(
-        th_new, th_old, R, M, S1, S0, sd_idx, blo, bhi, make_mh_const(FN, FP, p, q), A);
-    LAUNCH_CHECK("theta_log_ratio");
+    BNPC_LAUNCH(theta_log_ratio_kernel, 0, 0, cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream,  th_new, th_old, R, M, S1, S0, sd_idx, blo, bhi, make_mh_const(FN, FP, p, q), A);
     return 0;
 }
 
@@ -2639,15 +2662,13 @@ int bnpc_row_loglik(const float* theta, const int32_t* ids, int R, int M, const 
     for (int e = 0; e < E; ++e) { g.fn[e] = fn_h[e]; g.fp[e] = fp_h[e]; }
     g.p = p; g.q = q;
     g.betaln = lgamma(p) + lgamma(q) - lgamma(p + q);
-    row_loglik_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(theta, ids, R, M, S1, S0, g, out, prior_out);
-    LAUNCH_CHECK("row_loglik");
+    BNPC_LAUNCH(row_loglik_kernel, 256, 0, R, 256, 0, (cudaStream_t)stream, theta, ids, R, M, S1, S0, g, out, prior_out);
     return 0;
 }
 
 int bnpc_row_sum(const double* v, int R, int M, double* out, void* stream) {
     if (R <= 0) return 0;
-    row_sum_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(v, R, M, out);
-    LAUNCH_CHECK("row_sum");
+    BNPC_LAUNCH(row_sum_kernel, 256, 0, R, 256, 0, (cudaStream_t)stream, v, R, M, out);
     return 0;
 }
 
@@ -2655,19 +2676,15 @@ int bnpc_gather_members(const int32_t* assign, int N, int id_a, int id_b, int32_
                         int32_t* blk, void* stream) {
     if (N <= 0) return 0;
     const int nb = cdiv(N, 1024);
-    gather_count_kernel<<<nb, 1024, 0, (cudaStream_t)stream>>>(assign, N, id_a, id_b, blk);
-    LAUNCH_CHECK("gather_count");
-    gather_scan_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(blk, nb);
-    LAUNCH_CHECK("gather_scan");
-    gather_scatter_kernel<<<nb, 1024, 0, (cudaStream_t)stream>>>(assign, N, id_a, id_b, blk, cells_out);
-    LAUNCH_CHECK("gather_scatter");
+    BNPC_LAUNCH(gather_count_kernel, 1024, 0, nb, 1024, 0, (cudaStream_t)stream, assign, N, id_a, id_b, blk);
+    BNPC_LAUNCH(gather_scan_kernel, 0, 0, 1, 32, 0, (cudaStream_t)stream, blk, nb);
+    BNPC_LAUNCH(gather_scatter_kernel, 1024, 0, nb, 1024, 0, (cudaStream_t)stream, assign, N, id_a, id_b, blk, cells_out);
     return 0;
 }
 
 int bnpc_anchor_swaps(int32_t* cells, int n, int n_a, int idx_i, int idx_j, int is_merge, void* stream) {
     if (n < 2) return bad_arg("n < 2");
-    anchor_swaps_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(cells, n, n_a, idx_i, idx_j, is_merge);
-    LAUNCH_CHECK("anchor_swaps");
+    BNPC_LAUNCH(anchor_swaps_kernel, 0, 0, 1, 32, 0, (cudaStream_t)stream, cells, n, n_a, idx_i, idx_j, is_merge);
     return 0;
 }
 
@@ -2676,22 +2693,18 @@ int bnpc_rg_launch_halves(const uint32_t* x1, const uint32_t* x0, int W, const i
     if (n <= 2) return 0;
     K6 k;
     for (int i = 0; i < 6; ++i) k.k[i] = k6_h[i];
-    rg_launch_halves_kernel<<<cdiv(n - 2, 128), 128, 0, (cudaStream_t)stream>>>(x1, x0, W, cells, n, k, half);
-    LAUNCH_CHECK("rg_launch_halves");
+    BNPC_LAUNCH(rg_launch_halves_kernel, 0, 0, cdiv(n - 2, 128), 128, 0, (cudaStream_t)stream, x1, x0, W, cells, n, k, half);
     return 0;
 }
 
 int bnpc_rg_sides(const int32_t* cells, int n, const int32_t* half, int32_t* members, int32_t* seg_off,
                   void* stream) {
     if (n < 2) return bad_arg("n < 2");
-    cudaError_t e = cudaMemsetAsync(seg_off, 0, sizeof(int32_t) * 8, (cudaStream_t)stream);
-    if (e != cudaSuccess) return fail("rg_sides memset", e);
+    if (int rc = zero_async(seg_off, sizeof(int32_t) * 8, stream, "rg_sides memset")) return rc;
     if (n > 2) {
-        rg_count_kernel<<<cdiv(n - 2, 256), 256, 0, (cudaStream_t)stream>>>(half, n - 2, seg_off);
-        LAUNCH_CHECK("rg_count");
+        BNPC_LAUNCH(rg_count_kernel, 0, 0, cdiv(n - 2, 256), 256, 0, (cudaStream_t)stream, half, n - 2, seg_off);
     }
-    rg_sides_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(cells, n, half, members, seg_off);
-    LAUNCH_CHECK("rg_sides");
+    BNPC_LAUNCH(rg_sides_kernel, 0, 0, cdiv(n, 256), 256, 0, (cudaStream_t)stream, cells, n, half, members, seg_off);
     return 0;
 }
 
@@ -2705,27 +2718,21 @@ int bnpc_rg_scan(const double* ll2, int ldk, int n, const int32_t* perm, const d
     const int nf = n - 2;
     const int out_off = (nf + 3) & ~3;
     cudaStream_t st = (cudaStream_t)stream;
-    rg_prepare_kernel<<<cdiv(nf, 128), 128, 0, st>>>(ll2, ldk, n, perm, u, half, alpha, mode, cells, assign,
-                                                     id_i, work);
-    LAUNCH_CHECK("rg_prepare");
-    rg_serial_kernel<<<1, 32, 0, st>>>(half, nf, work, out_off);
-    LAUNCH_CHECK("rg_serial");
-    rg_finish_kernel<<<cdiv(nf, 128), 128, 0, st>>>(ll2, ldk, n, perm, half, alpha, mode, work, out_off, lq);
-    LAUNCH_CHECK("rg_finish");
+    BNPC_LAUNCH(rg_prepare_kernel, 0, 0, cdiv(nf, 128), 128, 0, st, ll2, ldk, n, perm, u, half, alpha, mode, cells, assign, id_i, work);
+    BNPC_LAUNCH(rg_serial_kernel, 32, 0, 1, 32, 0, st, half, nf, work, out_off);
+    BNPC_LAUNCH(rg_finish_kernel, 0, 0, cdiv(nf, 128), 128, 0, st, ll2, ldk, n, perm, half, alpha, mode, work, out_off, lq);
     return 0;
 }
 
 int bnpc_apply_split(const int32_t* cells, int n, const int32_t* half, int new_id, int32_t* assign,
                      void* stream) {
-    apply_split_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(cells, n, half, new_id, assign);
-    LAUNCH_CHECK("apply_split");
+    BNPC_LAUNCH(apply_split_kernel, 0, 0, cdiv(n, 256), 256, 0, (cudaStream_t)stream, cells, n, half, new_id, assign);
     return 0;
 }
 
 int bnpc_apply_merge(const int32_t* cells, int n_a, int n, int id, int32_t* assign, void* stream) {
     if (n <= n_a) return 0;
-    apply_merge_kernel<<<cdiv(n - n_a, 256), 256, 0, (cudaStream_t)stream>>>(cells, n_a, n, id, assign);
-    LAUNCH_CHECK("apply_merge");
+    BNPC_LAUNCH(apply_merge_kernel, 0, 0, cdiv(n - n_a, 256), 256, 0, (cudaStream_t)stream, cells, n_a, n, id, assign);
     return 0;
 }
 

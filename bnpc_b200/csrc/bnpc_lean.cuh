@@ -17,14 +17,13 @@
 //   compact_index_kernel    visit indices of the uncertain visits, in visiting order
 //   gibbs_exact_kernel      FP64 log-likelihoods of their options -> compacted visit/option records
 
-__global__ void lp_to_f32_kernel(const double2* __restrict__ lp, long long n, float2* __restrict__ lpf) {
+__device__ __forceinline__ void lp_to_f32_kernel(const double2* __restrict__ lp, long long n, float2* __restrict__ lpf) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const double2 v = lp[i]; lpf[i] = make_float2((float)v.x, (float)v.y); }
 }
 
 #define LLF_KT 16
-__global__ void __launch_bounds__(LL_THREADS)
-ll_matrix_f32_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
+__device__ __forceinline__ void ll_matrix_f32_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
                      const int32_t* __restrict__ cells, int cell_stride, int C,
                      const float2* __restrict__ lp, int K, float* __restrict__ ll, int ldk) {
     __shared__ float2 tile[LL_MT][LLF_KT];
@@ -77,8 +76,7 @@ ll_matrix_f32_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict
 // never exceed the total in magnitude and FP32 accumulation (rounded or truncated, in any order)
 // is off by at most terms * 2^-23 * |sum|; the factor 2 and the constant are head-room.  err_abs
 // = 0.05 + the absolute error of the rows (the quantisation of the integer rows, M * q / 2).
-__global__ void __launch_bounds__(CAND_THREADS)
-gibbs_options_kernel(const float* __restrict__ llf, int ldf, int K, const int32_t* __restrict__ col_of_id,
+__device__ __forceinline__ void gibbs_options_kernel(const float* __restrict__ llf, int ldf, int K, const int32_t* __restrict__ col_of_id,
                      const bnpc_visit_t* __restrict__ visit, bnpc_opt_t* __restrict__ opt,
                      int32_t* __restrict__ n_cert, int C, float slack, double c_norm, float err_rel,
                      float err_abs) {
@@ -123,8 +121,7 @@ gibbs_options_kernel(const float* __restrict__ llf, int ldf, int K, const int32_
     if (threadIdx.x < K && s_cert[threadIdx.x]) atomicAdd(&n_cert[threadIdx.x], s_cert[threadIdx.x]);
 }
 
-__global__ void __launch_bounds__(CAND_THREADS)
-gibbs_finalize_kernel(bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ n_cert, int C,
+__device__ __forceinline__ void gibbs_finalize_kernel(bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ n_cert, int C,
                       int32_t* __restrict__ blk) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     int uncertain = 0;
@@ -141,8 +138,7 @@ gibbs_finalize_kernel(bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ 
     if (threadIdx.x == 0) blk[blockIdx.x] = cnt;
 }
 
-__global__ void __launch_bounds__(CAND_THREADS)
-compact_index_kernel(const bnpc_opt_t* __restrict__ opt, int C, const int32_t* __restrict__ blk,
+__device__ __forceinline__ void compact_index_kernel(const bnpc_opt_t* __restrict__ opt, int C, const int32_t* __restrict__ blk,
                      int32_t* __restrict__ idx_c) {
     __shared__ int wcnt[CAND_THREADS / 32];
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,8 +158,7 @@ compact_index_kernel(const bnpc_opt_t* __restrict__ opt, int C, const int32_t* _
 // Visits of one cluster mostly share their option set, so the lanes of a warp read the same table
 // entries (shared-memory broadcasts instead of 4-8-way bank conflicts).  The order inside a group
 // is arbitrary -- every visit is computed independently and written to its own slot.
-__global__ void __launch_bounds__(256)
-exact_hist_kernel(const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ idx_c,
+__device__ __forceinline__ void exact_hist_kernel(const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ idx_c,
                   const int32_t* __restrict__ st, int32_t* __restrict__ comp) {
     __shared__ int h[BNPC_LEAN_MAXK];
     if (threadIdx.x < BNPC_LEAN_MAXK) h[threadIdx.x] = 0;
@@ -179,8 +174,7 @@ exact_hist_kernel(const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict_
     if (threadIdx.x < BNPC_LEAN_MAXK && h[threadIdx.x]) atomicAdd(&comp[256 + threadIdx.x], h[threadIdx.x]);
 }
 
-__global__ void __launch_bounds__(BNPC_LEAN_MAXK)
-exact_scan_kernel(int32_t* __restrict__ comp) {
+__device__ __forceinline__ void exact_scan_kernel(int32_t* __restrict__ comp) {
     __shared__ int v[BNPC_LEAN_MAXK];
     const int c = threadIdx.x;
     v[c] = comp[256 + c];
@@ -190,8 +184,7 @@ exact_scan_kernel(int32_t* __restrict__ comp) {
     comp[320 + c] = base;
 }
 
-__global__ void __launch_bounds__(256)
-exact_scatter_kernel(const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ idx_c,
+__device__ __forceinline__ void exact_scatter_kernel(const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ idx_c,
                      const int32_t* __restrict__ st, int32_t* __restrict__ comp, int32_t* __restrict__ order) {
     const int n_unc = st[BNPC_ST_NUNC];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -218,8 +211,7 @@ exact_scatter_kernel(const bnpc_opt_t* __restrict__ opt, const int32_t* __restri
 // is the log-probability selected by the entry (adding it is what fma(1, lp, acc) does in
 // ll_matrix_kernel).  The summation order differs from ll_matrix_kernel's, i.e. values agree to
 // ~1e-13 relative, far inside the guard band of the sweep's fast draws (SW_GUARD).
-__global__ void __launch_bounds__(EX_THREADS)
-gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
+__device__ __forceinline__ void gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
                    const double2* __restrict__ lp, int K, const bnpc_visit_t* __restrict__ visit,
                    const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ idx_c,
                    int32_t* __restrict__ st, bnpc_visit_t* __restrict__ visit_c,
@@ -386,8 +378,7 @@ gibbs_exact_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__
 
 // The same kernel staging ALL K columns per round (shared memory 2 KB x K per CTA): the variant
 // of most round-1 measurements, kept selectable (BNPC_EXACT_STAGING=all) for comparison.
-__global__ void __launch_bounds__(EX_THREADS)
-gibbs_exact_allcols_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
+__device__ __forceinline__ void gibbs_exact_allcols_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
                    const double2* __restrict__ lp, int K, const bnpc_visit_t* __restrict__ visit,
                    const bnpc_opt_t* __restrict__ opt, const int32_t* __restrict__ idx_c,
                    int32_t* __restrict__ st, bnpc_visit_t* __restrict__ visit_c,
@@ -528,8 +519,7 @@ gibbs_exact_allcols_kernel(const uint32_t* __restrict__ x1, const uint32_t* __re
 // column, [192,256) owner warp per column.  One block of 64 threads: connected components of the
 // option graph, then the components are dealt to `n_warps` warps, heaviest first, each to the
 // warp with the least records so far.
-__global__ void __launch_bounds__(BNPC_LEAN_MAXK)
-components_kernel(int32_t* __restrict__ comp, int K, int n_warps) {
+__device__ __forceinline__ void components_kernel(int32_t* __restrict__ comp, int K, int n_warps) {
     __shared__ unsigned long long m[BNPC_LEAN_MAXK];
     __shared__ int weight[BNPC_LEAN_MAXK], owner[BNPC_LEAN_MAXK], load[32];
     const int c = threadIdx.x;
@@ -581,8 +571,7 @@ components_kernel(int32_t* __restrict__ comp, int K, int n_warps) {
 // Owner warp of every compacted record (0xff: more options than a record holds or unknown own
 // column -- warp 0 posts it for the exact path), read by the parallel sequencer one byte per
 // record instead of two fields of the 64-byte visit records.
-__global__ void __launch_bounds__(256)
-owner_bytes_kernel(const bnpc_visit_t* __restrict__ visit_c, const int32_t* __restrict__ st,
+__device__ __forceinline__ void owner_bytes_kernel(const bnpc_visit_t* __restrict__ visit_c, const int32_t* __restrict__ st,
                    const int32_t* __restrict__ comp, uint8_t* __restrict__ owner) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= st[BNPC_ST_NUNC]) return;
@@ -594,8 +583,7 @@ owner_bytes_kernel(const bnpc_visit_t* __restrict__ visit_c, const int32_t* __re
 // Wide epochs: the dense FP64 matrix becomes option WEIGHTS in place, ll[t][k] <- exp(ll[t][k] - ref_t)
 // with ref_t = max(max_k ll[t][k], new-cluster score), and the visit record gets ref, the weight
 // of the new-cluster option and the column of the cell's own cluster.  One warp per visit.
-__global__ void __launch_bounds__(256)
-gibbs_weights_kernel(double* __restrict__ ll, int ldk, int K, const int32_t* __restrict__ col_of_id,
+__device__ __forceinline__ void gibbs_weights_kernel(double* __restrict__ ll, int ldk, int K, const int32_t* __restrict__ col_of_id,
                      bnpc_visit_t* __restrict__ visit, int C, double c_norm) {
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (r >= C) return;

@@ -87,7 +87,7 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* r) {
 // B table: chunk kc (64 reduction indices of one plane) x N rows x 64 bf16, each chunk stored
 // exactly as its shared-memory stage (K-major, 128-byte swizzle: 8-row groups of 1024 bytes, the
 // 16-byte piece c of row n at piece position c ^ (n & 7)).
-__global__ void lp_split_bf16_kernel(const double2* __restrict__ lp, int K, int M, int W, int KPAD,
+__device__ __forceinline__ void lp_split_bf16_kernel(const double2* __restrict__ lp, int K, int M, int W, int KPAD,
                                      uint16_t* __restrict__ Bg) {
     const int N = 2 * KPAD;
     const long long total = (long long)W * N * 64;          // W chunks: W/2 per plane
@@ -115,10 +115,9 @@ __global__ void lp_split_bf16_kernel(const double2* __restrict__ lp, int K, int 
 }
 
 template <int KPAD>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W,
+__device__ __forceinline__ void ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W,
                     const int32_t* __restrict__ cells, int cell_stride, int C,
-                    const uint16_t* __restrict__ Bg, float* __restrict__ llf, int ldf) {
+                    const uint16_t* __restrict__ Bg, float* __restrict__ llf, int ldf, int n_ctas) {
     constexpr int N = 2 * KPAD;
     // consecutive MMAs go to NACC independent accumulator tiles, summed in the epilogue (no
     // read-after-write chain on one TMEM tile between back-to-back instructions)
@@ -162,7 +161,7 @@ ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         uint32_t it = 0, tile_count = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_count) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += n_ctas, ++tile_count) {
             const int r = tile * 128 + row;
             const bool live = r < C;
             const long long cell = cells ? cells[(long long)(live ? r : 0) * cell_stride] : (live ? r : 0);
@@ -234,7 +233,7 @@ ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
             // instruction descriptor: D f32, A/B bf16, both K-major, N, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
             uint32_t it = 0, tile_count = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_count) {
+            for (int tile = blockIdx.x; tile < n_tiles; tile += n_ctas, ++tile_count) {
                 if (tile_count > 0) mbar_wait(acc_empty, (tile_count - 1) & 1);
                 tc_fence_after();
                 for (int sidx = 0; sidx < n_stages; ++sidx, ++it) {
@@ -262,7 +261,7 @@ ll_matrix_tc_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
         // ---- B loader ----
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < n_tiles; tile += n_ctas) {
                 for (int sidx = 0; sidx < n_stages; ++sidx, ++it) {
                     const int slot = it % TC_NST;
                     if (it >= TC_NST) mbar_wait(&empty[slot], ((it / TC_NST) - 1) & 1);
@@ -286,14 +285,10 @@ template <int KPAD>
 static int launch_ll_tc(const uint32_t* x1, const uint32_t* x0, int W, const int32_t* cells, int cell_stride,
                         int C, const uint16_t* Bg, float* llf, int ldf, cudaStream_t s) {
     const size_t smem = (size_t)TC_NST * TC_CPS * (2 * KPAD) * 128 + 256;
-    static std::atomic<unsigned long long> attr_done{0};
-    if (int rc = ensure_dyn_smem(ll_matrix_tc_kernel<KPAD>, (int)smem, attr_done, "ll_matrix_tc smem attribute")) return rc;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = cdiv(C, 128);
-    ll_matrix_tc_kernel<KPAD><<<tiles < sms ? tiles : sms, TC_THREADS, smem, s>>>(x1, x0, W, cells, cell_stride, C,
-                                                                                 Bg, llf, ldf);
-    LAUNCH_CHECK("ll_matrix_tc");
+    BNPC_LAUNCH(ll_matrix_tc_kernel<KPAD>, TC_THREADS, 1, tiles < sms ? tiles : sms, TC_THREADS, smem, s, x1, x0, W, cells, cell_stride, C, Bg, llf, ldf, tiles < sms ? tiles : sms);
     return 0;
 }
 

@@ -61,7 +61,7 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* r) {
 // Digit table: B chunk kc (128 reduction indices = two 64-bit pieces of one plane) x N rows x 128
 // bytes, each chunk stored exactly as its shared-memory image (K-major, 128-byte swizzle: 8-row
 // groups of 1024 bytes, the 16-byte piece c of row n at piece position c ^ (n & 7)).
-__global__ void lp_split_u8_kernel(const double2* __restrict__ lp, int K, int M, int W, int KPAD, double inv_q,
+__device__ __forceinline__ void lp_split_u8_kernel(const double2* __restrict__ lp, int K, int M, int W, int KPAD, double inv_q,
                                    uint8_t* __restrict__ Bg) {
     const int N = 2 * KPAD;
     const long long total = (long long)(W / 2) * N * 128;
@@ -92,11 +92,11 @@ __global__ void lp_split_u8_kernel(const double2* __restrict__ lp, int K, int M,
 static long long* g_t8_trace = nullptr;      // debug hook (bnpc_debug_set_trace)
 
 template <int KPAD>
-__global__ void __launch_bounds__(T8_THREADS, 1)
-ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W,
+__device__ __forceinline__ void ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W,
                     const int32_t* __restrict__ cells, int cell_stride, int C,
                     const uint8_t* __restrict__ Bg, float neg_q, float* __restrict__ llf, int ldf,
-                    long long* __restrict__ trace) {
+                    long long* __restrict__ trace, int n_ctas) {
+    // n_ctas: persistent CTAs of THIS chain's launch (a batched launch may hold more blocks)
     // trace (debug, normally NULL): clock64 stamps of CTA 0 -- [0,1024) producer warp 0 (3 per
     // stage: data expanded, previous store done + slot free, store issued), [1024,2048) MMA thread (4 per stage: stage full, first MMA issued, all issued, committed), [2048,..) epilogue warp 8 (2 per tile)
     const bool tr = trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
@@ -114,7 +114,7 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
     const int half = W / 2;
     const int n_stages = (W + T8_PIECES - 1) / T8_PIECES;           // (W is a multiple of 4: the last stage may be half)
     const int n_tiles = (C + 127) / 128;
-    const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / n_ctas + 1 : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < T8_NST; ++s) { mbar_init(&full[s], T8_PWARPS + 1); mbar_init(&empty[s], 1); }
@@ -153,8 +153,8 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
         };
         bool ok_cur, ok_n1, ok_n2;
         long long r_cur = row_of_tile(pf_tile, ok_cur);
-        long long r_n1 = row_of_tile(pf_tile + gridDim.x, ok_n1);
-        long long r_n2 = row_of_tile(pf_tile + 2 * gridDim.x, ok_n2);
+        long long r_n1 = row_of_tile(pf_tile + n_ctas, ok_n1);
+        long long r_n2 = row_of_tile(pf_tile + 2 * n_ctas, ok_n2);
         // cell of a row: loaded (or the row itself) -- always from a valid address
         int cell_cur = cells ? __ldg(cells + r_cur * cell_stride) : (int)r_cur;
         int cell_n1 = cells ? __ldg(cells + r_n1 * cell_stride) : (int)r_n1;
@@ -169,10 +169,10 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
                 ++pf_q;
                 if (++pf_sidx == n_stages) {
                     pf_sidx = 0;
-                    pf_tile += gridDim.x;
+                    pf_tile += n_ctas;
                     cell_cur = cell_n1; ok_cur = ok_n1;
                     cell_n1 = cell_n2; ok_n1 = ok_n2;
-                    r_n2 = row_of_tile(pf_tile + 2 * gridDim.x, ok_n2);
+                    r_n2 = row_of_tile(pf_tile + 2 * n_ctas, ok_n2);
                     cell_n2 = cells ? __ldg(cells + r_n2 * cell_stride) : (int)r_n2;
                 }
             }
@@ -232,7 +232,7 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         uint32_t tile_count = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_count) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += n_ctas, ++tile_count) {
             const uint32_t set = tile_count & 1u;
             mbar_wait(&acc_full[set], (tile_count >> 1) & 1);
             tc_fence_after();
@@ -269,7 +269,7 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
         const uint32_t idesc = (2u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
         const uint32_t smem_base = smem_u32(tc_smem);
         uint32_t it = 0, tile_count = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_count) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += n_ctas, ++tile_count) {
             const uint32_t set = tile_count & 1u;
             if (tile_count >= 2) mbar_wait(&acc_empty[set], ((tile_count >> 1) - 1) & 1);
             tc_fence_after();
@@ -308,7 +308,7 @@ ll_matrix_i8_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict_
         // ---- B loader ----
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < n_tiles; tile += n_ctas) {
                 for (int sidx = 0; sidx < n_stages; ++sidx, ++it) {
                     const int slot = it % T8_NST;
                     if (it >= T8_NST) mbar_wait(&empty[slot], ((it / T8_NST) - 1) & 1);
@@ -331,13 +331,9 @@ template <int KPAD>
 static int launch_ll_i8(const uint32_t* x1, const uint32_t* x0, int W, const int32_t* cells, int cell_stride,
                         int C, const uint8_t* Bg, float neg_q, float* llf, int ldf, cudaStream_t s) {
     const size_t smem = (size_t)T8_NST * (T8_PIECES / 2) * (2 * KPAD) * 128 + 256;
-    static std::atomic<unsigned long long> attr_done{0};
-    if (int rc = ensure_dyn_smem(ll_matrix_i8_kernel<KPAD>, (int)smem, attr_done, "ll_matrix_i8 smem attribute")) return rc;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = cdiv(C, 128);
-    ll_matrix_i8_kernel<KPAD><<<tiles < sms ? tiles : sms, T8_THREADS, smem, s>>>(x1, x0, W, cells, cell_stride, C,
-                                                                                 Bg, neg_q, llf, ldf, g_t8_trace);
-    LAUNCH_CHECK("ll_matrix_i8");
+    BNPC_LAUNCH(ll_matrix_i8_kernel<KPAD>, T8_THREADS, 1, tiles < sms ? tiles : sms, T8_THREADS, smem, s, x1, x0, W, cells, cell_stride, C, Bg, neg_q, llf, ldf, g_t8_trace, tiles < sms ? tiles : sms);
     return 0;
 }

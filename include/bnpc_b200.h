@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BNPC_ABI_VERSION 9
+#define BNPC_ABI_VERSION 10
 
 /* capacity of clusters born since the ll matrix of the current epoch was built */
 #define BNPC_MAX_EXTRA 32
@@ -441,6 +441,104 @@ int bnpc_chain_rg_scan_merged(const bnpc_chain_t* w, const bnpc_rg_t* g, int wan
 int bnpc_chain_rg_decide_split(const bnpc_chain_t* w, const bnpc_rg_t* g, int flat_prior, void* stream);
 int bnpc_chain_rg_decide_merge(const bnpc_chain_t* w, const bnpc_rg_t* g, int flat_prior, void* stream);
 int bnpc_chain_rg_apply(const bnpc_chain_t* w, const bnpc_rg_t* g, int new_id, void* stream);
+
+/* ==== chain group: all chains of one GPU stepped in lockstep by one host thread ==============
+ * The reference runs one process per chain (libs/MCMC.py:113-120), each looping over
+ * Chain.do_step + Chain.update_results (libs/MCMC.py:320-342, 242-282).  bnpc_group_run does the
+ * same for n chains of one device at once: per step the launches of all chains are recorded
+ * through the bnpc_chain_* entry points above and issued as chain-batched launches (one launch
+ * per kernel for up to 8 chains, blockIdx.z = chain), with one stream synchronisation per phase
+ * for the whole group.  Every chain draws from its own counter-based streams, so its trace does
+ * not depend on the group it runs in.
+ *
+ * bnpc_chain_state_t is the host-side state of one chain: constants of the model, then the
+ * mutable part (imported when a run starts, written back when it returns).  `live` is a HOST
+ * array of (id, size) pairs in list order.                                                    */
+typedef struct {
+    /* model constants (libs/CRP.py:27-66, libs/CRP_learning_errors.py:18-32) */
+    double p; double q; double mix0; double mix1;       /* Beta prior, _beta_mix_const            */
+    double dp_a0; double dp_b0;                         /* Gamma prior of alpha: shape, loc        */
+    double fp_mean; double fp_sd; double fn_mean; double fn_sd;
+    double fp_prior_const; double fn_prior_const;       /* truncnorm._logpdf(0, lo, hi) of the priors */
+    int32_t learning; int32_t beta_prior_uniform;
+    /* route switches of the sweep (bnpc_epoch_t.lean / serial_sweep) */
+    int32_t lean_enabled; int32_t lean_rows; int32_t serial_sweep; int32_t wide_enabled; int32_t force_wide;
+    /* mutable */
+    int32_t lean_ok; int32_t lean_cooldown; int32_t stats_fresh;
+    double DP_a; double FN; double FP;
+    uint64_t seed; uint64_t host_ctr /* host scalars drawn */; uint64_t dev_calls /* device streams reserved */;
+    int32_t K; int32_t live_cap /* pairs' ints available in live */; int32_t* live;
+    int64_t ll_cap; int64_t llx_cap /* doubles in bnpc_chain_t.ll / .llx */;
+    double mh_counter[10] /* [params, splits, merges, FP, FN] x [accepted, declined] */;
+    int32_t last_epochs; int32_t last_births; int32_t last_moved; int32_t last_nunc;
+} bnpc_chain_state_t;
+
+/* move probabilities of libs/MCMC.py:26-60 */
+typedef struct {
+    double sm_prob; double dpa_prob; double error_prob; double sm_ratios[2];
+    int32_t sm_steps; int32_t fix_assign;
+} bnpc_moves_t;
+
+/* per-chain trace destinations (libs/MCMC.py:231-282).  Scalar traces are host arrays indexed by
+ * step.  assign_h: PINNED host rows [.][assign_stride] int32 (NULL: the assignment trace stays in
+ * the device ring).  params_h: PINNED host [.][params_kcap][M] float, row (step - params_first)
+ * for steps >= params_first (NULL: not recorded): theta rows of the SORTED live cluster ids.     */
+typedef struct {
+    double* ml; double* map; double* alpha; double* fn; double* fp; int32_t* n_clusters;
+    int32_t* assign_h; int64_t assign_stride;
+    float* params_h; int32_t params_kcap; int32_t params_first;
+} bnpc_trace_t;
+
+/* the library never allocates device memory: when a chain needs more room it calls back.
+ * kind: BNPC_GROW_IDS (cluster id capacity >= need; the caller regrows the K-sized buffers and
+ * updates the bnpc_chain_t in place), _LL / _LLX (doubles in .ll / .llx; update ll_cap / llx_cap),
+ * _LIVE (ints in state.live), _PARAMS (trace.params_kcap >= need), _RING_K (theta ring clusters
+ * >= need: call bnpc_group_set_ring).  Returns 0 on success.                                  */
+#define BNPC_GROW_IDS 1
+#define BNPC_GROW_LL 2
+#define BNPC_GROW_LLX 3
+#define BNPC_GROW_LIVE 4
+#define BNPC_GROW_PARAMS 5
+#define BNPC_GROW_RING_K 6
+typedef int (*bnpc_grow_fn)(void* ctx, int chain, int kind, int64_t need);
+
+typedef struct bnpc_group bnpc_group_t;
+/* ws / st / tr: arrays of n pointers, kept by the group (the caller owns the structs and may
+ * update their fields from the grow callback).  streams: main (Gibbs + parameters), side
+ * (split-merge moves), copy (trace drain), cudaStream_t as void*.                             */
+bnpc_group_t* bnpc_group_create(int n, bnpc_chain_t* const* ws, bnpc_chain_state_t* const* st,
+                                bnpc_trace_t* const* tr, const bnpc_moves_t* moves,
+                                bnpc_grow_fn grow, void* grow_ctx,
+                                void* stream_main, void* stream_side, void* stream_copy);
+/* device trace rings: assign [slots][n][N] int32, theta [slots][n][kcap][M] float */
+int bnpc_group_set_ring(bnpc_group_t* g, int slots, int32_t* ring_assign, float* ring_theta, int kcap);
+/* steps step0 .. step0+n_steps-1 (trace rows of those indices) for all chains; returns after the
+ * traces have reached the host                                                                */
+int bnpc_group_run(bnpc_group_t* g, int step0, int n_steps);
+/* the trace row of the CURRENT state without a move (Chain.update_results(0), libs/MCMC.py:218) */
+int bnpc_group_record(bnpc_group_t* g, int step);
+void bnpc_group_destroy(bnpc_group_t* g);
+
+/* host scalars of a chain's random stream (draw *ctr, advanced): the Python mirror of the model
+ * draws from the same functions so that both hosts walk the same trajectory                    */
+double bnpc_host_random(uint64_t seed, uint64_t* ctr);
+double bnpc_host_gamma(uint64_t seed, uint64_t* ctr, double shape);
+double bnpc_host_beta(uint64_t seed, uint64_t* ctr, double a, double b);
+/* scipy.stats.truncnorm ppf / logpdf for scalars as the error-rate move uses them
+ * (libs/CRP_learning_errors.py:82-91)                                                          */
+double bnpc_host_truncnorm_ppf(double q, double lo, double hi);
+double bnpc_host_truncnorm_logpdf(double x, double lo, double hi, double loc, double scale);
+
+/* recorded launches: between begin and flush the bnpc_chain_* calls of the calling thread are
+ * queued under `slot` (bnpc_batch_slot) instead of launched; flush issues them on `stream`,
+ * merging the same launch of different slots into one chain-batched launch.                   */
+int bnpc_batch_begin(void);
+int bnpc_batch_slot(int slot);
+int bnpc_batch_flush(void* stream);
+/* per-kernel device times of the calling thread's launches (CUDA events around every launch; for
+ * profiling passes, not for timed runs).  report: text lines "name launches chains total_ms".   */
+int bnpc_prof_enable(int on);
+int bnpc_prof_report(char* buf, int cap);
 
 #ifdef __cplusplus
 }
