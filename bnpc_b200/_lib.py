@@ -5,6 +5,7 @@ loaded lazily.  There is no fallback: if the library is missing or a call fails
 a RuntimeError is raised.
 """
 import ctypes as C
+import glob
 import os
 import subprocess
 import threading
@@ -13,14 +14,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_HERE, 'libbnpc_b200.so')
 SOURCES = [os.path.join(_HERE, 'csrc', 'bnpc_kernels.cu')]
-HEADERS = [os.path.join(_HERE, 'csrc', 'bnpc_math.cuh'), os.path.join(_HERE, 'csrc', 'bnpc_chain.cuh'),
-           os.path.join(_HERE, 'csrc', 'bnpc_lean.cuh'), os.path.join(_HERE, 'csrc', 'bnpc_tc.cuh'),
-           os.path.join(_ROOT, 'include', 'bnpc_b200.h')]
+# every header of the translation unit: editing any of them makes the library stale
+HEADERS = sorted(glob.glob(os.path.join(_HERE, 'csrc', '*.cuh'))) + [os.path.join(_ROOT, 'include', 'bnpc_b200.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-fmad=false', '-std=c++17', '-shared', '-Xcompiler', '-fPIC']
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_EXTRA = 32
 ST_K, ST_TDONE, ST_FLAGS, ST_NEXTRA, ST_BIRTHS, ST_MOVED, ST_SLOW = range(7)
 ST_NUNC = 10
@@ -107,6 +107,35 @@ class RgMove(C.Structure):
         [('seed', C.c_uint64), ('stream_id', C.c_uint64)]
 
 
+class ChainState(C.Structure):
+    """bnpc_chain_state_t: host-side state of one chain of a group"""
+    _fields_ = [(n, C.c_double) for n in ('p', 'q', 'mix0', 'mix1', 'dp_a0', 'dp_b0', 'fp_mean', 'fp_sd', 'fn_mean',
+                                          'fn_sd', 'fp_prior_const', 'fn_prior_const')] + \
+        [(n, C.c_int32) for n in ('learning', 'beta_prior_uniform', 'lean_enabled', 'lean_rows', 'serial_sweep',
+                                  'wide_enabled', 'force_wide', 'lean_ok', 'lean_cooldown', 'stats_fresh')] + \
+        [(n, C.c_double) for n in ('DP_a', 'FN', 'FP')] + \
+        [(n, C.c_uint64) for n in ('seed', 'host_ctr', 'dev_calls')] + \
+        [('K', C.c_int32), ('live_cap', C.c_int32), ('live', C.c_void_p), ('ll_cap', C.c_int64),
+         ('llx_cap', C.c_int64), ('mh_counter', C.c_double * 10)] + \
+        [(n, C.c_int32) for n in ('last_epochs', 'last_births', 'last_moved', 'last_nunc')]
+
+
+class Moves(C.Structure):
+    """bnpc_moves_t"""
+    _fields_ = [('sm_prob', C.c_double), ('dpa_prob', C.c_double), ('error_prob', C.c_double),
+                ('sm_ratios', C.c_double * 2), ('sm_steps', C.c_int32), ('fix_assign', C.c_int32)]
+
+
+class Trace(C.Structure):
+    """bnpc_trace_t"""
+    _fields_ = [(n, C.c_void_p) for n in ('ml', 'map', 'alpha', 'fn', 'fp', 'n_clusters', 'assign_h')] + \
+        [('assign_stride', C.c_int64), ('params_h', C.c_void_p), ('params_kcap', C.c_int32),
+         ('params_first', C.c_int32)]
+
+
+GROW_IDS, GROW_LL, GROW_LLX, GROW_LIVE, GROW_PARAMS, GROW_RING_K = 1, 2, 3, 4, 5, 6
+GROW_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64)
+
 _WS, _EP, _RG = C.POINTER(ChainWs), C.POINTER(Epoch), C.POINTER(RgMove)
 
 # name -> argument ctypes, exactly as declared in include/bnpc_b200.h
@@ -158,7 +187,26 @@ SIGNATURES = {
     'bnpc_chain_rg_decide_split': [_WS, _RG, _I, _P],
     'bnpc_chain_rg_decide_merge': [_WS, _RG, _I, _P],
     'bnpc_chain_rg_apply': [_WS, _RG, _I, _P],
+    'bnpc_group_set_ring': [_P, _I, _P, _P, _I],
+    'bnpc_group_run': [_P, _I, _I],
+    'bnpc_group_record': [_P, _I],
+    'bnpc_batch_begin': [],
+    'bnpc_batch_slot': [_I],
+    'bnpc_batch_flush': [_P],
+    'bnpc_prof_enable': [_I],
+    'bnpc_prof_report': [C.c_char_p, _I],
 }
+
+# double-valued host helpers and the two entry points that do not return a status
+HOST_SCALAR_SIGNATURES = {
+    'bnpc_host_random': [_U64, C.POINTER(_U64)],
+    'bnpc_host_gamma': [_U64, C.POINTER(_U64), _D],
+    'bnpc_host_beta': [_U64, C.POINTER(_U64), _D, _D],
+    'bnpc_host_truncnorm_ppf': [_D, _D, _D],
+    'bnpc_host_truncnorm_logpdf': [_D, _D, _D, _D, _D],
+}
+OTHER_SYMBOLS = ('bnpc_abi_version', 'bnpc_last_error', 'bnpc_launch_count', 'bnpc_group_create',
+                 'bnpc_group_destroy')
 
 _lock = threading.Lock()
 _lib = None
@@ -175,6 +223,20 @@ class _Lib:
         self._dll.bnpc_last_error.restype = C.c_char_p
         self._dll.bnpc_abi_version.restype = C.c_int
         self._dll.bnpc_launch_count.restype = C.c_int64
+        if self._dll.bnpc_abi_version() != ABI_VERSION:
+            raise RuntimeError(f'{path} has ABI version {self._dll.bnpc_abi_version()}, this package expects '
+                               f'{ABI_VERSION}: rebuild it (python -c "import __graft_entry__ as g; g.build()")')
+        d = self._dll
+        d.bnpc_group_create.restype = C.c_void_p
+        d.bnpc_group_create.argtypes = [_I, C.POINTER(_WS), C.POINTER(C.POINTER(ChainState)),
+                                        C.POINTER(C.POINTER(Trace)), C.POINTER(Moves), GROW_FN, _P, _P, _P, _P]
+        d.bnpc_group_destroy.restype = None
+        d.bnpc_group_destroy.argtypes = [_P]
+        for name, args in HOST_SCALAR_SIGNATURES.items():
+            fn = getattr(d, name)
+            fn.restype = _D
+            fn.argtypes = args
+            setattr(self, name[len('bnpc_'):], fn)
         for name, args in SIGNATURES.items():
             fn = getattr(self._dll, name)
             fn.argtypes = args
@@ -192,6 +254,24 @@ class _Lib:
 
     def abi_version(self):
         return self._dll.bnpc_abi_version()
+
+    def group_create(self, *args):
+        h = self._dll.bnpc_group_create(*args)
+        if not h:
+            raise RuntimeError(f'bnpc_group_create failed: {self._dll.bnpc_last_error().decode()}')
+        return h
+
+    def group_destroy(self, h):
+        self._dll.bnpc_group_destroy(h)
+
+    def prof_report_text(self):
+        buf = C.create_string_buffer(1 << 16)
+        self.prof_report(buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, launches, chains, ms = line.rsplit(' ', 3)
+            out[name] = dict(launches=int(launches), chains=int(chains), total_ms=float(ms))
+        return out
 
 
 def lib():

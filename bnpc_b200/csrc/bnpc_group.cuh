@@ -181,8 +181,8 @@ struct Group {
     float* ring_theta;                     // [ring][n][ring_kcap][M]
     int ring_kcap;
     std::vector<cudaEvent_t> ev_snap, ev_drained;
-    long long steps_done;
-    char err[256];
+    long long steps_done, snaps;
+    std::vector<bnpc_trace_t*> tr;
 };
 
 static int group_fail(Group* g, const char* what) {
@@ -274,8 +274,11 @@ static int gibbs_enqueue(Group* g, int ci) {
     c.rows = c.lean ? N - c.t : (int)std::min<long long>(N - c.t, std::max<long long>(1, budget));
     c.ep.lean = c.lean ? c.s->lean_rows : (c.wide ? -1 : 0);
     if (!c.lean) {
-        if (g->grow(g->grow_ctx, ci, BNPC_GROW_LL, (long long)c.rows * ldk + 2)) return group_fail(g, "grow(ll) failed");
-        if (!c.wide && g->grow(g->grow_ctx, ci, BNPC_GROW_LLX, (long long)BNPC_MAX_EXTRA * c.rows))
+        const long long need = (long long)c.rows * ldk + 2, needx = (long long)BNPC_MAX_EXTRA * c.rows;
+        if (need > c.s->ll_cap && (g->grow(g->grow_ctx, ci, BNPC_GROW_LL, need) || need > c.s->ll_cap))
+            return group_fail(g, "grow(ll) failed");
+        if (!c.wide && needx > c.s->llx_cap &&
+            (g->grow(g->grow_ctx, ci, BNPC_GROW_LLX, needx) || needx > c.s->llx_cap))
             return group_fail(g, "grow(llx) failed");
     }
     c.ep.first = c.first; c.ep.K = K; c.ep.t = c.t; c.ep.rows = c.rows; c.ep.ldk = ldk;
@@ -541,7 +544,6 @@ static void propose_error(GroupChain& c, double cur, double sd0, double* prop, d
 static int params_enqueue(Group* g, int ci, bool do_errors) {
     GroupChain& c = g->ch[ci];
     const int K = c.K();
-    if (int rc = ensure_ids(g, ci, K + BNPC_MAX_EXTRA + 2)) return rc;
     if (!c.stats_fresh) {
         int32_t* h = c.w->h_in;
         int run = 0, mx = 0;
@@ -573,11 +575,13 @@ static int params_enqueue(Group* g, int ci, bool do_errors) {
     return bnpc_chain_loglik(c.w, K, fn, fp, E, want_prior, c.s->p, c.s->q, nullptr);
 }
 
-static void params_after(Group* g, GroupChain& c, double* ml, double* lprior) {
+static void params_after(Group* g, GroupChain& c, double* ml, double* lprior, bool with_moves) {
     const int K = c.K(), M = c.w->M;
-    const int declined = c.w->h_out[0];
-    c.s->mh_counter[0] += (double)((long long)K * M - declined);
-    c.s->mh_counter[1] += (double)declined;
+    if (with_moves) {
+        const int declined = c.w->h_out[0];
+        c.s->mh_counter[0] += (double)((long long)K * M - declined);
+        c.s->mh_counter[1] += (double)declined;
+    }
     const double* r = c.w->h_scal;
     double ll = r[0];
     if (c.err_move) {
@@ -611,13 +615,354 @@ static void params_after(Group* g, GroupChain& c, double* ml, double* lprior) {
     (void)g;
 }
 
-// ------------------------------------------------------------------ flush helpers
-static int flush_on(cudaStream_t s) { return recorder_flush(s); }
+// the trace row of the current state (Chain.update_results without a move)
+static int trace_only_enqueue(Group* g, int ci) {
+    GroupChain& c = g->ch[ci];
+    const int K = c.K();
+    if (!c.stats_fresh) {
+        int32_t* h = c.w->h_in;
+        int run = 0, mx = 0;
+        for (int j = 0; j < K; ++j) h[j] = c.ids[j];
+        h[K] = 0;
+        for (int j = 0; j < K; ++j) { run += c.sizes[j]; h[K + 1 + j] = run; mx = std::max(mx, c.sizes[j]); }
+        if (int rc = bnpc_chain_stats(c.w, K, mx, nullptr)) return rc;
+        c.stats_fresh = true;
+    }
+    c.err_move = false;
+    const double fn[1] = {c.s->FN}, fp[1] = {c.s->FP};
+    const int want_prior = c.s->beta_prior_uniform ? 0 : 1;
+    c.loglik_rows = 1 + want_prior;
+    (void)g;
+    return bnpc_chain_loglik(c.w, K, fn, fp, 1, want_prior, c.s->p, c.s->q, nullptr);
+}
 
+// ------------------------------------------------------------------ trace rows
 static int sync_stream(cudaStream_t s) {
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return fail("cudaStreamSynchronize", e);
     return 0;
 }
+#define CU(call, what)                                   \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return fail(what, e__);  \
+    } while (0)
+
+// snapshot of the assignment vector and of the theta rows of the sorted live ids into ring slot
+// `slot` (recorded: part of the phase-2 flush)
+static int snapshot_enqueue(Group* g, int ci, int slot, int step) {
+    GroupChain& c = g->ch[ci];
+    const bnpc_trace_t* tr = g->tr[ci];
+    const int N = c.w->N, M = c.w->M, K = c.K();
+    int32_t* dst = g->ring_assign + ((size_t)slot * g->n + ci) * N;
+    if (int rc = copy_async(dst, c.w->assign, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToDevice, nullptr)) return rc;
+    if (tr->params_h && step >= tr->params_first) {
+        if (K > g->ring_kcap) {
+            if (g->grow(g->grow_ctx, ci, BNPC_GROW_RING_K, K) || K > g->ring_kcap) return group_fail(g, "grow(ring) failed");
+        }
+        // sorted ids (libs/MCMC.py:261) behind the statistics' staging area of h_in
+        int32_t* h = c.w->h_in + 2 * K + 8;
+        std::vector<int> sorted(c.ids);
+        std::sort(sorted.begin(), sorted.end());
+        for (int j = 0; j < K; ++j) h[j] = sorted[j];
+        if (int rc = copy_async(c.w->cursor, h, sizeof(int32_t) * (size_t)K, cudaMemcpyHostToDevice, nullptr)) return rc;
+        float* rows = g->ring_theta + ((size_t)slot * g->n + ci) * (size_t)g->ring_kcap * M;
+        BNPC_LAUNCH(gather_rows_kernel, 0, 0, cdiv((long long)K * M, 256), 256, 0, nullptr, c.w->theta, c.w->cursor, K, M, rows);
+    }
+    return 0;
+}
+
+// ring slot -> the caller's pinned trace rows, on the copy stream
+static int drain_slot(Group* g, int slot, int step) {
+    for (int ci = 0; ci < g->n; ++ci) {
+        GroupChain& c = g->ch[ci];
+        bnpc_trace_t* tr = g->tr[ci];
+        const int N = c.w->N, M = c.w->M, K = c.K();
+        if (tr->assign_h) {
+            const int32_t* src = g->ring_assign + ((size_t)slot * g->n + ci) * N;
+            CU(cudaMemcpyAsync(tr->assign_h + (size_t)step * tr->assign_stride, src, sizeof(int32_t) * (size_t)N,
+                               cudaMemcpyDeviceToHost, g->sC), "trace copy (assignment)");
+        }
+        if (tr->params_h && step >= tr->params_first) {
+            if (K > tr->params_kcap) {
+                // the caller regrows its [steps][kcap][M] array (rows already written are kept)
+                CU(cudaStreamSynchronize(g->sC), "trace sync");
+                if (g->grow(g->grow_ctx, ci, BNPC_GROW_PARAMS, K) || K > tr->params_kcap)
+                    return group_fail(g, "grow(params) failed");
+            }
+            const float* src = g->ring_theta + ((size_t)slot * g->n + ci) * (size_t)g->ring_kcap * M;
+            float* dst = tr->params_h + (size_t)(step - tr->params_first) * tr->params_kcap * M;
+            CU(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)K * M, cudaMemcpyDeviceToHost, g->sC),
+               "trace copy (theta)");
+        }
+    }
+    return 0;
+}
+
+// phase 2 + trace row for all chains; with_moves = false records the current state only
+static int phase2_and_trace(Group* g, int step, bool with_moves) {
+    const int slot = (int)(g->snaps % g->ring);
+    // the ring slot must have been drained
+    CU(cudaStreamWaitEvent(g->sA, g->ev_drained[slot], 0), "wait(drained)");
+    g_rec.on = true;
+    int rc = 0;
+    for (int ci = 0; ci < g->n && !rc; ++ci) {
+        GroupChain& c = g->ch[ci];
+        g_rec.cur = ci;
+        if (with_moves) {
+            const bool do_err = c.s->learning && c.random() < g->mv.error_prob;
+            rc = params_enqueue(g, ci, do_err);
+        } else {
+            rc = trace_only_enqueue(g, ci);
+        }
+        if (!rc) rc = snapshot_enqueue(g, ci, slot, step);
+    }
+    g_rec.on = false;
+    if (rc) { for (int ci = 0; ci < GROUP_MAX; ++ci) g_rec.q[ci].clear(); return rc; }
+    if ((rc = recorder_flush(g->sA))) return rc;
+    CU(cudaEventRecord(g->ev_snap[slot], g->sA), "record(snapshot)");
+    if ((rc = sync_stream(g->sA))) return rc;
+    for (int ci = 0; ci < g->n; ++ci) {
+        GroupChain& c = g->ch[ci];
+        bnpc_trace_t* tr = g->tr[ci];
+        double ml, lprior;
+        params_after(g, c, &ml, &lprior, with_moves);
+        tr->ml[step] = ml;
+        tr->map[step] = ml + lprior;
+        tr->alpha[step] = c.s->DP_a;
+        tr->fn[step] = c.s->FN;
+        tr->fp[step] = c.s->FP;
+        if (tr->n_clusters) tr->n_clusters[step] = c.K();
+    }
+    CU(cudaStreamWaitEvent(g->sC, g->ev_snap[slot], 0), "wait(snapshot)");
+    if ((rc = drain_slot(g, slot, step))) return rc;
+    CU(cudaEventRecord(g->ev_drained[slot], g->sC), "record(drained)");
+    g->snaps += 1;
+    return 0;
+}
+
+// one MCMC step of all chains (libs/MCMC.py:320-342 + :242-282)
+static int group_step(Group* g, int step) {
+    int rc = 0;
+    unsigned long long maskG = 0, maskS = 0;
+    if (!g->mv.fix_assign) {
+        for (int ci = 0; ci < g->n; ++ci) {
+            GroupChain& c = g->ch[ci];
+            c.move = (c.random() < g->mv.sm_prob) ? 1 : 0;
+            if (c.move) maskS |= 1ull << ci; else maskG |= 1ull << ci;
+        }
+        // split-merge chains wait for the parameter phase of the previous step (stream A)
+        if (maskS) CU(cudaStreamWaitEvent(g->sB, g->evA, 0), "wait(phase 2)");
+        g_rec.on = true;
+        for (int ci = 0; ci < g->n && !rc; ++ci) {
+            GroupChain& c = g->ch[ci];
+            g_rec.cur = ci;
+            if (c.move) rc = sm_enqueue(g, ci);
+            else { gibbs_begin(g, c); rc = gibbs_enqueue(g, ci); }
+        }
+        g_rec.on = false;
+        if (rc) { for (int ci = 0; ci < GROUP_MAX; ++ci) g_rec.q[ci].clear(); return rc; }
+        if (maskS && (rc = recorder_flush(g->sB, maskS))) return rc;
+        if (maskG && (rc = recorder_flush(g->sA, maskG))) return rc;
+        // split-merge decisions
+        if (maskS) {
+            if ((rc = sync_stream(g->sB))) return rc;
+            g_rec.on = true;
+            for (int ci = 0; ci < g->n && !rc; ++ci)
+                if ((maskS >> ci) & 1ull) { g_rec.cur = ci; rc = sm_after(g, ci); }
+            g_rec.on = false;
+            if (rc) { for (int ci = 0; ci < GROUP_MAX; ++ci) g_rec.q[ci].clear(); return rc; }
+            if ((rc = recorder_flush(g->sB, maskS))) return rc;
+            CU(cudaEventRecord(g->evB, g->sB), "record(split-merge)");
+            CU(cudaStreamWaitEvent(g->sA, g->evB, 0), "wait(split-merge)");
+        }
+        // Gibbs epochs until every sweep is complete
+        unsigned long long open = maskG;
+        while (open) {
+            if ((rc = sync_stream(g->sA))) return rc;
+            g_rec.on = true;
+            for (int ci = 0; ci < g->n && !rc; ++ci) {
+                if (!((open >> ci) & 1ull)) continue;
+                int done = 0;
+                g_rec.cur = ci;
+                rc = gibbs_after(g, ci, &done);
+                if (!rc) {
+                    if (done) open &= ~(1ull << ci);
+                    else rc = gibbs_enqueue(g, ci);
+                }
+            }
+            g_rec.on = false;
+            if (rc) { for (int ci = 0; ci < GROUP_MAX; ++ci) g_rec.q[ci].clear(); return rc; }
+            if (open && (rc = recorder_flush(g->sA, open))) return rc;
+        }
+        for (int ci = 0; ci < g->n; ++ci) {
+            GroupChain& c = g->ch[ci];
+            if (c.random() < g->mv.dpa_prob) update_dp_alpha(c);
+        }
+    }
+    if ((rc = phase2_and_trace(g, step, true))) return rc;
+    CU(cudaEventRecord(g->evA, g->sA), "record(phase 2)");
+    g->steps_done += 1;
+    return 0;
+}
 
 }  // namespace bnpc
+
+extern "C" {
+
+double bnpc_host_random(uint64_t seed, uint64_t* ctr) { return bnpc::host_random(seed, ctr); }
+double bnpc_host_gamma(uint64_t seed, uint64_t* ctr, double shape) { return bnpc::host_gamma(seed, ctr, shape); }
+double bnpc_host_beta(uint64_t seed, uint64_t* ctr, double a, double b) { return bnpc::host_beta(seed, ctr, a, b); }
+double bnpc_host_truncnorm_ppf(double q, double lo, double hi) { return bnpc::h_tn_ppf(q, lo, hi); }
+double bnpc_host_truncnorm_logpdf(double x, double lo, double hi, double loc, double scale) {
+    return bnpc::h_tn_logpdf(x, lo, hi, loc, scale);
+}
+
+int bnpc_batch_begin(void) {
+    for (int c = 0; c < bnpc::GROUP_MAX; ++c) bnpc::g_rec.q[c].clear();
+    bnpc::g_rec.on = true;
+    bnpc::g_rec.cur = 0;
+    return 0;
+}
+int bnpc_batch_slot(int slot) {
+    if (slot < 0 || slot >= bnpc::GROUP_MAX) return bad_arg("slot");
+    bnpc::g_rec.cur = slot;
+    return 0;
+}
+int bnpc_batch_flush(void* stream) {
+    bnpc::g_rec.on = false;
+    return recorder_flush((cudaStream_t)stream);
+}
+
+int bnpc_prof_enable(int on) {
+    bnpc::g_prof.on = on != 0;
+    return 0;
+}
+int bnpc_prof_report(char* buf, int cap) {
+    using namespace bnpc;
+    struct Acc { const char* name; long long launches, chains; double ms; };
+    std::vector<Acc> acc;
+    for (ProfSlot& sl : g_prof.slots) {
+        float ms = 0.f;
+        cudaEventSynchronize(sl.b);
+        cudaEventElapsedTime(&ms, sl.a, sl.b);
+        Acc* a = nullptr;
+        for (Acc& x : acc) if (x.name == sl.name || strcmp(x.name, sl.name) == 0) { a = &x; break; }
+        if (!a) { acc.push_back(Acc{sl.name, 0, 0, 0.0}); a = &acc.back(); }
+        a->launches += 1; a->chains += sl.chains; a->ms += ms;
+        g_prof.pool.push_back(sl.a);
+        g_prof.pool.push_back(sl.b);
+    }
+    g_prof.slots.clear();
+    int off = 0;
+    for (Acc& x : acc) {
+        const int n = snprintf(buf + off, cap > off ? cap - off : 0, "%s %lld %lld %.6f\n", x.name, x.launches,
+                               x.chains, x.ms);
+        if (n < 0 || off + n >= cap) break;
+        off += n;
+    }
+    if (cap > 0) buf[off < cap ? off : cap - 1] = 0;
+    return 0;
+}
+
+bnpc_group_t* bnpc_group_create(int n, bnpc_chain_t* const* ws, bnpc_chain_state_t* const* st,
+                                bnpc_trace_t* const* tr, const bnpc_moves_t* moves, bnpc_grow_fn grow,
+                                void* grow_ctx, void* stream_main, void* stream_side, void* stream_copy) {
+    using namespace bnpc;
+    if (n <= 0 || n > GROUP_MAX || !ws || !st || !tr || !moves || !grow) { bad_arg("group arguments"); return nullptr; }
+    Group* g = new Group();
+    g->n = n;
+    g->ch.resize(n);
+    g->tr.assign(tr, tr + n);
+    for (int i = 0; i < n; ++i) { g->ch[i].w = ws[i]; g->ch[i].s = st[i]; }
+    g->mv = *moves;
+    g->grow = grow; g->grow_ctx = grow_ctx;
+    g->sA = (cudaStream_t)stream_main; g->sB = (cudaStream_t)stream_side; g->sC = (cudaStream_t)stream_copy;
+    g->ring = 0; g->ring_assign = nullptr; g->ring_theta = nullptr; g->ring_kcap = 0;
+    g->snaps = 0; g->steps_done = 0;
+    if (cudaEventCreateWithFlags(&g->evA, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g->evB, cudaEventDisableTiming) != cudaSuccess) {
+        delete g;
+        bad_arg("cudaEventCreate");
+        return nullptr;
+    }
+    cudaEventRecord(g->evA, g->sA);
+    return reinterpret_cast<bnpc_group_t*>(g);
+}
+
+int bnpc_group_set_ring(bnpc_group_t* gp, int slots, int32_t* ring_assign, float* ring_theta, int kcap) {
+    using namespace bnpc;
+    Group* g = reinterpret_cast<Group*>(gp);
+    if (!g || slots <= 0 || !ring_assign) return bad_arg("ring");
+    // pending drains read the old ring
+    if (cudaStreamSynchronize(g->sC) != cudaSuccess || cudaStreamSynchronize(g->sA) != cudaSuccess)
+        return bad_arg("ring sync");
+    while ((int)g->ev_snap.size() < slots) {
+        cudaEvent_t a, b;
+        if (cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) return bad_arg("cudaEventCreate");
+        cudaEventRecord(b, g->sC);
+        g->ev_snap.push_back(a);
+        g->ev_drained.push_back(b);
+    }
+    g->ring = slots; g->ring_assign = ring_assign; g->ring_theta = ring_theta; g->ring_kcap = kcap;
+    return 0;
+}
+
+static int group_enter(bnpc::Group* g) {
+    using namespace bnpc;
+    if (!g || g->ring <= 0) return bad_arg("group without a trace ring");
+    for (int ci = 0; ci < g->n; ++ci) {
+        GroupChain& c = g->ch[ci];
+        load_list(c);
+        c.stats_fresh = c.s->stats_fresh != 0;
+        c.move = -1;
+    }
+    for (int c = 0; c < GROUP_MAX; ++c) g_rec.q[c].clear();
+    return 0;
+}
+static int group_leave(bnpc::Group* g, int rc) {
+    using namespace bnpc;
+    g_rec.on = false;
+    // the traces have reached the host when this returns
+    cudaError_t e = cudaStreamSynchronize(g->sC);
+    if (!rc && e != cudaSuccess) rc = fail("trace drain", e);
+    cudaStreamSynchronize(g->sB);
+    cudaStreamSynchronize(g->sA);
+    for (int ci = 0; ci < g->n; ++ci) {
+        GroupChain& c = g->ch[ci];
+        if (int r2 = store_list(g, ci)) { if (!rc) rc = r2; }
+        c.s->stats_fresh = c.stats_fresh ? 1 : 0;
+    }
+    return rc;
+}
+
+int bnpc_group_run(bnpc_group_t* gp, int step0, int n_steps) {
+    using namespace bnpc;
+    Group* g = reinterpret_cast<Group*>(gp);
+    if (int rc = group_enter(g)) return rc;
+    int rc = 0;
+    for (int s = 0; s < n_steps && !rc; ++s) rc = group_step(g, step0 + s);
+    return group_leave(g, rc);
+}
+
+int bnpc_group_record(bnpc_group_t* gp, int step) {
+    using namespace bnpc;
+    Group* g = reinterpret_cast<Group*>(gp);
+    if (int rc = group_enter(g)) return rc;
+    return group_leave(g, phase2_and_trace(g, step, false));
+}
+
+void bnpc_group_destroy(bnpc_group_t* gp) {
+    using namespace bnpc;
+    Group* g = reinterpret_cast<Group*>(gp);
+    if (!g) return;
+    cudaStreamSynchronize(g->sC);
+    cudaEventDestroy(g->evA);
+    cudaEventDestroy(g->evB);
+    for (cudaEvent_t e : g->ev_snap) cudaEventDestroy(e);
+    for (cudaEvent_t e : g->ev_drained) cudaEventDestroy(e);
+    delete g;
+}
+
+}  // extern "C"

@@ -88,8 +88,10 @@ static int copy_async(void* dst, const void* src, size_t bytes, cudaMemcpyKind k
         const char* env = getenv("BNPC_UVA_COPIES");
         g_uva_copies = (env && env[0] == '0') ? 0 : 1;
     }
-    if (g_uva_copies && bnpc::g_rec.on && bytes <= BNPC_SMALL_COPY_BYTES && !(bytes & 3) &&
-        !(((uintptr_t)dst | (uintptr_t)src) & 3)) {
+    // recorded: device-to-device copies of any size and small copies from / to pinned host memory
+    // become kernel launches (they merge across chains); the rest stays a copy-engine operation
+    if (bnpc::g_rec.on && !(bytes & 3) && !(((uintptr_t)dst | (uintptr_t)src) & 3) &&
+        (kind == cudaMemcpyDeviceToDevice || (g_uva_copies && bytes <= BNPC_SMALL_COPY_BYTES))) {
         BNPC_LAUNCH(copy_words_kernel, 0, 0, cdiv((long long)(bytes >> 2), 256), 256, 0, stream,
                     reinterpret_cast<uint32_t*>(dst), reinterpret_cast<const uint32_t*>(src), (int)(bytes >> 2));
         return 0;
@@ -123,11 +125,12 @@ static int record_event(void* ev, void* stream) {
 // chains merged -- the slot with the most operations left leads (a chain that recorded an extra
 // operation catches up alone), every slot whose next operation is the same kernel with the same
 // block size joins its launch.
-static int recorder_flush(cudaStream_t s) {
+static int recorder_flush(cudaStream_t s, unsigned long long slots = ~0ull) {
     using namespace bnpc;
     Recorder& R = g_rec;
     size_t cur[GROUP_MAX];
-    for (int c = 0; c < GROUP_MAX; ++c) cur[c] = 0;
+    // slots outside the mask keep their queues (they go to another stream)
+    for (int c = 0; c < GROUP_MAX; ++c) cur[c] = ((slots >> c) & 1ull) ? 0 : R.q[c].size();
     int rc = 0;
     for (;;) {
         int lead = -1;
@@ -163,7 +166,8 @@ static int recorder_flush(cudaStream_t s) {
         if (rc) break;
         for (int i = 0; i < n; ++i) ++cur[who[i]];
     }
-    for (int c = 0; c < GROUP_MAX; ++c) R.q[c].clear();
+    for (int c = 0; c < GROUP_MAX; ++c)
+        if ((slots >> c) & 1ull) R.q[c].clear();
     return rc;
 }
 
@@ -2739,3 +2743,5 @@ int bnpc_apply_merge(const int32_t* cells, int n_a, int n, int id, int32_t* assi
 #include "bnpc_chain.cuh"
 
 }  // extern "C"
+
+#include "bnpc_group.cuh"

@@ -5,9 +5,11 @@ reference call site they stand in for:
 
 * `PhiloxRandom(seed)`  -- production.  Bulk draws are generated on the device by
   the library's Philox4x32-10 kernels (counter = element index, stream id =
-  running call counter), scalars by a host numpy Philox generator with the same
-  key.  A chain's stream depends only on its seed, never on which GPU or rank
-  runs it.
+  running call counter), host scalars by the library's host functions on the same
+  key (bnpc_host_random / _gamma / _beta: draw i of a chain is a function of
+  (seed, i)).  A chain's stream depends only on its seed, never on which GPU or
+  rank runs it, nor on whether this Python mirror or the native group driver
+  (bnpc_group_run) steps the chain.
 * `TapeRandom(tape)`    -- parity mode.  Replays a recorded sequence of primitive
   numpy-legacy draws ('u', 'int', 'perm', 'beta', 'gamma' records; see
   tests/golden/README.md) in the order the reference consumes them, uploading
@@ -15,6 +17,8 @@ reference call site they stand in for:
 
 Both return DEVICE tensors for bulk draws and Python scalars for host decisions.
 """
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -175,8 +179,8 @@ class PhiloxRandom(_Base):
 
     def __init__(self, seed):
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-        self.host = np.random.Generator(np.random.Philox(key=self.seed))
-        self.calls = 0
+        self.host_ctr = C.c_uint64(0)        # host scalars drawn so far
+        self.calls = 0                       # device streams reserved so far
         self.device_seed = self.seed
 
     def next_stream(self):
@@ -194,29 +198,30 @@ class PhiloxRandom(_Base):
 
     # scalars
     def random(self):
-        return float(self.host.random())
+        return _lib.lib().host_random(self.seed, C.byref(self.host_ctr))
 
     def uniform_host(self, n):
-        return self.host.random(n)
+        return np.array([self.random() for _ in range(n)])
 
     def randint(self, high):
-        return int(self.host.integers(0, high))
+        return int(np.floor(self.random() * high))
 
     def beta(self, a, b):
-        return float(self.host.beta(a, b))
+        return _lib.lib().host_beta(self.seed, C.byref(self.host_ctr), float(a), float(b))
 
     def gamma(self, shape, scale):
-        return float(self.host.gamma(shape, scale))
+        return _lib.lib().host_gamma(self.seed, C.byref(self.host_ctr), float(shape)) * scale
 
     def first_two_of_permutation(self, n):
-        i = int(self.host.integers(0, n))
-        j = int(self.host.integers(0, n - 1))
+        i = self.randint(n)
+        j = self.randint(n - 1)
         if j >= i:
             j += 1
         return i, j
 
     def init_labels(self, n):
-        return self.host.integers(0, n, size=n)
+        # initial labels are drawn once per chain, from a generator keyed like the chain
+        return np.random.Generator(np.random.Philox(key=self.seed)).integers(0, n, size=n)
 
     # bulk, device
     def _fill(self, count, levels=0):

@@ -3,11 +3,16 @@
 
 What changed against the reference driver:
   * chains are not forked into worker processes (libs/MCMC.py:113-120) -- a CUDA
-    context does not survive fork().  Each chain is one host thread driving its own
-    CUDA stream; chain c runs on GPU `c mod G`.  Under torchrun (WORLD_SIZE > 1)
-    rank r owns the chains {c : c mod WORLD_SIZE == r} on its LOCAL_RANK device and
-    the finished traces are gathered on rank 0 (`gather_results`); there is no
-    inter-GPU traffic inside the step loop.
+    context does not survive fork().  The chains that share a GPU form one
+    `bnpc_b200.group.ChainGroup`: ONE host thread steps them in lockstep through the
+    library's native driver (every kernel launched once for all chains, one stream
+    synchronisation per phase for the whole group); chain c runs on GPU `c mod G`.
+    Under torchrun (WORLD_SIZE > 1) rank r owns the chains {c : c mod WORLD_SIZE == r}
+    on its LOCAL_RANK device and the finished traces are gathered on rank 0
+    (`gather_chains`); there is no inter-GPU traffic inside the step loop.
+    `Chain.do_step` / `Chain.update_results` remain the per-chain public API (the
+    per-method Python mirror of the model, used by the parity tests); `Chain.run`,
+    `MCMC.run` and `run_chains` take the native driver whenever the models allow.
   * every chain draws from its own counter-based stream keyed by the chain seed, so
     a chain's trace does not depend on where it runs.
   * the number of chains is not capped at the CPU count (libs/MCMC.py:100).
@@ -27,6 +32,7 @@ except ImportError:                                    # pragma: no cover
     torch = None
 
 from bnpc_b200.rng import PhiloxRandom
+from bnpc_b200.group import ChainGroup, native_ok, pinned_zeros
 
 
 def _visible_gpus():
@@ -44,29 +50,6 @@ def dist_info():
 def chains_of_rank(n_chains, rank, world):
     """Chain c belongs to rank c mod world."""
     return [c for c in range(n_chains) if c % world == rank]
-
-
-def psrf_lugsail(ml_traces, burn_in):
-    """Lugsail batch-means potential scale reduction factor over the ML traces of several
-    chains with cube-root batches (Vats & Flegal 2018).  The lugsail run mode uses the reference's
-    own estimator, libs.utils.get_lugsail_batch_means_est (square-root batches); this variant is
-    kept for callers that want one common burn-in."""
-    x = np.stack([np.asarray(t[burn_in:], dtype=np.float64) for t in ml_traces])
-    m, n = x.shape
-    b = max(1, int(np.floor(n ** (1 / 3))))
-    if n < 3 * b or n // b < 2:
-        return np.inf
-
-    def tau(bs):
-        a = n // bs
-        means = x[:, :a * bs].reshape(m, a, bs).mean(axis=2)
-        mu = x.mean(axis=1, keepdims=True)
-        return bs * np.sum((means - mu) ** 2, axis=1) / (a - 1)
-
-    t2 = np.mean(2 * tau(b) - tau(max(1, b // 3)))
-    s2 = np.mean(np.var(x, axis=1, ddof=1))
-    sigma2 = ((n - 1) * s2 + t2) / n
-    return float(np.sqrt(sigma2 / s2)) if s2 > 0 else 1.0
 
 
 class MCMC:
@@ -115,7 +98,8 @@ class MCMC:
         # `assign=` (extension) only chooses the starting state
         self.fix_assign = bool(assign_file)
         if assign_file:
-            assign = [int(v) for v in np.loadtxt(assign_file, dtype=int).ravel()]
+            from libs.dpmmIO import load_txt
+            assign = load_txt(assign_file)
         # chain seeds as the reference derives them (libs/MCMC.py:102-104)
         if seed > 0:
             np.random.seed(seed)
@@ -136,69 +120,154 @@ class MCMC:
         mine = chains_of_rank(n, rank, world)
         gpus = max(1, _visible_gpus())
         self.chains = [None] * n
+        # the chains of one device are initialised one after another (the packed matrix is built
+        # once per device) and then stepped together by one host thread per device
+        by_device = {}
+        for c in mine:
+            dev = f'cuda:{local}' if world > 1 else f'cuda:{c % gpus}'
+            self.chains[c] = self.make_chain(chain_type, run_var, assign, c, verbosity, dev)
+            by_device.setdefault(dev, []).append(self.chains[c])
         errors = []
 
-        def work(c):
+        def work(group):
             try:
-                dev = f'cuda:{local}' if world > 1 else f'cuda:{c % gpus}'
-                self.chains[c] = self.run_chain(chain_type, run_var, assign, c, verbosity, dev)
+                run_chains(group)
             except BaseException as exc:              # surfaced below, never swallowed
-                errors.append((c, exc))
+                errors.append(exc)
 
-        if len(mine) == 1 or debug:
-            for c in mine:
-                work(c)
+        groups = list(by_device.values())
+        if len(groups) <= 1:
+            for group in groups:
+                work(group)
         else:
-            threads = [threading.Thread(target=work, args=(c,), name=f'chain{c}') for c in mine]
+            threads = [threading.Thread(target=work, args=(group,), name=f'gpu{i}')
+                       for i, group in enumerate(groups)]
             for t in threads:
                 t.start()
             for t in threads:
                 t.join()
         if errors:
-            raise RuntimeError(f'chain {errors[0][0]} failed: {errors[0][1]!r}') from errors[0][1]
+            raise RuntimeError(f'a chain group failed: {errors[0]!r}') from errors[0]
         if cutoff:
             self.run_lugsail_chains(cutoff, mine, verbosity_ls)
         if world > 1:
             self.chains = gather_chains(self.chains, n, rank, world)
         self.chains = [c for c in self.chains if c is not None]
 
-    def run_chain(self, chain_type, run_var, assign, i, verbosity, device=None):
+    def make_chain(self, chain_type, run_var, assign, i, verbosity, device=None):
+        """libs/MCMC.py:123-135 without the run: copy of the model, its own random stream keyed
+        by the chain seed, initial state, trace row 0."""
         model = deepcopy(self.model)
         if hasattr(model, 'device'):
             model.device = device
             model.rnd = PhiloxRandom(int(self.seeds[i]))
         model.init(assign=assign)
-        chain = chain_type(model, i + 1, *run_var, self.params, verbosity,
-                           getattr(self, 'fix_assign', False))
+        return chain_type(model, i + 1, *run_var, self.params, verbosity, getattr(self, 'fix_assign', False))
+
+    def run_chain(self, chain_type, run_var, assign, i, verbosity, device=None):
+        chain = self.make_chain(chain_type, run_var, assign, i, verbosity, device)
         chain.run()
         return chain
 
     def run_lugsail_chains(self, cutoff, mine, verbosity, n=200):
         """libs/MCMC.py:138-193: extend all chains by n steps until the PSRF of the ML
-        traces undercuts the cutoff."""
+        traces undercuts the cutoff.  Every rank takes part in every round (also one that owns
+        no chain: fewer chains than ranks)."""
+        from libs.utils import get_lugsail_batch_means_est
         local = [self.chains[c] for c in mine]
         while True:
-            steps_run = local[0].results['ML'].size
             traces = all_gather_objects([c.results['ML'] for c in local])
+            flat = [t for part in traces for t in part]
+            steps_run = flat[0].size
             # the reference's estimator (libs/utils.py:427-461), restated in libs/utils.py
-            from libs.utils import get_lugsail_batch_means_est
-            psrf = get_lugsail_batch_means_est([(t, steps_run // 2) for part in traces for t in part])
+            psrf = get_lugsail_batch_means_est([(t, steps_run // 2) for t in flat])
             if verbosity > 1:
                 print(f'\tPSRF at {steps_run}:\t{psrf:.5f}')
             for c in local:
                 c.results.setdefault('PSRF', []).append((steps_run, psrf))
             if psrf <= cutoff:
                 break
+            olds = [c.get_steps() for c in local]
             for c in local:
-                old = c.get_steps()
                 c._extend_results(n, False)
                 c.set_steps(n)
-                c.run(init_steps=old - 1)
+            if local:
+                run_chains(local, init_steps=olds[0] - 1)
         burn_in = (steps_run // 2) + 1
         for c in local:
             c.results['burn_in'] = burn_in
             c.results['params'] = c.results['params'][burn_in:]
             c.results['PSRF_cutoff'] = cutoff
+
+
+def run_chains(chains, init_steps=0):
+    """Run chains that share a device to completion: in lockstep through the native group driver
+    when their models allow it (CUDA model, counter-based random streams), else one after another
+    through the per-method Python mirror (parity tapes, foreign models)."""
+    if not chains:
+        return
+    native = torch is not None and all(native_ok(ch.model) for ch in chains)
+    if not native:
+        for ch in chains:
+            ch.run_python(init_steps) if isinstance(ch, Chain_steps) else ch.run_python()
+        return
+    group = ChainGroup(chains, chains[0].mcmc, chains[0].fix_assign)
+    try:
+        if isinstance(chains[0], Chain_steps):
+            _run_steps_native(group, chains, init_steps)
+        else:
+            _run_time_native(group, chains)
+    finally:
+        group.close()
+
+
+def _run_steps_native(group, chains, init_steps):
+    """Chain_steps.run (libs/MCMC.py:375-388) for a group: steps 1 .. steps-1, trace rows
+    init_steps + step; progress every tenth of the run."""
+    lead = chains[0]
+    steps = lead.steps
+    for ch in chains:
+        if ch.steps != steps:
+            raise RuntimeError('the chains of a group run the same number of steps')
+        ch._prepare_params(init_steps)
+    every = max(1, steps // 10) if lead.verbosity > 1 else steps
+    step = 1
+    while step < steps:
+        stop = min(steps, (step // every + 1) * every)
+        if lead.verbosity > 1 and step % every == 0:
+            for ch in chains:
+                ch.stdout_progress(step + init_steps, steps + init_steps)
+        group.run(step + init_steps, stop - step)
+        step = stop
+    for ch in chains:
+        ch.results['burn_in'] = ch.burn_in
+
+
+def _run_time_native(group, chains):
+    """Chain_time.run (libs/MCMC.py:423-440) for a group: step until the wall clock passes
+    end_time; theta rows are kept once it has passed burn_in."""
+    lead = chains[0]
+    step = 0
+    while True:
+        now = datetime.now()
+        if now > lead.end_time:
+            break
+        if lead.verbosity > 1 and step % 1000 == 0:
+            for ch in chains:
+                ch.stdout_progress(step, (lead.end_time - now).seconds / 60)
+        step += 1
+        try:
+            burn_in = now < lead.burn_in
+        except TypeError:
+            burn_in = False
+        for ch in chains:
+            if ch.results['ML'].size - step == 0:
+                ch._extend_results(burn_in=burn_in)
+            if not burn_in and ch._par_buf is None:
+                ch._par_alloc(step, len(ch.model.cells_per_cluster))
+        group.run(step, 1)
+    for ch in chains:
+        ch._trim(step + 1)
 
 
 # ------------------------------------------------------------------------------
@@ -216,28 +285,40 @@ def all_gather_objects(obj):
     return out
 
 
-def gather_trace_tensors(results, device):
-    """Gather the big per-chain trace arrays of all ranks on rank 0 with tensor collectives
-    (NCCL on GPUs, gloo on CPU): assignments [S,N] int32, params [S,Kmax,M] float32 zero-padded
-    to the global Kmax (as libs/utils.py:206-223 pads), scalar traces [S] float64.
+_SCALAR_KEYS = ('ML', 'MAP', 'DP_alpha', 'FN', 'FP')
+
+
+def gather_trace_tensors(results, device, chain_ids=None):
+    """Gather the per-chain trace arrays of all ranks on rank 0 with tensor collectives (NCCL on
+    GPUs, gloo on CPU): assignments [S,N] int32, params [Sp,Kmax,M] float32 zero-padded to the
+    global Kmax (as libs/utils.py:206-223 pads), scalar traces [S] float64.  Chains may differ in
+    length (run-time mode, libs/MCMC.py:395-440): every chain's (S, Sp, burn_in, id) header is
+    all-gathered first and the buffers are padded to the longest chain, then trimmed.
     `results` is this rank's list of chain result dicts (equal count on every rank).
-    Returns the list for all chains in rank-major order on rank 0, None elsewhere."""
+    Returns [(chain id, result dict)] for all chains on rank 0, None elsewhere."""
     dist = torch.distributed
     world, rank = dist.get_world_size(), dist.get_rank()
-    kmax = torch.tensor([max([r['params'].shape[1] for r in results] + [1])], device=device)
-    dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
-    kmax = int(kmax.item())
+    ids = list(chain_ids) if chain_ids is not None else [rank * len(results) + i for i in range(len(results))]
+    head = torch.tensor([[r['ML'].size, r['params'].shape[0], r['params'].shape[1], int(r['burn_in']), ids[i]]
+                         for i, r in enumerate(results)], dtype=torch.int64, device=device)
+    heads = [torch.empty_like(head) for _ in range(world)]
+    dist.all_gather(heads, head)
+    heads = torch.stack(heads).cpu().numpy()                    # [world][local][5]
+    s_max, sp_max, kmax = (int(heads[..., j].max()) for j in range(3))
+    kmax = max(kmax, 1)
     gathered = []
     for r in results:
-        S, k, M = r['params'].shape
-        par = np.zeros((S, kmax, M), dtype=np.float32)
-        par[:, :k] = r['params']
-        packs = {
-            'assignments': torch.as_tensor(r['assignments'].astype(np.int32), device=device),
-            'params': torch.as_tensor(par, device=device),
-            'scalars': torch.as_tensor(np.stack([r['ML'], r['MAP'], r['DP_alpha'], r['FN'], r['FP']]),
-                                       device=device),
-        }
+        S, (Sp, k, M) = r['ML'].size, r['params'].shape
+        N = r['assignments'].shape[1]
+        par = np.zeros((sp_max, kmax, M), dtype=np.float32)
+        par[:Sp, :k] = r['params']
+        asg = np.zeros((s_max, N), dtype=np.int32)
+        asg[:S] = r['assignments']
+        sc = np.zeros((len(_SCALAR_KEYS), s_max))
+        for j, key in enumerate(_SCALAR_KEYS):
+            sc[j, :S] = r[key]
+        packs = {'assignments': torch.as_tensor(asg, device=device), 'params': torch.as_tensor(par, device=device),
+                 'scalars': torch.as_tensor(sc, device=device)}
         parts = {}
         for key, t in packs.items():
             bufs = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
@@ -248,31 +329,45 @@ def gather_trace_tensors(results, device):
         return None
     out = []
     for w in range(world):
-        for li, r in enumerate(results):
+        for li in range(len(results)):
+            S, Sp, _, burn_in, cid = (int(v) for v in heads[w, li])
             sc = gathered[li]['scalars'][w].cpu().numpy()
-            out.append(dict(assignments=gathered[li]['assignments'][w].cpu().numpy().astype(np.int64),
-                            params=gathered[li]['params'][w].cpu().numpy(), ML=sc[0], MAP=sc[1],
-                            DP_alpha=sc[2], FN=sc[3], FP=sc[4], burn_in=r['burn_in']))
+            res = dict(assignments=gathered[li]['assignments'][w].cpu().numpy()[:S],
+                       params=gathered[li]['params'][w].cpu().numpy()[:Sp], burn_in=burn_in)
+            for j, key in enumerate(_SCALAR_KEYS):
+                res[key] = sc[j, :S]
+            out.append((cid, res))
     return out
 
 
 def gather_chains(chains, n, rank, world):
-    """End-of-run gather replacing the pickle-through-pipe of libs/MCMC.py:114-118.  Falls
-    back to object gather when ranks hold different chain counts."""
+    """End-of-run gather replacing the pickle-through-pipe of libs/MCMC.py:114-118; the chains
+    come back in chain (= seed) order.  Scalar extras of a result (PSRF values of the lugsail
+    mode) travel as objects; falls back to an object gather when ranks hold different chain
+    counts."""
     if not _dist_ready():
         return chains
-    mine = [c for c in chains if c is not None]
+    mine = [(c, ch) for c, ch in enumerate(chains) if ch is not None]
     counts = all_gather_objects(len(mine))
-    if len(set(counts)) == 1 and mine and 'params' in mine[0].results:
-        dev = mine[0].model.device if hasattr(mine[0].model, 'device') else 'cpu'
-        res = gather_trace_tensors([c.results for c in mine], dev)
+    extras = all_gather_objects([(c, {k: v for k, v in ch.results.items()
+                                      if k not in _SCALAR_KEYS + ('assignments', 'params', 'burn_in')})
+                                 for c, ch in mine])
+    if len(set(counts)) == 1 and mine and 'params' in mine[0][1].results:
+        dev = mine[0][1].model.device if hasattr(mine[0][1].model, 'device') else 'cpu'
+        res = gather_trace_tensors([ch.results for _, ch in mine], dev, [c for c, _ in mine])
         if rank != 0:
             return []
-        return [_ResultOnly(r) for r in res]
-    parts = all_gather_objects([c.results for c in mine])
-    if rank != 0:
-        return []
-    return [_ResultOnly(r) for part in parts for r in part]
+    else:
+        parts = all_gather_objects([(c, ch.results) for c, ch in mine])
+        if rank != 0:
+            return []
+        res = [item for part in parts for item in part]
+    extra_of = {c: e for part in extras for c, e in part}
+    out = []
+    for c, r in sorted(res, key=lambda item: item[0]):
+        r.update(extra_of.get(c, {}))
+        out.append(_ResultOnly(r))
+    return out
 
 
 class _ResultOnly:
@@ -308,41 +403,49 @@ class Chain:
 
     def init_results(self, steps):
         """libs/MCMC.py:231-239.  The assignment trace is int32 (the reference's `int` is 64-bit:
-        twice the host memory, 4 GB per chain at 100k cells x 5000 steps) and is touched once here so
-        that recording a step never page-faults."""
+        twice the host memory, 4 GB per chain at 100k cells x 5000 steps) in page-locked memory:
+        the native driver's copy stream writes the rows while the next step runs."""
         n = self.model.cells_total
+        self._owners = {}
+        asg, self._owners['assignments'] = pinned_zeros((steps, n), np.int32)
         self.results = dict(ML=np.zeros(steps), MAP=np.zeros(steps), DP_alpha=np.zeros(steps),
-                            FN=np.empty(steps), FP=np.empty(steps),
-                            assignments=np.empty((steps, n), dtype=np.int32))
-        self.results['assignments'].fill(0)
+                            FN=np.zeros(steps), FP=np.zeros(steps), assignments=asg)
         self._par_buf = None          # [kept steps, cluster capacity, M]; results['params'] views it
+        self._par_first = 0           # trace row of _par_buf[0]
         self._par_k = 0
 
-    def _params_row(self, step, room, k):
-        """Row of the theta trace for this step with room for k clusters.  The reference pads the
-        whole [steps, K, M] array by one cluster whenever K grows (libs/MCMC.py:271-276); here the
-        cluster axis has spare capacity and results['params'] is a view of the columns in use."""
+    # -- theta trace: the reference pads the whole [steps, K, M] array by one cluster whenever K
+    # grows (libs/MCMC.py:271-276); here the cluster axis has spare capacity and
+    # results['params'] is a view of the columns in use
+    def _par_alloc(self, first_step, k):
+        rows = self.results['ML'].size - first_step
+        self._par_first = first_step
+        self._par_buf, self._owners['params'] = pinned_zeros((rows, max(8, 2 * k), self.model.muts_total),
+                                                             np.float32)
+
+    def _par_grow(self, k):
+        old = self._par_buf
+        if k <= old.shape[1]:
+            return
+        self._par_buf, self._owners['params'] = pinned_zeros((old.shape[0], max(k, 2 * old.shape[1]),
+                                                              old.shape[2]), np.float32)
+        self._par_buf[:, :old.shape[1]] = old
+
+    def _params_row(self, step, k):
         r = self.results
         if self._par_buf is None:
-            cap = max(8, 2 * k)
-            self._par_buf = np.zeros((room, cap, self.model.muts_total), dtype=np.float32)
-        if k > self._par_buf.shape[1]:
-            grown = np.zeros((self._par_buf.shape[0], max(k, 2 * self._par_buf.shape[1]),
-                              self.model.muts_total), dtype=np.float32)
-            grown[:, :self._par_buf.shape[1]] = self._par_buf
-            self._par_buf = grown
+            self._par_alloc(step, k)
+        self._par_grow(k)
         if k > self._par_k or 'params' not in r or r['params'].base is not self._par_buf:
             self._par_k = max(self._par_k, k)
             r['params'] = self._par_buf[:, :self._par_k]
-        first_kept = r['ML'].size - self._par_buf.shape[0]
-        return self._par_buf[step - first_kept]
+        return self._par_buf[step - self._par_first]
 
     def update_results(self, step, burn_in=True):
         """libs/MCMC.py:242-282: one trace row per step; theta rows of the SORTED live
         cluster ids are kept after burn-in."""
         r = self.results
-        room = r['ML'].size - step
-        if room == 0:
+        if r['ML'].size - step == 0:
             self._extend_results(burn_in=burn_in)
         ll = self.model.get_ll_full()
         r['ML'][step] = ll
@@ -357,7 +460,7 @@ class Chain:
         if burn_in:
             return
         clusters = np.sort(np.fromiter(self.model.cells_per_cluster.keys(), dtype=int))
-        row = self._params_row(step, room, clusters.size)
+        row = self._params_row(step, clusters.size)
         if hasattr(self.model, 'parameters_into'):
             self.model.parameters_into(clusters, row)
         else:
@@ -368,13 +471,17 @@ class Chain:
         if not add_size:
             add_size = min(200, r['ML'].size)
         if not burn_in and self._par_buf is not None:
-            self._par_buf = np.concatenate(
-                [self._par_buf, np.zeros((add_size,) + self._par_buf.shape[1:], dtype=np.float32)])
+            old = self._par_buf
+            self._par_buf, self._owners['params'] = pinned_zeros((old.shape[0] + add_size,) + old.shape[1:],
+                                                                 np.float32)
+            self._par_buf[:old.shape[0]] = old
             r['params'] = self._par_buf[:, :self._par_k]
         for key in ('ML', 'MAP', 'DP_alpha', 'FN', 'FP'):
             r[key] = np.append(r[key], np.zeros(add_size))
-        r['assignments'] = np.concatenate(
-            [r['assignments'], np.zeros((add_size, self.model.cells_total), dtype=np.int32)])
+        old = r['assignments']
+        r['assignments'], self._owners['assignments'] = pinned_zeros((old.shape[0] + add_size, old.shape[1]),
+                                                                     np.int32)
+        r['assignments'][:old.shape[0]] = old
 
     def stdout_progress(self):
         def show(counter, name, tabs=2):
@@ -408,6 +515,10 @@ class Chain:
             self.MH_counter[3] += fp
             self.MH_counter[4] += fn
 
+    def run(self, *args):
+        """libs/MCMC.py:375-388 / 423-440: this chain alone (a group of one)."""
+        run_chains([self], *args)
+
 
 class Chain_steps(Chain):
     def __init__(self, model, no, steps, burn_in, mcmc, verbosity=1, fix_assign=False):
@@ -427,17 +538,27 @@ class Chain_steps(Chain):
         print(f'\t{self}\tstep:\t{step_no: >3} / {total - 1}\n\t\tmean MH accept. ratio:')
         super().stdout_progress()
 
-    def run(self, init_steps=0):
+    def _is_burn_in(self, step):
+        try:
+            return step < self.burn_in
+        except TypeError:
+            return False
+
+    def _prepare_params(self, init_steps):
+        """theta trace of the rows this run will keep (native driver: the buffer exists before
+        the run; its first row is the first step past burn-in)"""
+        first = next((s for s in range(1, self.steps) if not self._is_burn_in(s)), None)
+        if first is not None and self._par_buf is None:
+            self._par_alloc(first + init_steps, len(self.model.cells_per_cluster))
+
+    def run_python(self, init_steps=0):
+        """the reference's loop over the per-method API (do_step + update_results)"""
         every = max(1, self.steps // 10)
         for step in range(1, self.steps):
             if self.verbosity > 1 and step % every == 0:
                 self.stdout_progress(step + init_steps, self.steps + init_steps)
             self.do_step()
-            try:
-                burn_in = step < self.burn_in
-            except TypeError:
-                burn_in = False
-            self.update_results(step + init_steps, burn_in)
+            self.update_results(step + init_steps, self._is_burn_in(step))
         self.results['burn_in'] = self.burn_in
 
 
@@ -454,7 +575,20 @@ class Chain_time(Chain):
               '\t\tmean MH accept. ratio:')
         super().stdout_progress()
 
-    def run(self):
+    def _trim(self, used):
+        """keep the rows that were written (libs/MCMC.py:434-440)"""
+        if self._par_buf is not None:
+            kept = max(0, used - self._par_first)
+            self._par_buf = self._par_buf[:kept]
+            self.results['params'] = self._par_buf[:, :self._par_k]
+        for key in list(self.results):
+            if key == 'params':
+                continue
+            self.results[key] = self.results[key][:used]
+        n_par = self.results['params'].shape[0] if 'params' in self.results else 0
+        self.results['burn_in'] = self.results['ML'].size - n_par
+
+    def run_python(self):
         step = 0
         while True:
             now = datetime.now()
@@ -469,13 +603,4 @@ class Chain_time(Chain):
             except TypeError:
                 burn_in = False
             self.update_results(step, burn_in)
-        used = step + 1
-        if 'params' in self.results:
-            first_kept = self.results['ML'].size - self.results['params'].shape[0]
-            self.results['params'] = self.results['params'][:max(0, used - first_kept)]
-        for key in list(self.results):
-            if key == 'params':
-                continue
-            self.results[key] = self.results[key][:used]
-        n_par = self.results['params'].shape[0] if 'params' in self.results else 0
-        self.results['burn_in'] = self.results['ML'].size - n_par
+        self._trim(step + 1)

@@ -28,8 +28,9 @@ def test_library_exports_header_symbols():
 
 
 def test_ctypes_signatures_match_header():
-    declared = set(_declared()) - {'bnpc_abi_version', 'bnpc_last_error', 'bnpc_launch_count'}
-    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    declared = set(_declared()) - set(_lib.OTHER_SYMBOLS)
+    bound = set(_lib.SIGNATURES) | set(_lib.HOST_SCALAR_SIGNATURES)
+    assert declared == bound, declared ^ bound
     assert _lib.lib().abi_version() == _lib.ABI_VERSION
 
 
@@ -41,7 +42,9 @@ def _struct_fields(name):
 
 
 @pytest.mark.parametrize('c_name,mirror', [('bnpc_sweep_args_t', 'SweepArgs'), ('bnpc_chain_t', 'ChainWs'),
-                                           ('bnpc_epoch_t', 'Epoch'), ('bnpc_rg_t', 'RgMove')])
+                                           ('bnpc_epoch_t', 'Epoch'), ('bnpc_rg_t', 'RgMove'),
+                                           ('bnpc_chain_state_t', 'ChainState'), ('bnpc_moves_t', 'Moves'),
+                                           ('bnpc_trace_t', 'Trace')])
 def test_struct_layouts_match_c(c_name, mirror):
     # field order of the ctypes mirrors of the structs declared in the header
     cls = getattr(_lib, mirror)
@@ -53,14 +56,16 @@ def test_struct_sizes_match_c(tmp_path):
     # compile a tiny C program against the header and compare sizeof() with the mirrors
     import subprocess
     src = tmp_path / 'sizes.c'
-    src.write_text('#include <stdio.h>\n#include "bnpc_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "bnpc_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(bnpc_sweep_args_t),sizeof(bnpc_chain_t),sizeof(bnpc_epoch_t),sizeof(bnpc_rg_t),'
-                   'sizeof(bnpc_visit_t),sizeof(bnpc_cand_t));return 0;}\n')
+                   'sizeof(bnpc_visit_t),sizeof(bnpc_cand_t),sizeof(bnpc_chain_state_t),sizeof(bnpc_moves_t),'
+                   'sizeof(bnpc_trace_t));return 0;}\n')
     exe = tmp_path / 'sizes'
     subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [ctypes.sizeof(_lib.SweepArgs), ctypes.sizeof(_lib.ChainWs), ctypes.sizeof(_lib.Epoch),
-            ctypes.sizeof(_lib.RgMove), _lib.VISIT_BYTES, _lib.CAND_BYTES]
+            ctypes.sizeof(_lib.RgMove), _lib.VISIT_BYTES, _lib.CAND_BYTES, ctypes.sizeof(_lib.ChainState),
+            ctypes.sizeof(_lib.Moves), ctypes.sizeof(_lib.Trace)]
     assert got == want
 
 

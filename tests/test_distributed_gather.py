@@ -20,14 +20,18 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _fake_results(chain, steps=7, cells=50, muts=12):
-    """trace dict of one finished chain, as Chain.update_results leaves it; K differs by chain"""
+def _fake_results(chain, steps=7, cells=50, muts=12, ragged=False):
+    """trace dict of one finished chain, as Chain.update_results leaves it; K differs by chain and
+    -- ragged: the run-time mode, libs/MCMC.py:395-440 -- so do the length and the burn-in"""
     rng = np.random.default_rng(100 + chain)
     k = 2 + chain
+    burn = 0
+    if ragged:
+        steps, burn = steps + 3 * chain, 1 + chain
     return dict(ML=rng.random(steps), MAP=rng.random(steps), DP_alpha=rng.random(steps),
                 FN=rng.random(steps), FP=rng.random(steps),
-                assignments=rng.integers(0, k, (steps, cells)),
-                params=rng.random((steps, k, muts)).astype(np.float32), burn_in=0)
+                assignments=rng.integers(0, k, (steps, cells)).astype(np.int32),
+                params=rng.random((steps - burn, k, muts)).astype(np.float32), burn_in=burn)
 
 
 class _Chain:
@@ -39,7 +43,7 @@ class _Chain:
         return self.results
 
 
-def _worker(rank, world, port, n_chains, out_path):
+def _worker(rank, world, port, n_chains, out_path, ragged=False):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
                       WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     import torch.distributed as dist
@@ -48,18 +52,18 @@ def _worker(rank, world, port, n_chains, out_path):
     mine = chains_of_rank(n_chains, rank, world)
     chains = [None] * n_chains
     for c in mine:
-        chains[c] = _Chain(_fake_results(c))
+        chains[c] = _Chain(_fake_results(c, ragged=ragged))
     got = gather_chains(chains, n_chains, rank, world)
     if rank == 0:
         np.save(out_path, np.array([len(got)] + [g.get_result()['params'].shape[1] for g in got]))
-        # rank-major order: chains of rank 0 first, then rank 1
-        order = [c for r in range(world) for c in chains_of_rank(n_chains, r, world)]
+        # chain (= seed) order, whatever rank ran the chain
         kmax = max(2 + c for c in range(n_chains))
-        for g, c in zip(got, order):
-            want, res = _fake_results(c), g.get_result()
+        for g, c in zip(got, range(n_chains)):
+            want, res = _fake_results(c, ragged=ragged), g.get_result()
+            assert res['burn_in'] == want['burn_in']
             np.testing.assert_array_equal(res['assignments'], want['assignments'])
             k = want['params'].shape[1]
-            assert res['params'].shape[1] == kmax
+            assert res['params'].shape[1] == kmax and res['params'].shape[0] == want['params'].shape[0]
             np.testing.assert_array_equal(res['params'][:, :k], want['params'])
             assert not res['params'][:, k:].any()            # zero padding to the global Kmax
             for key in ('ML', 'MAP', 'DP_alpha', 'FN', 'FP'):
@@ -81,5 +85,14 @@ def test_chain_partition():
 def test_gather_traces_world_size_2(tmp_path):
     out = str(tmp_path / 'n.npy')
     mp.spawn(_worker, args=(2, _free_port(), 4, out), nprocs=2, join=True)
+    n = np.load(out)
+    assert n[0] == 4 and (n[1:] == 5).all()
+
+
+@pytest.mark.timeout(180)
+def test_gather_traces_of_unequal_length(tmp_path):
+    # chains of the run-time mode end after different numbers of steps with different burn-ins
+    out = str(tmp_path / 'n.npy')
+    mp.spawn(_worker, args=(2, _free_port(), 4, out, True), nprocs=2, join=True)
     n = np.load(out)
     assert n[0] == 4 and (n[1:] == 5).all()
