@@ -3,21 +3,28 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3]
 
-One "step" = one Chain.do_step() + Chain.update_results() (reference libs/MCMC.py:381-386)
-of ONE chain.  Workload (default): BASELINE.json configs[2] = synthetic 100k cells x 1k
-mutations, learned error rates, 10 % missing, 8 chains per GPU started from the true
-assignment (steady state, K=20), default move probabilities.  Chains are independent:
-with N GPUs every rank runs its own 8 chains (weak scaling, no data-path collective).
+One "step" = one Chain.do_step() + Chain.update_results() (reference libs/MCMC.py:381-386) of ONE
+chain.  Workload (default): BASELINE.json configs[2] = synthetic 100k cells x 1k mutations, learned
+error rates, 10 % missing, 8 chains per GPU started from the true assignment (K = 20), default move
+probabilities.  Chains are independent: with N GPUs every rank runs its own 8 chains (weak scaling,
+no data-path collective).
 
-Printed JSON (rank 0, one line):
-  value   box chain-steps/s with traces kept on the device (no per-step host copy of the
-          assignment vector);   e2e = the same through the public driver API
-          (libs.MCMC.Chain_steps: host-side traces, device->host copies every step).
-  roofline  the dominant kernel (by CUDA-event time inside the timed region)
-  cpu_baseline  the CPU restatement of the reference (oracle/) timed on the host cores on
-          a bounded cell sample, extrapolated linearly in N (every per-step cost of the
-          reference is linear in the number of cells at fixed K and M).
---impl reference times that CPU path with one process per chain on all host cores.
+Both legs go through the public driver (libs.MCMC.Chain_steps objects stepped by
+libs.MCMC / bnpc_b200.group.ChainGroup, what MCMC.run does):
+  value   box chain-steps/s with the assignment trace kept in the device ring (scalar traces and
+          theta rows still reach the host);
+  e2e     the same with the full host-side traces of the reference (assignment vector, theta rows,
+          ML/MAP/alpha/FN/FP copied to pinned host arrays every step inside the timed region).
+A timed window is W warm-up + K timed steps from freshly initialised chains (same seeds every
+window, so every window walks the same trajectory); it is repeated --windows times and the MEDIAN
+is reported with the spread.  Extra figures: one chain alone, the evolved state (250 more warm-up
+steps), the other BASELINE shapes (C2, C4, C5; one short window each).
+  roofline      the kernel with the largest share of the device time of the step (CUDA events
+                around every launch, a separate untimed pass), with its algorithmic bytes / flops
+  cpu_baseline  the UNMODIFIED reference classes (baseline/_ref, shipped by oracle/fetch_ref.py;
+                else the oracle port) on the host cores on a bounded cell sample
+--impl reference times the reference's own Chain_steps.do_step + update_results on the FULL
+workload, one process per chain (its mp.Pool layout), for as many steps as fit its time budget.
 """
 import argparse
 import json
@@ -25,7 +32,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -45,23 +51,26 @@ REF_US_PER_CELL_STEP = 550.0     # planning anchor to size
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='C3', choices=sorted(CONFIGS))
     ap.add_argument('--chains-per-gpu', type=int, default=8)
+    ap.add_argument('--windows', type=int, default=5, help='repetitions of the timed window (median reported)')
     ap.add_argument('--cells', type=int, default=0, help='override the number of cells (debug)')
     ap.add_argument('--muts', type=int, default=0, help='override the number of mutations (debug)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip single-chain / evolved-state / C2,C4,C5 figures')
     ap.add_argument('--cpu-sample-cells', type=int, default=0)
+    ap.add_argument('--ref-budget-s', type=float, default=240.0, help="--impl reference: seconds of stepping")
     return ap.parse_args()
 
 
-def workload(args):
-    cfg = dict(CONFIGS[args.config])
-    if args.cells:
+def workload(args, name=None):
+    cfg = dict(CONFIGS[name or args.config])
+    if args.cells and name is None:
         cfg['cells'] = args.cells
-    if args.muts:
+    if args.muts and name is None:
         cfg['muts'] = args.muts
     return cfg
 
@@ -81,62 +90,110 @@ def model_kwargs(cfg):
     return dict(DP_alpha=[-1, -1], param_beta=list(cfg['pp']), FN_error=cfg['FN'], FP_error=cfg['FP'])
 
 
+def describe(name, cfg):
+    return (f'{name}: synthetic {cfg["cells"]} cells x {cfg["muts"]} mutations, K_true={cfg["k_true"]}, '
+            f'{int(cfg["miss"] * 100)}% missing, {"learned" if cfg["learning"] else "fixed"} error rates, '
+            'start = true assignment')
+
+
 # ---------------------------------------------------------------------------------------
-# CPU arm: the oracle restatement of the reference (the only place bench.py touches oracle/)
+# CPU arm: the unmodified reference (baseline/_ref) or, without it, the oracle port -- the only
+# place bench.py touches oracle/
 # ---------------------------------------------------------------------------------------
+_CPU_DATA = {}
+
+
 def _cpu_chain(job):
-    """One chain of the CPU restatement on a cell sample; returns seconds for the timed steps."""
-    cfg, sample_cells, seed, warm, steps = job
+    """One chain on the host: the reference's own Chain_steps (do_step + update_results), timed
+    step by step until `budget_s` of stepping or `steps` steps; returns the per-step seconds."""
+    kind, cfg, cells, seed, warm, steps, budget_s = job
+    data, z = _CPU_DATA.get('d') or make_matrix(cells, cfg['muts'], cfg['k_true'], cfg['fn'], cfg['fp'],
+                                                cfg['miss'], seed=0)
+    moves = moves_of(cfg)
+    np.random.seed(seed)
+    if kind == 'reference':
+        from oracle.ref_shim import load_reference, ref_errstate
+        ref = load_reference(with_mcmc=True)
+        cls = ref.CRP_learning_errors.CRP_errors_learning if cfg['learning'] else ref.CRP.CRP
+        with ref_errstate():
+            model = cls(data, **model_kwargs(cfg))
+            model.init(assign=[int(v) for v in z])
+            params = dict(moves, param_proposal_sd=np.array([0.1, 0.25, 0.5]))
+            chain = ref.MCMC.Chain_steps(model, 1, warm + steps, 0, params, 0, False)
+
+            def one(i):
+                chain.do_step()                       # libs/MCMC.py:320-342
+                chain.update_results(i, False)        # libs/MCMC.py:242-282
+            return _timed_steps(one, warm, steps, budget_s)
     from oracle.crp_oracle import OracleCRP, OracleCRPLearnErrors, do_step
     from oracle.rng_tape import LegacyRandom
-    data, z = make_matrix(sample_cells, cfg['muts'], cfg['k_true'], cfg['fn'], cfg['fp'], cfg['miss'], seed=0)
-    np.random.seed(seed)
     rnd = LegacyRandom()
-    cls = OracleCRPLearnErrors if cfg['learning'] else OracleCRP
-    model = cls(data, rnd=rnd, **model_kwargs(cfg))
+    model = (OracleCRPLearnErrors if cfg['learning'] else OracleCRP)(data, rnd=rnd, **model_kwargs(cfg))
     model.init(assign=[int(v) for v in z])
-    moves = moves_of(cfg)
 
-    def one():
+    def one(i):
         do_step(model, rnd, moves, cfg['learning'])
         ll = model.get_ll_full()                       # Chain.update_results, libs/MCMC.py:252-258
         _ = ll + model.get_lprior_full()
         _ = model.assignment.copy()
-
-    for _ in range(warm):
-        one()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one()
-    return time.perf_counter() - t0
+    return _timed_steps(one, warm, steps, budget_s)
 
 
-def cpu_sample_cells(cfg, steps, warm, budget_s, forced=0):
-    if forced:
-        return min(forced, cfg['cells'])
-    per_cell = REF_US_PER_CELL_STEP * 1e-6 * cfg['muts'] / 1000.0
-    n = int(budget_s / max(1, steps + warm) / per_cell)
-    return int(min(cfg['cells'], max(300, min(n, 5000))))
+def _timed_steps(one, warm, steps, budget_s):
+    for i in range(warm):
+        one(1 + i)
+    secs, t_begin = [], time.perf_counter()
+    for i in range(steps):
+        t0 = time.perf_counter()
+        one(1 + warm + i)
+        secs.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    return secs
 
 
-def run_cpu(cfg, n_chains, steps, warm, budget_s, forced=0):
+def cpu_kind():
+    from oracle.ref_shim import reference_available
+    return 'reference' if reference_available() else 'port'
+
+
+def run_cpu(cfg, n_chains, steps, warm, budget_s, cells):
+    """n_chains chains, one process each on the host cores (the reference's mp.Pool layout,
+    libs/MCMC.py:100,113); chains beyond the core count queue, as in the reference."""
     import multiprocessing as mp
+    kind = cpu_kind()
+    if kind == 'reference':
+        from oracle.ref_shim import load_reference
+        load_reference(with_mcmc=True)                      # imported once, inherited by the workers
     cores = max(1, min(n_chains, os.cpu_count() or 1))
-    sample = cpu_sample_cells(cfg, steps, warm, budget_s, forced)
-    jobs = [(cfg, sample, 1000 + c, warm, steps) for c in range(cores)]
+    _CPU_DATA['d'] = make_matrix(cells, cfg['muts'], cfg['k_true'], cfg['fn'], cfg['fp'], cfg['miss'], seed=0)
+    jobs = [(kind, cfg, cells, 1000 + c, warm, steps, budget_s) for c in range(cores)]
     if cores == 1:
-        secs = [_cpu_chain(jobs[0])]
+        per_chain = [_cpu_chain(jobs[0])]
     else:
-        with mp.get_context('spawn').Pool(cores) as pool:
-            secs = pool.map(_cpu_chain, jobs)
-    scale = sample / cfg['cells']
-    # chain-steps/s on the sample, scaled to the full number of cells (costs linear in N)
-    box = sum(steps / s for s in secs) * scale
-    return dict(value=box, unit='chain-steps/s', cores=cores, kind='port',
-                sample=f'{sample} of {cfg["cells"]} cells x {cfg["muts"]} mutations, {steps} steps after '
-                       f'{warm} warm-up per chain, {cores} chain(s) = {cores} process(es); rate scaled by '
-                       f'{sample}/{cfg["cells"]} (per-step cost of the reference is linear in cells)',
-                per_chain=box / cores, seconds=max(secs))
+        with mp.get_context('fork').Pool(cores) as pool:     # the matrix is shared copy-on-write
+            per_chain = pool.map(_cpu_chain, jobs)
+    _CPU_DATA.clear()
+    done = min(len(s) for s in per_chain)                   # steps every chain completed
+    wall = max(sum(s[:done]) for s in per_chain)            # the slowest chain bounds the run
+    return dict(kind=kind, cores=cores, chains=cores, steps_done=done, seconds=wall,
+                box_rate=cores * done / wall, per_chain_rate=done / wall,
+                step_seconds_mean=float(np.mean([np.mean(s[:done]) for s in per_chain])))
+
+
+def cpu_baseline_sample(cfg, cells_forced=0):
+    """the bounded CPU leg of the default run: one chain on a cell sample (10-30 s of work)"""
+    per_cell = REF_US_PER_CELL_STEP * 1e-6 * cfg['muts'] / 1000.0
+    cells = cells_forced or int(min(cfg['cells'], max(300, min(int(25.0 / 3 / per_cell), 5000))))
+    r = run_cpu(cfg, 1, 2, 1, 60.0, cells)
+    scale = cells / cfg['cells']
+    return dict(value=r['box_rate'] * scale, unit='chain-steps/s', cores=1, kind=r['kind'],
+                sample=f'{cells} of {cfg["cells"]} cells x {cfg["muts"]} mutations, {r["steps_done"]} steps after 1 '
+                       f'warm-up, 1 chain = 1 process; rate scaled by {cells}/{cfg["cells"]} (every per-step cost '
+                       'of the reference is linear in cells); the full-size figure is `--impl reference`',
+                seconds=r['seconds'],
+                implementation='unmodified reference classes (baseline/_ref), numpy stand-in for bottleneck'
+                if r['kind'] == 'reference' else 'oracle/crp_oracle.py (CPU restatement of the reference)')
 
 
 # ---------------------------------------------------------------------------------------
@@ -151,7 +208,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}',
-                                       '--format=csv,noheader,nounits', '-lms', '200'],
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -184,36 +241,184 @@ class ClockSampler:
 
 
 def measured_peaks():
-    """(HBM GB/s, dense bf16 TFLOP/s sustained, source): the driver-written measurements of this
-    pool's B200s, else the fallback of B200_PROFILING.md."""
+    """(HBM GB/s, dense bf16 TFLOP/s burst, sustained, source): the driver-written measurements of
+    this pool's B200s, else the fallback of B200_PROFILING.md."""
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
             d = json.load(f)
-        return float(d['hbm_gbs']), float(d.get('bf16_tflops_sustained', d['bf16_tflops'])), \
-            'measured (MEASURED_PEAKS.json; bf16 = sustained figure, the kernel runs inside a long step)'
+        return (float(d['hbm_gbs']), float(d['bf16_tflops']), float(d.get('bf16_tflops_sustained', d['bf16_tflops'])),
+                'measured (MEASURED_PEAKS.json)')
     except Exception:
-        return 6650.0, 1400.0, 'fallback (B200_PROFILING.md)'
+        return 6650.0, 1590.0, 1400.0, 'fallback (B200_PROFILING.md)'
 
 
 def ncu_traffic():
     """DRAM bytes per launch of the profiled kernels (ncu --set full captures summarised under
     profiles/): {kernel: bytes} or {}."""
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
-            return json.load(f)
-    except Exception:
-        return {}
+    for name in ('r2_traffic.json', 'r1_traffic.json'):
+        try:
+            with open(os.path.join(ROOT, 'profiles', name)) as f:
+                return json.load(f)
+        except Exception:
+            continue
+    return {}
+
+
+class Bench:
+    """chains of one rank on one device + the timing protocol"""
+
+    def __init__(self, cfg, dev, rank, world, cpg):
+        import torch
+        import libs.CRP as crp
+        import libs.CRP_learning_errors as crple
+        self.torch = torch
+        self.cfg, self.dev, self.rank, self.world, self.cpg = cfg, dev, rank, world, cpg
+        self.N, self.M = cfg['cells'], cfg['muts']
+        data, z = make_matrix(self.N, self.M, cfg['k_true'], cfg['fn'], cfg['fp'], cfg['miss'], seed=0)
+        self.z_list = [int(v) for v in z]
+        cls = crple.CRP_errors_learning if cfg['learning'] else crp.CRP
+        self.proto = cls(data, **model_kwargs(cfg))
+        self.moves = dict(moves_of(cfg), param_proposal_sd=np.array([0.1, 0.25, 0.5]))
+
+    def chains(self, n, total_steps):
+        """n freshly initialised chains (seeds keyed by the global chain id) with trace room"""
+        from copy import deepcopy
+        from bnpc_b200.rng import PhiloxRandom
+        from libs.MCMC import Chain_steps
+        out = []
+        for c in range(n):
+            m = deepcopy(self.proto)
+            m.device = self.dev
+            m.rnd = PhiloxRandom(4242 + self.rank * self.cpg + c)
+            m.init(assign=self.z_list)
+            out.append(Chain_steps(m, self.rank * self.cpg + c + 1, total_steps, 0, self.moves, 0, False))
+        self.torch.cuda.synchronize()
+        return out
+
+    def window(self, n, warm, steps, host_assign, profile=False):
+        """one timed window: fresh chains, `warm` untimed steps, `steps` timed steps between
+        barriers + device synchronisation; returns (ms [max over ranks], launches, chains, extra)"""
+        import torch.distributed as dist
+        from bnpc_b200 import _lib
+        from bnpc_b200.group import ChainGroup
+        torch = self.torch
+        chains = self.chains(n, warm + steps + 1)
+        group = ChainGroup(chains, self.moves, False, host_assign=host_assign)
+        for ch in chains:
+            ch._prepare_params(0)
+        try:
+            group.run(1, warm)
+            for m in group.models:
+                m.h2d_bytes = m.d2h_bytes = 0
+            if self.world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            launches0 = _lib.launch_count()
+            if profile:
+                _lib.lib().prof_enable(1)
+            a.record()
+            group.run(1 + warm, steps)
+            torch.cuda.synchronize()
+            b.record()
+            b.synchronize()
+            prof = None
+            if profile:
+                _lib.lib().prof_enable(0)
+                prof = _lib.lib().prof_report_text()
+            ms = torch.tensor([a.elapsed_time(b)], device=self.dev, dtype=torch.float64)
+            launches = torch.tensor([_lib.launch_count() - launches0], device=self.dev, dtype=torch.float64)
+            if self.world > 1:
+                dist.barrier()
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+            m0 = chains[0].model
+            extra = dict(k_live=len(m0.cells_per_cluster), sweep=dict(m0.sweep_stats), prof=prof,
+                         ml_last=float(chains[0].results['ML'][warm + steps]),
+                         k_all=[len(ch.model.cells_per_cluster) for ch in chains])
+            return float(ms.item()), int(launches.item()), extra
+        finally:
+            group.close()
+
+    def trace_bytes_per_step(self, k_live):
+        """device->host bytes of one chain-step of the e2e leg, counted from the copies the driver
+        makes: the assignment row, the theta rows of the live clusters, five trace scalars, the
+        status words / live list / decision scalars of the phases (<= 1 KB)"""
+        return 4 * self.N + 4 * k_live * self.M + 5 * 8 + 1024
+
+    def repeat(self, n, warm, steps, windows, host_assign):
+        ms, launches, extra = [], [], None
+        for _ in range(windows):
+            t, l, extra = self.window(n, warm, steps, host_assign)
+            ms.append(t)
+            launches.append(l)
+        return ms, launches, extra
+
+
+def _rate(n_chains, steps, ms):
+    return n_chains * steps / (ms / 1e3)
+
+
+def _spread(vals):
+    v = np.asarray(vals, dtype=np.float64)
+    med = float(np.median(v))
+    return dict(median=med, min=float(v.min()), max=float(v.max()),
+                rel_spread=float((v.max() - v.min()) / med) if med else None, windows=len(vals))
+
+
+def kernel_table(prof, steps, n_chains, step_ms):
+    """per kernel: launches and device time per chain-step, share of the summed device time"""
+    total = sum(v['total_ms'] for v in prof.values()) or 1.0
+    rows = {}
+    for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['total_ms']):
+        rows[name] = dict(launches_per_step=v['launches'] / steps, chains_per_launch=v['chains'] / max(1, v['launches']),
+                          avg_launch_us=1e3 * v['total_ms'] / max(1, v['launches']),
+                          us_per_chain_step=1e3 * v['total_ms'] / (steps * n_chains),
+                          share_of_device_time=v['total_ms'] / total)
+    return rows, total / steps
+
+
+def roofline_of(name, row, work, peaks, traffic):
+    """roofline entry of one kernel from its measured launch time and its algorithmic work per
+    launch; work = dict(N, M, K, n_unc, chains)"""
+    hbm, bf16_burst, bf16_sus, src = peaks
+    N, M, K, n_unc = work['N'], work['M'], work['K'], work['n_unc']
+    chains = row['chains_per_launch']
+    sec = row['avg_launch_us'] * 1e-6
+    base = name.split('<')[0]
+    out = dict(kernel=name, avg_launch_us=row['avg_launch_us'], chains_per_launch=chains, peak_source=src,
+               share_of_device_time=row['share_of_device_time'], traffic=traffic.get(base))
+    if base == 'll_matrix_i8_kernel':
+        flops = 4.0 * N * M * K * chains
+        ach = flops / sec / 1e12
+        out.update(bound='tensor', achieved=ach, peak=bf16_sus, unit='TFLOP/s', frac=ach / bf16_sus,
+                   algorithmic_flops_per_launch=flops,
+                   note='4*N*M*K algorithmic flops per chain; the kernel executes two base-256 digits per '
+                        'log-probability on the int8 tensor pipe (nominal 2 x bf16); peak = sustained bf16')
+        return out
+    per_chain = {
+        'gibbs_sweep_kernel': 160.0 * n_unc + 4.0 * N,                 # records of the uncertain visits + assignments
+        'gibbs_exact_kernel': 160.0 * n_unc + 16.0 * K * M,            # records written + table read
+        'suffstat_kernel': N * M / 4.0 + 4.0 * N + 8.0 * K * M,        # planes + members + S1/S0
+        'mh_theta_kernel': 36.0 * K * M,                               # theta, S1, S0, three draws
+        'gibbs_options_kernel': 4.0 * N * ((K + 7) // 8 * 8) + 16.0 * N,
+        'rg_serial_kernel': 8.0 * N / max(K, 1),
+        'll_few_kernel': (N / max(K, 1)) * (M / 4.0 + 16.0),
+    }.get(base)
+    if per_chain is None:
+        per_chain = 4.0 * N
+    byts = per_chain * chains
+    ach = byts / sec / 1e9
+    out.update(bound='hbm', achieved=ach, peak=hbm, unit='GB/s', frac=ach / hbm, algorithmic_bytes_per_launch=byts)
+    if base in ('gibbs_sweep_kernel', 'rg_serial_kernel'):
+        out['note'] = ('sequential chain of dependent categorical draws, one CTA per chain: latency-bound by '
+                       'construction; the HBM fraction is reported for information')
+    return out
 
 
 def run_gpu(args, cfg):
     import torch
     import torch.distributed as dist
-    from bnpc_b200 import _lib
-    from bnpc_b200.rng import PhiloxRandom
-    import libs.CRP as crp
-    import libs.CRP_learning_errors as crple
-    from libs.MCMC import Chain_steps
-
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -221,206 +426,129 @@ def run_gpu(args, cfg):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    sys.setswitchinterval(2e-4)
-    n_gpus = world
-    cpg = args.chains_per_gpu
-    K, W = args.steps, max(args.warmup, 3)
-    N, M = cfg['cells'], cfg['muts']
+    cpg, K, W, R = args.chains_per_gpu, args.steps, max(args.warmup, 3), max(1, args.windows)
+    bench = Bench(cfg, dev, rank, world, cpg)
+    N, M = bench.N, bench.M
 
-    data, z = make_matrix(N, M, cfg['k_true'], cfg['fn'], cfg['fp'], cfg['miss'], seed=0)
-    z_list = [int(v) for v in z]
-    cls = crple.CRP_errors_learning if cfg['learning'] else crp.CRP
-    proto = cls(data, **model_kwargs(cfg))
-    moves = dict(moves_of(cfg), param_proposal_sd=np.array([0.1, 0.25, 0.5]))
+    bench.window(cpg, 2, 3, True)                      # library, allocator and clocks warm
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, launches, ex_dev = bench.repeat(cpg, W, K, R, host_assign=False)
+    ms_e2e, _, ex_e2e = bench.repeat(cpg, W, K, R, host_assign=True)
+    clocks = sampler.stop() if sampler else None
+    total_chains = cpg * world
+    med_dev, med_e2e = float(np.median(ms_dev)), float(np.median(ms_e2e))
+    value, e2e = _rate(total_chains, K, med_dev), _rate(total_chains, K, med_e2e)
 
-    from copy import deepcopy
-    chains = []
-
-    def make_chain(c):
-        m = deepcopy(proto)
-        m.device = dev
-        m.rnd = PhiloxRandom(4242 + rank * cpg + c)       # keyed by the global chain id
-        m.init(assign=z_list)
-        chains.append(Chain_steps(m, rank * cpg + c + 1, W + K + 2, 0, moves, 0, False))
-
-    def build_chains():
-        """(re)start all chains of this rank from the true assignment with their own seeds: the
-        two legs then walk the SAME trajectory (the cost of a step depends on the chain state,
-        which drifts while the chain runs)"""
-        chains.clear()
-        make_chain(0)                                      # packs the matrix once per device
-        ths = [threading.Thread(target=make_chain, args=(c,)) for c in range(1, cpg)]
-        [t.start() for t in ths]
-        [t.join() for t in ths]
-        chains.sort(key=lambda ch: ch.no)
-        torch.cuda.synchronize()
-
-    build_chains()
-    dev_trace = [torch.zeros((4, N), dtype=torch.int32, device=dev) for _ in range(cpg)]
-
-    def step_device(ch, i, tr):
-        """do_step + the per-step trace with the assignment row kept on the device."""
-        ch.do_step()
-        ll = ch.model.get_ll_full()
-        ch.results['ML'][i] = ll
-        ch.results['MAP'][i] = ll + ch.model.get_lprior_full()
-        ch.model.copy_assignment_to(tr[i % 4])
-
-    def step_e2e(ch, i, tr):
-        """the public driver path: Chain.do_step + Chain.update_results (host traces)."""
-        ch.do_step()
-        ch.update_results(i, False)
-
-    def leg(step_fn, n_warm, n_timed, profile):
-        bar = threading.Barrier(len(chains) + 1)
-        errs = []
-
-        def worker(ch, tr):
-            try:
-                torch.cuda.set_device(dev)                 # the current device is per host thread
-                for i in range(n_warm):
-                    step_fn(ch, 1 + i, tr)
-                ch.model.stream.synchronize()
-                ch.model.profile = profile
-                ch.model.kernel_times_ms()
-                ch.model.h2d_bytes = ch.model.d2h_bytes = 0
-                bar.wait()
-                bar.wait()
-                for i in range(n_timed):
-                    step_fn(ch, 1 + n_warm + i, tr)
-                ch.model.stream.synchronize()
-            except BaseException as e:                     # noqa: BLE001
-                errs.append(e)
-                bar.abort()
-
-        ths = [threading.Thread(target=worker, args=(ch, tr)) for ch, tr in zip(chains, dev_trace)]
-        [t.start() for t in ths]
-        bar.wait()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler = ClockSampler(local) if rank == 0 else None
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = _lib.launch_count()
-        start.record()
-        bar.wait()
-        [t.join() for t in ths]
-        torch.cuda.synchronize()
-        end.record()
-        end.synchronize()
-        if errs:
-            raise errs[0]
-        ms = torch.tensor([start.elapsed_time(end)], device=dev, dtype=torch.float64)
-        launches = torch.tensor([_lib.launch_count() - launches0], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.barrier()
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            dist.all_reduce(launches, op=dist.ReduceOp.SUM)
-        clocks = sampler.stop() if sampler else None
-        return float(ms.item()), int(launches.item()), clocks
-
-    # ---- leg 1: device-resident traces (value) ------------------------------------------
-    ms_dev, launches, clocks = leg(step_device, W, K, True)
-    ktimes, kwork = {}, {}
-    for ch in chains:
-        for name, v in ch.model.kernel_times_ms().items():
-            ktimes.setdefault(name, []).extend(v)
-        for name, v in ch.model.kernel_work().items():
-            kwork.setdefault(name, []).extend(v)
-        ch.model.profile = False
-    sweep_stats = chains[0].model.sweep_stats
-    k_live = len(chains[0].model.cells_per_cluster)
-    # ---- leg 2: public driver API with host traces (e2e) --------------------------------
-    build_chains()                                         # same seeds: the same K + W steps again
-    ms_e2e, _, _ = leg(step_e2e, W, K, False)
-    h2d = sum(ch.model.h2d_bytes for ch in chains) / (len(chains) * K)
-    d2h = sum(ch.model.d2h_bytes for ch in chains) / (len(chains) * K)
-    # the host-side int64 trace row is read back as int32 [N] + the theta snapshot + scalars
-    total_chains = cpg * n_gpus
-
+    # per-kernel device times: CUDA events around EVERY launch, a separate untimed pass
+    _, _, ex_prof = bench.window(cpg, W, K, False, profile=True)
+    extras = {}
+    if not args.no_extras:
+        s_ms, s_l, _ = bench.repeat(1, W, K, min(R, 3), host_assign=True)
+        extras['single_chain'] = dict(value=_rate(world, K, float(np.median(s_ms))), unit='chain-steps/s',
+                                      steps_per_sec_per_chain=_rate(1, K, float(np.median(s_ms))),
+                                      ms_per_step=float(np.median(s_ms)) / K, launches_per_step=float(np.median(s_l)) / K / world,
+                                      windows_ms=_spread(s_ms), api='e2e (host traces), 1 chain on 1 GPU')
+        ev_ms, _, ev_ex = bench.window(cpg, 250 + W, K, True)
+        extras['evolved_state'] = dict(value=_rate(total_chains, K, ev_ms), unit='chain-steps/s', warmup_steps=250 + W,
+                                       ms_per_step=ev_ms / K, live_clusters=ev_ex['k_all'], sweep=ev_ex['sweep'],
+                                       api='e2e (host traces)')
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return None
 
-    value = total_chains * K / (ms_dev / 1e3)
-    e2e = total_chains * K / (ms_e2e / 1e3)
-    hbm_peak, bf16_peak, peak_src = measured_peaks()
+    peaks = measured_peaks()
     traffic = ncu_traffic()
-    tot = {k: float(np.sum(v)) for k, v in ktimes.items()}
-    n_unc = float(sweep_stats.get('uncertain', N))
-    # algorithmic work per launch (DESIGN.md section 4):
-    #   likelihood rows  4*N*M*K flop (2 planes x multiply-add), N*M/4 + 16*K*M + 4*N*K bytes
-    #   sweep            the records of the uncertain visits (160 B each) + 4 B per visit of output
-    # per launch, from the live clusters / visits / uncertain visits of THAT launch (the list of
-    # clusters grows while the chain runs), averaged over the launches of the timed region
-    def mean_work(name, fn, fallback):
-        w = kwork.get(name) or []
-        return float(np.mean([fn(x) for x in w])) if w and len(w) == len(ktimes.get(name, [])) else fallback
-
-    alg = {
-        'll_matrix': dict(
-            flops=mean_work('ll_matrix', lambda x: 4.0 * x['rows'] * M * x['K'], 4.0 * N * M * k_live),
-            bytes=mean_work('ll_matrix', lambda x: x['rows'] * M / 4 + 16.0 * x['K'] * M + 4.0 * x['rows'] * x['K'],
-                            N * M / 4 + 16.0 * k_live * M + 4.0 * N * k_live)),
-        'gibbs_sweep': dict(
-            flops=0.0,
-            bytes=mean_work('gibbs_sweep', lambda x: 160.0 * x.get('n_unc', x['rows']) + 4.0 * x['rows'],
-                            160.0 * n_unc + 4.0 * N)),
-    }
-
-    def roof_of(name):
-        if name not in ktimes:
-            return None
-        avg_ms = float(np.mean(ktimes[name]))
-        if name == 'll_matrix':
-            ach = alg[name]['flops'] / (avg_ms * 1e-3) / 1e12
-            return dict(kernel='ll_matrix_i8_kernel (tcgen05 kind::i8 likelihood rows) + its digit-table kernel',
-                        bound='tensor', achieved=ach,
-                        peak=bf16_peak, unit='TFLOP/s', frac=ach / bf16_peak,
-                        traffic=traffic.get('ll_matrix_i8_kernel'), peak_source=peak_src, avg_launch_ms=avg_ms,
-                        algorithmic_flops_per_launch=alg[name]['flops'],
-                        algorithmic_bytes_per_launch=alg[name]['bytes'],
-                        hbm_frac=alg[name]['bytes'] / (avg_ms * 1e-3) / 1e9 / hbm_peak,
-                        note='algorithmic flops 4*N*M*K; the kernel executes two base-256 digits per '
-                             'log-probability on the int8 tensor pipe (nominal peak 2 x bf16) and pads K to a '
-                             'multiple of 8: algorithmic flops / measured bf16 peak = executed int8 ops / '
-                             '(2 x measured bf16 peak)')
-        ach = alg[name]['bytes'] / (avg_ms * 1e-3) / 1e9
-        return dict(kernel='gibbs_sweep_kernel', bound='hbm', achieved=ach, peak=hbm_peak, unit='GB/s',
-                    frac=ach / hbm_peak, traffic=traffic.get('gibbs_sweep_kernel'), peak_source=peak_src,
-                    avg_launch_ms=avg_ms, algorithmic_bytes_per_launch=alg[name]['bytes'],
-                    note='the sweep is a sequential chain of dependent categorical draws, one CTA per '
-                         'chain: latency-bound by construction; the HBM fraction is reported for information')
-
-    roof = roof_of(max(tot, key=tot.get)) if tot else None
-    roof_ll = roof_of('ll_matrix')
-    kernels = {k: dict(launches=len(v), avg_ms=float(np.mean(v)),
-                       share_of_step=float(np.sum(v)) / (len(chains) * ms_dev))
-               for k, v in ktimes.items()}
+    k_live = ex_prof['k_live']
+    n_unc = float(ex_prof['sweep'].get('uncertain', N) or N)
+    ktab, dev_ms_per_step = kernel_table(ex_prof['prof'], K, cpg, med_dev / K)
+    work = dict(N=N, M=M, K=k_live, n_unc=n_unc)
+    top = next(iter(ktab))
+    roof = roofline_of(top, ktab[top], work, peaks, traffic)
+    ll_name = next((n for n in ktab if n.startswith('ll_matrix_i8_kernel')), None)
+    roof_ll = roofline_of(ll_name, ktab[ll_name], work, peaks, traffic) if ll_name else None
+    d2h = bench.trace_bytes_per_step(ex_e2e['k_live'])
     out = dict(
-        metric=METRIC, value=value, unit='chain-steps/s', n_gpus=n_gpus, steps=K, warmup=W,
-        ms_per_step=ms_dev / K, higher_is_better=True, scaling='weak', vs_baseline=None,
+        metric=METRIC, value=value, unit='chain-steps/s', n_gpus=world, steps=K, warmup=W,
+        ms_per_step=med_dev / K, higher_is_better=True, scaling='weak', vs_baseline=None,
         dtype='f64', data='synthetic',
-        config=dict(workload=f'{args.config}: synthetic {N} cells x {M} mutations, K_true={cfg["k_true"]}, '
-                             f'{int(cfg["miss"] * 100)}% missing, '
-                             f'{"learned" if cfg["learning"] else "fixed"} error rates, start = true assignment',
-                    chains_per_gpu=cpg, chains_total=total_chains, moves=moves_of(cfg),
-                    live_clusters=k_live,
-                    l2='no explicit flush: every step streams its own visit records, approximate rows, '
-                       'option records and draws (about 130 B per cell per chain) besides the bit-planes: '
+        config=dict(workload=describe(args.config, cfg), chains_per_gpu=cpg, chains_total=total_chains,
+                    moves=moves_of(cfg), live_clusters=ex_dev['k_all'],
+                    windows=f'{R} timed windows of {W} warm-up + {K} timed steps, fresh chains with the same seeds '
+                            'per window; median reported',
+                    l2='no explicit flush: per step every chain streams its own visit records, approximate rows, '
+                       'option records and draws (about 130 B per cell per chain) besides the shared bit-planes: '
                        f'{cpg * 130 * N / 1e6 + N * M / 4e6:.0f} MB for the {cpg} concurrent chains vs 126 MB of L2'),
-        steps_per_sec_per_chain=K / (ms_dev / 1e3),
-        e2e=dict(value=e2e, unit='chain-steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                 steps_per_sec_per_chain=K / (ms_e2e / 1e3), ms_per_step=ms_e2e / K,
-                 api='libs.MCMC.Chain_steps.do_step + update_results (host traces)'),
-        gpu_launches=launches, roofline=roof, roofline_likelihood=roof_ll, kernels=kernels,
-        sweep=sweep_stats, clocks=clocks)
-    if not args.no_cpu_baseline and n_gpus == 1:
-        out['cpu_baseline'] = run_cpu(cfg, 1, 2, 1, 25.0, args.cpu_sample_cells)
+        steps_per_sec_per_chain=K / (med_dev / 1e3),
+        windows_ms=_spread(ms_dev),
+        e2e=dict(value=e2e, unit='chain-steps/s', h2d_bytes_per_step=4.0 * 4 * k_live + 64, d2h_bytes_per_step=d2h,
+                 steps_per_sec_per_chain=K / (med_e2e / 1e3), ms_per_step=med_e2e / K, windows_ms=_spread(ms_e2e),
+                 api='libs.MCMC.Chain_steps chains stepped by libs.MCMC.run_chains / bnpc_b200.group.ChainGroup (what '
+                     'MCMC.run does): full host traces, copied from the device rings by a copy stream'),
+        gpu_launches=int(np.median(launches)), launches_per_chain_step=float(np.median(launches)) / (K * total_chains),
+        roofline=roof, roofline_likelihood=roof_ll, kernels=ktab,
+        device_time=dict(sum_of_kernel_ms_per_step=dev_ms_per_step, wall_ms_per_step=med_dev / K,
+                         note='sum of the per-launch device times (profiling pass: launches serialised by their '
+                              'events) against the wall time of a step of the timed windows; the two streams overlap '
+                              'Gibbs and split-merge kernels, so sum > wall is possible'),
+        sweep=ex_prof['sweep'], clocks=clocks, **extras)
+    if not args.no_extras and world == 1:
+        out['other_configs'] = other_configs(args, dev)
+    if not args.no_cpu_baseline and world == 1:
+        out['cpu_baseline'] = cpu_baseline_sample(cfg, args.cpu_sample_cells)
     if world > 1:
         dist.destroy_process_group()
     return out
+
+
+def other_configs(args, dev):
+    """one short e2e window of the other BASELINE shapes (also C2, C4, C5)"""
+    import torch
+    out = {}
+    for name, n_chains in (('C2', 1), ('C4', 1), ('C5', 1)):
+        if name == args.config:
+            continue
+        try:
+            cfg = workload(args, name)
+            b = Bench(cfg, dev, 0, 1, n_chains)
+            steps = 20 if name != 'C5' else 6
+            ms, launches, ex = b.window(n_chains, 3, steps, True)
+            out[name] = dict(workload=describe(name, cfg), chains=n_chains, steps=steps, warmup=3,
+                             value=_rate(n_chains, steps, ms), unit='chain-steps/s', ms_per_step=ms / steps,
+                             live_clusters=ex['k_all'], sweep=ex['sweep'], api='e2e (host traces)')
+            del b
+            torch.cuda.empty_cache()
+        except Exception as exc:                              # noqa: BLE001  (reported, not hidden)
+            out[name] = dict(error=repr(exc))
+    return out
+
+
+def run_reference(args, cfg):
+    chains = args.chains_per_gpu * max(1, args.gpus)
+    warm = min(args.warmup, 1)
+    cells = args.cpu_sample_cells or cfg['cells']
+    r = run_cpu(cfg, chains, args.steps, warm, args.ref_budget_s, cells)
+    scale = cells / cfg['cells']
+    value = r['box_rate'] * scale
+    sample = (f'{cells} of {cfg["cells"]} cells x {cfg["muts"]} mutations (FULL workload), ' if scale == 1.0 else
+              f'{cells} of {cfg["cells"]} cells (rate scaled by {scale:g}), ')
+    sample += (f'{r["steps_done"]} timed steps of the {args.steps} requested (a step of this sample takes '
+               f'{r["step_seconds_mean"]:.1f} s per chain; stepping is bounded to {args.ref_budget_s:.0f} s) after '
+               f'{warm} warm-up, {r["chains"]} chains = {r["cores"]} processes on {os.cpu_count()} host cores')
+    return dict(impl='reference', metric=METRIC, value=value, unit='chain-steps/s', n_gpus=args.gpus,
+                steps=r['steps_done'], steps_requested=args.steps, warmup=warm,
+                ms_per_step=1e3 * r['seconds'] / max(1, r['steps_done']),
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
+                config=dict(workload=describe(args.config, cfg), chains_total=r['chains'], moves=moves_of(cfg),
+                            chains_requested=chains),
+                steps_per_sec_per_chain=r['per_chain_rate'] * scale,
+                cpu_baseline=dict(value=value, unit='chain-steps/s', cores=r['cores'], kind=r['kind'], sample=sample,
+                                  seconds=r['seconds'],
+                                  implementation='unmodified reference classes (baseline/_ref): Chain_steps.do_step + '
+                                                 'update_results, numpy stand-in for bottleneck'
+                                  if r['kind'] == 'reference' else 'oracle/crp_oracle.py (CPU restatement)'),
+                e2e=dict(value=value, unit='chain-steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
 
 
 def _emit(line, fd):
@@ -439,19 +567,7 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        chains = args.chains_per_gpu * max(1, args.gpus)
-        res = run_cpu(cfg, chains, args.steps, min(args.warmup, 1), 100.0, args.cpu_sample_cells)
-        out = dict(impl='reference', metric=METRIC, value=res['value'], unit='chain-steps/s',
-                   n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                   ms_per_step=1e3 * res['cores'] / res['value'] if res['value'] else None,
-                   higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
-                   config=dict(workload=f'{args.config}: synthetic {cfg["cells"]} cells x {cfg["muts"]} mutations '
-                                        '(CPU restatement of the reference, bounded cell sample)',
-                               chains_total=res['cores'], moves=moves_of(cfg)),
-                   steps_per_sec_per_chain=res['per_chain'], cpu_baseline=res,
-                   e2e=dict(value=res['value'], unit='chain-steps/s', h2d_bytes_per_step=0,
-                            d2h_bytes_per_step=0), gpu_launches=0)
-        _emit(json.dumps(out), out_fd)
+        _emit(json.dumps(run_reference(args, cfg)), out_fd)
         return
     out = run_gpu(args, cfg)
     sys.stdout.flush()

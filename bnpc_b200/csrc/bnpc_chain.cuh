@@ -74,12 +74,16 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
     const int N = w->N, M = w->M, K = e->K, t = e->t, rows = e->rows, ldk = e->ldk;
     if (K <= 0 || K > w->idcap || rows <= 0 || t < 0 || t + rows > N) return bad_arg("epoch range");
     if (e->first) {
-        if (!e->rand_ready) {
-            TRY(bnpc_fill_permutation(w->perm, N, e->seed, e->stream_id + 1, stream));
-            TRY(bnpc_fill_uniform(w->u, N, e->seed, e->stream_id + 2, 0, stream));
-        }
-        TRY(bnpc_gibbs_prepare(w->perm, w->u, w->assign, w->n1, w->n0, N, e->c1, e->c0, e->lnew_prior,
-                               w->visit, stream));
+        // production: the records are built from the chain's streams (stream_id+1 visiting order,
+        // +2 uniforms); parity mode: from the taped perm / u
+        TRY(gibbs_prepare_impl(e->rand_ready ? w->perm : nullptr, e->rand_ready ? w->u : nullptr, w->assign, w->n1,
+                               w->n0, N, e->c1, e->c0, e->lnew_prior, w->visit, e->seed, e->stream_id, stream));
+    }
+    const bool lean_epoch = e->lean > 0;
+    if (lean_epoch) {
+        // scratch of the option / exact passes, cleared in one launch
+        TRY(zero_async(w->n_cert, sizeof(int32_t) * BNPC_LEAN_MAXK, stream, "epoch memset"));
+        TRY(zero_async(w->comp, sizeof(int32_t) * 512, stream, "epoch memset"));
     }
     // live list (id, size) pairs in list order: host staging -> device
     TRY(copy_async(w->live_io, w->h_in, sizeof(int32_t) * 2 * (size_t)K, cudaMemcpyHostToDevice, stream));
@@ -115,10 +119,11 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
             TRY(bnpc_ll_matrix_f32(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp, w->lpf, K, w->llf, ldf,
                                    stream));
         TRY(record_event(e->ev_ll1, stream));
-        TRY(bnpc_gibbs_options(w->llf, ldf, K, w->col_of_id, w->visit + t, w->opt + t, w->n_cert, rows, e->log_n,
-                               e->c_norm, 2 * M, err_abs, stream));
-        TRY(bnpc_gibbs_exact(w->x1, w->x0, w->W, M, w->lp, K, w->visit + t, w->opt + t, w->n_cert, rows, w->cblk,
-                             w->idx_c, w->st, w->visit_c, w->cand_c, e->log_n, e->c_norm, w->comp, w->rg_perm, stream));
+        TRY(gibbs_options_impl(w->llf, ldf, K, w->col_of_id, w->visit + t, w->opt + t, w->n_cert, rows, e->log_n,
+                               e->c_norm, 2 * M, err_abs, false, stream));
+        TRY(gibbs_exact_impl(w->x1, w->x0, w->W, M, w->lp, K, w->visit + t, w->opt + t, w->n_cert, rows, w->cblk,
+                             w->idx_c, w->st, w->visit_c, w->cand_c, e->log_n, e->c_norm, w->comp, w->rg_perm, false,
+                             stream));
     } else {
         TRY(record_event(e->ev_ll0, stream));
         TRY(bnpc_ll_matrix(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp, K, w->ll, ldk, stream));
@@ -161,26 +166,25 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
 
 int bnpc_chain_stats(const bnpc_chain_t* w, int K, int max_len, void* stream) {
     if (!w || K <= 0) return bad_arg("workspace/K");
+    // cursors and statistics cleared in one launch
+    TRY(zero_async(w->cursor, sizeof(int32_t) * (size_t)K, stream, "stats memset"));
+    TRY(zero_async(w->S1, sizeof(int32_t) * (size_t)K * w->M, stream, "stats memset"));
+    TRY(zero_async(w->S0, sizeof(int32_t) * (size_t)K * w->M, stream, "stats memset"));
     // h_in = ids[K] then seg[K+1]
     TRY(copy_async(w->ids, w->h_in, sizeof(int32_t) * (size_t)K, cudaMemcpyHostToDevice, stream));
     TRY(copy_async(w->seg, w->h_in + K, sizeof(int32_t) * ((size_t)K + 1), cudaMemcpyHostToDevice, stream));
     TRY(bnpc_set_ranks(w->ids, K, w->rank_of_id, stream));
-    TRY(bnpc_group_members(w->assign, w->N, w->rank_of_id, w->seg, w->cursor, K, w->members, stream));
-    TRY(bnpc_suffstat(w->x1, w->x0, w->W, w->M, w->members, w->seg, K, max_len, w->S1, w->S0, stream));
+    TRY(group_members_impl(w->assign, w->N, w->rank_of_id, w->seg, w->cursor, K, w->members, false, stream));
+    TRY(suffstat_impl(w->x1, w->x0, w->W, w->M, w->members, w->seg, K, max_len, w->S1, w->S0, false, stream));
     return 0;
 }
 
 int bnpc_chain_mh_theta(const bnpc_chain_t* w, int K, int rand_ready, uint64_t seed, uint64_t stream_id,
                         double FN, double FP, double p, double q, void* stream) {
     if (!w || K <= 0) return bad_arg("workspace/K");
-    const long long RM = (long long)K * w->M;
-    if (!rand_ready) {
-        TRY(bnpc_fill_uniform(w->rnd, RM, seed, stream_id + 1, 3, stream));
-        TRY(bnpc_fill_uniform(w->rnd + RM, 2 * RM, seed, stream_id + 2, 0, stream));
-    }
     TRY(zero_async(w->declined, sizeof(int32_t) * ((size_t)K + 1), stream, "mh_theta memset"));
-    TRY(bnpc_mh_theta(w->theta, w->ids, K, w->M, w->S1, w->S0, w->rnd, FN, FP, p, q, 0, nullptr, w->declined,
-                      stream));
+    TRY(mh_theta_impl(w->theta, w->ids, K, w->M, w->S1, w->S0, rand_ready ? w->rnd : nullptr, seed, stream_id, FN, FP,
+                      p, q, 0, nullptr, w->declined, stream));
     BNPC_LAUNCH(sum_int_kernel, 0, 0, 1, 256, 0, (cudaStream_t)stream, w->declined, K, w->declined + K);
     TRY(copy_async(w->h_out, w->declined + K, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     return 0;
@@ -200,8 +204,11 @@ int bnpc_chain_loglik(const bnpc_chain_t* w, int K, const double* fn_h, const do
 
 // ---- split-merge (libs/CRP.py:527-567): launch state of the restricted Gibbs sampler ----------
 static int rg_side_stats(const bnpc_chain_t* w, int n, void* stream) {
-    TRY(bnpc_rg_sides(w->cells, n, w->half, w->members, w->seg3, stream));
-    TRY(bnpc_suffstat(w->x1, w->x0, w->W, w->M, w->members, w->seg3, 2, n, w->rg_S1, w->rg_S0, stream));
+    TRY(zero_async(w->seg3, sizeof(int32_t) * 8, stream, "rg stats memset"));
+    TRY(zero_async(w->rg_S1, sizeof(int32_t) * 2 * (size_t)w->M, stream, "rg stats memset"));
+    TRY(zero_async(w->rg_S0, sizeof(int32_t) * 2 * (size_t)w->M, stream, "rg stats memset"));
+    TRY(rg_sides_impl(w->cells, n, w->half, w->members, w->seg3, false, stream));
+    TRY(suffstat_impl(w->x1, w->x0, w->W, w->M, w->members, w->seg3, 2, n, w->rg_S1, w->rg_S0, false, stream));
     return 0;
 }
 
@@ -209,15 +216,12 @@ static int rg_mh(const bnpc_chain_t* w, const bnpc_rg_t* g, int row0, int rows, 
                  void* stream) {
     const int M = w->M;
     const long long RM = (long long)rows * M;
-    if (!g->rand_ready) {
-        TRY(bnpc_fill_uniform(w->rg_rnd, RM, g->seed, g->stream_id + *streams_used + 1, 3, stream));
-        TRY(bnpc_fill_uniform(w->rg_rnd + RM, 2 * RM, g->seed, g->stream_id + *streams_used + 2, 0, stream));
-        *streams_used += 2;
-    }
+    const uint64_t sid = g->stream_id + *streams_used;      // draws of streams sid+1, sid+2
+    if (!g->rand_ready) *streams_used += 2;
     const bool want = slot >= 0;
-    TRY(bnpc_mh_theta(w->rg_theta + (size_t)row0 * M, nullptr, rows, M, w->rg_S1 + (size_t)row0 * M,
-                      w->rg_S0 + (size_t)row0 * M, w->rg_rnd, g->FN, g->FP, g->p, g->q, want ? 1 : 0,
-                      want ? w->rg_logq : nullptr, w->rg_dec, stream));
+    TRY(mh_theta_impl(w->rg_theta + (size_t)row0 * M, nullptr, rows, M, w->rg_S1 + (size_t)row0 * M,
+                      w->rg_S0 + (size_t)row0 * M, g->rand_ready ? w->rg_rnd : nullptr, g->seed, sid, g->FN, g->FP,
+                      g->p, g->q, want ? 1 : 0, want ? w->rg_logq : nullptr, w->rg_dec, stream));
     if (want) TRY(bnpc_row_sum(w->rg_logq, 1, (int)RM, w->rg_scal + slot, stream));
     return 0;
 }
@@ -248,14 +252,16 @@ int bnpc_chain_rg_scan_split(const bnpc_chain_t* w, const bnpc_rg_t* g, int want
     const int n = g->n, nf = n - 2, M = w->M;
     int used = 0;
     if (n > 2) {
-        TRY(bnpc_logprob_tables(w->rg_theta, nullptr, 2, M, g->FN, g->FP, w->rg_lp, stream));
-        TRY(bnpc_ll_matrix(w->x1, w->x0, w->W, M, w->cells + 1, 1, nf, w->rg_lp, 2, w->rg_ll2, 2, stream));
-        if (!g->rand_ready) {
-            TRY(bnpc_fill_permutation(w->rg_perm, nf, g->seed, g->stream_id + 1, stream));
-            TRY(bnpc_fill_uniform(w->rg_u, nf, g->seed, g->stream_id + 2, 0, stream));
-            used = 2;
+        if (ll_few_fits(2, w->W)) {
+            TRY(ll_few_from_theta(w->x1, w->x0, w->W, M, w->cells + 1, 1, nf, w->rg_theta, 2, g->FN, g->FP, w->rg_ll2,
+                                  2, stream));
+        } else {
+            TRY(bnpc_logprob_tables(w->rg_theta, nullptr, 2, M, g->FN, g->FP, w->rg_lp, stream));
+            TRY(bnpc_ll_matrix(w->x1, w->x0, w->W, M, w->cells + 1, 1, nf, w->rg_lp, 2, w->rg_ll2, 2, stream));
         }
-        TRY(bnpc_rg_scan(w->rg_ll2, 2, n, w->rg_perm, w->rg_u, w->half, g->alpha, 0, nullptr, nullptr, -1,
+        if (!g->rand_ready) used = 2;                    // streams stream_id+1 (order), +2 (uniforms)
+        TRY(rg_scan_impl(w->rg_ll2, 2, n, g->rand_ready ? w->rg_perm : nullptr, g->rand_ready ? w->rg_u : nullptr,
+                         g->seed, g->stream_id, w->half, g->alpha, 0, nullptr, nullptr, -1,
                          want_logq ? w->rg_lq : nullptr, w->rg_work, stream));
         if (want_logq) TRY(bnpc_row_sum(w->rg_lq, 1, nf, w->rg_scal + 0, stream));
     }
@@ -278,9 +284,9 @@ int bnpc_chain_rg_decide_split(const bnpc_chain_t* w, const bnpc_rg_t* g, int fl
     if (!w || !g) return bad_arg("workspace/move");
     const int M = w->M;
     const float* th_old = w->theta + (size_t)g->cl_i * M;
-    if (!g->rand_ready) TRY(bnpc_fill_uniform(w->rg_sd, M, g->seed, g->stream_id + 1, 3, stream));
-    TRY(bnpc_theta_log_ratio(th_old, w->rg_theta + 2 * (size_t)M, 1, M, w->rg_S1 + 2 * M, w->rg_S0 + 2 * M,
-                             w->rg_sd, (float)kThetaLo, (float)kThetaHi, g->FN, g->FP, g->p, g->q, w->rg_A, stream));
+    TRY(theta_log_ratio_impl(th_old, w->rg_theta + 2 * (size_t)M, 1, M, w->rg_S1 + 2 * M, w->rg_S0 + 2 * M,
+                             g->rand_ready ? w->rg_sd : nullptr, g->seed, g->stream_id + 1, (float)kThetaLo,
+                             (float)kThetaHi, g->FN, g->FP, g->p, g->q, w->rg_A, stream));
     TRY(bnpc_row_sum(w->rg_A, 1, M, w->rg_scal + 2, stream));
     if (!flat_prior) {
         TRY(bnpc_row_loglik(w->rg_theta, nullptr, 2, M, w->rg_S1, w->rg_S0, nullptr, nullptr, 0, g->p, g->q,
@@ -301,15 +307,19 @@ int bnpc_chain_rg_decide_merge(const bnpc_chain_t* w, const bnpc_rg_t* g, int fl
     if (!w || !g) return bad_arg("workspace/move");
     const int M = w->M, n = g->n, nf = n - 2;
     BNPC_LAUNCH(copy_rows_kernel, 0, 0, cdiv(2 * M, 256), 256, 0, (cudaStream_t)stream,  w->theta + (size_t)g->cl_i * M, w->theta + (size_t)g->cl_j * M, w->rg_orig, M);
-    if (!g->rand_ready) TRY(bnpc_fill_uniform(w->rg_sd, 2 * M, g->seed, g->stream_id + 1, 3, stream));
     // probability of walking from the launch split back to the original split
-    TRY(bnpc_theta_log_ratio(w->rg_orig, w->rg_theta, 2, M, w->rg_S1, w->rg_S0, w->rg_sd, 0.0f, 1.0f, g->FN,
-                             g->FP, g->p, g->q, w->rg_A, stream));
+    TRY(theta_log_ratio_impl(w->rg_orig, w->rg_theta, 2, M, w->rg_S1, w->rg_S0, g->rand_ready ? w->rg_sd : nullptr,
+                             g->seed, g->stream_id + 1, 0.0f, 1.0f, g->FN, g->FP, g->p, g->q, w->rg_A, stream));
     TRY(bnpc_row_sum(w->rg_A, 1, 2 * M, w->rg_scal + 2, stream));
     if (n > 2) {
-        TRY(bnpc_logprob_tables(w->rg_orig, nullptr, 2, M, g->FN, g->FP, w->rg_lp, stream));
-        TRY(bnpc_ll_matrix(w->x1, w->x0, w->W, M, w->cells + 1, 1, nf, w->rg_lp, 2, w->rg_ll2, 2, stream));
-        TRY(bnpc_rg_scan(w->rg_ll2, 2, n, nullptr, nullptr, w->half, g->alpha, 1, w->cells, w->assign, g->cl_i,
+        if (ll_few_fits(2, w->W)) {
+            TRY(ll_few_from_theta(w->x1, w->x0, w->W, M, w->cells + 1, 1, nf, w->rg_orig, 2, g->FN, g->FP, w->rg_ll2, 2,
+                                  stream));
+        } else {
+            TRY(bnpc_logprob_tables(w->rg_orig, nullptr, 2, M, g->FN, g->FP, w->rg_lp, stream));
+            TRY(bnpc_ll_matrix(w->x1, w->x0, w->W, M, w->cells + 1, 1, nf, w->rg_lp, 2, w->rg_ll2, 2, stream));
+        }
+        TRY(rg_scan_impl(w->rg_ll2, 2, n, nullptr, nullptr, 0, 0, w->half, g->alpha, 1, w->cells, w->assign, g->cl_i,
                          w->rg_lq, w->rg_work, stream));
         TRY(bnpc_row_sum(w->rg_lq, 1, nf, w->rg_scal + 3, stream));
     }

@@ -46,18 +46,74 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 // =============================================================================
 // recordable stream operations (see bnpc_batch.cuh)
 // =============================================================================
-// zero-fill as a kernel body, so that the many small clears of a step merge across chains like
-// every other launch (cudaMemsetAsync nodes cannot be batched)
-__device__ __forceinline__ void zero_words_kernel(uint32_t* __restrict__ p, long long n_words, int vec) {
+// Zero-fills and small copies as kernel bodies, so that the many clears / staging copies of a step
+// merge across chains like every other launch (cudaMemsetAsync / cudaMemcpyAsync nodes cannot be
+// batched).  Up to SEG_MAX segments per launch (blockIdx.y = segment): consecutive recorded
+// clears (or copies) of one chain become ONE operation.
+#define SEG_MAX 4
+struct SegArgs {
+    void* dst[SEG_MAX];
+    const void* src[SEG_MAX];
+    long long n_words[SEG_MAX];
+    int vec[SEG_MAX];
+    int count;
+};
+__device__ __forceinline__ void seg_zero_kernel(SegArgs a) {
+    const int sg = blockIdx.y;
+    if (sg >= a.count) return;
+    uint32_t* p = reinterpret_cast<uint32_t*>(a.dst[sg]);
+    const long long n = a.n_words[sg];
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (!vec) {
-        if (i < n_words) p[i] = 0u;
+    if (!a.vec[sg]) {
+        if (i < n) p[i] = 0u;
         return;
     }
-    const long long n4 = n_words >> 2;
+    const long long n4 = n >> 2;
     if (i < n4) reinterpret_cast<uint4*>(p)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (i < (n_words & 3)) p[4 * n4 + i] = 0u;
+    if (i < (n & 3)) p[4 * n4 + i] = 0u;
 }
+// copies between device memory and PINNED host memory (reachable from the device under unified
+// addressing): the live list in, the status block out; device-to-device snapshots
+__device__ __forceinline__ void seg_copy_kernel(SegArgs a) {
+    const int sg = blockIdx.y;
+    if (sg >= a.count) return;
+    uint32_t* d = reinterpret_cast<uint32_t*>(a.dst[sg]);
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(a.src[sg]);
+    const long long n = a.n_words[sg];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (!a.vec[sg]) {
+        if (i < n) d[i] = s[i];
+        return;
+    }
+    const long long n4 = n >> 2;
+    if (i < n4) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(s)[i];
+    if (i < (n & 3)) d[4 * n4 + i] = s[4 * n4 + i];
+}
+
+template <auto Body>
+static int seg_launch(void* dst, const void* src, long long words, int vec, void* stream) {
+    using namespace bnpc;
+    const unsigned blocks = (unsigned)cdiv(vec ? (words + 3) / 4 : words, 256);
+    if (g_rec.on && !g_rec.q[g_rec.cur].empty()) {
+        Op& last = g_rec.q[g_rec.cur].back();
+        if (last.kind == 0 && last.merged == &launch_merged<Body, 0, 0>) {
+            SegArgs* a = reinterpret_cast<SegArgs*>(last.args);     // Pack<SegArgs>: head at offset 0
+            if (a->count < SEG_MAX) {
+                const int k = a->count++;
+                a->dst[k] = dst; a->src[k] = src; a->n_words[k] = words; a->vec[k] = vec;
+                last.gx = blocks > last.gx ? blocks : last.gx;
+                last.gy = (unsigned)a->count;
+                return 0;
+            }
+        }
+    }
+    SegArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dst[0] = dst; a.src[0] = src; a.n_words[0] = words; a.vec[0] = vec; a.count = 1;
+    BNPC_LAUNCH(Body, 0, 0, dim3(blocks, 1), 256, 0, stream, a);
+    return 0;
+}
+
 static int zero_async(void* ptr, size_t bytes, void* stream, const char* what) {
     if (bytes == 0) return 0;
     if ((bytes & 3) || ((uintptr_t)ptr & 3)) {
@@ -66,20 +122,9 @@ static int zero_async(void* ptr, size_t bytes, void* stream, const char* what) {
         if (e != cudaSuccess) return fail(what, e);
         return 0;
     }
-    const long long words = (long long)(bytes >> 2);
-    const int vec = ((uintptr_t)ptr & 15) ? 0 : 1;
-    BNPC_LAUNCH(zero_words_kernel, 0, 0, cdiv(vec ? (words + 3) / 4 : words, 256), 256, 0, stream,
-                reinterpret_cast<uint32_t*>(ptr), words, vec);
-    return 0;
+    return seg_launch<seg_zero_kernel>(ptr, nullptr, (long long)(bytes >> 2), ((uintptr_t)ptr & 15) ? 0 : 1, stream);
 }
 
-// small word copies between device memory and PINNED host memory (reachable from the device
-// under unified addressing) as a kernel body: the live list in, the status block out
-__device__ __forceinline__ void copy_words_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src,
-                                                  int n_words) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_words) dst[i] = src[i];
-}
 #define BNPC_SMALL_COPY_BYTES 8192
 static int g_uva_copies = -1;      // small host<->device copies as kernels over mapped pinned memory
 static int copy_async(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, void* stream) {
@@ -92,9 +137,8 @@ static int copy_async(void* dst, const void* src, size_t bytes, cudaMemcpyKind k
     // become kernel launches (they merge across chains); the rest stays a copy-engine operation
     if (bnpc::g_rec.on && !(bytes & 3) && !(((uintptr_t)dst | (uintptr_t)src) & 3) &&
         (kind == cudaMemcpyDeviceToDevice || (g_uva_copies && bytes <= BNPC_SMALL_COPY_BYTES))) {
-        BNPC_LAUNCH(copy_words_kernel, 0, 0, cdiv((long long)(bytes >> 2), 256), 256, 0, stream,
-                    reinterpret_cast<uint32_t*>(dst), reinterpret_cast<const uint32_t*>(src), (int)(bytes >> 2));
-        return 0;
+        const int vec = (((uintptr_t)dst | (uintptr_t)src) & 15) ? 0 : 1;
+        return seg_launch<seg_copy_kernel>(dst, src, (long long)(bytes >> 2), vec, stream);
     }
     if (bnpc::g_rec.on) {
         bnpc::g_rec.q[bnpc::g_rec.cur].emplace_back();
@@ -297,10 +341,16 @@ __device__ __forceinline__ uint32_t feistel_round(uint32_t r, uint32_t k) {
     h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13; h *= 0xC2B2AE3Du; h ^= h >> 16;
     return h;
 }
-__device__ __forceinline__ void fill_permutation_kernel(int32_t* __restrict__ out, int n, uint64_t seed,
-                                        uint64_t stream_id, int half_bits) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// Element i of the streams the fill kernels write, computed where it is consumed (production
+// mode: the consumers take a NULL buffer and the stream instead; one launch less per draw).
+__device__ __forceinline__ double uniform_at(uint64_t seed, uint64_t stream_id, long long i, int n_levels) {
+    Philox g(seed);
+    const uint4 r = g((uint64_t)(i >> 1), stream_id);
+    double v = (i & 1) ? u01(r.z, r.w) : u01(r.x, r.y);
+    if (n_levels > 0) v = floor(v * n_levels);
+    return v;
+}
+__device__ __forceinline__ int permutation_at(uint64_t seed, uint64_t stream_id, int i, int n, int half_bits) {
     Philox g(seed);
     const uint4 k0 = g(0xFE157E1ull, stream_id), k1 = g(0xFE157E2ull, stream_id);
     const uint32_t keys[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
@@ -315,7 +365,19 @@ __device__ __forceinline__ void fill_permutation_kernel(int32_t* __restrict__ ou
         }
         x = (l << half_bits) | r;
     } while (x >= (uint32_t)n);
-    out[i] = (int32_t)x;
+    return (int)x;
+}
+static inline int feistel_half_bits(int n) {
+    int bits = 2;
+    while ((1ll << bits) < n) ++bits;
+    if (bits & 1) ++bits;
+    return bits / 2;
+}
+__device__ __forceinline__ void fill_permutation_kernel(int32_t* __restrict__ out, int n, uint64_t seed,
+                                        uint64_t stream_id, int half_bits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = permutation_at(seed, stream_id, i, n, half_bits);
 }
 
 // =============================================================================
@@ -402,13 +464,21 @@ __device__ __forceinline__ void ll_matrix_kernel(const uint32_t* __restrict__ x1
 #define LLP_CELLS 32
 __device__ __forceinline__ void ll_few_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
               const int32_t* __restrict__ cells, int cell_stride, int C,
-              const double2* __restrict__ lp, int K, double* __restrict__ ll, int ldk) {
+              const double2* __restrict__ lp, int K, double* __restrict__ ll, int ldk,
+              const float* __restrict__ theta, double FN, double FP) {
     extern __shared__ __align__(16) unsigned char llp_smem[];
     double2* tab = reinterpret_cast<double2*>(llp_smem);          // [K][W * 32], zero beyond M
     const int Mp = W * 32;
+    // lp == NULL: the table is built here from the K rows of theta (what bnpc_logprob_tables
+    // would have written; one launch less per restricted Gibbs scan)
     for (int i = threadIdx.x; i < K * Mp; i += blockDim.x) {
         const int k = i / Mp, m = i % Mp;
-        tab[i] = (m < M) ? lp[(long long)k * M + m] : make_double2(0.0, 0.0);
+        double2 v = make_double2(0.0, 0.0);
+        if (m < M) {
+            if (lp) v = lp[(long long)k * M + m];
+            else log_p1_p0(theta[(long long)k * M + m], FN, FP, v.x, v.y);
+        }
+        tab[i] = v;
     }
     __syncthreads();
     const int sub = threadIdx.x & 7;
@@ -472,12 +542,15 @@ __device__ __forceinline__ double cell_row_ll(const uint32_t* __restrict__ r1,
 __device__ __forceinline__ void gibbs_prepare_kernel(const int32_t* __restrict__ perm, const double* __restrict__ u,
                                      const int32_t* __restrict__ assign, const int32_t* __restrict__ n1,
                                      const int32_t* __restrict__ n0, int N, double c1, double c0,
-                                     double lnew_prior, bnpc_visit_t* __restrict__ visit) {
+                                     double lnew_prior, bnpc_visit_t* __restrict__ visit, uint64_t seed,
+                                     uint64_t stream_id, int half_bits) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N) return;
-    const int c = perm[t];
+    // perm / u == NULL: the visiting order and the uniforms of streams stream_id+1, +2 (what
+    // bnpc_fill_permutation / bnpc_fill_uniform would have written)
+    const int c = perm ? perm[t] : permutation_at(seed, stream_id + 1, t, N, half_bits);
     bnpc_visit_t v;
-    v.u = u[t];
+    v.u = u ? u[t] : uniform_at(seed, stream_id + 2, t, 0);
     // popcount form of libs/CRP.py:230-234: every observed 1 contributes c1, every 0 c0
     v.lnew = ((double)n1[c] * c1 + (double)n0[c] * c0) + lnew_prior;
     v.e_new = 0.0;
@@ -1974,15 +2047,17 @@ __device__ __constant__ const double kStepSd[3] = {0.1, 0.25, 0.5};   // libs/CR
 __device__ __forceinline__ void mh_theta_kernel(float* theta, const int32_t* __restrict__ ids, int R, int M,
                                 const int32_t* __restrict__ S1, const int32_t* __restrict__ S0,
                                 const double* __restrict__ rnd, MhConst c, int flags,
-                                double* __restrict__ logq, int32_t* declined) {
+                                double* __restrict__ logq, int32_t* declined, uint64_t seed, uint64_t stream_id) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long RM = (long long)R * M;
     if (i >= RM) return;
     const int r = (int)(i / M), m = (int)(i % M);
     const long long row = ids ? ids[r] : r;
     const float old = theta[row * M + m];
-    const double sd = kStepSd[(int)rnd[i]];
-    const double ut = rnd[RM + i], ua = rnd[2 * RM + i];
+    // rnd == NULL: streams stream_id+1 (proposal-sd indices) and +2 (2 RM uniforms)
+    const double sd = kStepSd[rnd ? (int)rnd[i] : (int)uniform_at(seed, stream_id + 1, i, 3)];
+    const double ut = rnd ? rnd[RM + i] : uniform_at(seed, stream_id + 2, i, 0);
+    const double ua = rnd ? rnd[2 * RM + i] : uniform_at(seed, stream_id + 2, RM + i, 0);
     const float lo_f = (float)kThetaLo, hi_f = (float)kThetaHi;
     const double lo = (double)(lo_f - old) / sd, hi = (double)(hi_f - old) / sd;
     const double x = truncnorm_ppf_std(ut, lo, hi);
@@ -1998,11 +2073,12 @@ __device__ __forceinline__ void mh_theta_kernel(float* theta, const int32_t* __r
 __device__ __forceinline__ void theta_log_ratio_kernel(const float* __restrict__ th_new, const float* __restrict__ th_old,
                                        int R, int M, const int32_t* __restrict__ S1,
                                        const int32_t* __restrict__ S0, const double* __restrict__ sd_idx,
-                                       float blo, float bhi, MhConst c, double* __restrict__ A) {
+                                       float blo, float bhi, MhConst c, double* __restrict__ A, uint64_t seed,
+                                       uint64_t stream_id) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)R * M) return;
     const float old = th_old[i];
-    const double sd = kStepSd[(int)sd_idx[i]];
+    const double sd = kStepSd[sd_idx ? (int)sd_idx[i] : (int)uniform_at(seed, stream_id, i, 3)];
     const double lo = (double)(blo - old) / sd, hi = (double)(bhi - old) / sd;
     A[i] = theta_log_A(th_new[i], old, S1[i], S0[i], lo, hi, sd, c, true);
 }
@@ -2198,17 +2274,19 @@ __device__ __forceinline__ void rg_prepare_kernel(const double* __restrict__ ll2
                                   const int32_t* __restrict__ perm, const double* __restrict__ u,
                                   const int32_t* __restrict__ half, double alpha, int mode,
                                   const int32_t* __restrict__ cells, const int32_t* __restrict__ assign,
-                                  int id_i, int32_t* __restrict__ work) {
+                                  int id_i, int32_t* __restrict__ work, uint64_t seed, uint64_t stream_id,
+                                  int half_bits) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int nf = n - 2;
     if (s >= nf) return;
-    const int c = (mode == 0) ? perm[s] : s;
+    // mode 0 with perm / u == NULL: streams stream_id+1 (order) and +2 (uniforms)
+    const int c = (mode == 0) ? (perm ? perm[s] : permutation_at(seed, stream_id + 1, s, nf, half_bits)) : s;
     int tau;
     if (mode != 0) {
         tau = (assign[cells[c + 1]] == id_i) ? RG_FORCE_0 : RG_FORCE_1;
     } else {
         const double a0 = ll2[(long long)c * ldk], a1 = ll2[(long long)c * ldk + 1];
-        const double uu = u[s];
+        const double uu = u ? u[s] : uniform_at(seed, stream_id + 2, s, 0);
         const double cn = log((double)n - 1.0 + alpha);
         // side j iff n_j/(n-1) >= sigmoid(logit(1-u) - (a1-a0)); n_j = ex + 1
         const double x = (log1p(-uu) - log(uu)) - (a1 - a0);
@@ -2305,11 +2383,11 @@ __device__ __forceinline__ void rg_serial_kernel(const int32_t* __restrict__ hal
 __device__ __forceinline__ void rg_finish_kernel(const double* __restrict__ ll2, int ldk, int n,
                                  const int32_t* __restrict__ perm, int32_t* __restrict__ half,
                                  double alpha, int mode, const int32_t* __restrict__ work, int out_off,
-                                 double* __restrict__ lq) {
+                                 double* __restrict__ lq, uint64_t seed, uint64_t stream_id, int half_bits) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int nf = n - 2;
     if (s >= nf) return;
-    const int c = (mode == 0) ? perm[s] : s;
+    const int c = (mode == 0) ? (perm ? perm[s] : permutation_at(seed, stream_id + 1, s, nf, half_bits)) : s;
     const int o = work[out_off + s];
     const int side = o & 1, ex = o >> 1;
     half[c] = side;
@@ -2363,10 +2441,7 @@ int bnpc_fill_uniform(double* out, int64_t n, uint64_t seed, uint64_t stream_id,
 
 int bnpc_fill_permutation(int32_t* out, int n, uint64_t seed, uint64_t stream_id, void* stream) {
     if (n <= 0) return 0;
-    int bits = 2;
-    while ((1ll << bits) < n) ++bits;
-    if (bits & 1) ++bits;
-    BNPC_LAUNCH(fill_permutation_kernel, 0, 0, cdiv(n, 256), 256, 0, (cudaStream_t)stream, out, n, seed, stream_id, bits / 2);
+    BNPC_LAUNCH(fill_permutation_kernel, 0, 0, cdiv(n, 256), 256, 0, (cudaStream_t)stream, out, n, seed, stream_id, feistel_half_bits(n));
     return 0;
 }
 
@@ -2377,14 +2452,27 @@ int bnpc_logprob_tables(const float* theta, const int32_t* ids, int R, int M, do
     return 0;
 }
 
+static bool ll_few_fits(int K, int W) { return K <= 2 && sizeof(double2) * (size_t)K * W * 32 <= 200 * 1024; }
+
+// the K <= 2 rows of a restricted Gibbs scan straight from theta (libs/CRP.py:635-638): the
+// log-probability table is built inside the kernel
+static int ll_few_from_theta(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
+                             int cell_stride, int C, const float* theta, int K, double FN, double FP, double* ll,
+                             int ldk, void* stream) {
+    if (C <= 0 || K <= 0) return 0;
+    const size_t smem = sizeof(double2) * (size_t)K * W * 32;
+    BNPC_LAUNCH(ll_few_kernel, 8 * LLP_CELLS, 0, cdiv(C, LLP_CELLS), 8 * LLP_CELLS, smem, (cudaStream_t)stream,  x1, x0, W, M, cells, cell_stride, C, (const double2*)nullptr, K, ll, ldk, theta, FN, FP);
+    return 0;
+}
+
 int bnpc_ll_matrix(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
                    int cell_stride, int C, const double* lp, int K, double* ll, int ldk, void* stream) {
     if (C <= 0 || K <= 0) return 0;
     if (ldk < K) return bad_arg("ldk < K");
     if (W % 4 != 0) return bad_arg("W must be a multiple of 4");
-    if (K <= 2 && sizeof(double2) * (size_t)K * W * 32 <= 200 * 1024) {
+    if (ll_few_fits(K, W)) {
         const size_t smem = sizeof(double2) * (size_t)K * W * 32;
-        BNPC_LAUNCH(ll_few_kernel, 8 * LLP_CELLS, 0, cdiv(C, LLP_CELLS), 8 * LLP_CELLS, smem, (cudaStream_t)stream,  x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const double2*>(lp), K, ll, ldk);
+        BNPC_LAUNCH(ll_few_kernel, 8 * LLP_CELLS, 0, cdiv(C, LLP_CELLS), 8 * LLP_CELLS, smem, (cudaStream_t)stream,  x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const double2*>(lp), K, ll, ldk, (const float*)nullptr, 0.0, 0.0);
         return 0;
     }
     dim3 grid(cdiv(C, LL_THREADS), cdiv(K, LL_KT));
@@ -2393,12 +2481,20 @@ int bnpc_ll_matrix(const uint32_t* x1, const uint32_t* x0, int W, int M, const i
     return 0;
 }
 
+// perm / u == NULL: the kernel draws the visiting order and the uniforms itself (streams
+// stream_id+1, +2 of seed)
+static int gibbs_prepare_impl(const int32_t* perm, const double* u, const int32_t* assign, const int32_t* n1,
+                              const int32_t* n0, int N, double c1, double c0, double lnew_prior,
+                              bnpc_visit_t* visit, uint64_t seed, uint64_t stream_id, void* stream) {
+    if (N <= 0) return 0;
+    BNPC_LAUNCH(gibbs_prepare_kernel, 0, 0, cdiv(N, 256), 256, 0, (cudaStream_t)stream, perm, u, assign, n1, n0, N, c1, c0, lnew_prior, visit, seed, stream_id, feistel_half_bits(N));
+    return 0;
+}
 int bnpc_gibbs_prepare(const int32_t* perm, const double* u, const int32_t* assign, const int32_t* n1,
                        const int32_t* n0, int N, double c1, double c0, double lnew_prior,
                        bnpc_visit_t* visit, void* stream) {
-    if (N <= 0) return 0;
-    BNPC_LAUNCH(gibbs_prepare_kernel, 0, 0, cdiv(N, 256), 256, 0, (cudaStream_t)stream, perm, u, assign, n1, n0, N, c1, c0, lnew_prior, visit);
-    return 0;
+    if (!perm || !u) return bad_arg("perm/u");
+    return gibbs_prepare_impl(perm, u, assign, n1, n0, N, c1, c0, lnew_prior, visit, 0, 0, stream);
 }
 
 int bnpc_gibbs_candidates(const double* ll, int ldk, int K, const int32_t* col_of_id,
@@ -2511,28 +2607,39 @@ int bnpc_ll_matrix_i8(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
     }
 }
 
-int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_id,
-                       const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, int32_t* n_cert, int C,
-                       double log_n, double c_norm, int terms, double err_abs, void* stream) {
+// clear = false: the caller has zeroed n_cert already (the composite entry points clear all the
+// scratch of an epoch in one launch)
+static int gibbs_options_impl(const float* llf, int ldf, int K, const int32_t* col_of_id,
+                              const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, int32_t* n_cert, int C,
+                              double log_n, double c_norm, int terms, double err_abs, bool clear, void* stream) {
     if (C <= 0) return 0;
     if (K <= 0 || K > BNPC_LEAN_MAXK) return bad_arg("lean epochs need K <= BNPC_LEAN_MAXK");
-    if (int rc = zero_async(n_cert, sizeof(int32_t) * BNPC_LEAN_MAXK, stream, "gibbs_options memset")) return rc;
+    if (clear)
+        if (int rc = zero_async(n_cert, sizeof(int32_t) * BNPC_LEAN_MAXK, stream, "gibbs_options memset")) return rc;
     const float err_rel = (float)terms * 2.384185791015625e-07f;      // terms * 2^-22
     BNPC_LAUNCH(gibbs_options_kernel, CAND_THREADS, 0, cdiv(C, CAND_THREADS), CAND_THREADS, 0, (cudaStream_t)stream,  llf, ldf, K, col_of_id, visit_t0, opt_t0, n_cert, C, (float)log_n, c_norm, err_rel, 0.05f + (float)(err_abs > 0.0 ? err_abs : 0.0));
     return 0;
 }
 
-int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const double* lp, int K,
-                     const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, const int32_t* n_cert, int C,
-                     int32_t* blk, int32_t* idx_c, int32_t* st, bnpc_visit_t* visit_c,
-                     bnpc_cand_t* cand_c, double log_n, double c_norm, int32_t* comp, int32_t* order,
-                     void* stream) {
+int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_id,
+                       const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, int32_t* n_cert, int C,
+                       double log_n, double c_norm, int terms, double err_abs, void* stream) {
+    return gibbs_options_impl(llf, ldf, K, col_of_id, visit_t0, opt_t0, n_cert, C, log_n, c_norm, terms, err_abs, true,
+                              stream);
+}
+
+static int gibbs_exact_impl(const uint32_t* x1, const uint32_t* x0, int W, int M, const double* lp, int K,
+                            const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, const int32_t* n_cert, int C,
+                            int32_t* blk, int32_t* idx_c, int32_t* st, bnpc_visit_t* visit_c,
+                            bnpc_cand_t* cand_c, double log_n, double c_norm, int32_t* comp, int32_t* order,
+                            bool clear, void* stream) {
     if (C <= 0) return 0;
     if (K <= 0 || K > BNPC_LEAN_MAXK) return bad_arg("lean epochs need K <= BNPC_LEAN_MAXK");
     if (!comp || !order) return bad_arg("comp/order");
     const int nb = cdiv(C, CAND_THREADS);
     cudaStream_t s = (cudaStream_t)stream;
-    if (int rc = zero_async(comp, sizeof(int32_t) * 512, stream, "gibbs_exact memset")) return rc;
+    if (clear)
+        if (int rc = zero_async(comp, sizeof(int32_t) * 512, stream, "gibbs_exact memset")) return rc;
     BNPC_LAUNCH(gibbs_finalize_kernel, CAND_THREADS, 0, nb, CAND_THREADS, 0, s, opt_t0, n_cert, C, blk);
     BNPC_LAUNCH(compact_scan_kernel, 1024, 0, 1, 1024, 0, s, blk, nb, st);
     BNPC_LAUNCH(compact_index_kernel, CAND_THREADS, 0, nb, CAND_THREADS, 0, s, opt_t0, C, blk, idx_c);
@@ -2558,6 +2665,15 @@ int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const
     // (the processing order is not needed any more: its buffer receives the owner bytes)
     BNPC_LAUNCH(owner_bytes_kernel, 256, 0, cdiv(C, 256), 256, 0, s, visit_c, st, comp, reinterpret_cast<uint8_t*>(order));
     return 0;
+}
+
+int bnpc_gibbs_exact(const uint32_t* x1, const uint32_t* x0, int W, int M, const double* lp, int K,
+                     const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, const int32_t* n_cert, int C,
+                     int32_t* blk, int32_t* idx_c, int32_t* st, bnpc_visit_t* visit_c,
+                     bnpc_cand_t* cand_c, double log_n, double c_norm, int32_t* comp, int32_t* order,
+                     void* stream) {
+    return gibbs_exact_impl(x1, x0, W, M, lp, K, visit_t0, opt_t0, n_cert, C, blk, idx_c, st, visit_c, cand_c, log_n,
+                            c_norm, comp, order, true, stream);
 }
 
 int bnpc_gibbs_epoch_begin(const int32_t* live, int K, int32_t* lst, int32_t* cnt, int32_t* col_of_id,
@@ -2588,19 +2704,28 @@ int bnpc_set_ranks(const int32_t* ids, int K, int32_t* rank_of_id, void* stream)
     return 0;
 }
 
-int bnpc_group_members(const int32_t* assign, int N, const int32_t* rank_of_id, const int32_t* seg_off,
-                       int32_t* cursor, int K, int32_t* members, void* stream) {
+static int group_members_impl(const int32_t* assign, int N, const int32_t* rank_of_id, const int32_t* seg_off,
+                              int32_t* cursor, int K, int32_t* members, bool clear, void* stream) {
     if (N <= 0) return 0;
-    if (int rc = zero_async(cursor, sizeof(int32_t) * (size_t)K, stream, "group_members memset")) return rc;
+    if (clear)
+        if (int rc = zero_async(cursor, sizeof(int32_t) * (size_t)K, stream, "group_members memset")) return rc;
     BNPC_LAUNCH(group_members_kernel, 0, 0, cdiv(N, 256), 256, 0, (cudaStream_t)stream, assign, N, rank_of_id, seg_off, cursor, members);
     return 0;
 }
 
-int bnpc_suffstat(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* members,
-                  const int32_t* seg_off, int R, int max_len, int32_t* S1, int32_t* S0, void* stream) {
+int bnpc_group_members(const int32_t* assign, int N, const int32_t* rank_of_id, const int32_t* seg_off,
+                       int32_t* cursor, int K, int32_t* members, void* stream) {
+    return group_members_impl(assign, N, rank_of_id, seg_off, cursor, K, members, true, stream);
+}
+
+static int suffstat_impl(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* members,
+                         const int32_t* seg_off, int R, int max_len, int32_t* S1, int32_t* S0, bool clear,
+                         void* stream) {
     if (R <= 0) return 0;
-    if (int rc = zero_async(S1, sizeof(int32_t) * (size_t)R * M, stream, "suffstat memset")) return rc;
-    if (int rc = zero_async(S0, sizeof(int32_t) * (size_t)R * M, stream, "suffstat memset")) return rc;
+    if (clear) {
+        if (int rc = zero_async(S1, sizeof(int32_t) * (size_t)R * M, stream, "suffstat memset")) return rc;
+        if (int rc = zero_async(S0, sizeof(int32_t) * (size_t)R * M, stream, "suffstat memset")) return rc;
+    }
     if (max_len <= 0) return 0;
     int wc_log2 = 2;                       // word columns per CTA row group: 4, 8, 16 or 32
     while ((1 << wc_log2) < W && wc_log2 < 5) ++wc_log2;
@@ -2613,6 +2738,11 @@ int bnpc_suffstat(const uint32_t* x1, const uint32_t* x0, int W, int M, const in
         BNPC_LAUNCH(suffstat_kernel, SS_THREADS, 0, grid, SS_THREADS, 0, (cudaStream_t)stream, x1, x0, W, M, members, seg_off + r0, S1 + (size_t)r0 * M, S0 + (size_t)r0 * M, wc_log2, n_wblk);
     }
     return 0;
+}
+
+int bnpc_suffstat(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* members,
+                  const int32_t* seg_off, int R, int max_len, int32_t* S1, int32_t* S0, void* stream) {
+    return suffstat_impl(x1, x0, W, M, members, seg_off, R, max_len, S1, S0, true, stream);
 }
 
 int bnpc_beta_rows(const int32_t* S1, const int32_t* S0, int R, int M, double p, double q,
@@ -2638,21 +2768,36 @@ static MhConst make_mh_const(double FN, double FP, double p, double q) {
     return c;
 }
 
+// rnd == NULL: the kernel draws from streams stream_id+1, +2 of seed
+static int mh_theta_impl(float* theta, const int32_t* ids, int R, int M, const int32_t* S1, const int32_t* S0,
+                         const double* rnd, uint64_t seed, uint64_t stream_id, double FN, double FP, double p,
+                         double q, int flags, double* logq, int32_t* declined, void* stream) {
+    if (R <= 0) return 0;
+    if ((flags & 1) && !logq) return bad_arg("logq required when flags&1");
+    BNPC_LAUNCH(mh_theta_kernel, 0, 0, cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream,  theta, ids, R, M, S1, S0, rnd, make_mh_const(FN, FP, p, q), flags, logq, declined, seed, stream_id);
+    return 0;
+}
 int bnpc_mh_theta(float* theta, const int32_t* ids, int R, int M, const int32_t* S1, const int32_t* S0,
                   const double* rnd, double FN, double FP, double p, double q, int flags, double* logq,
                   int32_t* declined, void* stream) {
-    if (R <= 0) return 0;
-    if ((flags & 1) && !logq) return bad_arg("logq required when flags&1");
-    BNPC_LAUNCH(mh_theta_kernel, 0, 0, cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream,  theta, ids, R, M, S1, S0, rnd, make_mh_const(FN, FP, p, q), flags, logq, declined);
-    return 0;
+    if (!rnd) return bad_arg("rnd");
+    return mh_theta_impl(theta, ids, R, M, S1, S0, rnd, 0, 0, FN, FP, p, q, flags, logq, declined, stream);
 }
 
+// sd_idx == NULL: proposal-sd indices from stream stream_id of seed
+static int theta_log_ratio_impl(const float* th_new, const float* th_old, int R, int M, const int32_t* S1,
+                                const int32_t* S0, const double* sd_idx, uint64_t seed, uint64_t stream_id,
+                                float blo, float bhi, double FN, double FP, double p, double q, double* A,
+                                void* stream) {
+    if (R <= 0) return 0;
+    BNPC_LAUNCH(theta_log_ratio_kernel, 0, 0, cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream,  th_new, th_old, R, M, S1, S0, sd_idx, blo, bhi, make_mh_const(FN, FP, p, q), A, seed, stream_id);
+    return 0;
+}
 int bnpc_theta_log_ratio(const float* th_new, const float* th_old, int R, int M, const int32_t* S1,
                          const int32_t* S0, const double* sd_idx, float blo, float bhi, double FN,
                          double FP, double p, double q, double* A, void* stream) {
-    if (R <= 0) return 0;
-    BNPC_LAUNCH(theta_log_ratio_kernel, 0, 0, cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream,  th_new, th_old, R, M, S1, S0, sd_idx, blo, bhi, make_mh_const(FN, FP, p, q), A);
-    return 0;
+    if (!sd_idx) return bad_arg("sd_idx");
+    return theta_log_ratio_impl(th_new, th_old, R, M, S1, S0, sd_idx, 0, 0, blo, bhi, FN, FP, p, q, A, stream);
 }
 
 int bnpc_row_loglik(const float* theta, const int32_t* ids, int R, int M, const int32_t* S1,
@@ -2701,10 +2846,11 @@ int bnpc_rg_launch_halves(const uint32_t* x1, const uint32_t* x0, int W, const i
     return 0;
 }
 
-int bnpc_rg_sides(const int32_t* cells, int n, const int32_t* half, int32_t* members, int32_t* seg_off,
-                  void* stream) {
+static int rg_sides_impl(const int32_t* cells, int n, const int32_t* half, int32_t* members, int32_t* seg_off,
+                         bool clear, void* stream) {
     if (n < 2) return bad_arg("n < 2");
-    if (int rc = zero_async(seg_off, sizeof(int32_t) * 8, stream, "rg_sides memset")) return rc;
+    if (clear)
+        if (int rc = zero_async(seg_off, sizeof(int32_t) * 8, stream, "rg_sides memset")) return rc;
     if (n > 2) {
         BNPC_LAUNCH(rg_count_kernel, 0, 0, cdiv(n - 2, 256), 256, 0, (cudaStream_t)stream, half, n - 2, seg_off);
     }
@@ -2712,20 +2858,32 @@ int bnpc_rg_sides(const int32_t* cells, int n, const int32_t* half, int32_t* mem
     return 0;
 }
 
-int bnpc_rg_scan(const double* ll2, int ldk, int n, const int32_t* perm, const double* u, int32_t* half,
-                 double alpha, int mode, const int32_t* cells, const int32_t* assign, int id_i,
-                 double* lq, int32_t* work, void* stream) {
+// mode 0 with perm / u == NULL: order and uniforms from streams stream_id+1, +2 of seed
+static int rg_scan_impl(const double* ll2, int ldk, int n, const int32_t* perm, const double* u, uint64_t seed,
+                        uint64_t stream_id, int32_t* half, double alpha, int mode, const int32_t* cells,
+                        const int32_t* assign, int id_i, double* lq, int32_t* work, void* stream) {
     if (n <= 2) return 0;
-    if (mode == 0 && (!perm || !u)) return bad_arg("perm/u required for a sampled scan");
     if (mode == 1 && (!cells || !assign)) return bad_arg("cells/assign required for replay");
     if (!work) return bad_arg("work");
     const int nf = n - 2;
     const int out_off = (nf + 3) & ~3;
+    const int hb = feistel_half_bits(nf);
     cudaStream_t st = (cudaStream_t)stream;
-    BNPC_LAUNCH(rg_prepare_kernel, 0, 0, cdiv(nf, 128), 128, 0, st, ll2, ldk, n, perm, u, half, alpha, mode, cells, assign, id_i, work);
+    BNPC_LAUNCH(rg_prepare_kernel, 0, 0, cdiv(nf, 128), 128, 0, st, ll2, ldk, n, perm, u, half, alpha, mode, cells, assign, id_i, work, seed, stream_id, hb);
     BNPC_LAUNCH(rg_serial_kernel, 32, 0, 1, 32, 0, st, half, nf, work, out_off);
-    BNPC_LAUNCH(rg_finish_kernel, 0, 0, cdiv(nf, 128), 128, 0, st, ll2, ldk, n, perm, half, alpha, mode, work, out_off, lq);
+    BNPC_LAUNCH(rg_finish_kernel, 0, 0, cdiv(nf, 128), 128, 0, st, ll2, ldk, n, perm, half, alpha, mode, work, out_off, lq, seed, stream_id, hb);
     return 0;
+}
+int bnpc_rg_sides(const int32_t* cells, int n, const int32_t* half, int32_t* members, int32_t* seg_off,
+                  void* stream) {
+    return rg_sides_impl(cells, n, half, members, seg_off, true, stream);
+}
+
+int bnpc_rg_scan(const double* ll2, int ldk, int n, const int32_t* perm, const double* u, int32_t* half,
+                 double alpha, int mode, const int32_t* cells, const int32_t* assign, int id_i,
+                 double* lq, int32_t* work, void* stream) {
+    if (mode == 0 && (!perm || !u)) return bad_arg("perm/u required for a sampled scan");
+    return rg_scan_impl(ll2, ldk, n, perm, u, 0, 0, half, alpha, mode, cells, assign, id_i, lq, work, stream);
 }
 
 int bnpc_apply_split(const int32_t* cells, int n, const int32_t* half, int new_id, int32_t* assign,

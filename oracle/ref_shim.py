@@ -3,9 +3,10 @@
 Imports the UNMODIFIED reference (cbg-ethz/BnpC, read-only at /root/reference)
 in this container so that (a) the CPU restatement in oracle/crp_oracle.py can be
 pinned against it and (b) golden vectors can be generated from it
-(tests/golden/make_golden.py).  Nothing here travels to the GPU box:
-/root/reference does not exist there, and nothing in `-m gpu` tests, smoke() or
-bench.py imports this module.
+(tests/golden/make_golden.py).  /root/reference does not exist on the GPU box;
+an unmodified copy travels there under baseline/_ref (git-ignored, made by
+oracle/fetch_ref.py), which `bench.py --impl reference` times on the host cores.
+Nothing in the product path imports this module.
 
 The reference needs `bottleneck` (not installed; requirements.txt:1) -- a
 6-function numpy stand-in is injected for the duration of the import only
@@ -20,7 +21,20 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get('BNPC_REFERENCE_ROOT', '/root/reference')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIPPED = os.path.join(os.path.dirname(_HERE), 'baseline', '_ref', 'BnpC')      # oracle/fetch_ref.py
+
+
+def _find_root():
+    """the reference checkout: $BNPC_REFERENCE_ROOT, the build container's /root/reference, or the
+    unmodified copy shipped to the GPU box under baseline/_ref (git-ignored)"""
+    for cand in (os.environ.get('BNPC_REFERENCE_ROOT'), '/root/reference', _SHIPPED):
+        if cand and os.path.isfile(os.path.join(cand, 'libs', 'CRP.py')):
+            return cand
+    return '/root/reference'
+
+
+REF_ROOT = _find_root()
 
 
 def reference_available():
