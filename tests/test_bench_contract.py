@@ -1,5 +1,6 @@
-"""CPU: the reference arm of bench.py (`--impl reference`: the CPU restatement of the reference on a
-bounded cell sample, one process per chain) prints exactly ONE JSON line with the contract's keys."""
+"""CPU: the reference arm of bench.py (`--impl reference`: the unmodified reference classes from
+baseline/_ref when the copy is there, else the CPU restatement; one process per chain) prints exactly
+ONE JSON line with the contract's keys."""
 import json
 import os
 import subprocess
@@ -21,6 +22,9 @@ def test_reference_arm_prints_one_json_line():
     assert out['metric'].startswith('MCMC steps/sec/chain') and out['value'] > 0
     assert out['steps'] == 1 and out['n_gpus'] == 1 and out['data'] == 'synthetic' and out['vs_baseline'] is None
     cpu = out['cpu_baseline']
-    assert cpu['kind'] == 'port' and cpu['cores'] == 2 and cpu['value'] == out['value'] and '300 of 100000' in cpu['sample']
+    from oracle.ref_shim import reference_available
+    assert cpu['kind'] == ('reference' if reference_available() else 'port')
+    assert cpu['cores'] == 2 and cpu['value'] == out['value'] and '300 of 100000' in cpu['sample']
+    assert out['steps_requested'] == 1
     assert out['e2e'] == dict(value=out['value'], unit='chain-steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     assert 'workload' in out['config'] and 'model' not in out['config']
