@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -183,6 +184,8 @@ static int launch_wrapper(const char* name, const Batch<NB, P>& B, dim3 grid, in
         cudaEventRecord(eb, s);
         g_prof.slots.push_back(ProfSlot{name, ea, eb, chains});
     }
+    static const int sync_each = getenv("BNPC_SYNC_EACH") ? 1 : 0;      // debugging
+    if (sync_each) cudaStreamSynchronize(s);
     return 0;
 }
 
@@ -190,7 +193,8 @@ static int launch_wrapper(const char* name, const Batch<NB, P>& B, dim3 grid, in
 template <auto Body, int MAXT, int MINB>
 static int launch_merged(Op* const* ops, int n, cudaStream_t s) {
     using P = typename FnTraits<decltype(Body)>::pack_t;
-    if (n == 1) {
+    static const int force_nb8 = getenv("BNPC_FORCE_NB8") ? 1 : 0;      // debugging
+    if (n == 1 && !force_nb8) {
         Batch<1, P> B;
         B.gx[0] = ops[0]->gx; B.gy[0] = ops[0]->gy;
         memcpy(&B.a[0], ops[0]->args, sizeof(P));

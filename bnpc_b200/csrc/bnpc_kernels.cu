@@ -91,7 +91,7 @@ __device__ __forceinline__ void seg_copy_kernel(SegArgs a) {
 }
 
 template <auto Body>
-static int seg_launch(void* dst, const void* src, long long words, int vec, void* stream) {
+static int seg_launch(const char* name, void* dst, const void* src, long long words, int vec, void* stream) {
     using namespace bnpc;
     const unsigned blocks = (unsigned)cdiv(vec ? (words + 3) / 4 : words, 256);
     if (g_rec.on && !g_rec.q[g_rec.cur].empty()) {
@@ -110,8 +110,7 @@ static int seg_launch(void* dst, const void* src, long long words, int vec, void
     SegArgs a;
     memset(&a, 0, sizeof(a));
     a.dst[0] = dst; a.src[0] = src; a.n_words[0] = words; a.vec[0] = vec; a.count = 1;
-    BNPC_LAUNCH(Body, 0, 0, dim3(blocks, 1), 256, 0, stream, a);
-    return 0;
+    return bnpc::launch<Body, 0, 0>(name, dim3(blocks, 1), 256, 0, (cudaStream_t)stream, a);
 }
 
 static int zero_async(void* ptr, size_t bytes, void* stream, const char* what) {
@@ -122,7 +121,7 @@ static int zero_async(void* ptr, size_t bytes, void* stream, const char* what) {
         if (e != cudaSuccess) return fail(what, e);
         return 0;
     }
-    return seg_launch<seg_zero_kernel>(ptr, nullptr, (long long)(bytes >> 2), ((uintptr_t)ptr & 15) ? 0 : 1, stream);
+    return seg_launch<seg_zero_kernel>("seg_zero_kernel", ptr, nullptr, (long long)(bytes >> 2), ((uintptr_t)ptr & 15) ? 0 : 1, stream);
 }
 
 #define BNPC_SMALL_COPY_BYTES 8192
@@ -138,7 +137,7 @@ static int copy_async(void* dst, const void* src, size_t bytes, cudaMemcpyKind k
     if (bnpc::g_rec.on && !(bytes & 3) && !(((uintptr_t)dst | (uintptr_t)src) & 3) &&
         (kind == cudaMemcpyDeviceToDevice || (g_uva_copies && bytes <= BNPC_SMALL_COPY_BYTES))) {
         const int vec = (((uintptr_t)dst | (uintptr_t)src) & 15) ? 0 : 1;
-        return seg_launch<seg_copy_kernel>(dst, src, (long long)(bytes >> 2), vec, stream);
+        return seg_launch<seg_copy_kernel>("seg_copy_kernel", dst, src, (long long)(bytes >> 2), vec, stream);
     }
     if (bnpc::g_rec.on) {
         bnpc::g_rec.q[bnpc::g_rec.cur].emplace_back();
@@ -201,7 +200,19 @@ static int recorder_flush(cudaStream_t s, unsigned long long slots = ~0ull) {
         int who[BATCH_MAX];
         int n = 0;
         ops[n] = &key; who[n++] = lead;
-        for (int c = 0; c < GROUP_MAX && n < BATCH_MAX; ++c) {
+        // debugging: BNPC_NO_MERGE=1 one chain per launch; BNPC_MERGE_ONLY=a,b,... merges only the
+        // kernels whose name contains one of the tokens
+        static const int no_merge = getenv("BNPC_NO_MERGE") ? 1 : 0;
+        static const char* only = getenv("BNPC_MERGE_ONLY");
+        bool mergeable = !no_merge;
+        if (mergeable && only) {
+            mergeable = false;
+            char buf[512];
+            snprintf(buf, sizeof(buf), "%s", only);
+            for (char* tok = strtok(buf, ","); tok; tok = strtok(nullptr, ","))
+                if (strstr(key.name, tok)) mergeable = true;
+        }
+        for (int c = 0; c < GROUP_MAX && n < BATCH_MAX && mergeable; ++c) {
             if (c == lead || cur[c] >= R.q[c].size()) continue;
             Op& o = R.q[c][cur[c]];
             if (o.kind == 0 && o.merged == key.merged && o.block == key.block) { ops[n] = &o; who[n++] = c; }
@@ -1318,6 +1329,7 @@ __device__ void sweep_sequencer_par(const bnpc_sweep_args_t& a, SweepShared& sh)
         bool stopped = false;
         for (int base = 0; base < own && !stopped; base += 32) {
             int nc = min(32, own - base);
+            const int nc_batch = nc;
             const int rec = sh.own_idx[w][base + (lane < nc ? lane : 0)];
             const bnpc_visit_t v = vis[rec];
             double e[BNPC_MAX_OPT];
@@ -1350,7 +1362,10 @@ __device__ void sweep_sequencer_par(const bnpc_sweep_args_t& a, SweepShared& sh)
                 if (ab != 0x7fffffff) {
                     const unsigned keep = __ballot_sync(FULL, lane < nc && rec < ab);
                     nc = __popc(keep);                   // own_idx is ascending: a prefix survives
-                    stopped = true;
+                    // the walk of this warp ends here only if the posted record cuts THIS batch (then
+                    // all later batches lie behind it too); a batch that lies wholly in front of it is
+                    // followed by the next one -- every record in front of the posted one must be walked
+                    if (nc < nc_batch) stopped = true;
                     if (lo_lane >= nc) break;
                 }
                 if (need_eval) {

@@ -12,6 +12,7 @@ stream drains into pinned host arrays while the next step runs.
 path (random tape against the oracle); a chain walks the same trajectory under either host.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -63,6 +64,8 @@ class ChainGroup:
         n = len(self.chains)
         torch.cuda.set_device(self.device)
         self.sA, self.sB, self.sC = (torch.cuda.Stream(self.device) for _ in range(3))
+        if os.environ.get('BNPC_ONE_STREAM'):          # debugging: split-merge moves on the main stream
+            self.sB = self.sA
         self.states = [_lib.ChainState() for _ in range(n)]
         self.traces = [_lib.Trace() for _ in range(n)]
         self._live = [np.zeros(2 * max(m.idcap, 64), dtype=np.int32) for m in self.models]

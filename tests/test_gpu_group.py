@@ -138,3 +138,21 @@ def test_recorded_launches_merge_across_chains():
         counts[n] = (_lib.launch_count() - before) / 30
     assert counts[8] < 4 * counts[1], counts            # 8 chains for far less than 8x the launches
     assert counts[8] / 8 < 25, counts                   # launches per chain-step
+
+
+def test_parallel_sweep_equals_single_sequencer():
+    """The sweep walks the uncertain records with one warp per group of option-graph components;
+    the single-sequencer route (`serial_sweep`) is its sequential definition.  Same seeds -> same
+    traces, bit for bit (regression: a warp that saw a record posted for the exact path stopped
+    walking although more of its own records lay in front of the posted one -- seed 15, step 10)."""
+    from libs.MCMC import run_chains
+    data, z = simulate(4000, 256, k_true=8, miss=0.1, seed=5)
+    assign = [int(v) for v in z]
+    moves = _moves(sm_prob=0.4)
+    seeds = list(range(7, 17))
+    par = _chains(data, True, [0.25, 0.25], moves, 30, seeds, assign)
+    run_chains(par)
+    ser = _chains(data, True, [0.25, 0.25], moves, 30, seeds, assign, 0, dict(serial_sweep=True))
+    run_chains(ser)
+    for a, b in zip(par, ser):
+        _same(a, b, f'seed {seeds[a.no - 1]}', exact=True)

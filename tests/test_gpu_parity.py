@@ -74,6 +74,17 @@ CASES = [
     ('mostly_certain', 30000, 300, 10, 0.10, True, [0.25, 0.25], 'assign', 4, dict(DEFAULT_MOVES, sm_prob=0.25)),
 ]
 
+# the BASELINE.json shapes: C2 in full, slices of C3 / C4 with their full row widths (W = 32 and
+# W = 160 plane words per cell: the shapes the tensor-core rows and the exact rows are benchmarked
+# at), a C5-like panel with 30 % missing entries; K_true and noise as bench.py generates them
+BENCH_SHAPE_CASES = [
+    ('c2_full_10k_x_500', 10000, 500, 20, 0.10, True, [0.25, 0.25], 'assign', 3, dict(DEFAULT_MOVES, sm_prob=0.33)),
+    ('c3_rows_5k_x_1000', 5000, 1000, 20, 0.10, True, [0.25, 0.25], 'assign', 3, dict(DEFAULT_MOVES, sm_prob=0.33)),
+    ('c4_rows_2k_x_5000_smheavy', 2000, 5000, 20, 0.10, False, [0.25, 0.25], 'assign', 4,
+     dict(DEFAULT_MOVES, sm_prob=0.75)),
+    ('c5_panel_20k_x_50_miss30', 20000, 50, 10, 0.30, True, [1, 1], 'assign', 3, dict(DEFAULT_MOVES, sm_prob=0.33)),
+]
+
 
 @pytest.fixture
 def dense_rows(monkeypatch):
@@ -166,6 +177,12 @@ def test_cuda_matches_oracle_on_seeded_data(case):
         assert log == logs[s], f'{name} step {s + 1}: {log} vs {logs[s]}'
         assert rnd.tape.pos == pos[s + 1], f'{name} step {s + 1}: tape position'
         assert_state(snapshot(m), snaps[s + 1], f'{name} step {s + 1}', exact_float=False, rtol=RTOL)
+
+
+@pytest.mark.parametrize('case', BENCH_SHAPE_CASES, ids=[c[0] for c in BENCH_SHAPE_CASES])
+def test_cuda_matches_oracle_at_benchmark_shapes(case):
+    """tape parity (oracle-recorded tape, bit-identical decisions) at the shapes bench.py runs"""
+    test_cuda_matches_oracle_on_seeded_data(case)
 
 
 def test_production_mode_recovers_clusters_and_is_deterministic():
