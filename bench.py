@@ -62,6 +62,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip single-chain / evolved-state / C2,C4,C5 figures')
     ap.add_argument('--cpu-sample-cells', type=int, default=0)
+    ap.add_argument('--group-size', type=int, default=0,
+                    help='chains per lockstep group (0: libs.MCMC.GROUP_SIZE); experiment switch')
     ap.add_argument('--ref-budget-s', type=float, default=240.0, help="--impl reference: seconds of stepping")
     return ap.parse_args()
 
@@ -295,21 +297,42 @@ class Bench:
         self.torch.cuda.synchronize()
         return out
 
-    def window(self, n, warm, steps, host_assign, profile=False):
+    def window(self, n, warm, steps, host_assign, profile=False, group_size=0):
         """one timed window: fresh chains, `warm` untimed steps, `steps` timed steps between
-        barriers + device synchronisation; returns (ms [max over ranks], launches, chains, extra)"""
+        barriers + device synchronisation; returns (ms [max over ranks], launches, extra).
+        group_size: chains per lockstep group (0: libs.MCMC.GROUP_SIZE, the driver's default); several
+        groups of one device are stepped by one host thread each, as libs.MCMC.run_chains does."""
+        import threading
         import torch.distributed as dist
         from bnpc_b200 import _lib
         from bnpc_b200.group import ChainGroup
+        import libs.MCMC as mcmc
         torch = self.torch
         chains = self.chains(n, warm + steps + 1)
-        group = ChainGroup(chains, self.moves, False, host_assign=host_assign)
+        gs = group_size or mcmc.GROUP_SIZE
+        parts = [chains[i:i + gs] for i in range(0, n, gs)]
+        groups = [ChainGroup(p, self.moves, False, host_assign=host_assign) for p in parts]
         for ch in chains:
             ch._prepare_params(0)
+
+        def run_all(step0, count):
+            if len(groups) == 1:
+                groups[0].run(step0, count)
+                return
+            errs = []
+
+            def work(g):
+                try:
+                    g.run(step0, count)
+                except BaseException as exc:          # noqa: BLE001
+                    errs.append(exc)
+            ths = [threading.Thread(target=work, args=(g,)) for g in groups]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+            if errs:
+                raise errs[0]
         try:
-            group.run(1, warm)
-            for m in group.models:
-                m.h2d_bytes = m.d2h_bytes = 0
+            run_all(1, warm)
             if self.world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
@@ -318,7 +341,7 @@ class Bench:
             if profile:
                 _lib.lib().prof_enable(1)
             a.record()
-            group.run(1 + warm, steps)
+            run_all(1 + warm, steps)
             torch.cuda.synchronize()
             b.record()
             b.synchronize()
@@ -335,10 +358,11 @@ class Bench:
             m0 = chains[0].model
             extra = dict(k_live=len(m0.cells_per_cluster), sweep=dict(m0.sweep_stats), prof=prof,
                          ml_last=float(chains[0].results['ML'][warm + steps]),
-                         k_all=[len(ch.model.cells_per_cluster) for ch in chains])
+                         k_all=[len(ch.model.cells_per_cluster) for ch in chains], groups=len(groups))
             return float(ms.item()), int(launches.item()), extra
         finally:
-            group.close()
+            for g in groups:
+                g.close()
 
     def trace_bytes_per_step(self, k_live):
         """device->host bytes of one chain-step of the e2e leg, counted from the copies the driver
@@ -346,10 +370,10 @@ class Bench:
         status words / live list / decision scalars of the phases (<= 1 KB)"""
         return 4 * self.N + 4 * k_live * self.M + 5 * 8 + 1024
 
-    def repeat(self, n, warm, steps, windows, host_assign):
+    def repeat(self, n, warm, steps, windows, host_assign, group_size=0):
         ms, launches, extra = [], [], None
         for _ in range(windows):
-            t, l, extra = self.window(n, warm, steps, host_assign)
+            t, l, extra = self.window(n, warm, steps, host_assign, group_size=group_size)
             ms.append(t)
             launches.append(l)
         return ms, launches, extra
@@ -432,15 +456,15 @@ def run_gpu(args, cfg):
 
     bench.window(cpg, 2, 3, True)                      # library, allocator and clocks warm
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev, launches, ex_dev = bench.repeat(cpg, W, K, R, host_assign=False)
-    ms_e2e, _, ex_e2e = bench.repeat(cpg, W, K, R, host_assign=True)
+    ms_dev, launches, ex_dev = bench.repeat(cpg, W, K, R, host_assign=False, group_size=args.group_size)
+    ms_e2e, _, ex_e2e = bench.repeat(cpg, W, K, R, host_assign=True, group_size=args.group_size)
     clocks = sampler.stop() if sampler else None
     total_chains = cpg * world
     med_dev, med_e2e = float(np.median(ms_dev)), float(np.median(ms_e2e))
     value, e2e = _rate(total_chains, K, med_dev), _rate(total_chains, K, med_e2e)
 
     # per-kernel device times: CUDA events around EVERY launch, a separate untimed pass
-    _, _, ex_prof = bench.window(cpg, W, K, False, profile=True)
+    _, _, ex_prof = bench.window(cpg, W, K, False, profile=True, group_size=cpg)
     extras = {}
     if not args.no_extras:
         s_ms, s_l, _ = bench.repeat(1, W, K, min(R, 3), host_assign=True)
@@ -448,7 +472,7 @@ def run_gpu(args, cfg):
                                       steps_per_sec_per_chain=_rate(1, K, float(np.median(s_ms))),
                                       ms_per_step=float(np.median(s_ms)) / K, launches_per_step=float(np.median(s_l)) / K / world,
                                       windows_ms=_spread(s_ms), api='e2e (host traces), 1 chain on 1 GPU')
-        ev_ms, _, ev_ex = bench.window(cpg, 250 + W, K, True)
+        ev_ms, _, ev_ex = bench.window(cpg, 250 + W, K, True, group_size=args.group_size)
         extras['evolved_state'] = dict(value=_rate(total_chains, K, ev_ms), unit='chain-steps/s', warmup_steps=250 + W,
                                        ms_per_step=ev_ms / K, live_clusters=ev_ex['k_all'], sweep=ev_ex['sweep'],
                                        api='e2e (host traces)')
@@ -473,7 +497,7 @@ def run_gpu(args, cfg):
         ms_per_step=med_dev / K, higher_is_better=True, scaling='weak', vs_baseline=None,
         dtype='f64', data='synthetic',
         config=dict(workload=describe(args.config, cfg), chains_per_gpu=cpg, chains_total=total_chains,
-                    moves=moves_of(cfg), live_clusters=ex_dev['k_all'],
+                    moves=moves_of(cfg), live_clusters=ex_dev['k_all'], lockstep_groups_per_gpu=ex_dev['groups'],
                     windows=f'{R} timed windows of {W} warm-up + {K} timed steps, fresh chains with the same seeds '
                             'per window; median reported',
                     l2='no explicit flush: per step every chain streams its own visit records, approximate rows, '

@@ -200,6 +200,11 @@ class MCMC:
             c.results['PSRF_cutoff'] = cutoff
 
 
+# chains per lockstep group: the chains of one device are stepped in groups of at most this many,
+# one host thread per group (env BNPC_GROUP_SIZE; measured on B200 at 100k x 1k)
+GROUP_SIZE = int(os.environ.get('BNPC_GROUP_SIZE', 4))
+
+
 def run_chains(chains, init_steps=0):
     """Run chains that share a device to completion: in lockstep through the native group driver
     when their models allow it (CUDA model, counter-based random streams), else one after another
@@ -210,6 +215,24 @@ def run_chains(chains, init_steps=0):
     if not native:
         for ch in chains:
             ch.run_python(init_steps) if isinstance(ch, Chain_steps) else ch.run_python()
+        return
+    if len(chains) > GROUP_SIZE:
+        # several lockstep groups side by side on the device, one host thread each
+        parts = [chains[i:i + GROUP_SIZE] for i in range(0, len(chains), GROUP_SIZE)]
+        errors = []
+
+        def work(part):
+            try:
+                run_chains(part, init_steps)
+            except BaseException as exc:              # noqa: BLE001  (surfaced below)
+                errors.append(exc)
+        threads = [threading.Thread(target=work, args=(part,)) for part in parts]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
         return
     group = ChainGroup(chains, chains[0].mcmc, chains[0].fix_assign)
     try:
