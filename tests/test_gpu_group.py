@@ -122,11 +122,14 @@ def test_group_extends_and_resumes():
         _same(x, y, f'chain {x.no}', exact=True)
 
 
-def test_recorded_launches_merge_across_chains():
+def test_recorded_launches_merge_across_chains(monkeypatch):
     """the launches of a group step grow far slower than the number of chains: a step of 8 chains
-    costs one Gibbs sequence + one split-merge sequence + one parameter sequence, whoever drew what"""
+    in one lockstep group costs one Gibbs sequence + one split-merge sequence + one parameter
+    sequence, whoever drew what"""
     from bnpc_b200 import _lib
+    import libs.MCMC as mcmc
     from libs.MCMC import run_chains
+    monkeypatch.setattr(mcmc, 'GROUP_SIZE', 8)
     data, z = simulate(3000, 200, k_true=6, miss=0.1, seed=2)
     assign = [int(v) for v in z]
     moves = _moves()
