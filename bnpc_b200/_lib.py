@@ -152,6 +152,7 @@ SIGNATURES = {
     'bnpc_ll_matrix_tc': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P],
     'bnpc_cocluster_counts': [_P, _I, _I, _P, _P],
     'bnpc_mpear_sums': [_P, _I, _P, _I, _P, _P],
+    'bnpc_mpear_sums_weighted': [_P, _I, _P, _I, _P, _P, _P],
     'bnpc_debug_set_trace': [_P],
     'bnpc_ll_matrix_i8': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _D, _P, _I, _P],
     'bnpc_gibbs_options': [_P, _I, _I, _P, _P, _P, _P, _I, _D, _D, _I, _D, _P],

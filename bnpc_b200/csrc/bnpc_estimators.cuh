@@ -70,8 +70,10 @@ __device__ __forceinline__ void cocluster_counts_kernel(const int32_t* __restric
 }
 
 #define EST_CGROUP 32          /* candidate labellings staged per round */
+// weight (or NULL): multiplicity of every point -- the points are the distinct assignment profiles
+// of the cells and pair (i, j) stands for weight[i] * weight[j] pairs of cells
 __device__ __forceinline__ void mpear_sums_kernel(const int32_t* __restrict__ counts, int N, const int32_t* __restrict__ labels, int n_cand,
-                  unsigned long long* __restrict__ out) {
+                  unsigned long long* __restrict__ out, const int32_t* __restrict__ weight) {
     const int tj = blockIdx.x, ti = blockIdx.y;
     if (tj < ti) return;
     __shared__ int32_t li[EST_CGROUP][EST_TILE], lj[EST_CGROUP][EST_TILE];
@@ -80,6 +82,7 @@ __device__ __forceinline__ void mpear_sums_kernel(const int32_t* __restrict__ co
     const int i0 = ti * EST_TILE, j0 = tj * EST_TILE;
     int cnt[4][4];
     bool ok[4][4];
+    unsigned long long wt[4][4];
     unsigned long long t_loc = 0;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -89,7 +92,8 @@ __device__ __forceinline__ void mpear_sums_kernel(const int32_t* __restrict__ co
             const long long j = j0 + tx * 4 + b;
             ok[a][b] = i < j && j < N;
             cnt[a][b] = ok[a][b] ? counts[condensed_index(i, j, N)] : 0;
-            t_loc += (unsigned long long)cnt[a][b];
+            wt[a][b] = (ok[a][b] && weight) ? (unsigned long long)weight[i] * (unsigned long long)weight[j] : 1ull;
+            t_loc += wt[a][b] * (unsigned long long)cnt[a][b];
         }
     }
     if (threadIdx.x == 0) accT = 0ull;
@@ -121,7 +125,7 @@ __device__ __forceinline__ void mpear_sums_kernel(const int32_t* __restrict__ co
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
-                    if (ok[a][b] && ai[a] == bj[b]) { A += 1ull; B += (unsigned long long)cnt[a][b]; }
+                    if (ok[a][b] && ai[a] == bj[b]) { A += wt[a][b]; B += wt[a][b] * (unsigned long long)cnt[a][b]; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 A += __shfl_xor_sync(0xffffffffu, A, o);

@@ -470,8 +470,9 @@ __device__ __forceinline__ void ll_matrix_kernel(const uint32_t* __restrict__ x1
 // scans, libs/CRP.py:635-638): the cells of a split-merge move are few (one or two clusters), so
 // one thread per cell leaves the GPU idle.  Eight threads share a cell (thread s takes the words
 // w = s, s + 8, ...), the whole table sits in shared memory, partial sums are combined by a fixed
-// butterfly.  Lane s walks the bits of a word rotated by 4 s so that the eight lanes of a cell hit
-// different banks.
+// butterfly.  Lane s walks the bits of a word rotated by s: a table entry is 16 bytes (log p1, log p0),
+// so the eight lanes of a cell read eight different 16-byte bank groups (a rotation by 4 s left
+// only two distinct groups: 4-way conflicts, ncu: short-scoreboard stalls dominated).
 #define LLP_CELLS 32
 __device__ __forceinline__ void ll_few_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
               const int32_t* __restrict__ cells, int cell_stride, int C,
@@ -507,7 +508,7 @@ __device__ __forceinline__ void ll_few_kernel(const uint32_t* __restrict__ x1, c
             if ((u1 | u0) == 0u) continue;
 #pragma unroll 4
             for (int i = 0; i < 32; ++i) {
-                const int bit = (i + 4 * sub) & 31;
+                const int bit = (i + sub) & 31;
                 const uint32_t b1 = (u1 >> bit) & 1u, b0 = (u0 >> bit) & 1u;
                 const int at = 2 * (w * 32 + bit) + (b1 ? 0 : 1);
                 const bool any = (b1 | b0) != 0u;
@@ -1930,12 +1931,12 @@ __device__ __forceinline__ void group_members_kernel(const int32_t* __restrict__
 // (acc[j] += (x >> j) & 0x01010101 counts bits j, j+8, j+16, j+24), at most 255 rows per thread.
 __device__ __forceinline__ void suffstat_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
                 const int32_t* __restrict__ members, const int32_t* __restrict__ seg_off,
-                int32_t* __restrict__ S1, int32_t* __restrict__ S0, int wc_log2, int n_wblk) {
+                int32_t* __restrict__ S1, int32_t* __restrict__ S0, int wc_log2, int n_wblk, int chunk) {
     __shared__ int cnt[2][32][32];
     // blockIdx.y = segment * n_wblk + word block (blockIdx.z is the chain of a batched launch)
     const int r = blockIdx.y / n_wblk, wblk = blockIdx.y % n_wblk;
-    const int beg = seg_off[r] + blockIdx.x * SS_CHUNK;
-    const int end = min(seg_off[r + 1], beg + SS_CHUNK);
+    const int beg = seg_off[r] + blockIdx.x * chunk;
+    const int end = min(seg_off[r + 1], beg + chunk);
     if (beg >= end) return;
     const int wc = 1 << wc_log2;
     const int col = threadIdx.x & (wc - 1), rsub = threadIdx.x >> wc_log2, rstep = SS_THREADS >> wc_log2;
@@ -2579,6 +2580,11 @@ int bnpc_cocluster_counts(const int32_t* assign, int S, int N, int32_t* counts, 
 
 int bnpc_mpear_sums(const int32_t* counts, int N, const int32_t* labels, int n_cand, unsigned long long* out,
                     void* stream) {
+    return bnpc_mpear_sums_weighted(counts, N, labels, n_cand, nullptr, out, stream);
+}
+
+int bnpc_mpear_sums_weighted(const int32_t* counts, int N, const int32_t* labels, int n_cand, const int32_t* weight,
+                             unsigned long long* out, void* stream) {
     if (N < 2 || n_cand < 0) return bad_arg("mpear_sums needs N >= 2");
     const int T = cdiv(N, EST_TILE);
     if (T > 65535) return bad_arg("too many cells for one launch");
@@ -2586,7 +2592,7 @@ int bnpc_mpear_sums(const int32_t* counts, int N, const int32_t* labels, int n_c
                                      (cudaStream_t)stream);
     if (ce != cudaSuccess) return fail("mpear_sums memset", ce);
     dim3 grid(T, T);
-    BNPC_LAUNCH(mpear_sums_kernel, 256, 0, grid, 256, 0, (cudaStream_t)stream, counts, N, labels, n_cand, out);
+    BNPC_LAUNCH(mpear_sums_kernel, 256, 0, grid, 256, 0, (cudaStream_t)stream, counts, N, labels, n_cand, out, weight);
     return 0;
 }
 
@@ -2747,10 +2753,14 @@ static int suffstat_impl(const uint32_t* x1, const uint32_t* x0, int W, int M, c
     // grid.y = segments x word blocks, limited to 65535: tile the segment axis
     const int n_wblk = cdiv(W, 32);
     const int r_max = 65535 / n_wblk;
+    // rows per CTA: SS_CHUNK for the statistics of all clusters; the two sides of a restricted Gibbs
+    // scan are a few thousand rows -- a quarter of the chunk gives four times the CTAs to a kernel
+    // that is bound by the latency of its row gathers (ncu: 40 CTAs, 12 % of the warp slots)
+    const int chunk = ((long long)max_len * R <= 65536) ? SS_CHUNK / 4 : SS_CHUNK;
     for (int r0 = 0; r0 < R; r0 += r_max) {
         const int rr = min(r_max, R - r0);
-        dim3 grid(cdiv(max_len, SS_CHUNK), rr * n_wblk);
-        BNPC_LAUNCH(suffstat_kernel, SS_THREADS, 0, grid, SS_THREADS, 0, (cudaStream_t)stream, x1, x0, W, M, members, seg_off + r0, S1 + (size_t)r0 * M, S0 + (size_t)r0 * M, wc_log2, n_wblk);
+        dim3 grid(cdiv(max_len, chunk), rr * n_wblk);
+        BNPC_LAUNCH(suffstat_kernel, SS_THREADS, 0, grid, SS_THREADS, 0, (cudaStream_t)stream, x1, x0, W, M, members, seg_off + r0, S1 + (size_t)r0 * M, S0 + (size_t)r0 * M, wc_log2, n_wblk, chunk);
     }
     return 0;
 }

@@ -24,7 +24,11 @@ constexpr double kThetaLo = 1e-5;
 constexpr double kThetaHi = 1 - 1e-5;
 constexpr double kNormLogC = 0.91893853320467274178;                  // log(sqrt(2*pi))
 
-__device__ __forceinline__ double ndtr(double x) {
+// The special functions below are deliberately NOT inlined: the Metropolis-Hastings kernels call
+// them a dozen times per element in straight-line code that each thread runs once; inlined, that
+// code is ~290 KB of SASS and the kernel is bound by cold instruction fetches (ncu: 70 % of the
+// stall samples "no instructions"), not by the arithmetic.
+__device__ __noinline__ double ndtr(double x) {
     // Cephes ndtr as used by scipy.special.ndtr
     const double z = x * 0.70710678118654752440;
     const double az = fabs(z);
@@ -33,7 +37,7 @@ __device__ __forceinline__ double ndtr(double x) {
     return (z > 0) ? 1.0 - y : y;
 }
 
-__device__ __forceinline__ double log_ndtr(double x) {
+__device__ __noinline__ double log_ndtr(double x) {
     // scipy.special.log_ndtr: erfcx form in the left tail, log1p elsewhere
     const double t = x * 0.70710678118654752440;
     if (x < -1.0) return log(erfcx(-t) / 2) - t * t;
@@ -51,7 +55,7 @@ __device__ __forceinline__ double log_sum_exp2(double lp, double lq) {
     return log(exp(lp - m) + exp(lq - m)) + m;
 }
 
-__device__ __forceinline__ double log_gauss_mass(double a, double b) {
+__device__ __noinline__ double log_gauss_mass(double a, double b) {
     // scipy/stats/_continuous_distns.py:_log_gauss_mass
     if (b <= 0) return log_diff_exp(log_ndtr(b), log_ndtr(a));
     if (a > 0) return log_diff_exp(log_ndtr(-a), log_ndtr(-b));
@@ -64,7 +68,7 @@ __device__ __forceinline__ double truncnorm_logpdf_std(double y, double a, doubl
     return -(y * y) / 2.0 - kNormLogC - log_gauss_mass(a, b);
 }
 
-__device__ __forceinline__ double ndtri_exp(double y) {
+__device__ __noinline__ double ndtri_exp(double y) {
     // scipy.special.ndtri_exp = ndtri(exp(y)) with the upper branch kept accurate
     if (y > -0.14541345786885906) return -normcdfinv(-expm1(y));
     return normcdfinv(exp(y));
@@ -80,7 +84,7 @@ __device__ __forceinline__ double truncnorm_ppf_std(double q, double a, double b
     return -ndtri_exp(lphi);
 }
 
-__device__ __forceinline__ double beta_logpdf(double x, double p, double q, double betaln_pq) {
+__device__ __noinline__ double beta_logpdf(double x, double p, double q, double betaln_pq) {
     // scipy beta_gen._logpdf: xlog1py(q-1, -x) + xlogy(p-1, x) - betaln(p, q)
     double t1 = (q - 1.0 == 0.0) ? 0.0 : (q - 1.0) * log1p(-x);
     double t2 = (p - 1.0 == 0.0) ? 0.0 : (p - 1.0) * log(x);
@@ -89,7 +93,7 @@ __device__ __forceinline__ double beta_logpdf(double x, double p, double q, doub
 
 // Bernoulli-with-errors log-probabilities of one (cluster, mutation) entry,
 // reference libs/CRP.py:197-212.  theta is float32, (1 - theta) rounds in float32.
-__device__ __forceinline__ void log_p1_p0(float th, double FN, double FP, double& lp1, double& lp0) {
+__device__ __noinline__ void log_p1_p0(float th, double FN, double FP, double& lp1, double& lp0) {
     const double t = (double)th;
     const double omt = (double)(1.0f - th);
     lp1 = log(t * (1.0 - FN) + omt * FP);

@@ -205,6 +205,13 @@ int bnpc_ll_matrix_tc(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
 int bnpc_cocluster_counts(const int32_t* assign, int S, int N, int32_t* counts, void* stream);
 int bnpc_mpear_sums(const int32_t* counts, int N, const int32_t* labels, int n_cand,
                     unsigned long long* out, void* stream);
+/* The same sums when the N points are the DISTINCT assignment profiles of the cells and point i
+ * stands for weight[i] cells with that profile: pair (i, j) counts weight[i] * weight[j] times
+ * (pairs inside one profile never differ: the caller adds their number to out[1+2c]).  This is
+ * how the estimator reaches 100k cells: the N(N-1)/2 pair vector of the reference (20 GB there)
+ * shrinks to the profiles' pairs.                                                             */
+int bnpc_mpear_sums_weighted(const int32_t* counts, int N, const int32_t* labels, int n_cand,
+                             const int32_t* weight, unsigned long long* out, void* stream);
 /* Debug hook: buf = device array of 4096 int64 (or NULL) that CTA 0 of bnpc_ll_matrix_i8 fills with
  * clock64 stamps of its pipeline phases (tools/tc_trace.py). */
 int bnpc_debug_set_trace(void* buf);

@@ -13,6 +13,16 @@ estimator run on the GPU through the C ABI (`bnpc_cocluster_counts`, `bnpc_mpear
 The ward linkage itself (scipy, O(N^2) memory on the host) and the O(S N) genotype averaging stay
 on the host.  There is no CPU path for the two kernels: without the library or a CUDA device the
 posterior estimator raises.
+
+Large matrices (BASELINE config 3: 100k cells): the reference's N(N-1)/2 pair vector would be 20 GB
+per sample.  Cells with the SAME assignment profile over all posterior samples are at distance 0
+from each other and at equal distances from everybody else, and ward linkage merges them first:
+the dendrogram above those merges is the weighted ward dendrogram of the DISTINCT profiles
+(`_ward_linkage_weighted`: scipy's nearest-neighbour-chain algorithm with its ward update, started
+from clusters of the profiles' multiplicities), and the three pair sums of the MPEAR score follow
+from the profiles' pairs weighted by the multiplicities (`bnpc_mpear_sums_weighted`).  The result
+is the reference's whenever the dendrogram has no tie at a candidate cut (ties are broken by
+position in both, but the positions differ); the tests compare it with scipy on all cells.
 """
 import numpy as np
 import pandas as pd
@@ -25,6 +35,7 @@ from sklearn.metrics.cluster import v_measure_score
 EPSILON = np.finfo(np.float64).resolution
 log_EPSILON = np.log(EPSILON)
 MAX_LINKAGE_CELLS = 30_000       # condensed float64 distances of the host linkage: 3.6 GB at 30k cells
+MAX_PROFILES = 24_000            # square float64 distances of the weighted linkage: 4.6 GB at 24k profiles
 
 
 # ------------------------------------------------------------------------------ evaluation
@@ -83,15 +94,26 @@ class _PairCounts:
         """counts / S in float64 on the host (exactly the reference's `dist / steps`)."""
         return self.counts.cpu().numpy() / self.S
 
-    def sums(self, labels):
-        """labels int [n_cand, N] -> (T, A[n_cand], B[n_cand]) exact integers (bnpc_mpear_sums)."""
+    def dist_square(self):
+        """the same distances as a square float64 matrix (zero diagonal)"""
+        from scipy.spatial.distance import squareform
+        return squareform(self.dist(), checks=False)
+
+    def sums(self, labels, weight=None):
+        """labels int [n_cand, N] -> (T, A[n_cand], B[n_cand]) exact integers (bnpc_mpear_sums);
+        weight [N]: multiplicity of every point (bnpc_mpear_sums_weighted)."""
         torch = self.torch
         lab = np.ascontiguousarray(labels, dtype=np.int32)
         n_cand = lab.shape[0]
         with torch.cuda.device(self.device):
             lab_d = torch.from_numpy(lab).to(self.device)
             out = torch.zeros(1 + 2 * n_cand, dtype=torch.int64, device=self.device)
-            self.L.mpear_sums(self.counts.data_ptr(), self.N, lab_d.data_ptr(), n_cand, out.data_ptr(), self.stream)
+            if weight is None:
+                self.L.mpear_sums(self.counts.data_ptr(), self.N, lab_d.data_ptr(), n_cand, out.data_ptr(), self.stream)
+            else:
+                w_d = torch.from_numpy(np.ascontiguousarray(weight, dtype=np.int32)).to(self.device)
+                self.L.mpear_sums_weighted(self.counts.data_ptr(), self.N, lab_d.data_ptr(), n_cand, w_d.data_ptr(),
+                                           out.data_ptr(), self.stream)
             torch.cuda.current_stream(self.device).synchronize()
         o = out.cpu().numpy()
         return int(o[0]), o[1::2].copy(), o[2::2].copy()
@@ -131,25 +153,160 @@ def _calc_MPEAR(pi, c):
     return (index - expected) / (.5 * (i_sum + pi_sum) - expected)
 
 
+def _unique_profiles(assignments):
+    """Group the cells by their assignment profile (column of `assignments`).  Returns
+    (rep [U]: the LAST cell of every group, groups ordered by it -- the slot scipy's linkage leaves
+    a merged cluster in --, inverse [N]: group of every cell, weight [U]).  Columns are hashed with
+    two independent 64-bit multiplicative hashes and every cell is then compared with its group's
+    representative, so the grouping is exact."""
+    a = np.ascontiguousarray(assignments)
+    steps, cells = a.shape
+    rng = np.random.default_rng(0x5EED)
+    h = np.zeros((2, cells), dtype=np.uint64)
+    mult = rng.integers(1, 2 ** 63, size=(2, steps), dtype=np.uint64) | np.uint64(1)
+    with np.errstate(over='ignore'):
+        for s0 in range(0, steps, 256):                      # bounded temporaries
+            blk = a[s0:s0 + 256].astype(np.uint64) + np.uint64(1)
+            for k in range(2):
+                h[k] += (blk * mult[k, s0:s0 + 256, None]).sum(axis=0, dtype=np.uint64)
+    key = h[0] ^ (h[1] * np.uint64(0x9E3779B97F4A7C15))
+    order = np.lexsort((np.arange(cells), h[1], key))
+    sk, s1 = key[order], h[1][order]
+    new = np.ones(cells, dtype=bool)
+    new[1:] = (sk[1:] != sk[:-1]) | (s1[1:] != s1[:-1])
+    gid_sorted = np.cumsum(new) - 1
+    gid = np.empty(cells, dtype=np.int64)
+    gid[order] = gid_sorted
+    last = np.zeros(gid_sorted[-1] + 1, dtype=np.int64)
+    np.maximum.at(last, gid, np.arange(cells))
+    if not (a == a[:, last[gid]]).all():                     # a hash collision (never seen): split exactly
+        _, gid = np.unique(a.T, axis=0, return_inverse=True)
+        gid = gid.ravel()
+        last = np.zeros(gid.max() + 1, dtype=np.int64)
+        np.maximum.at(last, gid, np.arange(cells))
+    rank = np.argsort(np.argsort(last))                      # groups ordered by their last cell
+    inverse = rank[gid]
+    rep = np.sort(last)
+    weight = np.bincount(inverse, minlength=rep.size)
+    return rep, inverse, weight
+
+
+def _ward_linkage_weighted(dist_sq, weight):
+    """Ward linkage of points with multiplicities: scipy.cluster.hierarchy.linkage(method='ward')
+    (nearest-neighbour chain, `_ward` distance update, stable sort by height) started from clusters
+    of `weight[i]` coincident points instead of singletons.  dist_sq: square float64 matrix of the
+    plain distances (destroyed).  Returns a linkage matrix over the U points (column 3 counts points, as scipy
+    requires; the heights are those of the weighted problem)."""
+    D = dist_sq
+    n = D.shape[0]
+    size = np.asarray(weight, dtype=np.float64).copy()
+    active = np.ones(n, dtype=bool)
+    # ward distance of two clusters of coincident points (the state scipy's update reaches once the
+    # zero-distance merges are done): d * sqrt(2 n_u n_v / (n_u + n_v)); = d for single points
+    D *= np.sqrt(2.0 * np.outer(size, size) / np.add.outer(size, size))
+    np.fill_diagonal(D, np.inf)
+    merges = np.empty((n - 1, 3))
+    chain = []
+    lowest = 0
+    for k in range(n - 1):
+        if not chain:
+            while not active[lowest]:
+                lowest += 1
+            chain.append(lowest)
+        while True:
+            x = chain[-1]
+            row = D[x]
+            y = int(np.argmin(row))                          # first minimum, as the scan `dist < current_min`
+            if len(chain) > 1 and row[chain[-2]] <= row[y]:
+                y = chain[-2]                                # the previous element is preferred on ties
+            if len(chain) > 1 and y == chain[-2]:
+                break
+            chain.append(y)
+        d_xy = D[x, y]
+        chain.pop()
+        chain.pop()
+        if x > y:
+            x, y = y, x
+        nx, ny = size[x], size[y]
+        merges[k] = (x, y, d_xy)
+        # scipy _ward: sqrt((ni+nx) t dxi^2 + (ni+ny) t dyi^2 - ni t dxy^2), t = 1 / (nx + ny + ni)
+        t = 1.0 / (nx + ny + size)
+        with np.errstate(invalid='ignore'):
+            new = np.sqrt((size + nx) * t * D[x] * D[x] + (size + ny) * t * D[y] * D[y] - size * t * d_xy * d_xy)
+        new[~active] = np.inf
+        new[x] = new[y] = np.inf
+        D[y, :] = new
+        D[:, y] = new
+        D[x, :] = np.inf
+        D[:, x] = np.inf
+        active[x] = False
+        size[y] = nx + ny
+        size[x] = 0.0
+    order = np.argsort(merges[:, 2], kind='mergesort')
+    merges = merges[order]
+    # scipy `label`: union-find over the sorted merges -> ids of the merged clusters, point counts
+    parent = np.arange(2 * n - 1)
+    count = np.ones(2 * n - 1)
+    Z = np.empty((n - 1, 4))
+
+    def find(i):
+        root = i
+        while parent[root] != root:
+            root = parent[root]
+        while parent[i] != root:
+            parent[i], i = root, parent[i]
+        return root
+    for k in range(n - 1):
+        a, b = find(int(merges[k, 0])), find(int(merges[k, 1]))
+        if a > b:
+            a, b = b, a
+        Z[k] = (a, b, merges[k, 2], count[a] + count[b])
+        parent[a] = parent[b] = n + k
+        count[n + k] = count[a] + count[b]
+    return Z
+
+
+def _canonical_labels(labels):
+    """cluster numbers as scipy's cut_tree assigns them: clusters ranked by their first cell"""
+    _, first, inv = np.unique(labels, return_index=True, return_inverse=True)
+    return np.argsort(np.argsort(first))[inv.ravel()]
+
+
 def _get_MPEAR(assignments):
     """libs/utils.py:100-130."""
     assignments = np.asarray(assignments)
     steps, cells = assignments.shape
-    if cells > MAX_LINKAGE_CELLS:
-        raise NotImplementedError(
-            f'the ward linkage runs on the host over {cells * (cells - 1) // 2:.3g} float64 distances; '
-            f'more than {MAX_LINKAGE_CELLS} cells are not supported yet (use the MAP estimator)')
-    pc = _PairCounts(assignments)
-    Z = linkage(pc.dist(), method='ward')
     n_range = _candidate_cluster_numbers(assignments)
     if n_range.size == 0:
         return None
-    cuts = cut_tree(Z, n_clusters=n_range)                   # [cells, candidates]
-    total, same_pairs, same_counts = pc.sums(cuts.T)
+    rep, inverse, weight = _unique_profiles(assignments)
+    if rep.size == cells and cells <= MAX_LINKAGE_CELLS:
+        # no two cells share a profile: the reference's own route over all pairs of cells
+        pc = _PairCounts(assignments)
+        Z = linkage(pc.dist(), method='ward')
+        cuts = cut_tree(Z, n_clusters=n_range)                   # [cells, candidates]
+        total, same_pairs, same_counts = pc.sums(cuts.T)
+    else:
+        if rep.size > MAX_PROFILES:
+            raise NotImplementedError(
+                f'{rep.size} distinct assignment profiles among {cells} cells: the weighted ward linkage holds a '
+                f'square float64 distance matrix on the host and is limited to {MAX_PROFILES} profiles '
+                '(use fewer posterior samples or the MAP estimator)')
+        n_range = n_range[n_range < rep.size]                    # (cut_tree mislabels n_clusters == points)
+        if n_range.size == 0:
+            return None
+        pc = _PairCounts(assignments[:, rep])                    # pairs of distinct profiles
+        Z = _ward_linkage_weighted(pc.dist_square(), weight)
+        cuts_u = cut_tree(Z, n_clusters=n_range)                 # [profiles, candidates]
+        total, same_pairs, same_counts = pc.sums(cuts_u.T, weight)
+        same_pairs = same_pairs + int((weight.astype(np.int64) * (weight.astype(np.int64) - 1) // 2).sum())
+        cuts = cuts_u[inverse]
     with np.errstate(divide='ignore', invalid='ignore'):
         scores = _mpear_scores(total, same_pairs, same_counts, steps, cells)
     best = int(np.argmax(np.where(np.isnan(scores), -np.inf, scores)))   # first of equal scores, as `>`
-    return cuts[:, best].copy()
+    if rep.size == cells and cells <= MAX_LINKAGE_CELLS:
+        return cuts[:, best].copy()
+    return _canonical_labels(cuts[:, best])
 
 
 # --------------------------------------------------------------------- posterior estimator

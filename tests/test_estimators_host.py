@@ -70,3 +70,60 @@ def test_lugsail_psrf_matches_reference():
     np.testing.assert_allclose(ut.get_lugsail_batch_means_est(chains), want, rtol=1e-12)
     assert ut.get_lugsail_batch_means_est([(np.zeros(5), 0)]) == np.inf
     np.testing.assert_allclose(ut.get_cutoff_lugsail(0.1), ref.utils.get_cutoff_lugsail(0.1), rtol=1e-14)
+
+
+def _trace_with_shared_profiles(rng, n, steps, k, movers=0.15):
+    """assignment samples in which most cells never leave their cluster (they share a profile)"""
+    z = rng.integers(0, k, n)
+    moving = rng.random(n) < movers
+    out = np.zeros((steps, n), dtype=int)
+    for s in range(steps):
+        labels = rng.permutation(k + 2)[:k]                  # arbitrary ids, as cluster ids are
+        a = labels[z]
+        scat = moving & (rng.random(n) < 0.3)
+        a[scat] = rng.choice(labels, scat.sum())
+        out[s] = a
+    return out
+
+
+def test_weighted_ward_over_profiles_equals_scipy_over_cells():
+    """The route of large matrices (libs/utils.py::_get_MPEAR): ward linkage of the DISTINCT
+    assignment profiles, started from clusters of their multiplicities, cuts the cells exactly as
+    scipy's linkage over all cells (the reference, libs/utils.py:100-116) -- same heights, same
+    labels for every candidate number of clusters."""
+    from scipy.cluster.hierarchy import cut_tree, linkage
+    from scipy.spatial.distance import pdist, squareform
+    import libs.utils as ut
+    rng = np.random.default_rng(3)
+    for trial in range(8):
+        n, steps, k = int(rng.integers(60, 500)), int(rng.integers(5, 40)), int(rng.integers(2, 7))
+        a = _trace_with_shared_profiles(rng, n, steps, k)
+        d = sum(pdist(a[s][:, None], 'hamming') for s in range(steps)) / steps
+        Z = linkage(d, 'ward')
+        n_range = ut._candidate_cluster_numbers(a)
+        want = cut_tree(Z, n_clusters=n_range)
+        rep, inverse, weight = ut._unique_profiles(a)
+        assert weight.sum() == n and (a[:, rep][:, inverse] == a).all() and rep.size < n
+        du = sum(pdist(a[s][rep][:, None], 'hamming') for s in range(steps)) / steps
+        Zw = ut._ward_linkage_weighted(squareform(du), weight)
+        np.testing.assert_allclose(np.sort(Zw[:, 2]), Z[-(rep.size - 1):, 2], rtol=0, atol=1e-12)
+        n_ok = n_range[n_range < rep.size]          # as _get_MPEAR (cut_tree mislabels n_clusters == points)
+        got = cut_tree(Zw, n_clusters=n_ok)
+        checked = 0
+        for j, c in enumerate(n_ok):
+            applied = rep.size - int(c)                      # merges below the cut
+            if 0 < applied < rep.size - 1 and Zw[applied - 1, 2] >= Zw[applied, 2] - 1e-12:
+                continue                                     # a tie at the cut: either order is a valid dendrogram
+            np.testing.assert_array_equal(ut._canonical_labels(got[inverse][:, j]), want[:, j])
+            checked += 1
+        assert checked >= 1
+
+
+def test_unique_profiles_handles_all_distinct_and_all_equal():
+    import libs.utils as ut
+    a = np.arange(12).reshape(3, 4)
+    rep, inverse, weight = ut._unique_profiles(a)
+    assert rep.tolist() == [0, 1, 2, 3] and inverse.tolist() == [0, 1, 2, 3] and weight.tolist() == [1, 1, 1, 1]
+    b = np.zeros((5, 7), dtype=int)
+    rep, inverse, weight = ut._unique_profiles(b)
+    assert rep.tolist() == [6] and set(inverse.tolist()) == {0} and weight.tolist() == [7]

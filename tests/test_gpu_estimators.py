@@ -181,3 +181,43 @@ def test_run_time_mode():
         assert np.isfinite(r['ML']).all() and (r['ML'] < 0).all()
         k_last = np.unique(r['assignments'][-1]).size
         assert r['params'][-1, :k_last].min() > 0 and not r['params'][-1, k_last:].any()
+
+
+def test_mpear_over_profiles_equals_mpear_over_cells(monkeypatch):
+    """libs/utils.py::_get_MPEAR takes the profile route when cells share assignment profiles; on a
+    matrix small enough for both, it must return the assignment of the all-cells route (scipy
+    linkage + bnpc_mpear_sums over all pairs, the reference's arithmetic)."""
+    import libs.utils as ut
+    from test_estimators_host import _trace_with_shared_profiles
+    rng = np.random.default_rng(17)
+    for n, steps, k in ((900, 30, 5), (2500, 24, 8)):
+        a = _trace_with_shared_profiles(rng, n, steps, k)
+        got = ut._get_MPEAR(a)
+        # the all-cells route: as if no two cells shared a profile
+        monkeypatch.setattr(ut, '_unique_profiles', lambda x: (np.arange(x.shape[1]), np.arange(x.shape[1]),
+                                                               np.ones(x.shape[1], dtype=np.int64)))
+        want = ut._get_MPEAR(a)
+        monkeypatch.undo()
+        np.testing.assert_array_equal(got, want)
+
+
+def test_posterior_estimator_at_100k_cells():
+    """BASELINE config 3 asks for the posterior estimator at 100k cells: the reference's pair vector
+    would hold 5e9 entries per sample.  Simulated traces of 100k cells x 120 samples (20 clusters,
+    8 % of the cells wander): the estimator returns the simulated partition."""
+    import libs.utils as ut
+    rng = np.random.default_rng(5)
+    n, steps, k, m = 100_000, 120, 20, 64
+    z = rng.integers(0, k, n)
+    moving = rng.random(n) < 0.08
+    a = np.zeros((steps, n), dtype=np.int32)
+    for s in range(steps):
+        labels = rng.permutation(k + 3)[:k]
+        row = labels[z]
+        scat = moving & (rng.random(n) < 0.1)
+        row[scat] = rng.choice(labels, scat.sum())
+        a[s] = row
+    params = rng.random((steps, k, m)).astype(np.float32)
+    assign, geno = ut.get_mean_hierarchy_assignment(a, params)
+    assert ut.get_ARI(assign, z) > 0.999
+    assert geno.shape == (m, n)
