@@ -159,6 +159,11 @@ struct GroupChain {
     double fp_prop, fn_prop, fp_fwd, fp_rev, fn_fwd, fn_rev, fp_acc_u, fn_acc_u;
     int loglik_rows;
     bool stats_fresh;
+    // asynchronous scheduler
+    int state, step, sub;                  // CS_*, trace row of the step in hand, wave the chain travels in
+    long long snaps;                       // trace rows snapshot so far (ring slot = snaps % ring)
+    bool theta_direct;                     // more live clusters than a ring row holds: theta rows copied directly
+    cudaEvent_t prewait;                   // event the chain's next wave must wait for (ring slot drained) or NULL
 
     uint64_t seed() const { return s->seed; }
     double random() { return host_random(s->seed, &s->host_ctr); }
@@ -183,6 +188,12 @@ struct Group {
     std::vector<cudaEvent_t> ev_snap, ev_drained;
     long long steps_done, snaps;
     std::vector<bnpc_trace_t*> tr;
+    // asynchronous scheduler: waves (sets of chains that became ready together and travel through
+    // one phase on one stream) and per-(chain, ring slot) drain events
+    struct Wave { cudaStream_t s; cudaEvent_t ev; unsigned long long mask; bool busy; };
+    std::vector<Wave> waves;
+    std::vector<cudaEvent_t> ev_slot;      // [n][ring]: ring slot drained to the host
+    bool lockstep;
 };
 
 static int group_fail(Group* g, const char* what) {
@@ -222,6 +233,9 @@ static int store_list(Group* g, int ci) {
 static int ensure_ids(Group* g, int ci, int need) {
     GroupChain& c = g->ch[ci];
     if (need <= c.w->idcap) return 0;
+    // (the chain itself is idle here; the caller's allocator may reuse the old buffers at once, so
+    // nothing of this chain may still be in flight: recorded launches of OTHER chains are not touched)
+    cudaDeviceSynchronize();
     if (g->grow(g->grow_ctx, ci, BNPC_GROW_IDS, need)) return group_fail(g, "grow(ids) failed");
     if (need > c.w->idcap) return group_fail(g, "cluster id capacity");
     c.stats_fresh = false;                 // S1/S0 were reallocated
@@ -656,9 +670,13 @@ static int snapshot_enqueue(Group* g, int ci, int slot, int step) {
     const int N = c.w->N, M = c.w->M, K = c.K();
     int32_t* dst = g->ring_assign + ((size_t)slot * g->n + ci) * N;
     if (int rc = copy_async(dst, c.w->assign, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToDevice, nullptr)) return rc;
+    c.theta_direct = false;
     if (tr->params_h && step >= tr->params_first) {
         if (K > g->ring_kcap) {
-            if (g->grow(g->grow_ctx, ci, BNPC_GROW_RING_K, K) || K > g->ring_kcap) return group_fail(g, "grow(ring) failed");
+            // more live clusters than a ring row holds: the rows are copied straight from theta once
+            // the phase is done (theta_rows_direct); the ring is not regrown under recorded launches
+            c.theta_direct = true;
+            return 0;
         }
         // sorted ids (libs/MCMC.py:261) behind the statistics' staging area of h_in
         int32_t* h = c.w->h_in + 2 * K + 8;
@@ -672,30 +690,193 @@ static int snapshot_enqueue(Group* g, int ci, int slot, int step) {
     return 0;
 }
 
-// ring slot -> the caller's pinned trace rows, on the copy stream
-static int drain_slot(Group* g, int slot, int step) {
-    for (int ci = 0; ci < g->n; ++ci) {
-        GroupChain& c = g->ch[ci];
-        bnpc_trace_t* tr = g->tr[ci];
-        const int N = c.w->N, M = c.w->M, K = c.K();
-        if (tr->assign_h) {
-            const int32_t* src = g->ring_assign + ((size_t)slot * g->n + ci) * N;
-            CU(cudaMemcpyAsync(tr->assign_h + (size_t)step * tr->assign_stride, src, sizeof(int32_t) * (size_t)N,
-                               cudaMemcpyDeviceToHost, g->sC), "trace copy (assignment)");
+// theta rows of the sorted live ids straight from the chain's theta (synchronous; only for chains
+// with more live clusters than a ring row holds)
+static int theta_rows_direct(Group* g, int ci, int step) {
+    GroupChain& c = g->ch[ci];
+    bnpc_trace_t* tr = g->tr[ci];
+    const int M = c.w->M, K = c.K();
+    if (K > tr->params_kcap) {
+        CU(cudaStreamSynchronize(g->sC), "trace sync");
+        if (g->grow(g->grow_ctx, ci, BNPC_GROW_PARAMS, K) || K > tr->params_kcap) return group_fail(g, "grow(params) failed");
+    }
+    std::vector<int> sorted(c.ids);
+    std::sort(sorted.begin(), sorted.end());
+    float* dst = tr->params_h + (size_t)(step - tr->params_first) * tr->params_kcap * M;
+    for (int j = 0; j < K; ++j)
+        CU(cudaMemcpyAsync(dst + (size_t)j * M, c.w->theta + (size_t)sorted[j] * M, sizeof(float) * M,
+                           cudaMemcpyDeviceToHost, g->sC), "trace copy (theta rows)");
+    CU(cudaStreamSynchronize(g->sC), "trace sync");
+    return 0;
+}
+
+// one chain's ring slot -> its pinned trace rows, on the copy stream
+static int drain_chain(Group* g, int ci, int slot, int step) {
+    GroupChain& c = g->ch[ci];
+    bnpc_trace_t* tr = g->tr[ci];
+    const int N = c.w->N, M = c.w->M, K = c.K();
+    if (tr->assign_h) {
+        const int32_t* src = g->ring_assign + ((size_t)slot * g->n + ci) * N;
+        CU(cudaMemcpyAsync(tr->assign_h + (size_t)step * tr->assign_stride, src, sizeof(int32_t) * (size_t)N,
+                           cudaMemcpyDeviceToHost, g->sC), "trace copy (assignment)");
+    }
+    if (tr->params_h && step >= tr->params_first) {
+        if (c.theta_direct) return theta_rows_direct(g, ci, step);
+        if (K > tr->params_kcap) {
+            CU(cudaStreamSynchronize(g->sC), "trace sync");
+            if (g->grow(g->grow_ctx, ci, BNPC_GROW_PARAMS, K) || K > tr->params_kcap)
+                return group_fail(g, "grow(params) failed");
         }
-        if (tr->params_h && step >= tr->params_first) {
-            if (K > tr->params_kcap) {
-                // the caller regrows its [steps][kcap][M] array (rows already written are kept)
-                CU(cudaStreamSynchronize(g->sC), "trace sync");
-                if (g->grow(g->grow_ctx, ci, BNPC_GROW_PARAMS, K) || K > tr->params_kcap)
-                    return group_fail(g, "grow(params) failed");
+        const float* src = g->ring_theta + ((size_t)slot * g->n + ci) * (size_t)g->ring_kcap * M;
+        float* dst = tr->params_h + (size_t)(step - tr->params_first) * tr->params_kcap * M;
+        CU(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)K * M, cudaMemcpyDeviceToHost, g->sC),
+           "trace copy (theta)");
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ asynchronous scheduler
+// Chains do not wait for each other: whenever the GPU work a chain waits for is done, the host
+// advances THAT chain (decisions of the finished phase, recording of the next one).  The chains that
+// became ready in the same polling round and enter the same kind of phase form a WAVE: their
+// launches are merged (bnpc_batch.cuh) and go out on one stream of a pool, followed by one event the
+// members wait for.  Waves of different kinds (Gibbs epochs, split-merge moves, parameter phases) and
+// of different rounds run side by side on the GPU.
+enum { CS_START = 0, CS_WAIT_SM, CS_WAIT_GIBBS, CS_WAIT_P2, CS_FINISHED };
+enum { KIND_GIBBS = 0, KIND_SM = 1, KIND_P2 = 2, KIND_NONE = 3 };
+
+static int enqueue_phase2(Group* g, int ci) {
+    GroupChain& c = g->ch[ci];
+    if (!g->mv.fix_assign && c.random() < g->mv.dpa_prob) update_dp_alpha(c);
+    const bool do_err = c.s->learning && c.random() < g->mv.error_prob;
+    if (int rc = params_enqueue(g, ci, do_err)) return rc;
+    const int slot = (int)(c.snaps % g->ring);
+    c.prewait = g->ev_slot[(size_t)ci * g->ring + slot];       // the slot must have been drained
+    return snapshot_enqueue(g, ci, slot, c.step);
+}
+
+// the chain's pending GPU work is done: decide, record what comes next; *kind = phase recorded
+static int advance(Group* g, int ci, int end_step, int* kind) {
+    GroupChain& c = g->ch[ci];
+    *kind = KIND_NONE;
+    g_rec.cur = ci;
+    for (;;) {
+        switch (c.state) {
+            case CS_START:
+                if (c.step >= end_step) { c.state = CS_FINISHED; return 0; }
+                if (g->mv.fix_assign) {
+                    if (int rc = enqueue_phase2(g, ci)) return rc;
+                    c.state = CS_WAIT_P2; *kind = KIND_P2;
+                    return 0;
+                }
+                if (c.random() < g->mv.sm_prob) {
+                    if (int rc = sm_enqueue(g, ci)) return rc;
+                    c.state = CS_WAIT_SM; *kind = KIND_SM;
+                } else {
+                    gibbs_begin(g, c);
+                    if (int rc = gibbs_enqueue(g, ci)) return rc;
+                    c.state = CS_WAIT_GIBBS; *kind = KIND_GIBBS;
+                }
+                return 0;
+            case CS_WAIT_SM:
+                if (int rc = sm_after(g, ci)) return rc;            // an accepted move records its write-back
+                if (int rc = enqueue_phase2(g, ci)) return rc;
+                c.state = CS_WAIT_P2; *kind = KIND_P2;
+                return 0;
+            case CS_WAIT_GIBBS: {
+                int done = 0;
+                if (int rc = gibbs_after(g, ci, &done)) return rc;
+                if (!done) {
+                    if (int rc = gibbs_enqueue(g, ci)) return rc;
+                    *kind = KIND_GIBBS;
+                    return 0;
+                }
+                if (int rc = enqueue_phase2(g, ci)) return rc;
+                c.state = CS_WAIT_P2; *kind = KIND_P2;
+                return 0;
             }
-            const float* src = g->ring_theta + ((size_t)slot * g->n + ci) * (size_t)g->ring_kcap * M;
-            float* dst = tr->params_h + (size_t)(step - tr->params_first) * tr->params_kcap * M;
-            CU(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)K * M, cudaMemcpyDeviceToHost, g->sC),
-               "trace copy (theta)");
+            case CS_WAIT_P2: {
+                bnpc_trace_t* tr = g->tr[ci];
+                double ml, lprior;
+                params_after(g, c, &ml, &lprior, true);
+                tr->ml[c.step] = ml;
+                tr->map[c.step] = ml + lprior;
+                tr->alpha[c.step] = c.s->DP_a;
+                tr->fn[c.step] = c.s->FN;
+                tr->fp[c.step] = c.s->FP;
+                if (tr->n_clusters) tr->n_clusters[c.step] = c.K();
+                const int slot = (int)(c.snaps % g->ring);
+                // (the wave's event has completed: the copy stream may read the slot at once)
+                if (int rc = drain_chain(g, ci, slot, c.step)) return rc;
+                CU(cudaEventRecord(g->ev_slot[(size_t)ci * g->ring + slot], g->sC), "record(drained)");
+                c.snaps += 1;
+                c.step += 1;
+                c.state = CS_START;
+                break;                                               // straight on to the next step
+            }
+            default:
+                return 0;
         }
     }
+}
+
+static int group_run_async(Group* g, int step0, int n_steps) {
+    const int end_step = step0 + n_steps;
+    const int n = g->n;
+    for (int ci = 0; ci < n; ++ci) {
+        GroupChain& c = g->ch[ci];
+        c.state = CS_START; c.step = step0; c.sub = -1; c.prewait = nullptr; c.theta_direct = false;
+    }
+    int finished = 0;
+    unsigned long long ready = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+    long long idle_spins = 0;
+    while (finished < n) {
+        // waves whose event has completed release their members
+        for (Group::Wave& wv : g->waves) {
+            if (!wv.busy) continue;
+            const cudaError_t q = cudaEventQuery(wv.ev);
+            if (q == cudaErrorNotReady) continue;
+            if (q != cudaSuccess) return fail("cudaEventQuery", q);
+            ready |= wv.mask;
+            wv.busy = false;
+        }
+        if (!ready) {
+            if (++idle_spins > (1ll << 34)) return group_fail(g, "scheduler made no progress");
+            continue;
+        }
+        idle_spins = 0;
+        unsigned long long by_kind[3] = {0ull, 0ull, 0ull};
+        g_rec.on = true;
+        int rc = 0;
+        for (int ci = 0; ci < n && !rc; ++ci) {
+            if (!((ready >> ci) & 1ull)) continue;
+            int kind = KIND_NONE;
+            rc = advance(g, ci, end_step, &kind);
+            if (kind != KIND_NONE) by_kind[kind] |= 1ull << ci;
+            else if (!rc && g->ch[ci].state == CS_FINISHED) ++finished;
+        }
+        g_rec.on = false;
+        ready = 0ull;
+        if (rc) { for (int ci = 0; ci < GROUP_MAX; ++ci) g_rec.q[ci].clear(); return rc; }
+        for (int k = 0; k < 3; ++k) {
+            if (!by_kind[k]) continue;
+            Group::Wave* wv = nullptr;
+            for (Group::Wave& cand : g->waves) if (!cand.busy) { wv = &cand; break; }
+            if (!wv) return group_fail(g, "no free wave");
+            for (int ci = 0; ci < n; ++ci) {
+                GroupChain& c = g->ch[ci];
+                if (((by_kind[k] >> ci) & 1ull) && c.prewait) {
+                    CU(cudaStreamWaitEvent(wv->s, c.prewait, 0), "wait(drained)");
+                    c.prewait = nullptr;
+                }
+            }
+            if ((rc = recorder_flush(wv->s, by_kind[k]))) return rc;
+            CU(cudaEventRecord(wv->ev, wv->s), "record(wave)");
+            wv->mask = by_kind[k];
+            wv->busy = true;
+        }
+    }
+    g->steps_done += n_steps;
     return 0;
 }
 
@@ -735,7 +916,8 @@ static int phase2_and_trace(Group* g, int step, bool with_moves) {
         if (tr->n_clusters) tr->n_clusters[step] = c.K();
     }
     CU(cudaStreamWaitEvent(g->sC, g->ev_snap[slot], 0), "wait(snapshot)");
-    if ((rc = drain_slot(g, slot, step))) return rc;
+    for (int ci = 0; ci < g->n; ++ci)
+        if ((rc = drain_chain(g, ci, slot, step))) return rc;
     CU(cudaEventRecord(g->ev_drained[slot], g->sC), "record(drained)");
     g->snaps += 1;
     return 0;
@@ -887,6 +1069,17 @@ bnpc_group_t* bnpc_group_create(int n, bnpc_chain_t* const* ws, bnpc_chain_state
         return nullptr;
     }
     cudaEventRecord(g->evA, g->sA);
+    g->lockstep = getenv("BNPC_LOCKSTEP") != nullptr;        // the phase-synchronous driver, for comparison
+    // waves: every chain is in at most one, and a round opens at most three
+    g->waves.resize((size_t)n + 3);
+    for (Group::Wave& wv : g->waves) {
+        wv.mask = 0ull; wv.busy = false;
+        if (cudaStreamCreateWithFlags(&wv.s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&wv.ev, cudaEventDisableTiming) != cudaSuccess) {
+            bad_arg("wave stream / event");
+            return nullptr;
+        }
+    }
     return reinterpret_cast<bnpc_group_t*>(g);
 }
 
@@ -906,6 +1099,12 @@ int bnpc_group_set_ring(bnpc_group_t* gp, int slots, int32_t* ring_assign, float
         g->ev_drained.push_back(b);
     }
     g->ring = slots; g->ring_assign = ring_assign; g->ring_theta = ring_theta; g->ring_kcap = kcap;
+    while ((int)g->ev_slot.size() < g->n * slots) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bad_arg("cudaEventCreate");
+        cudaEventRecord(e, g->sC);
+        g->ev_slot.push_back(e);
+    }
     return 0;
 }
 
@@ -929,6 +1128,7 @@ static int group_leave(bnpc::Group* g, int rc) {
     if (!rc && e != cudaSuccess) rc = fail("trace drain", e);
     cudaStreamSynchronize(g->sB);
     cudaStreamSynchronize(g->sA);
+    for (Group::Wave& wv : g->waves) { cudaStreamSynchronize(wv.s); wv.busy = false; }
     for (int ci = 0; ci < g->n; ++ci) {
         GroupChain& c = g->ch[ci];
         if (int r2 = store_list(g, ci)) { if (!rc) rc = r2; }
@@ -942,7 +1142,11 @@ int bnpc_group_run(bnpc_group_t* gp, int step0, int n_steps) {
     Group* g = reinterpret_cast<Group*>(gp);
     if (int rc = group_enter(g)) return rc;
     int rc = 0;
-    for (int s = 0; s < n_steps && !rc; ++s) rc = group_step(g, step0 + s);
+    if (g->lockstep) {
+        for (int s = 0; s < n_steps && !rc; ++s) rc = group_step(g, step0 + s);
+    } else {
+        rc = group_run_async(g, step0, n_steps);
+    }
     return group_leave(g, rc);
 }
 
@@ -962,6 +1166,8 @@ void bnpc_group_destroy(bnpc_group_t* gp) {
     cudaEventDestroy(g->evB);
     for (cudaEvent_t e : g->ev_snap) cudaEventDestroy(e);
     for (cudaEvent_t e : g->ev_drained) cudaEventDestroy(e);
+    for (cudaEvent_t e : g->ev_slot) cudaEventDestroy(e);
+    for (Group::Wave& wv : g->waves) { cudaStreamSynchronize(wv.s); cudaEventDestroy(wv.ev); cudaStreamDestroy(wv.s); }
     delete g;
 }
 

@@ -85,7 +85,7 @@ class ChainGroup:
                                           self.sA.cuda_stream, self.sB.cuda_stream, self.sC.cuda_stream)
         N, M = self.models[0].cells_total, self.models[0].muts_total
         self.ring_assign = torch.zeros((RING_SLOTS, n, N), dtype=torch.int32, device=self.device)
-        self.ring_kcap = max(64, 2 * max(len(m.cells_per_cluster) for m in self.models))
+        self.ring_kcap = max(128, 2 * max(len(m.cells_per_cluster) for m in self.models))
         self.ring_theta = torch.zeros((RING_SLOTS, n, self.ring_kcap, M), dtype=torch.float32, device=self.device)
         torch.cuda.synchronize(self.device)
         self.L.group_set_ring(self.handle, RING_SLOTS, self.ring_assign.data_ptr(), self.ring_theta.data_ptr(),

@@ -124,12 +124,14 @@ def test_group_extends_and_resumes():
 
 def test_recorded_launches_merge_across_chains(monkeypatch):
     """the launches of a group step grow far slower than the number of chains: a step of 8 chains
-    in one lockstep group costs one Gibbs sequence + one split-merge sequence + one parameter
-    sequence, whoever drew what"""
+    in one phase-synchronous group (BNPC_LOCKSTEP) costs one Gibbs sequence + one split-merge
+    sequence + one parameter sequence, whoever drew what; the default asynchronous scheduler merges
+    the chains that become ready together and still stays well below the launches of 8 single chains"""
     from bnpc_b200 import _lib
     import libs.MCMC as mcmc
     from libs.MCMC import run_chains
     monkeypatch.setattr(mcmc, 'GROUP_SIZE', 8)
+    monkeypatch.setenv('BNPC_LOCKSTEP', '1')
     data, z = simulate(3000, 200, k_true=6, miss=0.1, seed=2)
     assign = [int(v) for v in z]
     moves = _moves()
@@ -141,6 +143,11 @@ def test_recorded_launches_merge_across_chains(monkeypatch):
         counts[n] = (_lib.launch_count() - before) / 30
     assert counts[8] < 4 * counts[1], counts            # 8 chains for far less than 8x the launches
     assert counts[8] / 8 < 25, counts                   # launches per chain-step
+    monkeypatch.delenv('BNPC_LOCKSTEP')
+    chains = _chains(data, True, [0.25, 0.25], moves, 30, list(range(50, 58)), assign)
+    before = _lib.launch_count()
+    run_chains(chains)
+    assert (_lib.launch_count() - before) / 30 < 0.85 * 8 * counts[1], counts
 
 
 def test_parallel_sweep_equals_single_sequencer():
@@ -159,3 +166,20 @@ def test_parallel_sweep_equals_single_sequencer():
     run_chains(ser)
     for a, b in zip(par, ser):
         _same(a, b, f'seed {seeds[a.no - 1]}', exact=True)
+
+
+def test_lockstep_driver_equals_asynchronous_scheduler(monkeypatch):
+    """the phase-synchronous driver (BNPC_LOCKSTEP=1) and the default asynchronous scheduler issue
+    the same per-chain work in different interleavings: identical traces"""
+    from libs.MCMC import run_chains
+    data, z = simulate(2500, 160, k_true=6, miss=0.1, seed=4)
+    assign = [int(v) for v in z]
+    moves = _moves(sm_prob=0.4)
+    seeds = [21, 22, 23, 24, 25]
+    a = _chains(data, True, [0.25, 0.25], moves, 25, seeds, assign)
+    run_chains(a)
+    monkeypatch.setenv('BNPC_LOCKSTEP', '1')
+    b = _chains(data, True, [0.25, 0.25], moves, 25, seeds, assign)
+    run_chains(b)
+    for x, y in zip(a, b):
+        _same(x, y, f'chain {x.no}', exact=True)
