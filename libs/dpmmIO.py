@@ -25,12 +25,54 @@ def _is_matrix_value(token):
         return token == ' '
 
 
-def load_data(in_file, transpose=True, get_names=False):
-    """libs/dpmmIO.py:27-98.  Text matrix of 0 | 1 | 2 (homozygous, read as 1) | 3 or empty (missing),
-    separated by tabs, commas or blanks, with an optional header row and an optional index column.
-    Returns float64 [cells, mutations] with NaN for missing (after the default transpose: files are
-    mutations x cells), i.e. what the model constructors take; they pack it into bit-planes on the
-    device (`bnpc_pack_planes`)."""
+CACHE_SUFFIX = '.bnpc_planes.npz'
+
+
+def _cache_path(in_file):
+    return in_file + CACHE_SUFFIX
+
+
+def _load_cache(in_file):
+    """The packed copy of a matrix file written by an earlier load (two bit-planes, the wire format
+    of the kernels: plane1 bit = entry is 1, plane0 bit = entry is 0, neither = missing) -- valid
+    while the text file has the size and modification time recorded in it."""
+    path = _cache_path(in_file)
+    if os.environ.get('BNPC_NO_CACHE') or not os.path.exists(path):
+        return None
+    try:
+        st = os.stat(in_file)
+        with np.load(path, allow_pickle=False) as z:
+            if int(z['src_size']) != st.st_size or int(z['src_mtime_ns']) != st.st_mtime_ns:
+                return None
+            rows, cols = (int(v) for v in z['shape'])
+            one = np.unpackbits(z['plane1'], axis=1, count=cols).astype(bool)
+            zero = np.unpackbits(z['plane0'], axis=1, count=cols).astype(bool)
+            values = np.full((rows, cols), np.nan)
+            values[one] = 1.0
+            values[zero] = 0.0
+            return values, (z['row_names'], z['col_names'])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def _save_cache(in_file, values, names):
+    """values: the parsed file matrix (rows x columns as in the file, {0, 1, NaN})"""
+    if os.environ.get('BNPC_NO_CACHE'):
+        return
+    try:
+        st = os.stat(in_file)
+        tmp = _cache_path(in_file) + f'.tmp{os.getpid()}'
+        with open(tmp, 'wb') as f:
+            np.savez(f, plane1=np.packbits(values == 1, axis=1), plane0=np.packbits(values == 0, axis=1),
+                     shape=np.array(values.shape), src_size=st.st_size, src_mtime_ns=st.st_mtime_ns,
+                     row_names=np.asarray(names[0]).astype(str), col_names=np.asarray(names[1]).astype(str))
+        os.replace(tmp, _cache_path(in_file))
+    except OSError:                                          # read-only input directory: no cache
+        pass
+
+
+def _parse_matrix_file(in_file):
+    """the text parse of libs/dpmmIO.py:27-86 -> (values rows x columns as in the file, names)"""
     with open(in_file, 'r') as f:
         head = [f.readline().strip() for _ in range(5)]
     head = [h for h in head if h]
@@ -42,13 +84,32 @@ def load_data(in_file, transpose=True, get_names=False):
     df = pd.read_csv(in_file, sep=sep, index_col=0 if index_col else None, header=0 if header_row else None,
                      na_values=[3, ' '] if (index_col and header_row) else None)
     df = df.astype(float)
-    if transpose:
-        df = df.T
     values = df.values.copy()
     values[values == 3] = np.nan
     values[values == 2] = 1
+    return values, (df.index.values, df.columns.values)
+
+
+def load_data(in_file, transpose=True, get_names=False):
+    """libs/dpmmIO.py:27-98.  Text matrix of 0 | 1 | 2 (homozygous, read as 1) | 3 or empty (missing),
+    separated by tabs, commas or blanks, with an optional header row and an optional index column.
+    Returns float64 [cells, mutations] with NaN for missing (after the default transpose: files are
+    mutations x cells), i.e. what the model constructors take; they pack it into bit-planes on the
+    device (`bnpc_pack_planes`).  The parse of a 100k x 1k text file dominates the start-up of a
+    run: the parsed matrix is kept next to the input as two packed bit-planes (`<file>.bnpc_planes.npz`,
+    1/32 of the float64 size) and read back from there while the text file is unchanged
+    (BNPC_NO_CACHE=1 switches that off)."""
+    cached = _load_cache(in_file)
+    if cached is None:
+        values, names = _parse_matrix_file(in_file)
+        _save_cache(in_file, values, names)
+    else:
+        values, names = cached
+    row_names, col_names = names
+    if transpose:
+        values, row_names, col_names = values.T.copy(), col_names, row_names
     if get_names:
-        return values, (df.index.values, df.columns.values)
+        return values, (np.asarray(row_names), np.asarray(col_names))
     return values
 
 

@@ -100,3 +100,35 @@ def test_termination_and_writers(tmp_path):
                                             'genotypes_cont_MAP_mean.tsv']
     io.save_ARI(inferred, [0, 1], str(tmp_path))
     assert float(pd.read_csv(tmp_path / 'ARI.txt', sep='\t')['ARI'][0]) == 1.0
+
+
+def test_packed_cache_replaces_the_text_parse(tmp_path, monkeypatch):
+    """the loader keeps the parsed matrix next to the input as two packed bit-planes and reads it
+    back while the text file is unchanged"""
+    rng = np.random.default_rng(2)
+    mat = rng.choice([0, 1, 2, 3], size=(11, 37), p=[0.5, 0.3, 0.05, 0.15])
+    path = str(tmp_path / 'm.csv')
+    _write(path, mat, '\t', True, True)
+    first, names = io.load_data(path, transpose=True, get_names=True)
+    assert os.path.exists(path + io.CACHE_SUFFIX)
+    monkeypatch.setattr(io.pd, 'read_csv', lambda *a, **k: (_ for _ in ()).throw(AssertionError('text parse')))
+    again, names2 = io.load_data(path, transpose=True, get_names=True)
+    np.testing.assert_array_equal(first, again)
+    assert list(names[0]) == list(names2[0]) and list(names[1]) == list(names2[1])
+    np.testing.assert_array_equal(io.load_data(path, transpose=False), first.T)
+    monkeypatch.undo()
+    # a changed input invalidates the cache
+    mat2 = mat.copy()
+    mat2[0, 0] = 1 - min(mat2[0, 0], 1)
+    _write(path, mat2, '\t', True, True)
+    os.utime(path, ns=(os.stat(path).st_atime_ns, os.stat(path).st_mtime_ns + 10 ** 9))
+    changed = io.load_data(path, transpose=True)
+    want = mat2.T.astype(float)
+    want[want == 3] = np.nan
+    want[want == 2] = 1
+    np.testing.assert_array_equal(changed, want)
+    # and it can be switched off
+    monkeypatch.setenv('BNPC_NO_CACHE', '1')
+    os.remove(path + io.CACHE_SUFFIX)
+    io.load_data(path)
+    assert not os.path.exists(path + io.CACHE_SUFFIX)
