@@ -55,17 +55,25 @@ def _load_cache(in_file):
         return None
 
 
+def _storable(names):
+    a = np.asarray(names)
+    return a if a.dtype.kind in 'iuf' else a.astype(str)
+
+
 def _save_cache(in_file, values, names):
     """values: the parsed file matrix (rows x columns as in the file, {0, 1, NaN})"""
     if os.environ.get('BNPC_NO_CACHE'):
         return
     try:
+        # a directory marked read-only stays untouched (also for root, whom the kernel would let write)
+        if not os.stat(os.path.dirname(os.path.abspath(in_file))).st_mode & 0o200:
+            return
         st = os.stat(in_file)
         tmp = _cache_path(in_file) + f'.tmp{os.getpid()}'
         with open(tmp, 'wb') as f:
             np.savez(f, plane1=np.packbits(values == 1, axis=1), plane0=np.packbits(values == 0, axis=1),
                      shape=np.array(values.shape), src_size=st.st_size, src_mtime_ns=st.st_mtime_ns,
-                     row_names=np.asarray(names[0]).astype(str), col_names=np.asarray(names[1]).astype(str))
+                     row_names=_storable(names[0]), col_names=_storable(names[1]))
         os.replace(tmp, _cache_path(in_file))
     except OSError:                                          # read-only input directory: no cache
         pass
