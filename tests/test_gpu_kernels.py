@@ -322,3 +322,26 @@ def test_rg_scan_matches_the_serial_scan(L, nf, spread):
     torch.cuda.synchronize()
     np.testing.assert_array_equal(half_d.cpu().numpy(), half.astype(np.int32))
     np.testing.assert_allclose(lq_d.cpu().numpy(), lq_want, rtol=1e-12, atol=1e-300)
+
+
+def test_device_beta_variates_follow_scipy(L):
+    """production mode: bnpc_beta_rows samples theta ~ Beta(p + S1, q + S0) on the device (Philox +
+    Marsaglia-Tsang, libs/CRP.py:172-175,183-188 draw them from numpy); Kolmogorov-Smirnov against
+    scipy for the shapes the model uses (sparse prior, flat prior, well-populated clusters)."""
+    from scipy.stats import beta, kstest
+    n = 200_000
+    for p, q, s1, s0 in ((0.25, 0.25, 0, 0), (1.0, 1.0, 0, 0), (0.25, 0.25, 3, 1), (1.0, 1.0, 400, 4000)):
+        S1 = torch.full((1, n), s1, dtype=torch.int32, device='cuda')
+        S0 = torch.full((1, n), s0, dtype=torch.int32, device='cuda')
+        out = torch.zeros((1, n), dtype=torch.float32, device='cuda')
+        L.beta_rows(S1.data_ptr(), S0.data_ptr(), 1, n, p, q, None, 1234, 77, out.data_ptr(), None,
+                    torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        x = out.cpu().numpy().ravel().astype(np.float64)
+        assert x.min() >= 1e-5 * 0.999 and x.max() <= 1 - 1e-5 * 0.999
+        inner = x[(x > 2e-5) & (x < 1 - 2e-5)]                       # the clipped mass sits on the two bounds
+        dist = beta(p + s1, q + s0)
+        lo, hi = dist.cdf(2e-5), dist.cdf(1 - 2e-5)
+        stat = kstest(inner, lambda v: (dist.cdf(v) - lo) / (hi - lo))
+        assert stat.pvalue > 1e-4, (p, q, s1, s0, stat)
+        assert abs((x <= 1.5e-5).mean() - dist.cdf(1e-5)) < 5e-3
