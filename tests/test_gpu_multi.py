@@ -30,4 +30,11 @@ def test_traces_do_not_depend_on_the_rank(tmp_path):
     for key in a.files:
         if key in ('n_chains', 'world'):
             continue
-        np.testing.assert_array_equal(a[key], b[key], err_msg=key)
+        x, y = a[key], b[key]
+        if key.endswith('_params'):
+            # the gather pads the cluster axis to the largest K of ALL chains (libs/utils.py:206-223 does
+            # the same when it concatenates chains)
+            k = min(x.shape[1], y.shape[1])
+            assert not x[:, k:].any() and not y[:, k:].any(), key
+            x, y = x[:, :k], y[:, :k]
+        np.testing.assert_array_equal(x, y, err_msg=key)

@@ -34,7 +34,11 @@ def main():
                                       FN_mean=0.2, FN_sd=0.1)
     mcmc = MCMC(model, sm_prob=0.33, dpa_prob=0.5, error_prob=0.1, sm_ratios=[0.75, 0.25], sm_steps=3)
     mcmc.run((args.steps, args.steps // 4), 42, n=args.chains, verbosity=0, assign=[int(v) for v in z])
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
     if rank != 0:
+        _shutdown(world)
         return
     out = {}
     for c, r in enumerate(mcmc.get_results()):
@@ -43,6 +47,14 @@ def main():
         out[f'chain{c}_burn_in'] = np.asarray(r['burn_in'])
     np.savez(args.out, n_chains=len(mcmc.get_results()), world=world, **out)
     print(f'{len(mcmc.get_results())} chains from {world} rank(s) -> {args.out}')
+    _shutdown(world)
+
+
+def _shutdown(world):
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == '__main__':
