@@ -464,7 +464,11 @@ def run_gpu(args, cfg):
     value, e2e = _rate(total_chains, K, med_dev), _rate(total_chains, K, med_e2e)
 
     # per-kernel device times: CUDA events around EVERY launch, a separate untimed pass
+    # (phase-synchronous driver on one stream for this pass: launches of different chains merge and
+    # nothing overlaps, so an event pair brackets exactly one launch)
+    os.environ['BNPC_LOCKSTEP'] = os.environ['BNPC_ONE_STREAM'] = '1'
     _, _, ex_prof = bench.window(cpg, W, K, False, profile=True, group_size=cpg)
+    del os.environ['BNPC_LOCKSTEP'], os.environ['BNPC_ONE_STREAM']
     extras = {}
     if not args.no_extras:
         s_ms, s_l, _ = bench.repeat(1, W, K, min(R, 3), host_assign=True)
@@ -512,9 +516,10 @@ def run_gpu(args, cfg):
         gpu_launches=int(np.median(launches)), launches_per_chain_step=float(np.median(launches)) / (K * total_chains),
         roofline=roof, roofline_likelihood=roof_ll, kernels=ktab,
         device_time=dict(sum_of_kernel_ms_per_step=dev_ms_per_step, wall_ms_per_step=med_dev / K,
-                         note='sum of the per-launch device times (profiling pass: launches serialised by their '
-                              'events) against the wall time of a step of the timed windows; the two streams overlap '
-                              'Gibbs and split-merge kernels, so sum > wall is possible'),
+                         note='sum of the per-launch device times of a step of all chains of the GPU (profiling pass: '
+                              'phase-synchronous driver on ONE stream, every launch between its own pair of events) '
+                              'against the wall time of such a step in the timed windows, where the waves of the '
+                              'asynchronous scheduler overlap on the GPU (sum > wall)'),
         sweep=ex_prof['sweep'], clocks=clocks, **extras)
     if not args.no_extras and world == 1:
         out['other_configs'] = other_configs(args, dev)

@@ -1932,7 +1932,10 @@ __device__ __forceinline__ void group_members_kernel(const int32_t* __restrict__
 __device__ __forceinline__ void suffstat_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
                 const int32_t* __restrict__ members, const int32_t* __restrict__ seg_off,
                 int32_t* __restrict__ S1, int32_t* __restrict__ S0, int wc_log2, int n_wblk, int chunk) {
-    __shared__ int cnt[2][32][32];
+    // [plane][word column][bit], rows padded to 33: the 32 lanes of a warp hold 32 different word
+    // columns and add to the SAME bit index at the same time -- unpadded that is one bank for all of
+    // them (ncu: 18 M shared-memory bank conflicts per launch of 4 chains)
+    __shared__ int cnt[2][32][33];
     // blockIdx.y = segment * n_wblk + word block (blockIdx.z is the chain of a batched launch)
     const int r = blockIdx.y / n_wblk, wblk = blockIdx.y % n_wblk;
     const int beg = seg_off[r] + blockIdx.x * chunk;
@@ -1941,7 +1944,7 @@ __device__ __forceinline__ void suffstat_kernel(const uint32_t* __restrict__ x1,
     const int wc = 1 << wc_log2;
     const int col = threadIdx.x & (wc - 1), rsub = threadIdx.x >> wc_log2, rstep = SS_THREADS >> wc_log2;
     const int w = wblk * 32 + col;
-    for (int i = threadIdx.x; i < 2 * 32 * 32; i += SS_THREADS) (&cnt[0][0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 2 * 32 * 33; i += SS_THREADS) (&cnt[0][0][0])[i] = 0;
     __syncthreads();
     if (w < W) {
         uint32_t a1[8], a0[8];
