@@ -256,14 +256,12 @@ def measured_peaks():
 
 def ncu_traffic():
     """DRAM bytes per launch of the profiled kernels (ncu --set full captures summarised under
-    profiles/): {kernel: bytes} or {}."""
-    for name in ('r2_traffic.json', 'r1_traffic.json'):
-        try:
-            with open(os.path.join(ROOT, 'profiles', name)) as f:
-                return json.load(f)
-        except Exception:
-            continue
-    return {}
+    profiles/): {kernel: {bytes, chains}} or {}."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')) as f:
+            return {k: v for k, v in json.load(f).items() if isinstance(v, dict)}
+    except Exception:
+        return {}
 
 
 class Bench:
@@ -411,7 +409,11 @@ def roofline_of(name, row, work, peaks, traffic):
     sec = row['avg_launch_us'] * 1e-6
     base = name.split('<')[0]
     out = dict(kernel=name, avg_launch_us=row['avg_launch_us'], chains_per_launch=chains, peak_source=src,
-               share_of_device_time=row['share_of_device_time'], traffic=traffic.get(base))
+               share_of_device_time=row['share_of_device_time'])
+    cap = traffic.get(base)
+    # DRAM bytes of an ncu capture of this kernel, scaled from the chains of the captured launch to
+    # the chains per launch measured here (chains of one launch share the bit-planes in L2)
+    out['traffic'] = cap['bytes'] * chains / cap['chains'] if cap else None
     if base == 'll_matrix_i8_kernel':
         flops = 4.0 * N * M * K * chains
         ach = flops / sec / 1e12

@@ -5,6 +5,7 @@
     profile_summary.py kernels  <report.ncu-rep> <out.md> "<command line that produced it>"
 """
 import collections
+import re
 import csv
 import io
 import subprocess
@@ -24,6 +25,10 @@ def launches(path, out, cmd):
         u = r[ui]
         v = v / 1e3 if u == 'ns' else v * 1e3 if u == 'ms' else v * 1e6 if u == 's' else v
         k = r[ki].split('(')[0].replace('void ', '')
+        # every kernel of the library runs behind the generic chain-batched wrapper: name the body
+        m = re.search(r'batched_kernel(?:_nb)?<&\(?(?:void )?([\w:]+(?:<[^>]*>)?)', r[ki])
+        if m:
+            k = m.group(1)
         agg[k][0] += 1
         agg[k][1] += v
         agg[k][2] = max(agg[k][2], v)
