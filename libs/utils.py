@@ -366,8 +366,15 @@ def _geno_error_rates(geno, data):
 
 
 def _get_latents_posterior_chain(result, data):
+    """libs/utils.py:224-241.  The theta trace of a chain starts at the first step after burn-in
+    (libs/MCMC.py:261-282) while the other traces keep their burn-in rows; the reference slices BOTH
+    by burn_in here (`--single_chains`), which pairs assignment rows with the theta rows of burn_in
+    steps later and runs off the end once burn_in > steps / 2.  This version pairs them row by row."""
     burn_in = result['burn_in']
-    assign, geno = get_mean_hierarchy_assignment(result['assignments'][burn_in:], result['params'][burn_in:])
+    params = result['params']
+    if params.shape[0] != result['assignments'].shape[0] - burn_in:
+        params = params[burn_in:]                            # a trace that does keep its burn-in rows
+    assign, geno = get_mean_hierarchy_assignment(result['assignments'][burn_in:], params)
     fn_geno, fp_geno = _geno_error_rates(geno, data)
     return {'a': _get_posterior_avg(result['DP_alpha'][burn_in:]), 'assignment': assign, 'genotypes': geno,
             'FN': _get_posterior_avg(result['FN'][burn_in:]), 'FP': _get_posterior_avg(result['FP'][burn_in:]),
