@@ -15,7 +15,7 @@ _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_HERE, 'libbnpc_b200.so')
 SOURCES = [os.path.join(_HERE, 'csrc', 'bnpc_kernels.cu')]
 # every header of the translation unit: editing any of them makes the library stale
-HEADERS = sorted(glob.glob(os.path.join(_HERE, 'csrc', '*.cuh'))) + [os.path.join(_ROOT, 'include', 'bnpc_b200.h')]
+HEADERS = sorted(glob.glob(os.path.join(_HERE, 'csrc', '*.cuh'))) + sorted(glob.glob(os.path.join(_ROOT, 'include', '*.h')))
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-fmad=false', '-std=c++17', '-shared', '-Xcompiler', '-fPIC']
@@ -153,7 +153,6 @@ SIGNATURES = {
     'bnpc_cocluster_counts': [_P, _I, _I, _P, _P],
     'bnpc_mpear_sums': [_P, _I, _P, _I, _P, _P],
     'bnpc_mpear_sums_weighted': [_P, _I, _P, _I, _P, _P, _P],
-    'bnpc_debug_set_trace': [_P],
     'bnpc_ll_matrix_i8': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _D, _P, _I, _P],
     'bnpc_gibbs_options': [_P, _I, _I, _P, _P, _P, _P, _I, _D, _D, _I, _D, _P],
     'bnpc_gibbs_exact': [_P, _P, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _D, _D, _P, _P, _P],
@@ -233,6 +232,10 @@ class _Lib:
                                         C.POINTER(C.POINTER(Trace)), C.POINTER(Moves), GROW_FN, _P, _P, _P, _P]
         d.bnpc_group_destroy.restype = None
         d.bnpc_group_destroy.argtypes = [_P]
+        # debugging hook (include/bnpc_b200_debug.h; tools/tc_trace.py), not part of the drop-in ABI
+        d.bnpc_debug_set_trace.argtypes = [_P]
+        d.bnpc_debug_set_trace.restype = C.c_int
+        self.debug_set_trace = d.bnpc_debug_set_trace
         for name, args in HOST_SCALAR_SIGNATURES.items():
             fn = getattr(d, name)
             fn.restype = _D

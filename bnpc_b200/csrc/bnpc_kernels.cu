@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include "../../include/bnpc_b200.h"
+#include "../../include/bnpc_b200_debug.h"
 #include "bnpc_math.cuh"
 
 using namespace bnpc;

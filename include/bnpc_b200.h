@@ -212,9 +212,6 @@ int bnpc_mpear_sums(const int32_t* counts, int N, const int32_t* labels, int n_c
  * shrinks to the profiles' pairs.                                                             */
 int bnpc_mpear_sums_weighted(const int32_t* counts, int N, const int32_t* labels, int n_cand,
                              const int32_t* weight, unsigned long long* out, void* stream);
-/* Debug hook: buf = device array of 4096 int64 (or NULL) that CTA 0 of bnpc_ll_matrix_i8 fills with
- * clock64 stamps of its pipeline phases (tools/tc_trace.py). */
-int bnpc_debug_set_trace(void* buf);
 int bnpc_ll_matrix_i8(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
                       int cell_stride, int C, const double* lp, uint8_t* bdigits, int K, double vmax,
                       float* llf, int ldf, void* stream);

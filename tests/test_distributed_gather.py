@@ -96,3 +96,31 @@ def test_gather_traces_of_unequal_length(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), 4, out, True), nprocs=2, join=True)
     n = np.load(out)
     assert n[0] == 4 and (n[1:] == 5).all()
+
+
+def _lugsail_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from libs.MCMC import MCMC
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+
+    class _Done:                       # a chain whose ML trace has converged: no extension round
+        def __init__(self, seed):
+            self.results = dict(ML=np.random.default_rng(seed).normal(-100, 1e-6, 400),
+                                params=np.zeros((400, 2, 3), dtype=np.float32))
+    mcmc = MCMC(model=None)
+    n = 1                              # fewer chains than ranks: rank 1 owns none
+    mine = chains_of_rank(n, rank, world)
+    mcmc.chains = [_Done(c) if c in mine else None for c in range(n)]
+    mcmc.run_lugsail_chains(1.5, mine, verbosity=0)
+    if rank == 0:
+        r = mcmc.chains[0].results
+        assert r['burn_in'] == 201 and r['PSRF_cutoff'] == 1.5 and r['PSRF'][-1][1] <= 1.5
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_lugsail_round_with_a_rank_that_owns_no_chain():
+    mp.spawn(_lugsail_worker, args=(2, _free_port()), nprocs=2, join=True)

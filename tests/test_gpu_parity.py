@@ -46,6 +46,36 @@ def test_cuda_replays_reference_tape(name):
     assert rnd.tape.exhausted()
 
 
+@pytest.mark.parametrize('name', golden_names())
+def test_chain_results_match_reference_fixtures(name):
+    """The trace recording of the chain driver (`Chain_steps.run` = `Chain.do_step` +
+    `Chain.update_results`, reference libs/MCMC.py:242-282, 320-342) over the reference's recorded
+    tape: every row of `Chain.results` -- ML, MAP, alpha, FN, FP, the assignment vector and the
+    theta rows of the SORTED live cluster ids -- equals the state the reference was in after that
+    step (fixtures generated from the reference, tests/golden/make_golden.py)."""
+    from libs.MCMC import Chain_steps
+    g = Golden(name)
+    m, rnd = cuda_model(g.meta['learning'], g.data, g.meta['kwargs'], g.tape_arrays)
+    m.init(assign=g.meta['init_assign'] if g.meta['init'] == 'assign' else None)
+    steps = g.meta['steps']
+    moves = dict(g.meta['moves'], param_proposal_sd=np.array([0.1, 0.25, 0.5]))
+    chain = Chain_steps(m, 1, steps, 0, moves, 0, False)
+    chain.run()                                              # a tape source: the per-method mirror steps the chain
+    assert rnd.tape.exhausted()
+    r = chain.get_result()
+    assert r['burn_in'] == 0 and r['ML'].size == steps + 1 and r['params'].shape[0] == steps + 1
+    k_max = max(g.state(s)['ids'].size for s in range(steps + 1))
+    assert r['params'].shape[1] == k_max
+    for s in range(steps + 1):
+        want = g.state(s)
+        np.testing.assert_array_equal(r['assignments'][s], want['assignment'], err_msg=f'{name} row {s}')
+        order = np.argsort(want['ids'])
+        np.testing.assert_array_equal(r['params'][s, :order.size], want['theta'][order], err_msg=f'{name} row {s}')
+        assert not r['params'][s, order.size:].any()
+        np.testing.assert_allclose([r['ML'][s], r['MAP'][s], r['DP_alpha'][s], r['FN'][s], r['FP'][s]],
+                                   [want['ll'], want['lpost'], want['alpha'], want['FN'], want['FP']], rtol=RTOL, atol=0)
+
+
 def _oracle_run(data, learning, kwargs, moves, steps, seed, assign):
     tape = Tape()
     rnd = LegacyRandom(record=tape)
