@@ -414,13 +414,16 @@ def roofline_of(name, row, work, peaks, traffic):
     # DRAM bytes of an ncu capture of this kernel, scaled from the chains of the captured launch to
     # the chains per launch measured here (chains of one launch share the bit-planes in L2)
     out['traffic'] = cap['bytes'] * chains / cap['chains'] if cap else None
-    if base == 'll_matrix_i8_kernel':
+    if base in ('ll_matrix_i8_kernel', 'll_matrix_i8s_kernel'):
         flops = 4.0 * N * M * K * chains
         ach = flops / sec / 1e12
         out.update(bound='tensor', achieved=ach, peak=bf16_sus, unit='TFLOP/s', frac=ach / bf16_sus,
                    algorithmic_flops_per_launch=flops,
                    note='4*N*M*K algorithmic flops per chain; the kernel executes two base-256 digits per '
-                        'log-probability on the int8 tensor pipe (nominal 2 x bf16); peak = sustained bf16')
+                        'log-probability on the int8 tensor pipe (nominal 2 x bf16); peak = sustained bf16'
+                        + ('; ll_matrix_i8s: the chains of a launch whose digit tables fit one MMA side by side '
+                           '(sum of 2*Kp <= 256) share the expanded data operand in tensor memory'
+                           if base == 'll_matrix_i8s_kernel' else ''))
         return out
     per_chain = {
         'gibbs_sweep_kernel': 160.0 * n_unc + 4.0 * N,                 # records of the uncertain visits + assignments
@@ -495,7 +498,10 @@ def run_gpu(args, cfg):
     work = dict(N=N, M=M, K=k_live, n_unc=n_unc)
     top = next(iter(ktab))
     roof = roofline_of(top, ktab[top], work, peaks, traffic)
-    ll_name = next((n for n in ktab if n.startswith('ll_matrix_i8_kernel')), None)
+    # the rows of a sweep's first epoch (cell order, tiles shared by the chains of a launch); the
+    # one-chain kernel only serves the gathered rows of later epochs
+    ll_name = next((n for n in ktab if n.startswith('ll_matrix_i8s_kernel')), None) or \
+        next((n for n in ktab if n.startswith('ll_matrix_i8_kernel')), None)
     roof_ll = roofline_of(ll_name, ktab[ll_name], work, peaks, traffic) if ll_name else None
     d2h = bench.trace_bytes_per_step(ex_e2e['k_live'])
     out = dict(

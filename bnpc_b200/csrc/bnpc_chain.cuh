@@ -102,6 +102,7 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
         const int ldf = (K + 7) & ~7;
         TRY(record_event(e->ev_ll0, stream));
         double err_abs = 0.0;
+        int by_cell = 0;
         if (e->lean == 3) {
             // integer rows: log-probabilities are linear in theta in [1e-5, 1 - 1e-5] before the
             // log, so the most negative one sits at an end of that interval
@@ -110,7 +111,10 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
                                      fmin(tl * e->FN + th * (1 - e->FP), th * e->FN + tl * (1 - e->FP)));
             const double vmax = -log(fmax(pmin, 1e-300)) * 1.0001 + 1e-6;
             err_abs = (double)M * (vmax / 65535.0) * 0.5;
-            TRY(bnpc_ll_matrix_i8(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp,
+            // an epoch over all cells writes its rows in CELL order: every chain of the GPU then
+            // reads the same tiles and chains in the same wave share them (bnpc_tc_i8s.cuh)
+            by_cell = (t == 0 && rows == N) ? 1 : 0;
+            TRY(bnpc_ll_matrix_i8(w->x1, w->x0, w->W, M, by_cell ? nullptr : cells, cstride, rows, w->lp,
                                   reinterpret_cast<uint8_t*>(w->bsplit), K, vmax, w->llf, ldf, stream));
         } else if (e->lean == 2)
             TRY(bnpc_ll_matrix_tc(w->x1, w->x0, w->W, M, cells, cstride, rows, w->lp, w->bsplit, K, w->llf, ldf,
@@ -120,7 +124,7 @@ int bnpc_chain_gibbs_epoch(const bnpc_chain_t* w, const bnpc_epoch_t* e, void* s
                                    stream));
         TRY(record_event(e->ev_ll1, stream));
         TRY(gibbs_options_impl(w->llf, ldf, K, w->col_of_id, w->visit + t, w->opt + t, w->n_cert, rows, e->log_n,
-                               e->c_norm, 2 * M, err_abs, false, stream));
+                               e->c_norm, 2 * M, err_abs, false, stream, by_cell));
         TRY(gibbs_exact_impl(w->x1, w->x0, w->W, M, w->lp, K, w->visit + t, w->opt + t, w->n_cert, rows, w->cblk,
                              w->idx_c, w->st, w->visit_c, w->cand_c, e->log_n, e->c_norm, w->comp, w->rg_perm, false,
                              stream));

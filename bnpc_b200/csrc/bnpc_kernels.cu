@@ -754,6 +754,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 #include "bnpc_lean.cuh"
 #include "bnpc_tc.cuh"
 #include "bnpc_tc_i8.cuh"
+#include "bnpc_tc_i8s.cuh"
 #include "bnpc_estimators.cuh"
 
 #define SW_STAGE_CELLS 32
@@ -2620,6 +2621,11 @@ int bnpc_ll_matrix_i8(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
     const long long total = (long long)(W / 2) * 2 * kpad * 128;
     BNPC_LAUNCH(lp_split_u8_kernel, 0, 0, cdiv(total, 256), 256, 0, s, reinterpret_cast<const double2*>(lp), K, M, W, kpad, 1.0 / q, bdigits);
     const float nq = -(float)q;
+    // rows in cell order (cells = NULL): the kernel that lets chains with equal tiles share the
+    // expanded data operand (bnpc_tc_i8s.cuh); BNPC_LL_I8_SINGLE=1 keeps the one-chain kernel of
+    // bnpc_tc_i8.cuh, which also serves the gathered rows of later epochs
+    static const int single = getenv("BNPC_LL_I8_SINGLE") ? 1 : 0;
+    if (!single && cells == nullptr) return launch_ll_i8s(x1, x0, W, C, bdigits, kpad, nq, llf, ldf, s);
     switch (kpad) {
         case 8: return launch_ll_i8<8>(x1, x0, W, cells, cell_stride, C, bdigits, nq, llf, ldf, s);
         case 16: return launch_ll_i8<16>(x1, x0, W, cells, cell_stride, C, bdigits, nq, llf, ldf, s);
@@ -2632,17 +2638,50 @@ int bnpc_ll_matrix_i8(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
     }
 }
 
+int bnpc_ll_matrix_i8_shared(const uint32_t* x1, const uint32_t* x0, int W, int M, int C, int n_chains,
+                             const double* const* lp, uint8_t* const* bdigits, const int* K, const double* vmax,
+                             float* const* llf, const int* ldf, void* stream) {
+    if (C <= 0 || n_chains <= 0) return 0;
+    if (n_chains > bnpc::BATCH_MAX) return bad_arg("at most 8 chains per call");
+    if (bnpc::g_rec.on) return bad_arg("bnpc_ll_matrix_i8_shared launches at once (no recorder)");
+    if (W % 4 != 0) return bad_arg("W must be a multiple of 4");
+    if (M >= 32768) return bad_arg("int32 accumulators hold rows of fewer than 32768 mutations");
+    cudaStream_t s = (cudaStream_t)stream;
+    bnpc::Op op[bnpc::BATCH_MAX];
+    bnpc::Op* ops[bnpc::BATCH_MAX];
+    for (int c = 0; c < n_chains; ++c) {
+        if (K[c] <= 0 || K[c] > BNPC_LEAN_MAXK) return bad_arg("tensor-core rows need 0 < K <= BNPC_LEAN_MAXK");
+        if (!(vmax[c] > 0.0)) return bad_arg("vmax must be positive");
+        const int kpad = (K[c] + 7) & ~7;
+        if (ldf[c] < kpad || ldf[c] % 4 != 0) return bad_arg("ldf must be a multiple of 4, >= K rounded up to 8");
+        const double q = vmax[c] / 65535.0;
+        const long long total = (long long)(W / 2) * 2 * kpad * 128;
+        BNPC_LAUNCH(lp_split_u8_kernel, 0, 0, cdiv(total, 256), 256, 0, s, reinterpret_cast<const double2*>(lp[c]), K[c], M, W, kpad, 1.0 / q, bdigits[c]);
+        ll_shared_t one;
+        memset(&one, 0, sizeof(one));
+        one.x1 = x1; one.x0 = x0; one.W = W; one.C = C;
+        one.nc = 1; one.n_tot = 2 * kpad;
+        one.ch[0].Bg = bdigits[c]; one.ch[0].llf = llf[c]; one.ch[0].neg_q = -(float)q; one.ch[0].ldf = ldf[c];
+        one.ch[0].kpad = kpad; one.ch[0].off = 0;
+        op[c].kind = 0; op[c].name = "ll_matrix_i8s_kernel"; op[c].block = T8S_THREADS;
+        memcpy(op[c].args, &one, sizeof(one));
+        ops[c] = &op[c];
+    }
+    return launch_ll_shared_merged(ops, n_chains, s);
+}
+
 // clear = false: the caller has zeroed n_cert already (the composite entry points clear all the
 // scratch of an epoch in one launch)
 static int gibbs_options_impl(const float* llf, int ldf, int K, const int32_t* col_of_id,
                               const bnpc_visit_t* visit_t0, bnpc_opt_t* opt_t0, int32_t* n_cert, int C,
-                              double log_n, double c_norm, int terms, double err_abs, bool clear, void* stream) {
+                              double log_n, double c_norm, int terms, double err_abs, bool clear, void* stream,
+                              int by_cell = 0) {
     if (C <= 0) return 0;
     if (K <= 0 || K > BNPC_LEAN_MAXK) return bad_arg("lean epochs need K <= BNPC_LEAN_MAXK");
     if (clear)
         if (int rc = zero_async(n_cert, sizeof(int32_t) * BNPC_LEAN_MAXK, stream, "gibbs_options memset")) return rc;
     const float err_rel = (float)terms * 2.384185791015625e-07f;      // terms * 2^-22
-    BNPC_LAUNCH(gibbs_options_kernel, CAND_THREADS, 0, cdiv(C, CAND_THREADS), CAND_THREADS, 0, (cudaStream_t)stream,  llf, ldf, K, col_of_id, visit_t0, opt_t0, n_cert, C, (float)log_n, c_norm, err_rel, 0.05f + (float)(err_abs > 0.0 ? err_abs : 0.0));
+    BNPC_LAUNCH(gibbs_options_kernel, CAND_THREADS, 0, cdiv(C, CAND_THREADS), CAND_THREADS, 0, (cudaStream_t)stream,  llf, ldf, K, col_of_id, visit_t0, opt_t0, n_cert, C, (float)log_n, c_norm, err_rel, 0.05f + (float)(err_abs > 0.0 ? err_abs : 0.0), by_cell);
     return 0;
 }
 

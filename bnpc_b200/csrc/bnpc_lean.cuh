@@ -79,13 +79,15 @@ __device__ __forceinline__ void ll_matrix_f32_kernel(const uint32_t* __restrict_
 __device__ __forceinline__ void gibbs_options_kernel(const float* __restrict__ llf, int ldf, int K, const int32_t* __restrict__ col_of_id,
                      const bnpc_visit_t* __restrict__ visit, bnpc_opt_t* __restrict__ opt,
                      int32_t* __restrict__ n_cert, int C, float slack, double c_norm, float err_rel,
-                     float err_abs) {
+                     float err_abs, int by_cell) {
     __shared__ int s_cert[BNPC_LEAN_MAXK];
     if (threadIdx.x < BNPC_LEAN_MAXK) s_cert[threadIdx.x] = 0;
     __syncthreads();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < C) {
-        const float* row = llf + (long long)r * ldf;
+        // by_cell: the rows were written in cell order (first epoch of a sweep, the tiles shared by
+        // the chains of the GPU); otherwise row r belongs to visit r of the epoch
+        const float* row = llf + (long long)(by_cell ? visit[r].cell : r) * ldf;
         const int c_old = col_of_id[visit[r].old];
         bnpc_opt_t o;
 #pragma unroll
@@ -224,10 +226,13 @@ __device__ __forceinline__ void gibbs_exact_kernel(const uint32_t* __restrict__ 
     __shared__ int s_cols[BNPC_LEAN_MAXK];
     double2* tile = reinterpret_cast<double2*>(ex_smem);          // [32 * EX_WORDS][EX_COLS]
     const double* tile_d = reinterpret_cast<const double*>(ex_smem);
+    // (the block may be narrower than EX_THREADS: few uncertain visits are spread over more, smaller
+    // CTAs -- one visit per thread either way, so the result does not depend on the block size)
     const int n_unc = st[BNPC_ST_NUNC];
-    if (blockIdx.x * EX_THREADS >= n_unc) return;
-    if (threadIdx.x < BNPC_LEAN_MAXK) { s_adj[threadIdx.x] = 0ull; s_num[threadIdx.x] = 0; }
-    const int q = blockIdx.x * EX_THREADS + threadIdx.x;
+    const int nthr = blockDim.x;
+    if (blockIdx.x * nthr >= n_unc) return;
+    for (int i = threadIdx.x; i < BNPC_LEAN_MAXK; i += nthr) { s_adj[i] = 0ull; s_num[i] = 0; }
+    const int q = blockIdx.x * nthr + threadIdx.x;
     const bool live = q < n_unc;
     const int j = live ? order[q] : order[0];        // slot of the visit among the compacted records
     const int r = idx_c[j];
@@ -260,8 +265,8 @@ __device__ __forceinline__ void gibbs_exact_kernel(const uint32_t* __restrict__ 
     __syncthreads();
     const unsigned long long used = s_used;
     const int n_used = __popcll(used);
-    if (threadIdx.x < BNPC_LEAN_MAXK && ((used >> threadIdx.x) & 1ull))
-        s_cols[__popcll(used & ((1ull << threadIdx.x) - 1ull))] = threadIdx.x;
+    for (int k = threadIdx.x; k < BNPC_LEAN_MAXK; k += nthr)
+        if ((used >> k) & 1ull) s_cols[__popcll(used & ((1ull << k) - 1ull))] = k;
     int lcol[BNPC_MAX_OPT];                                    // index of the option's column among the used ones
 #pragma unroll
     for (int i = 0; i < BNPC_MAX_OPT; ++i) lcol[i] = (i < nn) ? __popcll(used & ((1ull << col[i]) - 1ull)) : -1;
@@ -276,7 +281,7 @@ __device__ __forceinline__ void gibbs_exact_kernel(const uint32_t* __restrict__ 
             off[i] = (lcol[i] >= c0 && lcol[i] < c0 + nc) ? 2 * (lcol[i] - c0) : -1;
         for (int w0 = 0; w0 < words; w0 += EX_WORDS) {
             __syncthreads();
-            for (int i = threadIdx.x; i < 32 * EX_WORDS * nc; i += EX_THREADS) {
+            for (int i = threadIdx.x; i < 32 * EX_WORDS * nc; i += nthr) {
                 const int kk = i / (32 * EX_WORDS), mm = i % (32 * EX_WORDS), m = w0 * 32 + mm;   // coalesced along mutations
                 tile[mm * EX_COLS + kk] = (m < M) ? lp[(long long)s_cols[c0 + kk] * M + m] : make_double2(0.0, 0.0);
             }
@@ -369,10 +374,10 @@ __device__ __forceinline__ void gibbs_exact_kernel(const uint32_t* __restrict__ 
         }
     }
     __syncthreads();
-    if (threadIdx.x < K) {
+    for (int k = threadIdx.x; k < K; k += nthr) {
         unsigned long long* adj = reinterpret_cast<unsigned long long*>(comp);
-        if (s_adj[threadIdx.x]) atomicOr(&adj[threadIdx.x], s_adj[threadIdx.x]);
-        if (s_num[threadIdx.x]) atomicAdd(&comp[128 + threadIdx.x], s_num[threadIdx.x]);
+        if (s_adj[k]) atomicOr(&adj[k], s_adj[k]);
+        if (s_num[k]) atomicAdd(&comp[128 + k], s_num[k]);
     }
 }
 

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BNPC_ABI_VERSION 10
+#define BNPC_ABI_VERSION 11
 
 /* capacity of clusters born since the ll matrix of the current epoch was built */
 #define BNPC_MAX_EXTRA 32
@@ -215,6 +215,15 @@ int bnpc_mpear_sums_weighted(const int32_t* counts, int N, const int32_t* labels
 int bnpc_ll_matrix_i8(const uint32_t* x1, const uint32_t* x0, int W, int M, const int32_t* cells,
                       int cell_stride, int C, const double* lp, uint8_t* bdigits, int K, double vmax,
                       float* llf, int ldf, void* stream);
+/* The integer rows of n_chains <= 8 chains over the SAME cells in cell order (row r = cell r, the
+ * first epoch of a sweep): chains whose digit tables fit one MMA side by side (sum of 2*Kp <= 256)
+ * share the expanded data operand in tensor memory -- one pass over the bit-planes and one TMEM
+ * read per MMA for all of them (csrc/bnpc_tc_i8s.cuh).  Per-chain arguments are host arrays; the
+ * values equal bnpc_ll_matrix_i8's bit for bit (exact integer accumulation).  This is what the
+ * recorded bnpc_ll_matrix_i8 calls (cells = NULL) of the chains of one wave are merged into. */
+int bnpc_ll_matrix_i8_shared(const uint32_t* x1, const uint32_t* x0, int W, int M, int C, int n_chains,
+                             const double* const* lp, uint8_t* const* bdigits, const int* K,
+                             const double* vmax, float* const* llf, const int* ldf, void* stream);
 /* err_abs: absolute error of the approximate rows on top of the FP32 accumulation bound (0 for the
  * float rows). */
 int bnpc_gibbs_options(const float* llf, int ldf, int K, const int32_t* col_of_id,

@@ -283,6 +283,54 @@ def test_approximate_rows_within_their_error_bound(L, shape, rows):
     assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max() + 1e-3 + (0.02 if rows == 'tcgen05_i8' else 0)
 
 
+@pytest.mark.parametrize('shape', [(5000, 1000, (24, 28, 22, 25)), (777, 50, (40, 3)), (40000, 300, (9, 17)),
+                                   (90000, 200, (30, 31, 32, 8, 24, 16, 20, 12)), (300, 128, (64, 64, 5)),
+                                   (80000, 130, (20,))])
+def test_shared_integer_rows_equal_the_one_chain_rows(L, shape):
+    """bnpc_ll_matrix_i8_shared (csrc/bnpc_tc_i8s.cuh): the integer tensor-core rows of several chains
+    over the same cells in cell order, sharing the expanded data operand in tensor memory (and two
+    tiles per table chunk at the larger shapes), against one bnpc_ll_matrix_i8 call per chain with an
+    explicit cell list (the one-chain kernel of csrc/bnpc_tc_i8.cuh).  Integer accumulation is exact,
+    so the floats are identical.  The shapes cover mixed cluster counts (different paddings in one
+    MMA), more chains than fit one group, a last tile that is not full, a single chunk pair per row
+    (M = 50), resident and streamed tables."""
+    N, M, Ks = shape
+    rng = np.random.default_rng(N + M + len(Ks))
+    data = rng.integers(0, 2, (N, M)).astype(np.float64)
+    data[rng.random((N, M)) < 0.1] = np.nan
+    W, x1, x0, n1, n0 = pack(L, data)
+    cells = dev(np.arange(N, dtype=np.int32), torch.int32)
+    lps, bss, outs, refs, vmaxs, kps = [], [], [], [], [], []
+    for K in Ks:
+        theta = dev(np.clip(rng.random((K, M)), 1e-5, 1 - 1e-5).astype(np.float32), torch.float32)
+        lp = torch.zeros(2 * K * M, dtype=torch.float64, device='cuda')
+        L.logprob_tables(theta.data_ptr(), None, K, M, 0.2, 0.01, lp.data_ptr(), sp())
+        kp = (K + 7) & ~7
+        vmax = float(lp.abs().max().item()) * 1.0001
+        bs = torch.zeros(W * kp * 128, dtype=torch.uint8, device='cuda')
+        ref = torch.full((N, kp), float('nan'), dtype=torch.float32, device='cuda')
+        L.ll_matrix_i8(x1.data_ptr(), x0.data_ptr(), W, M, cells.data_ptr(), 1, N, lp.data_ptr(), bs.data_ptr(), K,
+                       vmax, ref.data_ptr(), kp, sp())
+        torch.cuda.synchronize()
+        lps.append(lp); bss.append(bs); refs.append(ref); vmaxs.append(vmax); kps.append(kp)
+        outs.append(torch.full((N, kp), float('nan'), dtype=torch.float32, device='cuda'))
+    nc = len(Ks)
+    P = C.c_void_p * nc
+    L.ll_matrix_i8_shared(x1.data_ptr(), x0.data_ptr(), W, M, N, nc, P(*[t.data_ptr() for t in lps]),
+                          P(*[t.data_ptr() for t in bss]), (C.c_int * nc)(*Ks), (C.c_double * nc)(*vmaxs),
+                          P(*[t.data_ptr() for t in outs]), (C.c_int * nc)(*kps), sp())
+    torch.cuda.synchronize()
+    for c, K in enumerate(Ks):
+        assert not torch.isnan(outs[c][:, :K]).any()
+        assert torch.equal(outs[c][:, :K], refs[c][:, :K]), f'chain {c} (K = {K})'
+    # the one-chain call without a cell list takes the same kernel (a group of one)
+    one = torch.full((N, kps[0]), float('nan'), dtype=torch.float32, device='cuda')
+    L.ll_matrix_i8(x1.data_ptr(), x0.data_ptr(), W, M, None, 1, N, lps[0].data_ptr(), bss[0].data_ptr(), Ks[0],
+                   vmaxs[0], one.data_ptr(), kps[0], sp())
+    torch.cuda.synchronize()
+    assert torch.equal(one[:, :Ks[0]], refs[0][:, :Ks[0]])
+
+
 @pytest.mark.parametrize('nf', [1, 37, 1024, 1025, 5000, 20000])
 @pytest.mark.parametrize('spread', [0.02, 3.0])
 def test_rg_scan_matches_the_serial_scan(L, nf, spread):
