@@ -225,7 +225,8 @@ static int rg_mh(const bnpc_chain_t* w, const bnpc_rg_t* g, int row0, int rows, 
     const bool want = slot >= 0;
     TRY(mh_theta_impl(w->rg_theta + (size_t)row0 * M, nullptr, rows, M, w->rg_S1 + (size_t)row0 * M,
                       w->rg_S0 + (size_t)row0 * M, g->rand_ready ? w->rg_rnd : nullptr, g->seed, sid, g->FN, g->FP,
-                      g->p, g->q, want ? 1 : 0, want ? w->rg_logq : nullptr, w->rg_dec, stream));
+                      g->p, g->q, want ? 1 : 0, want ? w->rg_logq : nullptr, w->rg_dec, stream,
+                      row0 == 0 ? w->rg_lp : nullptr));         // rows 0, 1: table of the next scan
     if (want) TRY(bnpc_row_sum(w->rg_logq, 1, (int)RM, w->rg_scal + slot, stream));
     return 0;
 }
@@ -239,8 +240,10 @@ int bnpc_chain_rg_setup(const bnpc_chain_t* w, const bnpc_rg_t* g, void* stream)
     if (n > 2) TRY(bnpc_rg_launch_halves(w->x1, w->x0, w->W, w->cells, n, g->k6, w->half, stream));
     TRY(rg_side_stats(w, n, stream));
     // theta of the two halves, then of all cells of the move (libs/CRP.py:562-566)
-    TRY(bnpc_beta_rows(w->rg_S1, w->rg_S0, 2, M, g->p, g->q, g->rand_ready ? w->rg_beta : nullptr, g->seed,
-                       g->stream_id + 1, w->rg_theta, nullptr, stream));
+    // (the kernels that write the theta rows of the two sides -- this draw and the Metropolis-Hastings
+    // update at the end of every scan -- also write their log-probability table rg_lp for the next scan)
+    TRY(beta_rows_impl(w->rg_S1, w->rg_S0, 2, M, g->p, g->q, g->rand_ready ? w->rg_beta : nullptr, g->seed,
+                       g->stream_id + 1, w->rg_theta, nullptr, w->rg_lp, g->FN, g->FP, stream));
     BNPC_LAUNCH(add_rows_kernel, 0, 0, cdiv(M, 256), 256, 0, (cudaStream_t)stream, w->rg_S1, w->rg_S1 + M, w->rg_S1 + 2 * M, M);
     BNPC_LAUNCH(add_rows_kernel, 0, 0, cdiv(M, 256), 256, 0, (cudaStream_t)stream, w->rg_S0, w->rg_S0 + M, w->rg_S0 + 2 * M, M);
     TRY(bnpc_beta_rows(w->rg_S1 + 2 * M, w->rg_S0 + 2 * M, 1, M, g->p, g->q,
@@ -256,13 +259,8 @@ int bnpc_chain_rg_scan_split(const bnpc_chain_t* w, const bnpc_rg_t* g, int want
     const int n = g->n, nf = n - 2, M = w->M;
     int used = 0;
     if (n > 2) {
-        if (ll_few_fits(2, w->W)) {
-            TRY(ll_few_from_theta(w->x1, w->x0, w->W, M, w->cells + 1, 1, nf, w->rg_theta, 2, g->FN, g->FP, w->rg_ll2,
-                                  2, stream));
-        } else {
-            TRY(bnpc_logprob_tables(w->rg_theta, nullptr, 2, M, g->FN, g->FP, w->rg_lp, stream));
-            TRY(bnpc_ll_matrix(w->x1, w->x0, w->W, M, w->cells + 1, 1, nf, w->rg_lp, 2, w->rg_ll2, 2, stream));
-        }
+        // rg_lp = log-probability table of rg_theta rows 0, 1 (written with them)
+        TRY(bnpc_ll_matrix(w->x1, w->x0, w->W, M, w->cells + 1, 1, nf, w->rg_lp, 2, w->rg_ll2, 2, stream));
         if (!g->rand_ready) used = 2;                    // streams stream_id+1 (order), +2 (uniforms)
         TRY(rg_scan_impl(w->rg_ll2, 2, n, g->rand_ready ? w->rg_perm : nullptr, g->rand_ready ? w->rg_u : nullptr,
                          g->seed, g->stream_id, w->half, g->alpha, 0, nullptr, nullptr, -1,

@@ -2008,7 +2008,8 @@ __device__ __forceinline__ void suffstat_kernel(const uint32_t* __restrict__ x1,
 __device__ __forceinline__ void beta_rows_kernel(const int32_t* __restrict__ S1, const int32_t* __restrict__ S0, int R,
                                  int M, double p, double q, const double* __restrict__ tape,
                                  uint64_t seed, uint64_t stream_id, float* __restrict__ theta_out,
-                                 const int32_t* __restrict__ out_ids) {
+                                 const int32_t* __restrict__ out_ids, double2* __restrict__ lp_out, double FN,
+                                 double FP) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)R * M) return;
     const int r = (int)(i / M), m = (int)(i % M);
@@ -2020,7 +2021,15 @@ __device__ __forceinline__ void beta_rows_kernel(const int32_t* __restrict__ S1,
         val = beta_sample(p + (double)S1[i], q + (double)S0[i], rs);
     }
     const long long row = out_ids ? out_ids[r] : r;
-    theta_out[row * M + m] = clip_theta(val);
+    const float th = clip_theta(val);
+    theta_out[row * M + m] = th;
+    // lp_out (rows in order, [R][M]): the (log p1, log p0) table of the rows just drawn, for the
+    // restricted Gibbs scan that follows (what bnpc_logprob_tables would write)
+    if (lp_out) {
+        double2 v;
+        log_p1_p0(th, FN, FP, v.x, v.y);
+        lp_out[i] = v;
+    }
 }
 
 __device__ __forceinline__ void theta_from_uniform_kernel(const double* __restrict__ u, int R, int M,
@@ -2040,7 +2049,8 @@ struct MhConst {
 
 // log acceptance ratio of libs/CRP.py:347-383 for one (row, mutation)
 __device__ __forceinline__ double theta_log_A(float th_new, float th_old, int s1, int s0, double lo,
-                                              double hi, double sd, const MhConst& c, bool clip) {
+                                              double hi, double sd, const MhConst& c, bool clip,
+                                              double2* lp_new = nullptr, double2* lp_old = nullptr) {
     const float lo_f = (float)kThetaLo, hi_f = (float)kThetaHi;
     const double lsd = log(sd);
     const double y = (double)(th_new - th_old) / sd;
@@ -2051,6 +2061,7 @@ __device__ __forceinline__ double theta_log_A(float th_new, float th_old, int s1
     double n1, n0, o1, o0;
     log_p1_p0(th_new, c.FN, c.FP, n1, n0);
     log_p1_p0(th_old, c.FN, c.FP, o1, o0);
+    if (lp_new) { *lp_new = make_double2(n1, n0); *lp_old = make_double2(o1, o0); }
     const double ll_new = (double)s1 * n1 + (double)s0 * n0;
     const double ll_old = (double)s1 * o1 + (double)s0 * o0;
     double pr_new = 0.0, pr_old = 0.0;
@@ -2068,7 +2079,8 @@ __device__ __constant__ const double kStepSd[3] = {0.1, 0.25, 0.5};   // libs/CR
 __device__ __forceinline__ void mh_theta_kernel(float* theta, const int32_t* __restrict__ ids, int R, int M,
                                 const int32_t* __restrict__ S1, const int32_t* __restrict__ S0,
                                 const double* __restrict__ rnd, MhConst c, int flags,
-                                double* __restrict__ logq, int32_t* declined, uint64_t seed, uint64_t stream_id) {
+                                double* __restrict__ logq, int32_t* declined, uint64_t seed, uint64_t stream_id,
+                                double2* __restrict__ lp_out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long RM = (long long)R * M;
     if (i >= RM) return;
@@ -2084,10 +2096,14 @@ __device__ __forceinline__ void mh_theta_kernel(float* theta, const int32_t* __r
     const double x = truncnorm_ppf_std(ut, lo, hi);
     const float prop = (float)(x * sd + (double)old);
     const bool want_logq = flags & 1;
-    const double A = theta_log_A(prop, old, S1[i], S0[i], lo, hi, sd, c, want_logq);
+    double2 lp_new, lp_old;
+    const double A = theta_log_A(prop, old, S1[i], S0[i], lo, hi, sd, c, want_logq, &lp_new, &lp_old);
     const bool rej = log(ua) >= A;
     if (!rej) theta[row * M + m] = prop;
     else atomicAdd(&declined[r], 1);
+    // lp_out ([R][M]): the (log p1, log p0) pair of the value the element keeps -- computed above
+    // for the acceptance ratio -- so the restricted Gibbs scan that follows reads a finished table
+    if (lp_out) lp_out[i] = rej ? lp_old : lp_new;
     if (want_logq) logq[i] = rej ? log(-1.0 * expm1(A)) : A;
 }
 
@@ -2715,7 +2731,7 @@ static int gibbs_exact_impl(const uint32_t* x1, const uint32_t* x0, int W, int M
         const char* env = getenv("BNPC_EXACT_STAGING");
         all_cols = (env && env[0] == 'a') ? 1 : 0;
     }
-    const size_t smem = all_cols ? sizeof(double2) * 32 * EX_WORDS * (size_t)K : sizeof(double2) * 32 * EX_WORDS * EX_COLS;
+    const size_t smem = all_cols ? sizeof(double2) * 32 * EX_WORDS * (size_t)K : sizeof(double2) * (EX_ROWS + 1) * (EX_COLS + 1);
     // processing order: uncertain visits grouped by their own cluster (see exact_hist_kernel)
     BNPC_LAUNCH(exact_hist_kernel, 256, 0, cdiv(C, 256), 256, 0, s, opt_t0, idx_c, st, comp);
     BNPC_LAUNCH(exact_scan_kernel, BNPC_LEAN_MAXK, 0, 1, BNPC_LEAN_MAXK, 0, s, comp);
@@ -2813,12 +2829,17 @@ int bnpc_suffstat(const uint32_t* x1, const uint32_t* x0, int W, int M, const in
     return suffstat_impl(x1, x0, W, M, members, seg_off, R, max_len, S1, S0, true, stream);
 }
 
+static int beta_rows_impl(const int32_t* S1, const int32_t* S0, int R, int M, double p, double q,
+                          const double* tape, uint64_t seed, uint64_t stream_id, float* theta_out,
+                          const int32_t* out_ids, double* lp_out, double FN, double FP, void* stream) {
+    if (R <= 0) return 0;
+    BNPC_LAUNCH(beta_rows_kernel, 0, 0, cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream,  S1, S0, R, M, p, q, tape, seed, stream_id, theta_out, out_ids, reinterpret_cast<double2*>(lp_out), FN, FP);
+    return 0;
+}
 int bnpc_beta_rows(const int32_t* S1, const int32_t* S0, int R, int M, double p, double q,
                    const double* tape, uint64_t seed, uint64_t stream_id, float* theta_out,
                    const int32_t* out_ids, void* stream) {
-    if (R <= 0) return 0;
-    BNPC_LAUNCH(beta_rows_kernel, 0, 0, cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream,  S1, S0, R, M, p, q, tape, seed, stream_id, theta_out, out_ids);
-    return 0;
+    return beta_rows_impl(S1, S0, R, M, p, q, tape, seed, stream_id, theta_out, out_ids, nullptr, 0.0, 0.0, stream);
 }
 
 int bnpc_theta_from_uniform(const double* u, int R, int M, float* theta_out, const int32_t* out_ids,
@@ -2839,10 +2860,11 @@ static MhConst make_mh_const(double FN, double FP, double p, double q) {
 // rnd == NULL: the kernel draws from streams stream_id+1, +2 of seed
 static int mh_theta_impl(float* theta, const int32_t* ids, int R, int M, const int32_t* S1, const int32_t* S0,
                          const double* rnd, uint64_t seed, uint64_t stream_id, double FN, double FP, double p,
-                         double q, int flags, double* logq, int32_t* declined, void* stream) {
+                         double q, int flags, double* logq, int32_t* declined, void* stream,
+                         double* lp_out = nullptr) {
     if (R <= 0) return 0;
     if ((flags & 1) && !logq) return bad_arg("logq required when flags&1");
-    BNPC_LAUNCH(mh_theta_kernel, 0, 0, cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream,  theta, ids, R, M, S1, S0, rnd, make_mh_const(FN, FP, p, q), flags, logq, declined, seed, stream_id);
+    BNPC_LAUNCH(mh_theta_kernel, 0, 0, cdiv((long long)R * M, 128), 128, 0, (cudaStream_t)stream,  theta, ids, R, M, S1, S0, rnd, make_mh_const(FN, FP, p, q), flags, logq, declined, seed, stream_id, reinterpret_cast<double2*>(lp_out));
     return 0;
 }
 int bnpc_mh_theta(float* theta, const int32_t* ids, int R, int M, const int32_t* S1, const int32_t* S0,

@@ -206,6 +206,31 @@ __device__ __forceinline__ void exact_scatter_kernel(const bnpc_opt_t* __restric
 #define EX_THREADS 128
 #define EX_WORDS 4            /* words of a row (128 mutations) staged per round */
 #define EX_COLS 16            /* columns staged per pass */
+#define EX_ROWS (32 * EX_WORDS)        /* mutations of a round; row EX_ROWS of the tile is all zeros */
+#define EX_STRIDE (2 * (EX_COLS + 1))  /* doubles per tile row: EX_COLS (log p1, log p0) pairs + a zero pair */
+// The additions of one round (EX_WORDS words of the visit's row) for NM options, branch-free: a
+// missing entry reads the zero row, an option whose column is not staged in this pass (or that the
+// visit does not have) reads the zero pair of the row -- adding 0.0 leaves a partial sum unchanged,
+// so the sums are those of the guarded loop.  Per entry: one address, then a load and an addition
+// per option (the guarded form cost ~22 instructions per option and entry: the compiler re-derived
+// the bit tests and the address inside every option's branch).
+template <int NM>
+__device__ __forceinline__ void ex_accumulate(const double* __restrict__ tile_d, const uint32_t (&u1)[EX_WORDS],
+                                              const uint32_t (&u0)[EX_WORDS], const int (&off)[BNPC_MAX_OPT],
+                                              double (&part)[EX_WORDS][BNPC_MAX_OPT]) {
+#pragma unroll 4
+    for (int bit = 0; bit < 32; ++bit) {
+#pragma unroll
+        for (int q = 0; q < EX_WORDS; ++q) {
+            const uint32_t b1 = (u1[q] >> bit) & 1u, b0 = (u0[q] >> bit) & 1u;
+            const int row = (b1 | b0) ? q * 32 + bit : EX_ROWS;
+            const double* t = tile_d + row * EX_STRIDE + (b1 ? 0 : 1);      // log p1 (.x) or log p0 (.y)
+#pragma unroll
+            for (int i = 0; i < NM; ++i) part[q][i] += t[off[i]];
+        }
+    }
+}
+
 // One thread per uncertain visit: FP64 log-likelihood of each of its options, then the option
 // weights exactly as gibbs_candidates_kernel derives them from the FP64 matrix.  The row is summed
 // in four interleaved partial sums per option (word w goes to partial w % 4; the chain of dependent
@@ -224,7 +249,7 @@ __device__ __forceinline__ void gibbs_exact_kernel(const uint32_t* __restrict__ 
     __shared__ int s_num[BNPC_LEAN_MAXK];
     __shared__ unsigned long long s_used;
     __shared__ int s_cols[BNPC_LEAN_MAXK];
-    double2* tile = reinterpret_cast<double2*>(ex_smem);          // [32 * EX_WORDS][EX_COLS]
+    double2* tile = reinterpret_cast<double2*>(ex_smem);          // [EX_ROWS + 1][EX_COLS + 1]
     const double* tile_d = reinterpret_cast<const double*>(ex_smem);
     // (the block may be narrower than EX_THREADS: few uncertain visits are spread over more, smaller
     // CTAs -- one visit per thread either way, so the result does not depend on the block size)
@@ -232,6 +257,9 @@ __device__ __forceinline__ void gibbs_exact_kernel(const uint32_t* __restrict__ 
     const int nthr = blockDim.x;
     if (blockIdx.x * nthr >= n_unc) return;
     for (int i = threadIdx.x; i < BNPC_LEAN_MAXK; i += nthr) { s_adj[i] = 0ull; s_num[i] = 0; }
+    // the zero pair of every row and the zero row (never overwritten by the staging below)
+    for (int i = threadIdx.x; i < EX_ROWS + EX_COLS + 1; i += nthr)
+        tile[i < EX_ROWS ? i * (EX_COLS + 1) + EX_COLS : EX_ROWS * (EX_COLS + 1) + (i - EX_ROWS)] = make_double2(0.0, 0.0);
     const int q = blockIdx.x * nthr + threadIdx.x;
     const bool live = q < n_unc;
     const int j = live ? order[q] : order[0];        // slot of the visit among the compacted records
@@ -275,37 +303,27 @@ __device__ __forceinline__ void gibbs_exact_kernel(const uint32_t* __restrict__ 
     const int words = (M + 31) >> 5;
     for (int c0 = 0; c0 < n_used; c0 += EX_COLS) {
         const int nc = min(EX_COLS, n_used - c0);
-        int off[BNPC_MAX_OPT];                                 // 2 * column slot in this pass, or -1
+        int off[BNPC_MAX_OPT];                                 // 2 * column slot in this pass, or the zero pair
 #pragma unroll
         for (int i = 0; i < BNPC_MAX_OPT; ++i)
-            off[i] = (lcol[i] >= c0 && lcol[i] < c0 + nc) ? 2 * (lcol[i] - c0) : -1;
+            off[i] = (lcol[i] >= c0 && lcol[i] < c0 + nc) ? 2 * (lcol[i] - c0) : 2 * EX_COLS;
         for (int w0 = 0; w0 < words; w0 += EX_WORDS) {
             __syncthreads();
             for (int i = threadIdx.x; i < 32 * EX_WORDS * nc; i += nthr) {
                 const int kk = i / (32 * EX_WORDS), mm = i % (32 * EX_WORDS), m = w0 * 32 + mm;   // coalesced along mutations
-                tile[mm * EX_COLS + kk] = (m < M) ? lp[(long long)s_cols[c0 + kk] * M + m] : make_double2(0.0, 0.0);
+                tile[mm * (EX_COLS + 1) + kk] = (m < M) ? lp[(long long)s_cols[c0 + kk] * M + m] : make_double2(0.0, 0.0);
             }
             __syncthreads();
             if (n_max == 0 || nn == 0) continue;
             const uint4 a = p1[w0 >> 2], b = p0[w0 >> 2];         // rows are padded with zeros to W words
             const uint32_t u1[EX_WORDS] = {a.x, a.y, a.z, a.w}, u0[EX_WORDS] = {b.x, b.y, b.z, b.w};
-#pragma unroll 2
-            for (int bit = 0; bit < 32; ++bit) {
-#pragma unroll
-                for (int q = 0; q < EX_WORDS; ++q) {
-                    const uint32_t b1 = (u1[q] >> bit) & 1u, b0 = (u0[q] >> bit) & 1u;
-                    // the entry selects log p1 (.x), log p0 (.y) or nothing
-                    const double* t = tile_d + (q * 32 + bit) * 2 * EX_COLS + (b1 ? 0 : 1);
-                    const bool any = (b1 | b0) != 0u;
-#pragma unroll
-                    for (int i = 0; i < BNPC_MAX_OPT; ++i) {
-                        if (i >= n_max) break;                               // warp-uniform
-                        if (off[i] >= 0) {
-                            const double term = t[off[i]];
-                            part[q][i] += any ? term : 0.0;
-                        }
-                    }
-                }
+            switch (n_max) {                                      // warp-uniform
+                case 1: ex_accumulate<1>(tile_d, u1, u0, off, part); break;
+                case 2: ex_accumulate<2>(tile_d, u1, u0, off, part); break;
+                case 3: ex_accumulate<3>(tile_d, u1, u0, off, part); break;
+                case 4: ex_accumulate<4>(tile_d, u1, u0, off, part); break;
+                case 5: case 6: ex_accumulate<6>(tile_d, u1, u0, off, part); break;
+                default: ex_accumulate<BNPC_MAX_OPT>(tile_d, u1, u0, off, part); break;
             }
         }
     }
