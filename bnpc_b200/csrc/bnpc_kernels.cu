@@ -1929,8 +1929,9 @@ __device__ __forceinline__ void group_members_kernel(const int32_t* __restrict__
 // grid (chunks, R, word blocks): a CTA counts ones/zeros per mutation over up to SS_CHUNK members
 // of one segment for a block of 32 mutation words.  A thread owns one word column and strides
 // over the rows, so that a warp reads whole 128-byte row pieces (coalesced); the 32 per-bit
-// counters of a word are kept as 8 registers of four byte-wide counters each
-// (acc[j] += (x >> j) & 0x01010101 counts bits j, j+8, j+16, j+24), at most 255 rows per thread.
+// counters of a word are bit-sliced (7 planes, carry-save adder tree over eight rows at a time) and
+// spread once per chunk into 8 registers of four byte-wide counters each (byte b of a[j] counts
+// bit j + 8 b) for the shared-memory accumulation; at most 127 rows per thread.
 __device__ __forceinline__ void suffstat_kernel(const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x0, int W, int M,
                 const int32_t* __restrict__ members, const int32_t* __restrict__ seg_off,
                 int32_t* __restrict__ S1, int32_t* __restrict__ S0, int wc_log2, int n_wblk, int chunk) {
@@ -1949,9 +1950,18 @@ __device__ __forceinline__ void suffstat_kernel(const uint32_t* __restrict__ x1,
     for (int i = threadIdx.x; i < 2 * 32 * 33; i += SS_THREADS) (&cnt[0][0][0])[i] = 0;
     __syncthreads();
     if (w < W) {
-        uint32_t a1[8], a0[8];
+        // Bit-sliced counters: plane k of c1 / c0 holds bit k of the 32 per-bit counts of this
+        // thread's word column.  Eight rows go through a carry-save adder tree (Harley-Seal):
+        // 7 full adders = 14 LOP3 for eight rows and 32 bit positions, against 8 x 24 shift/mask/add
+        // operations when every row is spread into byte-wide counters; the planes are spread into
+        // the byte counters once per chunk.  A thread sees at most chunk / rstep <= 127 rows.
+        uint32_t c1[7], c0[7];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { a1[j] = 0u; a0[j] = 0u; }
+        for (int k = 0; k < 7; ++k) { c1[k] = 0u; c0[k] = 0u; }
+        // (h, l) = carry and sum of a + b + c, bit position by bit position
+#define SS_CSA(h, l, a, b, c) { const uint32_t u__ = (a) ^ (b); const uint32_t h__ = ((a) & (b)) | (u__ & (c)); l = u__ ^ (c); h = h__; }
+        // add a number with the single plane `x` of weight 2^k0 into the counters
+#define SS_RIPPLE(cn, k0, x) { uint32_t cy__ = (x); _Pragma("unroll") for (int k = (k0); k < 7; ++k) { const uint32_t t__ = cn[k] & cy__; cn[k] ^= cy__; cy__ = t__; } }
         int i = beg + rsub;
         // eight rows in flight per thread: the row gather (member index, then its words) is the
         // latency of this kernel
@@ -1962,22 +1972,33 @@ __device__ __forceinline__ void suffstat_kernel(const uint32_t* __restrict__ x1,
             for (int k = 0; k < 8; ++k) c[k] = members[i + k * rstep];
 #pragma unroll
             for (int k = 0; k < 8; ++k) { p[k] = x1[c[k] * W + w]; q[k] = x0[c[k] * W + w]; }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    a1[j] += (p[k] >> j) & 0x01010101u;
-                    a0[j] += (q[k] >> j) & 0x01010101u;
-                }
-            }
+            uint32_t tA, tB, fA, fB, eC;
+            SS_CSA(tA, c1[0], c1[0], p[0], p[1]); SS_CSA(tB, c1[0], c1[0], p[2], p[3]); SS_CSA(fA, c1[1], c1[1], tA, tB);
+            SS_CSA(tA, c1[0], c1[0], p[4], p[5]); SS_CSA(tB, c1[0], c1[0], p[6], p[7]); SS_CSA(fB, c1[1], c1[1], tA, tB);
+            SS_CSA(eC, c1[2], c1[2], fA, fB);
+            SS_RIPPLE(c1, 3, eC);
+            SS_CSA(tA, c0[0], c0[0], q[0], q[1]); SS_CSA(tB, c0[0], c0[0], q[2], q[3]); SS_CSA(fA, c0[1], c0[1], tA, tB);
+            SS_CSA(tA, c0[0], c0[0], q[4], q[5]); SS_CSA(tB, c0[0], c0[0], q[6], q[7]); SS_CSA(fB, c0[1], c0[1], tA, tB);
+            SS_CSA(eC, c0[2], c0[2], fA, fB);
+            SS_RIPPLE(c0, 3, eC);
         }
         for (; i < end; i += rstep) {
-            const long long c0 = members[i];
-            const uint32_t p0 = x1[c0 * W + w], q0 = x0[c0 * W + w];
+            const long long cc = members[i];
+            const uint32_t p0 = x1[cc * W + w], q0 = x0[cc * W + w];
+            SS_RIPPLE(c1, 0, p0);
+            SS_RIPPLE(c0, 0, q0);
+        }
+#undef SS_CSA
+#undef SS_RIPPLE
+        // planes -> 8 registers of four byte-wide counters each (byte b of a[j] counts bit j + 8 b)
+        uint32_t a1[8], a0[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                a1[j] += (p0 >> j) & 0x01010101u;
-                a0[j] += (q0 >> j) & 0x01010101u;
+        for (int j = 0; j < 8; ++j) {
+            a1[j] = 0u; a0[j] = 0u;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                a1[j] += ((c1[k] >> j) & 0x01010101u) << k;
+                a0[j] += ((c0[k] >> j) & 0x01010101u) << k;
             }
         }
 #pragma unroll
@@ -2050,11 +2071,14 @@ struct MhConst {
 // log acceptance ratio of libs/CRP.py:347-383 for one (row, mutation)
 __device__ __forceinline__ double theta_log_A(float th_new, float th_old, int s1, int s0, double lo,
                                               double hi, double sd, const MhConst& c, bool clip,
-                                              double2* lp_new = nullptr, double2* lp_old = nullptr) {
+                                              double2* lp_new = nullptr, double2* lp_old = nullptr,
+                                              const double* fwd_mass = nullptr) {
     const float lo_f = (float)kThetaLo, hi_f = (float)kThetaHi;
     const double lsd = log(sd);
     const double y = (double)(th_new - th_old) / sd;
-    const double fwd = truncnorm_logpdf_std(y, lo, hi) - lsd;
+    // fwd_mass: log mass of [lo, hi] when the caller has it already (the proposal's ppf needs the
+    // same value: one of the three Gaussian-mass evaluations of an element saved)
+    const double fwd = (fwd_mass ? truncnorm_logpdf_mass(y, lo, hi, *fwd_mass) : truncnorm_logpdf_std(y, lo, hi)) - lsd;
     const double rlo = (double)(lo_f - th_new) / sd, rhi = (double)(hi_f - th_new) / sd;
     const double yr = (double)(th_old - th_new) / sd;
     const double rev = truncnorm_logpdf_std(yr, rlo, rhi) - lsd;
@@ -2093,11 +2117,12 @@ __device__ __forceinline__ void mh_theta_kernel(float* theta, const int32_t* __r
     const double ua = rnd ? rnd[2 * RM + i] : uniform_at(seed, stream_id + 2, RM + i, 0);
     const float lo_f = (float)kThetaLo, hi_f = (float)kThetaHi;
     const double lo = (double)(lo_f - old) / sd, hi = (double)(hi_f - old) / sd;
-    const double x = truncnorm_ppf_std(ut, lo, hi);
+    const double mass = log_gauss_mass(lo, hi);
+    const double x = truncnorm_ppf_mass(ut, lo, hi, mass);
     const float prop = (float)(x * sd + (double)old);
     const bool want_logq = flags & 1;
     double2 lp_new, lp_old;
-    const double A = theta_log_A(prop, old, S1[i], S0[i], lo, hi, sd, c, want_logq, &lp_new, &lp_old);
+    const double A = theta_log_A(prop, old, S1[i], S0[i], lo, hi, sd, c, want_logq, &lp_new, &lp_old, &mass);
     const bool rej = log(ua) >= A;
     if (!rej) theta[row * M + m] = prop;
     else atomicAdd(&declined[r], 1);
@@ -2694,6 +2719,7 @@ static int gibbs_options_impl(const float* llf, int ldf, int K, const int32_t* c
                               int by_cell = 0) {
     if (C <= 0) return 0;
     if (K <= 0 || K > BNPC_LEAN_MAXK) return bad_arg("lean epochs need K <= BNPC_LEAN_MAXK");
+    if (ldf % 4 != 0 || ldf < ((K + 3) & ~3) || ((uintptr_t)llf & 15)) return bad_arg("llf rows: 16-byte aligned, ldf a multiple of 4 >= K");
     if (clear)
         if (int rc = zero_async(n_cert, sizeof(int32_t) * BNPC_LEAN_MAXK, stream, "gibbs_options memset")) return rc;
     const float err_rel = (float)terms * 2.384185791015625e-07f;      // terms * 2^-22

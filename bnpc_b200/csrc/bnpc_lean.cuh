@@ -97,15 +97,25 @@ __device__ __forceinline__ void gibbs_options_kernel(const float* __restrict__ l
             const float v_old = row[c_old];
             const float err = err_rel * (fabsf(v_old) + 64.0f) + err_abs;
             const float thr = v_old - 40.0f - slack - 2.0f * err;
-            int n = 0, i_old = 0;
-            for (int k = 0; k < K; ++k) {
-                const float v = row[k];
-                if (k != c_old && !(v > thr)) continue;
-                if (k == c_old) i_old = n;
+            // options as a bit mask over the columns (rows are read four floats at a time: ldf is a
+            // multiple of 4 and the columns beyond K are masked), then the first BNPC_MAX_OPT set
+            // bits in increasing order
+            unsigned long long mask = 1ull << c_old;
+            const float4* row4 = reinterpret_cast<const float4*>(row);
+            for (int k4 = 0; k4 < (K + 3) / 4; ++k4) {
+                const float4 v = row4[k4];
+                const unsigned m4 = (v.x > thr ? 1u : 0u) | (v.y > thr ? 2u : 0u) | (v.z > thr ? 4u : 0u) | (v.w > thr ? 8u : 0u);
+                mask |= (unsigned long long)m4 << (4 * k4);
+            }
+            if (K < 64) mask &= (1ull << K) - 1ull;
+            const int n = __popcll(mask);
+            const int i_old = __popcll(mask & ((1ull << c_old) - 1ull));
 #pragma unroll
-                for (int i = 0; i < BNPC_MAX_OPT; ++i)
-                    if (i == n) o.col[i] = (uint8_t)k;
-                ++n;
+            for (int i = 0; i < BNPC_MAX_OPT; ++i) {
+                if (mask) {
+                    o.col[i] = (uint8_t)(__ffsll((long long)mask) - 1);
+                    mask &= mask - 1ull;
+                }
             }
             if (n <= BNPC_MAX_OPT) {
                 o.n_opt = (uint8_t)n; o.i_old = (uint8_t)i_old; o.flags = 0;

@@ -62,10 +62,15 @@ __device__ __noinline__ double log_gauss_mass(double a, double b) {
     return log1p(-ndtr(a) - ndtr(-b));
 }
 
-__device__ __forceinline__ double truncnorm_logpdf_std(double y, double a, double b) {
-    // rv_continuous.logpdf support mask (closed interval), then truncnorm_gen._logpdf
+__device__ __forceinline__ double truncnorm_logpdf_mass(double y, double a, double b, double log_mass) {
+    // rv_continuous.logpdf support mask (closed interval), then truncnorm_gen._logpdf with
+    // log_mass = _log_gauss_mass(a, b) supplied by the caller
     if (!(y >= a && y <= b)) return -BNPC_INF;
-    return -(y * y) / 2.0 - kNormLogC - log_gauss_mass(a, b);
+    return -(y * y) / 2.0 - kNormLogC - log_mass;
+}
+__device__ __forceinline__ double truncnorm_logpdf_std(double y, double a, double b) {
+    if (!(y >= a && y <= b)) return -BNPC_INF;
+    return truncnorm_logpdf_mass(y, a, b, log_gauss_mass(a, b));
 }
 
 __device__ __noinline__ double ndtri_exp(double y) {
@@ -74,14 +79,17 @@ __device__ __noinline__ double ndtri_exp(double y) {
     return normcdfinv(exp(y));
 }
 
-__device__ __forceinline__ double truncnorm_ppf_std(double q, double a, double b) {
-    // truncnorm_gen._ppf
+__device__ __forceinline__ double truncnorm_ppf_mass(double q, double a, double b, double log_mass) {
+    // truncnorm_gen._ppf with log_mass = _log_gauss_mass(a, b) supplied by the caller
     if (a < 0) {
-        const double lphi = log_sum_exp2(log_ndtr(a), log(q) + log_gauss_mass(a, b));
+        const double lphi = log_sum_exp2(log_ndtr(a), log(q) + log_mass);
         return ndtri_exp(lphi);
     }
-    const double lphi = log_sum_exp2(log_ndtr(-b), log1p(-q) + log_gauss_mass(a, b));
+    const double lphi = log_sum_exp2(log_ndtr(-b), log1p(-q) + log_mass);
     return -ndtri_exp(lphi);
+}
+__device__ __forceinline__ double truncnorm_ppf_std(double q, double a, double b) {
+    return truncnorm_ppf_mass(q, a, b, log_gauss_mass(a, b));
 }
 
 __device__ __noinline__ double beta_logpdf(double x, double p, double q, double betaln_pq) {
