@@ -480,12 +480,14 @@ __device__ __forceinline__ void ll_few_kernel(const uint32_t* __restrict__ x1, c
               const double2* __restrict__ lp, int K, double* __restrict__ ll, int ldk,
               const float* __restrict__ theta, double FN, double FP) {
     extern __shared__ __align__(16) unsigned char llp_smem[];
-    double2* tab = reinterpret_cast<double2*>(llp_smem);          // [K][W * 32], zero beyond M
+    double2* tab = reinterpret_cast<double2*>(llp_smem);          // [K][W * 32 + 1], zero beyond M
     const int Mp = W * 32;
     // lp == NULL: the table is built here from the K rows of theta (what bnpc_logprob_tables
-    // would have written; one launch less per restricted Gibbs scan)
-    for (int i = threadIdx.x; i < K * Mp; i += blockDim.x) {
-        const int k = i / Mp, m = i % Mp;
+    // would have written; one launch less per restricted Gibbs scan).  Entry Mp of every column
+    // is a zero pair: a missing entry of the data reads it, so the inner loop has no branch and
+    // no select (adding 0.0 leaves the sum as it is).
+    for (int i = threadIdx.x; i < K * (Mp + 1); i += blockDim.x) {
+        const int k = i / (Mp + 1), m = i % (Mp + 1);
         double2 v = make_double2(0.0, 0.0);
         if (m < M) {
             if (lp) v = lp[(long long)k * M + m];
@@ -501,7 +503,7 @@ __device__ __forceinline__ void ll_few_kernel(const uint32_t* __restrict__ x1, c
     const uint32_t* r1 = x1 + cell * W;
     const uint32_t* r0 = x0 + cell * W;
     const double* t0 = reinterpret_cast<const double*>(tab);
-    const double* t1 = t0 + 2 * Mp;
+    const double* t1 = t0 + 2 * (Mp + 1);
     double a0 = 0.0, a1 = 0.0;
     if (live) {
         for (int w = sub; w < W; w += 8) {
@@ -511,10 +513,9 @@ __device__ __forceinline__ void ll_few_kernel(const uint32_t* __restrict__ x1, c
             for (int i = 0; i < 32; ++i) {
                 const int bit = (i + sub) & 31;
                 const uint32_t b1 = (u1 >> bit) & 1u, b0 = (u0 >> bit) & 1u;
-                const int at = 2 * (w * 32 + bit) + (b1 ? 0 : 1);
-                const bool any = (b1 | b0) != 0u;
-                a0 += any ? t0[at] : 0.0;
-                if (K > 1) a1 += any ? t1[at] : 0.0;
+                const int at = (b1 | b0) ? 2 * (w * 32 + bit) + (b1 ? 0 : 1) : 2 * Mp;
+                a0 += t0[at];
+                if (K > 1) a1 += t1[at];
             }
         }
     }
@@ -2522,7 +2523,7 @@ static int ll_few_from_theta(const uint32_t* x1, const uint32_t* x0, int W, int 
                              int cell_stride, int C, const float* theta, int K, double FN, double FP, double* ll,
                              int ldk, void* stream) {
     if (C <= 0 || K <= 0) return 0;
-    const size_t smem = sizeof(double2) * (size_t)K * W * 32;
+    const size_t smem = sizeof(double2) * (size_t)K * (W * 32 + 1);
     BNPC_LAUNCH(ll_few_kernel, 8 * LLP_CELLS, 0, cdiv(C, LLP_CELLS), 8 * LLP_CELLS, smem, (cudaStream_t)stream,  x1, x0, W, M, cells, cell_stride, C, (const double2*)nullptr, K, ll, ldk, theta, FN, FP);
     return 0;
 }
@@ -2533,7 +2534,7 @@ int bnpc_ll_matrix(const uint32_t* x1, const uint32_t* x0, int W, int M, const i
     if (ldk < K) return bad_arg("ldk < K");
     if (W % 4 != 0) return bad_arg("W must be a multiple of 4");
     if (ll_few_fits(K, W)) {
-        const size_t smem = sizeof(double2) * (size_t)K * W * 32;
+        const size_t smem = sizeof(double2) * (size_t)K * (W * 32 + 1);
         BNPC_LAUNCH(ll_few_kernel, 8 * LLP_CELLS, 0, cdiv(C, LLP_CELLS), 8 * LLP_CELLS, smem, (cudaStream_t)stream,  x1, x0, W, M, cells, cell_stride, C, reinterpret_cast<const double2*>(lp), K, ll, ldk, (const float*)nullptr, 0.0, 0.0);
         return 0;
     }
