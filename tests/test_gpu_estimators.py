@@ -100,6 +100,47 @@ def test_estimator_ari_matches_the_reference_within_noise(name):
     assert min(fn_ref) - 0.05 < np.mean(got['fn']) < max(fn_ref) + 0.05
 
 
+def test_reference_example_c1():
+    """BASELINE configuration 1: the reference's own example (example_data/data.csv: 100 cells x 100
+    mutations, 5 simulated clusters -- example_data/data_params.txt) with the defaults of
+    run_BnpC.py.  The unmodified reference, run three times for 1500 steps
+    (tests/golden/make_c1.py -> c1_reference_posterior.json), ends all three runs with the same
+    posterior estimate: 5 clusters of 23 / 22 / 21 / 20 / 14 cells, FN ~ 0.06.  Two CUDA chains
+    through the public MCMC driver must find that partition and error rates in the same range.
+    The data file is read from the reference checkout (the unmodified copy under baseline/_ref on
+    the GPU box)."""
+    import json
+    import os
+    import libs.CRP_learning_errors as crple
+    import libs.dpmmIO as io
+    import libs.utils as ut
+    from libs.MCMC import MCMC
+    from helpers import GOLDEN_DIR
+    from oracle import ref_shim
+    path = os.path.join(ref_shim.REF_ROOT, 'example_data', 'data.csv')
+    if not os.path.isfile(path):
+        pytest.skip('the reference example data is not available (oracle/fetch_ref.py ships it under baseline/_ref)')
+    with open(os.path.join(GOLDEN_DIR, 'c1_reference_posterior.json')) as f:
+        ref = json.load(f)
+    data = io.load_data(path, transpose=True)
+    assert data.shape == (100, 100)
+    model = crple.CRP_errors_learning(data, DP_alpha=[-1, -1], param_beta=[0.25, 0.25], FP_mean=0.01, FP_sd=0.01,
+                                      FN_mean=0.2, FN_sd=0.1)
+    mcmc = MCMC(model, sm_prob=0.33, dpa_prob=0.25, error_prob=0.25, sm_ratios=[0.75, 0.25], sm_steps=3)
+    mcmc.run((ref['steps'], 0), 4, n=2, verbosity=0)
+    results = mcmc.get_results()
+    est = ut.get_latents_posterior(results, data, single_chains=False)[0]
+    a = np.unique(est['assignment'], return_inverse=True)[1]
+    assert sorted(np.bincount(a).tolist(), reverse=True) == ref['runs'][0]['sizes'] == [23, 22, 21, 20, 14]
+    assert len(set(a)) == ref['clusters_simulated']
+    for run in ref['runs']:
+        assert ut.get_ARI(a, np.array(run['assignment'])) == 1.0
+    fn_ref = [r['fn'] for r in ref['runs']]
+    fp_ref = [r['fp'] for r in ref['runs']]
+    assert min(fn_ref) - 0.03 < float(est['FN'][0]) < max(fn_ref) + 0.03
+    assert float(est['FP'][0]) < max(fp_ref) + 0.005
+
+
 def test_command_line_end_to_end(tmp_path):
     """run_BnpC.py on a generated matrix file: 2 chains, posterior + MAP estimators, text outputs
     in the reference's formats, ARI against the simulated clusters."""
