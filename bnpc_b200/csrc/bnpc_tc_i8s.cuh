@@ -7,8 +7,7 @@
 //
 // so one pass of the producers and one TMEM read of A per MMA serve nc chains.  With N = 48..64
 // columns (one chain) an MMA is bound by the 64 B/clk read of its 4 KB A operand (64 cycles for 24 to
-// 32 cycles of tensor-pipe work); at N = 256 the tensor pipe (128 cycles) is the bound and the
-// producers have 2048 instead of 1024 cycles per stage.
+// 32 cycles of tensor-pipe work); at N = 256 the tensor pipe (128 cycles) is the bound.
 //   A   producers as in ll_matrix_i8_kernel (16 warps, 512 reduction indices per stage, two stages
 //       in TMEM columns [256, 512)), for rows in CELL order only (row r = cell r: the first epoch of
 //       a sweep writes its rows by cell and gibbs_options_kernel reads them by cell; the gathered
@@ -16,11 +15,21 @@
 //   B   a ring of CHUNK slots (128 reduction indices x n_tot rows = n_tot * 128 bytes), decoupled
 //       from the A stages: a 256-column stage would not fit shared memory twice.  Chain c's rows sit
 //       at row offset off_c (a multiple of 16, so its 8-row swizzle groups keep their 1024-byte
-//       stride): one bulk copy per chain and chunk out of that chain's own table.
-//   D   columns [0, n_tot) (+ a second set at [n_tot, 2 n_tot) when n_tot <= 128).  With one set the
-//       MMAs of the next tile wait for the epilogue, so eight epilogue warps (two per TMEM lane
-//       quarter, alternating 8-column blocks) keep that gap short; producers and B loader run ahead.
-// Warps: 0-15 producers, 16-19 epilogue, 20 MMA issuer, 21 B loader.
+//       stride): one bulk copy per chain and chunk out of that chain's own table, issued by lane c
+//       of the loader warp.  When all chunks of a row fit (n_tot * W * 64 bytes <= 200 KB) every
+//       chunk has its own slot and the tables are loaded ONCE per CTA (resident): streaming them per
+//       tile costs about 10 us per chain and launch at 100k x 1k (100 MB through L2 -> SM).
+//   T   tiles per supertile (template parameter, 1 or 2): with T = 2 a stage of A holds two chunks of
+//       each of two tiles (producer group g: tile g % 2, chunk g / 2), so a table chunk is fetched
+//       and read from shared memory once for 256 cells; needs 2 * n_tot accumulator columns <= 256.
+//   D   columns [0, T * n_tot) (+ a second set behind them when T * n_tot <= 128: the epilogue of a
+//       supertile then overlaps the MMAs of the next one; with one set the MMAs wait for it).
+// Warps: 0-15 producers, 16-19 epilogue, 20 MMA issuer, 21 B loader (704 threads: the register
+// budget of the producers' loop, 80 per thread, is what fixes the warp count).
+// Measured on B200 (tools/ll_shared_bench.py, 100k x 1k, K = 22..28): 27 us for one chain (the
+// one-chain kernel: 28), 48 / 69 / 79 / 136 us for 2 / 3 / 4 / 8 chains, 38 us for two chains with
+// resident tables; in the benchmark 73 us per launch of 5.15 chains = 0.51 of the sustained bf16 peak
+// in algorithmic flops.
 
 #define T8S_MAXC 8
 #define T8S_EPI_WARPS 4
