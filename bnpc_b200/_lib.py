@@ -20,7 +20,7 @@ HEADERS = sorted(glob.glob(os.path.join(_HERE, 'csrc', '*.cuh'))) + sorted(glob.
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-fmad=false', '-std=c++17', '-shared', '-Xcompiler', '-fPIC']
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 MAX_EXTRA = 32
 ST_K, ST_TDONE, ST_FLAGS, ST_NEXTRA, ST_BIRTHS, ST_MOVED, ST_SLOW = range(7)
 ST_NUNC = 10
@@ -155,6 +155,7 @@ SIGNATURES = {
     'bnpc_mpear_sums_weighted': [_P, _I, _P, _I, _P, _P, _P],
     'bnpc_ll_matrix_i8': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _D, _P, _I, _P],
     'bnpc_ll_matrix_i8_shared': [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    'bnpc_ll_shared_plan': [_I, _P, _I, _I, _P, _P, _P, _P, _P, _P],
     'bnpc_gibbs_options': [_P, _I, _I, _P, _P, _P, _P, _I, _D, _D, _I, _D, _P],
     'bnpc_gibbs_exact': [_P, _P, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _D, _D, _P, _P, _P],
     'bnpc_gibbs_epoch_begin': [_P, _I, _P, _P, _P, _I, _P, _I, _P],

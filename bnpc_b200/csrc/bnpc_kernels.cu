@@ -2680,6 +2680,33 @@ int bnpc_ll_matrix_i8(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
     }
 }
 
+int bnpc_ll_shared_plan(int n, const int* kpad, int C, int W, int* group_of, int* column_of, int* tiles_per_supertile,
+                        int* ctas_of_group, int* slots_of_group, int* n_groups) {
+    if (n <= 0 || n > bnpc::BATCH_MAX) return bad_arg("1..8 chains");
+    if (C <= 0 || W <= 0 || W % 4 != 0) return bad_arg("C > 0, W a positive multiple of 4");
+    ll_shared_t ones[bnpc::BATCH_MAX];
+    memset(ones, 0, sizeof(ones));
+    for (int i = 0; i < n; ++i) {
+        if (kpad[i] <= 0 || kpad[i] % 8 != 0 || kpad[i] > BNPC_LEAN_MAXK) return bad_arg("kpad: a multiple of 8 in [8, 64]");
+        ones[i].W = W; ones[i].C = C; ones[i].nc = 1; ones[i].n_tot = 2 * kpad[i];
+        ones[i].ch[0].kpad = kpad[i];
+        ones[i].ch[0].ldf = i;                      // tag: which chain this block is
+    }
+    ll_plan_t plan;
+    ll_shared_plan(ones, n, false, plan);
+    for (int g = 0; g < plan.ng; ++g) {
+        ctas_of_group[g] = plan.groups[g].n_ctas;
+        slots_of_group[g] = plan.groups[g].b_slots;
+        for (int c = 0; c < plan.groups[g].nc; ++c) {
+            group_of[plan.groups[g].ch[c].ldf] = g;
+            column_of[plan.groups[g].ch[c].ldf] = plan.groups[g].ch[c].off;
+        }
+    }
+    *tiles_per_supertile = plan.T;
+    *n_groups = plan.ng;
+    return 0;
+}
+
 int bnpc_ll_matrix_i8_shared(const uint32_t* x1, const uint32_t* x0, int W, int M, int C, int n_chains,
                              const double* const* lp, uint8_t* const* bdigits, const int* K, const double* vmax,
                              float* const* llf, const int* ldf, void* stream) {

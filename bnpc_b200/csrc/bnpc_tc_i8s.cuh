@@ -335,16 +335,22 @@ static inline void ll_shared_append(ll_shared_t& g, const ll_shared_t& one) {
 
 // merged launch of the recorder: ops of chains that can share their tiles become one group each,
 // the groups of a launch are its blockIdx.z
-static int launch_ll_shared_merged(bnpc::Op* const* ops, int n, cudaStream_t s) {
-    using namespace bnpc;
-    using P = typename FnTraits<decltype(&ll_matrix_i8s_kernel<1>)>::pack_t;
-    static_assert(sizeof(P) <= ARG_BYTES, "ll_shared_t larger than ARG_BYTES");
-    static const int no_share = getenv("BNPC_LL_NO_SHARE") ? 1 : 0;      // debugging: one chain per group
-    ll_shared_t groups[BATCH_MAX];
+// Plan of one merged launch: the single-chain argument blocks `ones[0..n)` packed first-fit into
+// groups (chains with the same planes and cell count, at most T8S_MAXC chains and T8S_MAX_NTOT
+// columns per group), the tiles per supertile of the launch (two only when every group allows it:
+// one kernel instance per launch), and per group the persistent CTAs and the chunk slots.  Host
+// logic only (bnpc_ll_shared_plan exposes it to the CPU tests).
+struct ll_plan_t {
+    ll_shared_t groups[bnpc::BATCH_MAX];
+    int ng, T;
+    unsigned gx;
+    size_t smem;
+};
+static void ll_shared_plan(const ll_shared_t* ones, int n, bool no_share, ll_plan_t& plan) {
+    ll_shared_t* groups = plan.groups;
     int ng = 0;
     for (int i = 0; i < n; ++i) {
-        ll_shared_t one;
-        memcpy(&one, ops[i]->args, sizeof(one));
+        const ll_shared_t& one = ones[i];
         int g = -1;
         for (int j = 0; j < ng && g < 0 && !no_share; ++j)
             if (ll_shared_fits(groups[j], one)) g = j;
@@ -353,7 +359,6 @@ static int launch_ll_shared_merged(bnpc::Op* const* ops, int n, cudaStream_t s) 
     }
     unsigned gx = 1;
     size_t smem = 0;
-    // one kernel instance per launch: two tiles per supertile only when every group allows it
     int T = 2;
     for (int j = 0; j < ng; ++j) T = ll_shared_T(groups[j]) < T ? ll_shared_T(groups[j]) : T;
     for (int j = 0; j < ng; ++j) {
@@ -362,6 +367,23 @@ static int launch_ll_shared_merged(bnpc::Op* const* ops, int n, cudaStream_t s) 
         const size_t sm = ll_shared_smem(groups[j]);
         smem = sm > smem ? sm : smem;
     }
+    plan.ng = ng; plan.T = T; plan.gx = gx; plan.smem = smem;
+}
+
+static int launch_ll_shared_merged(bnpc::Op* const* ops, int n, cudaStream_t s) {
+    using namespace bnpc;
+    using P = typename FnTraits<decltype(&ll_matrix_i8s_kernel<1>)>::pack_t;
+    static_assert(sizeof(P) <= ARG_BYTES, "ll_shared_t larger than ARG_BYTES");
+    static const int no_share = getenv("BNPC_LL_NO_SHARE") ? 1 : 0;      // debugging: one chain per group
+    if (n > BATCH_MAX) return bad_arg("more than BATCH_MAX chains in one merged launch");
+    ll_shared_t ones[BATCH_MAX];
+    for (int i = 0; i < n; ++i) memcpy(&ones[i], ops[i]->args, sizeof(ll_shared_t));
+    ll_plan_t plan;
+    ll_shared_plan(ones, n, no_share != 0, plan);
+    const ll_shared_t* groups = plan.groups;
+    const int ng = plan.ng, T = plan.T;
+    const unsigned gx = plan.gx;
+    const size_t smem = plan.smem;
     if (ng == 1) {
         Batch<1, P> B;
         memset(&B, 0, sizeof(B));

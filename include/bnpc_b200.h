@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BNPC_ABI_VERSION 11
+#define BNPC_ABI_VERSION 12
 
 /* capacity of clusters born since the ll matrix of the current epoch was built */
 #define BNPC_MAX_EXTRA 32
@@ -221,6 +221,14 @@ int bnpc_ll_matrix_i8(const uint32_t* x1, const uint32_t* x0, int W, int M, cons
  * read per MMA for all of them (csrc/bnpc_tc_i8s.cuh).  Per-chain arguments are host arrays; the
  * values equal bnpc_ll_matrix_i8's bit for bit (exact integer accumulation).  This is what the
  * recorded bnpc_ll_matrix_i8 calls (cells = NULL) of the chains of one wave are merged into. */
+/* Host logic of that merge, without a launch (no device needed): for n <= 8 chains with paddings
+ * kpad[i] (multiples of 8, <= 64) over C cells with W plane words per row -> the group of every
+ * chain (first-fit, sum of 2*kpad <= 256 columns per group), its first column in the group, the
+ * tiles per supertile of the launch (2 only when every group has <= 128 columns and there are at
+ * least 4 tiles per SM), and per group the persistent CTAs and the table chunk slots (= W/2: the
+ * tables stay resident in shared memory). */
+int bnpc_ll_shared_plan(int n, const int* kpad, int C, int W, int* group_of, int* column_of,
+                        int* tiles_per_supertile, int* ctas_of_group, int* slots_of_group, int* n_groups);
 int bnpc_ll_matrix_i8_shared(const uint32_t* x1, const uint32_t* x0, int W, int M, int C, int n_chains,
                              const double* const* lp, uint8_t* const* bdigits, const int* K,
                              const double* vmax, float* const* llf, const int* ldf, void* stream);
